@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch]
+
+Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
+50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
+minimal samples -> K2 7-point solve + oriented-constraint test -> K3 MSAC scoring of every model against all points ->
+K4 argmax.  `value` counts only REAL models (valid model count x N), not empty root slots.
+At N > 1 every rank runs the same per-GPU workload on its own image pair (pairs shard with no collective: weak scaling).
+
+The JSON line follows the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches).
+--impl reference times the reference's CPU implementation of the same pass (oracle/_ref: the reference's scoring /
+driver headers compiled verbatim + restated estimators; falls back to the oracle port) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "graph-cut-ransac_b200"))
+
+FLOP_PER_EVAL = {"h": 21.0, "f": 35.0}  # H-MSAC 21, Sampson-MSAC 35 (counted from the reference lines)
+
+WORKLOADS = {
+    # name: problem, n points, outlier ratio, threshold, samples per step, pairs per GPU
+    "f4k": dict(problem="f", n=4096, outliers=0.5, thr=0.75, samples=262144, pairs=1,
+                desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
+    "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
+                      desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 (configs[3])"),
+}
+
+
+def make_points(wl, rank):
+    from pygcransac import synth
+    pts = []
+    for p in range(wl["pairs"]):
+        seed = 1000 * rank + p + 1
+        if wl["problem"] == "f":
+            pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])
+        else:
+            pts.append(synth.homography_pair(wl["n"], wl["outliers"], seed)[0])
+    return np.ascontiguousarray(np.stack(pts))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp32_peak_tflops(sm_count):
+    """FP32 FMA roofline: SMs x 128 lanes x 2 flop x max SM clock.  MEASURED_PEAKS.json carries HBM and bf16 tensor
+    peaks but no FP32-pipe figure; its measured sm_max_mhz is used for the clock (else the device attribute)."""
+    mhz, src = None, None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mhz = float(json.load(f)["sm_max_mhz"])
+            src = "derived: %d SMs x 128 x 2 x sm_max_mhz %.0f (MEASURED_PEAKS.json)" % (sm_count, mhz)
+    except (OSError, KeyError, ValueError):
+        pass
+    return mhz, src
+
+
+_CPU_IMPL = {}
+
+
+def cpu_round_worker(args):
+    """One CPU slice: `count` samples of the same workload through the reference scoring loop (or the port)."""
+    kind, problem, pts, seed, first, count, thr = args
+    if kind not in _CPU_IMPL:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        _CPU_IMPL[kind] = (O, O.Ref() if kind == "reference" else O.Oracle())
+    O, impl = _CPU_IMPL[kind]
+    score, idx, scored, _ = impl.round(O.F if problem == "f" else O.H, O.MSAC, pts, seed, first, count, thr)
+    return scored, score, idx
+
+
+def cpu_kind():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build_oracle()
+    return "reference" if O.build_ref() else "port"
+
+
+class CpuArm:
+    """The reference's single-threaded CPU path, one slice of the sample stream per host core (persistent pool)."""
+
+    def __init__(self, wl, pts0):
+        import multiprocessing as mp
+        self.kind = cpu_kind()
+        self.cores = os.cpu_count() or 1
+        self.wl, self.pts0 = wl, pts0
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.run(self.cores * 8)  # load the library in every worker
+
+    def run(self, samples_total, first=0):
+        """Returns (evals, wall seconds, samples actually run)."""
+        per = max(1, samples_total // (self.cores * 4))
+        jobs = [(self.kind, self.wl["problem"], self.pts0, 12345, first + c * per, per, self.wl["thr"])
+                for c in range(self.cores * 4)]
+        t0 = time.perf_counter()
+        out = self.pool.map(cpu_round_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        return sum(o[0] for o in out) * self.wl["n"], wall, per * len(jobs)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def bench_reference(args, wl, rank, world):
+    """--impl reference: the CPU arm on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    pts0 = make_points(dict(wl, pairs=1), 0)[0]
+    arm = CpuArm(wl, pts0)
+    # bounded sample per step: ~1 s of all-core CPU work on an 8-core host
+    per_step = (65536 if wl["problem"] == "f" else 8192) * arm.cores
+    for s in range(args.warmup):
+        arm.run(per_step // 8)
+    t_total, evals_total, used = 0.0, 0, 0
+    for s in range(args.steps):
+        evals, wall, used = arm.run(per_step, first=s * per_step)
+        t_total += wall
+        evals_total += evals
+    arm.close()
+    value = evals_total / t_total
+    line = {
+        "impl": "reference", "metric": "hypothesis x point evals/s", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "samples_per_step": used},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
+                         "sample": "%d samples/step of the same pair (7-pt solve + MSAC over all %d points), sliced "
+                                   "over the host cores" % (used, wl["n"])},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="f4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="minimal samples per step per pair (default: workload's)")
+    ap.add_argument("--variant", type=int, default=-1, help="force a K3 kernel variant (see gcr_set_score_variant)")
+    ap.add_argument("--no-exact", action="store_true", help="skip the FP64 threshold-band re-check in K3")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.samples:
+        wl["samples"] = args.samples
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        bench_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pygcransac import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    prob = _cabi.F if wl["problem"] == "f" else _cabi.H
+    flags = 0 if args.no_exact else _cabi.SCORE_EXACT_COUNTS
+    ctx = _cabi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    if args.variant >= 0:
+        ctx.set_score_variant(args.variant)
+    info = ctx.device_info()
+
+    pts_host = torch.from_numpy(make_points(wl, rank)).pin_memory()          # [pairs, n, 4] f64, pinned
+    pts_dev = pts_host.cuda(non_blocking=True)
+    n_pairs, n = wl["pairs"], wl["n"]
+    keys = torch.zeros(n_pairs, dtype=torch.int64, device="cuda")
+    best = torch.zeros(n_pairs, 9, dtype=torch.float64, device="cuda")
+    keys_host = torch.zeros(n_pairs, dtype=torch.int64).pin_memory()
+    best_host = torch.zeros(n_pairs, 9, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        flush.zero_()                                                       # L2 flush between steps
+        return ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
+                                flags, 0, keys.data_ptr(), best.data_ptr())
+
+    def step_e2e(i):
+        flush.zero_()
+        ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
+        ev = ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
+                              flags, 0, keys.data_ptr(), best.data_ptr())
+        keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
+        best_host.copy_(best, non_blocking=True)
+        stream.synchronize()
+        return ev
+
+    # ---- resident leg: inputs in HBM before the timed region ----
+    ctx.points_set_device(pts_dev.data_ptr(), n, 4, n_pairs)
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    ctx.counters(reset=True)
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    slot_evals = 0
+    for i in range(args.steps):
+        slot_evals += step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    score_ms, score_launches, score_slot_evals = ctx.profile_read()
+    ctx.profile_enable(False)
+    valid_models = ctx.counters(reset=True)[0]
+    evals = valid_models * n
+    best_key_score, best_key_index = ctx.key_decode(int(keys[0].item()) & ((1 << 64) - 1))
+
+    # ---- e2e leg: host buffers, H2D + D2H inside the timed region ----
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    ctx.counters(reset=True)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    g1.record()
+    barrier()
+    ms_e2e = g0.elapsed_time(g1)
+    evals_e2e = ctx.counters(reset=True)[0] * n
+
+    # ---- max over ranks, sum of work ----
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = torch.tensor([evals, evals_e2e, launches, slot_evals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = t.tolist()
+        evals, evals_e2e, launches, slot_evals = w.tolist()
+
+    if rank == 0:
+        flop = FLOP_PER_EVAL[wl["problem"]]
+        mhz, peak_src = fp32_peak_tflops(info["sm_count"])
+        if mhz is None:
+            mhz = info["sm_clock_khz"] / 1e3
+            peak_src = "derived: %d SMs x 128 x 2 x device clock %.0f MHz (MEASURED_PEAKS.json absent: fallback)" % (
+                info["sm_count"], mhz)
+        peak = info["sm_count"] * 128 * 2 * mhz * 1e6 / 1e12
+        # dominant kernel = K3 (k_score): algorithmic flops of the REAL models it scored / its own event time
+        k3_real_evals = (evals / world) if world > 1 else evals
+        achieved = k3_real_evals * flop / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
+        line = {
+            "metric": "hypothesis x point evals/s", "value": evals / (ms * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
+                       "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
+                       "exact_counts": not args.no_exact, "k3_variant": args.variant,
+                       "l2_flush": "256 MiB device memset between steps (inside the timed region)",
+                       "best_score_rank0": best_key_score},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "k_score (K3)", "flop_per_eval": flop, "k3_ms_per_launch": score_ms / max(1, score_launches),
+                         "k3_share_of_step": score_ms / ms if world == 1 else None, "peak_source": peak_src,
+                         "note": "FP32-FMA-pipe bound (projective divide / Sampson denominator; not a tensor-core "
+                                 "contraction, HBM traffic ~0): peak is the FP32 roofline, not hbm/tensor"},
+            "clocks": clock_info,
+            "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": int(pts_host.numel() * 8), "d2h_bytes_per_step": int(n_pairs * (8 + 72))},
+            "gpu_launches": int(launches),
+        }
+        if not args.no_cpu:
+            arm = CpuArm(wl, pts_host[0].numpy().copy())
+            cpu_samples = (65536 if wl["problem"] == "f" else 8192) * arm.cores * 10
+            c_evals, c_wall, used = arm.run(cpu_samples)
+            arm.close()
+            line["cpu_baseline"] = {"value": c_evals / c_wall, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
+                                    "sample": "%d samples of pair 0 (solve + MSAC over all %d points), sliced over the "
+                                              "host cores, %.1f s wall" % (used, n, c_wall)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,525 @@
+// gcr_ctx.cu -- context, device-memory helpers, point upload and the K0 "prepare points" kernels.
+//
+// Data layout in HBM (per context):
+//   d_pts64   [n_pairs][n][cols]        FP64 row-major, exactly what the caller handed over (the reference's cv::Mat)
+//   d_pts32   [n_pairs][n_pad]          float4 (x1' y1' x2' y2')   centred + power-of-two scaled FP32 copy
+//             (PnP: [n_pairs][n_pad][2] float4 (u' v' 0 0)(X' Y' Z' 0))
+//   d_pts32dup[n_pairs][n_pad][2]       float4 (x1' x1' y1' y1')(x2' x2' y2' y2') operand-duplicated copy for the
+//                                       packed f32x2 scoring kernel (4-column problems only)
+//   d_norm    [n_pairs][8]              FP64 normalisation (centres, scale) so models can be mapped alike
+// n_pad = n rounded up to GCR_TILE_POINTS; padding rows are NaN so they can never be inliers.
+#include "gcr_internal.cuh"
+
+#include <math.h>
+#include <new>
+#include <string.h>
+
+#define GCR_TILE_POINTS 256
+
+extern "C" const char *gcr_version(void) { return "gcr-b200 0.1 (sm_100a)"; }
+
+extern "C" gcr_status gcr_ctx_create(int device, gcr_ctx **out)
+{
+	if (!out)
+		return GCR_ERR_ARG;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0 || device < 0 || device >= count)
+	{
+		fprintf(stderr, "gcr_ctx_create: no usable CUDA device %d (%s); this library has no CPU fallback\n", device,
+		        e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+		return GCR_ERR_CUDA;
+	}
+	gcr_ctx *ctx = new (std::nothrow) gcr_ctx();
+	if (!ctx)
+		return GCR_ERR_NOMEM;
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+	{
+		delete ctx;
+		return GCR_ERR_CUDA;
+	}
+	ctx->stream = ctx->own_stream;
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	ctx->sm_count = prop.multiProcessorCount;
+	ctx->l2_bytes = (size_t)prop.l2CacheSize;
+	int khz = 0;
+	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+	ctx->sm_clock_khz = khz;
+	if (cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
+	{
+		delete ctx;
+		return GCR_ERR_CUDA;
+	}
+	*out = ctx;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
+{
+	if (!ctx)
+		return GCR_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->d_pts64_owned);
+	cudaFree(ctx->d_pts32);
+	cudaFree(ctx->d_pts32dup);
+	cudaFree(ctx->d_norm);
+	cudaFree(ctx->d_bbox);
+	cudaFree(ctx->d_magsac_lut);
+	cudaFree(ctx->d_magsac_lut64);
+	cudaFree(ctx->d_scratch);
+	cudaFree(ctx->d_prosac_growth);
+	cudaFree(ctx->d_round);
+	cudaFree(ctx->d_counters);
+	for (int i = 0; i < gcr_ctx::EV_RING; ++i)
+	{
+		if (ctx->ev_a[i]) cudaEventDestroy(ctx->ev_a[i]);
+		if (ctx->ev_b[i]) cudaEventDestroy(ctx->ev_b[i]);
+	}
+	if (ctx->h_pinned)
+		cudaFreeHost(ctx->h_pinned);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_ctx_set_stream(gcr_ctx *ctx, void *cuda_stream)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_sync(gcr_ctx *ctx)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return GCR_OK;
+}
+
+extern "C" const char *gcr_last_error(const gcr_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" gcr_status gcr_device_info(gcr_ctx *ctx, int *sm_count, int *sm_clock_khz, size_t *l2_bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (sm_count) *sm_count = ctx->sm_count;
+	if (sm_clock_khz) *sm_clock_khz = ctx->sm_clock_khz;
+	if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+	return GCR_OK;
+}
+
+extern "C" uint64_t gcr_launch_count(const gcr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out)
+{
+	if (!ctx || !d_out)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	GCR_CHECK_CUDA(ctx, cudaMalloc(d_out, bytes ? bytes : 1));
+	return GCR_OK;
+}
+extern "C" gcr_status gcr_free(gcr_ctx *ctx, void *d_ptr)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaFree(d_ptr));
+	return GCR_OK;
+}
+extern "C" gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return GCR_OK;
+}
+extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return GCR_OK;
+}
+extern "C" gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
+	return GCR_OK;
+}
+
+gcr_status gcr_ensure_scratch(gcr_ctx *ctx, size_t bytes)
+{
+	if (bytes <= ctx->scratch_capacity)
+		return GCR_OK;
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_scratch);
+	ctx->d_scratch = nullptr;
+	ctx->scratch_capacity = 0;
+	bytes = (bytes + (1u << 20)) & ~((size_t)(1u << 20) - 1);
+	GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_scratch, bytes));
+	ctx->scratch_capacity = bytes;
+	return GCR_OK;
+}
+
+gcr_status gcr_ensure_pinned(gcr_ctx *ctx, size_t bytes)
+{
+	if (bytes <= ctx->pinned_capacity)
+		return GCR_OK;
+	if (ctx->h_pinned)
+		cudaFreeHost(ctx->h_pinned);
+	ctx->h_pinned = nullptr;
+	ctx->pinned_capacity = 0;
+	bytes = (bytes + 4095) & ~(size_t)4095;
+	GCR_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, bytes));
+	ctx->pinned_capacity = bytes;
+	return GCR_OK;
+}
+
+// ------------------------------------------------------------------------------- instrumentation helpers ---
+static gcr_status profile_drain(gcr_ctx *ctx)
+{
+	while (ctx->ev_pending > 0)
+	{
+		const int slot = (ctx->ev_head - ctx->ev_pending + 2 * gcr_ctx::EV_RING) % gcr_ctx::EV_RING;
+		GCR_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->ev_b[slot]));
+		float ms = 0.f;
+		GCR_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a[slot], ctx->ev_b[slot]));
+		ctx->score_ms += ms;
+		--ctx->ev_pending;
+	}
+	return GCR_OK;
+}
+
+gcr_status gcr_profile_begin(gcr_ctx *ctx)
+{
+	if (!ctx->profile)
+		return GCR_OK;
+	if (ctx->ev_pending == gcr_ctx::EV_RING)
+	{
+		gcr_status st = profile_drain(ctx);
+		if (st)
+			return st;
+	}
+	const int slot = ctx->ev_head;
+	if (!ctx->ev_a[slot])
+	{
+		GCR_CHECK_CUDA(ctx, cudaEventCreate(&ctx->ev_a[slot]));
+		GCR_CHECK_CUDA(ctx, cudaEventCreate(&ctx->ev_b[slot]));
+	}
+	GCR_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_a[slot], ctx->stream));
+	return GCR_OK;
+}
+
+gcr_status gcr_profile_end(gcr_ctx *ctx, uint64_t evals)
+{
+	if (!ctx->profile)
+		return GCR_OK;
+	GCR_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_b[ctx->ev_head], ctx->stream));
+	ctx->ev_head = (ctx->ev_head + 1) % gcr_ctx::EV_RING;
+	++ctx->ev_pending;
+	++ctx->score_launches;
+	ctx->score_evals += evals;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_profile_enable(gcr_ctx *ctx, int on)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	gcr_status st = profile_drain(ctx);
+	ctx->profile = on != 0;
+	return st;
+}
+
+extern "C" gcr_status gcr_profile_read(gcr_ctx *ctx, double *score_ms, uint64_t *score_launches, uint64_t *score_evals)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	gcr_status st = profile_drain(ctx);
+	if (st)
+		return st;
+	if (score_ms) *score_ms = ctx->score_ms;
+	if (score_launches) *score_launches = ctx->score_launches;
+	if (score_evals) *score_evals = ctx->score_evals;
+	ctx->score_ms = 0.0;
+	ctx->score_launches = 0;
+	ctx->score_evals = 0;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[4], int reset)
+{
+	if (!ctx || !out)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_counters, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	if (reset)
+		GCR_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint64_t), ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return GCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K0 kernels ---
+__global__ void k_bbox_init(unsigned long long *bbox, int entries)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < entries)
+		bbox[i] = (i & 1) ? 0ull : ~0ull; // [..][0] = min -> +max key, [..][1] = max -> 0
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(256) k_bbox(const double *__restrict__ pts, int n, unsigned long long *bbox)
+{
+	const int pair = blockIdx.y;
+	const double *p = pts + (size_t)pair * n * COLS;
+	double mn[COLS], mx[COLS];
+#pragma unroll
+	for (int c = 0; c < COLS; ++c)
+	{
+		mn[c] = INFINITY;
+		mx[c] = -INFINITY;
+	}
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+#pragma unroll
+		for (int c = 0; c < COLS; ++c)
+		{
+			const double v = p[(size_t)i * COLS + c];
+			if (v < mn[c]) mn[c] = v;
+			if (v > mx[c]) mx[c] = v;
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < COLS; ++c)
+	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			const double a = __shfl_xor_sync(0xffffffffu, mn[c], o), b = __shfl_xor_sync(0xffffffffu, mx[c], o);
+			if (a < mn[c]) mn[c] = a;
+			if (b > mx[c]) mx[c] = b;
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicMin(&bbox[((size_t)pair * COLS + c) * 2 + 0], gcr_ordered_u64(mn[c]));
+			atomicMax(&bbox[((size_t)pair * COLS + c) * 2 + 1], gcr_ordered_u64(mx[c]));
+		}
+	}
+}
+
+__device__ __forceinline__ double pow2_scale(double half_extent)
+{
+	if (!(half_extent > 0.0) || isinf(half_extent))
+		return 1.0;
+	int e;
+	frexp(half_extent, &e); // half_extent = f * 2^e, f in [0.5, 1)
+	return ldexp(1.0, -e);
+}
+
+template <int COLS>
+__global__ void k_norm(const unsigned long long *bbox, double *norm, int n_pairs)
+{
+	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pair >= n_pairs)
+		return;
+	double mn[COLS], mx[COLS];
+	for (int c = 0; c < COLS; ++c)
+	{
+		mn[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 0]);
+		mx[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 1]);
+		if (!(mn[c] <= mx[c])) { mn[c] = 0.0; mx[c] = 0.0; }
+	}
+	double *o = norm + (size_t)pair * 8;
+	if (COLS == 4)
+	{
+		double h = 0.0;
+		for (int c = 0; c < 4; ++c)
+		{
+			o[c] = 0.5 * (mn[c] + mx[c]);
+			h = fmax(h, 0.5 * (mx[c] - mn[c]));
+		}
+		o[4] = pow2_scale(h);
+		o[5] = o[6] = o[7] = 0.0;
+	}
+	else
+	{
+		o[0] = 0.5 * (mn[0] + mx[0]);
+		o[1] = 0.5 * (mn[1] + mx[1]);
+		o[2] = pow2_scale(fmax(0.5 * (mx[0] - mn[0]), 0.5 * (mx[1] - mn[1])));
+		double h = 0.0;
+		for (int c = 2; c < 5; ++c)
+		{
+			o[3 + c - 2] = 0.5 * (mn[c] + mx[c]);
+			h = fmax(h, 0.5 * (mx[c] - mn[c]));
+		}
+		o[6] = pow2_scale(h);
+		o[7] = 0.0;
+	}
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(256) k_convert(const double *__restrict__ pts, const double *__restrict__ norm,
+                                                  int n, int n_pad, float4 *__restrict__ out32,
+                                                  float4 *__restrict__ out32dup)
+{
+	const int pair = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pad)
+		return;
+	const double *nm = norm + (size_t)pair * 8;
+	const float nanv = __int_as_float(0x7fc00000);
+	if (COLS == 4)
+	{
+		float4 q = make_float4(nanv, nanv, nanv, nanv);
+		if (i < n)
+		{
+			const double *p = pts + ((size_t)pair * n + i) * 4;
+			const double s = nm[4];
+			q.x = (float)((p[0] - nm[0]) * s);
+			q.y = (float)((p[1] - nm[1]) * s);
+			q.z = (float)((p[2] - nm[2]) * s);
+			q.w = (float)((p[3] - nm[3]) * s);
+		}
+		out32[(size_t)pair * n_pad + i] = q;
+		out32dup[((size_t)pair * n_pad + i) * 2 + 0] = make_float4(q.x, q.x, q.y, q.y);
+		out32dup[((size_t)pair * n_pad + i) * 2 + 1] = make_float4(q.z, q.z, q.w, q.w);
+	}
+	else
+	{
+		float4 a = make_float4(nanv, nanv, 0.f, 0.f), b = make_float4(nanv, nanv, nanv, 0.f);
+		if (i < n)
+		{
+			const double *p = pts + ((size_t)pair * n + i) * 5;
+			a.x = (float)((p[0] - nm[0]) * nm[2]);
+			a.y = (float)((p[1] - nm[1]) * nm[2]);
+			b.x = (float)((p[2] - nm[3]) * nm[6]);
+			b.y = (float)((p[3] - nm[4]) * nm[6]);
+			b.z = (float)((p[4] - nm[5]) * nm[6]);
+		}
+		out32[((size_t)pair * n_pad + i) * 2 + 0] = a;
+		out32[((size_t)pair * n_pad + i) * 2 + 1] = b;
+	}
+}
+
+static gcr_status prepare_points(gcr_ctx *ctx)
+{
+	const int n = ctx->n, cols = ctx->cols, n_pairs = ctx->n_pairs;
+	ctx->n_pad = (n + GCR_TILE_POINTS - 1) / GCR_TILE_POINTS * GCR_TILE_POINTS;
+	const size_t per_point32 = cols == 4 ? 1 : 2;
+	const size_t need32 = (size_t)n_pairs * ctx->n_pad * per_point32;
+	if (need32 > ctx->pts32_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_pts32);
+		cudaFree(ctx->d_pts32dup);
+		ctx->d_pts32 = ctx->d_pts32dup = nullptr;
+		ctx->pts32_capacity = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts32, need32 * sizeof(float4)));
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts32dup, (size_t)n_pairs * ctx->n_pad * 2 * sizeof(float4)));
+		ctx->pts32_capacity = need32;
+	}
+	if ((size_t)n_pairs > ctx->norm_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_norm);
+		cudaFree(ctx->d_bbox);
+		ctx->d_norm = nullptr;
+		ctx->d_bbox = nullptr;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_norm, (size_t)n_pairs * 8 * sizeof(double)));
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_bbox, (size_t)n_pairs * 5 * 2 * sizeof(unsigned long long)));
+		ctx->norm_capacity = n_pairs;
+	}
+	const int entries = n_pairs * cols * 2;
+	k_bbox_init<<<(entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_bbox, entries);
+	GCR_LAUNCHED(ctx);
+	int gx = (n + 255) / 256;
+	const int max_gx = n_pairs >= ctx->sm_count ? 1 : (4 * ctx->sm_count + n_pairs - 1) / n_pairs;
+	if (gx > max_gx) gx = max_gx;
+	if (gx < 1) gx = 1;
+	const dim3 gb(gx, n_pairs), gc((ctx->n_pad + 255) / 256, n_pairs);
+	if (cols == 4)
+	{
+		k_bbox<4><<<gb, 256, 0, ctx->stream>>>(ctx->d_pts64, n, ctx->d_bbox);
+		GCR_LAUNCHED(ctx);
+		k_norm<4><<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bbox, ctx->d_norm, n_pairs);
+		GCR_LAUNCHED(ctx);
+		k_convert<4><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32, ctx->d_pts32dup);
+		GCR_LAUNCHED(ctx);
+	}
+	else
+	{
+		k_bbox<5><<<gb, 256, 0, ctx->stream>>>(ctx->d_pts64, n, ctx->d_bbox);
+		GCR_LAUNCHED(ctx);
+		k_norm<5><<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bbox, ctx->d_norm, n_pairs);
+		GCR_LAUNCHED(ctx);
+		k_convert<5><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32, ctx->d_pts32dup);
+		GCR_LAUNCHED(ctx);
+	}
+	return GCR_OK;
+}
+
+static gcr_status check_shape(gcr_ctx *ctx, const void *p, int n, int cols, int n_pairs)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!p || n <= 0 || n_pairs <= 0 || (cols != 4 && cols != 5))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_points: need n > 0, n_pairs > 0, cols in {4,5} (got n=%d cols=%d pairs=%d)", n, cols, n_pairs);
+	if ((long long)n * n_pairs > (1ll << 31) - 1024)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_points: n * n_pairs too large");
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, int n, int cols, int n_pairs)
+{
+	gcr_status st = check_shape(ctx, h_points, n, cols, n_pairs);
+	if (st)
+		return st;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t bytes = (size_t)n * cols * n_pairs * sizeof(double);
+	if (bytes > ctx->pts64_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_pts64_owned);
+		ctx->d_pts64_owned = nullptr;
+		ctx->pts64_capacity = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts64_owned, bytes));
+		ctx->pts64_capacity = bytes;
+	}
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->d_pts64 = ctx->d_pts64_owned;
+	ctx->n = n;
+	ctx->cols = cols;
+	ctx->n_pairs = n_pairs;
+	return prepare_points(ctx);
+}
+
+extern "C" gcr_status gcr_points_set_device(gcr_ctx *ctx, const double *d_points, int n, int cols, int n_pairs)
+{
+	gcr_status st = check_shape(ctx, d_points, n, cols, n_pairs);
+	if (st)
+		return st;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	ctx->d_pts64 = d_points;
+	ctx->n = n;
+	ctx->cols = cols;
+	ctx->n_pairs = n_pairs;
+	return prepare_points(ctx);
+}
+
+extern "C" gcr_status gcr_points_get_norm(gcr_ctx *ctx, double *h_out)
+{
+	if (!ctx || !h_out)
+		return GCR_ERR_ARG;
+	if (!ctx->d_norm || ctx->n_pairs == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_points_get_norm: no points uploaded");
+	return gcr_memcpy_d2h(ctx, h_out, ctx->d_norm, (size_t)ctx->n_pairs * 8 * sizeof(double));
+}

@@ -1,0 +1,259 @@
+// gcr_internal.cuh -- shared declarations of the sm_100a kernels behind include/gcr/gcr.h.
+// Everything is compiled with -fmad=false: FP64 code then keeps the reference's separately-rounded mul/add
+// (bit parity with the CPU build, which has no FMA contraction), and the FP32 hot loops state their FMAs
+// explicitly (fmaf / __ffma2_rn).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "gcr/gcr.h"
+
+struct gcr_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t own_stream = nullptr;
+	char err[512] = {0};
+	int sm_count = 0;
+	int sm_clock_khz = 0;
+	size_t l2_bytes = 0;
+	uint64_t launches = 0;
+
+	// points
+	int n = 0, cols = 0, n_pairs = 0;
+	const double *d_pts64 = nullptr; // [n_pairs][n][cols]
+	double *d_pts64_owned = nullptr;
+	size_t pts64_capacity = 0;
+	float4 *d_pts32 = nullptr; // [n_pairs][n_pad] float4 (cols==4) or [n_pairs][n_pad][2] float4 (cols==5)
+	float4 *d_pts32dup = nullptr; // [n_pairs][n_pad][2] float4: (x1 x1 y1 y1)(x2 x2 y2 y2) for the packed f32x2 path
+	size_t pts32_capacity = 0;
+	int n_pad = 0;              // n rounded up to the tile granule; padding points can never be inliers
+	double *d_norm = nullptr;  // [n_pairs][8]
+	unsigned long long *d_bbox = nullptr; // [n_pairs][cols][2] ordered-u64 min/max
+	size_t norm_capacity = 0;
+
+	// MAGSAC weight table (FP32): (Gamma(1.5, k/1000) - gamma_k) / (Gamma(1.5) - gamma_k), k = 0..5000
+	float *d_magsac_lut = nullptr;
+	double *d_magsac_lut64 = nullptr; // Gamma(1.5, k/1000), k = 0..5000 (FP64 exact path)
+
+	// PROSAC growth function T'_n (prosac_sampler.h:129-160) for the current (n, m)
+	unsigned long long *d_prosac_growth = nullptr;
+	int prosac_n = 0, prosac_m = 0;
+
+	// per-round buffers of gcr_round (samples, models, valid flags, scores)
+	void *d_round = nullptr;
+	size_t round_capacity = 0;
+
+	// counters (device, u64): [0] valid models produced by K2 since the last reset
+	unsigned long long *d_counters = nullptr;
+	// optional per-launch timing of the scoring kernel (bench.py's roofline leg)
+	bool profile = false;
+	static const int EV_RING = 128;
+	cudaEvent_t ev_a[EV_RING] = {nullptr}, ev_b[EV_RING] = {nullptr};
+	int ev_head = 0, ev_pending = 0; // ring of recorded-but-unread event pairs
+	double score_ms = 0.0;
+	uint64_t score_launches = 0;
+	uint64_t score_evals = 0;
+
+	// scratch
+	void *d_scratch = nullptr;
+	size_t scratch_capacity = 0;
+	void *h_pinned = nullptr;
+	size_t pinned_capacity = 0;
+
+	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu
+	int score_variant = -1;    // -1 auto; else forces a kernel variant (bench / tests)
+};
+
+#define GCR_CHECK_CUDA(ctx, expr)                                                                              \
+	do                                                                                                         \
+	{                                                                                                          \
+		cudaError_t _e = (expr);                                                                               \
+		if (_e != cudaSuccess)                                                                                 \
+		{                                                                                                      \
+			snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,            \
+			         cudaGetErrorString(_e));                                                                  \
+			return GCR_ERR_CUDA;                                                                               \
+		}                                                                                                      \
+	} while (0)
+
+#define GCR_FAIL(ctx, code, ...)                                                                               \
+	do                                                                                                         \
+	{                                                                                                          \
+		snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);                                                 \
+		return (code);                                                                                         \
+	} while (0)
+
+#define GCR_LAUNCHED(ctx)                                                                                      \
+	do                                                                                                         \
+	{                                                                                                          \
+		++(ctx)->launches;                                                                                     \
+		GCR_CHECK_CUDA(ctx, cudaGetLastError());                                                               \
+	} while (0)
+
+gcr_status gcr_ensure_scratch(gcr_ctx *ctx, size_t bytes);
+gcr_status gcr_ensure_pinned(gcr_ctx *ctx, size_t bytes);
+gcr_status gcr_profile_begin(gcr_ctx *ctx);
+gcr_status gcr_profile_end(gcr_ctx *ctx, uint64_t evals);
+gcr_status gcr_ensure_prosac_growth(gcr_ctx *ctx, int m);
+
+static inline int gcr_cols_of(int problem) { return problem == GCR_PNP ? 5 : 4; }
+
+// ---- device helpers -------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Philox4x32-10 (same constants / round function as oracle gcro_philox4x32)
+__device__ __forceinline__ void gcr_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+	for (int r = 0; r < 10; ++r)
+	{
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct GcrDrawStream
+{
+	uint32_t c0, c1, block, stream, k0, k1, buf[4];
+	int pos;
+	__device__ GcrDrawStream(uint64_t seed, uint64_t index, uint32_t stream_)
+	    : c0((uint32_t)index), c1((uint32_t)(index >> 32)), block(0), stream(stream_), k0((uint32_t)seed),
+	      k1((uint32_t)(seed >> 32)), pos(4)
+	{
+	}
+	__device__ uint32_t next()
+	{
+		if (pos == 4)
+		{
+			gcr_philox4x32(c0, c1, block, stream, k0, k1, buf);
+			++block;
+			pos = 0;
+		}
+		// avoid dynamic register indexing
+		const uint32_t v = pos == 0 ? buf[0] : pos == 1 ? buf[1] : pos == 2 ? buf[2] : buf[3];
+		++pos;
+		return v;
+	}
+	__device__ uint32_t bounded(uint32_t range)
+	{
+		for (;;)
+		{
+			const uint32_t u = next();
+			const uint32_t lo = u * range;
+			if (lo < range)
+			{
+				const uint32_t thresh = (0u - range) % range;
+				if (lo < thresh)
+					continue;
+			}
+			return __umulhi(u, range);
+		}
+	}
+	// m <= 8 distinct values in [0, range) by draw-and-reject, kept in draw order
+	template <int MAXM>
+	__device__ void unique_set(uint32_t *out, int count, uint32_t range)
+	{
+#pragma unroll
+		for (int i = 0; i < MAXM; ++i)
+		{
+			if (i < count)
+			{
+				bool dup;
+				uint32_t v;
+				do
+				{
+					v = bounded(range);
+					dup = false;
+#pragma unroll
+					for (int j = 0; j < MAXM; ++j)
+						if (j < i && out[j] == v)
+							dup = true;
+				} while (dup);
+				out[i] = v;
+			}
+		}
+	}
+};
+
+__device__ __forceinline__ unsigned long long gcr_ordered_u64(double x)
+{
+	const long long b = __double_as_longlong(x);
+	return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double gcr_from_ordered_u64(unsigned long long k)
+{
+	const long long b = (k & 0x8000000000000000ull) ? (long long)(k ^ 0x8000000000000000ull) : (long long)~k;
+	return __longlong_as_double(b);
+}
+
+// monotone map float -> uint32 (larger float => larger uint)
+__host__ __device__ __forceinline__ uint32_t gcr_ordered_u32(float f)
+{
+#ifdef __CUDA_ARCH__
+	const uint32_t b = __float_as_uint(f);
+#else
+	union { float f; uint32_t u; } cvt; cvt.f = f; const uint32_t b = cvt.u;
+#endif
+	return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float gcr_from_ordered_u32(uint32_t k)
+{
+	const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(b);
+#else
+	union { float f; uint32_t u; } cvt; cvt.u = b; return cvt.f;
+#endif
+}
+
+// ---- FP64 residuals in the reference's operation order (no contraction: file is built with -fmad=false) -------
+__device__ __forceinline__ double gcr_sqres_h64(const double *s, const double *H)
+{
+	const double x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
+	const double t1 = H[0] * x1 + H[1] * y1 + H[2];
+	const double t2 = H[3] * x1 + H[4] * y1 + H[5];
+	const double t3 = H[6] * x1 + H[7] * y1 + H[8];
+	const double d1 = x2 - (t1 / t3);
+	const double d2 = y2 - (t2 / t3);
+	return d1 * d1 + d2 * d2;
+}
+__device__ __forceinline__ double gcr_sqres_sampson64(const double *s, const double *F)
+{
+	const double x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
+	const double rxc = F[0] * x2 + F[3] * y2 + F[6];
+	const double ryc = F[1] * x2 + F[4] * y2 + F[7];
+	const double rwc = F[2] * x2 + F[5] * y2 + F[8];
+	const double r = (x1 * rxc + y1 * ryc + rwc);
+	const double rx = F[0] * x1 + F[1] * y1 + F[2];
+	const double ry = F[3] * x1 + F[4] * y1 + F[5];
+	return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry);
+}
+__device__ __forceinline__ double gcr_sqres_pnp64(const double *s, const double *P)
+{
+	const double u = s[0], v = s[1], x = s[2], y = s[3], z = s[4];
+	const double px = P[0] * x + P[1] * y + P[2] * z + P[3];
+	const double py = P[4] * x + P[5] * y + P[6] * z + P[7];
+	const double pz = P[8] * x + P[9] * y + P[10] * z + P[11];
+	const double pu = px / pz, pv = py / pz;
+	const double du = pu - u, dv = pv - v;
+	return du * du + dv * dv;
+}
+template <int PROBLEM>
+__device__ __forceinline__ double gcr_sqres64(const double *pt, const double *model)
+{
+	if (PROBLEM == GCR_H)
+		return gcr_sqres_h64(pt, model);
+	if (PROBLEM == GCR_PNP)
+		return gcr_sqres_pnp64(pt, model);
+	return gcr_sqres_sampson64(pt, model);
+}
+
+#endif // __CUDACC__

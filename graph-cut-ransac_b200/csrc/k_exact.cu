@@ -1,0 +1,229 @@
+// k_exact.cu -- K5: FP64 scoring of a few models in the reference's operation order, with the ascending inlier list
+// (the side output of getScore, scoring_function.h:166-167 / :338-344) and optional per-point residuals (what
+// GCRANSAC::labeling, GCRANSAC.h:945-961, and the Tukey weights, :657-668, consume).
+//
+// One CTA per model; threads stride over the points in 1024-point blocks; the inlier list is written with a
+// ballot/prefix compaction so indices come out ascending exactly like the reference's emplace_back order.
+// HBM-bound: 32 B (40 B PnP) read per point per model; used O(log K) times per run (new-best events, LO, IRLS).
+#include "gcr_internal.cuh"
+
+#include <math.h>
+
+#define EX_THREADS 1024
+
+struct ExactArgs
+{
+	const double *pts;    // [n][cols] of the selected pair
+	const double *models; // [k][ML]
+	const double *lut64;  // MAGSAC: Gamma(1.5, j/1000), j = 0..5000
+	double *scores;
+	uint32_t *counts;
+	uint32_t *inlier_idx; // [k][n] or null
+	double *residuals;    // [k][n] or null
+	int n, k;
+	double thr;
+};
+
+template <int PROBLEM, int SCORING>
+__global__ void __launch_bounds__(EX_THREADS) k_score_exact(const ExactArgs a)
+{
+	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	__shared__ uint32_t warp_counts[32];
+	__shared__ double warp_sums[32];
+	__shared__ uint32_t base_shared;
+
+	const int model = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	double M[ML];
+	for (int i = 0; i < ML; ++i)
+		M[i] = a.models[(size_t)model * ML + i];
+
+	// thresholds exactly as the reference forms them
+	const double truncated_threshold = 3.0 / 2.0 * a.thr;                                 // GCRANSAC.h:253
+	const double squared_truncated_threshold = truncated_threshold * truncated_threshold; // GCRANSAC.h:254
+	// MAGSAC constants, scoring_function.h:257-296
+	const double gamma_k = 0.0036572608340910764;
+	const double gamma_difference = 0.88622692545275801365 - gamma_k; // tgamma(1.5)
+	const double C_times_two_ad_dof = 0.25 * 2.8284271247461903; // C * pow(2, 1.5)
+	const double squared_sigma_max_2 = a.thr * a.thr * 2.0;
+	const double one_over_sigma = C_times_two_ad_dof / a.thr;
+	const double weight_zero = one_over_sigma * gamma_difference;
+
+	if (tid == 0)
+		base_shared = 0;
+	__syncthreads();
+
+	double local_sum = 0.0;
+	for (int start = 0; start < a.n; start += EX_THREADS)
+	{
+		const int i = start + tid;
+		bool inlier = false;
+		if (i < a.n)
+		{
+			double pt[COLS];
+			for (int c = 0; c < COLS; ++c)
+				pt[c] = a.pts[(size_t)i * COLS + c];
+			const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+			if (a.residuals)
+				a.residuals[(size_t)model * a.n + i] = r2;
+			if (SCORING == GCR_MSAC)
+			{
+				if (r2 < squared_truncated_threshold) // scoring_function.h:163
+				{
+					inlier = true;
+					local_sum -= r2; // :177
+				}
+			}
+			else
+			{
+				const double residual = sqrt(r2); // :300-302
+				if (!(residual > a.thr))          // :304
+				{
+					double weight;
+					if (residual < 2.220446049250313e-16)
+						weight = weight_zero;
+					else
+					{
+						const double squared_residual = residual * residual;
+						unsigned long long x = (unsigned long long)round(1e4 * squared_residual / squared_sigma_max_2);
+						if (36000 < x)
+							x = 36000;
+						if (x > 5000)
+							x = 5000; // unreachable for residual <= thr; guards the 5001-entry table
+						weight = one_over_sigma * (a.lut64[x] - gamma_k);
+					}
+					local_sum += weight / weight_zero;
+					inlier = true; // residual <= threshold_ (:338)
+				}
+			}
+		}
+		// ordered compaction
+		const uint32_t ballot = __ballot_sync(0xffffffffu, inlier);
+		if (lane == 0)
+			warp_counts[warp] = __popc(ballot);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+		for (int w = 0; w < EX_THREADS / 32; ++w)
+		{
+			const uint32_t c = warp_counts[w];
+			if (w < warp) before += c;
+			total += c;
+		}
+		const uint32_t base = base_shared;
+		if (inlier && a.inlier_idx)
+			a.inlier_idx[(size_t)model * a.n + base + before + __popc(ballot & ((1u << lane) - 1))] = (uint32_t)i;
+		__syncthreads();
+		if (tid == 0)
+			base_shared = base + total;
+	}
+	// deterministic tree sum of the score terms
+	for (int o = 16; o > 0; o >>= 1)
+		local_sum += __shfl_xor_sync(0xffffffffu, local_sum, o);
+	if (lane == 0)
+		warp_sums[warp] = local_sum;
+	__syncthreads();
+	if (tid == 0)
+	{
+		double value = 0.0;
+		for (int w = 0; w < EX_THREADS / 32; ++w)
+			value += warp_sums[w];
+		const uint32_t inliers = base_shared;
+		double score;
+		if (SCORING == GCR_MSAC)
+			score = inliers == 0 ? 0.0
+			                     : (value + inliers * squared_truncated_threshold) / squared_truncated_threshold; // :221-229
+		else
+			score = value;
+		a.scores[model] = score;
+		a.counts[model] = inliers;
+	}
+}
+
+__global__ void k_fill_lut64(double *lut)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > 5000)
+		return;
+	const double x = k / 1000.0, sx = sqrt(x);
+	lut[k] = 0.88622692545275801365 * erfc(sx) + sx * exp(-x);
+}
+
+extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
+                                      double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
+                                      double *d_residuals)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_score_exact: no points uploaded");
+	if (problem < GCR_H || problem > GCR_PNP || gcr_cols_of(problem) != ctx->cols)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: problem does not match the uploaded points");
+	if (pair < 0 || pair >= ctx->n_pairs || k <= 0 || !d_models || !d_scores || !d_counts)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (scoring == GCR_MAGSAC && !ctx->d_magsac_lut64)
+	{
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_magsac_lut64, 5008 * sizeof(double)));
+		k_fill_lut64<<<(5001 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_magsac_lut64);
+		GCR_LAUNCHED(ctx);
+	}
+	ExactArgs a;
+	a.pts = ctx->d_pts64 + (size_t)pair * ctx->n * ctx->cols;
+	a.models = d_models;
+	a.lut64 = ctx->d_magsac_lut64;
+	a.scores = d_scores;
+	a.counts = d_counts;
+	a.inlier_idx = d_inlier_idx;
+	a.residuals = d_residuals;
+	a.n = ctx->n;
+	a.k = k;
+	a.thr = threshold;
+#define GCR_EX(P)                                                                                        \
+	do                                                                                                   \
+	{                                                                                                    \
+		if (scoring == GCR_MSAC)                                                                         \
+			k_score_exact<P, GCR_MSAC><<<k, EX_THREADS, 0, ctx->stream>>>(a);                             \
+		else                                                                                             \
+			k_score_exact<P, GCR_MAGSAC><<<k, EX_THREADS, 0, ctx->stream>>>(a);                           \
+	} while (0)
+	if (problem == GCR_H)
+		GCR_EX(GCR_H);
+	else if (problem == GCR_PNP)
+		GCR_EX(GCR_PNP);
+	else
+		GCR_EX(GCR_F);
+#undef GCR_EX
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_score_exact_host(gcr_ctx *ctx, int problem, int scoring, int pair, const double *h_models,
+                                           int k, double threshold, double *h_scores, uint32_t *h_counts,
+                                           uint32_t *h_inlier_idx, double *h_residuals)
+{
+	if (!ctx || !h_models || !h_scores || !h_counts || k <= 0)
+		return GCR_ERR_ARG;
+	const int ml = problem == GCR_PNP ? 12 : 9;
+	const size_t n = ctx->n;
+	void *d_m = nullptr, *d_s = nullptr, *d_c = nullptr, *d_i = nullptr, *d_r = nullptr;
+	gcr_status st = gcr_malloc(ctx, (size_t)k * ml * sizeof(double), &d_m);
+	if (!st) st = gcr_malloc(ctx, k * sizeof(double), &d_s);
+	if (!st) st = gcr_malloc(ctx, k * sizeof(uint32_t), &d_c);
+	if (!st && h_inlier_idx) st = gcr_malloc(ctx, (size_t)k * n * sizeof(uint32_t), &d_i);
+	if (!st && h_residuals) st = gcr_malloc(ctx, (size_t)k * n * sizeof(double), &d_r);
+	if (!st) st = gcr_memcpy_h2d(ctx, d_m, h_models, (size_t)k * ml * sizeof(double));
+	if (!st)
+		st = gcr_score_exact(ctx, problem, scoring, pair, (const double *)d_m, k, threshold, (double *)d_s,
+		                     (uint32_t *)d_c, (uint32_t *)d_i, (double *)d_r);
+	if (!st) st = gcr_memcpy_d2h(ctx, h_scores, d_s, k * sizeof(double));
+	if (!st) st = gcr_memcpy_d2h(ctx, h_counts, d_c, k * sizeof(uint32_t));
+	if (!st && h_inlier_idx) st = gcr_memcpy_d2h(ctx, h_inlier_idx, d_i, (size_t)k * n * sizeof(uint32_t));
+	if (!st && h_residuals) st = gcr_memcpy_d2h(ctx, h_residuals, d_r, (size_t)k * n * sizeof(double));
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_m);
+	cudaFree(d_s);
+	cudaFree(d_c);
+	cudaFree(d_i);
+	cudaFree(d_r);
+	return st;
+}

@@ -1,0 +1,195 @@
+// k_sample.cu -- K1: minimal-sample index sets from a counter-based generator.
+//
+// Replaces UniformSampler::sample (samplers/uniform_sampler.h:81-99) with
+// UniformRandomGenerator::generateUniqueRandomSet (uniform_random_generator.h:90-103) and ProsacSampler::sample /
+// incrementIterationNumber (samplers/prosac_sampler.h:65-88, 207-236).  The reference draws from a std::mt19937
+// seeded by std::random_device (not reproducible, inherently sequential); here sample i is a pure function of
+// (seed, i, pair) through Philox4x32-10, so any range of the sample stream can be generated in parallel, on any
+// GPU, and replayed on the CPU by the oracle (gcro_sample_uniform / gcro_sample_prosac) bit for bit.
+// One thread = one sample; integer work only.
+#include "gcr_internal.cuh"
+
+#include <math.h>
+#include <vector>
+
+#define GCR_PAIR_SEED_STRIDE 0x9E3779B97F4A7C15ull
+
+__global__ void __launch_bounds__(256) k_sample_uniform(uint32_t *__restrict__ out, int count, int m, uint32_t n,
+                                                         uint64_t first_index, uint64_t seed)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const int pair = blockIdx.y;
+	GcrDrawStream s(seed + (uint64_t)pair * GCR_PAIR_SEED_STRIDE, first_index + (uint64_t)i, 0u);
+	uint32_t v[8];
+	s.unique_set<8>(v, m, n);
+	uint32_t *o = out + ((size_t)pair * count + i) * m;
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		if (j < m)
+			o[j] = v[j];
+}
+
+// closed form of the subset-size recurrence of prosac_sampler.h:65-88 (see oracle gcro_prosac_subset_size)
+__device__ __forceinline__ uint32_t prosac_subset_size(const unsigned long long *__restrict__ growth, uint32_t n, int m,
+                                                       unsigned long long k)
+{
+	uint32_t lo = (uint32_t)m, hi = n;
+	if (lo >= hi)
+		return n < (uint32_t)m ? (uint32_t)m : hi;
+	while (lo < hi)
+	{
+		const uint32_t mid = lo + (hi - lo) / 2;
+		if (growth[mid - 1] >= k)
+			hi = mid;
+		else
+			lo = mid + 1;
+	}
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ out, int count, int m, uint32_t n,
+                                                        uint64_t first_k, uint64_t seed,
+                                                        const unsigned long long *__restrict__ growth,
+                                                        unsigned long long convergence)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const int pair = blockIdx.y;
+	const unsigned long long k = first_k + (unsigned long long)i;
+	GcrDrawStream s(seed + (uint64_t)pair * GCR_PAIR_SEED_STRIDE, k, 1u);
+	uint32_t v[8];
+	if (k > convergence)
+		s.unique_set<8>(v, m, n);
+	else
+	{
+		const uint32_t subset = prosac_subset_size(growth, n, m, k);
+		const uint32_t range = (k == 1) ? (uint32_t)m : subset - 1; // first-draw quirk, prosac_sampler.h:171-172
+		s.unique_set<8>(v, m - 1, range);
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (j == m - 1)
+				v[j] = subset - 1;
+	}
+	uint32_t *o = out + ((size_t)pair * count + i) * m;
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		if (j < m)
+			o[j] = v[j];
+}
+
+// GCRANSAC.h:842-846: uniform draws of m (<= 49) distinct positions in a pool, mapped through the pool
+__global__ void __launch_bounds__(128) k_sample_pool(const uint32_t *__restrict__ pool, uint32_t pool_size, int m,
+                                                      uint64_t first_index, int count, uint64_t seed, uint32_t stream,
+                                                      uint32_t *__restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	GcrDrawStream s(seed, first_index + (uint64_t)i, stream);
+	uint32_t *o = out + (size_t)i * m;
+	// draw-and-reject with the already chosen positions kept in the output row (positions first, mapped afterwards)
+	for (int j = 0; j < m; ++j)
+	{
+		bool dup;
+		uint32_t v;
+		do
+		{
+			v = s.bounded(pool_size);
+			dup = false;
+			for (int q = 0; q < j; ++q)
+				if (o[q] == v)
+					dup = true;
+		} while (dup);
+		o[j] = v;
+	}
+	for (int j = 0; j < m; ++j)
+		o[j] = pool[o[j]];
+}
+
+// prosac_sampler.h:129-160 growth function, FP64 recurrence on the host exactly as the reference runs it
+static void prosac_growth_host(uint32_t n, int m, uint64_t convergence_iters, std::vector<unsigned long long> &growth)
+{
+	const size_t sample_size = (size_t)m, point_number = n;
+	growth.assign(n, 0);
+	double T_n = (double)convergence_iters;
+	for (size_t i = 0; i < sample_size; i++)
+		T_n *= static_cast<double>(sample_size - i) / (point_number - i);
+	size_t T_n_prime = 1;
+	for (size_t i = 0; i < point_number; ++i)
+	{
+		if (i + 1 <= sample_size)
+		{
+			growth[i] = T_n_prime;
+			continue;
+		}
+		double Tn_plus1 = static_cast<double>(i + 1) * T_n / (i + 1 - sample_size);
+		growth[i] = T_n_prime + (unsigned int)ceil(Tn_plus1 - T_n);
+		T_n = Tn_plus1;
+		T_n_prime = growth[i];
+	}
+}
+
+gcr_status gcr_ensure_prosac_growth(gcr_ctx *ctx, int m)
+{
+	if (ctx->d_prosac_growth && ctx->prosac_n == ctx->n && ctx->prosac_m == m)
+		return GCR_OK;
+	std::vector<unsigned long long> growth;
+	prosac_growth_host((uint32_t)ctx->n, m, 100000, growth);
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_prosac_growth);
+	ctx->d_prosac_growth = nullptr;
+	GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_prosac_growth, growth.size() * sizeof(unsigned long long)));
+	GCR_CHECK_CUDA(ctx, cudaMemcpy(ctx->d_prosac_growth, growth.data(), growth.size() * sizeof(unsigned long long),
+	                               cudaMemcpyHostToDevice));
+	ctx->prosac_n = ctx->n;
+	ctx->prosac_m = m;
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_sample(gcr_ctx *ctx, int sampler, int m, uint64_t first_index, int count, uint64_t seed,
+                                 uint32_t *d_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_sample: no points uploaded (the pool is [0, n))");
+	if (m < 1 || m > 8 || count <= 0 || !d_out)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: need 1 <= m <= 8, count > 0");
+	if (m > ctx->n)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: sample size %d exceeds the %d points (uniform_sampler.h:87-88)", m, ctx->n);
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const dim3 grid((count + 255) / 256, ctx->n_pairs);
+	if (sampler == GCR_UNIFORM)
+		k_sample_uniform<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed);
+	else if (sampler == GCR_PROSAC)
+	{
+		if (first_index < 1)
+			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: PROSAC draws are numbered from k = 1");
+		gcr_status st = gcr_ensure_prosac_growth(ctx, m);
+		if (st)
+			return st;
+		k_sample_prosac<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed,
+		                                                ctx->d_prosac_growth, 100000ull);
+	}
+	else
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: unknown sampler %d", sampler);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_sample_from_pool(gcr_ctx *ctx, const uint32_t *d_pool, uint32_t pool_size, int m,
+                                           uint64_t first_index, int count, uint64_t seed, uint32_t stream,
+                                           uint32_t *d_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_pool || !d_out || m < 1 || count <= 0 || (uint32_t)m > pool_size)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample_from_pool: need 1 <= m <= pool_size, count > 0");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	k_sample_pool<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_pool, pool_size, m, first_index, count, seed, stream, d_out);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}

@@ -1,0 +1,231 @@
+// k_solve.cu -- K2: batched minimal solvers, one hypothesis (sample) per thread, FP64, with the sample / model
+// validity tests of the reference's estimators folded into the same kernel.
+//
+//   H  4-pt: RobustHomographyEstimator::isValidSample (estimators/homography_estimator.h:346-381) +
+//            HomographyFourPointSolver::estimateMinimalModel (estimators/solver_homography_four_point.h:109-190) with
+//            utils::gaussElimination<8> (math_utils.h:45-87) -- same operation order, no FMA contraction, so the
+//            models are bit-identical to the reference's.
+//   F  7-pt: FundamentalMatrixSevenPointSolver::estimateModel (estimators/solver_fundamental_matrix_seven_point.h
+//            :91-291): full-pivot LU null space (Eigen FullPivLU::kernel semantics), cubic det(lambda F1 + (1-lambda)
+//            F2) = 0 solved by bracketing at the derivative's roots + safeguarded Newton (only + - * / sqrt, so CPU
+//            oracle and GPU agree bit for bit), roots in ascending order; then the oriented epipolar constraint of
+//            FundamentalMatrixEstimator::estimateModel (estimators/fundamental_estimator.h:161-184, 737-800).
+// The solvers are O(K) work against the O(K N) of scoring: they run from L2-resident FP64 points with
+// per-thread local arrays; no attempt is made to put them on tensor cores.
+#include "gcr_internal.cuh"
+
+#include <math.h>
+
+#include "solve_f7.cuh"
+
+extern "C" int gcr_max_models(int problem)
+{
+	switch (problem)
+	{
+	case GCR_H: return 1;
+	case GCR_F: return 3;
+	case GCR_E: return 10;
+	case GCR_PNP: return 4;
+	default: return 0;
+	}
+}
+extern "C" int gcr_sample_size(int problem)
+{
+	switch (problem)
+	{
+	case GCR_H: return 4;
+	case GCR_F: return 7;
+	case GCR_E: return 5;
+	case GCR_PNP: return 3;
+	default: return 0;
+	}
+}
+extern "C" int gcr_model_len(int problem) { return problem == GCR_PNP ? 12 : 9; }
+
+// valid-model counter: one atomic per warp (threads that exited early simply do not take part)
+__device__ __forceinline__ void count_valid(unsigned long long *counters, uint32_t mine)
+{
+	const uint32_t active = __activemask();
+	// only the tail warp of a launch can be partial: per-thread atomics there, a shuffle reduction elsewhere
+	if (active == 0xffffffffu)
+	{
+		uint32_t total = mine;
+		for (int o = 16; o > 0; o >>= 1)
+			total += __shfl_xor_sync(0xffffffffu, total, o);
+		if ((threadIdx.x & 31) == 0 && total)
+			atomicAdd(&counters[0], (unsigned long long)total);
+	}
+	else if (mine)
+		atomicAdd(&counters[0], (unsigned long long)mine);
+}
+
+// ---------------------------------------------------------------------------------------------------- H4 ----
+__device__ __forceinline__ void h_cross(double *r, const double *v1, const double *v2)
+{
+	r[0] = v1[1] - v2[1];
+	r[1] = v2[0] - v1[0];
+	r[2] = v1[0] * v2[1] - v1[1] * v2[0];
+}
+
+__device__ bool h_valid_sample(const double *a, const double *b, const double *c, const double *d)
+{
+	double p[3], q[3];
+	h_cross(p, a, b);
+	h_cross(q, a + 2, b + 2);
+	if ((p[0] * c[0] + p[1] * c[1] + p[2]) * (q[0] * c[2] + q[1] * c[3] + q[2]) < 0)
+		return false;
+	if ((p[0] * d[0] + p[1] * d[1] + p[2]) * (q[0] * d[2] + q[1] * d[3] + q[2]) < 0)
+		return false;
+	h_cross(p, c, d);
+	h_cross(q, c + 2, d + 2);
+	if ((p[0] * a[0] + p[1] * a[1] + p[2]) * (q[0] * a[2] + q[1] * a[3] + q[2]) < 0)
+		return false;
+	if ((p[0] * b[0] + p[1] * b[1] + p[2]) * (q[0] * b[2] + q[1] * b[3] + q[2]) < 0)
+		return false;
+	return true;
+}
+
+__global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts, int n,
+                                                  const uint32_t *__restrict__ samples, int count,
+                                                  double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                  unsigned long long *__restrict__ counters)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const int pair = blockIdx.y;
+	const double *P = pts + (size_t)pair * n * 4;
+	const uint32_t *s = samples + ((size_t)pair * count + i) * 4;
+	double pt[4][4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j)
+	{
+		const double *p = P + (size_t)s[j] * 4;
+		pt[j][0] = p[0]; pt[j][1] = p[1]; pt[j][2] = p[2]; pt[j][3] = p[3];
+	}
+	double *out = models + ((size_t)pair * count + i) * 9;
+	bool ok = h_valid_sample(pt[0], pt[1], pt[2], pt[3]);
+	double M[8][9];
+	if (ok)
+	{
+		int row = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+		{
+			const double x1 = pt[j][0], y1 = pt[j][1], x2 = pt[j][2], y2 = pt[j][3];
+			const double weight = 1.0;
+			const double mwx1 = -weight * x1, mwy1 = -weight * y1, wx2 = weight * x2, wy2 = weight * y2;
+			M[row][0] = mwx1; M[row][1] = mwy1; M[row][2] = -weight; M[row][3] = 0; M[row][4] = 0; M[row][5] = 0;
+			M[row][6] = wx2 * x1; M[row][7] = wx2 * y1; M[row][8] = -wx2;
+			++row;
+			M[row][0] = 0; M[row][1] = 0; M[row][2] = 0; M[row][3] = mwx1; M[row][4] = mwy1; M[row][5] = -weight;
+			M[row][6] = wy2 * x1; M[row][7] = wy2 * y1; M[row][8] = -wy2;
+			++row;
+		}
+		// math_utils.h:54-62 "pivotisation"
+		for (int a = 0; a < 8; a++)
+			for (int k = a + 1; k < 8; k++)
+				if (fabs(M[a][a]) < fabs(M[k][a]))
+					for (int j = 0; j <= 8; j++)
+					{
+						const double temp = M[a][j];
+						M[a][j] = M[k][j];
+						M[k][j] = temp;
+					}
+		// :65-72 elimination
+		for (int a = 0; a < 7; a++)
+			for (int k = a + 1; k < 8; k++)
+			{
+				const double temp = M[k][a] / M[a][a];
+				for (int j = 0; j <= 8; j++)
+					M[k][j] = M[k][j] - temp * M[a][j];
+			}
+		// :75-86 back substitution
+		double h[8];
+		for (int a = 7; a >= 0; a--)
+		{
+			h[a] = M[a][8];
+			for (int j = a + 1; j < 8; j++)
+				h[a] = h[a] - M[a][j] * h[j];
+			h[a] = h[a] / M[a][a];
+		}
+		for (int j = 0; j < 8; ++j)
+			if (isnan(h[j]))
+				ok = false;
+		if (ok)
+		{
+			for (int j = 0; j < 8; ++j)
+				out[j] = h[j];
+			out[8] = 1.0;
+		}
+	}
+	if (!ok)
+		for (int j = 0; j < 9; ++j)
+			out[j] = 0.0;
+	valid[(size_t)pair * count + i] = ok ? 1 : 0;
+	count_valid(counters, ok ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------- F7 ----
+__global__ void __launch_bounds__(128) k_solve_f7(const double *__restrict__ pts, int n,
+                                                  const uint32_t *__restrict__ samples, int count,
+                                                  double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                  unsigned long long *__restrict__ counters)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const int pair = blockIdx.y;
+	const double *P = pts + (size_t)pair * n * 4;
+	const uint32_t *s = samples + ((size_t)pair * count + i) * 7;
+	double pt[7][4];
+	for (int j = 0; j < 7; ++j)
+	{
+		const double *p = P + (size_t)s[j] * 4;
+		pt[j][0] = p[0]; pt[j][1] = p[1]; pt[j][2] = p[2]; pt[j][3] = p[3];
+	}
+	double F[3][9];
+	const int nm = gcr_f7::solve(&pt[0][0], &F[0][0]);
+	double *out = models + ((size_t)pair * count + i) * 27;
+	uint8_t *v = valid + ((size_t)pair * count + i) * 3;
+	uint32_t n_ok = 0;
+	for (int mdl = 0; mdl < 3; ++mdl)
+	{
+		bool ok = mdl < nm;
+		if (ok)
+			ok = gcr_f7::orientation_valid(F[mdl], &pt[0][0], 7); // fundamental_estimator.h:175-180
+		for (int j = 0; j < 9; ++j)
+			out[mdl * 9 + j] = ok ? F[mdl][j] : 0.0;
+		v[mdl] = ok ? 1 : 0;
+		n_ok += ok ? 1u : 0u;
+	}
+	count_valid(counters, n_ok);
+}
+
+extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
+                                        double *d_models, uint8_t *d_valid)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_solve_minimal: no points uploaded");
+	if (problem < GCR_H || problem > GCR_PNP || gcr_cols_of(problem) != ctx->cols)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: problem does not match the uploaded points");
+	if (!d_samples || !d_models || !d_valid || count <= 0)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const dim3 grid((count + 127) / 128, ctx->n_pairs);
+	switch (problem)
+	{
+	case GCR_H:
+		k_solve_h4<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		break;
+	case GCR_F:
+		k_solve_f7<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		break;
+	default:
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: solver for problem %d is not built yet", problem);
+	}
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}

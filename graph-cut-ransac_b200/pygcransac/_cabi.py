@@ -1,0 +1,344 @@
+"""ctypes view of the C ABI in include/gcr/gcr.h (libgcr_b200.so, sm_100a).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is present, loading /
+context creation raises.  Nothing in here touches the CPU oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libgcr_b200.so")
+
+H, F, E, PNP = 0, 1, 2, 3
+MSAC, MAGSAC = 0, 1
+UNIFORM, PROSAC = 0, 1
+WEIGHT_NONE, WEIGHT_POSITIONAL, WEIGHT_BY_POINT = 0, 1, 2
+SCORE_EXACT_COUNTS = 1
+
+# every symbol include/gcr/gcr.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "gcr_ctx_create", "gcr_ctx_destroy", "gcr_ctx_set_stream", "gcr_sync", "gcr_last_error", "gcr_version",
+    "gcr_device_info", "gcr_launch_count", "gcr_malloc", "gcr_free", "gcr_memcpy_h2d", "gcr_memcpy_d2h", "gcr_memset",
+    "gcr_points_upload", "gcr_points_set_device", "gcr_points_get_norm", "gcr_sample", "gcr_sample_from_pool",
+    "gcr_solve_minimal", "gcr_max_models", "gcr_sample_size", "gcr_model_len", "gcr_score", "gcr_score_exact",
+    "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
+    "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
+    "gcr_profile_read", "gcr_counters_read",
+]
+
+_lib = None
+
+
+class GcrError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libgcr_b200.so; raises if it has not been built (python graph-cut-ransac_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GcrError("%s is missing: build it with `python graph-cut-ransac_b200/build.py` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64, f64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_double
+    sig = {
+        "gcr_ctx_create": (i32, [i32, C.POINTER(vp)]),
+        "gcr_ctx_destroy": (i32, [vp]),
+        "gcr_ctx_set_stream": (i32, [vp, vp]),
+        "gcr_sync": (i32, [vp]),
+        "gcr_last_error": (C.c_char_p, [vp]),
+        "gcr_version": (C.c_char_p, []),
+        "gcr_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)]),
+        "gcr_launch_count": (u64, [vp]),
+        "gcr_malloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
+        "gcr_free": (i32, [vp, vp]),
+        "gcr_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
+        "gcr_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+        "gcr_memset": (i32, [vp, vp, i32, C.c_size_t]),
+        "gcr_points_upload": (i32, [vp, vp, i32, i32, i32]),
+        "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
+        "gcr_points_get_norm": (i32, [vp, vp]),
+        "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
+        "gcr_sample_from_pool": (i32, [vp, vp, u32, i32, u64, i32, u64, u32, vp]),
+        "gcr_solve_minimal": (i32, [vp, i32, vp, i32, vp, vp]),
+        "gcr_max_models": (i32, [i32]),
+        "gcr_sample_size": (i32, [i32]),
+        "gcr_model_len": (i32, [i32]),
+        "gcr_score": (i32, [vp, i32, i32, vp, vp, i32, f64, i32, vp, vp]),
+        "gcr_score_exact": (i32, [vp, i32, i32, i32, vp, i32, f64, vp, vp, vp, vp]),
+        "gcr_score_host": (i32, [vp, i32, i32, vp, vp, i32, f64, i32, vp, vp]),
+        "gcr_score_exact_host": (i32, [vp, i32, i32, i32, vp, i32, f64, vp, vp, vp, vp]),
+        "gcr_argmax": (i32, [vp, vp, i32, u32, vp]),
+        "gcr_key_score": (C.c_float, [u64]),
+        "gcr_key_index": (u32, [u64]),
+        "gcr_refit": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp]),
+        "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
+        "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.gcr_set_band_factor.restype = i32
+    lib.gcr_set_band_factor.argtypes = [vp, f64]
+    lib.gcr_set_score_variant.restype = i32
+    lib.gcr_set_score_variant.argtypes = [vp, i32]
+    lib.gcr_profile_enable.restype = i32
+    lib.gcr_profile_enable.argtypes = [vp, i32]
+    lib.gcr_profile_read.restype = i32
+    lib.gcr_profile_read.argtypes = [vp, C.POINTER(f64), C.POINTER(u64), C.POINTER(u64)]
+    lib.gcr_counters_read.restype = i32
+    lib.gcr_counters_read.argtypes = [vp, C.POINTER(u64 * 4), i32]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One context per GPU per host thread (include/gcr/gcr.h)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.gcr_ctx_create(device, C.byref(h))
+        if st != 0 or not h.value:
+            raise GcrError("gcr_ctx_create(device=%d) failed with status %d: no CUDA device / driver "
+                           "(this library has no CPU fallback)" % (device, st))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.gcr_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st):
+        if st != 0:
+            raise GcrError("gcr status %d: %s" % (st, self.lib.gcr_last_error(self.h).decode()))
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.gcr_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def sync(self):
+        self.check(self.lib.gcr_sync(self.h))
+
+    def device_info(self):
+        sm, khz, l2 = C.c_int(), C.c_int(), C.c_size_t()
+        self.check(self.lib.gcr_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(l2)))
+        return dict(sm_count=sm.value, sm_clock_khz=khz.value, l2_bytes=l2.value)
+
+    def launch_count(self):
+        return int(self.lib.gcr_launch_count(self.h))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.gcr_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        self.check(self.lib.gcr_free(self.h, C.c_void_p(dptr)))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        d = self.malloc(arr.nbytes)
+        self.check(self.lib.gcr_memcpy_h2d(self.h, C.c_void_p(d), _ptr(arr), arr.nbytes))
+        return d
+
+    def to_host(self, dptr, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self.check(self.lib.gcr_memcpy_d2h(self.h, _ptr(out), C.c_void_p(dptr), out.nbytes))
+        return out
+
+    def set_band_factor(self, f):
+        self.check(self.lib.gcr_set_band_factor(self.h, f))
+
+    def set_score_variant(self, v):
+        self.check(self.lib.gcr_set_score_variant(self.h, v))
+
+    def profile_enable(self, on):
+        self.check(self.lib.gcr_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        ms, n, ev = C.c_double(), C.c_uint64(), C.c_uint64()
+        self.check(self.lib.gcr_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(ev)))
+        return ms.value, n.value, ev.value
+
+    def counters(self, reset=False):
+        out = (C.c_uint64 * 4)()
+        self.check(self.lib.gcr_counters_read(self.h, C.byref(out), 1 if reset else 0))
+        return list(out)
+
+    def round_device(self, problem, scoring, sampler, first_index, count, seed, thr, flags, index_base, d_keys, d_best):
+        """gcr_round with caller-owned device outputs (no host copies); returns the slot evaluations."""
+        ev = C.c_uint64()
+        self.check(self.lib.gcr_round(self.h, problem, scoring, sampler, first_index, count, seed, thr, flags,
+                                      index_base, C.c_void_p(d_keys), C.c_void_p(d_best), C.byref(ev)))
+        return ev.value
+
+    # ---- points ----
+    def points_upload(self, pts, n_pairs=1):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        cols = pts.shape[-1]
+        n = pts.size // cols // n_pairs
+        self._pts_keepalive = pts
+        self.check(self.lib.gcr_points_upload(self.h, _ptr(pts), n, cols, n_pairs))
+        self.n, self.cols, self.n_pairs = n, cols, n_pairs
+
+    def points_set_device(self, dptr, n, cols, n_pairs=1):
+        self.check(self.lib.gcr_points_set_device(self.h, C.c_void_p(dptr), n, cols, n_pairs))
+        self.n, self.cols, self.n_pairs = n, cols, n_pairs
+
+    def points_norm(self):
+        out = np.empty((self.n_pairs, 8))
+        self.check(self.lib.gcr_points_get_norm(self.h, _ptr(out)))
+        return out
+
+    # ---- K1 ----
+    def sample(self, sampler, m, first_index, count, seed):
+        d = self.malloc(self.n_pairs * count * m * 4)
+        try:
+            self.check(self.lib.gcr_sample(self.h, sampler, m, first_index, count, seed, C.c_void_p(d)))
+            return self.to_host(d, (self.n_pairs, count, m), np.uint32)
+        finally:
+            self.free(d)
+
+    def sample_from_pool(self, pool, m, first_index, count, seed, stream):
+        pool = np.ascontiguousarray(pool, dtype=np.uint32)
+        dp = self.to_device(pool)
+        d = self.malloc(count * m * 4)
+        try:
+            self.check(self.lib.gcr_sample_from_pool(self.h, C.c_void_p(dp), len(pool), m, first_index, count, seed,
+                                                     stream, C.c_void_p(d)))
+            return self.to_host(d, (count, m), np.uint32)
+        finally:
+            self.free(d)
+            self.free(dp)
+
+    # ---- K2 ----
+    def solve_minimal(self, problem, samples):
+        samples = np.ascontiguousarray(samples, dtype=np.uint32).reshape(self.n_pairs, -1, self.lib.gcr_sample_size(problem))
+        count = samples.shape[1]
+        mm, ml = self.lib.gcr_max_models(problem), self.lib.gcr_model_len(problem)
+        ds = self.to_device(samples)
+        dm = self.malloc(self.n_pairs * count * mm * ml * 8)
+        dv = self.malloc(self.n_pairs * count * mm)
+        try:
+            self.check(self.lib.gcr_solve_minimal(self.h, problem, C.c_void_p(ds), count, C.c_void_p(dm), C.c_void_p(dv)))
+            return (self.to_host(dm, (self.n_pairs, count, mm, ml), np.float64),
+                    self.to_host(dv, (self.n_pairs, count, mm), np.uint8))
+        finally:
+            for d in (ds, dm, dv):
+                self.free(d)
+
+    # ---- K3 ----
+    def score(self, problem, scoring, models, thr, valid=None, flags=0):
+        ml = self.lib.gcr_model_len(problem)
+        models = np.ascontiguousarray(models, dtype=np.float64).reshape(self.n_pairs, -1, ml)
+        k = models.shape[1]
+        scores = np.empty((self.n_pairs, k), dtype=np.float32)
+        inl = np.empty((self.n_pairs, k), dtype=np.uint32)
+        v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        self.check(self.lib.gcr_score_host(self.h, problem, scoring, _ptr(models), _ptr(v), k, thr, flags,
+                                           _ptr(scores), _ptr(inl)))
+        return scores, inl
+
+    def score_exact(self, problem, scoring, models, thr, pair=0, want_inliers=True, want_residuals=False):
+        ml = self.lib.gcr_model_len(problem)
+        models = np.ascontiguousarray(models, dtype=np.float64).reshape(-1, ml)
+        k = len(models)
+        scores = np.empty(k)
+        counts = np.empty(k, dtype=np.uint32)
+        idx = np.empty((k, self.n), dtype=np.uint32) if want_inliers else None
+        res = np.empty((k, self.n)) if want_residuals else None
+        self.check(self.lib.gcr_score_exact_host(self.h, problem, scoring, pair, _ptr(models), k, thr, _ptr(scores),
+                                                 _ptr(counts), _ptr(idx), _ptr(res)))
+        out = [scores, counts]
+        if want_inliers:
+            out.append([idx[j, : counts[j]].copy() for j in range(k)])
+        if want_residuals:
+            out.append(res)
+        return tuple(out)
+
+    # ---- K4 ----
+    def argmax(self, scores, index_base=0):
+        scores = np.ascontiguousarray(scores, dtype=np.float32).reshape(self.n_pairs, -1)
+        ds = self.to_device(scores)
+        dk = self.malloc(self.n_pairs * 8)
+        try:
+            self.check(self.lib.gcr_argmax(self.h, C.c_void_p(ds), scores.shape[1], index_base, C.c_void_p(dk)))
+            return self.to_host(dk, (self.n_pairs,), np.uint64)
+        finally:
+            self.free(ds)
+            self.free(dk)
+
+    def key_decode(self, key):
+        return float(self.lib.gcr_key_score(int(key))), int(self.lib.gcr_key_index(int(key)))
+
+    # ---- K6 ----
+    def refit(self, problem, index_sets, weights=None, weight_mode=WEIGHT_NONE, pair=0):
+        sizes = np.array([len(s) for s in index_sets], dtype=np.uint32)
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint32)
+        flat = np.concatenate([np.asarray(s, dtype=np.uint32) for s in index_sets]).astype(np.uint32)
+        count = len(index_sets)
+        d_flat, d_off, d_sz = self.to_device(flat), self.to_device(offsets), self.to_device(sizes)
+        d_w = None if weights is None else self.to_device(np.ascontiguousarray(weights, dtype=np.float64))
+        dm = self.malloc(count * 9 * 8)
+        dok = self.malloc(count)
+        try:
+            self.check(self.lib.gcr_refit(self.h, problem, pair, C.c_void_p(d_flat), C.c_void_p(d_off), C.c_void_p(d_sz),
+                                          count, C.c_void_p(d_w) if d_w else None, weight_mode, C.c_void_p(dm),
+                                          C.c_void_p(dok)))
+            return self.to_host(dm, (count, 3, 3), np.float64), self.to_host(dok, (count,), np.uint8)
+        finally:
+            for d in (d_flat, d_off, d_sz, dm, dok):
+                self.free(d)
+            if d_w:
+                self.free(d_w)
+
+    # ---- K7 ----
+    def grid_build(self, cell_sizes, cells_per_axis, pair=0):
+        cs = np.ascontiguousarray(cell_sizes, dtype=np.float64)
+        n = self.n
+        dk, ds, do = self.malloc(n * 8), self.malloc(n * 4), self.malloc((n + 1) * 4)
+        nc, nn = C.c_uint32(), C.c_uint64()
+        try:
+            self.check(self.lib.gcr_grid_build(self.h, pair, _ptr(cs), cells_per_axis, C.c_void_p(dk), C.c_void_p(ds),
+                                               C.c_void_p(do), C.byref(nc), C.byref(nn)))
+            return dict(keys=self.to_host(dk, (n,), np.uint64), sorted_idx=self.to_host(ds, (n,), np.uint32),
+                        cell_offsets=self.to_host(do, (n + 1,), np.uint32)[: nc.value + 1].copy(), n_cells=nc.value,
+                        neighbor_number=nn.value)
+        finally:
+            for d in (dk, ds, do):
+                self.free(d)
+
+    # ---- fused round ----
+    def round(self, problem, scoring, sampler, first_index, count, seed, thr, flags=0, index_base=0):
+        ml = self.lib.gcr_model_len(problem)
+        dk, dm = self.malloc(self.n_pairs * 8), self.malloc(self.n_pairs * ml * 8)
+        ev = C.c_uint64()
+        try:
+            self.check(self.lib.gcr_round(self.h, problem, scoring, sampler, first_index, count, seed, thr, flags,
+                                          index_base, C.c_void_p(dk), C.c_void_p(dm), C.byref(ev)))
+            return (self.to_host(dk, (self.n_pairs,), np.uint64), self.to_host(dm, (self.n_pairs, ml), np.float64),
+                    ev.value)
+        finally:
+            self.free(dk)
+            self.free(dm)

@@ -1,0 +1,173 @@
+/*
+ * include/gcr/gcr.h -- C ABI of the B200-native GC-RANSAC hot path (libgcr_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, one int status per call
+ * (0 = ok; gcr_last_error() explains anything else).  Each entry point names the reference function(s) of
+ * danini/graph-cut-ransac it replaces; paths are relative to src/pygcransac/include/ of the reference.
+ * INTEGRATION.md shows the adapter a reference maintainer adds on top (a ScoringFunction<> subclass and the
+ * find*_ drivers), and graph-cut-ransac_b200/host/ holds our C++ mirror of that template surface.
+ *
+ * Conventions
+ *  - "d_" pointers are device pointers on the context's GPU; "h_" pointers are host pointers.
+ *  - All work is enqueued on the context's stream; results in device buffers are valid after gcr_sync() (or any
+ *    stream-ordered consumer).  Functions with host outputs synchronise internally.
+ *  - Points are row-major FP64, `cols` = 4 (x1 y1 x2 y2: H, F, E) or 5 (u v X Y Z: PnP), `n_pairs` independent
+ *    problems of `n` points each stored back to back (n_pairs = 1 for a single problem).
+ *  - Models are row-major FP64: 9 doubles (3x3) for H/F/E, 12 (3x4) for PnP.
+ *  - There is no CPU fallback anywhere behind this ABI: without a CUDA device gcr_ctx_create() fails.
+ */
+#ifndef GCR_GCR_H_INCLUDED
+#define GCR_GCR_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcr_ctx gcr_ctx;
+typedef int gcr_status;
+
+enum { GCR_OK = 0, GCR_ERR_CUDA = 1, GCR_ERR_ARG = 2, GCR_ERR_STATE = 3, GCR_ERR_NOMEM = 4 };
+enum { GCR_H = 0, GCR_F = 1, GCR_E = 2, GCR_PNP = 3 };          /* problem */
+enum { GCR_MSAC = 0, GCR_MAGSAC = 1 };                          /* scoring function */
+enum { GCR_UNIFORM = 0, GCR_PROSAC = 1 };                       /* sampler */
+enum { GCR_WEIGHT_NONE = 0, GCR_WEIGHT_POSITIONAL = 1, GCR_WEIGHT_BY_POINT = 2 }; /* refit weight indexing */
+/* gcr_score flags */
+enum { GCR_SCORE_EXACT_COUNTS = 1 /* FP64 re-check of points within the FP32 error band of the threshold */ };
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+gcr_status gcr_ctx_create(int device, gcr_ctx **out);
+gcr_status gcr_ctx_destroy(gcr_ctx *ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream */
+gcr_status gcr_ctx_set_stream(gcr_ctx *ctx, void *cuda_stream);
+gcr_status gcr_sync(gcr_ctx *ctx);
+const char *gcr_last_error(const gcr_ctx *ctx);
+const char *gcr_version(void);
+/* number of SMs / SM clock (kHz) of the context's device -- used by bench.py for the FP32 roofline */
+gcr_status gcr_device_info(gcr_ctx *ctx, int *sm_count, int *sm_clock_khz, size_t *l2_bytes);
+/* how many kernels this context has launched so far (bench.py's gpu_launches claim) */
+uint64_t gcr_launch_count(const gcr_ctx *ctx);
+
+/* ---- tuning / instrumentation (no reference counterpart) --------------------------------------------------- */
+/* width of the FP32 error band (in units of FP32 epsilon, normalised coordinates) inside which
+ * GCR_SCORE_EXACT_COUNTS re-evaluates a point in FP64; default 16 */
+gcr_status gcr_set_band_factor(gcr_ctx *ctx, double factor);
+/* force a scoring-kernel variant: -1 auto, 0 scalar R=4, 1 scalar R=8, 2 packed-f32x2 R=4, 3 packed-f32x2 R=8 */
+gcr_status gcr_set_score_variant(gcr_ctx *ctx, int variant);
+/* CUDA-event timing of every K3 launch made through gcr_round / gcr_score (on the context's stream) */
+gcr_status gcr_profile_enable(gcr_ctx *ctx, int on);
+/* total K3 device time (ms), number of K3 launches and hypothesis x point evaluations they covered; resets */
+gcr_status gcr_profile_read(gcr_ctx *ctx, double *score_ms, uint64_t *score_launches, uint64_t *score_evals);
+/* device counters since the last reset: out[0] = valid models produced by gcr_solve_minimal */
+gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[4], int reset);
+
+/* device memory helpers so that C / ctypes callers need no other CUDA binding */
+gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out);
+gcr_status gcr_free(gcr_ctx *ctx, void *d_ptr);
+gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes);
+
+/* ---- points ----------------------------------------------------------------------------------------------- */
+/* Replaces the cv::Mat view the drivers build (py/gcransac_python.cpp:4274).  Copies host points to the device,
+ * keeps the FP64 copy and derives the centred / power-of-two-scaled FP32 copies the scoring kernels stream. */
+gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, int n, int cols, int n_pairs);
+/* Same, for points already resident in HBM (no copy; the caller keeps d_points alive). */
+gcr_status gcr_points_set_device(gcr_ctx *ctx, const double *d_points, int n, int cols, int n_pairs);
+/* per-pair normalisation the FP32 copy uses: out[8*pair + 0..4] = c1x c1y c2x c2y s (PnP: cu cv su cX cY cZ sX) */
+gcr_status gcr_points_get_norm(gcr_ctx *ctx, double *h_out /* 8 * n_pairs */);
+
+/* ---- K1 sampling ------------------------------------------------------------------------------------------ */
+/* UniformSampler::sample (samplers/uniform_sampler.h:81-99) + generateUniqueRandomSet
+ * (uniform_random_generator.h:90-103), ProsacSampler::sample (samplers/prosac_sampler.h:207-236), on a
+ * counter-based Philox4x32-10 stream: sample i of pair p is a pure function of (seed, first_index + i, p).
+ * d_out: [n_pairs][count][m] uint32.  For PROSAC first_index is the 1-based k of the first draw. */
+gcr_status gcr_sample(gcr_ctx *ctx, int sampler, int m, uint64_t first_index, int count, uint64_t seed,
+                      uint32_t *d_out);
+/* Uniform draws from explicit pools (GCRANSAC.h:842-846, the LO inner sampler): pool p has pool_sizes[p] entries
+ * at d_pool + pool_offsets[p]; out[i] = pool[draw_i].  stream distinguishes independent uses of one seed. */
+gcr_status gcr_sample_from_pool(gcr_ctx *ctx, const uint32_t *d_pool, uint32_t pool_size, int m,
+                                uint64_t first_index, int count, uint64_t seed, uint32_t stream, uint32_t *d_out);
+
+/* ---- K2 minimal solvers (+ fused sample / model validity tests) --------------------------------------------- */
+/* H: RobustHomographyEstimator::isValidSample (estimators/homography_estimator.h:346-381) +
+ *    HomographyFourPointSolver::estimateMinimalModel (estimators/solver_homography_four_point.h:109-190).
+ * F: FundamentalMatrixSevenPointSolver::estimateModel (estimators/solver_fundamental_matrix_seven_point.h:91-291)
+ *    + oriented epipolar constraint (estimators/fundamental_estimator.h:161-184, 737-800).
+ * E: EssentialMatrixFivePointNisterSolver::estimateModel (estimators/solver_essential_matrix_five_point_nister.h
+ *    :263-615) + orientation (estimators/essential_estimator.h:152-175).
+ * PnP: P3PSolver::estimateModel (estimators/solver_p3p.h:177-385).
+ * d_samples [n_pairs][count][m]; d_models [n_pairs][count][max_models][9|12] FP64; d_valid same shape, 1 = model
+ * present and passed the tests.  max_models = 1 (H), 3 (F), 10 (E), 4 (PnP). */
+gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count, double *d_models,
+                             uint8_t *d_valid);
+int gcr_max_models(int problem);
+int gcr_sample_size(int problem);
+int gcr_model_len(int problem);
+
+/* ---- K3 scoring ------------------------------------------------------------------------------------------- */
+/* MSACScoringFunction::getScore (scoring_function.h:137-233) / MAGSACScoringFunction::getScore (:246-348) with
+ * the estimator's squaredResidual (homography_estimator.h:181-199, fundamental_estimator.h:195-222,
+ * essential_estimator.h:186-213, perspective_n_point_estimator.h:148-184) for k models per pair at once.
+ * threshold is the user threshold (MSAC truncates at (1.5*threshold)^2 as GCRANSAC.h:253-255 does).
+ * d_valid may be NULL; models with valid == 0 get score -1 and 0 inliers.
+ * d_scores [n_pairs][k] float, d_inliers [n_pairs][k] uint32 (may be NULL). */
+gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid,
+                     int k, double threshold, int flags, float *d_scores, uint32_t *d_inliers);
+/* The same arithmetic in FP64, reference operation order, for a few models of pair `pair`: exact score, exact
+ * inlier count and (optionally) the ascending inlier index list -- the side output of getScore
+ * (scoring_function.h:166-167).  d_inlier_idx: [k][n] uint32 or NULL; d_residuals: [k][n] FP64 or NULL. */
+gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
+                           double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
+                           double *d_residuals);
+/* host-pointer convenience wrappers (H2D of models, D2H of results inside) */
+gcr_status gcr_score_host(gcr_ctx *ctx, int problem, int scoring, const double *h_models, const uint8_t *h_valid,
+                          int k, double threshold, int flags, float *h_scores, uint32_t *h_inliers);
+gcr_status gcr_score_exact_host(gcr_ctx *ctx, int problem, int scoring, int pair, const double *h_models, int k,
+                                double threshold, double *h_scores, uint32_t *h_counts, uint32_t *h_inlier_idx,
+                                double *h_residuals);
+
+/* ---- K4 selection ----------------------------------------------------------------------------------------- */
+/* Running-argmax of GCRANSAC.h:440-471 with Score::operator< (scoring_function.h:63-66): best score, ties to the
+ * LOWEST index.  d_keys [n_pairs] uint64 = (orderedFloatBits(score) << 32) | (0xFFFFFFFF - (index + index_base)):
+ * max over keys == best model, which is also what the hypothesis-sharded mode all-reduces (ncclMax). */
+gcr_status gcr_argmax(gcr_ctx *ctx, const float *d_scores, int k, uint32_t index_base, uint64_t *d_keys);
+/* decode helpers (pure functions, usable on the host) */
+float gcr_key_score(uint64_t key);
+uint32_t gcr_key_index(uint64_t key);
+
+/* ---- K6 non-minimal refits -------------------------------------------------------------------------------- */
+/* H: RobustHomographyEstimator::estimateModelNonminimal (homography_estimator.h:136-173) +
+ *    HomographyFourPointSolver::estimateNonMinimalModel (solver_homography_four_point.h:192-264).
+ * F: FundamentalMatrixEstimator::estimateModelNonminimal (fundamental_estimator.h:574-618) +
+ *    FundamentalMatrixEightPointSolver (solver_fundamental_matrix_eight_point.h:93-182).
+ * `count` index sets of pair `pair`; set j has set_sizes[j] indices at d_index_sets + set_offsets[j].
+ * d_weights: per-point weights or NULL; weight_mode: GCR_WEIGHT_POSITIONAL reproduces the reference's positional
+ * read, GCR_WEIGHT_BY_POINT reads weights[index].  d_models [count][9], d_ok [count]. */
+gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
+                     const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode,
+                     double *d_models, uint8_t *d_ok);
+
+/* ---- K7 grid neighbourhood -------------------------------------------------------------------------------- */
+/* GridNeighborhoodGraph<4>::initialize (neighborhood/grid_neighborhood_graph.h:229-292), pair `pair`.
+ * d_keys [n] uint64 cell key per point (GridCell index, :70-82); d_sorted_idx [n] point indices grouped by
+ * ascending key, ascending index inside a cell; d_cell_offsets [n+1] starts of the filled cells in d_sorted_idx
+ * (terminated by n); h_n_cells = filledCellNumber(); h_neighbor_number = sum n(n-1)/2 (:283-284). */
+gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell_sizes[4], uint64_t cells_per_axis,
+                          uint64_t *d_keys, uint32_t *d_sorted_idx, uint32_t *d_cell_offsets, uint32_t *h_n_cells,
+                          uint64_t *h_neighbor_number);
+
+/* ---- fused fixed-K round (the benchmarked step) ------------------------------------------------------------ */
+/* One pass of the hot path over every pair on the context: K1 sample `count` minimal samples -> K2 solve -> K3
+ * score (all models) -> K4 argmax.  Outputs per pair: packed key (see gcr_argmax; index = sample * max_models +
+ * model slot, offset by index_base) and the winning model (FP64).  evals_out = hypothesis x point evaluations done. */
+gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
+                     uint64_t seed, double threshold, int flags, uint32_t index_base, uint64_t *d_keys,
+                     double *d_best_models, uint64_t *evals_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+/*
+ * oracle/gcr_oracle.h -- CPU restatement of the reference's hypothesise-and-verify hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it, and only as the checker / baseline.
+ *
+ * Every function restates, in plain FP64 C++ with no Eigen/OpenCV, one function of danini/graph-cut-ransac
+ * (paths relative to /root/reference/src/pygcransac/include/), cited next to each declaration.  Arithmetic is
+ * written in the reference's operation order and compiled with -ffp-contract=off so that integer results are
+ * bit-exact and FP64 results differ from the reference only where the reference calls an Eigen decomposition
+ * (Eigen is absent from the reference tree and from this image; those solvers follow Eigen 3.4 semantics and are
+ * cross-checked against numpy/scipy -- see DESIGN.md "Oracle pinning").
+ *
+ * Pinning status: the reference ships no operator-level golden vectors.  The functions marked
+ * [pinned:_ref] are checked bit-for-bit (or to 1e-15) against the reference's own headers compiled verbatim into
+ * oracle/_ref/libgcr_ref.so (oracle/build_ref.sh); fixtures generated from that library are committed under
+ * tests/golden/.  Functions marked [unpinned] restate Eigen-dependent code that cannot be compiled here.
+ */
+#ifndef GCR_ORACLE_H
+#define GCR_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* problem ids (shared with include/gcr/gcr.h) */
+enum { GCRO_H = 0, GCRO_F = 1, GCRO_E = 2, GCRO_PNP = 3 };
+/* scoring ids */
+enum { GCRO_MSAC = 0, GCRO_MAGSAC = 1 };
+
+/* ---- residuals -------------------------------------------------------------------------------------------- */
+/* estimators/homography_estimator.h:181-199  [pinned:_ref via scoring]                                         */
+double gcro_sqres_h(const double *pt4, const double *H9);
+/* estimators/fundamental_estimator.h:195-222 == estimators/essential_estimator.h:186-213                       */
+double gcro_sqres_sampson(const double *pt4, const double *F9);
+/* estimators/fundamental_estimator.h:225-253 (symmetric epipolar)                                              */
+double gcro_sqres_symepi(const double *pt4, const double *F9);
+/* estimators/perspective_n_point_estimator.h:148-184 (pt = u v X Y Z, model 3x4 row-major)                     */
+double gcro_sqres_pnp(const double *pt5, const double *P12);
+/* dispatch: problem -> squared residual; cols = 4 (H,F,E) or 5 (PNP)                                           */
+double gcro_sqres(int problem, const double *pt, const double *model);
+int gcro_model_len(int problem); /* 9 or 12 */
+int gcro_point_cols(int problem); /* 4 or 5 */
+
+/* ---- scoring ---------------------------------------------------------------------------------------------- */
+/* Gamma(1.5, k/1000): value of gamma_values.cpp:2012 stored_gamma_values[k], k in [0, 38682]  [pinned:_ref]    */
+double gcro_gamma_lut(int k);
+/* scoring_function.h:137-233 MSACScoringFunction::getScore with squared_truncated_threshold = (1.5*thr)^2 as
+ * GCRANSAC.h:253-255 sets it.  Writes score (0 if no inliers), inlier count, and (if inl_idx) ascending indices. */
+void gcro_score_msac(int problem, const double *pts, int n, const double *model, double thr,
+                     double *score, uint64_t *n_inl, uint32_t *inl_idx);
+/* scoring_function.h:246-348 MAGSACScoringFunction::getScore (sigma_max = thr, inlier iff residual <= thr)      */
+void gcro_score_magsac(int problem, const double *pts, int n, const double *model, double thr,
+                       double *score, uint64_t *n_inl, uint32_t *inl_idx);
+/* K models at once (models: k x model_len) */
+void gcro_score_batch(int problem, int scoring, const double *pts, int n, const double *models, int k,
+                      double thr, double *scores, uint64_t *n_inl);
+/* per-point squared residuals of one model */
+void gcro_residuals(int problem, const double *pts, int n, const double *model, double *out);
+
+/* ---- samplers (a2, a3) ------------------------------------------------------------------------------------ */
+/* Philox4x32-10 block: ctr[4], key[2] -> out[4] (the counter-based generator the product's K1 kernel uses)     */
+void gcro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* uniform_sampler.h:81-99 + uniform_random_generator.h:90-103 semantics (m distinct uniform indices in
+ * [0, n-1] by draw-and-reject, kept in draw order) on the counter-based stream (seed, sample_index, stream).   */
+void gcro_sample_uniform(uint64_t seed, uint64_t sample_index, uint32_t stream, uint32_t n, int m, uint32_t *out);
+/* prosac_sampler.h:129-174 growth function T'_n (n entries)  [pinned:_ref]                                     */
+void gcro_prosac_growth(uint32_t n, int m, uint64_t convergence_iters, uint64_t *growth);
+/* prosac_sampler.h:65-88,207-236: subset size n_k the k-th (1-based) PROSAC draw uses  [pinned:_ref]           */
+uint32_t gcro_prosac_subset_size(const uint64_t *growth, uint32_t n, int m, uint64_t k);
+/* k-th PROSAC sample (1-based k) on the counter-based stream                                                   */
+void gcro_sample_prosac(uint64_t seed, uint64_t k, uint32_t n, int m, const uint64_t *growth,
+                        uint64_t convergence_iters, uint32_t *out);
+
+/* ---- homography (a4, a5, a7, a21) ------------------------------------------------------------------------- */
+/* homography_estimator.h:346-381 */
+int gcro_h_valid_sample(const double *pts, const uint32_t *sample);
+/* solver_homography_four_point.h:109-190 + math_utils.h:45-87; returns #models (0/1). sample==NULL -> rows 0..3 */
+int gcro_solve_h4(const double *pts, int cols, const uint32_t *sample, double *H9);
+/* homography_estimator.h:326-342 */
+int gcro_h_valid_model(const double *H9);
+/* homography_estimator.h:213-310: Hartley normalisation of the selected points; T1,T2 3x3 row-major */
+void gcro_normalize_points(const double *pts, int cols, const uint32_t *sample, int n, double *norm_pts,
+                           double *T1, double *T2);
+/* homography_estimator.h:136-173 + solver_homography_four_point.h:192-264; weights may be NULL.
+ * Weight indexing follows the reference literally: weights[i] with i the POSITION in the sample. */
+int gcro_refit_h(const double *pts, const uint32_t *sample, int n, const double *weights, double *H9);
+
+/* ---- fundamental (a8, a9, a11, a22) ----------------------------------------------------------------------- */
+/* solver_fundamental_matrix_seven_point.h:91-291; returns #models (0..3), F row-major 9 each  [unpinned]       */
+int gcro_solve_f7(const double *pts, const uint32_t *sample, double *F27);
+/* fundamental_estimator.h:737-800 oriented epipolar constraint on the sample (1 valid / 0 not) */
+int gcro_f_orientation_valid(const double *F9, const double *pts, const uint32_t *sample, int m);
+/* fundamental_estimator.h:161-184 estimateModel = 7pt + orientation filter */
+int gcro_estimate_f7(const double *pts, const uint32_t *sample, double *F27);
+/* fundamental_estimator.h:574-618 + :637-734 + solver_fundamental_matrix_eight_point.h:93-182  [unpinned]      */
+int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9);
+/* fundamental_estimator.h:287-338 symmetric-epipolar ratio test part of isValidModel (no DEGENSAC)              */
+int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t *inl, int n_inl, int m,
+                             double truncated_thr, double min_ratio);
+
+/* ---- essential (a12, a13, a14) ---------------------------------------------------------------------------- */
+/* solver_essential_matrix_five_point_nister.h:263-615; returns #models (0..10)  [unpinned] */
+int gcro_solve_e5_nister(const double *pts, const uint32_t *sample, double *E90);
+/* solver_essential_matrix_five_point_stewenius.h:114-231 (n >= 5, optional weights[sample[i]])  [unpinned]      */
+int gcro_solve_e5_stewenius(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
+/* essential_estimator.h:152-175 estimateModel = nister + orientation filter (:338-401) */
+int gcro_estimate_e5(const double *pts, const uint32_t *sample, double *E90);
+/* utils.h:65-110 normalizeCorrespondences: K^-1 on both images (K row-major 3x3) */
+void gcro_normalize_correspondences(const double *pts, int n, const double *K1, const double *K2, double *out);
+
+/* ---- absolute pose (a15) ---------------------------------------------------------------------------------- */
+/* solver_p3p.h:177-385 Lambda-Twist; returns #models (0..4), 3x4 row-major each  [unpinned] */
+int gcro_solve_p3p(const double *pts5, const uint32_t *sample, double *P48);
+
+/* ---- neighbourhood (a24) ---------------------------------------------------------------------------------- */
+/* grid_neighborhood_graph.h:229-292: keys[i] = cell key of point i; returns neighbor_number; *n_cells = filled
+ * cells.  sorted_idx (n) = point indices grouped by ascending key, ascending index inside a cell;
+ * cell_offsets (n+1 capacity) = start of each filled cell in sorted_idx, terminated by n.  [pinned:_ref]       */
+uint64_t gcro_grid_build(const double *pts, int n, int dims, const double *cell_sizes, uint64_t cells_per_axis,
+                         uint64_t *keys, uint32_t *sorted_idx, uint32_t *cell_offsets, uint32_t *n_cells);
+
+/* ---- fixed-K round (a1 inner loop, a19) -------------------------------------------------------------------- */
+/* GCRANSAC.h:297-471 without adaptive stop / LO; the CPU "port" arm bench.py times when oracle/_ref is absent */
+void gcro_round(int problem, int scoring, const double *pts, int n, uint64_t seed, uint64_t first, int count,
+                double thr, double *best_score, uint64_t *best_index, uint64_t *models_scored, double *best_model);
+
+/* ---- termination (a1) ------------------------------------------------------------------------------------- */
+/* GCRANSAC.h:158-172 */
+uint64_t gcro_iteration_number(uint64_t inliers, uint64_t n, int m, double log_probability);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

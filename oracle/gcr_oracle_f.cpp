@@ -1,0 +1,349 @@
+// oracle/gcr_oracle_f.cpp -- TEST INFRASTRUCTURE ONLY (see gcr_oracle.h).
+// Fundamental-matrix path: 7-point minimal solver, oriented epipolar constraint, normalised 8-point refit and the
+// symmetric-epipolar validity test, restated from the reference (file:line beside each function).
+// [unpinned]: the reference versions call Eigen (FullPivLU::kernel, PolynomialSolver, FullPivHouseholderQR), which is
+// neither vendored in /root/reference nor installed here; the restatement follows Eigen 3.4's documented semantics
+//  and is cross-checked against numpy in tests/test_oracle_solvers.py.
+#include "gcr_oracle.h"
+#include "linalg.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace
+{
+	// monic cubic x^3 + a x^2 + b x + c: real roots in ascending order by bracketing at the derivative's roots and a
+	// bisection-safeguarded Newton iteration (only + - * / sqrt: reproducible bit-for-bit on any IEEE machine).
+	struct Cubic
+	{
+		double a, b, c;
+		double p(double x) const { return ((x + a) * x + b) * x + c; }
+		double dp(double x) const { return (3.0 * x + 2.0 * a) * x + b; }
+		double bracket(double lo, double hi) const
+		{
+			const double fl = p(lo), fh = p(hi);
+			if (fl == 0.0) return lo;
+			if (fh == 0.0) return hi;
+			double xl, xh;
+			if (fl < 0.0) { xl = lo; xh = hi; }
+			else { xl = hi; xh = lo; }
+			double rts = 0.5 * (lo + hi);
+			double dxold = std::fabs(hi - lo), dx = dxold;
+			double f = p(rts), df = dp(rts);
+			for (int it = 0; it < 200; ++it)
+			{
+				if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (std::fabs(2.0 * f) > std::fabs(dxold * df)))
+				{
+					dxold = dx;
+					dx = 0.5 * (xh - xl);
+					rts = xl + dx;
+					if (xl == rts) return rts;
+				}
+				else
+				{
+					dxold = dx;
+					dx = f / df;
+					const double temp = rts;
+					rts -= dx;
+					if (temp == rts) return rts;
+				}
+				if (std::fabs(dx) <= 4.440892098500626e-16 * std::fabs(rts)) return rts;
+				f = p(rts);
+				df = dp(rts);
+				if (f < 0.0) xl = rts;
+				else xh = rts;
+			}
+			return rts;
+		}
+	};
+
+	int cubic_roots(double c0, double c1, double c2, double c3, double *roots)
+	{
+		Cubic q;
+		q.a = c2 / c3;
+		q.b = c1 / c3;
+		q.c = c0 / c3;
+		const double R = 1.0 + std::fmax(std::fabs(q.a), std::fmax(std::fabs(q.b), std::fabs(q.c)));
+		const double disc = q.a * q.a - 3.0 * q.b;
+		int n = 0;
+		if (!(disc > 0.0))
+		{
+			roots[n++] = q.bracket(-R, R);
+			return n;
+		}
+		const double sq = std::sqrt(disc);
+		const double x1 = (-q.a - sq) / 3.0, x2 = (-q.a + sq) / 3.0;
+		const double p1 = q.p(x1), p2 = q.p(x2);
+		if (p1 >= 0.0)
+			roots[n++] = (p1 == 0.0) ? x1 : q.bracket(-R, x1);
+		if (p1 > 0.0 && p2 < 0.0)
+			roots[n++] = q.bracket(x1, x2);
+		if (p2 <= 0.0)
+			roots[n++] = (p2 == 0.0) ? x2 : q.bracket(x2, R);
+		return n;
+	}
+}
+
+extern "C" {
+
+// solver_fundamental_matrix_seven_point.h:91-291, minimal branch (:159-170), weights_ == nullptr
+int gcro_solve_f7(const double *pts, const uint32_t *sample, double *F27)
+{
+	const double eps = std::numeric_limits<double>::epsilon();
+	double A[7 * 9];
+	for (int i = 0; i < 7; ++i)
+	{
+		const double *p = pts + 4 * (size_t)sample[i];
+		const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+		double *r = A + 9 * i;
+		r[0] = x1 * x0; r[1] = x1 * y0; r[2] = x1; r[3] = y1 * x0; r[4] = y1 * y0; r[5] = y1; r[6] = x0; r[7] = y0; r[8] = 1;
+	}
+	double ker[9 * 2];
+	const int dim = gcro::fullpiv_lu_kernel(A, 7, 9, ker, 2);
+	if (dim != 2) // :162-163
+		return 0;
+	double f1[9], f2[9];
+	for (int j = 0; j < 9; ++j)
+	{
+		f1[j] = ker[2 * j + 0];
+		f2[j] = ker[2 * j + 1];
+	}
+	for (int j = 0; j < 9; ++j) // :190
+		f1[j] -= f2[j];
+
+	double c[4], t0, t1, t2;
+	t0 = f2[4] * f2[8] - f2[5] * f2[7];
+	t1 = f2[3] * f2[8] - f2[5] * f2[6];
+	t2 = f2[3] * f2[7] - f2[4] * f2[6];
+	c[0] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+	c[1] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 -
+	       f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+	       f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+	       f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+	       f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) -
+	       f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+	       f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+	t0 = f1[4] * f1[8] - f1[5] * f1[7];
+	t1 = f1[3] * f1[8] - f1[5] * f1[6];
+	t2 = f1[3] * f1[7] - f1[4] * f1[6];
+	c[2] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 -
+	       f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+	       f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+	       f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+	       f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) -
+	       f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+	       f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+	c[3] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+
+	if (std::fabs(c[0] + c[1] + c[2] + c[3]) < 1e-9 || std::fabs(c[0]) < eps || std::fabs(c[1]) < eps ||
+	    std::fabs(c[2]) < eps || std::fabs(c[3]) < eps) // :246-251
+		return 0;
+
+	// :254-260 Eigen::PolynomialSolver<double,3>::realRoots -- restated as a direct real-root finder, ascending order
+	double roots[3];
+	const int nr = cubic_roots(c[0], c[1], c[2], c[3], roots);
+	int nm = 0;
+	for (int r = 0; r < nr; ++r)
+	{
+		double lambda = roots[r], mu = 1.;
+		const double s = f1[8] * roots[r] + f2[8];
+		if (std::fabs(s) > eps) // :273
+		{
+			mu = 1.0f / s;
+			lambda *= mu;
+			double *o = F27 + 9 * nm;
+			for (int j = 0; j < 8; ++j)
+				o[j] = f1[j] * lambda + f2[j] * mu;
+			o[8] = 1.0;
+			++nm;
+		}
+	}
+	return nm;
+}
+
+// fundamental_estimator.h:737-800 (getEpipole, getOrientationSignum, isOrientationValid)
+int gcro_f_orientation_valid(const double *F, const double *pts, const uint32_t *sample, int m)
+{
+	const double epsilon = 1.9984e-15;
+	double e[3];
+	gcro::cross3(F + 0, F + 6, e); // row(0).cross(row(2))
+	bool big = false;
+	for (int i = 0; i < 3; i++)
+		if ((e[i] > epsilon) || (e[i] < -epsilon))
+			big = true;
+	if (!big)
+		gcro::cross3(F + 3, F + 6, e);
+	double signum2 = 0.0;
+	for (int i = 0; i < m; ++i)
+	{
+		const double *p = pts + 4 * (size_t)(sample ? sample[i] : (uint32_t)i);
+		const double s1 = F[0] * p[2] + F[3] * p[3] + F[6], s2 = e[1] - e[2] * p[1];
+		const double signum1 = s1 * s2;
+		if (i == 0)
+			signum2 = signum1;
+		else if (signum2 * signum1 < 0)
+			return 0;
+	}
+	return 1;
+}
+
+// fundamental_estimator.h:161-184
+int gcro_estimate_f7(const double *pts, const uint32_t *sample, double *F27)
+{
+	double all[27];
+	const int n = gcro_solve_f7(pts, sample, all);
+	int kept = 0;
+	for (int i = 0; i < n; ++i)
+		if (gcro_f_orientation_valid(all + 9 * i, pts, sample, 7))
+		{
+			std::memcpy(F27 + 9 * kept, all + 9 * i, 9 * sizeof(double));
+			++kept;
+		}
+	return kept;
+}
+
+// FullPivHouseholderQR(M).matrixQ().rightCols<1>() for a square n x n matrix M (solver_fundamental_matrix_eight_point.h
+// :170-174).  Eigen: at step k the largest |entry| of the remaining corner is brought to (k,k) by a row and a column
+// transposition, then a Householder reflection zeroes the column below it; matrixQ() = product over k of
+// (row transposition_k * H_k).  Its last column is Q e_{n-1}.
+static void fullpiv_householder_q_lastcol(const double *M_in, int n, double *q)
+{
+	std::vector<double> M(M_in, M_in + (size_t)n * n);
+	std::vector<int> rowswap(n);
+	std::vector<std::vector<double>> vs(n); // essential parts
+	std::vector<double> taus(n, 0.0);
+	int steps = n;
+	for (int k = 0; k < n; ++k)
+	{
+		int pr = k, pc = k;
+		double biggest = 0.0;
+		for (int j = k; j < n; ++j)
+			for (int i = k; i < n; ++i)
+			{
+				const double a = std::fabs(M[(size_t)i * n + j]);
+				if (a > biggest) { biggest = a; pr = i; pc = j; }
+			}
+		if (biggest == 0.0) // Eigen: corner exactly zero -> remaining reflections are identity
+		{
+			steps = k;
+			break;
+		}
+		rowswap[k] = pr;
+		if (pr != k)
+			for (int j = 0; j < n; ++j) std::swap(M[(size_t)k * n + j], M[(size_t)pr * n + j]);
+		if (pc != k)
+			for (int i = 0; i < n; ++i) std::swap(M[(size_t)i * n + k], M[(size_t)i * n + pc]);
+		// makeHouseholderInPlace on column k, rows k..n-1: H = I - tau v v^T, v = [1; essential]
+		double tail2 = 0.0;
+		for (int i = k + 1; i < n; ++i) tail2 += M[(size_t)i * n + k] * M[(size_t)i * n + k];
+		const double c0 = M[(size_t)k * n + k];
+		std::vector<double> ess(n - k - 1, 0.0);
+		double tau = 0.0, beta = c0;
+		if (tail2 > std::numeric_limits<double>::min())
+		{
+			beta = std::sqrt(c0 * c0 + tail2);
+			if (c0 >= 0) beta = -beta;
+			for (int i = k + 1; i < n; ++i) ess[i - k - 1] = M[(size_t)i * n + k] / (c0 - beta);
+			tau = (beta - c0) / beta;
+		}
+		vs[k] = ess;
+		taus[k] = tau;
+		// apply H to the remaining columns (k+1..n-1) from the left
+		for (int j = k + 1; j < n; ++j)
+		{
+			double dot = M[(size_t)k * n + j];
+			for (int i = k + 1; i < n; ++i) dot += ess[i - k - 1] * M[(size_t)i * n + j];
+			dot *= tau;
+			M[(size_t)k * n + j] -= dot;
+			for (int i = k + 1; i < n; ++i) M[(size_t)i * n + j] -= dot * ess[i - k - 1];
+		}
+		M[(size_t)k * n + k] = beta;
+		for (int i = k + 1; i < n; ++i) M[(size_t)i * n + k] = 0.0;
+	}
+	// q = Q e_{n-1} with Q = T_0 H_0 T_1 H_1 ... : apply in reverse order
+	for (int i = 0; i < n; ++i) q[i] = 0.0;
+	q[n - 1] = 1.0;
+	for (int k = steps - 1; k >= 0; --k)
+	{
+		// H_k
+		double dot = q[k];
+		for (int i = k + 1; i < n; ++i) dot += vs[k][i - k - 1] * q[i];
+		dot *= taus[k];
+		q[k] -= dot;
+		for (int i = k + 1; i < n; ++i) q[i] -= dot * vs[k][i - k - 1];
+		// T_k
+		if (rowswap[k] != k) std::swap(q[k], q[rowswap[k]]);
+	}
+}
+
+// fundamental_estimator.h:574-618 (+ normalizePoints :637-734) + solver_fundamental_matrix_eight_point.h:93-182.
+// The 8-point solver receives the normalised copy with sample_ == nullptr, so it reads weights_[i] by POSITION (:113-118).
+int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9)
+{
+	if (n < 8)
+		return 0;
+	std::vector<double> np((size_t)n * 4);
+	double T1[9], T2[9];
+	gcro_normalize_points(pts, 4, sample, n, np.data(), T1, T2);
+	std::vector<double> A((size_t)n * 9);
+	for (int i = 0; i < n; ++i)
+	{
+		const double *p = np.data() + 4 * (size_t)i;
+		const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+		double *r = A.data() + 9 * (size_t)i;
+		if (!weights)
+		{
+			r[0] = x1 * x0; r[1] = x1 * y0; r[2] = x1; r[3] = y1 * x0; r[4] = y1 * y0; r[5] = y1; r[6] = x0; r[7] = y0; r[8] = 1;
+		}
+		else
+		{
+			const double weight = weights[i];
+			const double wx0 = weight * x0, wy0 = weight * y0, wx1 = weight * x1, wy1 = weight * y1;
+			r[0] = wx1 * x0; r[1] = wx1 * y0; r[2] = wx1; r[3] = wy1 * x0; r[4] = wy1 * y0; r[5] = wy1; r[6] = wx0; r[7] = wy0; r[8] = weight;
+		}
+	}
+	// coefficients.transpose() * coefficients (:171)
+	double AtA[81];
+	for (int a = 0; a < 9; ++a)
+		for (int b = 0; b < 9; ++b)
+		{
+			double s = 0.0;
+			for (int i = 0; i < n; ++i)
+				s += A[9 * (size_t)i + a] * A[9 * (size_t)i + b];
+			AtA[9 * a + b] = s;
+		}
+	double f[9];
+	fullpiv_householder_q_lastcol(AtA, 9, f);
+	// fundamental_estimator.h:606-616: F = T2^T * Fn * T1, Frobenius-normalise, sign so that F(2,2) >= 0
+	double T2t[9], tmp[9], F[9];
+	gcro::transpose3(T2, T2t);
+	gcro::mul3(T2t, f, tmp);
+	gcro::mul3(tmp, T1, F);
+	double nrm = 0.0;
+	for (int i = 0; i < 9; ++i) nrm += F[i] * F[i];
+	nrm = std::sqrt(nrm);
+	for (int i = 0; i < 9; ++i) F[i] /= nrm;
+	if (F[8] < 0)
+		for (int i = 0; i < 9; ++i) F[i] = -F[i];
+	std::memcpy(F9, F, sizeof(F));
+	return 1;
+}
+
+// fundamental_estimator.h:287-318 (and essential_estimator.h:279-305): the symmetric-epipolar part of isValidModel
+int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t *inl, int n_inl, int m,
+                             double truncated_thr, double min_ratio)
+{
+	size_t inlier_number = 0;
+	const double a = (double)m, b = n_inl * min_ratio;
+	const double minimum_inlier_number = a < b ? b : a; // MAX(sample_size, inliers_.size() * ratio)
+	const double squared_threshold = truncated_thr * truncated_thr;
+	for (int i = 0; i < n_inl; ++i)
+		if (gcro_sqres_symepi(pts + 4 * (size_t)inl[i], F9) < squared_threshold)
+			if (++inlier_number >= minimum_inlier_number)
+				return 1;
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,305 @@
+"""ctypes bindings for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+`Oracle()` loads oracle/libgcr_oracle.so -- the self-contained FP64 restatement of the reference's hot path
+(oracle/gcr_oracle.h cites the reference file:line each function follows).  `Ref()` loads
+oracle/_ref/libgcr_ref.so -- the reference's own headers compiled verbatim through the container shims (only
+buildable where /root/reference exists; the prebuilt .so travels to the GPU box).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+H, F, E, PNP = 0, 1, 2, 3
+MSAC, MAGSAC = 0, 1
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force=False):
+    so = os.path.join(HERE, "libgcr_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cpp", ".h")) and not f.startswith("ref_")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["bash", os.path.join(HERE, "build_oracle.sh")], stdout=subprocess.DEVNULL)
+    return so
+
+
+def build_ref(force=False):
+    """Build oracle/_ref/libgcr_ref.so when the reference tree is present; returns the path or None."""
+    so = os.path.join(HERE, "_ref", "libgcr_ref.so")
+    ref_dir = os.environ.get("GCR_REFERENCE_DIR", "/root/reference")
+    if os.path.isdir(ref_dir):
+        srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cpp", ".h"))]
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
+def _as_pts(pts):
+    return np.ascontiguousarray(pts, dtype=np.float64)
+
+
+def _round(fn, problem, scoring, pts, seed, first, count, thr):
+    pts = _as_pts(pts)
+    s, idx, n = C.c_double(), C.c_uint64(), C.c_uint64()
+    model = np.zeros(12 if problem == PNP else 9)
+    fn(problem, scoring, pts, len(pts), seed, first, count, thr, C.byref(s), C.byref(idx), C.byref(n), model)
+    return s.value, idx.value, n.value, model
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = lib = C.CDLL(build_oracle())
+        lib.gcro_sqres.restype = C.c_double
+        lib.gcro_sqres.argtypes = [C.c_int, _dp, _dp]
+        lib.gcro_gamma_lut.restype = C.c_double
+        lib.gcro_gamma_lut.argtypes = [C.c_int]
+        for name in ("gcro_score_msac", "gcro_score_magsac"):
+            fn = getattr(lib, name)
+            fn.restype = None
+            fn.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_void_p]
+        lib.gcro_score_batch.restype = None
+        lib.gcro_score_batch.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, _dp, _u64p]
+        lib.gcro_residuals.restype = None
+        lib.gcro_residuals.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp]
+        lib.gcro_philox4x32.restype = None
+        lib.gcro_philox4x32.argtypes = [_u32p, _u32p, _u32p]
+        lib.gcro_sample_uniform.restype = None
+        lib.gcro_sample_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _u32p]
+        lib.gcro_prosac_growth.restype = None
+        lib.gcro_prosac_growth.argtypes = [C.c_uint32, C.c_int, C.c_uint64, _u64p]
+        lib.gcro_prosac_subset_size.restype = C.c_uint32
+        lib.gcro_prosac_subset_size.argtypes = [_u64p, C.c_uint32, C.c_int, C.c_uint64]
+        lib.gcro_sample_prosac.restype = None
+        lib.gcro_sample_prosac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _u64p, C.c_uint64, _u32p]
+        lib.gcro_h_valid_sample.restype = C.c_int
+        lib.gcro_h_valid_sample.argtypes = [_dp, _u32p]
+        lib.gcro_solve_h4.restype = C.c_int
+        lib.gcro_solve_h4.argtypes = [_dp, C.c_int, C.c_void_p, _dp]
+        lib.gcro_h_valid_model.restype = C.c_int
+        lib.gcro_h_valid_model.argtypes = [_dp]
+        lib.gcro_normalize_points.restype = None
+        lib.gcro_normalize_points.argtypes = [_dp, C.c_int, _u32p, C.c_int, _dp, _dp, _dp]
+        for name in ("gcro_refit_h", "gcro_refit_f8"):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        for name in ("gcro_solve_f7", "gcro_estimate_f7", "gcro_solve_e5_nister", "gcro_estimate_e5", "gcro_solve_p3p"):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [_dp, _u32p, _dp]
+        lib.gcro_solve_e5_stewenius.restype = C.c_int
+        lib.gcro_solve_e5_stewenius.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        lib.gcro_f_orientation_valid.restype = C.c_int
+        lib.gcro_f_orientation_valid.argtypes = [_dp, _dp, _u32p, C.c_int]
+        lib.gcro_f_valid_model_ratio.restype = C.c_int
+        lib.gcro_f_valid_model_ratio.argtypes = [_dp, _dp, _u32p, C.c_int, C.c_int, C.c_double, C.c_double]
+        lib.gcro_normalize_correspondences.restype = None
+        lib.gcro_normalize_correspondences.argtypes = [_dp, C.c_int, _dp, _dp, _dp]
+        lib.gcro_grid_build.restype = C.c_uint64
+        lib.gcro_grid_build.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_uint64, _u64p, _u32p, _u32p, C.POINTER(C.c_uint32)]
+        lib.gcro_iteration_number.restype = C.c_uint64
+        lib.gcro_iteration_number.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_double]
+        lib.gcro_round.restype = None
+        lib.gcro_round.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _dp]
+
+    def round(self, problem, scoring, pts, seed, first, count, thr):
+        """Fixed-K pass (sample -> solve -> score -> best); returns (score, index, models_scored, model)."""
+        return _round(self.lib.gcro_round, problem, scoring, pts, seed, first, count, thr)
+
+    # ---- scoring ----
+    def sqres(self, problem, pt, model):
+        return self.lib.gcro_sqres(problem, _as_pts(pt), _as_pts(model).ravel())
+
+    def residuals(self, problem, pts, model):
+        pts = _as_pts(pts)
+        out = np.empty(len(pts))
+        self.lib.gcro_residuals(problem, pts, len(pts), _as_pts(model).ravel(), out)
+        return out
+
+    def score(self, problem, scoring, pts, model, thr, want_inliers=False):
+        pts = _as_pts(pts)
+        s, n = C.c_double(), C.c_uint64()
+        idx = np.empty(len(pts), dtype=np.uint32) if want_inliers else None
+        fn = self.lib.gcro_score_msac if scoring == MSAC else self.lib.gcro_score_magsac
+        fn(problem, pts, len(pts), _as_pts(model).ravel(), thr, C.byref(s), C.byref(n),
+           idx.ctypes.data if want_inliers else None)
+        if want_inliers:
+            return s.value, n.value, idx[: n.value].copy()
+        return s.value, n.value
+
+    def score_batch(self, problem, scoring, pts, models, thr):
+        pts = _as_pts(pts)
+        models = _as_pts(models).reshape(len(models), -1)
+        scores = np.empty(len(models))
+        ninl = np.empty(len(models), dtype=np.uint64)
+        self.lib.gcro_score_batch(problem, scoring, pts, len(pts), models, len(models), thr, scores, ninl)
+        return scores, ninl
+
+    def gamma_lut(self, k):
+        return self.lib.gcro_gamma_lut(int(k))
+
+    # ---- samplers ----
+    def philox(self, ctr, key):
+        out = np.empty(4, dtype=np.uint32)
+        self.lib.gcro_philox4x32(np.asarray(ctr, dtype=np.uint32), np.asarray(key, dtype=np.uint32), out)
+        return out
+
+    def sample_uniform(self, seed, first, count, n, m, stream=0):
+        out = np.empty((count, m), dtype=np.uint32)
+        for i in range(count):
+            self.lib.gcro_sample_uniform(seed, first + i, stream, n, m, out[i])
+        return out
+
+    def prosac_growth(self, n, m, conv=100000):
+        g = np.empty(n, dtype=np.uint64)
+        self.lib.gcro_prosac_growth(n, m, conv, g)
+        return g
+
+    def prosac_subset_size(self, growth, n, m, k):
+        return self.lib.gcro_prosac_subset_size(growth, n, m, k)
+
+    def sample_prosac(self, seed, first_k, count, n, m, growth, conv=100000):
+        out = np.empty((count, m), dtype=np.uint32)
+        for i in range(count):
+            self.lib.gcro_sample_prosac(seed, first_k + i, n, m, growth, conv, out[i])
+        return out
+
+    # ---- solvers ----
+    def h_valid_sample(self, pts, sample):
+        return bool(self.lib.gcro_h_valid_sample(_as_pts(pts), np.asarray(sample, dtype=np.uint32)))
+
+    def solve_h4(self, pts, sample):
+        out = np.empty(9)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        pts = _as_pts(pts)
+        ok = self.lib.gcro_solve_h4(pts, pts.shape[1], s.ctypes.data, out)
+        return out.reshape(3, 3) if ok else None
+
+    def h_valid_model(self, Hm):
+        return bool(self.lib.gcro_h_valid_model(_as_pts(Hm).ravel()))
+
+    def refit(self, problem, pts, sample, weights=None):
+        out = np.empty(9)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        fn = self.lib.gcro_refit_h if problem == H else self.lib.gcro_refit_f8
+        ok = fn(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
+        return out.reshape(3, 3) if ok else None
+
+    def _multi(self, fn, pts, sample, maxn, rows, cols):
+        out = np.empty(maxn * rows * cols)
+        cnt = fn(_as_pts(pts), np.ascontiguousarray(sample, dtype=np.uint32), out)
+        return out[: cnt * rows * cols].reshape(cnt, rows, cols).copy()
+
+    def solve_f7(self, pts, sample):
+        return self._multi(self.lib.gcro_solve_f7, pts, sample, 3, 3, 3)
+
+    def estimate_f7(self, pts, sample):
+        return self._multi(self.lib.gcro_estimate_f7, pts, sample, 3, 3, 3)
+
+    def solve_e5(self, pts, sample):
+        return self._multi(self.lib.gcro_solve_e5_nister, pts, sample, 10, 3, 3)
+
+    def estimate_e5(self, pts, sample):
+        return self._multi(self.lib.gcro_estimate_e5, pts, sample, 10, 3, 3)
+
+    def solve_e5_stewenius(self, pts, sample, weights=None):
+        out = np.empty(90)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        cnt = self.lib.gcro_solve_e5_stewenius(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
+        return out[: cnt * 9].reshape(cnt, 3, 3).copy()
+
+    def solve_p3p(self, pts5, sample):
+        return self._multi(self.lib.gcro_solve_p3p, pts5, sample, 4, 3, 4)
+
+    def normalize_correspondences(self, pts, K1, K2):
+        pts = _as_pts(pts)
+        out = np.empty_like(pts)
+        self.lib.gcro_normalize_correspondences(pts, len(pts), _as_pts(K1), _as_pts(K2), out)
+        return out
+
+    # ---- grid / termination ----
+    def grid_build(self, pts, cell_sizes, cells_per_axis):
+        pts = _as_pts(pts)
+        n, dims = pts.shape
+        keys = np.empty(n, dtype=np.uint64)
+        order = np.empty(n, dtype=np.uint32)
+        offs = np.empty(n + 1, dtype=np.uint32)
+        nc = C.c_uint32()
+        nn = self.lib.gcro_grid_build(pts, n, dims, _as_pts(cell_sizes), cells_per_axis, keys, order, offs, C.byref(nc))
+        return dict(keys=keys, sorted_idx=order, cell_offsets=offs[: nc.value + 1].copy(), n_cells=nc.value,
+                    neighbor_number=nn)
+
+    def iteration_number(self, inliers, n, m, log_probability):
+        return self.lib.gcro_iteration_number(inliers, n, m, log_probability)
+
+
+class Ref:
+    """The reference's own headers compiled verbatim (oracle/_ref/libgcr_ref.so)."""
+
+    def __init__(self):
+        so = build_ref()
+        if so is None:
+            raise FileNotFoundError("oracle/_ref/libgcr_ref.so is not built and /root/reference is absent")
+        self.lib = lib = C.CDLL(so)
+        lib.ref_score.restype = None
+        lib.ref_score.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_double, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_uint64), C.c_void_p]
+        lib.ref_gamma_value.restype = C.c_double
+        lib.ref_gamma_value.argtypes = [C.c_int]
+        lib.ref_gamma_table_size.restype = C.c_int
+        lib.ref_prosac.restype = None
+        lib.ref_prosac.argtypes = [C.c_int, C.c_int, C.c_uint64, _u64p, C.c_int, _u32p, _u32p]
+        lib.ref_grid.restype = C.c_uint64
+        lib.ref_grid.argtypes = [_dp, C.c_int, _dp, C.c_uint64, _u64p, _u32p, _u32p, C.POINTER(C.c_uint32)]
+        lib.ref_iteration_number.restype = C.c_uint64
+        lib.ref_iteration_number.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_double]
+        lib.ref_round.restype = None
+        lib.ref_round.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _dp]
+
+    def round(self, problem, scoring, pts, seed, first, count, thr):
+        return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
+
+    def score(self, problem, scoring, pts, model, thr, want_inliers=False):
+        pts = _as_pts(pts)
+        s, n = C.c_double(), C.c_uint64()
+        idx = np.empty(len(pts), dtype=np.uint32) if want_inliers else None
+        self.lib.ref_score(problem, scoring, pts, len(pts), _as_pts(model).ravel(), thr, C.byref(s), C.byref(n),
+                           idx.ctypes.data if want_inliers else None)
+        if want_inliers:
+            return s.value, n.value, idx[: n.value].copy()
+        return s.value, n.value
+
+    def gamma_table(self):
+        return np.array([self.lib.ref_gamma_value(k) for k in range(self.lib.ref_gamma_table_size())])
+
+    def prosac(self, n, m, conv, calls):
+        growth = np.empty(n, dtype=np.uint64)
+        sizes = np.empty(calls, dtype=np.uint32)
+        last = np.empty(calls, dtype=np.uint32)
+        self.lib.ref_prosac(n, m, conv, growth, calls, sizes, last)
+        return growth, sizes, last
+
+    def grid(self, pts, cell_sizes, cells_per_axis):
+        pts = _as_pts(pts)
+        n = len(pts)
+        keys = np.empty(n, dtype=np.uint64)
+        order = np.empty(n, dtype=np.uint32)
+        offs = np.empty(n + 1, dtype=np.uint32)
+        nc = C.c_uint32()
+        nn = self.lib.ref_grid(pts, n, _as_pts(cell_sizes), cells_per_axis, keys, order, offs, C.byref(nc))
+        return dict(keys=keys, sorted_idx=order, cell_offsets=offs[: nc.value + 1].copy(), n_cells=nc.value,
+                    neighbor_number=nn)
+
+    def iteration_number(self, inliers, n, m, log_probability):
+        return self.lib.ref_iteration_number(inliers, n, m, log_probability)

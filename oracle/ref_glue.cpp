@@ -1,0 +1,350 @@
+// oracle/ref_glue.cpp -- TEST INFRASTRUCTURE ONLY.  Built ONLY where /root/reference exists (this container), by
+// oracle/build_ref.sh, into oracle/_ref/libgcr_ref.so.  It #includes the reference's own headers UNMODIFIED from
+// /root/reference/src/pygcransac/include (GCRANSAC.h, scoring_function.h + gamma_values.cpp, samplers, grid graph,
+// BK max-flow) through the two container shims in oracle/shim/, and exposes them over a small C API so that
+//   (1) the self-contained restatement in oracle/gcr_oracle*.cpp can be pinned against the real reference code, and
+//   (2) golden fixtures (tests/golden/) can be generated from the reference itself (oracle/gen_golden.py).
+// The reference's estimator classes need real Eigen decompositions and cannot be compiled here, so the Estimator
+// template parameter is an adapter over the restated solvers of oracle/gcr_oracle*.cpp (kind = "reference driver +
+// restated estimators"; stated wherever results of this library are quoted).
+#include <opencv2/core/core.hpp>
+
+#include "GCRANSAC.h"
+#include "neighborhood/grid_neighborhood_graph.h"
+#include "samplers/prosac_sampler.h"
+#include "samplers/uniform_sampler.h"
+
+#include "gcr_oracle.h"
+
+#include <cstdint>
+#include <cstring>
+
+using namespace gcransac;
+
+namespace
+{
+	template <int PROBLEM>
+	struct ProblemTraits;
+	template <> struct ProblemTraits<GCRO_H> { static constexpr size_t m = 4, nonmin = 4, maxsol = 1, rows = 3, cols = 3; static constexpr bool weighting = true; };
+	template <> struct ProblemTraits<GCRO_F> { static constexpr size_t m = 7, nonmin = 8, maxsol = 3, rows = 3, cols = 3; static constexpr bool weighting = true; };
+	template <> struct ProblemTraits<GCRO_E> { static constexpr size_t m = 5, nonmin = 6, maxsol = 10, rows = 3, cols = 3; static constexpr bool weighting = true; };
+	template <> struct ProblemTraits<GCRO_PNP> { static constexpr size_t m = 3, nonmin = 6, maxsol = 4, rows = 3, cols = 4; static constexpr bool weighting = false; };
+
+	inline void to_flat(const Eigen::MatrixXd &d, double *out)
+	{
+		for (int i = 0; i < d.rows(); ++i)
+			for (int j = 0; j < d.cols(); ++j)
+				out[i * d.cols() + j] = d(i, j);
+	}
+	inline Model from_flat(const double *in, int rows, int cols)
+	{
+		Model m((Eigen::MatrixXd(rows, cols)));
+		for (int i = 0; i < rows; ++i)
+			for (int j = 0; j < cols; ++j)
+				m.descriptor(i, j) = in[i * cols + j];
+		return m;
+	}
+
+	// Estimator concept (estimators/estimator.h:48-108) over the restated solvers.
+	template <int PROBLEM>
+	class OracleEstimator
+	{
+	public:
+		typedef ProblemTraits<PROBLEM> T;
+		double f_min_ratio = 0.5; // fundamental_estimator.h minimum_inlier_ratio_in_validity_check default
+		bool use_degensac = false;
+
+		static constexpr size_t sampleSize() { return T::m; }
+		static constexpr size_t nonMinimalSampleSize() { return T::nonmin; }
+		static constexpr size_t maximumMinimalSolutions() { return T::maxsol; }
+		static constexpr bool isWeightingApplicable() { return T::weighting; }
+		size_t inlierLimit() const { return 7 * sampleSize(); }
+
+		double squaredResidual(const cv::Mat &point_, const Eigen::MatrixXd &descriptor_) const
+		{
+			// the shim's MatrixXd is contiguous row-major, which is the layout the restated residuals take
+			const double *flat = descriptor_.rowmajor();
+			const double *pt = reinterpret_cast<const double *>(point_.data);
+			if constexpr (PROBLEM == GCRO_H)
+				return gcro_sqres_h(pt, flat);
+			else if constexpr (PROBLEM == GCRO_PNP)
+				return gcro_sqres_pnp(pt, flat);
+			else
+				return gcro_sqres_sampson(pt, flat);
+		}
+		double squaredResidual(const cv::Mat &point_, const Model &model_) const { return squaredResidual(point_, model_.descriptor); }
+		double residual(const cv::Mat &point_, const Eigen::MatrixXd &descriptor_) const { return sqrt(squaredResidual(point_, descriptor_)); }
+		double residual(const cv::Mat &point_, const Model &model_) const { return residual(point_, model_.descriptor); }
+
+		bool isValidSample(const cv::Mat &data_, const size_t *sample_) const
+		{
+			if constexpr (PROBLEM == GCRO_H)
+			{
+				uint32_t s[4] = {(uint32_t)sample_[0], (uint32_t)sample_[1], (uint32_t)sample_[2], (uint32_t)sample_[3]};
+				return gcro_h_valid_sample(reinterpret_cast<const double *>(data_.data), s) != 0;
+			}
+			return true;
+		}
+
+		bool estimateModel(const cv::Mat &data_, const size_t *sample_, std::vector<Model> *models_) const
+		{
+			uint32_t s[8];
+			for (size_t i = 0; i < T::m; ++i)
+				s[i] = (uint32_t)sample_[i];
+			const double *pts = reinterpret_cast<const double *>(data_.data);
+			double out[10 * 12];
+			int count = 0;
+			if constexpr (PROBLEM == GCRO_H)
+				count = gcro_solve_h4(pts, data_.cols, s, out);
+			else if constexpr (PROBLEM == GCRO_F)
+				count = gcro_estimate_f7(pts, s, out);
+			else if constexpr (PROBLEM == GCRO_E)
+				count = gcro_estimate_e5(pts, s, out);
+			else
+				count = gcro_solve_p3p(pts, s, out);
+			for (int i = 0; i < count; ++i)
+				models_->emplace_back(from_flat(out + i * T::rows * T::cols, T::rows, T::cols));
+			if constexpr (PROBLEM == GCRO_H)
+				return count > 0; // solver_homography_four_point.h returns the solver's bool
+			return models_->size() > 0;
+		}
+
+		bool estimateModelNonminimal(const cv::Mat &data_, const size_t *sample_, const size_t &sample_number_,
+		                             std::vector<Model> *models_, const double *weights_ = nullptr) const
+		{
+			if (sample_number_ < nonMinimalSampleSize())
+				return false;
+			std::vector<uint32_t> s(sample_number_);
+			for (size_t i = 0; i < sample_number_; ++i)
+				s[i] = (uint32_t)sample_[i];
+			const double *pts = reinterpret_cast<const double *>(data_.data);
+			double out[10 * 12];
+			int count = 0;
+			if constexpr (PROBLEM == GCRO_H)
+				count = gcro_refit_h(pts, s.data(), (int)sample_number_, weights_, out);
+			else if constexpr (PROBLEM == GCRO_F)
+				count = gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
+			else if constexpr (PROBLEM == GCRO_E)
+				count = gcro_solve_e5_stewenius(pts, s.data(), (int)sample_number_, weights_, out);
+			else
+				count = 0;
+			for (int i = 0; i < count; ++i)
+				models_->emplace_back(from_flat(out + i * T::rows * T::cols, T::rows, T::cols));
+			return count > 0;
+		}
+
+		bool isValidModel(Model &model, const cv::Mat &data, const std::vector<size_t> &inliers,
+		                  const size_t *minimal_sample_, const double threshold_, bool &model_updated_) const
+		{
+			model_updated_ = false;
+			double flat[12];
+			to_flat(model.descriptor, flat);
+			if constexpr (PROBLEM == GCRO_H)
+				return gcro_h_valid_model(flat) != 0;
+			else if constexpr (PROBLEM == GCRO_F || PROBLEM == GCRO_E)
+			{
+				std::vector<uint32_t> inl(inliers.size());
+				for (size_t i = 0; i < inliers.size(); ++i)
+					inl[i] = (uint32_t)inliers[i];
+				const double ratio = PROBLEM == GCRO_F ? f_min_ratio : 0.1;
+				return gcro_f_valid_model_ratio(flat, reinterpret_cast<const double *>(data.data), inl.data(),
+				                                (int)inl.size(), (int)T::m, threshold_, ratio) != 0;
+			}
+			return true;
+		}
+	};
+
+	template <int PROBLEM>
+	void score_with_reference(int scoring, const cv::Mat &points, const double *model_flat, double thr, double *score,
+	                          uint64_t *n_inl, uint32_t *inl_idx)
+	{
+		typedef OracleEstimator<PROBLEM> Est;
+		Est est;
+		Model model = from_flat(model_flat, Est::T::rows, Est::T::cols);
+		std::vector<size_t> inliers;
+		Score s;
+		if (scoring == GCRO_MSAC)
+		{
+			MSACScoringFunction<Est> f;
+			const double tt = 3.0 / 2.0 * thr; // GCRANSAC.h:253-255
+			f.initialize(tt * tt, points.rows);
+			s = f.getScore(points, model, est, thr, inliers);
+		}
+		else
+		{
+			MAGSACScoringFunction<Est> f;
+			f.initialize(0, points.rows);
+			s = f.getScore(points, model, est, thr, inliers);
+		}
+		*score = s.value;
+		*n_inl = s.inlier_number;
+		if (inl_idx)
+			for (size_t i = 0; i < inliers.size(); ++i)
+				inl_idx[i] = (uint32_t)inliers[i];
+	}
+
+	class ProsacProbe : public sampler::ProsacSampler
+	{
+	public:
+		ProsacProbe(const cv::Mat *c, size_t m, size_t conv) : sampler::ProsacSampler(c, m, conv) {}
+		const std::vector<size_t> &growth() const { return growth_function; }
+		size_t subsetSize() const { return subset_size; }
+		size_t kth() const { return kth_sample_number; }
+	};
+
+	// exposes GCRANSAC<>::getIterationNumber (protected)
+	struct IterProbe : public GCRANSAC<OracleEstimator<GCRO_H>, neighborhood::GridNeighborhoodGraph<4>>
+	{
+		size_t get(size_t a, size_t b, size_t c, double d) { return getIterationNumber(a, b, c, d); }
+	};
+}
+
+extern "C" {
+
+// scoring_function.h verbatim (MSAC :103-234, MAGSAC :237-349)
+void ref_score(int problem, int scoring, const double *pts, int n, const double *model, double thr, double *score,
+               uint64_t *n_inl, uint32_t *inl_idx)
+{
+	const int cols = gcro_point_cols(problem);
+	cv::Mat points(n, cols, CV_64F, const_cast<double *>(pts));
+	switch (problem)
+	{
+	case GCRO_H: score_with_reference<GCRO_H>(scoring, points, model, thr, score, n_inl, inl_idx); break;
+	case GCRO_F: score_with_reference<GCRO_F>(scoring, points, model, thr, score, n_inl, inl_idx); break;
+	case GCRO_E: score_with_reference<GCRO_E>(scoring, points, model, thr, score, n_inl, inl_idx); break;
+	default: score_with_reference<GCRO_PNP>(scoring, points, model, thr, score, n_inl, inl_idx); break;
+	}
+}
+
+// gamma_values.cpp:2012 table entry
+double ref_gamma_value(int k) { return stored_gamma_values[k]; }
+int ref_gamma_table_size() { return (int)(sizeof(stored_gamma_values) / sizeof(double)); }
+
+// prosac_sampler.h growth function and the subset size used by each of the first `calls` sample() calls
+void ref_prosac(int n, int m, uint64_t conv, uint64_t *growth, int calls, uint32_t *subset_sizes, uint32_t *last_index)
+{
+	cv::Mat dummy(n, 4, CV_64F);
+	ProsacProbe p(&dummy, (size_t)m, (size_t)conv);
+	for (int i = 0; i < n; ++i)
+		growth[i] = p.growth()[i];
+	std::vector<size_t> pool, subset(m);
+	for (int c = 0; c < calls; ++c)
+	{
+		subset_sizes[c] = (uint32_t)p.subsetSize();
+		p.sample(pool, subset.data(), (size_t)m);
+		last_index[c] = (uint32_t)subset[m - 1];
+	}
+}
+
+// grid_neighborhood_graph.h verbatim
+uint64_t ref_grid(const double *pts, int n, const double *cell_sizes, uint64_t cells_per_axis, uint64_t *keys,
+                  uint32_t *sorted_idx, uint32_t *cell_offsets, uint32_t *n_cells)
+{
+	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
+	std::vector<double> cs(cell_sizes, cell_sizes + 4);
+	neighborhood::GridNeighborhoodGraph<4> g(&points, cs, (size_t)cells_per_axis);
+	// keys through getNeighbors(): every point of a cell reports the same list; recover the key from getCells()
+	std::vector<std::pair<size_t, const std::vector<size_t> *>> cells;
+	for (const auto &kv : g.getCells())
+		cells.emplace_back(kv.first, &kv.second.first);
+	std::sort(cells.begin(), cells.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+	uint32_t pos = 0, c = 0;
+	for (const auto &cell : cells)
+	{
+		cell_offsets[c++] = pos;
+		for (size_t idx : *cell.second)
+		{
+			keys[idx] = cell.first;
+			sorted_idx[pos++] = (uint32_t)idx;
+		}
+	}
+	cell_offsets[c] = pos;
+	*n_cells = (uint32_t)g.filledCellNumber();
+	return g.getNeighborNumber();
+}
+
+} // extern "C" (templates below need C++ linkage)
+
+// One fixed-K pass of the reference's hypothesise-and-verify inner loop (GCRANSAC.h:297-471 without the adaptive
+// stop and LO): counter-based samples -> isValidSample -> estimateModel -> MSAC/MAGSAC getScore (verbatim) -> strict
+// '<' best-so-far.  This is what bench.py times as the CPU arm.
+template <int PROBLEM, class Scoring>
+static void round_with_reference(const cv::Mat &points, uint64_t seed, uint64_t first, int count, double thr,
+                                 double *best_score, uint64_t *best_index, uint64_t *models_scored, double *best_model)
+{
+	typedef OracleEstimator<PROBLEM> Est;
+	Est est;
+	Scoring scoring;
+	const double tt = 3.0 / 2.0 * thr;
+	scoring.initialize(tt * tt, points.rows);
+	std::vector<Model> models;
+	std::vector<size_t> inliers;
+	inliers.reserve(points.rows);
+	Score best;
+	uint64_t best_idx = ~0ull, scored = 0;
+	constexpr size_t m = Est::sampleSize();
+	uint32_t s32[8];
+	size_t s[8];
+	for (int i = 0; i < count; ++i)
+	{
+		gcro_sample_uniform(seed, first + (uint64_t)i, 0u, (uint32_t)points.rows, (int)m, s32);
+		for (size_t j = 0; j < m; ++j)
+			s[j] = s32[j];
+		models.resize(0);
+		if (!est.isValidSample(points, s))
+			continue;
+		if (!est.estimateModel(points, s, &models))
+			continue;
+		for (size_t j = 0; j < models.size(); ++j)
+		{
+			Score sc = scoring.getScore(points, models[j], est, thr, inliers, best, true);
+			++scored;
+			if (best < sc)
+			{
+				best = sc;
+				best_idx = (uint64_t)i * Est::maximumMinimalSolutions() + j;
+				if (best_model)
+					to_flat(models[j].descriptor, best_model);
+			}
+		}
+	}
+	*best_score = best.value;
+	*best_index = best_idx;
+	*models_scored = scored;
+}
+
+extern "C" {
+
+void ref_round(int problem, int scoring, const double *pts, int n, uint64_t seed, uint64_t first, int count, double thr,
+               double *best_score, uint64_t *best_index, uint64_t *models_scored, double *best_model)
+{
+	const int cols = gcro_point_cols(problem);
+	cv::Mat points(n, cols, CV_64F, const_cast<double *>(pts));
+#define GCR_RR(P)                                                                                                       \
+	do                                                                                                                  \
+	{                                                                                                                   \
+		if (scoring == GCRO_MSAC)                                                                                       \
+			round_with_reference<P, MSACScoringFunction<OracleEstimator<P>>>(points, seed, first, count, thr, best_score, \
+			                                                                best_index, models_scored, best_model);      \
+		else                                                                                                            \
+			round_with_reference<P, MAGSACScoringFunction<OracleEstimator<P>>>(points, seed, first, count, thr,          \
+			                                                                  best_score, best_index, models_scored,     \
+			                                                                  best_model);                               \
+	} while (0)
+	switch (problem)
+	{
+	case GCRO_H: GCR_RR(GCRO_H); break;
+	case GCRO_F: GCR_RR(GCRO_F); break;
+	case GCRO_E: GCR_RR(GCRO_E); break;
+	default: GCR_RR(GCRO_PNP); break;
+	}
+#undef GCR_RR
+}
+
+uint64_t ref_iteration_number(uint64_t inliers, uint64_t n, int m, double log_probability)
+{
+	IterProbe p;
+	return p.get(inliers, n, (size_t)m, log_probability);
+}
+
+} // extern "C"

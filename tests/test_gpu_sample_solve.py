@@ -1,0 +1,99 @@
+"""K1 / K2 / K4 parity through the C ABI: sample indices bit-exact with the oracle's counter-based stream,
+H4 models bit-exact (same FP64 operation order), argmax key semantics."""
+import numpy as np
+import oracle as O
+import pytest
+from pygcransac import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+PAIR_STRIDE = 0x9E3779B97F4A7C15
+MASK = (1 << 64) - 1
+
+
+def test_uniform_samples_bit_exact(gcr_ctx, oracle):
+    pts = np.stack([synth.homography_pair(333, 0.3, seed=s)[0] for s in (1, 2)])
+    gcr_ctx.points_upload(pts, n_pairs=2)
+    for m in (3, 4, 5, 7):
+        got = gcr_ctx.sample(_cabi.UNIFORM, m, 1000, 3000, seed=77)
+        for p in range(2):
+            want = oracle.sample_uniform((77 + p * PAIR_STRIDE) & MASK, 1000, 3000, 333, m)
+            assert np.array_equal(got[p], want), (m, p)
+
+
+def test_uniform_tiny_pool(gcr_ctx, oracle):
+    pts = synth.homography_pair(7, 0.0, seed=3)[0]
+    gcr_ctx.points_upload(pts)
+    got = gcr_ctx.sample(_cabi.UNIFORM, 7, 0, 500, seed=1)[0]
+    assert np.array_equal(got, oracle.sample_uniform(1, 0, 500, 7, 7))
+    assert all(sorted(r) == list(range(7)) for r in got)
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.sample(_cabi.UNIFORM, 8, 0, 10, seed=1)  # uniform_sampler.h:87-88: sample larger than the pool
+
+
+def test_prosac_samples_bit_exact(gcr_ctx, oracle):
+    for n, m in ((762, 4), (4096, 7), (64, 5)):
+        pts = synth.homography_pair(n, 0.3, seed=5)[0]
+        gcr_ctx.points_upload(pts)
+        growth = oracle.prosac_growth(n, m)
+        got = gcr_ctx.sample(_cabi.PROSAC, m, 1, 5000, seed=9)[0]
+        assert np.array_equal(got, oracle.sample_prosac(9, 1, 5000, n, m, growth)), (n, m)
+        # beyond the convergence point PROSAC degenerates to uniform draws over all points (prosac_sampler.h:224-229)
+        got = gcr_ctx.sample(_cabi.PROSAC, m, 99990, 30, seed=9)[0]
+        assert np.array_equal(got, oracle.sample_prosac(9, 99990, 30, n, m, growth)), (n, m)
+
+
+def test_pool_sampler(gcr_ctx, oracle):
+    pool = np.arange(10, 500, 3, dtype=np.uint32)
+    got = gcr_ctx.sample_from_pool(pool, 28, 0, 50, seed=4, stream=2)
+    want = oracle.sample_uniform(4, 0, 50, len(pool), 28, stream=2)
+    assert np.array_equal(got, pool[want])
+
+
+def test_h4_models_bit_exact(gcr_ctx, oracle):
+    pts, Hm, _ = synth.homography_pair(500, 0.3, seed=13)
+    gcr_ctx.points_upload(pts)
+    samples = oracle.sample_uniform(3, 0, 4000, 500, 4)
+    models, valid = gcr_ctx.solve_minimal(O.H, samples)
+    models, valid = models[0, :, 0], valid[0, :, 0]
+    n_valid = 0
+    for s, mdl, v in zip(samples, models, valid):
+        ok = oracle.h_valid_sample(pts, s)
+        want = oracle.solve_h4(pts, s) if ok else None
+        assert bool(v) == (want is not None)
+        if want is not None:
+            n_valid += 1
+            assert np.array_equal(mdl.reshape(3, 3), want)  # bit-exact FP64
+    assert 500 < n_valid < 4000  # both branches exercised
+
+
+def test_argmax_first_wins(gcr_ctx):
+    pts = np.stack([synth.homography_pair(64, 0.3, seed=s)[0] for s in (1, 2)])
+    gcr_ctx.points_upload(pts, n_pairs=2)
+    scores = np.zeros((2, 5000), dtype=np.float32)
+    scores[0, [700, 4000]] = 12.5   # tie: the lower index must win (GCRANSAC.h:440 strict '<')
+    scores[1, :] = -1.0
+    scores[1, 4999] = 0.0
+    keys = gcr_ctx.argmax(scores, index_base=100)
+    assert gcr_ctx.key_decode(keys[0]) == (12.5, 800)
+    assert gcr_ctx.key_decode(keys[1]) == (0.0, 5099)
+
+
+def test_round_h_matches_stagewise_oracle(gcr_ctx, oracle):
+    pts, Hm, _ = synth.homography_pair(1500, 0.3, seed=17)
+    gcr_ctx.points_upload(pts)
+    keys, best, evals = gcr_ctx.round(O.H, _cabi.MSAC, _cabi.UNIFORM, 0, 2048, seed=21, thr=3.0,
+                                      flags=_cabi.SCORE_EXACT_COUNTS)
+    score, idx = gcr_ctx.key_decode(keys[0])
+    samples = oracle.sample_uniform(21, 0, 2048, 1500, 4)
+    scores = np.full(2048, -1.0)
+    for i, s in enumerate(samples):
+        if oracle.h_valid_sample(pts, s):
+            mdl = oracle.solve_h4(pts, s)
+            if mdl is not None:
+                scores[i] = oracle.score(O.H, O.MSAC, pts, mdl, 3.0)[0]
+    order = np.argsort(-scores, kind="stable")
+    # the FP32 winner must be the FP64 winner unless the two best are closer than the FP32 score tolerance
+    assert idx == order[0] or abs(scores[order[0]] - scores[idx]) <= 1e-5 * scores[order[0]]
+    assert abs(score - scores[idx]) <= 1e-5 * scores[idx]
+    assert np.array_equal(best[0].reshape(3, 3), oracle.solve_h4(pts, samples[idx]))
+    assert evals == 2048 * 1500
