@@ -221,7 +221,10 @@ def main():
     prob = _cabi.F if wl["problem"] == "f" else _cabi.H
     flags = 0 if args.no_exact else _cabi.SCORE_EXACT_COUNTS
     ctx = _cabi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "restore the context's own stream" to gcr_ctx_set_stream, and
+    # the CUDA events below must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     if args.variant >= 0:
         ctx.set_score_variant(args.variant)
@@ -243,23 +246,34 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident(i):
-        flush.zero_()                                                       # L2 flush between steps
         return ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
                                 flags, 0, keys.data_ptr(), best.data_ptr())
 
     def step_e2e(i):
-        flush.zero_()
         ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
         ev = ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
                               flags, 0, keys.data_ptr(), best.data_ptr())
         keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
         best_host.copy_(best, non_blocking=True)
-        stream.synchronize()
         return ev
+
+    def timed(step_fn, first):
+        """K steps, each bracketed by its own CUDA event pair on the launching stream; the L2 flush (a 256 MiB device
+        memset) runs BETWEEN steps, outside the event pairs.  Returns (sum of step times in ms, slot evaluations)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        slot = 0
+        for i, (a, b) in enumerate(evs):
+            flush.zero_()
+            a.record()
+            slot += step_fn(first + i)
+            b.record()
+        stream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs), slot
 
     # ---- resident leg: inputs in HBM before the timed region ----
     ctx.points_set_device(pts_dev.data_ptr(), n, 4, n_pairs)
     for i in range(args.warmup):
+        flush.zero_()
         step_resident(i)
     barrier()
     ctx.counters(reset=True)
@@ -268,35 +282,28 @@ def main():
     launches0 = ctx.launch_count()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
-    slot_evals = 0
-    for i in range(args.steps):
-        slot_evals += step_resident(args.warmup + i)
-    e1.record()
+    ms, slot_evals = timed(step_resident, args.warmup)
     barrier()
-    clock_info = clocks.stop()
-    ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
     score_ms, score_launches, score_slot_evals = ctx.profile_read()
     ctx.profile_enable(False)
-    valid_models = ctx.counters(reset=True)[0]
+    counters = ctx.counters(reset=True)
+    valid_models, dropped = counters[0], counters[1]
+    if dropped:
+        raise SystemExit("bench.py: %d FP64 re-check evaluations were dropped (work list full)" % dropped)
     evals = valid_models * n
     best_key_score, best_key_index = ctx.key_decode(int(keys[0].item()) & ((1 << 64) - 1))
 
     # ---- e2e leg: host buffers, H2D + D2H inside the timed region ----
     for i in range(args.warmup):
+        flush.zero_()
         step_e2e(i)
     barrier()
     ctx.counters(reset=True)
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-    g1.record()
+    ms_e2e, _ = timed(step_e2e, args.warmup)
     barrier()
-    ms_e2e = g0.elapsed_time(g1)
+    clock_info = clocks.stop()
     evals_e2e = ctx.counters(reset=True)[0] * n
 
     # ---- max over ranks, sum of work ----
@@ -326,7 +333,7 @@ def main():
             "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
                        "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
                        "exact_counts": not args.no_exact, "k3_variant": args.variant,
-                       "l2_flush": "256 MiB device memset between steps (inside the timed region)",
+                       "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs)",
                        "best_score_rank0": best_key_score},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,

@@ -2,10 +2,9 @@
 //
 // Data layout in HBM (per context):
 //   d_pts64   [n_pairs][n][cols]        FP64 row-major, exactly what the caller handed over (the reference's cv::Mat)
-//   d_pts32   [n_pairs][n_pad]          float4 (x1' y1' x2' y2')   centred + power-of-two scaled FP32 copy
-//             (PnP: [n_pairs][n_pad][2] float4 (u' v' 0 0)(X' Y' Z' 0))
-//   d_pts32dup[n_pairs][n_pad][2]       float4 (x1' x1' y1' y1')(x2' x2' y2' y2') operand-duplicated copy for the
-//                                       packed f32x2 scoring kernel (4-column problems only)
+//   d_pts32   [n_pairs][n_pad][2]       float4 (x1' x1' y1' y1')(x2' x2' y2' y2'): centred + power-of-two scaled FP32
+//                                       copy, operand-duplicated for the packed f32x2 scoring kernel
+//             (PnP: (u' v' 0 0)(X' Y' Z' 0))
 //   d_norm    [n_pairs][8]              FP64 normalisation (centres, scale) so models can be mapped alike
 // n_pad = n rounded up to GCR_TILE_POINTS; padding rows are NaN so they can never be inliers.
 #include "gcr_internal.cuh"
@@ -66,7 +65,7 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_pts64_owned);
 	cudaFree(ctx->d_pts32);
-	cudaFree(ctx->d_pts32dup);
+	cudaFree(ctx->d_score_ws);
 	cudaFree(ctx->d_norm);
 	cudaFree(ctx->d_bbox);
 	cudaFree(ctx->d_magsac_lut);
@@ -368,8 +367,7 @@ __global__ void k_norm(const unsigned long long *bbox, double *norm, int n_pairs
 
 template <int COLS>
 __global__ void __launch_bounds__(256) k_convert(const double *__restrict__ pts, const double *__restrict__ norm,
-                                                  int n, int n_pad, float4 *__restrict__ out32,
-                                                  float4 *__restrict__ out32dup)
+                                                  int n, int n_pad, float4 *__restrict__ out32)
 {
 	const int pair = blockIdx.y;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,9 +387,8 @@ __global__ void __launch_bounds__(256) k_convert(const double *__restrict__ pts,
 			q.z = (float)((p[2] - nm[2]) * s);
 			q.w = (float)((p[3] - nm[3]) * s);
 		}
-		out32[(size_t)pair * n_pad + i] = q;
-		out32dup[((size_t)pair * n_pad + i) * 2 + 0] = make_float4(q.x, q.x, q.y, q.y);
-		out32dup[((size_t)pair * n_pad + i) * 2 + 1] = make_float4(q.z, q.z, q.w, q.w);
+		out32[((size_t)pair * n_pad + i) * 2 + 0] = make_float4(q.x, q.x, q.y, q.y);
+		out32[((size_t)pair * n_pad + i) * 2 + 1] = make_float4(q.z, q.z, q.w, q.w);
 	}
 	else
 	{
@@ -414,17 +411,14 @@ static gcr_status prepare_points(gcr_ctx *ctx)
 {
 	const int n = ctx->n, cols = ctx->cols, n_pairs = ctx->n_pairs;
 	ctx->n_pad = (n + GCR_TILE_POINTS - 1) / GCR_TILE_POINTS * GCR_TILE_POINTS;
-	const size_t per_point32 = cols == 4 ? 1 : 2;
-	const size_t need32 = (size_t)n_pairs * ctx->n_pad * per_point32;
+	const size_t need32 = (size_t)n_pairs * ctx->n_pad * 2;
 	if (need32 > ctx->pts32_capacity)
 	{
 		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_pts32);
-		cudaFree(ctx->d_pts32dup);
-		ctx->d_pts32 = ctx->d_pts32dup = nullptr;
+		ctx->d_pts32 = nullptr;
 		ctx->pts32_capacity = 0;
 		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts32, need32 * sizeof(float4)));
-		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts32dup, (size_t)n_pairs * ctx->n_pad * 2 * sizeof(float4)));
 		ctx->pts32_capacity = need32;
 	}
 	if ((size_t)n_pairs > ctx->norm_capacity)
@@ -452,7 +446,7 @@ static gcr_status prepare_points(gcr_ctx *ctx)
 		GCR_LAUNCHED(ctx);
 		k_norm<4><<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bbox, ctx->d_norm, n_pairs);
 		GCR_LAUNCHED(ctx);
-		k_convert<4><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32, ctx->d_pts32dup);
+		k_convert<4><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32);
 		GCR_LAUNCHED(ctx);
 	}
 	else
@@ -461,7 +455,7 @@ static gcr_status prepare_points(gcr_ctx *ctx)
 		GCR_LAUNCHED(ctx);
 		k_norm<5><<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_bbox, ctx->d_norm, n_pairs);
 		GCR_LAUNCHED(ctx);
-		k_convert<5><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32, ctx->d_pts32dup);
+		k_convert<5><<<gc, 256, 0, ctx->stream>>>(ctx->d_pts64, ctx->d_norm, n, ctx->n_pad, ctx->d_pts32);
 		GCR_LAUNCHED(ctx);
 	}
 	return GCR_OK;

@@ -25,8 +25,9 @@ struct gcr_ctx
 	const double *d_pts64 = nullptr; // [n_pairs][n][cols]
 	double *d_pts64_owned = nullptr;
 	size_t pts64_capacity = 0;
-	float4 *d_pts32 = nullptr; // [n_pairs][n_pad] float4 (cols==4) or [n_pairs][n_pad][2] float4 (cols==5)
-	float4 *d_pts32dup = nullptr; // [n_pairs][n_pad][2] float4: (x1 x1 y1 y1)(x2 x2 y2 y2) for the packed f32x2 path
+	// [n_pairs][n_pad][2] float4: (x1 x1 y1 y1)(x2 x2 y2 y2) operand-duplicated for the packed f32x2 scoring path
+	// (cols == 4), or (u v 0 0)(X Y Z 0) (cols == 5)
+	float4 *d_pts32 = nullptr;
 	size_t pts32_capacity = 0;
 	int n_pad = 0;              // n rounded up to the tile granule; padding points can never be inliers
 	double *d_norm = nullptr;  // [n_pairs][8]
@@ -45,7 +46,12 @@ struct gcr_ctx
 	void *d_round = nullptr;
 	size_t round_capacity = 0;
 
-	// counters (device, u64): [0] valid models produced by K2 since the last reset
+	// FP64 score / exact inlier count of each pair's winner, written by the last gcr_round (inside d_round)
+	double *d_round_best_scores = nullptr;
+	uint32_t *d_round_best_counts = nullptr;
+
+	// counters (device, u64): [0] valid models produced by K2, [1] FP64 re-check entries dropped (work list full),
+	// [2] FP64 re-check entries queued -- since the last reset
 	unsigned long long *d_counters = nullptr;
 	// optional per-launch timing of the scoring kernel (bench.py's roofline leg)
 	bool profile = false;
@@ -55,6 +61,10 @@ struct gcr_ctx
 	double score_ms = 0.0;
 	uint64_t score_launches = 0;
 	uint64_t score_evals = 0;
+
+	// workspace of gcr_score (compact model list, accumulators, FP64 work list)
+	void *d_score_ws = nullptr;
+	size_t score_ws_capacity = 0;
 
 	// scratch
 	void *d_scratch = nullptr;
@@ -97,6 +107,7 @@ gcr_status gcr_ensure_pinned(gcr_ctx *ctx, size_t bytes);
 gcr_status gcr_profile_begin(gcr_ctx *ctx);
 gcr_status gcr_profile_end(gcr_ctx *ctx, uint64_t evals);
 gcr_status gcr_ensure_prosac_growth(gcr_ctx *ctx, int m);
+gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx);
 
 static inline int gcr_cols_of(int problem) { return problem == GCR_PNP ? 5 : 4; }
 

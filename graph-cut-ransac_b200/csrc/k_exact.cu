@@ -148,6 +148,16 @@ __global__ void k_fill_lut64(double *lut)
 	lut[k] = 0.88622692545275801365 * erfc(sx) + sx * exp(-x);
 }
 
+gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx)
+{
+	if (ctx->d_magsac_lut64)
+		return GCR_OK;
+	GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_magsac_lut64, 5008 * sizeof(double)));
+	k_fill_lut64<<<(5001 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_magsac_lut64);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
 extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                       double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
                                       double *d_residuals)
@@ -161,11 +171,11 @@ extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, in
 	if (pair < 0 || pair >= ctx->n_pairs || k <= 0 || !d_models || !d_scores || !d_counts)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-	if (scoring == GCR_MAGSAC && !ctx->d_magsac_lut64)
+	if (scoring == GCR_MAGSAC)
 	{
-		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_magsac_lut64, 5008 * sizeof(double)));
-		k_fill_lut64<<<(5001 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_magsac_lut64);
-		GCR_LAUNCHED(ctx);
+		gcr_status lst = gcr_ensure_magsac_lut64(ctx);
+		if (lst)
+			return lst;
 	}
 	ExactArgs a;
 	a.pts = ctx->d_pts64 + (size_t)pair * ctx->n * ctx->cols;

@@ -1,0 +1,264 @@
+// k_grid.cu -- K7: the grid neighbourhood graph as an integer binning / sort problem.
+//
+// Replaces GridNeighborhoodGraph<4>::initialize (neighborhood/grid_neighborhood_graph.h:229-292): per point
+// idx_d = floor(coord_d / cell_size_d) in FP64 (:251-252), key = sum idx_d * C^d (GridCell, :70-82); the reference
+// then inserts every point into an unordered_map<key, vector<point>> in point order (:260-267), so each cell's list
+// is ascending in the point index; neighbor_number = sum n (n - 1) / 2 over the filled cells (:283-284).
+//
+// Here: k_grid_keys (one thread per point; the divide + floor stay FP64 so keys are bit-exact), a stable LSD radix
+// sort of (key, point index) -- 8-bit digits, only over the significant key bits; the payload starts as 0..n-1 and
+// every pass is stable, so points stay ascending inside a cell -- then head flags + scan give the cell offsets, and
+// an integer atomic accumulates neighbor_number.  HBM-bound integer work: 32 B/point read for the keys, then
+// 12 B/point read + 12 B/point written per radix pass.
+#include "gcr_internal.cuh"
+
+#include <math.h>
+
+#define GT 256 /* threads per CTA and elements per CTA tile */
+
+__global__ void __launch_bounds__(GT) k_grid_keys(const double *__restrict__ pts, int n, double c0, double c1, double c2,
+                                                  double c3, unsigned long long cells, unsigned long long *__restrict__ keys,
+                                                  uint32_t *__restrict__ idx, unsigned long long *key_or)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long index = 0;
+	if (i < n)
+	{
+	const double *p = pts + (size_t)i * 4;
+	// (size_t) of a double like the reference's implicit conversion (:251-252)
+	const unsigned long long i0 = (unsigned long long)(long long)floor(p[0] / c0);
+	const unsigned long long i1 = (unsigned long long)(long long)floor(p[1] / c1);
+	const unsigned long long i2 = (unsigned long long)(long long)floor(p[2] / c2);
+	const unsigned long long i3 = (unsigned long long)(long long)floor(p[3] / c3);
+	unsigned long long offset = 1;
+	index += offset * i0; offset *= cells;
+	index += offset * i1; offset *= cells;
+	index += offset * i2; offset *= cells;
+	index += offset * i3;
+	keys[i] = index;
+	idx[i] = (uint32_t)i;
+	}
+	// OR of all keys: tells the host how many radix passes the sort needs
+	unsigned long long any = index;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		any |= __shfl_xor_sync(0xffffffffu, any, o);
+	if ((threadIdx.x & 31) == 0 && any)
+		atomicOr(key_or, any);
+}
+
+// per-CTA digit histogram: hist[digit * n_blocks + block]
+__global__ void __launch_bounds__(GT) k_radix_hist(const unsigned long long *__restrict__ keys, int n, int shift,
+                                                   uint32_t *__restrict__ hist, int n_blocks)
+{
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const int i = blockIdx.x * GT + threadIdx.x;
+	if (i < n)
+		atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+	__syncthreads();
+	hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of a u32 array in place (single CTA; arrays here are <= 256 * n_blocks entries)
+__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *__restrict__ data, size_t len, uint32_t *total_out)
+{
+	__shared__ uint32_t warp_tot[32];
+	__shared__ uint32_t carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const size_t per = (len + 1023) / 1024;
+	const size_t lo = (size_t)tid * per, hi = lo + per < len ? lo + per : len;
+	uint32_t sum = 0;
+	for (size_t i = lo; i < hi; ++i)
+		sum += data[i];
+	uint32_t x = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+		if (lane >= o) x += y;
+	}
+	if (lane == 31)
+		warp_tot[warp] = x;
+	if (tid == 0)
+		carry = 0;
+	__syncthreads();
+	uint32_t before = 0;
+	for (int w = 0; w < warp; ++w)
+		before += warp_tot[w];
+	uint32_t run = before + x - sum;
+	for (size_t i = lo; i < hi; ++i)
+	{
+		const uint32_t v = data[i];
+		data[i] = run;
+		run += v;
+	}
+	if (tid == 1023 && total_out)
+		*total_out = before + x;
+}
+
+// stable scatter: rank inside the CTA = elements of the same digit at lower thread ids
+__global__ void __launch_bounds__(GT) k_radix_scatter(const unsigned long long *__restrict__ keys_in,
+                                                      const uint32_t *__restrict__ idx_in, int n, int shift,
+                                                      const uint32_t *__restrict__ hist_scanned, int n_blocks,
+                                                      unsigned long long *__restrict__ keys_out,
+                                                      uint32_t *__restrict__ idx_out)
+{
+	__shared__ uint32_t warp_digit_count[GT / 32][256];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (int j = tid; j < (GT / 32) * 256; j += GT)
+		(&warp_digit_count[0][0])[j] = 0;
+	__syncthreads();
+	const int i = blockIdx.x * GT + tid;
+	const bool ok = i < n;
+	unsigned long long key = 0;
+	uint32_t digit = 0;
+	if (ok)
+	{
+		key = keys_in[i];
+		digit = (uint32_t)(key >> shift) & 255u;
+	}
+	// peers in this warp with the same digit (inactive lanes use a digit no active lane can match)
+	const uint32_t peers = __match_any_sync(0xffffffffu, ok ? digit : 0x100u + lane);
+	const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+	if (ok && rank_in_warp == 0)
+		warp_digit_count[warp][digit] = __popc(peers);
+	__syncthreads();
+	if (ok)
+	{
+		uint32_t before = 0;
+		for (int w = 0; w < warp; ++w)
+			before += warp_digit_count[w][digit];
+		const uint32_t dst = hist_scanned[(size_t)digit * n_blocks + blockIdx.x] + before + rank_in_warp;
+		keys_out[dst] = key;
+		idx_out[dst] = idx_in[i];
+	}
+}
+
+// head flags of the sorted key array: flag[i] = key[i] != key[i-1]
+__global__ void __launch_bounds__(GT) k_grid_heads(const unsigned long long *__restrict__ sorted_keys, int n,
+                                                   uint32_t *__restrict__ flags)
+{
+	const int i = blockIdx.x * GT + threadIdx.x;
+	if (i < n)
+		flags[i] = (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ? 1u : 0u;
+}
+
+// flags_scanned[i] = index of the cell point i starts (for heads): write the offsets, terminate with n
+__global__ void __launch_bounds__(GT) k_grid_offsets(const unsigned long long *__restrict__ sorted_keys, int n,
+                                                     const uint32_t *__restrict__ flags_scanned,
+                                                     uint32_t *__restrict__ cell_offsets, const uint32_t *n_cells)
+{
+	const int i = blockIdx.x * GT + threadIdx.x;
+	if (i < n && (i == 0 || sorted_keys[i] != sorted_keys[i - 1]))
+		cell_offsets[flags_scanned[i]] = (uint32_t)i;
+	if (i == 0)
+		cell_offsets[*n_cells] = (uint32_t)n;
+}
+
+__global__ void __launch_bounds__(GT) k_grid_neighbors(const uint32_t *__restrict__ cell_offsets, const uint32_t *n_cells,
+                                                       unsigned long long *neighbor_number)
+{
+	const uint32_t c = blockIdx.x * GT + threadIdx.x;
+	unsigned long long mine = 0;
+	if (c < *n_cells)
+	{
+		const unsigned long long sz = cell_offsets[c + 1] - cell_offsets[c];
+		mine = sz * (sz - 1) / 2;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		mine += __shfl_xor_sync(0xffffffffu, mine, o);
+	if ((threadIdx.x & 31) == 0 && mine)
+		atomicAdd(neighbor_number, mine);
+}
+
+extern "C" gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell_sizes[4], uint64_t cells_per_axis,
+                                     uint64_t *d_keys, uint32_t *d_sorted_idx, uint32_t *d_cell_offsets, uint32_t *h_n_cells,
+                                     uint64_t *h_neighbor_number)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_grid_build: no points uploaded");
+	if (ctx->cols != 4)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_grid_build: the grid graph is defined on 4-column correspondences");
+	if (pair < 0 || pair >= ctx->n_pairs || !h_cell_sizes || cells_per_axis == 0 || !d_keys || !d_sorted_idx || !d_cell_offsets)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_grid_build: bad arguments");
+	for (int d = 0; d < 4; ++d)
+		if (!(h_cell_sizes[d] > 0.0))
+			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_grid_build: cell size %d must be positive", d);
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int n = ctx->n;
+	const int n_blocks = (n + GT - 1) / GT;
+	// scratch: keys_b | idx_a | idx_b | hist | flags | n_cells | neighbor_number
+	size_t off = 0;
+	auto take = [&](size_t bytes) {
+		const size_t o = off;
+		off += (bytes + 255) & ~(size_t)255;
+		return o;
+	};
+	const size_t o_keys_a = take((size_t)n * 8), o_keys_b = take((size_t)n * 8), o_idx_b = take((size_t)n * 4);
+	const size_t o_hist = take((size_t)256 * n_blocks * 4), o_flags = take((size_t)n * 4), o_small = take(64);
+	gcr_status st = gcr_ensure_scratch(ctx, off);
+	if (st)
+		return st;
+	char *base = (char *)ctx->d_scratch;
+	unsigned long long *keys_a = (unsigned long long *)(base + o_keys_a), *keys_b = (unsigned long long *)(base + o_keys_b);
+	uint32_t *idx_a = d_sorted_idx, *idx_b = (uint32_t *)(base + o_idx_b);
+	uint32_t *hist = (uint32_t *)(base + o_hist), *flags = (uint32_t *)(base + o_flags);
+	uint32_t *d_n_cells = (uint32_t *)(base + o_small);
+	unsigned long long *d_nn = (unsigned long long *)(base + o_small + 8);
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(base + o_small, 0, 64, ctx->stream));
+
+	const double *pts = ctx->d_pts64 + (size_t)pair * n * 4;
+	k_grid_keys<<<n_blocks, GT, 0, ctx->stream>>>(pts, n, h_cell_sizes[0], h_cell_sizes[1], h_cell_sizes[2], h_cell_sizes[3],
+	                                               cells_per_axis, (unsigned long long *)d_keys, idx_a,
+	                                               (unsigned long long *)(base + o_small + 16));
+	GCR_LAUNCHED(ctx);
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(keys_a, d_keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	// significant key bits decide the number of radix passes (keys of in-image points stay below C^4)
+	st = gcr_ensure_pinned(ctx, 64);
+	if (st)
+		return st;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, base + o_small + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	int key_bits = 1;
+	{
+		const unsigned long long any = *(unsigned long long *)ctx->h_pinned;
+		while (key_bits < 64 && (any >> key_bits) != 0)
+			++key_bits;
+	}
+	const int passes = (key_bits + 7) / 8;
+	unsigned long long *kin = keys_a, *kout = keys_b;
+	uint32_t *iin = idx_a, *iout = idx_b;
+	for (int p = 0; p < passes; ++p)
+	{
+		k_radix_hist<<<n_blocks, GT, 0, ctx->stream>>>(kin, n, 8 * p, hist, n_blocks);
+		GCR_LAUNCHED(ctx);
+		k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(hist, (size_t)256 * n_blocks, nullptr);
+		GCR_LAUNCHED(ctx);
+		k_radix_scatter<<<n_blocks, GT, 0, ctx->stream>>>(kin, iin, n, 8 * p, hist, n_blocks, kout, iout);
+		GCR_LAUNCHED(ctx);
+		unsigned long long *tk = kin; kin = kout; kout = tk;
+		uint32_t *ti = iin; iin = iout; iout = ti;
+	}
+	if (iin != d_sorted_idx)
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_sorted_idx, iin, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+	k_grid_heads<<<n_blocks, GT, 0, ctx->stream>>>(kin, n, flags);
+	GCR_LAUNCHED(ctx);
+	k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(flags, (size_t)n, d_n_cells);
+	GCR_LAUNCHED(ctx);
+	k_grid_offsets<<<n_blocks, GT, 0, ctx->stream>>>(kin, n, flags, d_cell_offsets, d_n_cells);
+	GCR_LAUNCHED(ctx);
+	k_grid_neighbors<<<n_blocks, GT, 0, ctx->stream>>>(d_cell_offsets, d_n_cells, d_nn);
+	GCR_LAUNCHED(ctx);
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, base + o_small, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (h_n_cells)
+		*h_n_cells = *(uint32_t *)ctx->h_pinned;
+	if (h_neighbor_number)
+		*h_neighbor_number = *(unsigned long long *)((char *)ctx->h_pinned + 8);
+	return GCR_OK;
+}

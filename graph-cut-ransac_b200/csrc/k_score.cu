@@ -3,30 +3,44 @@
 // MAGSACScoringFunction::getScore (:246-348) of the reference together with the estimators' squaredResidual
 // (homography_estimator.h:181-199, fundamental_estimator.h:195-222, perspective_n_point_estimator.h:148-184).
 //
-// Mapping (B200-first, not a translation of the reference's per-model point loop):
-//   * lane = hypothesis.  Each thread keeps R hypotheses in registers for the whole kernel (9 or 12 FP32 each,
-//     mapped into the centred/scaled coordinate frame of the FP32 point copy); all 32 lanes of a warp read the SAME
-//     point from shared memory (one broadcast LDS.128 per point), so there is no cross-lane reduction at all and no
-//     bank conflict; per-hypothesis (score, inliers) accumulate in registers and are written once.
-//   * point tiles (256 points, 4 KB / 8 KB) stream through a 4-stage shared-memory ring filled by 1-D bulk TMA
-//     (cp.async.bulk ... mbarrier::complete_tx), issued by one elected thread; consumers wait on the stage's mbarrier.
-//   * W = 2 variant: two hypotheses per thread are packed into f32x2 registers and evaluated with FFMA2 / FMUL2 /
-//     FADD2 (sm_100 packed FP32), reading an operand-duplicated point copy, which halves the issue slots per
-//     evaluation on the FMA pipe.
-//   * arithmetic is FP32 FMA + one MUFU.RCP per evaluation (projective divide / Sampson denominator): FP32-pipe
-//     bound, not a tensor-core contraction.
-//   * GCR_SCORE_EXACT_COUNTS: an evaluation whose |r^2 - t^2| falls inside the FP32 error band is re-evaluated in
-//     FP64 in the reference's operation order from the FP64 point/model copies (rare, divergent slow path), so inlier
-//     counts equal the FP64 reference's.
-//   * small K: the grid also splits the points into chunks (blockIdx.y) and a second tiny kernel adds the partials
-//     in a fixed order (deterministic; no float atomics).
+// Pipeline of one gcr_score() call (all on the context's stream, no host synchronisation):
+//   k_score_prepare   one thread per model slot: zero the slot's accumulators, append VALID slots to a per-pair compact
+//                     list (warp-aggregated atomics) and map their FP64 model into the centred / scaled FP32 frame of
+//                     the point copy.  Invalid slots (failed solver, oriented-constraint reject: ~90 % of 7-point
+//                     slots) never reach the scoring kernel.
+//   k_score_plan      one CTA: per-pair prefix of hypothesis tiles; picks how many point chunks each tile is split
+//                     into so that the persistent grid below has >= 2 work items per CTA.
+//   k_score_main      the hot kernel.  Persistent CTAs (128 threads) pull (pair, hypothesis tile, point chunk) items
+//                     from an atomic ticket.  lane = hypothesis: each thread keeps R hypotheses in registers for the
+//                     whole item, packed two-by-two into f32x2 registers and evaluated with FFMA2 / FMUL2 / FADD2
+//                     (sm_100 packed FP32: half the issue slots per evaluation, which leaves the issue port to the
+//                     MUFU.RCP, the min/compare/count work and the shared-memory loads).  All 32 lanes of a warp read
+//                     the SAME point (broadcast LDS.128 of an operand-duplicated copy), so there is no cross-lane
+//                     reduction and no bank conflict.  Point tiles (256 points, 8 KB) stream through a 4-stage
+//                     shared-memory ring filled by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) issued by one
+//                     elected thread.  Per-hypothesis (score, inliers) accumulate in registers (FP32, flushed per
+//                     tile into a second-level FP32 sum) and are added once per item to the slot's accumulators
+//                     as fixed-point int64 / uint32 atomics -- integer addition is associative, so the result does not
+//                     depend on the order in which chunks finish (deterministic, no float atomics).
+//   k_score_fixup     GCR_SCORE_EXACT_COUNTS: evaluations whose |r^2 - t^2| fell inside the FP32 error band were left
+//                     out by the hot kernel and appended to a work list; they are evaluated here in FP64 in the
+//                     reference's operation order, so inlier counts equal the FP64 reference's.
+//   k_score_finalize  accumulators -> float score / uint32 inliers per slot (-1 / 0 for invalid slots).
+//
+// Arithmetic is FP32 FMA + one MUFU.RCP per evaluation (projective divide / Sampson denominator): FP32-pipe bound,
+// not a tensor-core contraction.
 #include "gcr_internal.cuh"
 
 #include <math.h>
+#include <string.h>
 
 #define TILE 256
 #define STAGES 4
-#define THREADS 256
+#define THREADS 128
+#define WARPS (THREADS / 32)
+#define MAX_TILES_PER_CHUNK 64 /* bounds one FP32 second-level sum to 64 tile sums */
+#define AMB_CAPACITY (4u << 20)
+#define FIX_ONE 4294967296.0 /* 2^32: fixed-point unit of the score accumulators */
 
 // ------------------------------------------------------------------------------------------ mbarrier / TMA ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,16 +145,13 @@ __device__ __forceinline__ void normalise_model(const double *__restrict__ M, co
 		out[i] = (float)(B[i] * inv);
 }
 
-// squared-threshold in the primed frame and the FP32 error band around it
+// squared threshold in the primed frame and the FP32 error band around it
 struct Thresholds
 {
 	float negT;  // -(t'^2)
-	float band;  // |u| < band  => FP64 re-check (u = r'^2 - t'^2)
+	float band;  // |u| < band  => FP64 evaluation instead (u = r'^2 - t'^2)
 	float c_idx; // MAGSAC: 1e4 / (2 t'^2)
-	float invT;  // 1 / t'^2
-	double T64;  // pixel-frame squared threshold, as the reference computes it
-	double thr64;
-	double s2;   // s^2 (frame scale)
+	double scale; // FP32 partial sum -> fixed point: MSAC -2^32 / t'^2, MAGSAC 2^32
 };
 
 template <int PROBLEM, int SCORING>
@@ -156,109 +167,229 @@ __device__ __forceinline__ Thresholds make_thresholds(const double *nm, double t
 	}
 	else
 		T = thr * thr;
-	t.T64 = T;
-	t.thr64 = thr;
-	t.s2 = s * s;
 	const double Tp = T * s * s;
 	t.negT = -(float)Tp;
-	t.invT = (float)(1.0 / Tp);
 	t.c_idx = (float)(1e4 / (2.0 * Tp));
+	t.scale = SCORING == GCR_MSAC ? -FIX_ONE / Tp : FIX_ONE;
 	// |x'| <= 1 in the primed frame; delta_d ~ band_factor * eps32; |u| error ~ 2 t' delta_d + delta_d^2
 	const double dd = band_factor * 1.1920929e-7;
 	t.band = (float)(2.0 * sqrt(Tp) * dd + dd * dd);
 	return t;
 }
 
-// ------------------------------------------------------------------------------------ FP64 slow-path fix-up ---
-// Called for one (hypothesis, point) evaluation that landed inside the error band.  Removes the FP32 contribution
-// and adds the FP64 one (reference operation order).
-template <int PROBLEM, int SCORING>
-__device__ __noinline__ void exact_fixup(const double *__restrict__ pts64, const double *__restrict__ model64,
-                                         const Thresholds &th, const float *__restrict__ lut, float u, float w32,
-                                         float &S, uint32_t &cnt)
+// ------------------------------------------------------------------------------------------------ plumbing ----
+struct ScorePlan
 {
-	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
-	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
-	double pt[COLS], M[ML];
-	for (int i = 0; i < COLS; ++i)
-		pt[i] = pts64[i];
-	for (int i = 0; i < ML; ++i)
-		M[i] = model64[i];
-	const double r2 = gcr_sqres64<PROBLEM>(pt, M);
-	if (SCORING == GCR_MSAC)
-	{
-		if (u < 0.f)
-		{
-			S -= u;
-			cnt -= 1;
-		}
-		if (r2 < th.T64)
-		{
-			S += (float)((r2 - th.T64) * th.s2);
-			cnt += 1;
-		}
-	}
-	else
-	{
-		if (u <= 0.f)
-		{
-			S -= w32;
-			cnt -= 1;
-		}
-		const double residual = sqrt(r2);
-		if (!(residual > th.thr64))
-		{
-			const double squared_residual = residual * residual;
-			long long x = llround(1e4 * squared_residual / (th.thr64 * th.thr64 * 2.0));
-			if (x > 5000) x = 5000;
-			S += residual < 2.220446049250313e-16 ? 1.0f : lut[x];
-			cnt += 1;
-		}
-	}
-}
+	uint32_t ticket;      // next work item (persistent scheduler)
+	uint32_t amb_count;   // entries appended to the FP64 work list
+	uint32_t amb_dropped; // entries that did not fit (reported through gcr_counters_read)
+	uint32_t total_items, n_chunks, tiles_per_chunk;
+	uint32_t pad[2];
+};
 
-// --------------------------------------------------------------------------------------------- the kernel ----
 struct ScoreArgs
 {
-	const float4 *pts32;
+	// inputs
+	const float4 *pts32; // [n_pairs][n_pad][2] operand-duplicated (PnP: (u v 0 0)(X Y Z 0))
 	const double *pts64;
-	const double *models;
-	const uint8_t *valid;
-	const double *norm;
-	const float *lut;
+	const double *models; // [n_pairs][k][ML]
+	const uint8_t *valid; // [n_pairs][k] or null
+	const double *norm;   // [n_pairs][8]
+	const float *lut;     // MAGSAC FP32 weight table
+	const double *lut64;  // MAGSAC Gamma(1.5, j/1000)
+	// workspace
+	uint32_t *counts;        // [n_pairs] valid models per pair
+	uint32_t *prefix;        // [n_pairs + 1] hypothesis tiles before pair p
+	ScorePlan *plan;
+	uint32_t *slots;         // [n_pairs][k] compact list -> slot
+	float *m32;              // [n_pairs][k][ML] normalised FP32 models, compact order
+	unsigned long long *accS; // [n_pairs][k] fixed-point score accumulators (by slot)
+	uint32_t *accC;          // [n_pairs][k] inlier counters (by slot)
+	unsigned long long *amb; // [AMB_CAPACITY] (global slot << 32) | point index
+	unsigned long long *counters;
+	// outputs
 	float *scores;
 	uint32_t *inliers;
-	float *part_scores;  // [n_chunks][n_pairs][k]
-	uint32_t *part_inl;
 	int n, n_pad, k, n_pairs;
-	int tiles_per_chunk, n_chunks;
+	int hyps_per_item, grid;
 	double thr;
 	float band_factor;
 };
 
-// W = 1: scalar FP32, point tile = float4 (x1 y1 x2 y2) [PnP: 2 x float4]
-// W = 2: packed f32x2, point tile = 2 x float4 (x1 x1 y1 y1)(x2 x2 y2 y2); hypotheses 2r and 2r+1 share registers
-template <int PROBLEM, int SCORING, int R, int W, bool EXACT>
-__global__ void __launch_bounds__(THREADS, (R * (PROBLEM == GCR_PNP ? 12 : 9) > 40) ? 2 : 3) k_score(const ScoreArgs a)
+// ------------------------------------------------------------------------------------------------- prepare ----
+template <int PROBLEM>
+__global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
 {
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
-	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
-	constexpr int F4 = (W == 2 || PROBLEM == GCR_PNP) ? 2 : 1; // float4 per point in the tile
-	constexpr uint32_t TILE_BYTES = TILE * F4 * sizeof(float4);
-	static_assert(W == 1 || (R % 2 == 0 && PROBLEM != GCR_PNP), "packed variant needs an even R and 4-column data");
+	const int pair = blockIdx.y;
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t g = (size_t)pair * a.k + slot;
+	const bool in_range = slot < a.k;
+	const bool ok = in_range && (a.valid == nullptr || a.valid[g] != 0);
+	if (in_range)
+	{
+		a.accS[g] = 0ull;
+		a.accC[g] = 0u;
+	}
+	const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+	if (ballot == 0u)
+		return;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(ballot) - 1)
+		base = atomicAdd(&a.counts[pair], (uint32_t)__popc(ballot));
+	base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+	if (!ok)
+		return;
+	const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+	a.slots[(size_t)pair * a.k + pos] = (uint32_t)slot;
+	float m[ML];
+	normalise_model<PROBLEM>(a.models + g * ML, a.norm + (size_t)pair * 8, m);
+	float *o = a.m32 + ((size_t)pair * a.k + pos) * ML;
+#pragma unroll
+	for (int j = 0; j < ML; ++j)
+		o[j] = m[j];
+}
+
+// ---------------------------------------------------------------------------------------------------- plan ----
+__global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
+{
+	__shared__ uint32_t warp_tot[32];
+	__shared__ uint32_t carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0)
+		carry = 0;
+	__syncthreads();
+	for (int base = 0; base < a.n_pairs; base += 1024)
+	{
+		const int p = base + tid;
+		const uint32_t tiles = p < a.n_pairs ? (a.counts[p] + a.hyps_per_item - 1) / a.hyps_per_item : 0u;
+		uint32_t x = tiles;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31)
+			warp_tot[warp] = x;
+		__syncthreads();
+		uint32_t before = carry;
+		for (int w = 0; w < warp; ++w)
+			before += warp_tot[w];
+		if (p < a.n_pairs)
+			a.prefix[p] = before + x - tiles; // exclusive
+		__syncthreads();
+		if (tid == 1023)
+			carry = before + x;
+		__syncthreads();
+	}
+	if (tid == 0)
+	{
+		const uint32_t total_tiles = carry;
+		a.prefix[a.n_pairs] = total_tiles;
+		const uint32_t n_point_tiles = (uint32_t)(a.n_pad / TILE);
+		uint32_t n_chunks = 1;
+		if (total_tiles > 0 && total_tiles < 2u * a.grid)
+			n_chunks = (2u * a.grid + total_tiles - 1) / total_tiles;
+		const uint32_t min_chunks = (n_point_tiles + MAX_TILES_PER_CHUNK - 1) / MAX_TILES_PER_CHUNK;
+		if (n_chunks < min_chunks) n_chunks = min_chunks;
+		if (n_chunks > n_point_tiles) n_chunks = n_point_tiles;
+		const uint32_t tpc = (n_point_tiles + n_chunks - 1) / n_chunks;
+		n_chunks = (n_point_tiles + tpc - 1) / tpc;
+		a.plan->tiles_per_chunk = tpc;
+		a.plan->n_chunks = n_chunks;
+		a.plan->total_items = total_tiles * n_chunks;
+	}
+}
+
+// ----------------------------------------------------------------------------------- per-evaluation maths ----
+// u = r'^2 - t'^2 (MSAC) or r'^2 (MAGSAC) for two hypotheses side by side; point operands are duplicated pairs
+template <int PROBLEM, int SCORING>
+__device__ __forceinline__ float2 eval2(const float2 (&h)[9], const float2 X1, const float2 Y1, const float2 X2,
+                                        const float2 Y2, const float2 NEGT)
+{
+	if (PROBLEM == GCR_H)
+	{
+		const float2 t1 = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
+		const float2 t2 = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
+		const float2 t3 = __ffma2_rn(h[6], X1, __ffma2_rn(h[7], Y1, h[8]));
+		const float2 inv = make_float2(rcp_approx(t3.x), rcp_approx(t3.y));
+		// the caller hands over -x2, -y2 (negated once per point), so d = t/t3 - x2 is one FMA
+		const float2 d1 = __ffma2_rn(t1, inv, X2);
+		const float2 d2 = __ffma2_rn(t2, inv, Y2);
+		if (SCORING == GCR_MSAC)
+			return __ffma2_rn(d2, d2, __ffma2_rn(d1, d1, NEGT));
+		return __ffma2_rn(d2, d2, __fmul2_rn(d1, d1));
+	}
+	else
+	{
+		const float2 rxc = __ffma2_rn(h[0], X2, __ffma2_rn(h[3], Y2, h[6]));
+		const float2 ryc = __ffma2_rn(h[1], X2, __ffma2_rn(h[4], Y2, h[7]));
+		const float2 rwc = __ffma2_rn(h[2], X2, __ffma2_rn(h[5], Y2, h[8]));
+		const float2 rr = __ffma2_rn(X1, rxc, __ffma2_rn(Y1, ryc, rwc));
+		const float2 rx = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
+		const float2 ry = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
+		const float2 den = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, __ffma2_rn(ryc, ryc, __fmul2_rn(rxc, rxc))));
+		const float2 inv = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+		const float2 rr2 = __fmul2_rn(rr, rr);
+		if (SCORING == GCR_MSAC)
+			return __ffma2_rn(rr2, inv, NEGT);
+		return __fmul2_rn(rr2, inv);
+	}
+}
+
+// PnP, scalar: point = (u' v' . .)(X' Y' Z' .)
+template <int SCORING>
+__device__ __forceinline__ float eval_pnp(const float (&h)[12], const float4 qa, const float4 qb, const float negT)
+{
+	const float px = fmaf(h[0], qb.x, fmaf(h[1], qb.y, fmaf(h[2], qb.z, h[3])));
+	const float py = fmaf(h[4], qb.x, fmaf(h[5], qb.y, fmaf(h[6], qb.z, h[7])));
+	const float pz = fmaf(h[8], qb.x, fmaf(h[9], qb.y, fmaf(h[10], qb.z, h[11])));
+	const float inv = rcp_approx(pz);
+	const float du = fmaf(px, inv, -qa.x);
+	const float dv = fmaf(py, inv, -qa.y);
+	if (SCORING == GCR_MSAC)
+		return fmaf(dv, dv, fmaf(du, du, negT));
+	return fmaf(dv, dv, du * du);
+}
+
+// MAGSAC weight of one evaluation: LUT index with the reference's integer rounding (scoring_function.h:320-331)
+__device__ __forceinline__ float magsac_weight(const float *s_lut, float r2, float c_idx)
+{
+	// round-to-nearest via the 1.5 * 2^23 trick (FMA pipe + one integer subtract instead of F2I on the XU pipe)
+	const float t = fmaf(r2, c_idx, 12582912.0f);
+	const uint32_t idx = min((uint32_t)(__float_as_int(t) - 0x4B400000), 5000u);
+	return s_lut[idx];
+}
+
+__device__ __forceinline__ void amb_record(const ScoreArgs &a, size_t gslot, int pidx)
+{
+	const uint32_t pos = atomicAdd(&a.plan->amb_count, 1u);
+	if (pos < AMB_CAPACITY)
+		a.amb[pos] = ((unsigned long long)gslot << 32) | (unsigned long long)(uint32_t)pidx;
+	else
+		atomicAdd(&a.plan->amb_dropped, 1u);
+}
+
+// --------------------------------------------------------------------------------------------- the kernel ----
+template <int PROBLEM, int SCORING, int R, bool EXACT>
+__global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_score_main(const ScoreArgs a)
+{
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	constexpr bool PACKED = PROBLEM != GCR_PNP;
+	constexpr int NQ = PACKED ? R / 2 : R; // register groups per thread
+	constexpr int HQ = PACKED ? 2 : 1;     // hypotheses per group
+	constexpr uint32_t TILE_BYTES = TILE * 2 * sizeof(float4);
+	static_assert(!PACKED || R % 2 == 0, "packed variant needs an even R");
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	float4(*tiles)[TILE * F4] = reinterpret_cast<float4(*)[TILE * F4]>(smem_raw);
+	float4(*tiles)[TILE * 2] = reinterpret_cast<float4(*)[TILE * 2]>(smem_raw);
 	uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TILE_BYTES);
+	uint32_t *s_item = reinterpret_cast<uint32_t *>(smem_raw + STAGES * TILE_BYTES + 8 * STAGES);
 	float *s_lut = reinterpret_cast<float *>(smem_raw + STAGES * TILE_BYTES + 64);
 
-	const int pair = blockIdx.z, chunk = blockIdx.y, tid = threadIdx.x;
-	const int tile0 = chunk * a.tiles_per_chunk;
-	const int n_tiles_total = a.n_pad / TILE;
-	int my_tiles = n_tiles_total - tile0;
-	if (my_tiles > a.tiles_per_chunk) my_tiles = a.tiles_per_chunk;
-	const float4 *src = a.pts32 + ((size_t)pair * a.n_pad + (size_t)tile0 * TILE) * F4;
-
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0)
 	{
 #pragma unroll
@@ -269,292 +400,335 @@ __global__ void __launch_bounds__(THREADS, (R * (PROBLEM == GCR_PNP ? 12 : 9) > 
 	if (SCORING == GCR_MAGSAC)
 		for (int i = tid; i < 5001; i += THREADS)
 			s_lut[i] = a.lut[i];
-	__syncthreads();
-	if (tid == 0)
-	{
-#pragma unroll
-		for (int s = 0; s < STAGES; ++s)
-			if (s < my_tiles)
-			{
-				mbar_expect_tx(&full_bar[s], TILE_BYTES);
-				tma_load_1d(&tiles[s][0], src + (size_t)s * TILE * F4, TILE_BYTES, &full_bar[s]);
-			}
-	}
 
-	// ---- prologue: this thread's R hypotheses, mapped to the primed frame ----
-	const double *nm = a.norm + (size_t)pair * 8;
-	const Thresholds th = make_thresholds<PROBLEM, SCORING>(nm, a.thr, a.band_factor);
-	const int hyp_base = blockIdx.x * (THREADS * R);
-	float m[R][ML];
-	bool present[R];
-#pragma unroll
-	for (int r = 0; r < R; ++r)
+	const uint32_t total_items = a.plan->total_items, n_chunks = a.plan->n_chunks, tiles_per_chunk = a.plan->tiles_per_chunk;
+	const int n_tiles_total = a.n_pad / TILE;
+	uint32_t ring = 0; // tiles this CTA has consumed so far: stage = ring % STAGES, parity = (ring / STAGES) & 1
+
+	for (;;)
 	{
-		const int h = hyp_base + r * THREADS + tid;
-		present[r] = h < a.k && (a.valid == nullptr || a.valid[(size_t)pair * a.k + h] != 0);
-		if (h < a.k)
-			normalise_model<PROBLEM>(a.models + ((size_t)pair * a.k + h) * ML, nm, m[r]);
-		else
+		__syncthreads(); // everyone is done with the previous item's stages and with s_item
+		if (tid == 0)
+			*s_item = atomicAdd(&a.plan->ticket, 1u);
+		__syncthreads();
+		const uint32_t item = *s_item;
+		if (item >= total_items)
+			break;
+		const uint32_t chunk = item % n_chunks, ht = item / n_chunks;
+		int lo = 0, hi = a.n_pairs; // prefix[lo] <= ht < prefix[hi]
+		while (hi - lo > 1)
 		{
-#pragma unroll
-			for (int j = 0; j < ML; ++j)
-				m[r][j] = __int_as_float(0x7fc00000);
+			const int mid = (lo + hi) >> 1;
+			if (a.prefix[mid] <= ht) lo = mid;
+			else hi = mid;
 		}
-	}
-	float S[R];
-	uint32_t cnt[R];
-#pragma unroll
-	for (int r = 0; r < R; ++r)
-	{
-		S[r] = 0.f;
-		cnt[r] = 0;
-	}
-
-	// ---- main loop over point tiles ----
-	for (int t = 0; t < my_tiles; ++t)
-	{
-		const int stage = t % STAGES;
-		mbar_wait(&full_bar[stage], (uint32_t)((t / STAGES) & 1));
-		const float4 *tp = &tiles[stage][0];
-#pragma unroll 2
-		for (int i = 0; i < TILE; ++i)
+		const int pair = lo;
+		const int count = (int)a.counts[pair];
+		const int tile0 = (int)(chunk * tiles_per_chunk);
+		int my_tiles = n_tiles_total - tile0;
+		if (my_tiles > (int)tiles_per_chunk) my_tiles = (int)tiles_per_chunk;
+		const float4 *src = a.pts32 + ((size_t)pair * a.n_pad + (size_t)tile0 * TILE) * 2;
+		if (tid == 0)
 		{
-			float u[R], w[R];
-			bool amb = false;
-			if (W == 1)
+#pragma unroll
+			for (int s = 0; s < STAGES; ++s)
+				if (s < my_tiles)
+				{
+					const uint32_t st = (ring + s) % STAGES;
+					mbar_expect_tx(&full_bar[st], TILE_BYTES);
+					tma_load_1d(&tiles[st][0], src + (size_t)s * TILE * 2, TILE_BYTES, &full_bar[st]);
+				}
+		}
+
+		// ---- prologue: this thread's R hypotheses (compact order; hypothesis = lane within a warp's block) ----
+		const double *nm = a.norm + (size_t)pair * 8;
+		const Thresholds th = make_thresholds<PROBLEM, SCORING>(nm, a.thr, a.band_factor);
+		const int hyp0 = (int)(ht - a.prefix[pair]) * (THREADS * R) + warp * (32 * R) + lane; // + 32 * (HQ * q + e)
+		const float *mbase = a.m32 + (size_t)pair * a.k * ML;
+		// warps whose block of 32 R hypotheses lies beyond the pair's list idle through the item; inside an active warp
+		// every register group is evaluated (absent hypotheses are NaN models and contribute nothing), which keeps the
+		// 2 NQ evaluation chains of an unrolled iteration in ONE basic block for the scheduler to interleave
+		const int nq_active = (hyp0 - lane) < count ? NQ : 0;
+
+		float2 h2[PACKED ? NQ : 1][9];
+		float h1[PACKED ? 1 : NQ][12];
+		const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+		for (int q = 0; q < NQ; ++q)
+		{
+			if (PACKED)
 			{
-				float x1, y1, x2, y2, z3 = 0.f;
-				if (PROBLEM == GCR_PNP)
+				const int ja = hyp0 + 32 * (2 * q), jb = ja + 32;
+#pragma unroll
+				for (int j = 0; j < 9; ++j)
+				{
+					h2[q][j].x = ja < count ? mbase[(size_t)ja * 9 + j] : qnan;
+					h2[q][j].y = jb < count ? mbase[(size_t)jb * 9 + j] : qnan;
+				}
+			}
+			else
+			{
+				const int ja = hyp0 + 32 * q;
+#pragma unroll
+				for (int j = 0; j < 12; ++j)
+					h1[q][j] = ja < count ? mbase[(size_t)ja * 12 + j] : qnan;
+			}
+		}
+		float2 S2[PACKED ? NQ : 1], T2[PACKED ? NQ : 1];
+		float S1[PACKED ? 1 : NQ], T1[PACKED ? 1 : NQ];
+		uint32_t cnt[R];
+#pragma unroll
+		for (int q = 0; q < NQ; ++q)
+		{
+			if (PACKED) S2[q] = make_float2(0.f, 0.f), T2[q] = make_float2(0.f, 0.f);
+			else S1[q] = 0.f, T1[q] = 0.f;
+		}
+#pragma unroll
+		for (int r = 0; r < R; ++r)
+			cnt[r] = 0;
+		const float2 NEGT = make_float2(th.negT, th.negT);
+
+		// ---- main loop over this item's point tiles ----
+		for (int t = 0; t < my_tiles; ++t)
+		{
+			const uint32_t st = (ring + t) % STAGES;
+			mbar_wait(&full_bar[st], ((ring + t) / STAGES) & 1u);
+			const float4 *tp = &tiles[st][0];
+			if (nq_active > 0)
+			{
+#pragma unroll 2
+				for (int i = 0; i < TILE; ++i)
 				{
 					const float4 qa = tp[2 * i], qb = tp[2 * i + 1];
-					x1 = qa.x; y1 = qa.y; x2 = qb.x; y2 = qb.y; z3 = qb.z; // (u v) (X Y Z)
-				}
-				else
-				{
-					const float4 q = tp[i];
-					x1 = q.x; y1 = q.y; x2 = q.z; y2 = q.w;
-				}
+					float mn = 3.0e38f; // min |u| over this thread's evaluations of the point (EXACT)
+					// H evaluates d = t/t3 - x2: negate the second-image operands once per point
+					const float sg = PROBLEM == GCR_H ? -1.f : 1.f;
+					const float2 X1 = make_float2(qa.x, qa.y), Y1 = make_float2(qa.z, qa.w);
+					const float2 X2 = make_float2(sg * qb.x, sg * qb.y), Y2 = make_float2(sg * qb.z, sg * qb.w);
+					if (PACKED)
+					{
 #pragma unroll
-				for (int r = 0; r < R; ++r)
-				{
-					const float *h = m[r];
-					float r2;
-					if (PROBLEM == GCR_H)
-					{
-						const float t1 = fmaf(h[0], x1, fmaf(h[1], y1, h[2]));
-						const float t2 = fmaf(h[3], x1, fmaf(h[4], y1, h[5]));
-						const float t3 = fmaf(h[6], x1, fmaf(h[7], y1, h[8]));
-						const float inv = rcp_approx(t3);
-						const float d1 = fmaf(t1, inv, -x2);
-						const float d2 = fmaf(t2, inv, -y2);
-						if (SCORING == GCR_MSAC)
-							u[r] = fmaf(d2, d2, fmaf(d1, d1, th.negT));
-						else
-							r2 = fmaf(d2, d2, d1 * d1);
-					}
-					else if (PROBLEM == GCR_PNP)
-					{
-						const float px = fmaf(h[0], x2, fmaf(h[1], y2, fmaf(h[2], z3, h[3])));
-						const float py = fmaf(h[4], x2, fmaf(h[5], y2, fmaf(h[6], z3, h[7])));
-						const float pz = fmaf(h[8], x2, fmaf(h[9], y2, fmaf(h[10], z3, h[11])));
-						const float inv = rcp_approx(pz);
-						const float du = fmaf(px, inv, -x1);
-						const float dv = fmaf(py, inv, -y1);
-						if (SCORING == GCR_MSAC)
-							u[r] = fmaf(dv, dv, fmaf(du, du, th.negT));
-						else
-							r2 = fmaf(dv, dv, du * du);
-					}
-					else
-					{
-						const float rxc = fmaf(h[0], x2, fmaf(h[3], y2, h[6]));
-						const float ryc = fmaf(h[1], x2, fmaf(h[4], y2, h[7]));
-						const float rwc = fmaf(h[2], x2, fmaf(h[5], y2, h[8]));
-						const float rr = fmaf(x1, rxc, fmaf(y1, ryc, rwc));
-						const float rx = fmaf(h[0], x1, fmaf(h[1], y1, h[2]));
-						const float ry = fmaf(h[3], x1, fmaf(h[4], y1, h[5]));
-						const float den = fmaf(ry, ry, fmaf(rx, rx, fmaf(ryc, ryc, rxc * rxc)));
-						const float inv = rcp_approx(den);
-						if (SCORING == GCR_MSAC)
-							u[r] = fmaf(rr * rr, inv, th.negT);
-						else
-							r2 = rr * rr * inv;
-					}
-					if (SCORING == GCR_MSAC)
-					{
-						S[r] += fminf(u[r], 0.f);
-						cnt[r] += __float_as_uint(u[r]) >> 31; // u < 0 (generated NaNs are the positive canonical NaN)
-					}
-					else
-					{
-						u[r] = r2 + th.negT;
-						int idx = __float2int_rn(r2 * th.c_idx);
-						idx = min(max(idx, 0), 5000);
-						const float wv = s_lut[idx];
-						const bool in = u[r] <= 0.f;
-						w[r] = in ? wv : 0.f;
-						S[r] += w[r];
-						cnt[r] += in ? 1u : 0u;
-					}
-					if (EXACT)
-						amb |= fabsf(u[r]) < th.band;
-				}
-			}
-			else // W == 2: packed f32x2
-			{
-				const float4 qa = tp[2 * i], qb = tp[2 * i + 1];
-				const float2 X1 = make_float2(qa.x, qa.y), Y1 = make_float2(qa.z, qa.w);
-				const float2 X2 = make_float2(qb.x, qb.y), Y2 = make_float2(qb.z, qb.w);
-				const float2 NEGT = make_float2(th.negT, th.negT);
-#pragma unroll
-				for (int r = 0; r < R; r += 2)
-				{
-					// hypotheses r and r+1 side by side
-					float2 h[9];
-#pragma unroll
-					for (int j = 0; j < 9; ++j)
-						h[j] = make_float2(m[r][j], m[r + 1][j]);
-					float2 uu, r2v;
-					if (PROBLEM == GCR_H)
-					{
-						const float2 t1 = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
-						const float2 t2 = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
-						const float2 t3 = __ffma2_rn(h[6], X1, __ffma2_rn(h[7], Y1, h[8]));
-						const float2 inv = make_float2(rcp_approx(t3.x), rcp_approx(t3.y));
-						// the duplicated copy stores x2, y2 (positive); d = x2 - t/t3 = fma(-t, inv, x2): use
-						// nd = fma(t, inv, -x2) via the negated constants below
-						const float2 d1 = __ffma2_rn(t1, inv, make_float2(-X2.x, -X2.y));
-						const float2 d2 = __ffma2_rn(t2, inv, make_float2(-Y2.x, -Y2.y));
-						if (SCORING == GCR_MSAC)
-							uu = __ffma2_rn(d2, d2, __ffma2_rn(d1, d1, NEGT));
-						else
-							r2v = __ffma2_rn(d2, d2, __fmul2_rn(d1, d1));
-					}
-					else
-					{
-						const float2 rxc = __ffma2_rn(h[0], X2, __ffma2_rn(h[3], Y2, h[6]));
-						const float2 ryc = __ffma2_rn(h[1], X2, __ffma2_rn(h[4], Y2, h[7]));
-						const float2 rwc = __ffma2_rn(h[2], X2, __ffma2_rn(h[5], Y2, h[8]));
-						const float2 rr = __ffma2_rn(X1, rxc, __ffma2_rn(Y1, ryc, rwc));
-						const float2 rx = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
-						const float2 ry = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
-						const float2 den = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, __ffma2_rn(ryc, ryc, __fmul2_rn(rxc, rxc))));
-						const float2 inv = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-						const float2 rr2 = __fmul2_rn(rr, rr);
-						if (SCORING == GCR_MSAC)
-							uu = __ffma2_rn(rr2, inv, NEGT);
-						else
-							r2v = __fmul2_rn(rr2, inv);
-					}
-					if (SCORING == GCR_MSAC)
-					{
-						u[r] = uu.x;
-						u[r + 1] = uu.y;
-						const float2 acc = __fadd2_rn(make_float2(S[r], S[r + 1]), make_float2(fminf(uu.x, 0.f), fminf(uu.y, 0.f)));
-						S[r] = acc.x;
-						S[r + 1] = acc.y;
-						cnt[r] += __float_as_uint(uu.x) >> 31;
-						cnt[r + 1] += __float_as_uint(uu.y) >> 31;
-					}
-					else
-					{
-						const float rs[2] = {r2v.x, r2v.y};
-#pragma unroll
-						for (int e = 0; e < 2; ++e)
+						for (int q = 0; q < NQ; ++q)
 						{
-							u[r + e] = rs[e] + th.negT;
-							int idx = __float2int_rn(rs[e] * th.c_idx);
-							idx = min(max(idx, 0), 5000);
-							const float wv = s_lut[idx];
-							const bool in = u[r + e] <= 0.f;
-							w[r + e] = in ? wv : 0.f;
-							S[r + e] += w[r + e];
-							cnt[r + e] += in ? 1u : 0u;
+							{
+								const float2 v = eval2<PROBLEM, SCORING>(h2[q], X1, Y1, X2, Y2, NEGT);
+								if (SCORING == GCR_MSAC)
+								{
+									T2[q] = __fadd2_rn(T2[q], make_float2(fminf(v.x, 0.f), fminf(v.y, 0.f)));
+									cnt[2 * q] += __float_as_uint(v.x) >> 31; // u < 0 (generated NaNs are the positive canonical NaN)
+									cnt[2 * q + 1] += __float_as_uint(v.y) >> 31;
+									if (EXACT) mn = fminf(mn, fminf(fabsf(v.x), fabsf(v.y)));
+								}
+								else
+								{
+									const float ux = v.x + th.negT, uy = v.y + th.negT;
+									const float wx = magsac_weight(s_lut, v.x, th.c_idx), wy = magsac_weight(s_lut, v.y, th.c_idx);
+									const bool inx = ux <= 0.f, iny = uy <= 0.f;
+									T2[q] = __fadd2_rn(T2[q], make_float2(inx ? wx : 0.f, iny ? wy : 0.f));
+									cnt[2 * q] += inx ? 1u : 0u;
+									cnt[2 * q + 1] += iny ? 1u : 0u;
+									if (EXACT) mn = fminf(mn, fminf(fabsf(ux), fabsf(uy)));
+								}
+							}
 						}
 					}
-					if (EXACT)
-						amb |= (fabsf(u[r]) < th.band) | (fabsf(u[r + 1]) < th.band);
-				}
-			}
-			if (EXACT && amb)
-			{
-				const int pidx = (tile0 + t) * TILE + i;
+					else
+					{
 #pragma unroll
-				for (int r = 0; r < R; ++r)
+						for (int q = 0; q < NQ; ++q)
+						{
+							{
+								const float v = eval_pnp<SCORING>(h1[q], qa, qb, th.negT);
+								if (SCORING == GCR_MSAC)
+								{
+									T1[q] += fminf(v, 0.f);
+									cnt[q] += __float_as_uint(v) >> 31;
+									if (EXACT) mn = fminf(mn, fabsf(v));
+								}
+								else
+								{
+									const float u = v + th.negT;
+									const float w = magsac_weight(s_lut, v, th.c_idx);
+									const bool in = u <= 0.f;
+									T1[q] += in ? w : 0.f;
+									cnt[q] += in ? 1u : 0u;
+									if (EXACT) mn = fminf(mn, fabsf(u));
+								}
+							}
+						}
+					}
+					if (EXACT && mn < th.band)
+					{
+						// rare: take the FP32 contribution of every in-band evaluation back out and queue it for FP64.
+						// Recomputing v here gives the same bits as above (same instructions on the same operands).
+						const int pidx = (tile0 + t) * TILE + i;
+#pragma unroll
+						for (int q = 0; q < NQ; ++q)
+						{
+							float vv[2];
+							if (PACKED)
+							{
+								const float2 v = eval2<PROBLEM, SCORING>(h2[q], X1, Y1, X2, Y2, NEGT);
+								vv[0] = v.x;
+								vv[1] = v.y;
+							}
+							else
+								vv[0] = vv[1] = eval_pnp<SCORING>(h1[q], qa, qb, th.negT);
+#pragma unroll
+							for (int e = 0; e < HQ; ++e)
+							{
+								const float u = SCORING == GCR_MSAC ? vv[e] : vv[e] + th.negT;
+								const int j = hyp0 + 32 * (HQ * q + e);
+								if (q < nq_active && fabsf(u) < th.band && j < count && pidx < a.n)
+								{
+									float back;
+									uint32_t was_in;
+									if (SCORING == GCR_MSAC)
+									{
+										back = fminf(u, 0.f);
+										was_in = __float_as_uint(u) >> 31;
+									}
+									else
+									{
+										was_in = u <= 0.f ? 1u : 0u;
+										back = was_in ? magsac_weight(s_lut, vv[e], th.c_idx) : 0.f;
+									}
+									if (PACKED)
+									{
+										if (e == 0) T2[q].x -= back;
+										else T2[q].y -= back;
+									}
+									else
+										T1[q] -= back;
+									cnt[HQ * q + e] -= was_in;
+									amb_record(a, (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j], pidx);
+								}
+							}
+						}
+					}
+				}
+				// second-level sum: one rounding per tile instead of one per point on the long accumulator
+#pragma unroll
+				for (int q = 0; q < NQ; ++q)
 				{
-					const int h = hyp_base + r * THREADS + tid;
-					if (fabsf(u[r]) < th.band && h < a.k && pidx < a.n)
-						exact_fixup<PROBLEM, SCORING>(a.pts64 + ((size_t)pair * a.n + pidx) * COLS,
-						                              a.models + ((size_t)pair * a.k + h) * ML, th,
-						                              SCORING == GCR_MAGSAC ? s_lut : nullptr, u[r],
-						                              SCORING == GCR_MAGSAC ? w[r] : 0.f, S[r], cnt[r]);
+					if (PACKED)
+					{
+						S2[q] = __fadd2_rn(S2[q], T2[q]);
+						T2[q] = make_float2(0.f, 0.f);
+					}
+					else
+					{
+						S1[q] += T1[q];
+						T1[q] = 0.f;
+					}
 				}
 			}
+			__syncthreads(); // everyone is done with this stage -> refill it
+			if (tid == 0 && t + STAGES < my_tiles)
+			{
+				mbar_expect_tx(&full_bar[st], TILE_BYTES);
+				tma_load_1d(&tiles[st][0], src + (size_t)(t + STAGES) * TILE * 2, TILE_BYTES, &full_bar[st]);
+			}
 		}
-		__syncthreads(); // everyone is done with this stage -> refill it
-		if (tid == 0 && t + STAGES < my_tiles)
-		{
-			mbar_expect_tx(&full_bar[stage], TILE_BYTES);
-			tma_load_1d(&tiles[stage][0], src + (size_t)(t + STAGES) * TILE * F4, TILE_BYTES, &full_bar[stage]);
-		}
-	}
+		ring += (uint32_t)my_tiles;
 
-	// ---- epilogue ----
+		// ---- epilogue: fixed-point accumulate into the slot ----
 #pragma unroll
-	for (int r = 0; r < R; ++r)
+		for (int q = 0; q < NQ; ++q)
+#pragma unroll
+			for (int e = 0; e < HQ; ++e)
+			{
+				const int j = hyp0 + 32 * (HQ * q + e);
+				if (j < count)
+				{
+					const float S = PACKED ? (e == 0 ? S2[q].x : S2[q].y) : S1[q];
+					const size_t g = (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j];
+					const long long fx = __double2ll_rn((double)S * th.scale);
+					if (fx != 0)
+						atomicAdd(&a.accS[g], (unsigned long long)fx);
+					if (cnt[HQ * q + e] != 0)
+						atomicAdd(&a.accC[g], cnt[HQ * q + e]);
+				}
+			}
+	}
+}
+
+// ------------------------------------------------------------------------------------ FP64 slow-path fix-up ---
+template <int PROBLEM, int SCORING>
+__global__ void __launch_bounds__(256) k_score_fixup(const ScoreArgs a)
+{
+	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	uint32_t total = a.plan->amb_count;
+	if (total > AMB_CAPACITY) total = AMB_CAPACITY;
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
 	{
-		const int h = hyp_base + r * THREADS + tid;
-		if (h >= a.k)
-			continue;
-		if (a.n_chunks == 1)
+		const unsigned long long ent = a.amb[e];
+		const size_t g = (size_t)(ent >> 32);
+		const uint32_t pidx = (uint32_t)(ent & 0xffffffffull);
+		const size_t pair = g / (size_t)a.k;
+		double pt[COLS], M[ML];
+		const double *p = a.pts64 + (pair * a.n + pidx) * COLS;
+		for (int i = 0; i < COLS; ++i) pt[i] = p[i];
+		for (int i = 0; i < ML; ++i) M[i] = a.models[g * ML + i];
+		const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+		if (SCORING == GCR_MSAC)
 		{
-			float score;
-			if (!present[r])
-				score = -1.f, cnt[r] = 0;
-			else if (SCORING == GCR_MSAC)
-				score = cnt[r] == 0 ? 0.f : -S[r] * th.invT; // scoring_function.h:221-229
-			else
-				score = S[r];
-			a.scores[(size_t)pair * a.k + h] = score;
-			if (a.inliers)
-				a.inliers[(size_t)pair * a.k + h] = cnt[r];
+			const double truncated_threshold = 3.0 / 2.0 * a.thr;
+			const double T = truncated_threshold * truncated_threshold;
+			if (r2 < T) // scoring_function.h:163
+			{
+				atomicAdd(&a.accS[g], (unsigned long long)__double2ll_rn((T - r2) / T * FIX_ONE));
+				atomicAdd(&a.accC[g], 1u);
+			}
 		}
 		else
 		{
-			const size_t o = ((size_t)chunk * a.n_pairs + pair) * a.k + h;
-			a.part_scores[o] = S[r];
-			a.part_inl[o] = cnt[r];
+			const double residual = sqrt(r2);
+			if (!(residual > a.thr)) // scoring_function.h:304
+			{
+				double w = 1.0; // weight / weight_zero
+				if (!(residual < 2.220446049250313e-16))
+				{
+					const double squared_residual = residual * residual;
+					unsigned long long x = (unsigned long long)round(1e4 * squared_residual / (a.thr * a.thr * 2.0));
+					if (x > 5000) x = 5000;
+					const double gamma_k = 0.0036572608340910764;
+					w = (a.lut64[x] - gamma_k) / (0.88622692545275801365 - gamma_k);
+				}
+				atomicAdd(&a.accS[g], (unsigned long long)__double2ll_rn(w * FIX_ONE));
+				atomicAdd(&a.accC[g], 1u);
+			}
 		}
 	}
 }
 
-template <int PROBLEM, int SCORING>
-__global__ void k_score_reduce(const ScoreArgs a)
+// ------------------------------------------------------------------------------------------------ finalize ----
+template <int SCORING>
+__global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 {
 	const int pair = blockIdx.y;
-	const int h = blockIdx.x * blockDim.x + threadIdx.x;
-	if (h >= a.k)
-		return;
-	float S = 0.f;
-	uint32_t c = 0;
-	for (int ch = 0; ch < a.n_chunks; ++ch)
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot == 0 && pair == 0 && a.plan->amb_count)
 	{
-		const size_t o = ((size_t)ch * a.n_pairs + pair) * a.k + h;
-		S += a.part_scores[o];
-		c += a.part_inl[o];
+		atomicAdd(&a.counters[1], (unsigned long long)a.plan->amb_dropped);
+		atomicAdd(&a.counters[2], (unsigned long long)a.plan->amb_count);
 	}
-	const Thresholds th = make_thresholds<PROBLEM, SCORING>(a.norm + (size_t)pair * 8, a.thr, a.band_factor);
-	const bool present = a.valid == nullptr || a.valid[(size_t)pair * a.k + h] != 0;
+	if (slot >= a.k)
+		return;
+	const size_t g = (size_t)pair * a.k + slot;
+	const bool present = a.valid == nullptr || a.valid[g] != 0;
+	const uint32_t c = a.accC[g];
 	float score;
 	if (!present)
-		score = -1.f, c = 0;
-	else if (SCORING == GCR_MSAC)
-		score = c == 0 ? 0.f : -S * th.invT;
+		score = -1.f;
+	else if (SCORING == GCR_MSAC && c == 0)
+		score = 0.f; // scoring_function.h:221-222
 	else
-		score = S;
-	a.scores[(size_t)pair * a.k + h] = score;
+		score = (float)((double)(long long)a.accS[g] * (1.0 / FIX_ONE));
+	a.scores[g] = score;
 	if (a.inliers)
-		a.inliers[(size_t)pair * a.k + h] = c;
+		a.inliers[g] = present ? c : 0u;
 }
 
 // ----------------------------------------------------------------------------------------------- dispatch ----
@@ -573,85 +747,110 @@ __global__ void k_fill_lut(float *lut)
 
 static gcr_status ensure_lut(gcr_ctx *ctx)
 {
-	if (ctx->d_magsac_lut)
-		return GCR_OK;
+	gcr_status st = gcr_ensure_magsac_lut64(ctx);
+	if (st || ctx->d_magsac_lut)
+		return st;
 	GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_magsac_lut, 5008 * sizeof(float)));
 	k_fill_lut<<<(5001 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_magsac_lut);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }
 
-template <int PROBLEM, int SCORING, int R, int W>
+// workspace carve-up (one allocation, grown on demand)
+static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
+{
+	const size_t PK = (size_t)a.n_pairs * a.k;
+	size_t off = 0;
+	auto take = [&](size_t bytes) {
+		const size_t o = off;
+		off += (bytes + 255) & ~(size_t)255;
+		return o;
+	};
+	const size_t o_head = take(sizeof(ScorePlan) + (size_t)a.n_pairs * sizeof(uint32_t)); // plan | counts: one memset
+	const size_t o_prefix = take(((size_t)a.n_pairs + 1) * sizeof(uint32_t));
+	const size_t o_slots = take(PK * sizeof(uint32_t));
+	const size_t o_m32 = take(PK * ml * sizeof(float));
+	const size_t o_accS = take(PK * sizeof(unsigned long long));
+	const size_t o_accC = take(PK * sizeof(uint32_t));
+	const size_t o_amb = take((size_t)AMB_CAPACITY * sizeof(unsigned long long));
+	if (off > ctx->score_ws_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_score_ws);
+		ctx->d_score_ws = nullptr;
+		ctx->score_ws_capacity = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_score_ws, off));
+		ctx->score_ws_capacity = off;
+	}
+	char *base = (char *)ctx->d_score_ws;
+	a.plan = (ScorePlan *)(base + o_head);
+	a.counts = (uint32_t *)(base + o_head + sizeof(ScorePlan));
+	a.prefix = (uint32_t *)(base + o_prefix);
+	a.slots = (uint32_t *)(base + o_slots);
+	a.m32 = (float *)(base + o_m32);
+	a.accS = (unsigned long long *)(base + o_accS);
+	a.accC = (uint32_t *)(base + o_accC);
+	a.amb = (unsigned long long *)(base + o_amb);
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(base + o_head, 0, sizeof(ScorePlan) + (size_t)a.n_pairs * sizeof(uint32_t), ctx->stream));
+	return GCR_OK;
+}
+
+template <int PROBLEM, int SCORING, int R>
 static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 {
-	const int hyp_tiles = (a.k + THREADS * R - 1) / (THREADS * R);
-	const int n_tiles = a.n_pad / TILE;
-	// fill the machine: aim for >= 2 CTAs per SM slot; split the points when K alone cannot do it
-	const long long ctas = (long long)hyp_tiles * a.n_pairs;
-	const long long target = 2ll * 3 * ctx->sm_count;
-	int n_chunks = 1;
-	if (ctas < target)
-	{
-		n_chunks = (int)((target + ctas - 1) / ctas);
-		if (n_chunks > n_tiles) n_chunks = n_tiles;
-		if (n_chunks > 64) n_chunks = 64;
-	}
-	a.tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
-	a.n_chunks = (n_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
-	if (a.n_chunks > 1)
-	{
-		const size_t per = (size_t)a.n_chunks * a.n_pairs * a.k;
-		gcr_status st = gcr_ensure_scratch(ctx, per * (sizeof(float) + sizeof(uint32_t)) + 256);
-		if (st)
-			return st;
-		a.part_scores = (float *)ctx->d_scratch;
-		a.part_inl = (uint32_t *)((char *)ctx->d_scratch + ((per * sizeof(float) + 255) & ~(size_t)255));
-	}
-	a.pts32 = (W == 2) ? ctx->d_pts32dup : ctx->d_pts32;
-	const dim3 grid(hyp_tiles, a.n_chunks, a.n_pairs);
-	constexpr int F4 = (W == 2 || PROBLEM == GCR_PNP) ? 2 : 1;
-	const size_t smem = (size_t)STAGES * TILE * F4 * sizeof(float4) + 64 + (SCORING == GCR_MAGSAC ? 5008 * sizeof(float) : 0);
-	gcr_status pst = gcr_profile_begin(ctx);
-	if (pst)
-		return pst;
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	gcr_status st = ensure_score_ws(ctx, a, ML);
+	if (st)
+		return st;
+	a.hyps_per_item = THREADS * R;
+	const size_t smem = (size_t)STAGES * TILE * 2 * sizeof(float4) + 64 + (SCORING == GCR_MAGSAC ? 5008 * sizeof(float) : 0);
+	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true> : k_score_main<PROBLEM, SCORING, R, false>;
+	GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+	if (per_sm < 1)
+		GCR_FAIL(ctx, GCR_ERR_CUDA, "gcr_score: scoring kernel does not fit on an SM");
+	a.grid = per_sm * ctx->sm_count;
+
+	const dim3 gslots((a.k + 255) / 256, a.n_pairs);
+	k_score_prepare<PROBLEM><<<gslots, 256, 0, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
+	k_score_plan<<<1, 1024, 0, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
+	st = gcr_profile_begin(ctx);
+	if (st)
+		return st;
+	kern<<<a.grid, THREADS, smem, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
+	st = gcr_profile_end(ctx, (uint64_t)a.k * a.n_pairs * a.n);
+	if (st)
+		return st;
 	if (exact)
 	{
-		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_score<PROBLEM, SCORING, R, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_score<PROBLEM, SCORING, R, W, true><<<grid, THREADS, smem, ctx->stream>>>(a);
-	}
-	else
-	{
-		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_score<PROBLEM, SCORING, R, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_score<PROBLEM, SCORING, R, W, false><<<grid, THREADS, smem, ctx->stream>>>(a);
-	}
-	GCR_LAUNCHED(ctx);
-	pst = gcr_profile_end(ctx, (uint64_t)a.k * a.n_pairs * a.n);
-	if (pst)
-		return pst;
-	if (a.n_chunks > 1)
-	{
-		const dim3 g2((a.k + 255) / 256, a.n_pairs);
-		k_score_reduce<PROBLEM, SCORING><<<g2, 256, 0, ctx->stream>>>(a);
+		k_score_fixup<PROBLEM, SCORING><<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(a);
 		GCR_LAUNCHED(ctx);
 	}
+	k_score_finalize<SCORING><<<gslots, 256, 0, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }
 
 template <int PROBLEM, int SCORING>
 static gcr_status launch_problem(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 {
-	// variants: 0 = scalar R4, 1 = scalar R8, 2 = packed R4, 3 = packed R8 (PnP: scalar only)
-	int v = ctx->score_variant;
-	if (PROBLEM == GCR_PNP)
-		return launch_variant<PROBLEM, SCORING, 2, 1>(ctx, a, exact);
-	if (v < 0)
-		v = 2;
-	switch (v)
+	// variants: hypotheses per thread (PnP is scalar: 2 or 4; the packed problems take 4, 6 or 8)
+	const int v = ctx->score_variant;
+	if constexpr (PROBLEM == GCR_PNP)
+		return v == 1 ? launch_variant<PROBLEM, SCORING, 4>(ctx, a, exact) : launch_variant<PROBLEM, SCORING, 2>(ctx, a, exact);
+	else
 	{
-	case 0: return launch_variant<PROBLEM, SCORING, 4, 1>(ctx, a, exact);
-	case 1: return launch_variant<PROBLEM, SCORING, 8, 1>(ctx, a, exact);
-	case 3: return launch_variant < PROBLEM, SCORING, 8, PROBLEM == GCR_PNP ? 1 : 2 > (ctx, a, exact);
-	default: return launch_variant < PROBLEM, SCORING, 4, PROBLEM == GCR_PNP ? 1 : 2 > (ctx, a, exact);
+		switch (v)
+		{
+		case 0: return launch_variant<PROBLEM, SCORING, 4>(ctx, a, exact);
+		case 1: return launch_variant<PROBLEM, SCORING, 6>(ctx, a, exact);
+		case 2: return launch_variant<PROBLEM, SCORING, 8>(ctx, a, exact);
+		default: return launch_variant<PROBLEM, SCORING, 4>(ctx, a, exact);
+		}
 	}
 }
 
@@ -670,6 +869,8 @@ extern "C" gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const do
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score: need models, scores, k > 0 and threshold > 0");
 	if (ctx->n_pairs > 65535)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score: at most 65535 pairs per context");
+	if ((unsigned long long)ctx->n_pairs * (unsigned long long)k >= (1ull << 32))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score: n_pairs * k must stay below 2^32 model slots per call");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (scoring == GCR_MAGSAC)
 	{
@@ -678,22 +879,21 @@ extern "C" gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const do
 			return st;
 	}
 	ScoreArgs a;
-	a.pts32 = nullptr;
+	memset(&a, 0, sizeof(a));
+	a.pts32 = ctx->d_pts32;
 	a.pts64 = ctx->d_pts64;
 	a.models = d_models;
 	a.valid = d_valid;
 	a.norm = ctx->d_norm;
 	a.lut = ctx->d_magsac_lut;
+	a.lut64 = ctx->d_magsac_lut64;
+	a.counters = ctx->d_counters;
 	a.scores = d_scores;
 	a.inliers = d_inliers;
-	a.part_scores = nullptr;
-	a.part_inl = nullptr;
 	a.n = ctx->n;
 	a.n_pad = ctx->n_pad;
 	a.k = k;
 	a.n_pairs = ctx->n_pairs;
-	a.tiles_per_chunk = 0;
-	a.n_chunks = 1;
 	a.thr = threshold;
 	a.band_factor = (float)ctx->band_factor;
 	const bool exact = (flags & GCR_SCORE_EXACT_COUNTS) != 0;

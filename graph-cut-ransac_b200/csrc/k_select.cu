@@ -89,6 +89,186 @@ extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 	return GCR_OK;
 }
 
+// ------------------------------------------------------------------------------- exact winner selection ---
+// The FP32 scores of K3 rank the hypotheses, but FP32 cannot separate two models whose scores differ by less than its
+// own error (~2e-5 relative for Sampson: the model coefficients themselves are rounded to FP32).  gcr_round therefore
+// keeps, per pair, the best FP32 key of each of SEL_BUCKETS index classes (slot % SEL_BUCKETS; max is order-independent,
+// so this is deterministic), re-scores in FP64 -- reference operation order per point -- every bucket winner within
+// SEL_MARGIN of the best, and picks the winner by (FP64 score, lowest index): the strict '<' first-wins rule of
+// GCRANSAC.h:440 evaluated in the reference's precision.
+#define SEL_BUCKETS 64
+#define SEL_MARGIN 2e-4f
+#define SEL_THREADS 256
+
+__global__ void __launch_bounds__(256) k_bucket_argmax(const float *__restrict__ scores, int k, uint32_t index_base,
+                                                       unsigned long long *__restrict__ buckets)
+{
+	__shared__ unsigned long long sb[SEL_BUCKETS];
+	const int pair = blockIdx.y;
+	if (threadIdx.x < SEL_BUCKETS)
+		sb[threadIdx.x] = 0ull;
+	__syncthreads();
+	const float *s = scores + (size_t)pair * k;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
+	{
+		const float v = s[i];
+		if (v > 0.f)
+		{
+			const unsigned long long key = ((unsigned long long)gcr_ordered_u32(v) << 32) |
+			                               (unsigned long long)(0xFFFFFFFFu - ((uint32_t)i + index_base));
+			atomicMax(&sb[i % SEL_BUCKETS], key);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < SEL_BUCKETS && sb[threadIdx.x])
+		atomicMax(&buckets[(size_t)pair * SEL_BUCKETS + threadIdx.x], sb[threadIdx.x]);
+}
+
+struct SelectArgs
+{
+	const double *pts; // [n_pairs][n][cols]
+	const double *models; // [n_pairs][k][ML]
+	const double *lut64;
+	const unsigned long long *buckets; // [n_pairs][SEL_BUCKETS]
+	unsigned long long *keys;          // [n_pairs]
+	double *best_models;               // [n_pairs][ML] or null
+	double *best_scores;               // [n_pairs] or null (FP64 score of the winner)
+	uint32_t *best_counts;             // [n_pairs] or null (exact inlier count of the winner)
+	int n, k;
+	uint32_t index_base;
+	double thr;
+};
+
+template <int PROBLEM, int SCORING>
+__global__ void __launch_bounds__(SEL_THREADS) k_select_exact(const SelectArgs a)
+{
+	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	__shared__ unsigned long long s_keys[SEL_BUCKETS];
+	__shared__ int s_cand[SEL_BUCKETS];
+	__shared__ int s_ncand;
+	__shared__ double s_model[ML];
+	__shared__ double warp_sum[SEL_THREADS / 32];
+	__shared__ uint32_t warp_cnt[SEL_THREADS / 32];
+	__shared__ double s_best_score;
+	__shared__ uint32_t s_best_slot, s_best_count;
+	const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < SEL_BUCKETS)
+		s_keys[tid] = a.buckets[(size_t)pair * SEL_BUCKETS + tid];
+	__syncthreads();
+	if (tid == 0)
+	{
+		unsigned long long best = 0ull;
+		for (int b = 0; b < SEL_BUCKETS; ++b)
+			if (s_keys[b] > best) best = s_keys[b];
+		int nc = 0;
+		if (best)
+		{
+			const float top = gcr_from_ordered_u32((uint32_t)(best >> 32));
+			const float floor_score = top - SEL_MARGIN * top;
+			for (int b = 0; b < SEL_BUCKETS; ++b)
+				if (s_keys[b] && gcr_from_ordered_u32((uint32_t)(s_keys[b] >> 32)) >= floor_score)
+					s_cand[nc++] = b;
+		}
+		s_ncand = nc;
+		s_best_score = -1.0;
+		s_best_slot = 0xFFFFFFFFu;
+		s_best_count = 0;
+	}
+	__syncthreads();
+	const double *P = a.pts + (size_t)pair * a.n * COLS;
+	// thresholds / MAGSAC constants exactly as the reference forms them (GCRANSAC.h:253-254, scoring_function.h:257-296)
+	const double truncated_threshold = 3.0 / 2.0 * a.thr;
+	const double T = truncated_threshold * truncated_threshold;
+	const double gamma_k = 0.0036572608340910764;
+	const double gamma_difference = 0.88622692545275801365 - gamma_k;
+	const double one_over_sigma = 0.25 * 2.8284271247461903 / a.thr;
+	const double weight_zero = one_over_sigma * gamma_difference;
+	const double squared_sigma_max_2 = a.thr * a.thr * 2.0;
+	for (int c = 0; c < s_ncand; ++c)
+	{
+		const uint32_t gidx = 0xFFFFFFFFu - (uint32_t)(s_keys[s_cand[c]] & 0xFFFFFFFFull);
+		const uint32_t slot = gidx - a.index_base;
+		if (tid < ML)
+			s_model[tid] = a.models[((size_t)pair * a.k + slot) * ML + tid];
+		__syncthreads();
+		double M[ML];
+		for (int j = 0; j < ML; ++j) M[j] = s_model[j];
+		double sum = 0.0;
+		uint32_t cnt = 0;
+		for (int i = tid; i < a.n; i += SEL_THREADS)
+		{
+			double pt[COLS];
+			for (int j = 0; j < COLS; ++j) pt[j] = P[(size_t)i * COLS + j];
+			const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+			if (SCORING == GCR_MSAC)
+			{
+				if (r2 < T) { sum -= r2; ++cnt; }
+			}
+			else
+			{
+				const double residual = sqrt(r2);
+				if (!(residual > a.thr))
+				{
+					double weight;
+					if (residual < 2.220446049250313e-16)
+						weight = weight_zero;
+					else
+					{
+						const double squared_residual = residual * residual;
+						unsigned long long x = (unsigned long long)round(1e4 * squared_residual / squared_sigma_max_2);
+						if (x > 5000) x = 5000;
+						weight = one_over_sigma * (a.lut64[x] - gamma_k);
+					}
+					sum += weight / weight_zero;
+					++cnt;
+				}
+			}
+		}
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			sum += __shfl_xor_sync(0xffffffffu, sum, o);
+			cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+		}
+		if (lane == 0) { warp_sum[warp] = sum; warp_cnt[warp] = cnt; }
+		__syncthreads();
+		if (tid == 0)
+		{
+			double value = 0.0;
+			uint32_t inl = 0;
+			for (int w = 0; w < SEL_THREADS / 32; ++w) { value += warp_sum[w]; inl += warp_cnt[w]; }
+			const double score = SCORING == GCR_MSAC ? (inl == 0 ? 0.0 : (value + inl * T) / T) : value;
+			if (score > s_best_score || (score == s_best_score && gidx < s_best_slot))
+			{
+				s_best_score = score;
+				s_best_slot = gidx;
+				s_best_count = inl;
+			}
+		}
+		__syncthreads();
+	}
+	if (s_ncand == 0)
+	{
+		if (tid == 0)
+		{
+			a.keys[pair] = 0ull;
+			if (a.best_scores) a.best_scores[pair] = 0.0;
+			if (a.best_counts) a.best_counts[pair] = 0;
+		}
+		if (a.best_models && tid < ML)
+			a.best_models[(size_t)pair * ML + tid] = 0.0;
+		return;
+	}
+	if (tid == 0)
+	{
+		a.keys[pair] = ((unsigned long long)gcr_ordered_u32((float)s_best_score) << 32) | (unsigned long long)(0xFFFFFFFFu - s_best_slot);
+		if (a.best_scores) a.best_scores[pair] = s_best_score;
+		if (a.best_counts) a.best_counts[pair] = s_best_count;
+	}
+	if (a.best_models && tid < ML)
+		a.best_models[(size_t)pair * ML + tid] = a.models[((size_t)pair * a.k + (s_best_slot - a.index_base)) * ML + tid];
+}
+
 // ------------------------------------------------------------------------------------------------ gcr_round ---
 extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
                                 uint64_t seed, double threshold, int flags, uint32_t index_base, uint64_t *d_keys,
@@ -115,6 +295,9 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	const size_t o_models = take(P * K * ml * sizeof(double));
 	const size_t o_valid = take(P * K);
 	const size_t o_scores = take(P * K * sizeof(float));
+	const size_t o_buckets = take(P * SEL_BUCKETS * sizeof(unsigned long long));
+	const size_t o_best_scores = take(P * sizeof(double));
+	const size_t o_best_counts = take(P * sizeof(uint32_t));
 	if (off > ctx->round_capacity)
 	{
 		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -136,15 +319,64 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	if (st) return st;
 	st = gcr_score(ctx, problem, scoring, d_models, d_valid, (int)K, threshold, flags, d_scores, nullptr);
 	if (st) return st;
-	st = gcr_argmax(ctx, d_scores, (int)K, index_base, d_keys);
-	if (st) return st;
-	if (d_best_models)
+	// K4: FP32 ranking -> bucket winners -> FP64 re-score of the near-best -> winner (see k_select_exact)
+	unsigned long long *d_buckets = (unsigned long long *)(base + o_buckets);
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_buckets, 0, P * SEL_BUCKETS * sizeof(unsigned long long), ctx->stream));
 	{
-		k_gather_best<<<(ctx->n_pairs + 127) / 128, 128, 0, ctx->stream>>>((const unsigned long long *)d_keys, index_base,
-		                                                                 d_models, (int)K, ml, d_best_models, ctx->n_pairs);
+		int gx = (int)((K + 255) / 256);
+		const int cap = ctx->n_pairs >= 2 * ctx->sm_count ? 1 : (4 * ctx->sm_count + ctx->n_pairs - 1) / ctx->n_pairs;
+		if (gx > cap) gx = cap;
+		k_bucket_argmax<<<dim3(gx, ctx->n_pairs), 256, 0, ctx->stream>>>(d_scores, (int)K, index_base, d_buckets);
 		GCR_LAUNCHED(ctx);
 	}
+	if (scoring == GCR_MAGSAC)
+	{
+		st = gcr_ensure_magsac_lut64(ctx);
+		if (st) return st;
+	}
+	SelectArgs sa;
+	sa.pts = ctx->d_pts64;
+	sa.models = d_models;
+	sa.lut64 = ctx->d_magsac_lut64;
+	sa.buckets = d_buckets;
+	sa.keys = (unsigned long long *)d_keys;
+	sa.best_models = d_best_models;
+	sa.best_scores = (double *)(base + o_best_scores);
+	sa.best_counts = (uint32_t *)(base + o_best_counts);
+	sa.n = ctx->n;
+	sa.k = (int)K;
+	sa.index_base = index_base;
+	sa.thr = threshold;
+#define GCR_SEL(PR)                                                                                          \
+	do                                                                                                       \
+	{                                                                                                        \
+		if (scoring == GCR_MSAC)                                                                             \
+			k_select_exact<PR, GCR_MSAC><<<ctx->n_pairs, SEL_THREADS, 0, ctx->stream>>>(sa);                  \
+		else                                                                                                 \
+			k_select_exact<PR, GCR_MAGSAC><<<ctx->n_pairs, SEL_THREADS, 0, ctx->stream>>>(sa);                \
+	} while (0)
+	if (problem == GCR_H) GCR_SEL(GCR_H);
+	else if (problem == GCR_PNP) GCR_SEL(GCR_PNP);
+	else GCR_SEL(GCR_F);
+#undef GCR_SEL
+	GCR_LAUNCHED(ctx);
+	ctx->d_round_best_scores = sa.best_scores;
+	ctx->d_round_best_counts = sa.best_counts;
 	if (evals_out)
 		*evals_out = (uint64_t)P * K * (uint64_t)ctx->n;
 	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_round_results(gcr_ctx *ctx, double *h_best_scores, uint32_t *h_best_counts)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_round_best_scores)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_round_results: no round has run on this context");
+	gcr_status st = GCR_OK;
+	if (h_best_scores)
+		st = gcr_memcpy_d2h(ctx, h_best_scores, ctx->d_round_best_scores, (size_t)ctx->n_pairs * sizeof(double));
+	if (!st && h_best_counts)
+		st = gcr_memcpy_d2h(ctx, h_best_counts, ctx->d_round_best_counts, (size_t)ctx->n_pairs * sizeof(uint32_t));
+	return st;
 }

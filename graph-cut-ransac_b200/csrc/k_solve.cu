@@ -167,39 +167,64 @@ __global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts
 }
 
 // ---------------------------------------------------------------------------------------------------- F7 ----
-__global__ void __launch_bounds__(128) k_solve_f7(const double *__restrict__ pts, int n,
-                                                  const uint32_t *__restrict__ samples, int count,
-                                                  double *__restrict__ models, uint8_t *__restrict__ valid,
-                                                  unsigned long long *__restrict__ counters)
+#define F7_THREADS 64
+#define F7_SMEM (81 * F7_THREADS * sizeof(double))
+
+struct SamplePoints // sample point i, column c, straight from the (L2-resident) FP64 point array
 {
+	const double *P;
+	const uint32_t *s;
+	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 4 + c]; }
+};
+
+__global__ void __launch_bounds__(F7_THREADS) k_solve_f7(const double *__restrict__ pts, int n,
+                                                         const uint32_t *__restrict__ samples, int count,
+                                                         double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                         unsigned long long *__restrict__ counters)
+{
+	extern __shared__ double f7_smem[];
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
 	const int pair = blockIdx.y;
-	const double *P = pts + (size_t)pair * n * 4;
-	const uint32_t *s = samples + ((size_t)pair * count + i) * 7;
-	double pt[7][4];
-	for (int j = 0; j < 7; ++j)
-	{
-		const double *p = P + (size_t)s[j] * 4;
-		pt[j][0] = p[0]; pt[j][1] = p[1]; pt[j][2] = p[2]; pt[j][3] = p[3];
-	}
-	double F[3][9];
-	const int nm = gcr_f7::solve(&pt[0][0], &F[0][0]);
-	double *out = models + ((size_t)pair * count + i) * 27;
-	uint8_t *v = valid + ((size_t)pair * count + i) * 3;
 	uint32_t n_ok = 0;
-	for (int mdl = 0; mdl < 3; ++mdl)
+	if (i < count)
 	{
-		bool ok = mdl < nm;
-		if (ok)
-			ok = gcr_f7::orientation_valid(F[mdl], &pt[0][0], 7); // fundamental_estimator.h:175-180
-		for (int j = 0; j < 9; ++j)
-			out[mdl * 9 + j] = ok ? F[mdl][j] : 0.0;
-		v[mdl] = ok ? 1 : 0;
-		n_ok += ok ? 1u : 0u;
+		uint32_t sidx[7];
+		const uint32_t *s = samples + ((size_t)pair * count + i) * 7;
+#pragma unroll
+		for (int j = 0; j < 7; ++j)
+			sidx[j] = s[j];
+		const SamplePoints pt{pts + (size_t)pair * n * 4, sidx};
+		const gcr_f7::SmemMat A{f7_smem + threadIdx.x, F7_THREADS};
+		double f1[9], f2[9], roots[3];
+		const int nr = gcr_f7::solve(pt, A, f1, f2, roots);
+		double *out = models + ((size_t)pair * count + i) * 27;
+		uint8_t *v = valid + ((size_t)pair * count + i) * 3;
+		// model slot = root index (ascending roots); a root the reference skips (|s| <= eps) leaves its slot invalid
+#pragma unroll
+		for (int mdl = 0; mdl < 3; ++mdl)
+		{
+			double F[9];
+			bool ok = mdl < nr && gcr_f7::model(f1, f2, roots[mdl], F);
+			if (ok)
+				ok = gcr_f7::orientation_valid(F, pt, 7); // fundamental_estimator.h:175-180
+#pragma unroll
+			for (int j = 0; j < 9; ++j)
+				out[mdl * 9 + j] = ok ? F[j] : 0.0;
+			v[mdl] = ok ? 1 : 0;
+			n_ok += ok ? 1u : 0u;
+		}
 	}
-	count_valid(counters, n_ok);
+	// valid-model counter: block reduction through shared memory (the matrix space is free again)
+	__syncthreads();
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(f7_smem);
+	if (threadIdx.x == 0)
+		cnt[0] = 0;
+	__syncthreads();
+	if (n_ok)
+		atomicAdd(&cnt[0], n_ok);
+	__syncthreads();
+	if (threadIdx.x == 0 && cnt[0])
+		atomicAdd(&counters[0], (unsigned long long)cnt[0]);
 }
 
 extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
@@ -221,7 +246,9 @@ extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_
 		k_solve_h4<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_F:
-		k_solve_f7<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SMEM));
+		k_solve_f7<<<dim3((count + F7_THREADS - 1) / F7_THREADS, ctx->n_pairs), F7_THREADS, F7_SMEM, ctx->stream>>>(
+		    ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
 		break;
 	default:
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: solver for problem %d is not built yet", problem);

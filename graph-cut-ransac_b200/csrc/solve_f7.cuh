@@ -82,77 +82,116 @@ namespace gcr_f7
 		return n;
 	}
 
-	// pt: 7 x 4 (x0 y0 x1 y1), F: up to 3 x 9; returns the number of models
-	__device__ inline int solve(const double *pt, double *F)
+	// The 7 x 9 epipolar matrix lives in SHARED memory, one column of doubles per thread (element e of thread t at
+	// base[e * stride + t]): the full-pivot LU indexes rows / columns by data-dependent pivots, which in registers
+	// would mean local memory (measured: 984 B stack per thread and 0.45 ms for 262144 samples; HBM/L2-bound spills).
+	// 81 doubles per thread: 63 for the matrix, 18 for the two null vectors.
+	struct SmemMat
+	{
+		double *base; // already offset by the thread index
+		int stride;   // threads per CTA
+		__device__ __forceinline__ double &operator()(int i, int j) const { return base[(i * 9 + j) * stride]; }
+		__device__ __forceinline__ double &f(int which, int j) const { return base[(63 + which * 9 + j) * stride]; }
+	};
+
+	// pt(i, c): sample point i, column c (x0 y0 x1 y1).  Returns the number of real roots (0..3, ascending) of
+	// det(lambda f1 + (1 - lambda) f2) = 0 together with the two null vectors (f1 already holds f1 - f2, :190);
+	// model(f1, f2, root, F) turns one root into a matrix.
+	template <class PointFn>
+	__device__ inline int solve(const PointFn &pt, const SmemMat &A, double *f1, double *f2, double *roots)
 	{
 		const double eps = 2.220446049250313e-16;
-		double A[7][9];
+#pragma unroll
 		for (int i = 0; i < 7; ++i)
 		{
-			const double x0 = pt[4 * i], y0 = pt[4 * i + 1], x1 = pt[4 * i + 2], y1 = pt[4 * i + 3];
-			A[i][0] = x1 * x0; A[i][1] = x1 * y0; A[i][2] = x1;
-			A[i][3] = y1 * x0; A[i][4] = y1 * y0; A[i][5] = y1;
-			A[i][6] = x0; A[i][7] = y0; A[i][8] = 1;
+			const double x0 = pt(i, 0), y0 = pt(i, 1), x1 = pt(i, 2), y1 = pt(i, 3);
+			A(i, 0) = x1 * x0; A(i, 1) = x1 * y0; A(i, 2) = x1;
+			A(i, 3) = y1 * x0; A(i, 4) = y1 * y0; A(i, 5) = y1;
+			A(i, 6) = x0; A(i, 7) = y0; A(i, 8) = 1;
 		}
-		int colperm[9];
-		for (int j = 0; j < 9; ++j)
-			colperm[j] = j;
+		unsigned long long colperm = 0x876543210ull; // nibble j = original column now at position j
 		double maxpivot = 0.0;
 		int nonzero = 7;
+#pragma unroll
 		for (int k = 0; k < 7; ++k)
 		{
-			int pr = k, pc = k;
-			double biggest = 0.0;
-			for (int j = k; j < 9; ++j) // column-major search like Eigen's maxCoeff on a column-major block
-				for (int i = k; i < 7; ++i)
+			if (k < nonzero)
+			{
+				int pr = k, pc = k;
+				double biggest = 0.0;
+#pragma unroll
+				for (int j = k; j < 9; ++j) // column-major search like Eigen's maxCoeff on a column-major block
+#pragma unroll
+					for (int i = k; i < 7; ++i)
+					{
+						const double a = fabs(A(i, j));
+						if (a > biggest) { biggest = a; pr = i; pc = j; }
+					}
+				if (biggest == 0.0)
+					nonzero = k;
+				else
 				{
-					const double a = fabs(A[i][j]);
-					if (a > biggest) { biggest = a; pr = i; pc = j; }
+					if (biggest > maxpivot) maxpivot = biggest;
+					if (pr != k)
+#pragma unroll
+						for (int j = 0; j < 9; ++j) { const double t = A(k, j); A(k, j) = A(pr, j); A(pr, j) = t; }
+					if (pc != k)
+					{
+#pragma unroll
+						for (int i = 0; i < 7; ++i) { const double t = A(i, k); A(i, k) = A(i, pc); A(i, pc) = t; }
+						const unsigned long long a = (colperm >> (4 * k)) & 15ull, b = (colperm >> (4 * pc)) & 15ull;
+						colperm &= ~((15ull << (4 * k)) | (15ull << (4 * pc)));
+						colperm |= (b << (4 * k)) | (a << (4 * pc));
+					}
+					const double piv = A(k, k);
+					double rowk[9];
+#pragma unroll
+					for (int j = k + 1; j < 9; ++j) rowk[j] = A(k, j);
+#pragma unroll
+					for (int i = k + 1; i < 7; ++i)
+					{
+						const double f = A(i, k) / piv;
+						A(i, k) = f;
+#pragma unroll
+						for (int j = k + 1; j < 9; ++j)
+							A(i, j) -= f * rowk[j];
+					}
 				}
-			if (biggest == 0.0) { nonzero = k; break; }
-			if (biggest > maxpivot) maxpivot = biggest;
-			if (pr != k)
-				for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = t; }
-			if (pc != k)
-			{
-				for (int i = 0; i < 7; ++i) { const double t = A[i][k]; A[i][k] = A[i][pc]; A[i][pc] = t; }
-				const int t = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = t;
-			}
-			const double piv = A[k][k];
-			for (int i = k + 1; i < 7; ++i)
-			{
-				const double f = A[i][k] / piv;
-				A[i][k] = f;
-				for (int j = k + 1; j < 9; ++j)
-					A[i][j] -= f * A[k][j];
 			}
 		}
 		// dimensionOfKernel() == 2  <=>  all 7 pivots above eps * 7 * maxpivot (:161-163)
 		const double premult = maxpivot * eps * 7.0;
 		int rank = 0;
-		for (int k = 0; k < nonzero; ++k)
-			if (fabs(A[k][k]) > premult) ++rank;
+#pragma unroll
+		for (int k = 0; k < 7; ++k)
+			if (k < nonzero && fabs(A(k, k)) > premult) ++rank;
 		if (rank != 7)
 			return 0;
-		double f1[9], f2[9];
+#pragma unroll
 		for (int c = 0; c < 2; ++c)
 		{
 			double x[7];
+#pragma unroll
 			for (int i = 6; i >= 0; --i)
 			{
-				double s = -A[i][7 + c];
+				double s = -A(i, 7 + c);
+#pragma unroll
 				for (int j = i + 1; j < 7; ++j)
-					s -= A[i][j] * x[j];
-				x[i] = s / A[i][i];
+					s -= A(i, j) * x[j];
+				x[i] = s / A(i, i);
 			}
-			double *f = c == 0 ? f1 : f2;
+#pragma unroll
 			for (int i = 0; i < 7; ++i)
-				f[colperm[i]] = x[i];
-			f[colperm[7 + c]] = 1.0;
-			f[colperm[7 + (1 - c)]] = 0.0;
+				A.f(c, (int)((colperm >> (4 * i)) & 15ull)) = x[i];
+			A.f(c, (int)((colperm >> (4 * (7 + c))) & 15ull)) = 1.0;
+			A.f(c, (int)((colperm >> (4 * (7 + (1 - c)))) & 15ull)) = 0.0;
 		}
-		for (int j = 0; j < 9; ++j) // :190 f1 -= f2
-			f1[j] -= f2[j];
+#pragma unroll
+		for (int j = 0; j < 9; ++j)
+		{
+			f2[j] = A.f(1, j);
+			f1[j] = A.f(0, j) - f2[j]; // :190 f1 -= f2
+		}
 
 		double c[4], t0, t1, t2;
 		t0 = f2[4] * f2[8] - f2[5] * f2[7];
@@ -182,29 +221,29 @@ namespace gcr_f7
 		    fabs(c[3]) < eps) // :246-251
 			return 0;
 
-		double roots[3];
-		const int nr = cubic_roots(c[0], c[1], c[2], c[3], roots);
-		int nm = 0;
-		for (int r = 0; r < nr; ++r)
-		{
-			double lambda = roots[r], mu = 1.;
-			const double s = f1[8] * roots[r] + f2[8];
-			if (fabs(s) > eps) // :273
-			{
-				mu = 1.0 / s;
-				lambda *= mu;
-				double *o = F + 9 * nm;
-				for (int j = 0; j < 8; ++j)
-					o[j] = f1[j] * lambda + f2[j] * mu;
-				o[8] = 1.0;
-				++nm;
-			}
-		}
-		return nm;
+		return cubic_roots(c[0], c[1], c[2], c[3], roots);
+	}
+
+	// :267-288: F = lambda f1 + mu f2 scaled so that F33 = 1; false if |s| <= eps (the reference skips the root)
+	__device__ __forceinline__ bool model(const double *f1, const double *f2, double root, double *F)
+	{
+		const double eps = 2.220446049250313e-16;
+		double lambda = root, mu = 1.;
+		const double s = f1[8] * root + f2[8];
+		if (!(fabs(s) > eps)) // :273
+			return false;
+		mu = 1.0 / s;
+		lambda *= mu;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			F[j] = f1[j] * lambda + f2[j] * mu;
+		F[8] = 1.0;
+		return true;
 	}
 
 	// fundamental_estimator.h:737-800 (sample given as m rows of x0 y0 x1 y1)
-	__device__ inline bool orientation_valid(const double *F, const double *pt, int m)
+	template <class PointFn>
+	__device__ inline bool orientation_valid(const double *F, const PointFn &pt, int m)
 	{
 		const double epsilon = 1.9984e-15;
 		double e[3];
@@ -224,9 +263,8 @@ namespace gcr_f7
 		double sig2 = 0.0;
 		for (int i = 0; i < m; ++i)
 		{
-			const double *p = pt + 4 * i;
-			const double s1 = F[0] * p[2] + F[3] * p[3] + F[6];
-			const double s2 = e[1] - e[2] * p[1];
+			const double s1 = F[0] * pt(i, 2) + F[3] * pt(i, 3) + F[6];
+			const double s2 = e[1] - e[2] * pt(i, 1);
 			const double sig = s1 * s2;
 			if (i == 0)
 				sig2 = sig;

@@ -25,7 +25,7 @@ EXPORTS = [
     "gcr_solve_minimal", "gcr_max_models", "gcr_sample_size", "gcr_model_len", "gcr_score", "gcr_score_exact",
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
-    "gcr_profile_read", "gcr_counters_read",
+    "gcr_profile_read", "gcr_counters_read", "gcr_round_results",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load_library():
         "gcr_refit": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp]),
         "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
+        "gcr_round_results": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -328,6 +329,13 @@ class Context:
         finally:
             for d in (dk, ds, do):
                 self.free(d)
+
+    def round_results(self):
+        """FP64 score and exact inlier count of each pair's winner of the last round."""
+        sc = np.empty(self.n_pairs)
+        cn = np.empty(self.n_pairs, dtype=np.uint32)
+        self.check(self.lib.gcr_round_results(self.h, _ptr(sc), _ptr(cn)))
+        return sc, cn
 
     # ---- fused round ----
     def round(self, problem, scoring, sampler, first_index, count, seed, thr, flags=0, index_base=0):

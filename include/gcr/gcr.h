@@ -54,13 +54,14 @@ uint64_t gcr_launch_count(const gcr_ctx *ctx);
 /* width of the FP32 error band (in units of FP32 epsilon, normalised coordinates) inside which
  * GCR_SCORE_EXACT_COUNTS re-evaluates a point in FP64; default 16 */
 gcr_status gcr_set_band_factor(gcr_ctx *ctx, double factor);
-/* force a scoring-kernel variant: -1 auto, 0 scalar R=4, 1 scalar R=8, 2 packed-f32x2 R=4, 3 packed-f32x2 R=8 */
+/* force a scoring-kernel variant (hypotheses per thread): -1 auto, 0 R=4, 1 R=6, 2 R=8 (PnP: 0 R=2, 1 R=4) */
 gcr_status gcr_set_score_variant(gcr_ctx *ctx, int variant);
 /* CUDA-event timing of every K3 launch made through gcr_round / gcr_score (on the context's stream) */
 gcr_status gcr_profile_enable(gcr_ctx *ctx, int on);
 /* total K3 device time (ms), number of K3 launches and hypothesis x point evaluations they covered; resets */
 gcr_status gcr_profile_read(gcr_ctx *ctx, double *score_ms, uint64_t *score_launches, uint64_t *score_evals);
-/* device counters since the last reset: out[0] = valid models produced by gcr_solve_minimal */
+/* device counters since the last reset: out[0] = valid models produced by gcr_solve_minimal, out[1] = FP64
+ * re-check evaluations dropped because the work list was full (must stay 0), out[2] = FP64 re-checks queued */
 gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[4], int reset);
 
 /* device memory helpers so that C / ctypes callers need no other CUDA binding */
@@ -161,11 +162,17 @@ gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell_sizes[4], 
 
 /* ---- fused fixed-K round (the benchmarked step) ------------------------------------------------------------ */
 /* One pass of the hot path over every pair on the context: K1 sample `count` minimal samples -> K2 solve -> K3
- * score (all models) -> K4 argmax.  Outputs per pair: packed key (see gcr_argmax; index = sample * max_models +
- * model slot, offset by index_base) and the winning model (FP64).  evals_out = hypothesis x point evaluations done. */
+ * score (FP32, valid models only) -> K4: the near-best candidates of the FP32 ranking are re-scored in FP64 and the
+ * winner is picked by (FP64 score, lowest index), i.e. GCRANSAC.h:440's strict '<' in the reference's precision.
+ * Outputs per pair: packed key (see gcr_argmax; score = the winner's FP64 score rounded to float, index = sample *
+ * max_models + model slot, offset by index_base; 0 if no model scored > 0) and the winning model (FP64).
+ * evals_out = model slots x points of this round (valid models are counted by gcr_counters_read). */
 gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
                      uint64_t seed, double threshold, int flags, uint32_t index_base, uint64_t *d_keys,
                      double *d_best_models, uint64_t *evals_out);
+
+/* FP64 score and exact inlier count of each pair's winner of the last gcr_round (host outputs, [n_pairs]). */
+gcr_status gcr_round_results(gcr_ctx *ctx, double *h_best_scores, uint32_t *h_best_counts);
 
 #ifdef __cplusplus
 }

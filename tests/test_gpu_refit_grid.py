@@ -1,0 +1,124 @@
+"""K6 (weighted least-squares refits) and K7 (grid neighbourhood) parity through the C ABI against the oracle.
+
+Tolerances (BASELINE.json north_star): final models <= 1e-5 relative, compared up to scale; grid cell keys, cell
+lists, filled-cell count and neighbor_number bit-exact."""
+import numpy as np
+import oracle as O
+import pytest
+from pygcransac import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+RTOL_MODEL = 1e-5
+
+
+def _up_to_scale(A, B):
+    A = A / np.linalg.norm(A)
+    B = B / np.linalg.norm(B)
+    if (A * B).sum() < 0:
+        B = -B
+    return np.abs(A - B).max() / np.abs(A).max()
+
+
+def _index_sets(rng, inl_idx, sizes):
+    return [rng.choice(inl_idx, size=s, replace=False).astype(np.uint32) for s in sizes]
+
+
+def test_refit_h_matches_oracle(gcr_ctx, oracle):
+    pts, Hm, inl = synth.homography_pair(3000, 0.3, seed=51)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(1)
+    inl_idx = np.nonzero(inl)[0]
+    # LO-sized sets (7 m = 28), the minimal n == 4 branch, a large "all inliers" set, and one with outliers mixed in
+    sets = _index_sets(rng, inl_idx, [28] * 20 + [4] * 6 + [5, 9, 200, len(inl_idx)])
+    sets.append(rng.choice(3000, size=40, replace=False).astype(np.uint32))
+    models, ok = gcr_ctx.refit(_cabi.H, sets)
+    worst = 0.0
+    for s, mdl, k in zip(sets, models, ok):
+        want = oracle.refit(O.H, pts, s)
+        assert bool(k) == (want is not None)
+        if want is not None:
+            worst = max(worst, _up_to_scale(want, mdl))
+    assert worst < RTOL_MODEL, worst
+
+
+def test_refit_h_weighted_both_index_modes(gcr_ctx, oracle):
+    pts, Hm, inl = synth.homography_pair(1200, 0.2, seed=52)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(2)
+    idx = np.sort(rng.choice(np.nonzero(inl)[0], size=300, replace=False)).astype(np.uint32)
+    w_point = rng.uniform(0.05, 1.0, size=1200)
+    # reference behaviour: the solver reads weights[i] by POSITION in the set
+    got, ok = gcr_ctx.refit(_cabi.H, [idx], weights=w_point, weight_mode=_cabi.WEIGHT_POSITIONAL)
+    want = oracle.refit(O.H, pts, idx, weights=w_point)
+    assert ok[0] and _up_to_scale(want, got[0]) < RTOL_MODEL
+    # by-point indexing == positional indexing of the gathered weights
+    got2, ok2 = gcr_ctx.refit(_cabi.H, [idx], weights=w_point, weight_mode=_cabi.WEIGHT_BY_POINT)
+    want2 = oracle.refit(O.H, pts, idx, weights=np.ascontiguousarray(w_point[idx]))
+    assert ok2[0] and _up_to_scale(want2, got2[0]) < RTOL_MODEL
+    assert _up_to_scale(want, want2) > 1e-9  # the two modes really differ
+
+
+def test_refit_f8_matches_oracle(gcr_ctx, oracle):
+    pts, Fm, Em, Kc, inl = synth.epipolar_pair(2500, 0.4, seed=53)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(3)
+    inl_idx = np.nonzero(inl)[0]
+    sets = _index_sets(rng, inl_idx, [49] * 20 + [8, 8, 9, 15, 300, len(inl_idx)])
+    models, ok = gcr_ctx.refit(_cabi.F, sets)
+    worst = 0.0
+    for s, mdl, k in zip(sets, models, ok):
+        want = oracle.refit(O.F, pts, s)
+        assert bool(k) == (want is not None)
+        worst = max(worst, _up_to_scale(want, mdl))
+    assert worst < RTOL_MODEL, worst
+    w = rng.uniform(0.05, 1.0, size=2500)
+    got, ok = gcr_ctx.refit(_cabi.F, [sets[-1]], weights=w, weight_mode=_cabi.WEIGHT_POSITIONAL)
+    assert ok[0] and _up_to_scale(oracle.refit(O.F, pts, sets[-1], weights=w), got[0]) < RTOL_MODEL
+
+
+def test_refit_too_small_sets_and_errors(gcr_ctx):
+    pts, Hm, inl = synth.homography_pair(100, 0.0, seed=54)
+    gcr_ctx.points_upload(pts)
+    models, ok = gcr_ctx.refit(_cabi.H, [np.arange(3, dtype=np.uint32), np.arange(10, dtype=np.uint32)])
+    assert list(ok) == [0, 1] and not models[0].any()
+    models, ok = gcr_ctx.refit(_cabi.F, [np.arange(7, dtype=np.uint32)])
+    assert list(ok) == [0]
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.refit(_cabi.PNP, [np.arange(10, dtype=np.uint32)])
+
+
+@pytest.mark.parametrize("n,cells", [(762, 4), (4096, 8), (5000, 20), (100000, 3), (1, 4), (257, 64)])
+def test_grid_bit_exact(gcr_ctx, oracle, n, cells):
+    pts = synth.homography_pair(n, 0.5, seed=60 + cells)[0]
+    gcr_ctx.points_upload(pts)
+    cs = np.array([synth.SIZE / cells] * 4) + (1e-9 if cells == 4 else 0.0)
+    want = oracle.grid_build(pts, cs, cells)
+    got = gcr_ctx.grid_build(cs, cells)
+    assert np.array_equal(got["keys"], want["keys"])
+    assert np.array_equal(got["sorted_idx"], want["sorted_idx"])
+    assert got["n_cells"] == want["n_cells"] and got["neighbor_number"] == want["neighbor_number"]
+    assert np.array_equal(got["cell_offsets"], want["cell_offsets"][: want["n_cells"] + 1])
+
+
+def test_grid_golden_fixture(gcr_ctx):
+    """The committed fixture was generated from the reference's own GridNeighborhoodGraph (oracle/gen_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "grid.npz"))
+    gcr_ctx.points_upload(g["pts"])
+    for Cn in (3, 4, 8):
+        got = gcr_ctx.grid_build(g["cell_sizes_%d" % Cn], Cn)
+        assert np.array_equal(got["keys"], g["keys_%d" % Cn])
+        assert np.array_equal(got["sorted_idx"], g["sorted_idx_%d" % Cn])
+        assert [got["n_cells"], got["neighbor_number"]] == list(g["meta_%d" % Cn])
+
+
+def test_grid_second_pair_and_errors(gcr_ctx, oracle):
+    pairs = np.stack([synth.homography_pair(900, 0.3, seed=s)[0] for s in (71, 72)])
+    gcr_ctx.points_upload(pairs, n_pairs=2)
+    cs = np.array([synth.SIZE / 5.0] * 4)
+    got = gcr_ctx.grid_build(cs, 5, pair=1)
+    want = oracle.grid_build(pairs[1], cs, 5)
+    assert np.array_equal(got["sorted_idx"], want["sorted_idx"]) and got["neighbor_number"] == want["neighbor_number"]
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.grid_build(np.array([0.0, 1.0, 1.0, 1.0]), 4)
