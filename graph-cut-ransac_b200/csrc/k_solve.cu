@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "solve_f7.cuh"
+#include "solve_e5.cuh"
 
 extern "C" int gcr_max_models(int problem)
 {
@@ -227,6 +228,57 @@ __global__ void __launch_bounds__(F7_THREADS) k_solve_f7(const double *__restric
 		atomicAdd(&counters[0], (unsigned long long)cnt[0]);
 }
 
+// ---------------------------------------------------------------------------------------------------- E5 ----
+// One thread per sample; the solver's working set (10 x 20 constraint matrix, Sturm chain, interval stack: ~6 KB) is
+// thread-local memory served from L1/L2.  O(K) work next to the O(K N) scoring.
+struct SamplePoints5
+{
+	const double *P;
+	const uint32_t *s;
+	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 4 + c]; }
+};
+
+__global__ void __launch_bounds__(64) k_solve_e5(const double *__restrict__ pts, int n,
+                                                 const uint32_t *__restrict__ samples, int count,
+                                                 double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                 unsigned long long *__restrict__ counters)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int pair = blockIdx.y;
+	uint32_t n_ok = 0;
+	if (i < count)
+	{
+		uint32_t sidx[5];
+		const uint32_t *s = samples + ((size_t)pair * count + i) * 5;
+		for (int j = 0; j < 5; ++j)
+			sidx[j] = s[j];
+		const SamplePoints5 pt{pts + (size_t)pair * n * 4, sidx};
+		double *out = models + ((size_t)pair * count + i) * 90;
+		uint8_t *v = valid + ((size_t)pair * count + i) * 10;
+		const int nm = gcr_e5::solve(pt, out); // models land in slots 0..nm-1 of the output row
+		for (int mdl = 0; mdl < 10; ++mdl)
+		{
+			bool ok = mdl < nm;
+			if (ok)
+				ok = gcr_f7::orientation_valid(out + 9 * mdl, pt, 5); // essential_estimator.h:165-171, 338-401
+			if (!ok)
+				for (int j = 0; j < 9; ++j)
+					out[9 * mdl + j] = 0.0;
+			v[mdl] = ok ? 1 : 0;
+			n_ok += ok ? 1u : 0u;
+		}
+	}
+	__shared__ uint32_t cnt;
+	if (threadIdx.x == 0)
+		cnt = 0;
+	__syncthreads();
+	if (n_ok)
+		atomicAdd(&cnt, n_ok);
+	__syncthreads();
+	if (threadIdx.x == 0 && cnt)
+		atomicAdd(&counters[0], (unsigned long long)cnt);
+}
+
 extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
                                         double *d_models, uint8_t *d_valid)
 {
@@ -249,6 +301,10 @@ extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SMEM));
 		k_solve_f7<<<dim3((count + F7_THREADS - 1) / F7_THREADS, ctx->n_pairs), F7_THREADS, F7_SMEM, ctx->stream>>>(
 		    ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		break;
+	case GCR_E:
+		k_solve_e5<<<dim3((count + 63) / 64, ctx->n_pairs), 64, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count,
+		                                                                         d_models, d_valid, ctx->d_counters);
 		break;
 	default:
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: solver for problem %d is not built yet", problem);

@@ -84,6 +84,43 @@ def test_f7_models_match_oracle(gcr_ctx, oracle):
     assert 300 < n_models < 9000
 
 
+def test_e5_models_match_oracle(gcr_ctx, oracle):
+    """K2 5-point (Nister): statement-for-statement the oracle's arithmetic -> the same models, sample by sample."""
+    pts, Fm, Em, Kc, _ = synth.epipolar_pair(600, 0.5, seed=15)
+    npts = oracle.normalize_correspondences(pts, Kc, Kc)
+    gcr_ctx.points_upload(npts)
+    samples = oracle.sample_uniform(9, 0, 2000, 600, 5)
+    models, valid = gcr_ctx.solve_minimal(O.E, samples)
+    models, valid = models[0], valid[0]
+    n_models = 0
+    for s, mdl, v in zip(samples, models, valid):
+        want = oracle.estimate_e5(npts, s)                     # Nister + oriented-constraint filter, ascending roots
+        got = mdl[v.astype(bool)].reshape(-1, 3, 3)
+        assert len(got) == len(want), (s, len(got), len(want))
+        for g, w in zip(got, want):
+            assert np.abs(g - w).max() <= 1e-9 * np.abs(w).max(), (s, np.abs(g - w).max())
+        n_models += len(want)
+    assert 500 < n_models < 20000
+
+
+def test_round_e_magsac_matches_cpu_round(gcr_ctx, oracle):
+    """BASELINE configs[2] shape: 5-point + MAGSAC++ on K-normalised correspondences, threshold / focal length."""
+    pts, Fm, Em, Kc, _ = synth.epipolar_pair(800, 0.6, seed=16)
+    npts = oracle.normalize_correspondences(pts, Kc, Kc)
+    thr = 0.75 / synth.FOCAL
+    gcr_ctx.points_upload(npts)
+    keys, best, evals = gcr_ctx.round(O.E, _cabi.MAGSAC, _cabi.UNIFORM, 0, 1500, seed=11, thr=thr,
+                                      flags=_cabi.SCORE_EXACT_COUNTS)
+    score, idx = gcr_ctx.key_decode(keys[0])
+    want_score, want_idx, scored, want_model = oracle.round(O.E, O.MAGSAC, npts, 11, 0, 1500, thr)
+    assert idx // 10 == want_idx // 10
+    r64, rc = gcr_ctx.round_results()
+    assert abs(r64[0] - want_score) <= 1e-9 * want_score
+    err = np.abs(best[0] / np.linalg.norm(best[0]) - want_model / np.linalg.norm(want_model)).max()
+    assert err < 1e-9
+    assert gcr_ctx.counters()[1] == 0
+
+
 def test_argmax_first_wins(gcr_ctx):
     pts = np.stack([synth.homography_pair(64, 0.3, seed=s)[0] for s in (1, 2)])
     gcr_ctx.points_upload(pts, n_pairs=2)
