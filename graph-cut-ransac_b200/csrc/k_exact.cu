@@ -8,6 +8,7 @@
 #include "gcr_internal.cuh"
 
 #include <math.h>
+#include <string.h>
 
 #define EX_THREADS 1024
 
@@ -22,6 +23,7 @@ struct ExactArgs
 	double *residuals;    // [k][n] or null
 	int n, k;
 	double thr;
+	double T_override; // > 0: squared truncated threshold handed over as is (ScoringFunction::initialize), else from thr
 };
 
 template <int PROBLEM, int SCORING>
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_score_exact(const ExactArgs a)
 
 	// thresholds exactly as the reference forms them
 	const double truncated_threshold = 3.0 / 2.0 * a.thr;                                 // GCRANSAC.h:253
-	const double squared_truncated_threshold = truncated_threshold * truncated_threshold; // GCRANSAC.h:254
+	const double squared_truncated_threshold =
+	    a.T_override > 0.0 ? a.T_override : truncated_threshold * truncated_threshold; // GCRANSAC.h:254
 	// MAGSAC constants, scoring_function.h:257-296
 	const double gamma_k = 0.0036572608340910764;
 	const double gamma_difference = 0.88622692545275801365 - gamma_k; // tgamma(1.5)
@@ -158,9 +161,21 @@ gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx)
 	return GCR_OK;
 }
 
+static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
+                                   double threshold, double T_override, double *d_scores, uint32_t *d_counts,
+                                   uint32_t *d_inlier_idx, double *d_residuals);
+
 extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                       double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
                                       double *d_residuals)
+{
+	return score_exact_impl(ctx, problem, scoring, pair, d_models, k, threshold, 0.0, d_scores, d_counts, d_inlier_idx,
+	                        d_residuals);
+}
+
+static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
+                                   double threshold, double T_override, double *d_scores, uint32_t *d_counts,
+                                   uint32_t *d_inlier_idx, double *d_residuals)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
@@ -188,6 +203,7 @@ extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, in
 	a.n = ctx->n;
 	a.k = k;
 	a.thr = threshold;
+	a.T_override = T_override;
 #define GCR_EX(P)                                                                                        \
 	do                                                                                                   \
 	{                                                                                                    \
@@ -236,4 +252,49 @@ extern "C" gcr_status gcr_score_exact_host(gcr_ctx *ctx, int problem, int scorin
 	cudaFree(d_i);
 	cudaFree(d_r);
 	return st;
+}
+
+// ScoringFunction::getScore for ONE model with host in / out -- what gcr::CudaScoringFunction (host/gcr_scoring_function.h)
+// calls.  squared_truncated_threshold is the value MSACScoringFunction::initialize received (GCRANSAC.h:253-255) and is
+// used as is; threshold is getScore's threshold_ argument (MAGSAC's sigma_max).  Device buffers live in the context.
+extern "C" gcr_status gcr_getscore_host(gcr_ctx *ctx, int problem, int scoring, int pair, const double *h_model,
+                                        double squared_truncated_threshold, double threshold, double *h_score,
+                                        uint32_t *h_count, uint32_t *h_inlier_idx)
+{
+	if (!ctx || !h_model || !h_score || !h_count)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_getscore_host: no points uploaded");
+	if (scoring == GCR_MSAC && !(squared_truncated_threshold > 0.0))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_getscore_host: MSAC needs the squared truncated threshold of initialize()");
+	if (scoring == GCR_MAGSAC && !(threshold > 0.0))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_getscore_host: MAGSAC needs threshold > 0");
+	const int ml = problem == GCR_PNP ? 12 : 9;
+	const size_t n = ctx->n;
+	// scratch: model | score | count | inlier list
+	const size_t o_model = 0, o_score = 128, o_count = 136, o_idx = 256;
+	gcr_status st = gcr_ensure_scratch(ctx, o_idx + n * sizeof(uint32_t));
+	if (st)
+		return st;
+	st = gcr_ensure_pinned(ctx, o_idx + n * sizeof(uint32_t));
+	if (st)
+		return st;
+	char *d = (char *)ctx->d_scratch, *h = (char *)ctx->h_pinned;
+	memcpy(h + o_model, h_model, ml * sizeof(double));
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d + o_model, h + o_model, ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	st = score_exact_impl(ctx, problem, scoring, pair, (const double *)(d + o_model), 1, threshold,
+	                      scoring == GCR_MSAC ? squared_truncated_threshold : 0.0, (double *)(d + o_score),
+	                      (uint32_t *)(d + o_count), h_inlier_idx ? (uint32_t *)(d + o_idx) : nullptr, nullptr);
+	if (st)
+		return st;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h + o_score, d + o_score, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*h_score = *(double *)(h + o_score);
+	*h_count = *(uint32_t *)(h + o_count);
+	if (h_inlier_idx && *h_count)
+	{
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_inlier_idx, d + o_idx, (size_t)*h_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	return GCR_OK;
 }

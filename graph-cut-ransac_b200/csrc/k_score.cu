@@ -8,20 +8,21 @@
 //                     list (warp-aggregated atomics) and map their FP64 model into the centred / scaled FP32 frame of
 //                     the point copy.  Invalid slots (failed solver, oriented-constraint reject: ~90 % of 7-point
 //                     slots) never reach the scoring kernel.
-//   k_score_plan      one CTA: per-pair prefix of hypothesis tiles; picks how many point chunks each tile is split
-//                     into so that the persistent grid below has >= 2 work items per CTA.
-//   k_score_main      the hot kernel.  Persistent CTAs (128 threads) pull (pair, hypothesis tile, point chunk) items
-//                     from an atomic ticket.  lane = hypothesis: each thread keeps R hypotheses in registers for the
-//                     whole item, packed two-by-two into f32x2 registers and evaluated with FFMA2 / FMUL2 / FADD2
+//   k_score_plan      one CTA: per-pair prefix of hypothesis tiles.
+//   k_score_main      the hot kernel.  One persistent CTA (128 threads) per SM slot; the work space (hypothesis tiles x
+//                     point granules) is cut into equal contiguous slices, one per CTA ("stream-K"), so there is no
+//                     tail wave whatever K, N and the pair count are.  lane = hypothesis: each thread keeps R
+//                     hypotheses in registers for a whole segment, packed two-by-two into f32x2 registers and
+//                     evaluated with FFMA2 / FMUL2 / FADD2
 //                     (sm_100 packed FP32: half the issue slots per evaluation, which leaves the issue port to the
 //                     MUFU.RCP, the min/compare/count work and the shared-memory loads).  All 32 lanes of a warp read
 //                     the SAME point (broadcast LDS.128 of an operand-duplicated copy), so there is no cross-lane
 //                     reduction and no bank conflict.  Point tiles (256 points, 8 KB) stream through a 4-stage
 //                     shared-memory ring filled by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) issued by one
 //                     elected thread.  Per-hypothesis (score, inliers) accumulate in registers (FP32, flushed per
-//                     tile into a second-level FP32 sum) and are added once per item to the slot's accumulators
+//                     tile into a second-level FP32 sum) and are added once per segment to the slot's accumulators
 //                     as fixed-point int64 / uint32 atomics -- integer addition is associative, so the result does not
-//                     depend on the order in which chunks finish (deterministic, no float atomics).
+//                     depend on the order in which segments finish (deterministic, no float atomics).
 //   k_score_fixup     GCR_SCORE_EXACT_COUNTS: evaluations whose |r^2 - t^2| fell inside the FP32 error band were left
 //                     out by the hot kernel and appended to a work list; they are evaluated here in FP64 in the
 //                     reference's operation order, so inlier counts equal the FP64 reference's.
@@ -180,10 +181,8 @@ __device__ __forceinline__ Thresholds make_thresholds(const double *nm, double t
 // ------------------------------------------------------------------------------------------------ plumbing ----
 struct ScorePlan
 {
-	uint32_t ticket;      // next work item (persistent scheduler)
 	uint32_t amb_count;   // entries appended to the FP64 work list
 	uint32_t amb_dropped; // entries that did not fit (reported through gcr_counters_read)
-	uint32_t total_items, n_chunks, tiles_per_chunk;
 	uint32_t pad[2];
 };
 
@@ -252,6 +251,7 @@ __global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------- plan ----
+// one CTA: exclusive prefix of hypothesis tiles over the pairs (prefix[n_pairs] = total)
 __global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
 {
 	__shared__ uint32_t warp_tot[32];
@@ -285,22 +285,7 @@ __global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
 		__syncthreads();
 	}
 	if (tid == 0)
-	{
-		const uint32_t total_tiles = carry;
-		a.prefix[a.n_pairs] = total_tiles;
-		const uint32_t n_point_tiles = (uint32_t)(a.n_pad / TILE);
-		uint32_t n_chunks = 1;
-		if (total_tiles > 0 && total_tiles < 2u * a.grid)
-			n_chunks = (2u * a.grid + total_tiles - 1) / total_tiles;
-		const uint32_t min_chunks = (n_point_tiles + MAX_TILES_PER_CHUNK - 1) / MAX_TILES_PER_CHUNK;
-		if (n_chunks < min_chunks) n_chunks = min_chunks;
-		if (n_chunks > n_point_tiles) n_chunks = n_point_tiles;
-		const uint32_t tpc = (n_point_tiles + n_chunks - 1) / n_chunks;
-		n_chunks = (n_point_tiles + tpc - 1) / tpc;
-		a.plan->tiles_per_chunk = tpc;
-		a.plan->n_chunks = n_chunks;
-		a.plan->total_items = total_tiles * n_chunks;
-	}
+		a.prefix[a.n_pairs] = carry;
 }
 
 // ----------------------------------------------------------------------------------- per-evaluation maths ----
@@ -373,21 +358,27 @@ __device__ __forceinline__ void amb_record(const ScoreArgs &a, size_t gslot, int
 }
 
 // --------------------------------------------------------------------------------------------- the kernel ----
+// Work decomposition ("stream-K" over hypothesis tiles x points): the work space is the concatenation, over all
+// hypothesis tiles (THREADS * R hypotheses of one pair), of that pair's points in granules of GRAN; CTA b of G owns
+// the contiguous slice [b W / G, (b + 1) W / G) of it and walks it as a few segments (hypothesis tile, point range).
+// Every CTA gets the same amount of work to within one granule whatever K, N and the pair count are -- no tail wave
+// and no scheduler atomics -- and partial sums meet in the integer accumulators.
+#define GRAN 32
+
 template <int PROBLEM, int SCORING, int R, bool EXACT>
-__global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_score_main(const ScoreArgs a)
+__global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const ScoreArgs a)
 {
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
 	constexpr bool PACKED = PROBLEM != GCR_PNP;
 	constexpr int NQ = PACKED ? R / 2 : R; // register groups per thread
 	constexpr int HQ = PACKED ? 2 : 1;     // hypotheses per group
-	constexpr uint32_t TILE_BYTES = TILE * 2 * sizeof(float4);
+	constexpr int NQP = PACKED ? NQ : 1, NQS = PACKED ? 1 : NQ;
 	static_assert(!PACKED || R % 2 == 0, "packed variant needs an even R");
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	float4(*tiles)[TILE * 2] = reinterpret_cast<float4(*)[TILE * 2]>(smem_raw);
-	uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TILE_BYTES);
-	uint32_t *s_item = reinterpret_cast<uint32_t *>(smem_raw + STAGES * TILE_BYTES + 8 * STAGES);
-	float *s_lut = reinterpret_cast<float *>(smem_raw + STAGES * TILE_BYTES + 64);
+	uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TILE * 2 * sizeof(float4));
+	float *s_lut = reinterpret_cast<float *>(smem_raw + STAGES * TILE * 2 * sizeof(float4) + 64);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0)
@@ -400,21 +391,23 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 	if (SCORING == GCR_MAGSAC)
 		for (int i = tid; i < 5001; i += THREADS)
 			s_lut[i] = a.lut[i];
+	__syncthreads();
 
-	const uint32_t total_items = a.plan->total_items, n_chunks = a.plan->n_chunks, tiles_per_chunk = a.plan->tiles_per_chunk;
-	const int n_tiles_total = a.n_pad / TILE;
-	uint32_t ring = 0; // tiles this CTA has consumed so far: stage = ring % STAGES, parity = (ring / STAGES) & 1
+	const unsigned long long n_gran = (unsigned long long)(a.n_pad / GRAN);
+	const unsigned long long W = (unsigned long long)a.prefix[a.n_pairs] * n_gran;
+	unsigned long long pos = W * blockIdx.x / gridDim.x;
+	const unsigned long long pos_end = W * (blockIdx.x + 1ull) / gridDim.x;
+	uint32_t ring = 0; // ring tiles this CTA has consumed so far: stage = ring % STAGES, parity = (ring / STAGES) & 1
+	const float qnan = __int_as_float(0x7fc00000);
 
-	for (;;)
+	while (pos < pos_end)
 	{
-		__syncthreads(); // everyone is done with the previous item's stages and with s_item
-		if (tid == 0)
-			*s_item = atomicAdd(&a.plan->ticket, 1u);
-		__syncthreads();
-		const uint32_t item = *s_item;
-		if (item >= total_items)
-			break;
-		const uint32_t chunk = item % n_chunks, ht = item / n_chunks;
+		// ---- segment: hypothesis tile ht, granules [g0, g1) of its pair's points ----
+		const uint32_t ht = (uint32_t)(pos / n_gran);
+		const uint32_t g0 = (uint32_t)(pos % n_gran);
+		uint32_t g1 = (uint32_t)n_gran;
+		if (pos_end - pos < (unsigned long long)(g1 - g0)) g1 = g0 + (uint32_t)(pos_end - pos);
+		pos += g1 - g0;
 		int lo = 0, hi = a.n_pairs; // prefix[lo] <= ht < prefix[hi]
 		while (hi - lo > 1)
 		{
@@ -424,35 +417,34 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 		}
 		const int pair = lo;
 		const int count = (int)a.counts[pair];
-		const int tile0 = (int)(chunk * tiles_per_chunk);
-		int my_tiles = n_tiles_total - tile0;
-		if (my_tiles > (int)tiles_per_chunk) my_tiles = (int)tiles_per_chunk;
-		const float4 *src = a.pts32 + ((size_t)pair * a.n_pad + (size_t)tile0 * TILE) * 2;
+		const int p0 = (int)g0 * GRAN, p1 = (int)g1 * GRAN;
+		const int seg_tiles = (p1 - p0 + TILE - 1) / TILE;
+		const float4 *src = a.pts32 + ((size_t)pair * a.n_pad + p0) * 2;
 		if (tid == 0)
 		{
 #pragma unroll
 			for (int s = 0; s < STAGES; ++s)
-				if (s < my_tiles)
+				if (s < seg_tiles)
 				{
 					const uint32_t st = (ring + s) % STAGES;
-					mbar_expect_tx(&full_bar[st], TILE_BYTES);
-					tma_load_1d(&tiles[st][0], src + (size_t)s * TILE * 2, TILE_BYTES, &full_bar[st]);
+					const int np = min(TILE, p1 - p0 - s * TILE);
+					mbar_expect_tx(&full_bar[st], (uint32_t)np * 32u);
+					tma_load_1d(&tiles[st][0], src + (size_t)s * TILE * 2, (uint32_t)np * 32u, &full_bar[st]);
 				}
 		}
 
-		// ---- prologue: this thread's R hypotheses (compact order; hypothesis = lane within a warp's block) ----
+		// ---- prologue: this thread's R hypotheses (compact order; a warp owns 32 R consecutive ones, lane = hypothesis) ----
 		const double *nm = a.norm + (size_t)pair * 8;
 		const Thresholds th = make_thresholds<PROBLEM, SCORING>(nm, a.thr, a.band_factor);
 		const int hyp0 = (int)(ht - a.prefix[pair]) * (THREADS * R) + warp * (32 * R) + lane; // + 32 * (HQ * q + e)
 		const float *mbase = a.m32 + (size_t)pair * a.k * ML;
-		// warps whose block of 32 R hypotheses lies beyond the pair's list idle through the item; inside an active warp
-		// every register group is evaluated (absent hypotheses are NaN models and contribute nothing), which keeps the
-		// 2 NQ evaluation chains of an unrolled iteration in ONE basic block for the scheduler to interleave
-		const int nq_active = (hyp0 - lane) < count ? NQ : 0;
+		// warps whose block of hypotheses lies beyond the pair's list idle through the segment; inside an active warp every
+		// register group is evaluated (absent hypotheses are NaN models and contribute nothing), which keeps all the
+		// evaluation chains of one loop iteration in ONE basic block for the scheduler to interleave
+		const bool warp_active = (hyp0 - lane) < count;
 
-		float2 h2[PACKED ? NQ : 1][9];
-		float h1[PACKED ? 1 : NQ][12];
-		const float qnan = __int_as_float(0x7fc00000);
+		float2 h2[NQP][9];
+		float h1[NQS][12];
 #pragma unroll
 		for (int q = 0; q < NQ; ++q)
 		{
@@ -474,42 +466,72 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 					h1[q][j] = ja < count ? mbase[(size_t)ja * 12 + j] : qnan;
 			}
 		}
-		float2 S2[PACKED ? NQ : 1], T2[PACKED ? NQ : 1];
-		float S1[PACKED ? 1 : NQ], T1[PACKED ? 1 : NQ];
+		float2 S2[NQP], T2[NQP]; // packed: second-level sums / per-tile sums
+		float S1[NQS], T1[NQS];  // scalar (PnP)
 		uint32_t cnt[R];
 #pragma unroll
-		for (int q = 0; q < NQ; ++q)
-		{
-			if (PACKED) S2[q] = make_float2(0.f, 0.f), T2[q] = make_float2(0.f, 0.f);
-			else S1[q] = 0.f, T1[q] = 0.f;
-		}
+		for (int q = 0; q < NQP; ++q) S2[q] = make_float2(0.f, 0.f), T2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+		for (int q = 0; q < NQS; ++q) S1[q] = 0.f, T1[q] = 0.f;
 #pragma unroll
 		for (int r = 0; r < R; ++r)
 			cnt[r] = 0;
 		const float2 NEGT = make_float2(th.negT, th.negT);
+		// H evaluates d = t / t3 - x2: the second-image operands are negated once per point
+		const float sg = PROBLEM == GCR_H ? -1.f : 1.f;
 
-		// ---- main loop over this item's point tiles ----
-		for (int t = 0; t < my_tiles; ++t)
+		// fixed-point flush of the register accumulators into the slot accumulators (segment end / every 64 tiles)
+		auto flush = [&]() {
+#pragma unroll
+			for (int q = 0; q < NQ; ++q)
+#pragma unroll
+				for (int e = 0; e < HQ; ++e)
+				{
+					const int j = hyp0 + 32 * (HQ * q + e);
+					if (j < count)
+					{
+						const float S = PACKED ? (e == 0 ? S2[q].x : S2[q].y) : S1[q];
+						const size_t g = (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j];
+						const long long fx = __double2ll_rn((double)S * th.scale);
+						if (fx != 0)
+							atomicAdd(&a.accS[g], (unsigned long long)fx);
+						if (cnt[HQ * q + e] != 0)
+							atomicAdd(&a.accC[g], cnt[HQ * q + e]);
+					}
+					cnt[HQ * q + e] = 0;
+				}
+#pragma unroll
+			for (int q = 0; q < NQP; ++q) S2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+			for (int q = 0; q < NQS; ++q) S1[q] = 0.f;
+		};
+
+		// ---- main loop over the segment's ring tiles ----
+		for (int t = 0; t < seg_tiles; ++t)
 		{
 			const uint32_t st = (ring + t) % STAGES;
+			const int np = min(TILE, p1 - p0 - t * TILE); // multiple of GRAN
 			mbar_wait(&full_bar[st], ((ring + t) / STAGES) & 1u);
 			const float4 *tp = &tiles[st][0];
-			if (nq_active > 0)
+			if (warp_active)
 			{
-#pragma unroll 2
-				for (int i = 0; i < TILE; ++i)
+				// two points per iteration, the next pair of points prefetched into registers while these are evaluated
+				float4 na0 = tp[0], nb0 = tp[1], na1 = tp[2], nb1 = tp[3];
+				for (int i = 0; i < np; i += 2)
 				{
-					const float4 qa = tp[2 * i], qb = tp[2 * i + 1];
-					float mn = 3.0e38f; // min |u| over this thread's evaluations of the point (EXACT)
-					// H evaluates d = t/t3 - x2: negate the second-image operands once per point
-					const float sg = PROBLEM == GCR_H ? -1.f : 1.f;
-					const float2 X1 = make_float2(qa.x, qa.y), Y1 = make_float2(qa.z, qa.w);
-					const float2 X2 = make_float2(sg * qb.x, sg * qb.y), Y2 = make_float2(sg * qb.z, sg * qb.w);
-					if (PACKED)
-					{
+					const float4 qa[2] = {na0, na1}, qb[2] = {nb0, nb1};
+					const int inext = min(i + 2, np - 2);
+					na0 = tp[2 * inext]; nb0 = tp[2 * inext + 1]; na1 = tp[2 * inext + 2]; nb1 = tp[2 * inext + 3];
+					float mn = 3.0e38f; // min |u| over this thread's evaluations of the two points (EXACT)
 #pragma unroll
-						for (int q = 0; q < NQ; ++q)
+					for (int pp = 0; pp < 2; ++pp)
+					{
+						if (PACKED)
 						{
+							const float2 X1 = make_float2(qa[pp].x, qa[pp].y), Y1 = make_float2(qa[pp].z, qa[pp].w);
+							const float2 X2 = make_float2(sg * qb[pp].x, sg * qb[pp].y), Y2 = make_float2(sg * qb[pp].z, sg * qb[pp].w);
+#pragma unroll
+							for (int q = 0; q < NQP; ++q)
 							{
 								const float2 v = eval2<PROBLEM, SCORING>(h2[q], X1, Y1, X2, Y2, NEGT);
 								if (SCORING == GCR_MSAC)
@@ -531,14 +553,12 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 								}
 							}
 						}
-					}
-					else
-					{
-#pragma unroll
-						for (int q = 0; q < NQ; ++q)
+						else
 						{
+#pragma unroll
+							for (int q = 0; q < NQS; ++q)
 							{
-								const float v = eval_pnp<SCORING>(h1[q], qa, qb, th.negT);
+								const float v = eval_pnp<SCORING>(h1[q], qa[pp], qb[pp], th.negT);
 								if (SCORING == GCR_MSAC)
 								{
 									T1[q] += fminf(v, 0.f);
@@ -561,47 +581,53 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 					{
 						// rare: take the FP32 contribution of every in-band evaluation back out and queue it for FP64.
 						// Recomputing v here gives the same bits as above (same instructions on the same operands).
-						const int pidx = (tile0 + t) * TILE + i;
 #pragma unroll
-						for (int q = 0; q < NQ; ++q)
+						for (int pp = 0; pp < 2; ++pp)
 						{
-							float vv[2];
-							if (PACKED)
-							{
-								const float2 v = eval2<PROBLEM, SCORING>(h2[q], X1, Y1, X2, Y2, NEGT);
-								vv[0] = v.x;
-								vv[1] = v.y;
-							}
-							else
-								vv[0] = vv[1] = eval_pnp<SCORING>(h1[q], qa, qb, th.negT);
+							const int pidx = p0 + t * TILE + i + pp;
+							const float2 X1 = make_float2(qa[pp].x, qa[pp].y), Y1 = make_float2(qa[pp].z, qa[pp].w);
+							const float2 X2 = make_float2(sg * qb[pp].x, sg * qb[pp].y), Y2 = make_float2(sg * qb[pp].z, sg * qb[pp].w);
 #pragma unroll
-							for (int e = 0; e < HQ; ++e)
+							for (int q = 0; q < NQ; ++q)
 							{
-								const float u = SCORING == GCR_MSAC ? vv[e] : vv[e] + th.negT;
-								const int j = hyp0 + 32 * (HQ * q + e);
-								if (q < nq_active && fabsf(u) < th.band && j < count && pidx < a.n)
+								float vv[2];
+								if (PACKED)
 								{
-									float back;
-									uint32_t was_in;
-									if (SCORING == GCR_MSAC)
+									const float2 v = eval2<PROBLEM, SCORING>(h2[PACKED ? q : 0], X1, Y1, X2, Y2, NEGT);
+									vv[0] = v.x;
+									vv[1] = v.y;
+								}
+								else
+									vv[0] = vv[1] = eval_pnp<SCORING>(h1[PACKED ? 0 : q], qa[pp], qb[pp], th.negT);
+#pragma unroll
+								for (int e = 0; e < HQ; ++e)
+								{
+									const float u = SCORING == GCR_MSAC ? vv[e] : vv[e] + th.negT;
+									const int j = hyp0 + 32 * (HQ * q + e);
+									if (fabsf(u) < th.band && j < count && pidx < a.n)
 									{
-										back = fminf(u, 0.f);
-										was_in = __float_as_uint(u) >> 31;
+										float back;
+										uint32_t was_in;
+										if (SCORING == GCR_MSAC)
+										{
+											back = fminf(u, 0.f);
+											was_in = __float_as_uint(u) >> 31;
+										}
+										else
+										{
+											was_in = u <= 0.f ? 1u : 0u;
+											back = was_in ? magsac_weight(s_lut, vv[e], th.c_idx) : 0.f;
+										}
+										if (PACKED)
+										{
+											if (e == 0) T2[PACKED ? q : 0].x -= back;
+											else T2[PACKED ? q : 0].y -= back;
+										}
+										else
+											T1[PACKED ? 0 : q] -= back;
+										cnt[HQ * q + e] -= was_in;
+										amb_record(a, (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j], pidx);
 									}
-									else
-									{
-										was_in = u <= 0.f ? 1u : 0u;
-										back = was_in ? magsac_weight(s_lut, vv[e], th.c_idx) : 0.f;
-									}
-									if (PACKED)
-									{
-										if (e == 0) T2[q].x -= back;
-										else T2[q].y -= back;
-									}
-									else
-										T1[q] -= back;
-									cnt[HQ * q + e] -= was_in;
-									amb_record(a, (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j], pidx);
 								}
 							}
 						}
@@ -609,47 +635,31 @@ __global__ void __launch_bounds__(THREADS, R >= 8 ? 4 : (R >= 6 ? 4 : 5)) k_scor
 				}
 				// second-level sum: one rounding per tile instead of one per point on the long accumulator
 #pragma unroll
-				for (int q = 0; q < NQ; ++q)
+				for (int q = 0; q < NQP; ++q)
 				{
-					if (PACKED)
-					{
-						S2[q] = __fadd2_rn(S2[q], T2[q]);
-						T2[q] = make_float2(0.f, 0.f);
-					}
-					else
-					{
-						S1[q] += T1[q];
-						T1[q] = 0.f;
-					}
+					S2[q] = __fadd2_rn(S2[q], T2[q]);
+					T2[q] = make_float2(0.f, 0.f);
 				}
+#pragma unroll
+				for (int q = 0; q < NQS; ++q)
+				{
+					S1[q] += T1[q];
+					T1[q] = 0.f;
+				}
+				if ((t & (MAX_TILES_PER_CHUNK - 1)) == MAX_TILES_PER_CHUNK - 1)
+					flush(); // third level: bounds every FP32 sum to 64 tile sums whatever N is
 			}
 			__syncthreads(); // everyone is done with this stage -> refill it
-			if (tid == 0 && t + STAGES < my_tiles)
+			if (tid == 0 && t + STAGES < seg_tiles)
 			{
-				mbar_expect_tx(&full_bar[st], TILE_BYTES);
-				tma_load_1d(&tiles[st][0], src + (size_t)(t + STAGES) * TILE * 2, TILE_BYTES, &full_bar[st]);
+				const int npn = min(TILE, p1 - p0 - (t + STAGES) * TILE);
+				mbar_expect_tx(&full_bar[st], (uint32_t)npn * 32u);
+				tma_load_1d(&tiles[st][0], src + (size_t)(t + STAGES) * TILE * 2, (uint32_t)npn * 32u, &full_bar[st]);
 			}
 		}
-		ring += (uint32_t)my_tiles;
-
-		// ---- epilogue: fixed-point accumulate into the slot ----
-#pragma unroll
-		for (int q = 0; q < NQ; ++q)
-#pragma unroll
-			for (int e = 0; e < HQ; ++e)
-			{
-				const int j = hyp0 + 32 * (HQ * q + e);
-				if (j < count)
-				{
-					const float S = PACKED ? (e == 0 ? S2[q].x : S2[q].y) : S1[q];
-					const size_t g = (size_t)pair * a.k + a.slots[(size_t)pair * a.k + j];
-					const long long fx = __double2ll_rn((double)S * th.scale);
-					if (fx != 0)
-						atomicAdd(&a.accS[g], (unsigned long long)fx);
-					if (cnt[HQ * q + e] != 0)
-						atomicAdd(&a.accC[g], cnt[HQ * q + e]);
-				}
-			}
+		ring += (uint32_t)seg_tiles;
+		if (warp_active)
+			flush();
 	}
 }
 

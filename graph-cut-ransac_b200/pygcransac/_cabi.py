@@ -25,7 +25,7 @@ EXPORTS = [
     "gcr_solve_minimal", "gcr_max_models", "gcr_sample_size", "gcr_model_len", "gcr_score", "gcr_score_exact",
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
-    "gcr_profile_read", "gcr_counters_read", "gcr_round_results",
+    "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host",
 ]
 
 _lib = None
@@ -79,6 +79,7 @@ def load_library():
         "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
         "gcr_round_results": (i32, [vp, vp, vp]),
+        "gcr_getscore_host": (i32, [vp, i32, i32, i32, vp, f64, f64, C.POINTER(f64), C.POINTER(u32), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

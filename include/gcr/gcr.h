@@ -130,6 +130,14 @@ gcr_status gcr_score_exact_host(gcr_ctx *ctx, int problem, int scoring, int pair
                                 double threshold, double *h_scores, uint32_t *h_counts, uint32_t *h_inlier_idx,
                                 double *h_residuals);
 
+/* ScoringFunction<Estimator>::getScore (scoring_function.h:88-96) for ONE model, host in / out: the call the drop-in
+ * adapter gcr::CudaScoringFunction (graph-cut-ransac_b200/host/gcr_scoring_function.h) makes from the reference's own
+ * GCRANSAC<> loop.  squared_truncated_threshold = the value initialize() received (used as is by MSAC, :163);
+ * threshold = getScore's threshold_ (MAGSAC's sigma_max, :257).  h_inlier_idx: [n] uint32 or NULL. */
+gcr_status gcr_getscore_host(gcr_ctx *ctx, int problem, int scoring, int pair, const double *h_model,
+                             double squared_truncated_threshold, double threshold, double *h_score, uint32_t *h_count,
+                             uint32_t *h_inlier_idx);
+
 /* ---- K4 selection ----------------------------------------------------------------------------------------- */
 /* Running-argmax of GCRANSAC.h:440-471 with Score::operator< (scoring_function.h:63-66): best score, ties to the
  * LOWEST index.  d_keys [n_pairs] uint64 = (orderedFloatBits(score) << 32) | (0xFFFFFFFF - (index + index_base)):
