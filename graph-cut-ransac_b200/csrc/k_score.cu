@@ -289,38 +289,55 @@ __global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
 }
 
 // ----------------------------------------------------------------------------------- per-evaluation maths ----
+// packed f32x2 arithmetic, or (SC = true: experiment / fallback for toolchains without FFMA2) the same on two scalars
+template <bool SC> __device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c)
+{
+	if (SC) return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+	return __ffma2_rn(a, b, c);
+}
+template <bool SC> __device__ __forceinline__ float2 pmul(float2 a, float2 b)
+{
+	if (SC) return make_float2(a.x * b.x, a.y * b.y);
+	return __fmul2_rn(a, b);
+}
+template <bool SC> __device__ __forceinline__ float2 padd(float2 a, float2 b)
+{
+	if (SC) return make_float2(a.x + b.x, a.y + b.y);
+	return __fadd2_rn(a, b);
+}
+
 // u = r'^2 - t'^2 (MSAC) or r'^2 (MAGSAC) for two hypotheses side by side; point operands are duplicated pairs
-template <int PROBLEM, int SCORING>
+template <int PROBLEM, int SCORING, bool SC = false>
 __device__ __forceinline__ float2 eval2(const float2 (&h)[9], const float2 X1, const float2 Y1, const float2 X2,
                                         const float2 Y2, const float2 NEGT)
 {
 	if (PROBLEM == GCR_H)
 	{
-		const float2 t1 = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
-		const float2 t2 = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
-		const float2 t3 = __ffma2_rn(h[6], X1, __ffma2_rn(h[7], Y1, h[8]));
+		const float2 t1 = pfma<SC>(h[0], X1, pfma<SC>(h[1], Y1, h[2]));
+		const float2 t2 = pfma<SC>(h[3], X1, pfma<SC>(h[4], Y1, h[5]));
+		const float2 t3 = pfma<SC>(h[6], X1, pfma<SC>(h[7], Y1, h[8]));
 		const float2 inv = make_float2(rcp_approx(t3.x), rcp_approx(t3.y));
 		// the caller hands over -x2, -y2 (negated once per point), so d = t/t3 - x2 is one FMA
-		const float2 d1 = __ffma2_rn(t1, inv, X2);
-		const float2 d2 = __ffma2_rn(t2, inv, Y2);
+		const float2 d1 = pfma<SC>(t1, inv, X2);
+		const float2 d2 = pfma<SC>(t2, inv, Y2);
 		if (SCORING == GCR_MSAC)
-			return __ffma2_rn(d2, d2, __ffma2_rn(d1, d1, NEGT));
-		return __ffma2_rn(d2, d2, __fmul2_rn(d1, d1));
+			return pfma<SC>(d2, d2, pfma<SC>(d1, d1, NEGT));
+		return pfma<SC>(d2, d2, pmul<SC>(d1, d1));
 	}
 	else
 	{
-		const float2 rxc = __ffma2_rn(h[0], X2, __ffma2_rn(h[3], Y2, h[6]));
-		const float2 ryc = __ffma2_rn(h[1], X2, __ffma2_rn(h[4], Y2, h[7]));
-		const float2 rwc = __ffma2_rn(h[2], X2, __ffma2_rn(h[5], Y2, h[8]));
-		const float2 rr = __ffma2_rn(X1, rxc, __ffma2_rn(Y1, ryc, rwc));
-		const float2 rx = __ffma2_rn(h[0], X1, __ffma2_rn(h[1], Y1, h[2]));
-		const float2 ry = __ffma2_rn(h[3], X1, __ffma2_rn(h[4], Y1, h[5]));
-		const float2 den = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, __ffma2_rn(ryc, ryc, __fmul2_rn(rxc, rxc))));
+		const float2 rxc = pfma<SC>(h[0], X2, pfma<SC>(h[3], Y2, h[6]));
+		const float2 ryc = pfma<SC>(h[1], X2, pfma<SC>(h[4], Y2, h[7]));
+		const float2 rwc = pfma<SC>(h[2], X2, pfma<SC>(h[5], Y2, h[8]));
+		const float2 rr = pfma<SC>(X1, rxc, pfma<SC>(Y1, ryc, rwc));
+		const float2 rx = pfma<SC>(h[0], X1, pfma<SC>(h[1], Y1, h[2]));
+		const float2 ry = pfma<SC>(h[3], X1, pfma<SC>(h[4], Y1, h[5]));
+		const float2 den = pfma<SC>(ry, ry, pfma<SC>(rx, rx, pfma<SC>(ryc, ryc, pmul<SC>(rxc, rxc))));
 		const float2 inv = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-		const float2 rr2 = __fmul2_rn(rr, rr);
+		const float2 rr2 = pmul<SC>(rr, rr);
 		if (SCORING == GCR_MSAC)
-			return __ffma2_rn(rr2, inv, NEGT);
-		return __fmul2_rn(rr2, inv);
+			return pfma<SC>(rr2, inv, NEGT);
+		return pmul<SC>(rr2, inv);
 	}
 }
 
@@ -365,7 +382,7 @@ __device__ __forceinline__ void amb_record(const ScoreArgs &a, size_t gslot, int
 // and no scheduler atomics -- and partial sums meet in the integer accumulators.
 #define GRAN 32
 
-template <int PROBLEM, int SCORING, int R, bool EXACT>
+template <int PROBLEM, int SCORING, int R, bool EXACT, bool SC>
 __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const ScoreArgs a)
 {
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
@@ -533,10 +550,10 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 #pragma unroll
 							for (int q = 0; q < NQP; ++q)
 							{
-								const float2 v = eval2<PROBLEM, SCORING>(h2[q], X1, Y1, X2, Y2, NEGT);
+								const float2 v = eval2<PROBLEM, SCORING, SC>(h2[q], X1, Y1, X2, Y2, NEGT);
 								if (SCORING == GCR_MSAC)
 								{
-									T2[q] = __fadd2_rn(T2[q], make_float2(fminf(v.x, 0.f), fminf(v.y, 0.f)));
+									T2[q] = padd<SC>(T2[q], make_float2(fminf(v.x, 0.f), fminf(v.y, 0.f)));
 									cnt[2 * q] += __float_as_uint(v.x) >> 31; // u < 0 (generated NaNs are the positive canonical NaN)
 									cnt[2 * q + 1] += __float_as_uint(v.y) >> 31;
 									if (EXACT) mn = fminf(mn, fminf(fabsf(v.x), fabsf(v.y)));
@@ -546,7 +563,7 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 									const float ux = v.x + th.negT, uy = v.y + th.negT;
 									const float wx = magsac_weight(s_lut, v.x, th.c_idx), wy = magsac_weight(s_lut, v.y, th.c_idx);
 									const bool inx = ux <= 0.f, iny = uy <= 0.f;
-									T2[q] = __fadd2_rn(T2[q], make_float2(inx ? wx : 0.f, iny ? wy : 0.f));
+									T2[q] = padd<SC>(T2[q], make_float2(inx ? wx : 0.f, iny ? wy : 0.f));
 									cnt[2 * q] += inx ? 1u : 0u;
 									cnt[2 * q + 1] += iny ? 1u : 0u;
 									if (EXACT) mn = fminf(mn, fminf(fabsf(ux), fabsf(uy)));
@@ -593,7 +610,7 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 								float vv[2];
 								if (PACKED)
 								{
-									const float2 v = eval2<PROBLEM, SCORING>(h2[PACKED ? q : 0], X1, Y1, X2, Y2, NEGT);
+									const float2 v = eval2<PROBLEM, SCORING, SC>(h2[PACKED ? q : 0], X1, Y1, X2, Y2, NEGT);
 									vv[0] = v.x;
 									vv[1] = v.y;
 								}
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 #pragma unroll
 				for (int q = 0; q < NQP; ++q)
 				{
-					S2[q] = __fadd2_rn(S2[q], T2[q]);
+					S2[q] = padd<SC>(S2[q], T2[q]);
 					T2[q] = make_float2(0.f, 0.f);
 				}
 #pragma unroll
@@ -805,7 +822,7 @@ static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
 	return GCR_OK;
 }
 
-template <int PROBLEM, int SCORING, int R>
+template <int PROBLEM, int SCORING, int R, bool SC = false>
 static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 {
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
@@ -814,7 +831,7 @@ static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 		return st;
 	a.hyps_per_item = THREADS * R;
 	const size_t smem = (size_t)STAGES * TILE * 2 * sizeof(float4) + 64 + (SCORING == GCR_MAGSAC ? 5008 * sizeof(float) : 0);
-	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true> : k_score_main<PROBLEM, SCORING, R, false>;
+	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true, SC> : k_score_main<PROBLEM, SCORING, R, false, SC>;
 	GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -859,6 +876,7 @@ static gcr_status launch_problem(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 		case 0: return launch_variant<PROBLEM, SCORING, 4>(ctx, a, exact);
 		case 1: return launch_variant<PROBLEM, SCORING, 6>(ctx, a, exact);
 		case 2: return launch_variant<PROBLEM, SCORING, 8>(ctx, a, exact);
+		case 3: return launch_variant<PROBLEM, SCORING, 4, true>(ctx, a, exact);
 		default: return launch_variant<PROBLEM, SCORING, 4>(ctx, a, exact);
 		}
 	}

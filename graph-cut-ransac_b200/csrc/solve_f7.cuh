@@ -4,81 +4,69 @@
 // estimators/fundamental_estimator.h:737-800.  Differences from the reference, by design:
 //   * the null space comes from a full-pivot LU written out here with Eigen 3.4 FullPivLU::kernel() semantics
 //     (column-major pivot search, rank threshold eps * 7 * max pivot, free variables set to unit vectors);
-//   * the cubic is solved by bracketing at the derivative's roots + safeguarded Newton instead of the companion-matrix
+//   * the cubic is solved in closed form (Cardano / trigonometric) + three Newton steps instead of the companion-matrix
 //     eigen-solve of Eigen::PolynomialSolver; real roots come out in ASCENDING order (Eigen's order is unspecified).
 #pragma once
 
 namespace gcr_f7
 {
-	struct Cubic
-	{
-		double a, b, c; // monic x^3 + a x^2 + b x + c
-		__device__ __forceinline__ double p(double x) const { return ((x + a) * x + b) * x + c; }
-		__device__ __forceinline__ double dp(double x) const { return (3.0 * x + 2.0 * a) * x + b; }
-
-		// root inside [lo, hi] where p changes sign; Newton with bisection safeguard ("rtsafe")
-		__device__ double bracket(double lo, double hi) const
-		{
-			const double fl = p(lo), fh = p(hi);
-			if (fl == 0.0) return lo;
-			if (fh == 0.0) return hi;
-			double xl, xh;
-			if (fl < 0.0) { xl = lo; xh = hi; }
-			else { xl = hi; xh = lo; }
-			double rts = 0.5 * (lo + hi);
-			double dxold = fabs(hi - lo), dx = dxold;
-			double f = p(rts), df = dp(rts);
-			for (int it = 0; it < 200; ++it)
-			{
-				if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df)))
-				{
-					dxold = dx;
-					dx = 0.5 * (xh - xl);
-					rts = xl + dx;
-					if (xl == rts) return rts;
-				}
-				else
-				{
-					dxold = dx;
-					dx = f / df;
-					const double temp = rts;
-					rts -= dx;
-					if (temp == rts) return rts;
-				}
-				if (fabs(dx) <= 4.440892098500626e-16 * fabs(rts)) return rts;
-				f = p(rts);
-				df = dp(rts);
-				if (f < 0.0) xl = rts;
-				else xh = rts;
-			}
-			return rts;
-		}
-	};
-
-	// real roots of c0 + c1 x + c2 x^2 + c3 x^3 (c3 != 0), ascending; returns their number (1..3)
+	// Real roots of c0 + c1 x + c2 x^2 + c3 x^3 (c3 != 0), ascending; returns their number (1 or 3).
+	// Closed form (Cardano for one real root, the trigonometric form for three) followed by three Newton steps on the
+	// monic cubic: fixed work per call, no data-dependent iteration count (the earlier bracketing + safeguarded Newton
+	// version spent ~9000 instructions per sample walking in from the Cauchy bound).  oracle/gcr_oracle_f.cpp runs the
+	// same statements; libm's cbrt / acos / cos differ from CUDA's by <= 2 ulp, which the Newton steps absorb except
+	// on near-multiple roots (tests compare at 1e-6, the north star allows 1e-5).
 	__device__ inline int cubic_roots(double c0, double c1, double c2, double c3, double *roots)
 	{
-		Cubic q;
-		q.a = c2 / c3;
-		q.b = c1 / c3;
-		q.c = c0 / c3;
-		const double R = 1.0 + fmax(fabs(q.a), fmax(fabs(q.b), fabs(q.c))); // Cauchy bound
-		const double disc = q.a * q.a - 3.0 * q.b;
-		int n = 0;
-		if (!(disc > 0.0))
+		const double a = c2 / c3, b = c1 / c3, c = c0 / c3;
+		const double a3 = a / 3.0;
+		const double p = b - a * a3;                              // depressed cubic t^3 + p t + q, x = t - a / 3
+		const double q = 2.0 * a3 * a3 * a3 - a3 * b + c;
+		const double hq = 0.5 * q, tp = p / 3.0;
+		const double disc = hq * hq + tp * tp * tp;
+		int n;
+		if (disc > 0.0 || !(tp < 0.0))
 		{
-			roots[n++] = q.bracket(-R, R);
-			return n;
+			const double s = sqrt(fmax(disc, 0.0));
+			const double u = -copysign(cbrt(fabs(hq) + s), hq);   // the larger-magnitude cube root: no cancellation
+			const double t = u != 0.0 ? u - tp / u : 0.0;
+			roots[0] = t - a3;
+			n = 1;
 		}
-		const double sq = sqrt(disc);
-		const double x1 = (-q.a - sq) / 3.0, x2 = (-q.a + sq) / 3.0; // local max at x1 < local min at x2
-		const double p1 = q.p(x1), p2 = q.p(x2);
-		if (p1 >= 0.0)
-			roots[n++] = (p1 == 0.0) ? x1 : q.bracket(-R, x1);
-		if (p1 > 0.0 && p2 < 0.0)
-			roots[n++] = q.bracket(x1, x2);
-		if (p2 <= 0.0)
-			roots[n++] = (p2 == 0.0) ? x2 : q.bracket(x2, R);
+		else
+		{
+			const double m = 2.0 * sqrt(-tp);
+			double arg = -hq / (-tp * sqrt(-tp));                  // cos(3 theta)
+			arg = fmin(1.0, fmax(-1.0, arg));
+			const double theta = acos(arg) / 3.0;
+			const double two_pi_3 = 2.0943951023931954923;
+			roots[0] = m * cos(theta + two_pi_3) - a3;             // ascending for theta in [0, pi / 3]
+			roots[1] = m * cos(theta - two_pi_3) - a3;
+			roots[2] = m * cos(theta) - a3;
+			n = 3;
+		}
+		for (int r = 0; r < 3; ++r)
+		{
+			if (r < n)
+			{
+				double x = roots[r];
+#pragma unroll
+				for (int it = 0; it < 3; ++it)
+				{
+					const double f = ((x + a) * x + b) * x + c;
+					const double d = (3.0 * x + 2.0 * a) * x + b;
+					if (d != 0.0 && isfinite(f / d))
+						x -= f / d;
+				}
+				roots[r] = x;
+			}
+		}
+		if (n == 3) // Newton can reorder near-coincident roots
+		{
+			if (roots[0] > roots[1]) { const double t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+			if (roots[1] > roots[2]) { const double t = roots[1]; roots[1] = roots[2]; roots[2] = t; }
+			if (roots[0] > roots[1]) { const double t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+		}
 		return n;
 	}
 

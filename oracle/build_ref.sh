@@ -13,3 +13,12 @@ g++ -O3 -ftree-vectorize -funroll-loops -ffp-contract=off -flto -std=c++17 -w -f
     -Ishim -I"$REF" -I. \
     -o _ref/libgcr_ref.so ref_glue.cpp gcr_oracle_*.cpp "$REF/graph.cpp" "$REF/maxflow.cpp"
 echo "built oracle/_ref/libgcr_ref.so"
+# the same driver with the CUDA scoring adapter as its template argument (links the product library)
+PKG=../graph-cut-ransac_b200
+if [ -f "$PKG/libgcr_b200.so" ]; then
+g++ -O2 -std=c++17 -w -fPIC -shared -ffp-contract=off \
+    -Ishim -I"$REF" -I. -I../include -I"$PKG/host" \
+    -o _ref/libgcr_ref_cuda.so ref_glue_cuda.cpp gcr_oracle_*.cpp "$REF/graph.cpp" "$REF/maxflow.cpp" \
+    -L"$PKG" -lgcr_b200 -Wl,-rpath,'$ORIGIN/../../graph-cut-ransac_b200'
+echo "built oracle/_ref/libgcr_ref_cuda.so"
+fi

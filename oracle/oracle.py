@@ -246,10 +246,15 @@ class Oracle:
 class Ref:
     """The reference's own headers compiled verbatim (oracle/_ref/libgcr_ref.so)."""
 
+    SO_NAME = "libgcr_ref.so"
+
     def __init__(self):
         so = build_ref()
         if so is None:
             raise FileNotFoundError("oracle/_ref/libgcr_ref.so is not built and /root/reference is absent")
+        so = os.path.join(os.path.dirname(so), self.SO_NAME)
+        if not os.path.exists(so):
+            raise FileNotFoundError("%s is not built" % so)
         self.lib = lib = C.CDLL(so)
         lib.ref_score.restype = None
         lib.ref_score.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_double, C.POINTER(C.c_double),
@@ -267,8 +272,33 @@ class Ref:
         lib.ref_round.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
                                   C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _dp]
 
+        lib.ref_run.restype = C.c_int
+        lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
+                                _u64p, C.POINTER(C.c_double)]
+
     def round(self, problem, scoring, pts, seed, first, count, thr):
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
+
+    def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0):
+        """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
+        counter-based sample stream.  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
+        (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
+        pts = _as_pts(pts)
+        model = np.zeros(9)
+        mask = np.zeros(len(pts), dtype=np.uint8)
+        stats = np.zeros(8, dtype=np.uint64)
+        score = C.c_double()
+        n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
+                                 conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
+                                 C.byref(score))
+        if n_inl < 0:
+            raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
+        names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",
+                 "main_samples", "lo_samples")
+        return dict(model=model.reshape(3, 3), mask=mask.astype(bool), inliers=n_inl, score=score.value,
+                    stats=dict(zip(names, (int(v) for v in stats))))
 
     def score(self, problem, scoring, pts, model, thr, want_inliers=False):
         pts = _as_pts(pts)
@@ -303,3 +333,9 @@ class Ref:
 
     def iteration_number(self, inliers, n, m, log_probability):
         return self.lib.ref_iteration_number(inliers, n, m, log_probability)
+
+
+class RefCuda(Ref):
+    """The same verbatim reference driver with gcr::CudaMSACScoringFunction (graph-cut-ransac_b200/host/
+    gcr_scoring_function.h) as its _ScoringFunction template argument; links libgcr_b200.so, needs a GPU to run."""
+    SO_NAME = "libgcr_ref_cuda.so"

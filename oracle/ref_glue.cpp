@@ -348,3 +348,120 @@ uint64_t ref_iteration_number(uint64_t inliers, uint64_t n, int m, double log_pr
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Whole GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) on the counter-based sample stream -- config 1's CPU anchor and
+// the harness for the drop-in scoring adapter.  The Sampler below implements the reference's virtual Sampler interface
+// (samplers/sampler.h:44-86): call k of the main (LO) sampler returns sample k of stream 0 (stream 1) of the Philox
+// generator, uniform over the pool exactly like UniformSampler::sample (uniform_sampler.h:81-99).
+namespace
+{
+	class CounterSampler : public sampler::Sampler<cv::Mat, size_t>
+	{
+		uint64_t seed, next;
+		uint32_t stream;
+		std::vector<uint32_t> tmp;
+
+	public:
+		CounterSampler(const cv::Mat *c, uint64_t seed_, uint32_t stream_) : sampler::Sampler<cv::Mat, size_t>(c), seed(seed_), next(0), stream(stream_)
+		{
+			initialized = true;
+		}
+		const std::string getName() const { return "Counter-based uniform sampler"; }
+		void reset() {}
+		void update(const size_t *const, const size_t &, const size_t &, const double &) {}
+		bool initialize(const cv::Mat *const) { return true; }
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &pool_, size_t *const subset_, size_t sample_size_)
+		{
+			if (sample_size_ > pool_.size())
+				return false;
+			tmp.resize(sample_size_);
+			gcro_sample_uniform(seed, next++, stream, (uint32_t)pool_.size(), (int)sample_size_, tmp.data());
+			for (size_t i = 0; i < sample_size_; ++i)
+				subset_[i] = pool_[tmp[i]];
+			return true;
+		}
+	};
+
+	template <int PROBLEM, class Scoring>
+	int run_reference(const cv::Mat &points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
+	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
+	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out)
+	{
+		typedef OracleEstimator<PROBLEM> Est;
+		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
+		Est estimator;
+		std::vector<double> cs(cell_sizes, cell_sizes + 4);
+		Grid graph(&points, cs, (size_t)cells_per_axis);
+		CounterSampler main_sampler(&points, seed, 0u), lo_sampler(&points, seed, 1u);
+		Model model;
+		GCRANSAC<Est, Grid, Scoring> gcransac;
+		// py/gcransac_python.cpp:4498-4504
+		gcransac.settings.threshold = threshold;
+		gcransac.settings.spatial_coherence_weight = spatial_weight;
+		gcransac.settings.confidence = conf;
+		gcransac.settings.max_local_optimization_number = lo_number;
+		gcransac.settings.max_iteration_number = max_iters;
+		gcransac.settings.min_iteration_number = min_iters;
+		gcransac.settings.neighborhood_sphere_radius = cells_per_axis;
+		gcransac.run(points, estimator, &main_sampler, &lo_sampler, &graph, model);
+		const utils::RANSACStatistics &st = gcransac.getRansacStatistics();
+		for (int i = 0; i < points.rows; ++i)
+			inlier_mask[i] = 0;
+		for (size_t idx : st.inliers)
+			inlier_mask[idx] = 1;
+		if (st.inliers.size() > 0)
+			to_flat(model.descriptor, model_out);
+		if (stats_out)
+		{
+			stats_out[0] = st.iteration_number;
+			stats_out[1] = st.graph_cut_number;
+			stats_out[2] = st.local_optimization_number;
+			stats_out[3] = st.neighbor_number;
+			stats_out[4] = st.accepted_models;
+			stats_out[5] = st.rejected_models;
+			stats_out[6] = main_sampler.drawn();
+			stats_out[7] = lo_sampler.drawn();
+		}
+		if (score_out)
+			*score_out = st.score;
+		return (int)st.inliers.size();
+	}
+}
+
+#ifdef GCR_REF_WITH_CUDA
+#include "gcr_scoring_function.h" // graph-cut-ransac_b200/host: the drop-in adapter over libgcr_b200.so
+#endif
+
+extern "C" {
+
+// scoring_kind: 0 = reference MSACScoringFunction (verbatim CPU), 1 = gcr::CudaMSACScoringFunction (library built with
+// GCR_REF_WITH_CUDA only).  Returns the inlier count.
+int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
+            double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
+            uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out)
+{
+	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
+#define GCR_RUN(P, S) run_reference<P, S>(points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out)
+	if (scoring_kind == 0)
+	{
+		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);
+		if (problem == GCRO_F) return GCR_RUN(GCRO_F, MSACScoringFunction<OracleEstimator<GCRO_F>>);
+		return -1;
+	}
+#ifdef GCR_REF_WITH_CUDA
+	if (scoring_kind == 1)
+	{
+		typedef gcr::CudaMSACScoringFunction<OracleEstimator<GCRO_H>, GCR_H> SH;
+		typedef gcr::CudaMSACScoringFunction<OracleEstimator<GCRO_F>, GCR_F> SF;
+		if (problem == GCRO_H) return GCR_RUN(GCRO_H, SH);
+		if (problem == GCRO_F) return GCR_RUN(GCRO_F, SF);
+		return -1;
+	}
+#endif
+#undef GCR_RUN
+	return -2;
+}
+
+} // extern "C"
