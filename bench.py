@@ -34,6 +34,10 @@ WORKLOADS = {
                 desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
     "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
                       desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 (configs[3])"),
+    # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL max all-reduce of the key
+    "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps",
+                        desc="single F problem, N=1048576 x K=1048576 7-pt samples sharded over the GPUs, MSAC, "
+                             "NCCL max all-reduce of the (score, index) key (configs[4])"),
 }
 
 
@@ -41,7 +45,7 @@ def make_points(wl, rank):
     from pygcransac import synth
     pts = []
     for p in range(wl["pairs"]):
-        seed = 1000 * rank + p + 1
+        seed = (0 if wl.get("shard") == "hyps" else 1000 * rank) + p + 1   # a sharded problem is the SAME on every rank
         if wl["problem"] == "f":
             pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])
         else:
@@ -110,6 +114,12 @@ def fp32_peak_tflops(sm_count):
 _CPU_IMPL = {}
 
 
+def cpu_samples_per_core(wl):
+    """Bounded CPU sample: ~1 s of single-core work per step (65536 7-point / 8192 4-point samples at N = 4096, scaled by N)."""
+    base = 65536 if wl["problem"] == "f" else 8192
+    return max(8, int(base * 4096 / wl["n"]))
+
+
 def cpu_round_worker(args):
     """One CPU slice: `count` samples of the same workload through the reference scoring loop (or the port)."""
     kind, problem, pts, seed, first, count, thr = args
@@ -162,7 +172,7 @@ def bench_reference(args, wl, rank, world):
     pts0 = make_points(dict(wl, pairs=1), 0)[0]
     arm = CpuArm(wl, pts0)
     # bounded sample per step: ~1 s of all-core CPU work on an 8-core host
-    per_step = (65536 if wl["problem"] == "f" else 8192) * arm.cores
+    per_step = cpu_samples_per_core(wl) * arm.cores
     for s in range(args.warmup):
         arm.run(per_step // 8)
     t_total, evals_total, used = 0.0, 0, 0
@@ -245,14 +255,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(i):
+    hyps_sharded = wl.get("shard") == "hyps"
+
+    def one_round(i):
+        if hyps_sharded:
+            from pygcransac import sharded
+            return sharded.sharded_round(ctx, prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
+                                         wl["thr"], flags, keys, best, 3 if wl["problem"] == "f" else 1, rank, world)
         return ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
                                 flags, 0, keys.data_ptr(), best.data_ptr())
 
+    def step_resident(i):
+        return one_round(i)
+
     def step_e2e(i):
         ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
-        ev = ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
-                              flags, 0, keys.data_ptr(), best.data_ptr())
+        ev = one_round(i)
         keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
         best_host.copy_(best, non_blocking=True)
         return ev
@@ -329,7 +347,8 @@ def main():
         line = {
             "metric": "hypothesis x point evals/s", "value": evals / (ms * 1e-3), "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if hyps_sharded else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
                        "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
                        "exact_counts": not args.no_exact, "k3_variant": args.variant,
@@ -348,7 +367,7 @@ def main():
         }
         if not args.no_cpu:
             arm = CpuArm(wl, pts_host[0].numpy().copy())
-            cpu_samples = (65536 if wl["problem"] == "f" else 8192) * arm.cores * 10
+            cpu_samples = cpu_samples_per_core(wl) * arm.cores * 10
             c_evals, c_wall, used = arm.run(cpu_samples)
             arm.close()
             line["cpu_baseline"] = {"value": c_evals / c_wall, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,

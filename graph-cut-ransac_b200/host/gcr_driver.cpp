@@ -1,0 +1,680 @@
+// gcr_driver.cpp -- see gcr_driver.h.  Host C++; the only compile-time dependency on the reference tree is its
+// vendored Boykov-Kolmogorov max-flow (energy.h / graph.h + graph.cpp / maxflow.cpp), which stays the reference's code.
+#include "gcr_driver.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "energy.h" // reference: src/pygcransac/include/energy.h (Energy<> over Graph<>, BK max-flow)
+
+namespace
+{
+	struct Score
+	{
+		double value = 0.0;
+		uint64_t inliers = 0;
+	};
+
+	// GCRANSAC.h:158-172
+	uint64_t iteration_number(uint64_t inliers, uint64_t n, int m, double log_probability)
+	{
+		const double q = std::pow(static_cast<double>(inliers) / n, m);
+		const double log2 = std::log(1 - q);
+		if (std::fabs(log2) < std::numeric_limits<double>::epsilon())
+			return std::numeric_limits<uint64_t>::max();
+		const double iter = log_probability / log2;
+		return static_cast<uint64_t>(iter) + 1;
+	}
+
+	// fundamental_estimator.h:225-253
+	double sq_symmetric_epipolar(const double *s, const double *F)
+	{
+		const double x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
+		const double rxc = F[0] * x2 + F[3] * y2 + F[6];
+		const double ryc = F[1] * x2 + F[4] * y2 + F[7];
+		const double rwc = F[2] * x2 + F[5] * y2 + F[8];
+		const double r = (x1 * rxc + y1 * ryc + rwc);
+		const double rx = F[0] * x1 + F[1] * y1 + F[2];
+		const double ry = F[3] * x1 + F[4] * y1 + F[5];
+		const double a = rxc * rxc + ryc * ryc;
+		const double b = rx * rx + ry * ry;
+		return r * r * (a + b) / (a * b);
+	}
+
+	struct DeviceBuffer
+	{
+		gcr_ctx *ctx = nullptr;
+		void *p = nullptr;
+		size_t bytes = 0;
+		~DeviceBuffer() { if (p) gcr_free(ctx, p); }
+		bool ensure(gcr_ctx *c, size_t need)
+		{
+			ctx = c;
+			if (need <= bytes)
+				return true;
+			if (p) gcr_free(ctx, p);
+			p = nullptr;
+			bytes = 0;
+			if (gcr_malloc(ctx, need, &p) != GCR_OK)
+				return false;
+			bytes = need;
+			return true;
+		}
+		template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+	};
+
+	// One of the two inlier containers of GCRANSAC::run (temp_inner_inliers, GCRANSAC.h:245-247).  Every getScore of the
+	// reference overwrites the current container; here the contents are only materialised when somebody reads them.
+	struct InlierBuffer
+	{
+		bool lazy = false;      // holds "the inliers of `model`", not fetched yet
+		double model[9] = {0};
+		uint64_t lazy_count = 0;
+		std::vector<uint32_t> idx;
+		size_t size() const { return lazy ? (size_t)lazy_count : idx.size(); }
+	};
+
+	class Driver
+	{
+	public:
+		gcr_ctx *ctx;
+		int problem, n, m, mm;
+		const double *pts;
+		gcr_run_settings S;
+		gcr_run_stats st;
+		double T; // squared truncated threshold (GCRANSAC.h:253-254)
+		double truncated_threshold;
+		std::string error;
+
+		// main-loop batch
+		int B = 0;
+		uint64_t batch_first = 0;
+		int batch_count = 0;
+		DeviceBuffer d_samples, d_models, d_valid, d_scores, d_counts;
+		std::vector<uint8_t> h_valid;
+		std::vector<float> h_scores;
+		std::vector<uint32_t> h_counts;
+		std::vector<double> h_models;
+		// exact scoring
+		DeviceBuffer d_one_model, d_one_score, d_one_count, d_idx, d_res;
+		// LO batch
+		DeviceBuffer d_pool, d_sets, d_offsets, d_sizes, d_lmodels, d_lok, d_lscores, d_lcounts, d_weights;
+		// grid
+		std::vector<uint32_t> cell_of_point, sorted_idx, cell_offsets;
+		bool have_grid = false;
+
+		bool fail(const char *what)
+		{
+			error = std::string(what) + ": " + gcr_last_error(ctx);
+			return false;
+		}
+
+		// ---- FP64 getScore of one model (scoring_function.h:137-233): score, count, ascending inlier list ----
+		bool exact(const double *model, Score &s, std::vector<uint32_t> *inliers, std::vector<double> *residuals = nullptr)
+		{
+			++st.exact_rescores;
+			if (!residuals)
+			{
+				uint32_t count = 0;
+				if (inliers) inliers->resize(n);
+				if (gcr_getscore_host(ctx, problem, GCR_MSAC, 0, model, T, S.threshold, &s.value, &count,
+				                      inliers ? inliers->data() : nullptr) != GCR_OK)
+					return fail("gcr_getscore_host");
+				s.inliers = count;
+				if (inliers) inliers->resize(count);
+				return true;
+			}
+			if (!d_one_model.ensure(ctx, 9 * sizeof(double)) || !d_one_score.ensure(ctx, sizeof(double)) ||
+			    !d_one_count.ensure(ctx, sizeof(uint32_t)) || !d_idx.ensure(ctx, (size_t)n * sizeof(uint32_t)) ||
+			    !d_res.ensure(ctx, (size_t)n * sizeof(double)))
+				return fail("gcr_malloc");
+			if (gcr_memcpy_h2d(ctx, d_one_model.p, model, 9 * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_h2d");
+			if (gcr_score_exact(ctx, problem, GCR_MSAC, 0, d_one_model.as<double>(), 1, S.threshold, d_one_score.as<double>(),
+			                    d_one_count.as<uint32_t>(), d_idx.as<uint32_t>(), d_res.as<double>()) != GCR_OK)
+				return fail("gcr_score_exact");
+			uint32_t count = 0;
+			if (gcr_memcpy_d2h(ctx, &s.value, d_one_score.p, sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, &count, d_one_count.p, sizeof(uint32_t)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			s.inliers = count;
+			residuals->resize(n);
+			if (gcr_memcpy_d2h(ctx, residuals->data(), d_res.p, (size_t)n * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			if (inliers)
+			{
+				inliers->resize(count);
+				if (count && gcr_memcpy_d2h(ctx, inliers->data(), d_idx.p, (size_t)count * sizeof(uint32_t)) != GCR_OK)
+					return fail("gcr_memcpy_d2h");
+			}
+			return true;
+		}
+
+		bool materialise(InlierBuffer &b)
+		{
+			if (!b.lazy)
+				return true;
+			Score s;
+			if (!exact(b.model, s, &b.idx))
+				return false;
+			b.lazy = false;
+			return true;
+		}
+
+		// ---- isValidModel ----
+		bool is_valid_model(const double *model, const std::vector<uint32_t> &inliers) const
+		{
+			if (problem == GCR_H)
+			{
+				// homography_estimator.h:326-342: |det H| >= 1e-2
+				const double *H = model;
+				const double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) +
+				                   H[2] * (H[3] * H[7] - H[4] * H[6]);
+				return !(std::fabs(det) < 1e-2);
+			}
+			// fundamental_estimator.h:287-318 (symmetric-epipolar ratio test; DEGENSAC stays with the host estimator)
+			const double a = (double)m, b = inliers.size() * 0.5;
+			const double minimum_inlier_number = a < b ? b : a;
+			const double squared_threshold = truncated_threshold * truncated_threshold;
+			size_t inlier_number = 0;
+			for (uint32_t i : inliers)
+				if (sq_symmetric_epipolar(pts + 4 * (size_t)i, model) < squared_threshold)
+					if (++inlier_number >= minimum_inlier_number)
+						return true;
+			return false;
+		}
+
+		// ---- one GPU batch of the main loop: samples [first, first + B) -> models, valid flags, FP32 scores, exact counts ----
+		bool run_batch(uint64_t first)
+		{
+			const size_t K = (size_t)B * mm;
+			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * 9 * sizeof(double)) ||
+			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
+				return fail("gcr_malloc");
+			if (gcr_sample(ctx, GCR_UNIFORM, m, first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
+				return fail("gcr_sample");
+			if (gcr_solve_minimal(ctx, problem, d_samples.as<uint32_t>(), B, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
+				return fail("gcr_solve_minimal");
+			if (gcr_score(ctx, problem, GCR_MSAC, d_models.as<double>(), d_valid.as<uint8_t>(), (int)K, S.threshold,
+			              GCR_SCORE_EXACT_COUNTS, d_scores.as<float>(), d_counts.as<uint32_t>()) != GCR_OK)
+				return fail("gcr_score");
+			h_valid.resize(K);
+			h_scores.resize(K);
+			h_counts.resize(K);
+			h_models.resize(K * 9);
+			if (gcr_memcpy_d2h(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			batch_first = first;
+			batch_count = B;
+			++st.gpu_batches;
+			return true;
+		}
+
+		// ---- GCRANSAC::labeling (GCRANSAC.h:913-1021): unary terms from GPU residuals, BK min-cut on the host ----
+		bool labeling(const double *model, std::vector<uint32_t> &inliers)
+		{
+			Score s;
+			std::vector<double> r2;
+			if (!exact(model, s, nullptr, &r2))
+				return false;
+			const auto t0 = std::chrono::steady_clock::now();
+			const double lambda = S.spatial_coherence_weight;
+			Energy<double, double, double> *problem_graph = new Energy<double, double, double>(n, 0, NULL);
+			for (int i = 0; i < n; ++i)
+				problem_graph->add_node();
+			std::vector<double> distance_per_threshold(n);
+			const double squared_truncated_threshold = S.threshold * S.threshold * 9 / 4;
+			const double one_minus_lambda = 1.0 - lambda;
+			for (int i = 0; i < n; ++i)
+			{
+				const double d = r2[i] / squared_truncated_threshold;
+				distance_per_threshold[i] = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : d); // utils::clamp
+				const double tmp_energy = 1 - distance_per_threshold[i];
+				if (r2[i] <= squared_truncated_threshold)
+					problem_graph->add_term1(i, one_minus_lambda * tmp_energy, 0);
+				else
+					problem_graph->add_term1(i, 0, one_minus_lambda * (1 - tmp_energy));
+			}
+			if (lambda > 0 && have_grid)
+			{
+				// the reference walks point_idx ascending and, per point, its cell's list ascending, skipping pairs already
+				// used (the N x N used_edges matrix, :963): exactly the pairs (i, j > i) of a cell, in this order
+				for (int i = 0; i < n; ++i)
+				{
+					const uint32_t c = cell_of_point[i];
+					const double energy1 = distance_per_threshold[i];
+					for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
+					{
+						const uint32_t j = sorted_idx[q];
+						if ((int)j <= i)
+							continue;
+						const double e00 = 0.5 * (energy1 + distance_per_threshold[j]);
+						problem_graph->add_term2(i, j, e00 * lambda, lambda, lambda, 0 * lambda);
+					}
+				}
+			}
+			problem_graph->minimize();
+			inliers.clear();
+			for (int i = 0; i < n; ++i)
+				if (problem_graph->what_segment(i) == Graph<double, double, double>::SINK)
+					inliers.push_back((uint32_t)i);
+			delete problem_graph;
+			st.graph_cut_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			return true;
+		}
+
+		// ---- non-minimal refit of `count` index sets (one GPU launch) ----
+		bool refit(const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
+		           const double *weights_by_point, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
+		           bool sets_on_device = false)
+		{
+			const int count = (int)sizes.size();
+			size_t total = 0;
+			for (uint32_t v : sizes) total += v;
+			if (!sets_on_device)
+			{
+				if (!d_sets.ensure(ctx, std::max<size_t>(total, 1) * sizeof(uint32_t)))
+					return fail("gcr_malloc");
+				if (gcr_memcpy_h2d(ctx, d_sets.p, flat, total * sizeof(uint32_t)) != GCR_OK)
+					return fail("gcr_memcpy_h2d");
+			}
+			if (!d_offsets.ensure(ctx, count * sizeof(uint32_t)) || !d_sizes.ensure(ctx, count * sizeof(uint32_t)) ||
+			    !d_lmodels.ensure(ctx, (size_t)count * 9 * sizeof(double)) || !d_lok.ensure(ctx, count))
+				return fail("gcr_malloc");
+			if (gcr_memcpy_h2d(ctx, d_offsets.p, offsets.data(), count * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_h2d(ctx, d_sizes.p, sizes.data(), count * sizeof(uint32_t)) != GCR_OK)
+				return fail("gcr_memcpy_h2d");
+			const double *d_w = nullptr;
+			if (weights_by_point)
+			{
+				if (!d_weights.ensure(ctx, (size_t)n * sizeof(double)))
+					return fail("gcr_malloc");
+				if (gcr_memcpy_h2d(ctx, d_weights.p, weights_by_point, (size_t)n * sizeof(double)) != GCR_OK)
+					return fail("gcr_memcpy_h2d");
+				d_w = d_weights.as<double>();
+			}
+			if (gcr_refit(ctx, problem, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
+			              weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
+				return fail("gcr_refit");
+			models.resize((size_t)count * 9);
+			ok.resize(count);
+			if (gcr_memcpy_d2h(ctx, models.data(), d_lmodels.p, (size_t)count * 9 * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, ok.data(), d_lok.p, count) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			return true;
+		}
+
+		// ---- graphCutLocalOptimization (GCRANSAC.h:780-910) ----
+		bool local_optimization(InlierBuffer &best_inliers_out, double *best_model, Score &best_score)
+		{
+			const size_t inlier_limit = 7 * (size_t)m; // estimator.inlierLimit()
+			const int trials = (int)S.max_local_optimization_number;
+			Score max_score = best_score;
+			double lbest_model[9];
+			memcpy(lbest_model, best_model, sizeof(lbest_model));
+			std::vector<uint32_t> lbest_inliers, inliers, tmp;
+			++st.local_optimization_number;
+			while (++st.graph_cut_number < S.max_graph_cut_number)
+			{
+				bool updated = false;
+				if (!labeling(lbest_model, inliers))
+					return false;
+				const size_t sample_size = std::min(inlier_limit, inliers.size());
+				std::vector<double> models;
+				std::vector<uint8_t> ok;
+				std::vector<float> scores32;
+				int n_models = 0;
+				if (sample_size < inliers.size() && trials > 0)
+				{
+					// inner RANSAC as one batch: `trials` pool samples -> refits -> FP32 scores
+					if (!d_pool.ensure(ctx, inliers.size() * sizeof(uint32_t)) ||
+					    !d_sets.ensure(ctx, (size_t)trials * sample_size * sizeof(uint32_t)))
+						return fail("gcr_malloc");
+					if (gcr_memcpy_h2d(ctx, d_pool.p, inliers.data(), inliers.size() * sizeof(uint32_t)) != GCR_OK)
+						return fail("gcr_memcpy_h2d");
+					if (gcr_sample_from_pool(ctx, d_pool.as<uint32_t>(), (uint32_t)inliers.size(), (int)sample_size, st.lo_samples,
+					                         trials, S.seed, 1u, d_sets.as<uint32_t>()) != GCR_OK)
+						return fail("gcr_sample_from_pool");
+					st.lo_samples += trials;
+					std::vector<uint32_t> offsets(trials), sizes(trials, (uint32_t)sample_size);
+					for (int t = 0; t < trials; ++t) offsets[t] = (uint32_t)(t * sample_size);
+					if (!refit(nullptr, offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, true))
+						return false;
+					n_models = trials;
+				}
+				else if ((size_t)m < inliers.size() && trials > 0)
+				{
+					// all inliers, every trial fits the same model: once is enough (later trials cannot beat it, strict '<')
+					std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
+					if (!refit(inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
+						return false;
+					n_models = ok[0] ? 1 : 0;
+				}
+				if (n_models > 0)
+				{
+					if (!d_lscores.ensure(ctx, n_models * sizeof(float)))
+						return fail("gcr_malloc");
+					if (gcr_score(ctx, problem, GCR_MSAC, d_lmodels.as<double>(), d_lok.as<uint8_t>(), n_models, S.threshold, 0,
+					              d_lscores.as<float>(), nullptr) != GCR_OK)
+						return fail("gcr_score");
+					scores32.resize(n_models);
+					if (gcr_memcpy_d2h(ctx, scores32.data(), d_lscores.p, n_models * sizeof(float)) != GCR_OK)
+						return fail("gcr_memcpy_d2h");
+					st.models_scored += n_models;
+					for (int t = 0; t < n_models; ++t)
+					{
+						if (!ok[t])
+							continue;
+						if (!((double)scores32[t] > max_score.value * (1.0 - 2e-4)))
+							continue; // FP32 ranking says it cannot beat the best so far
+						Score s;
+						if (!exact(&models[(size_t)t * 9], s, &tmp))
+							return false;
+						if (max_score.value < s.value) // :880
+						{
+							updated = true;
+							max_score = s;
+							memcpy(lbest_model, &models[(size_t)t * 9], sizeof(lbest_model));
+							lbest_inliers.swap(tmp);
+						}
+					}
+				}
+				if (!updated)
+					break;
+			}
+			if (best_score.value < max_score.value) // :900
+			{
+				best_score = max_score;
+				memcpy(best_model, lbest_model, sizeof(lbest_model));
+				best_inliers_out.lazy = false;
+				best_inliers_out.idx.swap(lbest_inliers);
+			}
+			return true;
+		}
+
+		// ---- iteratedLeastSquaresFitting (GCRANSAC.h:630-758), single-model estimators ----
+		bool iterated_least_squares(std::vector<uint32_t> &inliers, double *model, bool &success)
+		{
+			success = false;
+			if (inliers.size() <= (size_t)m)
+				return true;
+			size_t iterations = 0;
+			std::vector<double> weights(n, 0.0), r2, models;
+			std::vector<uint8_t> ok;
+			std::vector<uint32_t> tmp;
+			while (++iterations < S.max_least_squares_iterations)
+			{
+				Score s;
+				if (!exact(model, s, nullptr, &r2))
+					return false;
+				for (uint32_t idx : inliers) // Tukey bisquare weights, written by POINT index (:657-668)
+				{
+					const double w = std::max(0.0, 1.0 - r2[idx] / T);
+					weights[idx] = w * w;
+				}
+				// ... and read by POSITION by the H / 8-point solvers: reproduced literally
+				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
+				if (!refit(inliers.data(), offsets, sizes, weights.data(), GCR_WEIGHT_POSITIONAL, models, ok))
+					return false;
+				for (uint32_t idx : inliers)
+					weights[idx] = 0;
+				if (!ok[0])
+					break;
+				if (!exact(models.data(), s, &tmp))
+					return false;
+				if (tmp.size() < (size_t)m)
+					break;
+				if (s.inliers <= inliers.size())
+					break;
+				memcpy(model, models.data(), 9 * sizeof(double));
+				inliers.swap(tmp);
+			}
+			success = iterations > 1;
+			return true;
+		}
+
+		bool build_grid()
+		{
+			have_grid = false;
+			if (!(S.spatial_coherence_weight > 0.0) || !S.do_local_optimization)
+				return true;
+			DeviceBuffer dk, ds, dof;
+			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
+				return fail("gcr_malloc");
+			uint32_t n_cells = 0;
+			uint64_t neighbor_number = 0;
+			if (gcr_grid_build(ctx, 0, S.cell_sizes, S.cells_per_axis, dk.as<uint64_t>(), ds.as<uint32_t>(), dof.as<uint32_t>(),
+			                   &n_cells, &neighbor_number) != GCR_OK)
+				return fail("gcr_grid_build");
+			sorted_idx.resize(n);
+			cell_offsets.resize((size_t)n_cells + 1);
+			if (gcr_memcpy_d2h(ctx, sorted_idx.data(), ds.p, (size_t)n * 4) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, cell_offsets.data(), dof.p, ((size_t)n_cells + 1) * 4) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			cell_of_point.resize(n);
+			for (uint32_t c = 0; c < n_cells; ++c)
+				for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
+					cell_of_point[sorted_idx[q]] = c;
+			have_grid = true;
+			return true;
+		}
+
+		// ---- GCRANSAC::run ----
+		int run(double *model_out, uint8_t *inlier_mask)
+		{
+			memset(&st, 0, sizeof(st));
+			m = gcr_sample_size(problem);
+			mm = gcr_max_models(problem);
+			B = S.batch > 0 ? S.batch : 1024;
+			truncated_threshold = 3.0 / 2.0 * S.threshold;
+			T = truncated_threshold * truncated_threshold;
+			if (gcr_points_upload(ctx, pts, n, 4, 1) != GCR_OK)
+			{
+				fail("gcr_points_upload");
+				return -1;
+			}
+			if (!build_grid())
+				return -1;
+			const double log_probability = std::log(1.0 - S.confidence);
+			uint64_t max_iteration = iteration_number(1, n, m, log_probability);
+			uint64_t &it = st.iteration_number;
+			uint64_t cursor = 0; // next sample of the main stream
+			Score best;
+			double best_model[9] = {0};
+			InlierBuffer buf[2];
+			int offset = 0;
+			batch_count = 0;
+
+			while (S.min_iteration_number > it || it < std::min<uint64_t>(max_iteration, S.max_iteration_number))
+			{
+				bool do_lo = false;
+				++it;
+				uint64_t unsuccessful = 0;
+				long long success_at = -1;
+				while (unsuccessful < S.max_unsuccessful_model_generations)
+				{
+					const uint64_t g = cursor++;
+					if (batch_count == 0 || g < batch_first || g >= batch_first + (uint64_t)batch_count)
+						if (!run_batch(g))
+							return -1;
+					const size_t j = (size_t)(g - batch_first);
+					bool any = false;
+					for (int q = 0; q < mm; ++q)
+						any |= h_valid[j * mm + q] != 0;
+					if (any) { success_at = (long long)j; break; }
+					++unsuccessful;
+				}
+				st.main_samples = cursor;
+				it += unsuccessful;
+				if (success_at >= 0)
+				{
+					for (int q = 0; q < mm; ++q)
+					{
+						const size_t slot = (size_t)success_at * mm + q;
+						if (!h_valid[slot])
+							continue;
+						++st.models_scored;
+						const double *model = &h_models[slot * 9];
+						// the reference's getScore writes this model's inliers into the current container
+						InlierBuffer &cur = buf[offset];
+						cur.lazy = true;
+						memcpy(cur.model, model, sizeof(cur.model));
+						cur.lazy_count = h_counts[slot];
+						cur.idx.clear();
+						if (!((double)h_scores[slot] > best.value * (1.0 - 2e-4)))
+							continue; // FP32 ranking: cannot beat the best so far (:440)
+						Score s;
+						if (!exact(model, s, &cur.idx))
+							return -1;
+						cur.lazy = false;
+						if (best.value < s.value && is_valid_model(model, cur.idx)) // :440-446
+						{
+							offset = (offset + 1) % 2;
+							memcpy(best_model, model, sizeof(best_model));
+							best = s;
+							do_lo = it > S.min_iteration_number_before_lo && best.inliers > (uint64_t)m; // :463-464
+							max_iteration = iteration_number(best.inliers, n, m, log_probability);
+						}
+					}
+				}
+				if (S.do_local_optimization && do_lo)
+				{
+					++st.local_optimization_number; // :485 (and once more inside, :805 -- the reference counts twice)
+					if (!local_optimization(buf[offset], best_model, best))
+						return -1;
+					max_iteration = iteration_number(best.inliers, n, m, log_probability);
+				}
+			}
+
+			for (int i = 0; i < n; ++i)
+				inlier_mask[i] = 0;
+			if (best.inliers <= (uint64_t)m) // :521-527
+				return 0;
+			if (S.do_local_optimization && st.local_optimization_number == 0) // :530-543
+			{
+				++st.local_optimization_number;
+				if (!local_optimization(buf[offset], best_model, best))
+					return -1;
+			}
+			// :547-555 consistency of the stored inlier set (by SIZE, as the reference does)
+			if (buf[offset].size() != best.inliers)
+				offset = (offset + 1) % 2;
+			if (buf[offset].size() != best.inliers)
+			{
+				buf[offset].lazy = false;
+				if (!exact(best_model, best, &buf[offset].idx))
+					return -1;
+			}
+			if (!materialise(buf[offset]))
+				return -1;
+
+			bool iterative_refitting_applied = false;
+			if (S.do_final_iterated_least_squares) // :559-586
+			{
+				double model[9];
+				memcpy(model, best_model, sizeof(model));
+				bool success = false;
+				if (!iterated_least_squares(buf[offset].idx, model, success))
+					return -1;
+				if (success)
+				{
+					const int idx2 = (offset + 1) % 2;
+					Score cur;
+					buf[idx2].lazy = false;
+					if (!exact(model, cur, &buf[idx2].idx))
+						return -1;
+					if (best.value < cur.value)
+					{
+						iterative_refitting_applied = true;
+						memcpy(best_model, model, sizeof(model));
+						offset = idx2;
+					}
+				}
+			}
+			if (!iterative_refitting_applied) // :588-617: one least-squares fit on the first best.inliers entries
+			{
+				std::vector<double> models;
+				std::vector<uint8_t> ok;
+				const uint32_t cnt = (uint32_t)std::min<size_t>(best.inliers, buf[offset].idx.size());
+				std::vector<uint32_t> offsets(1, 0u), sizes(1, cnt);
+				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
+					return -1;
+				if (ok[0])
+				{
+					const int idx2 = (offset + 1) % 2;
+					Score cur;
+					buf[idx2].lazy = false;
+					if (!exact(models.data(), cur, &buf[idx2].idx))
+						return -1;
+					if (best.value < cur.value)
+					{
+						memcpy(best_model, models.data(), 9 * sizeof(double));
+						offset = idx2;
+					}
+				}
+			}
+			for (uint32_t i : buf[offset].idx)
+				inlier_mask[i] = 1;
+			memcpy(model_out, best_model, sizeof(best_model));
+			st.score = best.value;
+			return (int)buf[offset].idx.size();
+		}
+	};
+
+	thread_local std::string g_driver_error;
+}
+
+extern "C" void gcr_run_settings_default(gcr_run_settings *s)
+{
+	if (!s)
+		return;
+	memset(s, 0, sizeof(*s));
+	s->threshold = 2.0;              // settings.h:82
+	s->confidence = 0.95;            // :83
+	s->spatial_coherence_weight = 0.14;
+	s->max_iteration_number = std::numeric_limits<uint64_t>::max();
+	s->min_iteration_number = 20;
+	s->max_local_optimization_number = 10;
+	s->min_iteration_number_before_lo = 20;
+	s->max_graph_cut_number = 10;
+	s->max_least_squares_iterations = 10;
+	s->max_unsuccessful_model_generations = 100;
+	s->do_local_optimization = 1;
+	s->do_final_iterated_least_squares = 1;
+	s->cells_per_axis = 4;
+	s->seed = 1;
+	s->batch = 1024;
+}
+
+extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,
+                              double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats)
+{
+	if (!ctx || !h_points || !settings || !model_out || !inlier_mask || n <= 0)
+		return -2;
+	if (problem != GCR_H && problem != GCR_F)
+		return -3; // E / PnP refits are not linear: not wired into this driver yet
+	Driver d;
+	d.ctx = ctx;
+	d.problem = problem;
+	d.n = n;
+	d.pts = h_points;
+	d.S = *settings;
+	const int r = d.run(model_out, inlier_mask);
+	if (stats)
+		*stats = d.st;
+	if (r < 0)
+	{
+		g_driver_error = d.error;
+		fprintf(stderr, "gcr_find_model: %s\n", d.error.c_str());
+	}
+	return r;
+}

@@ -1,0 +1,72 @@
+// gcr_driver.h -- batched host driver: GCRANSAC<>::run (GCRANSAC.h:202-627) with the data-parallel parts on the B200.
+//
+// The reference's loop is sequential and adaptive (best-so-far, iteration bound, local optimisation all change as it
+// goes).  This driver returns what that loop returns from the same sample stream, but runs the loop body in batches
+// (SURVEY.md 7.3): B minimal samples are drawn, solved and scored on the GPU at once (gcr_sample / gcr_solve_minimal /
+// gcr_score); the host then replays the reference's sequential bookkeeping over the batch -- unsuccessful-sample
+// accounting (:297-339), strict '<' best-so-far with isValidModel (:437-471), LO trigger, getIterationNumber
+// (:158-172) and the loop condition (:282-283).  Candidates that may beat the best so far are confirmed in FP64
+// (gcr_score_exact: exact score, exact ascending inlier list), so every decision is taken on the reference's numbers.
+// Local optimisation (:780-910): residuals for the unary terms come from the GPU, the graph is built exactly as
+// GCRANSAC::labeling does (:913-1021) from the GPU-built grid cells (gcr_grid_build) and cut by the REFERENCE's own
+// BK max-flow (energy.h / graph.h, compiled from the reference tree -- the min-cut stays in the reference's host code);
+// the inner RANSAC (<= lo_number x {pool sample, non-minimal refit, full scoring}) is one GPU batch
+// (gcr_sample_from_pool / gcr_refit / gcr_score).  IRLS (:630-758) and the final fit use gcr_refit / gcr_score_exact.
+//
+// C ABI (libgcr_driver.so): see gcr_find_model below.  Python: graph-cut-ransac_b200/pygcransac/__init__.py.
+#ifndef GCR_DRIVER_H_INCLUDED
+#define GCR_DRIVER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gcr/gcr.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcr_run_settings
+{
+	/* utils::Settings (settings.h:43-86) as the drivers set it (py/gcransac_python.cpp:4498-4504) */
+	double threshold;
+	double confidence;
+	double spatial_coherence_weight;
+	uint64_t max_iteration_number;
+	uint64_t min_iteration_number;
+	uint64_t max_local_optimization_number; /* lo_number */
+	uint64_t min_iteration_number_before_lo; /* 20 */
+	uint64_t max_graph_cut_number;           /* 10 */
+	uint64_t max_least_squares_iterations;   /* 10 */
+	uint64_t max_unsuccessful_model_generations; /* 100 */
+	int do_local_optimization;
+	int do_final_iterated_least_squares;
+	/* grid neighbourhood (GridNeighborhoodGraph<4>) */
+	double cell_sizes[4];
+	uint64_t cells_per_axis;
+	/* driver */
+	uint64_t seed;  /* counter-based sample streams: main = stream 0, local optimisation = stream 1 */
+	int batch;      /* minimal samples per GPU batch (default 1024) */
+} gcr_run_settings;
+
+typedef struct gcr_run_stats
+{
+	uint64_t iteration_number, graph_cut_number, local_optimization_number, main_samples, lo_samples;
+	uint64_t gpu_batches, exact_rescores, models_scored;
+	double score;
+	double graph_cut_seconds; /* host min-cut, timed separately (north star) */
+} gcr_run_stats;
+
+/* defaults of utils::Settings + the Python drivers */
+void gcr_run_settings_default(gcr_run_settings *s);
+
+/* GCRANSAC<>::run for problem GCR_H or GCR_F on `n` correspondences (row-major FP64 n x 4, host memory).
+ * model_out: 9 doubles; inlier_mask: n bytes (1 = inlier).  Returns the inlier count (0 = no model), < 0 on error
+ * (gcr_last_error(ctx)). */
+int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,
+                   double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -45,19 +45,27 @@ def key_index(key_i64):
 
 
 def sharded_round(ctx, problem, scoring, sampler, first_index, total_samples, seed, thr, flags, keys, best, max_models,
-                  rank, world, group=None):
+                  rank, world, group=None, chunk_samples=65536):
     """One fixed-K pass with the K samples sharded over the ranks.  `keys` int64 [n_pairs] and `best` float64
     [n_pairs, model_len] are device tensors; on return every rank holds the global winner key and model.
-    Returns the model-slot x point evaluations THIS rank enqueued."""
+    A rank walks its share in chunks of `chunk_samples` (bounds the per-call workspace and the FP64 re-check list:
+    N = 2^20 points x 65536 samples is ~2e10 evaluations, ~1e6 of them inside the threshold band) and keeps the running
+    maximum of the chunk keys on the device.  Returns the model-slot x point evaluations THIS rank enqueued."""
     lo, hi = shard_range(total_samples, rank, world)
     evals = 0
-    if hi > lo:
-        evals = ctx.round_device(problem, scoring, sampler, first_index + lo, hi - lo, seed, thr, flags, lo * max_models,
-                                 keys.data_ptr(), best.data_ptr())
-    else:
-        keys.zero_()
+    run_keys = torch.full_like(keys, _FLIP)          # flipped domain: smallest possible key
+    run_best = torch.zeros_like(best)
+    for c0 in range(lo, hi, chunk_samples):
+        c1 = min(hi, c0 + chunk_samples)
+        evals += ctx.round_device(problem, scoring, sampler, first_index + c0, c1 - c0, seed, thr, flags, c0 * max_models,
+                                  keys.data_ptr(), best.data_ptr())
+        flipped = keys ^ _FLIP
+        better = flipped > run_keys                   # strictly: an equal key cannot occur (indices are unique)
+        run_keys = torch.where(better, flipped, run_keys)
+        run_best = torch.where(better[:, None], best, run_best)
+    keys.copy_(run_keys ^ _FLIP)
+    best.copy_(run_best)
     if world > 1:
-        torch.cuda.current_stream().synchronize() if keys.is_cuda and False else None  # same stream: ordered already
         reduce_keys(keys, group)
         # the winner's model lives on the rank that scored it
         for p in range(keys.numel()):
