@@ -1,0 +1,16 @@
+#!/bin/bash
+# graph-cut-ransac_b200/host/build_driver.sh -- builds the batched host driver (gcr_driver.cpp) into
+# host/_ref/libgcr_driver.so.  The driver's graph-cut step is the REFERENCE's own Boykov-Kolmogorov max-flow
+# (energy.h / graph.h / graph.cpp / maxflow.cpp), compiled from the reference tree where it lies: the min-cut stays
+# in the reference's host code (north star), nothing of it is copied into this repository.  Only runs where the
+# reference tree exists; the .so travels to the GPU box with the snapshot (host/_ref/ is git-ignored).
+set -e
+cd "$(dirname "$0")"
+REF=${GCR_REFERENCE_DIR:-/root/reference}/src/pygcransac/include
+if [ ! -f "$REF/energy.h" ]; then echo "reference tree not present; skipping host/_ref/libgcr_driver.so"; exit 0; fi
+if [ ! -f ../libgcr_b200.so ]; then echo "build libgcr_b200.so first (python graph-cut-ransac_b200/build.py)"; exit 1; fi
+mkdir -p _ref
+g++ -O2 -std=c++17 -w -fPIC -shared -ffp-contract=off -I"$REF" -I../../include -I. \
+    -o _ref/libgcr_driver.so gcr_driver.cpp \
+    -L.. -lgcr_b200 -Wl,-rpath,'$ORIGIN/../..'
+echo "built graph-cut-ransac_b200/host/_ref/libgcr_driver.so"

@@ -11,7 +11,11 @@
 #include <string>
 #include <vector>
 
-#include "energy.h" // reference: src/pygcransac/include/energy.h (Energy<> over Graph<>, BK max-flow)
+// The reference's own Boykov-Kolmogorov max-flow, included from the reference tree exactly as its GCoptimization.h:110-111
+// does (graph.cpp / maxflow.cpp hold the template definitions): the min-cut stays the reference's host code.
+#include "energy.h"
+#include "graph.cpp"
+#include "maxflow.cpp"
 
 namespace
 {

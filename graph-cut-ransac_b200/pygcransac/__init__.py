@@ -1,0 +1,141 @@
+"""pygcransac (B200) -- the reference's Python entry points on top of libgcr_b200.so.
+
+    findHomography / findFundamentalMatrix          same names, arguments, defaults and return values as
+                                                    danini/graph-cut-ransac's pybind11 module (py/bindings.cpp:1003-1178)
+
+The data-parallel loop body runs on the GPU through the batched host driver (graph-cut-ransac_b200/host/gcr_driver.cpp:
+GCRANSAC<>::run's sequential semantics replayed over GPU batches; the graph-cut min-cut is the reference's own BK
+max-flow on the host).  There is no CPU fallback: without a CUDA device / the built libraries these functions raise.
+
+Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
+tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
+so the flags are accepted and ignored.  `sampler` must be 0/1 (uniform; the counter-based stream) -- the stateful
+samplers (2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are host-side plug-ins of the reference's virtual Sampler interface and are
+not part of this path.  `neighborhood` must be 0 (grid) when `spatial_coherence_weight` > 0 (FLANN is out of scope).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _cabi
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_DRIVER_PATH = os.path.join(_PKG, "host", "_ref", "libgcr_driver.so")
+_driver = None
+_contexts = {}
+
+
+class RunSettings(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("confidence", C.c_double), ("spatial_coherence_weight", C.c_double),
+                ("max_iteration_number", C.c_uint64), ("min_iteration_number", C.c_uint64),
+                ("max_local_optimization_number", C.c_uint64), ("min_iteration_number_before_lo", C.c_uint64),
+                ("max_graph_cut_number", C.c_uint64), ("max_least_squares_iterations", C.c_uint64),
+                ("max_unsuccessful_model_generations", C.c_uint64), ("do_local_optimization", C.c_int),
+                ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
+                ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("iteration_number", C.c_uint64), ("graph_cut_number", C.c_uint64),
+                ("local_optimization_number", C.c_uint64), ("main_samples", C.c_uint64), ("lo_samples", C.c_uint64),
+                ("gpu_batches", C.c_uint64), ("exact_rescores", C.c_uint64), ("models_scored", C.c_uint64),
+                ("score", C.c_double), ("graph_cut_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+def _load_driver():
+    global _driver
+    if _driver is None:
+        _cabi.load_library()
+        if not os.path.exists(_DRIVER_PATH):
+            raise _cabi.GcrError("%s is missing: build it with graph-cut-ransac_b200/host/build_driver.sh (needs the "
+                                 "reference tree for its BK max-flow); there is no CPU fallback" % _DRIVER_PATH)
+        lib = C.CDLL(_DRIVER_PATH)
+        lib.gcr_run_settings_default.restype = None
+        lib.gcr_run_settings_default.argtypes = [C.POINTER(RunSettings)]
+        lib.gcr_find_model.restype = C.c_int
+        lib.gcr_find_model.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(RunSettings), C.c_void_p,
+                                       C.c_void_p, C.POINTER(RunStats)]
+        _driver = lib
+    return _driver
+
+
+def _context(device=0):
+    if device not in _contexts:
+        _contexts[device] = _cabi.Context(device)
+    return _contexts[device]
+
+
+last_statistics = None  # RunStats of the most recent call (the reference fills utils::RANSACStatistics; not returned by its API either)
+
+
+def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
+          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device):
+    global last_statistics
+    pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
+    if pts.ndim != 2 or pts.shape[1] != 4:
+        raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % (4 if problem == _cabi.H else 7))
+    min_n = 4 if problem == _cabi.H else 7
+    if pts.shape[0] < min_n:
+        raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
+    if sampler not in (0, 1):
+        raise NotImplementedError("sampler=%d: only the uniform sampler (0/1) runs on the counter-based GPU stream" % sampler)
+    if spatial_coherence_weight > np.finfo(np.float64).eps and neighborhood != 0:
+        raise NotImplementedError("neighborhood=%d: only the grid neighbourhood (0) is built on the GPU" % neighborhood)
+    lib = _load_driver()
+    ctx = _context(device)
+    s = RunSettings()
+    lib.gcr_run_settings_default(C.byref(s))
+    s.threshold, s.confidence, s.spatial_coherence_weight = threshold, conf, spatial_coherence_weight
+    s.max_iteration_number, s.min_iteration_number = max_iters, min_iters
+    s.max_local_optimization_number = lo_number
+    cells = int(neighborhood_size)                                          # static_cast<size_t>(neighborhood_size)
+    h1, w1, h2, w2 = sizes
+    eps = np.finfo(np.float64).eps if eps_in_cell_size else 0.0            # gcransac_python.cpp:4290-4297 vs :1672-1677
+    s.cells_per_axis = max(cells, 1)
+    for i, v in enumerate((w1, h1, w2, h2)):
+        s.cell_sizes[i] = (v + eps) / max(cells, 1)
+    s.seed = seed
+    model = np.zeros(9)
+    mask = np.zeros(len(pts), dtype=np.uint8)
+    stats = RunStats()
+    n_inl = lib.gcr_find_model(ctx.h, problem, pts.ctypes.data, len(pts), C.byref(s), model.ctypes.data, mask.ctypes.data,
+                               C.byref(stats))
+    if n_inl < 0:
+        raise _cabi.GcrError("gcr_find_model failed (%d): %s" % (n_inl, ctx.lib.gcr_last_error(ctx.h).decode()))
+    last_statistics = stats.as_dict()
+    if n_inl == 0:
+        return None, mask.astype(bool)                                      # bindings.cpp:973-975
+    return model.reshape(3, 3), mask.astype(bool)
+
+
+def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
+                   spatial_coherence_weight=0.975, max_iters=10000, min_iters=50, use_sprt=True,
+                   min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=0, neighborhood_size=4.0,
+                   use_space_partitioning=True, lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0):
+    """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
+    None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
+    return _find(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device)
+
+
+def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
+                          spatial_coherence_weight=0.0, max_iters=10000, min_iters=50, use_sprt=True,
+                          min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=1, neighborhood_size=20.0,
+                          lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0):
+    """py/bindings.cpp:279-400, 1003-1022 -> findFundamentalMatrix_ (py/gcransac_python.cpp:1600-1921), with the
+    linear 8-point non-minimal solver (the reference's default wraps it in an LM polish: SURVEY.md 8f N2, out of
+    scope) and without DEGENSAC."""
+    return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device)
+
+
+def findEssentialMatrix(*args, **kwargs):
+    """py/bindings.cpp:710-857.  The minimal 5-point solver, the Sampson / MAGSAC++ scoring and the K-normalisation
+    run on the GPU (gcr_solve_minimal(GCR_E), gcr_score), but the reference's non-minimal E refit (Stewenius action
+    matrix + EigenSolver) is not built yet, so the full driver is not wired for E."""
+    raise NotImplementedError("findEssentialMatrix: the non-minimal E refit is not built yet; use gcr_round(GCR_E) "
+                              "through pygcransac._cabi for the hypothesise-and-verify part")

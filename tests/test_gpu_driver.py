@@ -1,0 +1,85 @@
+"""The batched host driver (graph-cut-ransac_b200/host/gcr_driver.cpp) through pygcransac.findHomography /
+findFundamentalMatrix against the reference's GCRANSAC<>::run compiled verbatim (oracle/_ref) on the SAME counter-based
+sample streams: same iteration counts, same local optimisations, same inlier mask; models to 1e-5 (north star)."""
+import os
+
+import numpy as np
+import oracle as O
+import pytest
+from conftest import GOLDEN
+from pygcransac import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _up_to_scale(A, B):
+    A = A / np.linalg.norm(A)
+    B = B / np.linalg.norm(B)
+    if (A * B).sum() < 0:
+        B = -B
+    return np.abs(A - B).max() / np.abs(A).max()
+
+
+@pytest.fixture(scope="module")
+def pyg():
+    import pygcransac
+    try:
+        pygcransac._load_driver()
+    except Exception as e:  # built only where the reference tree (BK max-flow) exists
+        pytest.skip("host driver not available: %s" % e)
+    return pygcransac
+
+
+def test_findhomography_cfg1_matches_reference_run(pyg, ref):
+    g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
+    pts = g["pts"]                                   # float32 N x 4, like the reference's tests pass it
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    for seed in (1, 2, 3):
+        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, [], threshold=3.0, conf=0.99, spatial_coherence_weight=0.975,
+                                     max_iters=10000, min_iters=50, use_sprt=False, sampler=1, neighborhood=0,
+                                     neighborhood_size=4.0, use_space_partitioning=False, lo_number=50, seed=seed)
+        st = pyg.last_statistics
+        want = ref.run(O.H, pts.astype(np.float64), g["cell_sizes"], 4, 3.0, conf=0.99, spatial_weight=0.975, max_iters=10000,
+                       min_iters=50, lo_number=50, seed=seed)
+        assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
+        assert st["graph_cut_number"] == want["stats"]["graph_cuts"]
+        assert st["local_optimization_number"] == want["stats"]["local_optimizations"]
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert np.array_equal(mask, want["mask"]), (seed, int(mask.sum()), int(want["mask"].sum()))
+        assert _up_to_scale(want["model"], H) < 1e-5
+        assert abs(st["score"] - want["score"]) <= 1e-9 * want["score"]
+        assert np.array_equal(mask, g["mask_%d" % seed])      # and the committed fixture
+
+
+def test_findhomography_synthetic_and_errors(pyg, ref):
+    pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
+    H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)
+    cs = np.array([(1024 + np.finfo(np.float64).eps) / 4] * 4)
+    want = ref.run(O.H, pts, cs, 4, 2.0, conf=0.99, spatial_weight=0.975, max_iters=10000, min_iters=50, lo_number=50, seed=5)
+    assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5
+    assert (mask & inl).sum() > 0.97 * inl.sum()
+    with pytest.raises(ValueError):
+        pyg.findHomography(np.zeros((3, 4)), 10, 10, 10, 10, [])
+    with pytest.raises(ValueError):
+        pyg.findHomography(np.zeros((10, 3)), 10, 10, 10, 10, [])
+    with pytest.raises(NotImplementedError):
+        pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], sampler=4)
+    # no model: pure noise, tiny threshold -> (None, all-false mask) like bindings.cpp:973-975
+    rng = np.random.default_rng(0)
+    Hn, maskn = pyg.findHomography(rng.uniform(0, 1000, (50, 4)), 1000, 1000, 1000, 1000, [], threshold=1e-6, max_iters=200)
+    assert Hn is None and not maskn.any()
+
+
+def test_findfundamental_matches_reference_run(pyg, ref):
+    pts, Fm, Em, K, inl = synth.epipolar_pair(2000, 0.5, seed=34)
+    for seed, weight in ((7, 0.0), (8, 0.1)):
+        F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
+                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+        st = pyg.last_statistics
+        cs = np.array([1024 / 4.0] * 4)
+        want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50, seed=seed)
+        assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert np.array_equal(mask, want["mask"])
+        assert _up_to_scale(want["model"], F) < 1e-5
+        assert (mask & inl).sum() > 0.95 * inl.sum()
