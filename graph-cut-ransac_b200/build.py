@@ -20,15 +20,14 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(HERE, "host", "*.cpp")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))  # host/ (adapter header, batched driver) builds separately
 
 
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "gcr", "*.h")) \
-        + glob.glob(os.path.join(HERE, "host", "*.h"))
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "gcr", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
