@@ -18,6 +18,7 @@
 
 #include "solve_f7.cuh"
 #include "solve_e5.cuh"
+#include "solve_p3p.cuh"
 
 extern "C" int gcr_max_models(int problem)
 {
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts
 
 // ---------------------------------------------------------------------------------------------------- F7 ----
 #define F7_THREADS 64
-#define F7_SMEM (81 * F7_THREADS * sizeof(double))
+#define F7_SMEM (63 * F7_THREADS * sizeof(double))
 
 struct SamplePoints // sample point i, column c, straight from the (L2-resident) FP64 point array
 {
@@ -178,7 +179,7 @@ struct SamplePoints // sample point i, column c, straight from the (L2-resident)
 	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 4 + c]; }
 };
 
-__global__ void __launch_bounds__(F7_THREADS) k_solve_f7(const double *__restrict__ pts, int n,
+__global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__restrict__ pts, int n,
                                                          const uint32_t *__restrict__ samples, int count,
                                                          double *__restrict__ models, uint8_t *__restrict__ valid,
                                                          unsigned long long *__restrict__ counters)
@@ -279,6 +280,56 @@ __global__ void __launch_bounds__(64) k_solve_e5(const double *__restrict__ pts,
 		atomicAdd(&counters[0], (unsigned long long)cnt);
 }
 
+// --------------------------------------------------------------------------------------------------- P3P ----
+struct SamplePoints3
+{
+	const double *P; // rows of 5: u v X Y Z
+	const uint32_t *s;
+	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 5 + c]; }
+};
+
+__global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pts, int n,
+                                                   const uint32_t *__restrict__ samples, int count,
+                                                   double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                   unsigned long long *__restrict__ counters)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int pair = blockIdx.y;
+	uint32_t n_ok = 0;
+	if (i < count)
+	{
+		uint32_t sidx[3];
+		const uint32_t *s = samples + ((size_t)pair * count + i) * 3;
+		for (int j = 0; j < 3; ++j)
+			sidx[j] = s[j];
+		const SamplePoints3 pt{pts + (size_t)pair * n * 5, sidx};
+		double P[48];
+		const int nm = gcr_p3p::solve(pt, P);
+		double *out = models + ((size_t)pair * count + i) * 48;
+		uint8_t *v = valid + ((size_t)pair * count + i) * 4;
+		for (int mdl = 0; mdl < 4; ++mdl)
+		{
+			bool ok = mdl < nm;
+			if (ok)
+				for (int j = 0; j < 12; ++j)
+					if (!isfinite(P[12 * mdl + j])) ok = false; // PerspectiveNPointEstimator::estimateModel keeps what the solver returns
+			for (int j = 0; j < 12; ++j)
+				out[12 * mdl + j] = ok ? P[12 * mdl + j] : 0.0;
+			v[mdl] = ok ? 1 : 0;
+			n_ok += ok ? 1u : 0u;
+		}
+	}
+	__shared__ uint32_t cnt;
+	if (threadIdx.x == 0)
+		cnt = 0;
+	__syncthreads();
+	if (n_ok)
+		atomicAdd(&cnt, n_ok);
+	__syncthreads();
+	if (threadIdx.x == 0 && cnt)
+		atomicAdd(&counters[0], (unsigned long long)cnt);
+}
+
 extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
                                         double *d_models, uint8_t *d_valid)
 {
@@ -306,8 +357,11 @@ extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_
 		k_solve_e5<<<dim3((count + 63) / 64, ctx->n_pairs), 64, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count,
 		                                                                         d_models, d_valid, ctx->d_counters);
 		break;
+	case GCR_PNP:
+		k_solve_p3p<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		break;
 	default:
-		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: solver for problem %d is not built yet", problem);
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: unknown problem %d", problem);
 	}
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;

@@ -73,13 +73,13 @@ namespace gcr_f7
 	// The 7 x 9 epipolar matrix lives in SHARED memory, one column of doubles per thread (element e of thread t at
 	// base[e * stride + t]): the full-pivot LU indexes rows / columns by data-dependent pivots, which in registers
 	// would mean local memory (measured: 984 B stack per thread and 0.45 ms for 262144 samples; HBM/L2-bound spills).
-	// 81 doubles per thread: 63 for the matrix, 18 for the two null vectors.
+	// 63 doubles per thread; the two null vectors overlay rows 0..1 of the matrix once both back-substitutions are done.
 	struct SmemMat
 	{
 		double *base; // already offset by the thread index
 		int stride;   // threads per CTA
 		__device__ __forceinline__ double &operator()(int i, int j) const { return base[(i * 9 + j) * stride]; }
-		__device__ __forceinline__ double &f(int which, int j) const { return base[(63 + which * 9 + j) * stride]; }
+		__device__ __forceinline__ double &f(int which, int j) const { return base[(which * 9 + j) * stride]; }
 	};
 
 	// pt(i, c): sample point i, column c (x0 y0 x1 y1).  Returns the number of real roots (0..3, ascending) of
@@ -155,22 +155,27 @@ namespace gcr_f7
 			if (k < nonzero && fabs(A(k, k)) > premult) ++rank;
 		if (rank != 7)
 			return 0;
+		double x[2][7];
 #pragma unroll
 		for (int c = 0; c < 2; ++c)
 		{
-			double x[7];
 #pragma unroll
 			for (int i = 6; i >= 0; --i)
 			{
 				double s = -A(i, 7 + c);
 #pragma unroll
 				for (int j = i + 1; j < 7; ++j)
-					s -= A(i, j) * x[j];
-				x[i] = s / A(i, i);
+					s -= A(i, j) * x[c][j];
+				x[c][i] = s / A(i, i);
 			}
+		}
+		// the matrix is dead from here on: its first two rows become f1 / f2 (un-permuted)
+#pragma unroll
+		for (int c = 0; c < 2; ++c)
+		{
 #pragma unroll
 			for (int i = 0; i < 7; ++i)
-				A.f(c, (int)((colperm >> (4 * i)) & 15ull)) = x[i];
+				A.f(c, (int)((colperm >> (4 * i)) & 15ull)) = x[c][i];
 			A.f(c, (int)((colperm >> (4 * (7 + c))) & 15ull)) = 1.0;
 			A.f(c, (int)((colperm >> (4 * (7 + (1 - c)))) & 15ull)) = 0.0;
 		}

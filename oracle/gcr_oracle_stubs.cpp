@@ -2,5 +2,4 @@
 #include "gcr_oracle.h"
 extern "C" {
 int gcro_solve_e5_stewenius(const double *, const uint32_t *, int, const double *, double *) { return 0; }
-int gcro_solve_p3p(const double *, const uint32_t *, double *) { return 0; }
 }

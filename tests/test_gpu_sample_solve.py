@@ -122,6 +122,41 @@ def test_round_e_magsac_matches_cpu_round(gcr_ctx, oracle):
     assert gcr_ctx.counters()[1] == 0
 
 
+def test_p3p_models_match_oracle(gcr_ctx, oracle):
+    """K2 P3P (Lambda-Twist): same statements as the oracle; cbrt / acos / cos are the only libm calls."""
+    pts, Pm, _ = synth.pnp_scene(500, 0.4, seed=17)
+    gcr_ctx.points_upload(pts)
+    samples = oracle.sample_uniform(10, 0, 3000, 500, 3)
+    models, valid = gcr_ctx.solve_minimal(O.PNP, samples)
+    models, valid = models[0], valid[0]
+    n_models = 0
+    for s, mdl, v in zip(samples, models, valid):
+        want = oracle.solve_p3p(pts, s)
+        got = mdl[v.astype(bool)].reshape(-1, 3, 4)
+        assert len(got) == len(want), (s, len(got), len(want))
+        for g, w in zip(got, want):
+            assert np.abs(g - w).max() <= 1e-7 * max(1.0, np.abs(w).max()), (s, np.abs(g - w).max())
+        n_models += len(want)
+    assert 3000 < n_models < 12000
+
+
+def test_round_pnp_matches_cpu_round(gcr_ctx, oracle):
+    """P3P + reprojection-error MSAC (find6DPose's inner loop, py/gcransac_python.cpp:1026-1272)."""
+    pts, Pm, inl = synth.pnp_scene(900, 0.5, seed=18)
+    thr = 2.0 / synth.FOCAL
+    gcr_ctx.points_upload(pts)
+    keys, best, evals = gcr_ctx.round(O.PNP, _cabi.MSAC, _cabi.UNIFORM, 0, 2000, seed=13, thr=thr,
+                                      flags=_cabi.SCORE_EXACT_COUNTS)
+    score, idx = gcr_ctx.key_decode(keys[0])
+    want_score, want_idx, scored, want_model = oracle.round(O.PNP, O.MSAC, pts, 13, 0, 2000, thr)
+    assert idx // 4 == want_idx // 4
+    r64, rc = gcr_ctx.round_results()
+    assert abs(r64[0] - want_score) <= 1e-6 * want_score
+    assert np.abs(best[0].reshape(3, 4) - want_model.reshape(3, 4)).max() < 1e-7
+    assert np.abs(best[0].reshape(3, 4) - Pm).max() < 5e-3      # and it is the true pose
+    assert gcr_ctx.counters()[1] == 0
+
+
 def test_argmax_first_wins(gcr_ctx):
     pts = np.stack([synth.homography_pair(64, 0.3, seed=s)[0] for s in (1, 2)])
     gcr_ctx.points_upload(pts, n_pairs=2)

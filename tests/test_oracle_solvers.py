@@ -95,3 +95,24 @@ def test_f7_against_numpy_null_space(oracle):
             best = min(best, np.abs(Fq - Fn).max(), np.abs(Fq + Fn).max())
         hits += best < 1e-7
     assert hits >= 48
+
+
+def test_p3p_lambda_twist(oracle):
+    pts, P, inl = synth.pnp_scene(300, 0.0, seed=3, sigma=0.0)
+    rng = np.random.default_rng(0)
+    hit = total = 0
+    for t in range(200):
+        s = rng.choice(300, 3, replace=False).astype(np.uint32)
+        Ps = oracle.solve_p3p(pts, s)
+        assert 1 <= len(Ps) <= 4
+        best = 1.0
+        for Q in Ps:
+            total += 1
+            R = Q[:, :3]
+            assert np.abs(R @ R.T - np.eye(3)).max() < 1e-8 and np.linalg.det(R) > 0.99
+            pc = pts[s, 2:] @ R.T + Q[:, 3]
+            assert np.abs(pc[:, :2] / pc[:, 2:] - pts[s, :2]).max() < 1e-8      # the three sample points reproject exactly
+            assert (pc[:, 2] > 0).all()                                         # lambda_i > 0: in front of the camera
+            best = min(best, np.abs(Q - P).max())
+        hit += best < 1e-7
+    assert hit == 200 and total > 300
