@@ -204,7 +204,10 @@ def main():
     ap.add_argument("--workload", default="f4k", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="minimal samples per step per pair (default: workload's)")
     ap.add_argument("--variant", type=int, default=-1, help="force a K3 kernel variant (see gcr_set_score_variant)")
-    ap.add_argument("--no-exact", action="store_true", help="skip the FP64 threshold-band re-check in K3")
+    ap.add_argument("--exact-counts", action="store_true",
+                    help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
+                         "round -- the winner's FP64 score / exact count come from K4 either way")
+    ap.add_argument("--no-exact", action="store_true", help=argparse.SUPPRESS)  # old spelling of the default
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -229,7 +232,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     prob = _cabi.F if wl["problem"] == "f" else _cabi.H
-    flags = 0 if args.no_exact else _cabi.SCORE_EXACT_COUNTS
+    flags = _cabi.SCORE_EXACT_COUNTS if args.exact_counts else 0
     ctx = _cabi.Context(local_rank)
     # a real (non-default) stream: handle 0 would mean "restore the context's own stream" to gcr_ctx_set_stream, and
     # the CUDA events below must sit on the stream the kernels are launched on
@@ -351,7 +354,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
                        "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
-                       "exact_counts": not args.no_exact, "k3_variant": args.variant,
+                       "k3_exact_counts": bool(args.exact_counts), "winner": "FP64 re-score of the near-best candidates (K4)", "k3_variant": args.variant,
                        "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs)",
                        "best_score_rank0": best_key_score},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

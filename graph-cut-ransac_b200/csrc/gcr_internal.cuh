@@ -108,6 +108,14 @@ gcr_status gcr_profile_begin(gcr_ctx *ctx);
 gcr_status gcr_profile_end(gcr_ctx *ctx, uint64_t evals);
 gcr_status gcr_ensure_prosac_growth(gcr_ctx *ctx, int m);
 gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx);
+#define GCR_SEL_BUCKETS 64 /* index classes of K4's first stage */
+// gcr_score with K4's first stage fused into the finalize kernel (d_buckets may be null)
+gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid, int k,
+                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_buckets,
+                           uint32_t index_base);
+// K2 with the sample drawn inside the solver kernel (gcr_round's fused K1 + K2)
+gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, uint64_t first_index, int count, uint64_t seed,
+                                       double *d_models, uint8_t *d_valid);
 
 static inline int gcr_cols_of(int problem) { return problem == GCR_PNP ? 5 : 4; }
 
@@ -193,6 +201,85 @@ struct GcrDrawStream
 		}
 	}
 };
+
+
+// ---- minimal-sample generation (shared by K1's kernels and by K2's fused "generate in registers" path) --------
+#define GCR_PAIR_SEED_STRIDE 0x9E3779B97F4A7C15ull
+
+// where a solver kernel takes its sample from: an explicit index array, or the counter-based stream itself
+struct GcrSampleSource
+{
+	const uint32_t *samples;            // [n_pairs][count][m], or nullptr = generate
+	unsigned long long seed, first_index;
+	int sampler;                        // GCR_UNIFORM / GCR_PROSAC
+	const unsigned long long *growth;   // PROSAC growth function
+	uint32_t n;                         // pool size = number of points
+};
+
+// closed form of the subset-size recurrence of prosac_sampler.h:65-88 (see oracle gcro_prosac_subset_size)
+__device__ __forceinline__ uint32_t gcr_prosac_subset_size(const unsigned long long *__restrict__ growth, uint32_t n, int m,
+                                                           unsigned long long k)
+{
+	uint32_t lo = (uint32_t)m, hi = n;
+	if (lo >= hi)
+		return n < (uint32_t)m ? (uint32_t)m : hi;
+	while (lo < hi)
+	{
+		const uint32_t mid = lo + (hi - lo) / 2;
+		if (growth[mid - 1] >= k)
+			hi = mid;
+		else
+			lo = mid + 1;
+	}
+	return lo;
+}
+
+// sample `index` of pair `pair`: v[0..m) (m <= 8)
+__device__ __forceinline__ void gcr_gen_uniform(unsigned long long seed, int pair, unsigned long long index, int m, uint32_t n,
+                                                uint32_t *v)
+{
+	GcrDrawStream s(seed + (unsigned long long)pair * GCR_PAIR_SEED_STRIDE, index, 0u);
+	s.unique_set<8>(v, m, n);
+}
+__device__ __forceinline__ void gcr_gen_prosac(unsigned long long seed, int pair, unsigned long long k, int m, uint32_t n,
+                                               const unsigned long long *__restrict__ growth, unsigned long long convergence,
+                                               uint32_t *v)
+{
+	GcrDrawStream s(seed + (unsigned long long)pair * GCR_PAIR_SEED_STRIDE, k, 1u);
+	if (k > convergence)
+		s.unique_set<8>(v, m, n);
+	else
+	{
+		const uint32_t subset = gcr_prosac_subset_size(growth, n, m, k);
+		const uint32_t range = (k == 1) ? (uint32_t)m : subset - 1; // first-draw quirk, prosac_sampler.h:171-172
+		s.unique_set<8>(v, m - 1, range);
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (j == m - 1)
+				v[j] = subset - 1;
+	}
+}
+// the M indices of sample i of pair `pair` for a solver kernel
+template <int M>
+__device__ __forceinline__ void gcr_load_sample(const GcrSampleSource &src, int pair, int count, int i, uint32_t *sidx)
+{
+	if (src.samples)
+	{
+		const uint32_t *s = src.samples + ((size_t)pair * count + i) * M;
+#pragma unroll
+		for (int j = 0; j < M; ++j)
+			sidx[j] = s[j];
+		return;
+	}
+	uint32_t v[8];
+	if (src.sampler == GCR_PROSAC)
+		gcr_gen_prosac(src.seed, pair, src.first_index + (unsigned long long)i, M, src.n, src.growth, 100000ull, v);
+	else
+		gcr_gen_uniform(src.seed, pair, src.first_index + (unsigned long long)i, M, src.n, v);
+#pragma unroll
+	for (int j = 0; j < M; ++j)
+		sidx[j] = v[j];
+}
 
 __device__ __forceinline__ unsigned long long gcr_ordered_u64(double x)
 {

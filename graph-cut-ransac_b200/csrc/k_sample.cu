@@ -12,7 +12,6 @@
 #include <math.h>
 #include <vector>
 
-#define GCR_PAIR_SEED_STRIDE 0x9E3779B97F4A7C15ull
 
 __global__ void __launch_bounds__(256) k_sample_uniform(uint32_t *__restrict__ out, int count, int m, uint32_t n,
                                                          uint64_t first_index, uint64_t seed)
@@ -21,32 +20,13 @@ __global__ void __launch_bounds__(256) k_sample_uniform(uint32_t *__restrict__ o
 	if (i >= count)
 		return;
 	const int pair = blockIdx.y;
-	GcrDrawStream s(seed + (uint64_t)pair * GCR_PAIR_SEED_STRIDE, first_index + (uint64_t)i, 0u);
 	uint32_t v[8];
-	s.unique_set<8>(v, m, n);
+	gcr_gen_uniform(seed, pair, first_index + (uint64_t)i, m, n, v);
 	uint32_t *o = out + ((size_t)pair * count + i) * m;
 #pragma unroll
 	for (int j = 0; j < 8; ++j)
 		if (j < m)
 			o[j] = v[j];
-}
-
-// closed form of the subset-size recurrence of prosac_sampler.h:65-88 (see oracle gcro_prosac_subset_size)
-__device__ __forceinline__ uint32_t prosac_subset_size(const unsigned long long *__restrict__ growth, uint32_t n, int m,
-                                                       unsigned long long k)
-{
-	uint32_t lo = (uint32_t)m, hi = n;
-	if (lo >= hi)
-		return n < (uint32_t)m ? (uint32_t)m : hi;
-	while (lo < hi)
-	{
-		const uint32_t mid = lo + (hi - lo) / 2;
-		if (growth[mid - 1] >= k)
-			hi = mid;
-		else
-			lo = mid + 1;
-	}
-	return lo;
 }
 
 __global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ out, int count, int m, uint32_t n,
@@ -59,20 +39,8 @@ __global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ ou
 		return;
 	const int pair = blockIdx.y;
 	const unsigned long long k = first_k + (unsigned long long)i;
-	GcrDrawStream s(seed + (uint64_t)pair * GCR_PAIR_SEED_STRIDE, k, 1u);
 	uint32_t v[8];
-	if (k > convergence)
-		s.unique_set<8>(v, m, n);
-	else
-	{
-		const uint32_t subset = prosac_subset_size(growth, n, m, k);
-		const uint32_t range = (k == 1) ? (uint32_t)m : subset - 1; // first-draw quirk, prosac_sampler.h:171-172
-		s.unique_set<8>(v, m - 1, range);
-#pragma unroll
-		for (int j = 0; j < 8; ++j)
-			if (j == m - 1)
-				v[j] = subset - 1;
-	}
+	gcr_gen_prosac(seed, pair, k, m, n, growth, convergence, v);
 	uint32_t *o = out + ((size_t)pair * count + i) * m;
 #pragma unroll
 	for (int j = 0; j < 8; ++j)

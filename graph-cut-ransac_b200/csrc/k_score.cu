@@ -8,7 +8,7 @@
 //                     list (warp-aggregated atomics) and map their FP64 model into the centred / scaled FP32 frame of
 //                     the point copy.  Invalid slots (failed solver, oriented-constraint reject: ~90 % of 7-point
 //                     slots) never reach the scoring kernel.
-//   k_score_plan      one CTA: per-pair prefix of hypothesis tiles.
+//                     The last CTA to finish also builds the per-pair prefix of hypothesis tiles.
 //   k_score_main      the hot kernel.  One persistent CTA (128 threads) per SM slot; the work space (hypothesis tiles x
 //                     point granules) is cut into equal contiguous slices, one per CTA ("stream-K"), so there is no
 //                     tail wave whatever K, N and the pair count are.  lane = hypothesis: each thread keeps R
@@ -26,7 +26,8 @@
 //   k_score_fixup     GCR_SCORE_EXACT_COUNTS: evaluations whose |r^2 - t^2| fell inside the FP32 error band were left
 //                     out by the hot kernel and appended to a work list; they are evaluated here in FP64 in the
 //                     reference's operation order, so inlier counts equal the FP64 reference's.
-//   k_score_finalize  accumulators -> float score / uint32 inliers per slot (-1 / 0 for invalid slots).
+//   k_score_finalize  accumulators -> float score / uint32 inliers per slot (-1 / 0 for invalid slots); inside gcr_round
+//                     it also keeps the best key per index class (K4's first stage, see k_select.cu).
 //
 // Arithmetic is FP32 FMA + one MUFU.RCP per evaluation (projective divide / Sampson denominator): FP32-pipe bound,
 // not a tensor-core contraction.
@@ -183,7 +184,8 @@ struct ScorePlan
 {
 	uint32_t amb_count;   // entries appended to the FP64 work list
 	uint32_t amb_dropped; // entries that did not fit (reported through gcr_counters_read)
-	uint32_t pad[2];
+	uint32_t blocks_done; // k_score_prepare: the last CTA to finish builds the hypothesis-tile prefix
+	uint32_t pad;
 };
 
 struct ScoreArgs
@@ -209,6 +211,8 @@ struct ScoreArgs
 	// outputs
 	float *scores;
 	uint32_t *inliers;
+	unsigned long long *buckets; // optional [n_pairs][GCR_SEL_BUCKETS]: finalize also keeps the best key per index class
+	uint32_t index_base;
 	int n, n_pad, k, n_pairs;
 	int hyps_per_item, grid;
 	double thr;
@@ -216,54 +220,19 @@ struct ScoreArgs
 };
 
 // ------------------------------------------------------------------------------------------------- prepare ----
-template <int PROBLEM>
-__global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
+// exclusive prefix of hypothesis tiles over the pairs (prefix[n_pairs] = total), by one CTA of 256 threads
+__device__ void plan_prefix(const ScoreArgs &a)
 {
-	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
-	const int pair = blockIdx.y;
-	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const size_t g = (size_t)pair * a.k + slot;
-	const bool in_range = slot < a.k;
-	const bool ok = in_range && (a.valid == nullptr || a.valid[g] != 0);
-	if (in_range)
-	{
-		a.accS[g] = 0ull;
-		a.accC[g] = 0u;
-	}
-	const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
-	if (ballot == 0u)
-		return;
-	const int lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == __ffs(ballot) - 1)
-		base = atomicAdd(&a.counts[pair], (uint32_t)__popc(ballot));
-	base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-	if (!ok)
-		return;
-	const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-	a.slots[(size_t)pair * a.k + pos] = (uint32_t)slot;
-	float m[ML];
-	normalise_model<PROBLEM>(a.models + g * ML, a.norm + (size_t)pair * 8, m);
-	float *o = a.m32 + ((size_t)pair * a.k + pos) * ML;
-#pragma unroll
-	for (int j = 0; j < ML; ++j)
-		o[j] = m[j];
-}
-
-// ---------------------------------------------------------------------------------------------------- plan ----
-// one CTA: exclusive prefix of hypothesis tiles over the pairs (prefix[n_pairs] = total)
-__global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
-{
-	__shared__ uint32_t warp_tot[32];
+	__shared__ uint32_t warp_tot[8];
 	__shared__ uint32_t carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0)
 		carry = 0;
 	__syncthreads();
-	for (int base = 0; base < a.n_pairs; base += 1024)
+	for (int base = 0; base < a.n_pairs; base += 256)
 	{
 		const int p = base + tid;
-		const uint32_t tiles = p < a.n_pairs ? (a.counts[p] + a.hyps_per_item - 1) / a.hyps_per_item : 0u;
+		const uint32_t tiles = p < a.n_pairs ? (__ldcg(&a.counts[p]) + a.hyps_per_item - 1) / a.hyps_per_item : 0u;
 		uint32_t x = tiles;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -280,12 +249,57 @@ __global__ void __launch_bounds__(1024) k_score_plan(const ScoreArgs a)
 		if (p < a.n_pairs)
 			a.prefix[p] = before + x - tiles; // exclusive
 		__syncthreads();
-		if (tid == 1023)
+		if (tid == 255)
 			carry = before + x;
 		__syncthreads();
 	}
 	if (tid == 0)
 		a.prefix[a.n_pairs] = carry;
+}
+
+template <int PROBLEM>
+__global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
+{
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	__shared__ uint32_t s_last;
+	const int pair = blockIdx.y;
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t g = (size_t)pair * a.k + slot;
+	const bool in_range = slot < a.k;
+	const bool ok = in_range && (a.valid == nullptr || a.valid[g] != 0);
+	if (in_range)
+	{
+		a.accS[g] = 0ull;
+		a.accC[g] = 0u;
+	}
+	const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+	if (ballot != 0u)
+	{
+		const int lane = threadIdx.x & 31;
+		uint32_t base = 0;
+		if (lane == __ffs(ballot) - 1)
+			base = atomicAdd(&a.counts[pair], (uint32_t)__popc(ballot));
+		base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+		if (ok)
+		{
+			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+			a.slots[(size_t)pair * a.k + pos] = (uint32_t)slot;
+			float m[ML];
+			normalise_model<PROBLEM>(a.models + g * ML, a.norm + (size_t)pair * 8, m);
+			float *o = a.m32 + ((size_t)pair * a.k + pos) * ML;
+#pragma unroll
+			for (int j = 0; j < ML; ++j)
+				o[j] = m[j];
+		}
+	}
+	// the last CTA to get here sees every pair's final count and builds the hypothesis-tile prefix (saves a launch)
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		s_last = atomicAdd(&a.plan->blocks_done, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+	__syncthreads();
+	if (s_last)
+		plan_prefix(a);
 }
 
 // ----------------------------------------------------------------------------------- per-evaluation maths ----
@@ -734,28 +748,44 @@ __global__ void __launch_bounds__(256) k_score_fixup(const ScoreArgs a)
 template <int SCORING>
 __global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 {
+	__shared__ unsigned long long sb[GCR_SEL_BUCKETS];
 	const int pair = blockIdx.y;
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (a.buckets && threadIdx.x < GCR_SEL_BUCKETS)
+		sb[threadIdx.x] = 0ull;
+	if (a.buckets)
+		__syncthreads();
 	if (slot == 0 && pair == 0 && a.plan->amb_count)
 	{
 		atomicAdd(&a.counters[1], (unsigned long long)a.plan->amb_dropped);
 		atomicAdd(&a.counters[2], (unsigned long long)a.plan->amb_count);
 	}
-	if (slot >= a.k)
-		return;
-	const size_t g = (size_t)pair * a.k + slot;
-	const bool present = a.valid == nullptr || a.valid[g] != 0;
-	const uint32_t c = a.accC[g];
-	float score;
-	if (!present)
-		score = -1.f;
-	else if (SCORING == GCR_MSAC && c == 0)
-		score = 0.f; // scoring_function.h:221-222
-	else
-		score = (float)((double)(long long)a.accS[g] * (1.0 / FIX_ONE));
-	a.scores[g] = score;
-	if (a.inliers)
-		a.inliers[g] = present ? c : 0u;
+	if (slot < a.k)
+	{
+		const size_t g = (size_t)pair * a.k + slot;
+		const bool present = a.valid == nullptr || a.valid[g] != 0;
+		const uint32_t c = a.accC[g];
+		float score;
+		if (!present)
+			score = -1.f;
+		else if (SCORING == GCR_MSAC && c == 0)
+			score = 0.f; // scoring_function.h:221-222
+		else
+			score = (float)((double)(long long)a.accS[g] * (1.0 / FIX_ONE));
+		a.scores[g] = score;
+		if (a.inliers)
+			a.inliers[g] = present ? c : 0u;
+		if (a.buckets && score > 0.f) // K4's first stage, fused: best key per index class (see k_select.cu)
+			atomicMax(&sb[slot % GCR_SEL_BUCKETS],
+			          ((unsigned long long)gcr_ordered_u32(score) << 32) | (unsigned long long)(0xFFFFFFFFu - ((uint32_t)slot + a.index_base)));
+	}
+	if (a.buckets)
+	{
+		__syncthreads();
+		// most CTAs cannot raise the class maximum: look before the (contended) atomic
+		if (threadIdx.x < GCR_SEL_BUCKETS && sb[threadIdx.x] > __ldcg(&a.buckets[(size_t)pair * GCR_SEL_BUCKETS + threadIdx.x]))
+			atomicMax(&a.buckets[(size_t)pair * GCR_SEL_BUCKETS + threadIdx.x], sb[threadIdx.x]);
+	}
 }
 
 // ----------------------------------------------------------------------------------------------- dispatch ----
@@ -840,9 +870,7 @@ static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 	a.grid = per_sm * ctx->sm_count;
 
 	const dim3 gslots((a.k + 255) / 256, a.n_pairs);
-	k_score_prepare<PROBLEM><<<gslots, 256, 0, ctx->stream>>>(a);
-	GCR_LAUNCHED(ctx);
-	k_score_plan<<<1, 1024, 0, ctx->stream>>>(a);
+	k_score_prepare<PROBLEM><<<gslots, 256, 0, ctx->stream>>>(a); // + the hypothesis-tile prefix, by its last CTA
 	GCR_LAUNCHED(ctx);
 	st = gcr_profile_begin(ctx);
 	if (st)
@@ -885,6 +913,13 @@ static gcr_status launch_problem(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 extern "C" gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid,
                                 int k, double threshold, int flags, float *d_scores, uint32_t *d_inliers)
 {
+	return gcr_score_fused(ctx, problem, scoring, d_models, d_valid, k, threshold, flags, d_scores, d_inliers, nullptr, 0);
+}
+
+gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid, int k,
+                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_buckets,
+                           uint32_t index_base)
+{
 	if (!ctx)
 		return GCR_ERR_ARG;
 	if (!ctx->d_pts32 || ctx->n == 0)
@@ -918,6 +953,8 @@ extern "C" gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const do
 	a.counters = ctx->d_counters;
 	a.scores = d_scores;
 	a.inliers = d_inliers;
+	a.buckets = d_buckets;
+	a.index_base = index_base;
 	a.n = ctx->n;
 	a.n_pad = ctx->n_pad;
 	a.k = k;

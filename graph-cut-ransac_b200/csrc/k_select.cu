@@ -93,36 +93,12 @@ extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 // The FP32 scores of K3 rank the hypotheses, but FP32 cannot separate two models whose scores differ by less than its
 // own error (~2e-5 relative for Sampson: the model coefficients themselves are rounded to FP32).  gcr_round therefore
 // keeps, per pair, the best FP32 key of each of SEL_BUCKETS index classes (slot % SEL_BUCKETS; max is order-independent,
-// so this is deterministic), re-scores in FP64 -- reference operation order per point -- every bucket winner within
+// so this is deterministic; done inside K3's finalize kernel, k_score.cu), re-scores in FP64 -- reference operation order per point -- every bucket winner within
 // SEL_MARGIN of the best, and picks the winner by (FP64 score, lowest index): the strict '<' first-wins rule of
 // GCRANSAC.h:440 evaluated in the reference's precision.
-#define SEL_BUCKETS 64
+#define SEL_BUCKETS GCR_SEL_BUCKETS
 #define SEL_MARGIN 2e-4f
 #define SEL_THREADS 256
-
-__global__ void __launch_bounds__(256) k_bucket_argmax(const float *__restrict__ scores, int k, uint32_t index_base,
-                                                       unsigned long long *__restrict__ buckets)
-{
-	__shared__ unsigned long long sb[SEL_BUCKETS];
-	const int pair = blockIdx.y;
-	if (threadIdx.x < SEL_BUCKETS)
-		sb[threadIdx.x] = 0ull;
-	__syncthreads();
-	const float *s = scores + (size_t)pair * k;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
-	{
-		const float v = s[i];
-		if (v > 0.f)
-		{
-			const unsigned long long key = ((unsigned long long)gcr_ordered_u32(v) << 32) |
-			                               (unsigned long long)(0xFFFFFFFFu - ((uint32_t)i + index_base));
-			atomicMax(&sb[i % SEL_BUCKETS], key);
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x < SEL_BUCKETS && sb[threadIdx.x])
-		atomicMax(&buckets[(size_t)pair * SEL_BUCKETS + threadIdx.x], sb[threadIdx.x]);
-}
 
 struct SelectArgs
 {
@@ -313,22 +289,15 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	uint8_t *d_valid = (uint8_t *)(base + o_valid);
 	float *d_scores = (float *)(base + o_scores);
 
-	gcr_status st = gcr_sample(ctx, sampler, m, first_index, count, seed, d_samples);
+	(void)d_samples; // K1 is fused into K2: the solver kernel draws its sample in registers
+	gcr_status st = gcr_solve_minimal_generated(ctx, problem, sampler, first_index, count, seed, d_models, d_valid);
 	if (st) return st;
-	st = gcr_solve_minimal(ctx, problem, d_samples, count, d_models, d_valid);
-	if (st) return st;
-	st = gcr_score(ctx, problem, scoring, d_models, d_valid, (int)K, threshold, flags, d_scores, nullptr);
-	if (st) return st;
-	// K4: FP32 ranking -> bucket winners -> FP64 re-score of the near-best -> winner (see k_select_exact)
+	// K3 (+ K4's first stage inside its finalize kernel: best FP32 key per index class)
 	unsigned long long *d_buckets = (unsigned long long *)(base + o_buckets);
 	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_buckets, 0, P * SEL_BUCKETS * sizeof(unsigned long long), ctx->stream));
-	{
-		int gx = (int)((K + 255) / 256);
-		const int cap = ctx->n_pairs >= 2 * ctx->sm_count ? 1 : (4 * ctx->sm_count + ctx->n_pairs - 1) / ctx->n_pairs;
-		if (gx > cap) gx = cap;
-		k_bucket_argmax<<<dim3(gx, ctx->n_pairs), 256, 0, ctx->stream>>>(d_scores, (int)K, index_base, d_buckets);
-		GCR_LAUNCHED(ctx);
-	}
+	st = gcr_score_fused(ctx, problem, scoring, d_models, d_valid, (int)K, threshold, flags, d_scores, nullptr, d_buckets, index_base);
+	if (st) return st;
+	// K4: FP64 re-score of the near-best candidates -> winner (see k_select_exact)
 	if (scoring == GCR_MAGSAC)
 	{
 		st = gcr_ensure_magsac_lut64(ctx);

@@ -88,7 +88,7 @@ __device__ bool h_valid_sample(const double *a, const double *b, const double *c
 }
 
 __global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts, int n,
-                                                  const uint32_t *__restrict__ samples, int count,
+                                                  const GcrSampleSource src, int count,
                                                   double *__restrict__ models, uint8_t *__restrict__ valid,
                                                   unsigned long long *__restrict__ counters)
 {
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts
 		return;
 	const int pair = blockIdx.y;
 	const double *P = pts + (size_t)pair * n * 4;
-	const uint32_t *s = samples + ((size_t)pair * count + i) * 4;
+	uint32_t s[4];
+	gcr_load_sample<4>(src, pair, count, i, s);
 	double pt[4][4];
 #pragma unroll
 	for (int j = 0; j < 4; ++j)
@@ -180,7 +181,7 @@ struct SamplePoints // sample point i, column c, straight from the (L2-resident)
 };
 
 __global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__restrict__ pts, int n,
-                                                         const uint32_t *__restrict__ samples, int count,
+                                                         const GcrSampleSource src, int count,
                                                          double *__restrict__ models, uint8_t *__restrict__ valid,
                                                          unsigned long long *__restrict__ counters)
 {
@@ -191,10 +192,7 @@ __global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__rest
 	if (i < count)
 	{
 		uint32_t sidx[7];
-		const uint32_t *s = samples + ((size_t)pair * count + i) * 7;
-#pragma unroll
-		for (int j = 0; j < 7; ++j)
-			sidx[j] = s[j];
+		gcr_load_sample<7>(src, pair, count, i, sidx);
 		const SamplePoints pt{pts + (size_t)pair * n * 4, sidx};
 		const gcr_f7::SmemMat A{f7_smem + threadIdx.x, F7_THREADS};
 		double f1[9], f2[9], roots[3];
@@ -240,7 +238,7 @@ struct SamplePoints5
 };
 
 __global__ void __launch_bounds__(64) k_solve_e5(const double *__restrict__ pts, int n,
-                                                 const uint32_t *__restrict__ samples, int count,
+                                                 const GcrSampleSource src, int count,
                                                  double *__restrict__ models, uint8_t *__restrict__ valid,
                                                  unsigned long long *__restrict__ counters)
 {
@@ -250,9 +248,7 @@ __global__ void __launch_bounds__(64) k_solve_e5(const double *__restrict__ pts,
 	if (i < count)
 	{
 		uint32_t sidx[5];
-		const uint32_t *s = samples + ((size_t)pair * count + i) * 5;
-		for (int j = 0; j < 5; ++j)
-			sidx[j] = s[j];
+		gcr_load_sample<5>(src, pair, count, i, sidx);
 		const SamplePoints5 pt{pts + (size_t)pair * n * 4, sidx};
 		double *out = models + ((size_t)pair * count + i) * 90;
 		uint8_t *v = valid + ((size_t)pair * count + i) * 10;
@@ -289,7 +285,7 @@ struct SamplePoints3
 };
 
 __global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pts, int n,
-                                                   const uint32_t *__restrict__ samples, int count,
+                                                   const GcrSampleSource src, int count,
                                                    double *__restrict__ models, uint8_t *__restrict__ valid,
                                                    unsigned long long *__restrict__ counters)
 {
@@ -299,9 +295,7 @@ __global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pt
 	if (i < count)
 	{
 		uint32_t sidx[3];
-		const uint32_t *s = samples + ((size_t)pair * count + i) * 3;
-		for (int j = 0; j < 3; ++j)
-			sidx[j] = s[j];
+		gcr_load_sample<3>(src, pair, count, i, sidx);
 		const SamplePoints3 pt{pts + (size_t)pair * n * 5, sidx};
 		double P[48];
 		const int nm = gcr_p3p::solve(pt, P);
@@ -330,39 +324,84 @@ __global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pt
 		atomicAdd(&counters[0], (unsigned long long)cnt);
 }
 
-extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
-                                        double *d_models, uint8_t *d_valid)
+static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource &src, int count, double *d_models,
+                               uint8_t *d_valid)
 {
-	if (!ctx)
-		return GCR_ERR_ARG;
 	if (!ctx->d_pts64 || ctx->n == 0)
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_solve_minimal: no points uploaded");
 	if (problem < GCR_H || problem > GCR_PNP || gcr_cols_of(problem) != ctx->cols)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: problem does not match the uploaded points");
-	if (!d_samples || !d_models || !d_valid || count <= 0)
+	if (!d_models || !d_valid || count <= 0)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	const dim3 grid((count + 127) / 128, ctx->n_pairs);
 	switch (problem)
 	{
 	case GCR_H:
-		k_solve_h4<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		k_solve_h4<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_F:
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SMEM));
 		k_solve_f7<<<dim3((count + F7_THREADS - 1) / F7_THREADS, ctx->n_pairs), F7_THREADS, F7_SMEM, ctx->stream>>>(
-		    ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_E:
-		k_solve_e5<<<dim3((count + 63) / 64, ctx->n_pairs), 64, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count,
-		                                                                         d_models, d_valid, ctx->d_counters);
+		k_solve_e5<<<dim3((count + 63) / 64, ctx->n_pairs), 64, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models,
+		                                                                         d_valid, ctx->d_counters);
 		break;
 	case GCR_PNP:
-		k_solve_p3p<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, d_models, d_valid, ctx->d_counters);
+		k_solve_p3p<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	default:
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: unknown problem %d", problem);
 	}
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count,
+                                        double *d_models, uint8_t *d_valid)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_samples)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: bad arguments");
+	GcrSampleSource src;
+	src.samples = d_samples;
+	src.seed = src.first_index = 0;
+	src.sampler = GCR_UNIFORM;
+	src.growth = nullptr;
+	src.n = (uint32_t)ctx->n;
+	return solve_launch(ctx, problem, src, count, d_models, d_valid);
+}
+
+// gcr_round's K1 + K2 in one kernel: the sample is drawn from the counter-based stream inside the solver kernel
+// (bit-identical to gcr_sample's output for the same (seed, index, pair)) and never touches HBM.
+gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, uint64_t first_index, int count, uint64_t seed,
+                                       double *d_models, uint8_t *d_valid)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	const int m = gcr_sample_size(problem);
+	if (m == 0 || m > ctx->n)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: sample size %d exceeds the %d points (uniform_sampler.h:87-88)", m, ctx->n);
+	GcrSampleSource src;
+	src.samples = nullptr;
+	src.seed = seed;
+	src.first_index = first_index;
+	src.sampler = sampler;
+	src.growth = nullptr;
+	src.n = (uint32_t)ctx->n;
+	if (sampler == GCR_PROSAC)
+	{
+		if (first_index < 1)
+			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: PROSAC draws are numbered from k = 1");
+		gcr_status st = gcr_ensure_prosac_growth(ctx, m);
+		if (st)
+			return st;
+		src.growth = ctx->d_prosac_growth;
+	}
+	else if (sampler != GCR_UNIFORM)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: unknown sampler %d", sampler);
+	return solve_launch(ctx, problem, src, count, d_models, d_valid);
 }
