@@ -8,6 +8,10 @@
 //      normalizePoints (:637-734) and FundamentalMatrixEightPointSolver::estimateModel
 //      (estimators/solver_fundamental_matrix_eight_point.h:93-182).
 //
+//   E: EssentialMatrixEstimator::estimateModelNonminimal (estimators/essential_estimator.h:306-336) with
+//      EssentialMatrixFivePointSteweniusSolver::estimateModel
+//      (estimators/solver_essential_matrix_five_point_stewenius.h:114-231): up to 10 models per set.
+//
 // Mapping: one CTA per index set (the LO step hands over <= lo_number sets of <= 7 m indices; IRLS / final fit one set
 // of all inliers).  Threads stride over the set: Hartley normalisation (centroid, mean distance) and the normal
 // equations are three block reductions in FP64 with a fixed reduction tree (deterministic), then one thread solves.
@@ -18,9 +22,16 @@
 //      the same 45 accumulators, then the same full-pivot Householder QR in one thread (the result is NOT the
 //      smallest eigenvector when A^T A has full rank, so the decomposition itself is reproduced, not replaced).
 //      No rank-2 enforcement, as in the reference.
+//   E: weighted epipolar rows on the K-normalised points (no Hartley step), A^T A (45 accumulators), then in one
+//      thread the reference's ColPivHouseholderQR(A^T A).matrixQ().rightCols<4>() as the 4-D "null space" (the
+//      decomposition is reproduced: for noisy data that span is NOT the four smallest eigenvectors), the GrevLex
+//      trace / determinant constraints, the full-pivot 10 x 10 elimination, the action matrix and its real
+//      eigen-pairs (solve_e_stewenius.cuh; Hessenberg + Francis QR stands in for Eigen::EigenSolver).
+//      n == 5 takes the LU null space like the reference (:175-180).
 // Weight indexing: GCR_WEIGHT_POSITIONAL reads weights[i] with i the position inside the set, which is
 // what the reference's H / 8-point solvers do; GCR_WEIGHT_BY_POINT reads weights[index].
 #include "gcr_internal.cuh"
+#include "solve_e_stewenius.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -34,8 +45,8 @@ struct RefitArgs
 	const uint32_t *sets, *offsets, *sizes;
 	const double *weights;
 	int weight_mode;
-	double *models; // [count][9]
-	uint8_t *ok;    // [count]
+	double *models; // [count][R][9], R = gcr_max_refit_models(problem)
+	uint8_t *ok;    // [count][R]
 };
 
 // fixed-tree block sum of NV values per thread; result valid in out[] for every thread after the call
@@ -375,6 +386,201 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 	a.ok[set] = ok ? 1 : 0;
 }
 
+// Eigen ColPivHouseholderQR(M).matrixQ().rightCols<4>() of a 9 x 9 row-major M (destroyed): N[b][j] = Q(j, 5 + b).
+// Same pivoting rule as Eigen 3.4 computeInPlace (first column of largest down-dated norm, LAPACK-style down-dating,
+// recomputation below sqrt(eps)) and makeHouseholder's (beta, tau, essential) convention.
+__device__ void colpiv_householder_q_last4_9(double *M, double (&N)[4][9])
+{
+	const int n = 9;
+	double updated[9], direct[9], tau[9];
+	for (int j = 0; j < n; ++j)
+	{
+		double s = 0.0;
+		for (int i = 0; i < n; ++i) s += M[i * n + j] * M[i * n + j];
+		updated[j] = direct[j] = sqrt(s);
+	}
+	const double downdate_threshold = 1.4901161193847656e-08; // sqrt(eps)
+	for (int k = 0; k < n; ++k)
+	{
+		int big = k;
+		for (int j = k + 1; j < n; ++j)
+			if (updated[j] > updated[big]) big = j;
+		if (big != k)
+		{
+			for (int i = 0; i < n; ++i) { const double t = M[i * n + k]; M[i * n + k] = M[i * n + big]; M[i * n + big] = t; }
+			double t = updated[k]; updated[k] = updated[big]; updated[big] = t;
+			t = direct[k]; direct[k] = direct[big]; direct[big] = t;
+		}
+		double tail = 0.0;
+		for (int i = k + 1; i < n; ++i) tail += M[i * n + k] * M[i * n + k];
+		const double c0 = M[k * n + k];
+		double beta;
+		if (tail <= DBL_MIN)
+		{
+			tau[k] = 0.0;
+			beta = c0;
+			for (int i = k + 1; i < n; ++i) M[i * n + k] = 0.0;
+		}
+		else
+		{
+			beta = sqrt(c0 * c0 + tail);
+			if (c0 >= 0) beta = -beta;
+			for (int i = k + 1; i < n; ++i) M[i * n + k] /= (c0 - beta);
+			tau[k] = (beta - c0) / beta;
+		}
+		M[k * n + k] = beta;
+		for (int j = k + 1; j < n; ++j)
+		{
+			double dot = M[k * n + j];
+			for (int i = k + 1; i < n; ++i) dot += M[i * n + k] * M[i * n + j];
+			dot *= tau[k];
+			M[k * n + j] -= dot;
+			for (int i = k + 1; i < n; ++i) M[i * n + j] -= dot * M[i * n + k];
+		}
+		for (int j = k + 1; j < n; ++j)
+			if (updated[j] != 0.0)
+			{
+				double temp = fabs(M[k * n + j]) / updated[j];
+				temp = (1.0 + temp) * (1.0 - temp);
+				if (temp < 0) temp = 0;
+				const double r = updated[j] / direct[j];
+				const double temp2 = temp * r * r;
+				if (temp2 <= downdate_threshold)
+				{
+					double s = 0.0;
+					for (int i = k + 1; i < n; ++i) s += M[i * n + j] * M[i * n + j];
+					direct[j] = sqrt(s);
+					updated[j] = direct[j];
+				}
+				else
+					updated[j] *= sqrt(temp);
+			}
+	}
+	// columns 5..8 of Q = H_0 ... H_8 applied to the unit vectors e_5..e_8
+	for (int b = 0; b < 4; ++b)
+	{
+		double q[9];
+		for (int i = 0; i < n; ++i) q[i] = i == 5 + b ? 1.0 : 0.0;
+		for (int k = n - 1; k >= 0; --k)
+		{
+			double dot = q[k];
+			for (int i = k + 1; i < n; ++i) dot += M[i * n + k] * q[i];
+			dot *= tau[k];
+			q[k] -= dot;
+			for (int i = k + 1; i < n; ++i) q[i] -= dot * M[i * n + k];
+		}
+		for (int i = 0; i < n; ++i) N[b][i] = q[i];
+	}
+}
+
+#define RF_E_MODELS 10
+
+__global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a)
+{
+	__shared__ double red[RF_WARPS * 45];
+	__shared__ double tot[45];
+	const int set = blockIdx.x, tid = threadIdx.x;
+	const uint32_t *idx = a.sets + a.offsets[set];
+	const int n = (int)a.sizes[set];
+	double *models = a.models + (size_t)set * RF_E_MODELS * 9;
+	uint8_t *ok = a.ok + (size_t)set * RF_E_MODELS;
+	if (n < 5) // nonMinimalSampleSize() (essential_estimator.h:315-316)
+	{
+		for (int j = tid; j < RF_E_MODELS * 9; j += RF_THREADS) models[j] = 0.0;
+		if (tid < RF_E_MODELS) ok[tid] = 0;
+		return;
+	}
+	double N[4][9];
+	bool have_basis = true;
+	if (n == 5)
+	{
+		// stewenius.h:175-180: LU kernel of the (weighted) 5 x 9 matrix
+		if (tid == 0)
+		{
+			double lu[5][9];
+			for (int i = 0; i < 5; ++i)
+			{
+				const double *p = a.pts + (size_t)idx[i] * 4;
+				const double w = !a.weights ? 1.0 : a.weight_mode == GCR_WEIGHT_BY_POINT ? a.weights[idx[i]] : a.weights[i];
+				const double wx0 = w * p[0], wx1 = w * p[2], wy0 = w * p[1], wy1 = w * p[3];
+				lu[i][0] = wx0 * p[2]; lu[i][1] = wx0 * p[3]; lu[i][2] = wx0; lu[i][3] = wy0 * p[2]; lu[i][4] = wy0 * p[3];
+				lu[i][5] = wy0; lu[i][6] = wx1; lu[i][7] = wy1; lu[i][8] = w;
+			}
+			have_basis = gcr_e5::null_space_lu(lu, N);
+		}
+	}
+	else
+	{
+		double acc[45];
+#pragma unroll
+		for (int j = 0; j < 45; ++j) acc[j] = 0.0;
+		for (int i = tid; i < n; i += RF_THREADS)
+		{
+			const double *p = a.pts + (size_t)idx[i] * 4;
+			const double w = !a.weights ? 1.0 : a.weight_mode == GCR_WEIGHT_BY_POINT ? a.weights[idx[i]] : a.weights[i];
+			const double wx0 = w * p[0], wx1 = w * p[2], wy0 = w * p[1], wy1 = w * p[3];
+			const double r[9] = {wx0 * p[2], wx0 * p[3], wx0, wy0 * p[2], wy0 * p[3], wy0, wx1, wy1, w};
+			int q = 0;
+#pragma unroll
+			for (int i2 = 0; i2 < 9; ++i2)
+#pragma unroll
+				for (int c = i2; c < 9; ++c)
+					acc[q++] += r[i2] * r[c];
+		}
+		block_sum<45>(acc, red, tot);
+		if (tid == 0)
+		{
+			double AtA[81];
+			int q = 0;
+			for (int r = 0; r < 9; ++r)
+				for (int c = r; c < 9; ++c)
+				{
+					AtA[9 * r + c] = tot[q];
+					AtA[9 * c + r] = tot[q];
+					++q;
+				}
+			colpiv_householder_q_last4_9(AtA, N);
+		}
+	}
+	if (tid != 0)
+		return;
+	double E[RF_E_MODELS * 9];
+	int count = 0;
+	if (have_basis)
+	{
+		bool finite = true;
+		for (int b = 0; b < 4; ++b)
+			for (int j = 0; j < 9; ++j)
+				if (!isfinite(N[b][j])) finite = false;
+		if (finite)
+			count = gcr_e_nm::solve_from_basis(N, E);
+	}
+	// essential_estimator.h:327-333: Frobenius-normalise, sign so that E(2,2) >= 0
+	for (int m = 0; m < RF_E_MODELS; ++m)
+	{
+		bool good = m < count;
+		double out[9];
+		if (good)
+		{
+			double nrm = 0.0;
+			for (int i = 0; i < 9; ++i) nrm += E[9 * m + i] * E[9 * m + i];
+			nrm = sqrt(nrm);
+			for (int i = 0; i < 9; ++i) out[i] = E[9 * m + i] / nrm;
+			if (out[8] < 0)
+				for (int i = 0; i < 9; ++i) out[i] = -out[i];
+			for (int i = 0; i < 9; ++i)
+				if (isnan(out[i])) good = false;
+		}
+		for (int i = 0; i < 9; ++i) models[9 * m + i] = good ? out[i] : 0.0;
+		ok[m] = good ? 1 : 0;
+	}
+}
+
+extern "C" int gcr_max_refit_models(int problem)
+{
+	return problem == GCR_E ? RF_E_MODELS : (problem == GCR_H || problem == GCR_F) ? 1 : 0;
+}
+
 extern "C" gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets,
                                 const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count,
                                 const double *d_weights, int weight_mode, double *d_models, uint8_t *d_ok)
@@ -383,9 +589,8 @@ extern "C" gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint3
 		return GCR_ERR_ARG;
 	if (!ctx->d_pts64 || ctx->n == 0)
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_refit: no points uploaded");
-	if (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F))
-		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: linear refits exist for H and F (8-point) on 4-column points only; "
-		                           "E refits use the 5-point solver on the sample (gcr_solve_minimal)");
+	if (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F && problem != GCR_E))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: non-minimal refits exist for H, F (8-point) and E (Stewenius) on 4-column points");
 	if (pair < 0 || pair >= ctx->n_pairs || count <= 0 || !d_index_sets || !d_set_offsets || !d_set_sizes || !d_models || !d_ok)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: bad arguments");
 	if (d_weights && weight_mode != GCR_WEIGHT_POSITIONAL && weight_mode != GCR_WEIGHT_BY_POINT)
@@ -402,6 +607,8 @@ extern "C" gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint3
 	a.ok = d_ok;
 	if (problem == GCR_H)
 		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	else if (problem == GCR_E)
+		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else
 		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);

@@ -206,19 +206,11 @@ namespace gcr_e5
 		return n_roots;
 	}
 
-	// pt(i, c): sample point i (x0 y0 x1 y1, K-normalised); E: up to 10 x 9 row-major; returns the number of models
-	template <class PointFn>
-	__device__ inline int solve(const PointFn &pt, double *E_out)
+	// 4-D null space of the 5 x 9 epipolar matrix `lu` (destroyed) with Eigen FullPivLU::kernel() semantics; N[b][j] =
+	// coefficient j of basis vector b.  false if the rank is not 5 (dimensionOfKernel() != 4, :326-328).
+	__device__ inline bool null_space_lu(double (&lu)[5][9], double (&N)[4][9])
 	{
 		const double eps = 2.220446049250313e-16;
-		// ---- 5 x 9 epipolar rows and the complete-pivoting LU ----
-		double lu[5][9];
-		for (int i = 0; i < 5; ++i)
-		{
-			const double x0 = pt(i, 0), y0 = pt(i, 1), x1 = pt(i, 2), y1 = pt(i, 3);
-			lu[i][0] = x0 * x1; lu[i][1] = x0 * y1; lu[i][2] = x0; lu[i][3] = y0 * x1; lu[i][4] = y0 * y1; lu[i][5] = y0;
-			lu[i][6] = x1; lu[i][7] = y1; lu[i][8] = 1.0;
-		}
 		int colperm[9];
 		for (int j = 0; j < 9; ++j)
 			colperm[j] = j;
@@ -256,10 +248,9 @@ namespace gcr_e5
 		int rank = 0;
 		for (int k = 0; k < nonzero; ++k)
 			if (fabs(lu[k][k]) > premult) ++rank;
-		if (rank != 5) // dimensionOfKernel() != 4 (:326-328)
-			return 0;
+		if (rank != 5)
+			return false;
 		// kernel basis: N[b][j], b = 0..3
-		double N[4][9];
 		for (int c = 0; c < 4; ++c)
 		{
 			double x[5];
@@ -275,7 +266,13 @@ namespace gcr_e5
 			for (int q = 0; q < 4; ++q)
 				N[c][colperm[5 + q]] = q == c ? 1.0 : 0.0;
 		}
+		return true;
+	}
 
+	// Everything after the null space (:204-261, :350-612): E = x N0 + y N1 + z N2 + N3 -> up to 10 models (row-major).
+	// Also the back end of the non-minimal E refit (k_refit.cu), whose basis comes from a pivoted QR of A^T A.
+	__device__ inline int solve_from_basis(const double (&N)[4][9], double *E_out)
+	{
 		// ---- constraints ----
 		double C[10][20];
 		for (int i = 0; i < 10; ++i)
@@ -424,5 +421,22 @@ namespace gcr_e5
 			++n_models;
 		}
 		return n_models;
+	}
+	// pt(i, c): sample point i (x0 y0 x1 y1, K-normalised); E: up to 10 x 9 row-major; returns the number of models
+	template <class PointFn>
+	__device__ inline int solve(const PointFn &pt, double *E_out)
+	{
+		// ---- 5 x 9 epipolar rows and the complete-pivoting LU ----
+		double lu[5][9];
+		for (int i = 0; i < 5; ++i)
+		{
+			const double x0 = pt(i, 0), y0 = pt(i, 1), x1 = pt(i, 2), y1 = pt(i, 3);
+			lu[i][0] = x0 * x1; lu[i][1] = x0 * y1; lu[i][2] = x0; lu[i][3] = y0 * x1; lu[i][4] = y0 * y1; lu[i][5] = y0;
+			lu[i][6] = x1; lu[i][7] = y1; lu[i][8] = 1.0;
+		}
+		double N[4][9];
+		if (!null_space_lu(lu, N))
+			return 0;
+		return solve_from_basis(N, E_out);
 	}
 }

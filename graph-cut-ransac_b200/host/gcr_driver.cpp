@@ -88,8 +88,9 @@ namespace
 	{
 	public:
 		gcr_ctx *ctx;
-		int problem, n, m, mm;
+		int problem, n, m, mm, rm; // rm = models per non-minimal refit (1: H, F; up to 10: E)
 		const double *pts;
+		const double *grid_pts = nullptr; // points the neighbourhood grid is built on (E: pixel coordinates; else = pts)
 		gcr_run_settings S;
 		gcr_run_stats st;
 		double T; // squared truncated threshold (GCRANSAC.h:253-254)
@@ -182,9 +183,10 @@ namespace
 				                   H[2] * (H[3] * H[7] - H[4] * H[6]);
 				return !(std::fabs(det) < 1e-2);
 			}
-			// fundamental_estimator.h:287-318 (symmetric-epipolar ratio test; DEGENSAC stays with the host estimator)
-			const double a = (double)m, b = inliers.size() * 0.5;
-			const double minimum_inlier_number = a < b ? b : a;
+			// fundamental_estimator.h:287-318 (symmetric-epipolar ratio test; DEGENSAC stays with the host estimator),
+			// essential_estimator.h:279-305 (ratio 0.1).  `const size_t x = MAX(size_t, double)`: truncated.
+			const double a = (double)m, b = inliers.size() * (problem == GCR_E ? 0.1 : 0.5);
+			const size_t minimum_inlier_number = (size_t)(a > b ? a : b);
 			const double squared_threshold = truncated_threshold * truncated_threshold;
 			size_t inlier_number = 0;
 			for (uint32_t i : inliers)
@@ -292,7 +294,7 @@ namespace
 					return fail("gcr_memcpy_h2d");
 			}
 			if (!d_offsets.ensure(ctx, count * sizeof(uint32_t)) || !d_sizes.ensure(ctx, count * sizeof(uint32_t)) ||
-			    !d_lmodels.ensure(ctx, (size_t)count * 9 * sizeof(double)) || !d_lok.ensure(ctx, count))
+			    !d_lmodels.ensure(ctx, (size_t)count * rm * 9 * sizeof(double)) || !d_lok.ensure(ctx, (size_t)count * rm))
 				return fail("gcr_malloc");
 			if (gcr_memcpy_h2d(ctx, d_offsets.p, offsets.data(), count * sizeof(uint32_t)) != GCR_OK ||
 			    gcr_memcpy_h2d(ctx, d_sizes.p, sizes.data(), count * sizeof(uint32_t)) != GCR_OK)
@@ -309,10 +311,10 @@ namespace
 			if (gcr_refit(ctx, problem, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
 			              weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_refit");
-			models.resize((size_t)count * 9);
-			ok.resize(count);
-			if (gcr_memcpy_d2h(ctx, models.data(), d_lmodels.p, (size_t)count * 9 * sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, ok.data(), d_lok.p, count) != GCR_OK)
+			models.resize((size_t)count * rm * 9);
+			ok.resize((size_t)count * rm);
+			if (gcr_memcpy_d2h(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, ok.data(), d_lok.p, (size_t)count * rm) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			return true;
 		}
@@ -353,7 +355,7 @@ namespace
 					for (int t = 0; t < trials; ++t) offsets[t] = (uint32_t)(t * sample_size);
 					if (!refit(nullptr, offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, true))
 						return false;
-					n_models = trials;
+					n_models = trials * rm; // trial-major, the solver's model order inside a trial (:866)
 				}
 				else if ((size_t)m < inliers.size() && trials > 0)
 				{
@@ -361,7 +363,9 @@ namespace
 					std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
 					if (!refit(inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
 						return false;
-					n_models = ok[0] ? 1 : 0;
+					n_models = 0;
+					for (int q = 0; q < rm; ++q)
+						if (ok[q]) n_models = rm;
 				}
 				if (n_models > 0)
 				{
@@ -415,6 +419,7 @@ namespace
 			std::vector<double> weights(n, 0.0), r2, models;
 			std::vector<uint8_t> ok;
 			std::vector<uint32_t> tmp;
+			Score irls_best; // :648
 			while (++iterations < S.max_least_squares_iterations)
 			{
 				Score s;
@@ -425,22 +430,52 @@ namespace
 					const double w = std::max(0.0, 1.0 - r2[idx] / T);
 					weights[idx] = w * w;
 				}
-				// ... and read by POSITION by the H / 8-point solvers: reproduced literally
+				// ... and read by POSITION by the H / 8-point solvers, by POINT by the Stewenius solver
+				// (solver_essential_matrix_five_point_stewenius.h:143): reproduced literally
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
-				if (!refit(inliers.data(), offsets, sizes, weights.data(), GCR_WEIGHT_POSITIONAL, models, ok))
+				if (!refit(inliers.data(), offsets, sizes, weights.data(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
+				           models, ok))
 					return false;
 				for (uint32_t idx : inliers)
 					weights[idx] = 0;
-				if (!ok[0])
+				std::vector<const double *> found;
+				for (int q = 0; q < rm; ++q)
+					if (ok[q]) found.push_back(&models[(size_t)q * 9]);
+				if (found.empty()) // :690
 					break;
-				if (!exact(models.data(), s, &tmp))
-					return false;
-				if (tmp.size() < (size_t)m)
-					break;
-				if (s.inliers <= inliers.size())
-					break;
-				memcpy(model, models.data(), 9 * sizeof(double));
-				inliers.swap(tmp);
+				if (found.size() == 1) // :692-714
+				{
+					if (!exact(found[0], s, &tmp))
+						return false;
+					if (tmp.size() < (size_t)m)
+						break;
+					if (s.inliers <= inliers.size())
+						break;
+					memcpy(model, found[0], 9 * sizeof(double));
+					inliers.swap(tmp);
+				}
+				else // :715-748 several models: the best by inlier count, `best_score` lives across the rounds
+				{
+					bool updated = false;
+					for (const double *cand : found)
+					{
+						if (!exact(cand, s, &tmp))
+							return false;
+						if (tmp.size() < (size_t)m)
+							continue;
+						if (s.inliers <= inliers.size())
+							continue;
+						if (s.inliers >= irls_best.inliers)
+						{
+							updated = true;
+							irls_best = s;
+							memcpy(model, cand, 9 * sizeof(double));
+							inliers.swap(tmp);
+						}
+					}
+					if (!updated)
+						break;
+				}
 			}
 			success = iterations > 1;
 			return true;
@@ -481,12 +516,25 @@ namespace
 			B = S.batch > 0 ? S.batch : 1024;
 			truncated_threshold = 3.0 / 2.0 * S.threshold;
 			T = truncated_threshold * truncated_threshold;
+			rm = gcr_max_refit_models(problem);
+			if (grid_pts && grid_pts != pts)
+			{
+				// findEssentialMatrix_ builds the grid on the pixel coordinates and runs on the K-normalised ones
+				// (py/gcransac_python.cpp:2592-2600, 2641-2645)
+				if (gcr_points_upload(ctx, grid_pts, n, 4, 1) != GCR_OK)
+				{
+					fail("gcr_points_upload");
+					return -1;
+				}
+				if (!build_grid())
+					return -1;
+			}
 			if (gcr_points_upload(ctx, pts, n, 4, 1) != GCR_OK)
 			{
 				fail("gcr_points_upload");
 				return -1;
 			}
-			if (!build_grid())
+			if (!(grid_pts && grid_pts != pts) && !build_grid())
 				return -1;
 			const double log_probability = std::log(1.0 - S.confidence);
 			uint64_t max_iteration = iteration_number(1, n, m, log_probability);
@@ -612,16 +660,18 @@ namespace
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, cnt);
 				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
 					return -1;
-				if (ok[0])
+				for (int q = 0; q < rm; ++q) // :597-613 every returned model, in order; the best SCORE is not updated there
 				{
+					if (!ok[q])
+						continue;
 					const int idx2 = (offset + 1) % 2;
 					Score cur;
 					buf[idx2].lazy = false;
-					if (!exact(models.data(), cur, &buf[idx2].idx))
+					if (!exact(&models[(size_t)q * 9], cur, &buf[idx2].idx))
 						return -1;
 					if (best.value < cur.value)
 					{
-						memcpy(best_model, models.data(), 9 * sizeof(double));
+						memcpy(best_model, &models[(size_t)q * 9], 9 * sizeof(double));
 						offset = idx2;
 					}
 				}
@@ -664,8 +714,8 @@ extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points,
 {
 	if (!ctx || !h_points || !settings || !model_out || !inlier_mask || n <= 0)
 		return -2;
-	if (problem != GCR_H && problem != GCR_F)
-		return -3; // E / PnP refits are not linear: not wired into this driver yet
+	if (problem != GCR_H && problem != GCR_F && problem != GCR_E)
+		return -3; // PnP is not wired into this driver (find6DPose: SURVEY 8f N4)
 	Driver d;
 	d.ctx = ctx;
 	d.problem = problem;
@@ -679,6 +729,56 @@ extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points,
 	{
 		g_driver_error = d.error;
 		fprintf(stderr, "gcr_find_model: %s\n", d.error.c_str());
+	}
+	return r;
+}
+
+// findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855) up to, not including, its LM bundle-adjustment polish:
+// grid on the pixel coordinates, K^-1 normalisation (utils.h:65-110), threshold / mean focal length (:2624-2626, 2737).
+extern "C" int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, const double *K1, const double *K2,
+                                  const gcr_run_settings *settings, double *model_out, uint8_t *inlier_mask,
+                                  gcr_run_stats *stats)
+{
+	if (!ctx || !h_points || !K1 || !K2 || !settings || !model_out || !inlier_mask || n <= 0)
+		return -2;
+	auto inverse3 = [](const double *M, double *R) {
+		// Eigen's 3 x 3 inverse: cofactors / determinant
+		const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+		const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+		const double inv = 1.0 / det;
+		R[0] = c00 * inv; R[1] = (M[2] * M[7] - M[1] * M[8]) * inv; R[2] = (M[1] * M[5] - M[2] * M[4]) * inv;
+		R[3] = c01 * inv; R[4] = (M[0] * M[8] - M[2] * M[6]) * inv; R[5] = (M[2] * M[3] - M[0] * M[5]) * inv;
+		R[6] = c02 * inv; R[7] = (M[1] * M[6] - M[0] * M[7]) * inv; R[8] = (M[0] * M[4] - M[1] * M[3]) * inv;
+	};
+	double K1i[9], K2i[9];
+	inverse3(K1, K1i);
+	inverse3(K2, K2i);
+	std::vector<double> normalized((size_t)n * 4);
+	for (int r = 0; r < n; ++r)
+	{
+		const double x0 = h_points[4 * (size_t)r], y0 = h_points[4 * (size_t)r + 1], x1 = h_points[4 * (size_t)r + 2],
+		             y1 = h_points[4 * (size_t)r + 3];
+		normalized[4 * (size_t)r + 0] = K1i[0] * x0 + K1i[1] * y0 + K1i[2] * 1.0;
+		normalized[4 * (size_t)r + 1] = K1i[3] * x0 + K1i[4] * y0 + K1i[5] * 1.0;
+		normalized[4 * (size_t)r + 2] = K2i[0] * x1 + K2i[1] * y1 + K2i[2] * 1.0;
+		normalized[4 * (size_t)r + 3] = K2i[3] * x1 + K2i[4] * y1 + K2i[5] * 1.0;
+	}
+	const double threshold_normalizer = 0.25 * (K1[0] + K1[4] + K2[0] + K2[4]);
+	Driver d;
+	d.ctx = ctx;
+	d.problem = GCR_E;
+	d.n = n;
+	d.pts = normalized.data();
+	d.grid_pts = h_points;
+	d.S = *settings;
+	d.S.threshold = settings->threshold / threshold_normalizer;
+	const int r = d.run(model_out, inlier_mask);
+	if (stats)
+		*stats = d.st;
+	if (r < 0)
+	{
+		g_driver_error = d.error;
+		fprintf(stderr, "gcr_find_essential: %s\n", d.error.c_str());
 	}
 	return r;
 }

@@ -60,11 +60,17 @@ typedef struct gcr_run_stats
 /* defaults of utils::Settings + the Python drivers */
 void gcr_run_settings_default(gcr_run_settings *s);
 
-/* GCRANSAC<>::run for problem GCR_H or GCR_F on `n` correspondences (row-major FP64 n x 4, host memory).
+/* GCRANSAC<>::run for problem GCR_H, GCR_F or GCR_E (points already K-normalised) on `n` correspondences (row-major FP64 n x 4, host memory).
  * model_out: 9 doubles; inlier_mask: n bytes (1 = inlier).  Returns the inlier count (0 = no model), < 0 on error
  * (gcr_last_error(ctx)). */
 int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,
                    double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
+
+/* findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855) without its final LM bundle-adjustment polish (SURVEY 8f
+ * N2): the neighbourhood grid is built on the pixel coordinates, the run uses K^-1-normalised points and
+ * settings->threshold / mean focal length.  K1, K2: row-major 3 x 3 intrinsics.  model_out: E, 9 doubles. */
+int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, const double *K1, const double *K2,
+                       const gcr_run_settings *settings, double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,8 @@
 """pygcransac (B200) -- the reference's Python entry points on top of libgcr_b200.so.
 
-    findHomography / findFundamentalMatrix          same names, arguments, defaults and return values as
-                                                    danini/graph-cut-ransac's pybind11 module (py/bindings.cpp:1003-1178)
+    findHomography / findFundamentalMatrix / findEssentialMatrix
+                                same names, arguments, defaults and return values as danini/graph-cut-ransac's
+                                pybind11 module (py/bindings.cpp:1003-1178)
 
 The data-parallel loop body runs on the GPU through the batched host driver (graph-cut-ransac_b200/host/gcr_driver.cpp:
 GCRANSAC<>::run's sequential semantics replayed over GPU batches; the graph-cut min-cut is the reference's own BK
@@ -59,6 +60,9 @@ def _load_driver():
         lib.gcr_find_model.restype = C.c_int
         lib.gcr_find_model.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(RunSettings), C.c_void_p,
                                        C.c_void_p, C.POINTER(RunStats)]
+        lib.gcr_find_essential.restype = C.c_int
+        lib.gcr_find_essential.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(RunSettings),
+                                           C.c_void_p, C.c_void_p, C.POINTER(RunStats)]
         _driver = lib
     return _driver
 
@@ -73,12 +77,12 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
-          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device):
+          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
+    min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
     if pts.ndim != 2 or pts.shape[1] != 4:
-        raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % (4 if problem == _cabi.H else 7))
-    min_n = 4 if problem == _cabi.H else 7
+        raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)
     if pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
     if sampler not in (0, 1):
@@ -102,8 +106,13 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()
-    n_inl = lib.gcr_find_model(ctx.h, problem, pts.ctypes.data, len(pts), C.byref(s), model.ctypes.data, mask.ctypes.data,
-                               C.byref(stats))
+    if intrinsics is None:
+        n_inl = lib.gcr_find_model(ctx.h, problem, pts.ctypes.data, len(pts), C.byref(s), model.ctypes.data,
+                                   mask.ctypes.data, C.byref(stats))
+    else:
+        K1, K2 = intrinsics
+        n_inl = lib.gcr_find_essential(ctx.h, pts.ctypes.data, len(pts), K1.ctypes.data, K2.ctypes.data, C.byref(s),
+                                       model.ctypes.data, mask.ctypes.data, C.byref(stats))
     if n_inl < 0:
         raise _cabi.GcrError("gcr_find_model failed (%d): %s" % (n_inl, ctx.lib.gcr_last_error(ctx.h).decode()))
     last_statistics = stats.as_dict()
@@ -133,9 +142,21 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device)
 
 
-def findEssentialMatrix(*args, **kwargs):
-    """py/bindings.cpp:710-857.  The minimal 5-point solver, the Sampson / MAGSAC++ scoring and the K-normalisation
-    run on the GPU (gcr_solve_minimal(GCR_E), gcr_score), but the reference's non-minimal E refit (Stewenius action
-    matrix + EigenSolver) is not built yet, so the full driver is not wired for E."""
-    raise NotImplementedError("findEssentialMatrix: the non-minimal E refit is not built yet; use gcr_round(GCR_E) "
-                              "through pygcransac._cabi for the hypothesise-and-verify part")
+def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
+                        spatial_coherence_weight=0.1, max_iters=10000, min_iters=50, use_sprt=True,
+                        min_inlier_ratio_for_sprt=0.01, sampler=1, neighborhood=1, neighborhood_size=20.0, lo_number=50,
+                        sampler_variance=0.1, solver=0, seed=1, device=0):
+    """py/bindings.cpp:710-857, 1091-1112 -> findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855): 5-point (Nister)
+    minimal solver, Stewenius non-minimal refits, MSAC on the K-normalised points with threshold / mean focal length,
+    grid neighbourhood on the pixel coordinates.  Without the reference's final LM bundle-adjustment polish
+    (out of scope) -- the returned E is GC-RANSAC's own result."""
+    if solver != 0:
+        raise NotImplementedError("solver=%d: only point correspondences (solver 0) are on this path" % solver)
+    K1 = np.ascontiguousarray(K1, dtype=np.float64)
+    K2 = np.ascontiguousarray(K2, dtype=np.float64)
+    if K1.shape != (3, 3):
+        raise ValueError("K1 shape should be [3x3]")                        # bindings.cpp:752-754
+    if K2.shape != (3, 3):
+        raise ValueError("K2 shape should be [3x3]")
+    return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2))

@@ -25,7 +25,7 @@ EXPORTS = [
     "gcr_solve_minimal", "gcr_max_models", "gcr_sample_size", "gcr_model_len", "gcr_score", "gcr_score_exact",
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
-    "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host",
+    "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load_library():
         "gcr_sample_from_pool": (i32, [vp, vp, u32, i32, u64, i32, u64, u32, vp]),
         "gcr_solve_minimal": (i32, [vp, i32, vp, i32, vp, vp]),
         "gcr_max_models": (i32, [i32]),
+        "gcr_max_refit_models": (i32, [i32]),
         "gcr_sample_size": (i32, [i32]),
         "gcr_model_len": (i32, [i32]),
         "gcr_score": (i32, [vp, i32, i32, vp, vp, i32, f64, i32, vp, vp]),
@@ -302,13 +303,16 @@ class Context:
         count = len(index_sets)
         d_flat, d_off, d_sz = self.to_device(flat), self.to_device(offsets), self.to_device(sizes)
         d_w = None if weights is None else self.to_device(np.ascontiguousarray(weights, dtype=np.float64))
-        dm = self.malloc(count * 9 * 8)
-        dok = self.malloc(count)
+        R = self.lib.gcr_max_refit_models(problem)          # 1 (H, F) or 10 (E: Stewenius returns up to 10 models)
+        dm = self.malloc(count * R * 9 * 8)
+        dok = self.malloc(count * R)
         try:
             self.check(self.lib.gcr_refit(self.h, problem, pair, C.c_void_p(d_flat), C.c_void_p(d_off), C.c_void_p(d_sz),
                                           count, C.c_void_p(d_w) if d_w else None, weight_mode, C.c_void_p(dm),
                                           C.c_void_p(dok)))
-            return self.to_host(dm, (count, 3, 3), np.float64), self.to_host(dok, (count,), np.uint8)
+            if R == 1:
+                return self.to_host(dm, (count, 3, 3), np.float64), self.to_host(dok, (count,), np.uint8)
+            return self.to_host(dm, (count, R, 3, 3), np.float64), self.to_host(dok, (count, R), np.uint8)
         finally:
             for d in (d_flat, d_off, d_sz, dm, dok):
                 self.free(d)

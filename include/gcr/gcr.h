@@ -152,12 +152,17 @@ uint32_t gcr_key_index(uint64_t key);
  *    HomographyFourPointSolver::estimateNonMinimalModel (solver_homography_four_point.h:192-264).
  * F: FundamentalMatrixEstimator::estimateModelNonminimal (fundamental_estimator.h:574-618) +
  *    FundamentalMatrixEightPointSolver (solver_fundamental_matrix_eight_point.h:93-182).
+ * E: EssentialMatrixEstimator::estimateModelNonminimal (essential_estimator.h:306-336) +
+ *    EssentialMatrixFivePointSteweniusSolver::estimateModel (solver_essential_matrix_five_point_stewenius.h:114-231):
+ *    up to 10 models per set; weights are read BY POINT there (:143).
  * `count` index sets of pair `pair`; set j has set_sizes[j] indices at d_index_sets + set_offsets[j].
  * d_weights: per-point weights or NULL; weight_mode: GCR_WEIGHT_POSITIONAL reproduces the reference's positional
- * read, GCR_WEIGHT_BY_POINT reads weights[index].  d_models [count][9], d_ok [count]. */
+ * read, GCR_WEIGHT_BY_POINT reads weights[index].
+ * d_models [count][R][9], d_ok [count][R] with R = gcr_max_refit_models(problem): 1 (H, F), 10 (E). */
 gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
                      const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode,
                      double *d_models, uint8_t *d_ok);
+int gcr_max_refit_models(int problem);
 
 /* ---- K7 grid neighbourhood -------------------------------------------------------------------------------- */
 /* GridNeighborhoodGraph<4>::initialize (neighborhood/grid_neighborhood_graph.h:229-292), pair `pair`.

@@ -107,10 +107,18 @@ int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t
 int gcro_solve_e5_nister(const double *pts, const uint32_t *sample, double *E90);
 /* solver_essential_matrix_five_point_stewenius.h:114-231 (n >= 5, optional weights[sample[i]])  [unpinned]      */
 int gcro_solve_e5_stewenius(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
+/* essential_estimator.h:306-336 estimateModelNonminimal = Stewenius + Frobenius normalisation + sign (E33 >= 0);
+ * weights (optional) are read by POINT index (stewenius.h:143)  [unpinned]                                      */
+int gcro_refit_e(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
 /* essential_estimator.h:152-175 estimateModel = nister + orientation filter (:338-401) */
 int gcro_estimate_e5(const double *pts, const uint32_t *sample, double *E90);
 /* utils.h:65-110 normalizeCorrespondences: K^-1 on both images (K row-major 3x3) */
 void gcro_normalize_correspondences(const double *pts, int n, const double *K1, const double *K2, double *out);
+
+/* test hooks: the dense kernels of oracle/linalg.h that stand in for Eigen (pinned against numpy) */
+void gcro_test_colpiv_q(const double *A, int n, double *Q);
+int gcro_test_eigenvalues(const double *A, int n, double *wr, double *wi);
+void gcro_test_eigenvector(const double *A, int n, double lambda, double *v);
 
 /* ---- absolute pose (a15) ---------------------------------------------------------------------------------- */
 /* solver_p3p.h:177-385 Lambda-Twist; returns #models (0..4), 3x4 row-major each  [unpinned] */

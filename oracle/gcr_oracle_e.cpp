@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace
 {
@@ -208,6 +209,180 @@ int gcro_solve_e5_nister(const double *pts, const uint32_t *sample, double *E90)
 	}
 	return n_models;
 }
+
+// ---- Stewenius non-minimal solver ------------------------------------------------------------------------------------
+namespace
+{
+	// GrevLex orders of solver_essential_matrix_five_point_stewenius.h:232-318
+	// degree <= 2: x^2 xy y^2 xz yz z^2 x y z 1
+	const int S_MONO2[10][3] = {{2, 0, 0}, {1, 1, 0}, {0, 2, 0}, {1, 0, 1}, {0, 1, 1}, {0, 0, 2}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+	// degree <= 3: x^3 x^2y xy^2 y^3 x^2z xyz y^2z xz^2 yz^2 z^3 x^2 xy y^2 xz yz z^2 x y z 1
+	const int S_MONO3[20][3] = {{3, 0, 0}, {2, 1, 0}, {1, 2, 0}, {0, 3, 0}, {2, 0, 1}, {1, 1, 1}, {0, 2, 1}, {1, 0, 2}, {0, 1, 2}, {0, 0, 3},
+	                            {2, 0, 0}, {1, 1, 0}, {0, 2, 0}, {1, 0, 1}, {0, 1, 1}, {0, 0, 2}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+	// c (deg 2, GrevLex) += s * a * b  (multiplyDegOnePoly, :235-260)
+	void s_mul11(const double *a, const double *b, double *c, double s)
+	{
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j)
+				c[find_mono(S_MONO2, 10, MONO1[i][0] + MONO1[j][0], MONO1[i][1] + MONO1[j][1], MONO1[i][2] + MONO1[j][2])] += s * a[i] * b[j];
+	}
+	// c (deg 3, GrevLex) += s * a (deg 2) * b (deg 1)  (multiplyDegTwoDegOnePoly, :264-309)
+	void s_mul21(const double *a, const double *b, double *c, double s)
+	{
+		for (int i = 0; i < 10; ++i)
+			for (int j = 0; j < 4; ++j)
+				c[find_mono(S_MONO3, 20, S_MONO2[i][0] + MONO1[j][0], S_MONO2[i][1] + MONO1[j][1], S_MONO2[i][2] + MONO1[j][2])] += s * a[i] * b[j];
+	}
+}
+
+extern "C" {
+
+// solver_essential_matrix_five_point_stewenius.h:114-231.  weights (optional) are read by POINT index
+// (weights_[sample_[i]], :143) -- unlike the H / 8-point solvers.  Models come out un-normalised, in the order of the
+// action matrix' real eigenvalues as our QR iteration deflates them (Eigen's order is equally an artefact of its
+// Schur form; callers compare score-wise, GCRANSAC.h:866-890).
+int gcro_solve_e5_stewenius(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90)
+{
+	if (n < 5)
+		return 0;
+	// :127-168 weighted epipolar rows, and their normal matrix (:182-183)
+	std::vector<double> A((size_t)n * 9);
+	for (int i = 0; i < n; ++i)
+	{
+		const size_t idx = sample ? sample[i] : (size_t)i;
+		const double *p = pts + 4 * idx;
+		const double w = weights ? weights[idx] : 1.0;
+		const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+		const double wx0 = w * x0, wx1 = w * x1, wy0 = w * y0, wy1 = w * y1;
+		double *r = &A[(size_t)i * 9];
+		r[0] = wx0 * x1; r[1] = wx0 * y1; r[2] = wx0; r[3] = wy0 * x1; r[4] = wy0 * y1; r[5] = wy0; r[6] = wx1; r[7] = wy1; r[8] = w;
+	}
+	double N[9][4]; // nullSpace (9 x 4)
+	if (n == 5)
+	{
+		double ker[9 * 4];
+		if (gcro::fullpiv_lu_kernel(A.data(), 5, 9, ker, 4) != 4) // :176-180
+			return 0;
+		for (int j = 0; j < 9; ++j)
+			for (int b = 0; b < 4; ++b)
+				N[j][b] = ker[j * 4 + b];
+	}
+	else
+	{
+		double AtA[81], Q[81];
+		for (int a = 0; a < 9; ++a)
+			for (int b = 0; b < 9; ++b)
+			{
+				double s = 0;
+				for (int i = 0; i < n; ++i)
+					s += A[(size_t)i * 9 + a] * A[(size_t)i * 9 + b];
+				AtA[9 * a + b] = s;
+			}
+		gcro::colpiv_householder_q(AtA, 9, Q); // :182-187 ColPivHouseholderQR(A^T A).matrixQ().rightCols<4>()
+		for (int j = 0; j < 9; ++j)
+			for (int b = 0; b < 4; ++b)
+				N[j][b] = Q[9 * j + 5 + b];
+	}
+	// :189-192 E(i, j) as a polynomial in [x y z 1]: row i + 3 j of the null space
+	const double *Ee[3][3];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			Ee[i][j] = N[i + 3 * j];
+	// :195, :361-390 trace constraint rows 0..8, determinant row 9
+	double C[10][20];
+	std::memset(C, 0, sizeof(C));
+	double eet[3][3][10], trace[10];
+	std::memset(eet, 0, sizeof(eet));
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			for (int k = 0; k < 3; ++k)
+				s_mul11(Ee[i][k], Ee[j][k], eet[i][j], 2.0);
+	for (int m = 0; m < 10; ++m)
+		trace[m] = eet[0][0][m] + eet[1][1][m] + eet[2][2][m];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+		{
+			for (int k = 0; k < 3; ++k)
+				s_mul21(eet[i][k], Ee[k][j], C[3 * i + j], 1.0);
+			s_mul21(trace, Ee[i][j], C[3 * i + j], -0.5);
+		}
+	{
+		double d[10];
+		std::memset(d, 0, sizeof(d)); s_mul11(Ee[0][1], Ee[1][2], d, 1.0); s_mul11(Ee[0][2], Ee[1][1], d, -1.0); s_mul21(d, Ee[2][0], C[9], 1.0);
+		std::memset(d, 0, sizeof(d)); s_mul11(Ee[0][2], Ee[1][0], d, 1.0); s_mul11(Ee[0][0], Ee[1][2], d, -1.0); s_mul21(d, Ee[2][1], C[9], 1.0);
+		std::memset(d, 0, sizeof(d)); s_mul11(Ee[0][0], Ee[1][1], d, 1.0); s_mul11(Ee[0][1], Ee[1][0], d, -1.0); s_mul21(d, Ee[2][2], C[9], 1.0);
+	}
+	// :198-199 FullPivLU of the left block, solve for the right block
+	double L[100], R[100], X[100];
+	for (int i = 0; i < 10; ++i)
+		for (int j = 0; j < 10; ++j)
+		{
+			L[10 * i + j] = C[i][j];
+			R[10 * i + j] = C[i][10 + j];
+		}
+	if (!gcro::fullpiv_lu_solve(L, 10, R, 10, X))
+		return 0;
+	// :201-209 action matrix
+	double Am[100];
+	std::memset(Am, 0, sizeof(Am));
+	const int src_row[6] = {0, 1, 2, 4, 5, 7};
+	for (int r = 0; r < 6; ++r)
+		for (int j = 0; j < 10; ++j)
+			Am[10 * r + j] = X[10 * src_row[r] + j];
+	Am[10 * 6 + 0] = -1.0;
+	Am[10 * 7 + 1] = -1.0;
+	Am[10 * 8 + 3] = -1.0;
+	Am[10 * 9 + 6] = -1.0;
+	// :211-228 real eigenvalues -> eigenvector tail (x y z 1) -> E
+	double wr[10], wi[10];
+	for (int i = 0; i < 100; ++i)
+		if (!std::isfinite(Am[i]))
+			return 0;
+	if (!gcro::real_eigenvalues(Am, 10, wr, wi))
+		return 0;
+	int n_models = 0;
+	for (int e = 0; e < 10; ++e)
+	{
+		if (wi[e] != 0.0)
+			continue;
+		double v[10];
+		gcro::eigenvector_of(Am, 10, wr[e], v);
+		double *E = E90 + 9 * n_models;
+		for (int k = 0; k < 9; ++k) // E.data()[k] (column-major) = nullSpace.row(k) . v.tail<4>()
+		{
+			const double val = N[k][0] * v[6] + N[k][1] * v[7] + N[k][2] * v[8] + N[k][3] * v[9];
+			E[3 * (k % 3) + k / 3] = val;
+		}
+		++n_models;
+	}
+	return n_models;
+}
+
+// essential_estimator.h:306-336 estimateModelNonminimal: Stewenius + Frobenius normalisation + sign (E33 >= 0)
+int gcro_refit_e(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90)
+{
+	if (n < 5) // nonMinimalSampleSize()
+		return 0;
+	const int count = gcro_solve_e5_stewenius(pts, sample, n, weights, E90);
+	for (int m = 0; m < count; ++m)
+	{
+		double *E = E90 + 9 * m;
+		double s = 0;
+		for (int k = 0; k < 9; ++k) s += E[k] * E[k];
+		s = std::sqrt(s);
+		for (int k = 0; k < 9; ++k) E[k] /= s;
+		if (E[8] < 0)
+			for (int k = 0; k < 9; ++k) E[k] = -E[k];
+	}
+	return count;
+}
+
+/* test hooks for the dense kernels of linalg.h (pinned against numpy in tests/test_oracle_solvers.py) */
+void gcro_test_colpiv_q(const double *A, int n, double *Q) { gcro::colpiv_householder_q(A, n, Q); }
+int gcro_test_eigenvalues(const double *A, int n, double *wr, double *wi) { return gcro::real_eigenvalues(A, n, wr, wi) ? 1 : 0; }
+void gcro_test_eigenvector(const double *A, int n, double lambda, double *v) { gcro::eigenvector_of(A, n, lambda, v); }
+
+} // extern "C"
 
 // essential_estimator.h:338-401 (same arithmetic as fundamental_estimator.h:737-800)
 static int e_orientation_valid(const double *E, const double *pts, const uint32_t *sample, int m)

@@ -326,7 +326,7 @@ int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t
 {
 	size_t inlier_number = 0;
 	const double a = (double)m, b = n_inl * min_ratio;
-	const double minimum_inlier_number = a < b ? b : a; // MAX(sample_size, inliers_.size() * ratio)
+	const size_t minimum_inlier_number = (size_t)(a > b ? a : b); // const size_t x = MAX(sample_size, inliers_.size() * ratio): truncated
 	const double squared_threshold = truncated_thr * truncated_thr;
 	for (int i = 0; i < n_inl; ++i)
 		if (gcro_sqres_symepi(pts + 4 * (size_t)inl[i], F9) < squared_threshold)

@@ -446,4 +446,333 @@ namespace gcro
 				V[(size_t)i * n + c] = Vt[(size_t)i * n + o];
 		}
 	}
+
+	// ---- Eigen ColPivHouseholderQR::matrixQ() of a square n x n matrix (n <= 16) ------------------------------
+	// Restates Eigen 3.4 ColPivHouseholderQR::computeInPlace: pivot = first column of largest (down-dated) norm,
+	// LAPACK-style norm down-dating with recomputation below sqrt(eps), Householder vectors (1, essential) with
+	// beta = -sign(c0) |x| and tau = (beta - c0) / beta (MatrixBase::makeHouseholder).  Q = H_0 H_1 ... H_{n-1},
+	// row-major.  Used by the Stewenius non-minimal solver: Q.rightCols<4>() of A^T A
+	// (solver_essential_matrix_five_point_stewenius.h:182-187).
+	inline void colpiv_householder_q(const double *A_in, int n, double *Q)
+	{
+		std::vector<double> A(A_in, A_in + (size_t)n * n);
+		std::vector<double> updated(n), direct(n), tau(n, 0.0);
+		auto at = [&](int i, int j) -> double & { return A[(size_t)i * n + j]; };
+		for (int j = 0; j < n; ++j)
+		{
+			double s = 0;
+			for (int i = 0; i < n; ++i) s += at(i, j) * at(i, j);
+			updated[j] = direct[j] = std::sqrt(s);
+		}
+		const double downdate_threshold = std::sqrt(std::numeric_limits<double>::epsilon());
+		for (int k = 0; k < n; ++k)
+		{
+			int big = k;
+			for (int j = k + 1; j < n; ++j)
+				if (updated[j] > updated[big]) big = j;
+			if (big != k)
+			{
+				for (int i = 0; i < n; ++i) std::swap(at(i, k), at(i, big));
+				std::swap(updated[k], updated[big]);
+				std::swap(direct[k], direct[big]);
+			}
+			// makeHouseholderInPlace on A[k:, k]
+			double tail = 0;
+			for (int i = k + 1; i < n; ++i) tail += at(i, k) * at(i, k);
+			const double c0 = at(k, k);
+			double beta;
+			if (tail <= std::numeric_limits<double>::min())
+			{
+				tau[k] = 0.0;
+				beta = c0;
+				for (int i = k + 1; i < n; ++i) at(i, k) = 0.0;
+			}
+			else
+			{
+				beta = std::sqrt(c0 * c0 + tail);
+				if (c0 >= 0) beta = -beta;
+				for (int i = k + 1; i < n; ++i) at(i, k) /= (c0 - beta);
+				tau[k] = (beta - c0) / beta;
+			}
+			at(k, k) = beta;
+			// apply H_k = I - tau v v^T (v = [1; essential]) to the trailing columns
+			for (int j = k + 1; j < n; ++j)
+			{
+				double dot = at(k, j);
+				for (int i = k + 1; i < n; ++i) dot += at(i, k) * at(i, j);
+				dot *= tau[k];
+				at(k, j) -= dot;
+				for (int i = k + 1; i < n; ++i) at(i, j) -= dot * at(i, k);
+			}
+			for (int j = k + 1; j < n; ++j)
+			{
+				if (updated[j] != 0.0)
+				{
+					double temp = std::fabs(at(k, j)) / updated[j];
+					temp = (1.0 + temp) * (1.0 - temp);
+					if (temp < 0) temp = 0;
+					const double r = updated[j] / direct[j];
+					const double temp2 = temp * r * r;
+					if (temp2 <= downdate_threshold)
+					{
+						double s = 0;
+						for (int i = k + 1; i < n; ++i) s += at(i, j) * at(i, j);
+						direct[j] = std::sqrt(s);
+						updated[j] = direct[j];
+					}
+					else
+						updated[j] *= std::sqrt(temp);
+				}
+			}
+		}
+		// Q = H_0 ... H_{n-1} applied to the identity (from the last reflector backwards)
+		for (int i = 0; i < n; ++i)
+			for (int j = 0; j < n; ++j)
+				Q[(size_t)i * n + j] = i == j ? 1.0 : 0.0;
+		for (int k = n - 1; k >= 0; --k)
+			for (int j = 0; j < n; ++j)
+			{
+				double dot = Q[(size_t)k * n + j];
+				for (int i = k + 1; i < n; ++i) dot += at(i, k) * Q[(size_t)i * n + j];
+				dot *= tau[k];
+				Q[(size_t)k * n + j] -= dot;
+				for (int i = k + 1; i < n; ++i) Q[(size_t)i * n + j] -= dot * at(i, k);
+			}
+	}
+
+	// ---- eigenvalues of a real non-symmetric n x n matrix (n <= 16): Householder reduction to Hessenberg form +
+	// Francis double-shift QR (the EISPACK orthes / hqr pair Eigen's RealSchur derives from; no balancing, like
+	// Eigen::EigenSolver).  wr / wi = real / imaginary parts.  Returns false if an eigenvalue fails to converge.
+	inline bool real_eigenvalues(const double *A_in, int n, double *wr, double *wi)
+	{
+		std::vector<double> a(A_in, A_in + (size_t)n * n);
+		auto A = [&](int i, int j) -> double & { return a[(size_t)i * n + j]; };
+		// orthogonal reduction to upper Hessenberg form
+		for (int m = 1; m < n - 1; ++m)
+		{
+			double scale = 0;
+			for (int i = m; i < n; ++i) scale += std::fabs(A(i, m - 1));
+			if (scale == 0.0) continue;
+			std::vector<double> ort(n, 0.0);
+			double h = 0;
+			for (int i = n - 1; i >= m; --i)
+			{
+				ort[i] = A(i, m - 1) / scale;
+				h += ort[i] * ort[i];
+			}
+			double g = std::sqrt(h);
+			if (ort[m] > 0) g = -g;
+			h -= ort[m] * g;
+			ort[m] -= g;
+			for (int j = m; j < n; ++j)
+			{
+				double f = 0;
+				for (int i = n - 1; i >= m; --i) f += ort[i] * A(i, j);
+				f /= h;
+				for (int i = m; i < n; ++i) A(i, j) -= f * ort[i];
+			}
+			for (int i = 0; i < n; ++i)
+			{
+				double f = 0;
+				for (int j = n - 1; j >= m; --j) f += ort[j] * A(i, j);
+				f /= h;
+				for (int j = m; j < n; ++j) A(i, j) -= f * ort[j];
+			}
+			A(m, m - 1) = scale * g;
+			for (int i = m + 1; i < n; ++i) A(i, m - 1) = 0.0;
+		}
+		// hqr
+		double anorm = 0;
+		for (int i = 0; i < n; ++i)
+			for (int j = std::max(i - 1, 0); j < n; ++j)
+				anorm += std::fabs(A(i, j));
+		int nn = n - 1;
+		double t = 0.0;
+		auto sign = [](double x, double y) { return y >= 0 ? std::fabs(x) : -std::fabs(x); };
+		while (nn >= 0)
+		{
+			int its = 0, l;
+			do
+			{
+				for (l = nn; l >= 1; --l)
+				{
+					double s = std::fabs(A(l - 1, l - 1)) + std::fabs(A(l, l));
+					if (s == 0.0) s = anorm;
+					if (std::fabs(A(l, l - 1)) + s == s)
+					{
+						A(l, l - 1) = 0.0;
+						break;
+					}
+				}
+				double x = A(nn, nn);
+				if (l == nn)
+				{
+					wr[nn] = x + t;
+					wi[nn--] = 0.0;
+				}
+				else
+				{
+					double y = A(nn - 1, nn - 1);
+					double w = A(nn, nn - 1) * A(nn - 1, nn);
+					if (l == nn - 1)
+					{
+						double p = 0.5 * (y - x);
+						double q = p * p + w;
+						double z = std::sqrt(std::fabs(q));
+						x += t;
+						if (q >= 0.0)
+						{
+							z = p + sign(z, p);
+							wr[nn - 1] = wr[nn] = x + z;
+							if (z != 0.0) wr[nn] = x - w / z;
+							wi[nn - 1] = wi[nn] = 0.0;
+						}
+						else
+						{
+							wr[nn - 1] = wr[nn] = x + p;
+							wi[nn - 1] = -(wi[nn] = z);
+						}
+						nn -= 2;
+					}
+					else
+					{
+						if (its == 60) return false;
+						if (its == 10 || its == 20)
+						{
+							t += x;
+							for (int i = 0; i <= nn; ++i) A(i, i) -= x;
+							const double s = std::fabs(A(nn, nn - 1)) + std::fabs(A(nn - 1, nn - 2));
+							y = x = 0.75 * s;
+							w = -0.4375 * s * s;
+						}
+						++its;
+						int m;
+						double p = 0, q = 0, r = 0, z;
+						for (m = nn - 2; m >= l; --m)
+						{
+							z = A(m, m);
+							r = x - z;
+							double s = y - z;
+							p = (r * s - w) / A(m + 1, m) + A(m, m + 1);
+							q = A(m + 1, m + 1) - z - r - s;
+							r = A(m + 2, m + 1);
+							s = std::fabs(p) + std::fabs(q) + std::fabs(r);
+							p /= s; q /= s; r /= s;
+							if (m == l) break;
+							const double u = std::fabs(A(m, m - 1)) * (std::fabs(q) + std::fabs(r));
+							const double v = std::fabs(p) * (std::fabs(A(m - 1, m - 1)) + std::fabs(z) + std::fabs(A(m + 1, m + 1)));
+							if (u + v == v) break;
+						}
+						for (int i = m + 2; i <= nn; ++i)
+						{
+							A(i, i - 2) = 0.0;
+							if (i != m + 2) A(i, i - 3) = 0.0;
+						}
+						for (int k = m; k <= nn - 1; ++k)
+						{
+							if (k != m)
+							{
+								p = A(k, k - 1);
+								q = A(k + 1, k - 1);
+								r = 0.0;
+								if (k != nn - 1) r = A(k + 2, k - 1);
+								if ((x = std::fabs(p) + std::fabs(q) + std::fabs(r)) != 0.0)
+								{
+									p /= x; q /= x; r /= x;
+								}
+							}
+							const double s = sign(std::sqrt(p * p + q * q + r * r), p);
+							if (s != 0.0)
+							{
+								if (k == m)
+								{
+									if (l != m) A(k, k - 1) = -A(k, k - 1);
+								}
+								else
+									A(k, k - 1) = -s * x;
+								p += s;
+								x = p / s;
+								y = q / s;
+								z = r / s;
+								q /= p;
+								r /= p;
+								for (int j = k; j <= nn; ++j)
+								{
+									p = A(k, j) + q * A(k + 1, j);
+									if (k != nn - 1)
+									{
+										p += r * A(k + 2, j);
+										A(k + 2, j) -= p * z;
+									}
+									A(k + 1, j) -= p * y;
+									A(k, j) -= p * x;
+								}
+								const int mmin = nn < k + 3 ? nn : k + 3;
+								for (int i = l; i <= mmin; ++i)
+								{
+									p = x * A(i, k) + y * A(i, k + 1);
+									if (k != nn - 1)
+									{
+										p += z * A(i, k + 2);
+										A(i, k + 2) -= p * r;
+									}
+									A(i, k + 1) -= p * q;
+									A(i, k) -= p;
+								}
+							}
+						}
+					}
+				}
+			} while (l < nn - 1);
+		}
+		return true;
+	}
+
+	// ---- eigenvector of the real eigenvalue lambda of A (n <= 16) by inverse iteration on A - lambda I
+	// (partial-pivot LU with tiny pivots replaced by eps |A|, two solves), unit 2-norm like EigenSolver's.
+	inline void eigenvector_of(const double *A_in, int n, double lambda, double *v)
+	{
+		std::vector<double> M(A_in, A_in + (size_t)n * n);
+		double anorm = 0;
+		for (double e : M) anorm = std::max(anorm, std::fabs(e));
+		for (int i = 0; i < n; ++i) M[(size_t)i * n + i] -= lambda;
+		const double tiny = std::numeric_limits<double>::epsilon() * (anorm > 0 ? anorm : 1.0);
+		std::vector<int> piv(n);
+		for (int k = 0; k < n; ++k)
+		{
+			int p = k;
+			for (int i = k + 1; i < n; ++i)
+				if (std::fabs(M[(size_t)i * n + k]) > std::fabs(M[(size_t)p * n + k])) p = i;
+			piv[k] = p;
+			if (p != k)
+				for (int j = 0; j < n; ++j) std::swap(M[(size_t)k * n + j], M[(size_t)p * n + j]);
+			if (std::fabs(M[(size_t)k * n + k]) < tiny) M[(size_t)k * n + k] = tiny;
+			for (int i = k + 1; i < n; ++i)
+			{
+				const double f = M[(size_t)i * n + k] / M[(size_t)k * n + k];
+				M[(size_t)i * n + k] = f;
+				for (int j = k + 1; j < n; ++j) M[(size_t)i * n + j] -= f * M[(size_t)k * n + j];
+			}
+		}
+		for (int i = 0; i < n; ++i) v[i] = 1.0;
+		for (int iter = 0; iter < 3; ++iter)
+		{
+			if (iter > 0) // the first pass starts from U x = 1 (LAPACK xLAEIN's choice); later ones apply L too
+				for (int k = 0; k < n; ++k)
+				{
+					std::swap(v[k], v[piv[k]]);
+					for (int i = k + 1; i < n; ++i) v[i] -= M[(size_t)i * n + k] * v[k];
+				}
+			for (int i = n - 1; i >= 0; --i)
+			{
+				double s = v[i];
+				for (int j = i + 1; j < n; ++j) s -= M[(size_t)i * n + j] * v[j];
+				v[i] = s / M[(size_t)i * n + i];
+			}
+			double nrm = 0;
+			for (int i = 0; i < n; ++i) nrm += v[i] * v[i];
+			nrm = std::sqrt(nrm);
+			for (int i = 0; i < n; ++i) v[i] /= nrm;
+		}
+	}
 }

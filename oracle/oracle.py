@@ -96,6 +96,14 @@ class Oracle:
             fn.argtypes = [_dp, _u32p, _dp]
         lib.gcro_solve_e5_stewenius.restype = C.c_int
         lib.gcro_solve_e5_stewenius.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        lib.gcro_refit_e.restype = C.c_int
+        lib.gcro_refit_e.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        lib.gcro_test_colpiv_q.restype = None
+        lib.gcro_test_colpiv_q.argtypes = [_dp, C.c_int, _dp]
+        lib.gcro_test_eigenvalues.restype = C.c_int
+        lib.gcro_test_eigenvalues.argtypes = [_dp, C.c_int, _dp, _dp]
+        lib.gcro_test_eigenvector.restype = None
+        lib.gcro_test_eigenvector.argtypes = [_dp, C.c_int, C.c_double, _dp]
         lib.gcro_f_orientation_valid.restype = C.c_int
         lib.gcro_f_orientation_valid.argtypes = [_dp, _dp, _u32p, C.c_int]
         lib.gcro_f_valid_model_ratio.restype = C.c_int
@@ -218,6 +226,33 @@ class Oracle:
         cnt = self.lib.gcro_solve_e5_stewenius(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
         return out[: cnt * 9].reshape(cnt, 3, 3).copy()
 
+    def refit_e(self, pts, sample, weights=None):
+        """EssentialMatrixEstimator::estimateModelNonminimal: normalised, E33 >= 0 models [cnt, 3, 3]."""
+        out = np.empty(90)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        cnt = self.lib.gcro_refit_e(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
+        return out[: cnt * 9].reshape(cnt, 3, 3).copy()
+
+    def colpiv_q(self, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        Q = np.empty_like(A)
+        self.lib.gcro_test_colpiv_q(A, A.shape[0], Q)
+        return Q
+
+    def eigenvalues(self, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        n = A.shape[0]
+        wr, wi = np.empty(n), np.empty(n)
+        ok = self.lib.gcro_test_eigenvalues(A, n, wr, wi)
+        return bool(ok), wr + 1j * wi
+
+    def eigenvector(self, A, lam):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        v = np.empty(A.shape[0])
+        self.lib.gcro_test_eigenvector(A, A.shape[0], float(lam), v)
+        return v
+
     def solve_p3p(self, pts5, sample):
         return self._multi(self.lib.gcro_solve_p3p, pts5, sample, 4, 3, 4)
 
@@ -275,13 +310,13 @@ class Ref:
         lib.ref_run.restype = C.c_int
         lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
-                                _u64p, C.POINTER(C.c_double)]
+                                _u64p, C.POINTER(C.c_double), C.c_void_p]
 
     def round(self, problem, scoring, pts, seed, first, count, thr):
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
-            min_iters=50, lo_number=50, seed=1, scoring_kind=0):
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
@@ -292,7 +327,7 @@ class Ref:
         score = C.c_double()
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
-                                 C.byref(score))
+                                 C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data)
         if n_inl < 0:
             raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
         names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",

@@ -27,7 +27,7 @@ namespace
 	struct ProblemTraits;
 	template <> struct ProblemTraits<GCRO_H> { static constexpr size_t m = 4, nonmin = 4, maxsol = 1, rows = 3, cols = 3; static constexpr bool weighting = true; };
 	template <> struct ProblemTraits<GCRO_F> { static constexpr size_t m = 7, nonmin = 8, maxsol = 3, rows = 3, cols = 3; static constexpr bool weighting = true; };
-	template <> struct ProblemTraits<GCRO_E> { static constexpr size_t m = 5, nonmin = 6, maxsol = 10, rows = 3, cols = 3; static constexpr bool weighting = true; };
+	template <> struct ProblemTraits<GCRO_E> { static constexpr size_t m = 5, nonmin = 5, maxsol = 10, rows = 3, cols = 3; static constexpr bool weighting = true; };
 	template <> struct ProblemTraits<GCRO_PNP> { static constexpr size_t m = 3, nonmin = 6, maxsol = 4, rows = 3, cols = 4; static constexpr bool weighting = false; };
 
 	inline void to_flat(const Eigen::MatrixXd &d, double *out)
@@ -125,7 +125,7 @@ namespace
 			else if constexpr (PROBLEM == GCRO_F)
 				count = gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
 			else if constexpr (PROBLEM == GCRO_E)
-				count = gcro_solve_e5_stewenius(pts, s.data(), (int)sample_number_, weights_, out);
+				count = gcro_refit_e(pts, s.data(), (int)sample_number_, weights_, out);
 			else
 				count = 0;
 			for (int i = 0; i < count; ++i)
@@ -385,7 +385,7 @@ namespace
 	};
 
 	template <int PROBLEM, class Scoring>
-	int run_reference(const cv::Mat &points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
+	int run_reference(const cv::Mat &points, const cv::Mat &grid_points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
 	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
 	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out)
 	{
@@ -393,7 +393,7 @@ namespace
 		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
 		Est estimator;
 		std::vector<double> cs(cell_sizes, cell_sizes + 4);
-		Grid graph(&points, cs, (size_t)cells_per_axis);
+		Grid graph(&grid_points, cs, (size_t)cells_per_axis); // E: built on the pixel coordinates (py/gcransac_python.cpp:2592-2600)
 		CounterSampler main_sampler(&points, seed, 0u), lo_sampler(&points, seed, 1u);
 		Model model;
 		GCRANSAC<Est, Grid, Scoring> gcransac;
@@ -440,14 +440,17 @@ extern "C" {
 // GCR_REF_WITH_CUDA only).  Returns the inlier count.
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
-            uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out)
+            uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
+            const double *grid_pts)
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
-#define GCR_RUN(P, S) run_reference<P, S>(points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out)
+	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
+#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out)
 	if (scoring_kind == 0)
 	{
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);
 		if (problem == GCRO_F) return GCR_RUN(GCRO_F, MSACScoringFunction<OracleEstimator<GCRO_F>>);
+		if (problem == GCRO_E) return GCR_RUN(GCRO_E, MSACScoringFunction<OracleEstimator<GCRO_E>>);
 		return -1;
 	}
 #ifdef GCR_REF_WITH_CUDA
@@ -456,7 +459,9 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
 		typedef gcr::CudaMSACScoringFunction<OracleEstimator<GCRO_H>, GCR_H> SH;
 		typedef gcr::CudaMSACScoringFunction<OracleEstimator<GCRO_F>, GCR_F> SF;
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, SH);
+		typedef gcr::CudaMSACScoringFunction<OracleEstimator<GCRO_E>, GCR_E> SE;
 		if (problem == GCRO_F) return GCR_RUN(GCRO_F, SF);
+		if (problem == GCRO_E) return GCR_RUN(GCRO_E, SE);
 		return -1;
 	}
 #endif

@@ -57,3 +57,45 @@ def five_point(P):
         e=N[0]*x+N[1]*y+N[2]*z+N[3]; Em_=e.reshape(3,3).T
         out.append(Em_/np.linalg.norm(Em_))
     return out, c
+
+
+# GrevLex column order of solver_essential_matrix_five_point_stewenius.h:264-309
+S3=[(3,0,0),(2,1,0),(1,2,0),(0,3,0),(2,0,1),(1,1,1),(0,2,1),(1,0,2),(0,1,2),(0,0,3),(2,0,0),(1,1,0),(0,2,0),(1,0,1),(0,1,1),(0,0,2),(1,0,0),(0,1,0),(0,0,1),(0,0,0)]
+def stewenius(P, w=None):
+    """Independent numpy statement of EssentialMatrixFivePointSteweniusSolver::estimateModel for n > 5 points followed
+    by EssentialMatrixEstimator::estimateModelNonminimal's normalisation: pivoted QR of A^T A (LAPACK dgeqp3 via scipy),
+    dictionary polynomials, numpy.linalg.solve / eig.  Returns the normalised models (E33 >= 0), any order."""
+    from scipy.linalg import qr
+    P=np.asarray(P,dtype=float); w=np.ones(len(P)) if w is None else np.asarray(w,dtype=float)
+    A=np.array([[p[0]*p[2],p[0]*p[3],p[0],p[1]*p[2],p[1]*p[3],p[1],p[2],p[3],1] for p in P])*w[:,None]
+    Q,_,_=qr(A.T@A,pivoting=True)
+    N=Q[:,5:]                      # 9 x 4
+    E=[[{mono1[b]:N[i+3*j][b] for b in range(4)} for j in range(3)] for i in range(3)]
+    EET=[[{} for j in range(3)] for i in range(3)]
+    for i in range(3):
+        for j in range(3):
+            for k in range(3): EET[i][j]=padd(EET[i][j],pmul(E[i][k],E[j][k]),2)
+    tr={}
+    for i in range(3): tr=padd(tr,EET[i][i])
+    rows=[]
+    for i in range(3):
+        for j in range(3):
+            r={}
+            for k in range(3): r=padd(r,pmul(EET[i][k],E[k][j]))
+            rows.append(padd(r,pmul(tr,E[i][j]),-0.5))
+    d=padd(pmul(pmul(E[0][1],E[1][2]),E[2][0]),pmul(pmul(E[0][2],E[1][1]),E[2][0]),-1)
+    d=padd(d,pmul(padd(pmul(E[0][2],E[1][0]),pmul(E[0][0],E[1][2]),-1),E[2][1]))
+    d=padd(d,pmul(padd(pmul(E[0][0],E[1][1]),pmul(E[0][1],E[1][0]),-1),E[2][2]))
+    rows.append(d)
+    C=np.array([[r.get(m,0) for m in S3] for r in rows])
+    X=np.linalg.solve(C[:,:10],C[:,10:])
+    Am=np.zeros((10,10)); Am[:3]=X[:3]; Am[3]=X[4]; Am[4]=X[5]; Am[5]=X[7]
+    Am[6,0]=Am[7,1]=Am[8,3]=Am[9,6]=-1
+    lam,V=np.linalg.eig(Am)
+    out=[]
+    for i in range(10):
+        if lam[i].imag!=0: continue
+        e=N@V[6:,i].real; Em_=e.reshape(3,3).T
+        Em_=Em_/np.linalg.norm(Em_)
+        out.append(-Em_ if Em_[2,2]<0 else Em_)
+    return out

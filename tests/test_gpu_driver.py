@@ -83,3 +83,29 @@ def test_findfundamental_matches_reference_run(pyg, ref):
         assert np.array_equal(mask, want["mask"])
         assert _up_to_scale(want["model"], F) < 1e-5
         assert (mask & inl).sum() > 0.95 * inl.sum()
+
+
+def test_findessential_matches_reference_run(pyg, ref, oracle):
+    """findEssentialMatrix (5-point minimal, Stewenius non-minimal refits with up to 10 models each, MSAC on K-normalised
+    points, grid on the pixel coordinates) against the reference's verbatim GCRANSAC<>::run over the oracle's E estimator."""
+    pts, Fm, Em, K, inl = synth.epipolar_pair(1500, 0.5, seed=35)
+    npts = oracle.normalize_correspondences(pts, K, K)
+    for seed, weight in ((7, 0.0), (8, 0.1)):
+        E, mask = pyg.findEssentialMatrix(pts, K, K, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
+                                          neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+        st = pyg.last_statistics
+        cs = np.array([1024 / 4.0] * 4)
+        thr = 0.75 / (0.25 * (K[0, 0] + K[1, 1] + K[0, 0] + K[1, 1]))          # py/gcransac_python.cpp:2624-2626, 2737
+        want = ref.run(O.E, npts, cs, 4, thr, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50,
+                       seed=seed, grid_pts=pts)
+        assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+        assert st["graph_cut_number"] == want["stats"]["graph_cuts"]
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert (mask != want["mask"]).sum() <= 2, (int(mask.sum()), int(want["mask"].sum()))
+        assert _up_to_scale(want["model"], E) < 1e-5
+        assert abs(st["score"] - want["score"]) <= 1e-6 * want["score"]
+        assert (mask & inl).sum() > 0.95 * inl.sum()
+    with pytest.raises(ValueError):
+        pyg.findEssentialMatrix(pts, np.eye(2), K, 10, 10, 10, 10, [])
+    with pytest.raises(ValueError):
+        pyg.findEssentialMatrix(np.zeros((4, 4)), K, K, 10, 10, 10, 10, [])

@@ -76,6 +76,57 @@ def test_refit_f8_matches_oracle(gcr_ctx, oracle):
     assert ok[0] and _up_to_scale(oracle.refit(O.F, pts, sets[-1], weights=w), got[0]) < RTOL_MODEL
 
 
+def _e_set_distance(got, want):
+    """every model of `got` has a partner in `want` (normalised, E33 >= 0 on both sides): worst partner distance"""
+    return max(min(np.abs(E - q).max() for q in want) for E in got) if len(got) else 0.0
+
+
+def test_refit_e_stewenius_matches_oracle(gcr_ctx, oracle):
+    """K6 for E (pivoted-QR null space of A^T A + the 5-point kernel's Sturm back end) against the oracle's restatement of
+    the reference's Stewenius action-matrix solver: same model set to 1e-5 (SURVEY a13's acceptance), LO-sized sets,
+    small sets, all inliers, weights read by POINT (stewenius.h:143) and the n == 5 LU branch."""
+    pts, Fm, Em, Kc, inl = synth.epipolar_pair(2048, 0.5, seed=57)
+    npts = oracle.normalize_correspondences(pts, Kc, Kc)
+    gcr_ctx.points_upload(npts)
+    rng = np.random.default_rng(4)
+    inl_idx = np.nonzero(inl)[0]
+    sets = _index_sets(rng, inl_idx, [35] * 40 + [5, 5, 6, 7, 12, 100, len(inl_idx)])
+    sets += [rng.choice(2048, size=35, replace=False).astype(np.uint32) for _ in range(6)]       # outliers mixed in
+    models, ok = gcr_ctx.refit(_cabi.E, sets)
+    assert models.shape == (len(sets), 10, 3, 3) and ok.shape == (len(sets), 10)
+    worst, exact_sets, best_worst = 0.0, 0, 0.0
+    thr = 0.75 / 1000.0
+    for s, mdl, k in zip(sets, models, ok):
+        want = oracle.refit_e(npts, s)
+        got = mdl[k.astype(bool)]
+        assert np.all(np.diff(k.astype(int)) <= 0)                    # valid slots first
+        for E in got:
+            assert abs(np.linalg.norm(E) - 1) < 1e-12 and E[2, 2] >= 0
+        if len(got) == len(want):
+            exact_sets += 1
+            worst = max(worst, _e_set_distance(got, want))
+        # what the LO step uses -- the best-scoring model of the set -- always agrees
+        if len(want):
+            sw = [oracle.score(O.E, O.MSAC, npts, E, thr)[0] for E in want]
+            sg = [oracle.score(O.E, O.MSAC, npts, E, thr)[0] for E in got]
+            if max(sw) > 10:
+                bw, bg = want[int(np.argmax(sw))], got[int(np.argmax(sg))]
+                best_worst = max(best_worst, np.abs(bw - bg).max())
+    assert exact_sets >= len(sets) - 2, exact_sets      # a near-double root may split differently in the two root finders
+    assert worst < RTOL_MODEL, worst
+    assert best_worst < RTOL_MODEL, best_worst
+    # weights by point
+    w = rng.uniform(0.05, 1.0, size=2048)
+    got, k = gcr_ctx.refit(_cabi.E, [sets[0], sets[-7]], weights=w, weight_mode=_cabi.WEIGHT_BY_POINT)
+    for i, s in enumerate((sets[0], sets[-7])):
+        want = oracle.refit_e(npts, s, w)
+        g = got[i][k[i].astype(bool)]
+        assert len(g) == len(want) and _e_set_distance(g, want) < RTOL_MODEL
+    # too small
+    got, k = gcr_ctx.refit(_cabi.E, [inl_idx[:4].astype(np.uint32)])
+    assert not k.any()
+
+
 def test_refit_too_small_sets_and_errors(gcr_ctx):
     pts, Hm, inl = synth.homography_pair(100, 0.0, seed=54)
     gcr_ctx.points_upload(pts)

@@ -116,3 +116,61 @@ def test_p3p_lambda_twist(oracle):
             best = min(best, np.abs(Q - P).max())
         hit += best < 1e-7
     assert hit == 200 and total > 300
+
+
+def test_dense_kernels_against_numpy(oracle):
+    """oracle/linalg.h: non-symmetric eigenvalues (Hessenberg + Francis QR), eigenvectors by inverse iteration, and the
+    Eigen-style column-pivoted Householder Q -- the stand-ins for EigenSolver / ColPivHouseholderQR in the Stewenius
+    solver -- against numpy.linalg.eig and LAPACK dgeqp3 (scipy)."""
+    from scipy.linalg import qr
+    rng = np.random.default_rng(0)
+    for t in range(100):
+        A = rng.standard_normal((10, 10))
+        ok, w = oracle.eigenvalues(A)
+        assert ok
+        assert np.allclose(np.sort_complex(w), np.sort_complex(np.linalg.eigvals(A)), atol=1e-9)
+        for lam in w[w.imag == 0].real:
+            v = oracle.eigenvector(A, lam)
+            assert abs(np.linalg.norm(v) - 1) < 1e-12 and np.linalg.norm(A @ v - lam * v) < 1e-9 * np.linalg.norm(A)
+    for t in range(50):
+        B = rng.standard_normal((30, 9))
+        A = B.T @ B
+        Q = oracle.colpiv_q(A)
+        Qs = qr(A, pivoting=True)[0]
+        assert np.allclose(Q.T @ Q, np.eye(9), atol=1e-12)
+        assert np.allclose(Q[:, 5:] @ Q[:, 5:].T, Qs[:, 5:] @ Qs[:, 5:].T, atol=1e-9)   # the same 4-D complement
+
+
+def test_refit_e_stewenius_against_numpy(oracle):
+    """EssentialMatrixEstimator::estimateModelNonminimal (Stewenius action matrix) against tests/np_five_point.stewenius:
+    same model count, every model within 1e-6 of a numpy one; recovers the ground truth from noisy inliers."""
+    from np_five_point import stewenius
+    pts, Fm, Em, K, inl = synth.epipolar_pair(2048, 0.5, seed=3)
+    npts = oracle.normalize_correspondences(pts, K, K)
+    rng = np.random.default_rng(1)
+    inl_idx = np.flatnonzero(inl)
+    En = Em / np.linalg.norm(Em)
+    En = -En if En[2, 2] < 0 else En
+    recovered = 0
+    for t in range(60):
+        n = 35 if t % 2 == 0 else int(rng.integers(6, 200))
+        pool = inl_idx if t % 4 else np.arange(len(pts))
+        s = rng.choice(pool, size=n, replace=False).astype(np.uint32)
+        w = None if t % 3 else rng.uniform(0.1, 1, len(pts))
+        got = oracle.refit_e(npts, s, w)
+        want = stewenius(npts[s], None if w is None else w[s])      # the solver reads weights[sample[i]]
+        assert len(got) == len(want) and 1 <= len(got) <= 10
+        for E in got:
+            assert abs(np.linalg.norm(E) - 1) < 1e-12 and E[2, 2] >= 0
+            assert min(np.abs(E - q).max() for q in want) < 1e-6
+        if t % 4 and n >= 35:
+            recovered += min(np.abs(E - En).max() for E in got) < 2e-2
+    assert recovered >= 20
+    assert len(oracle.refit_e(npts, inl_idx[:4].astype(np.uint32))) == 0       # below nonMinimalSampleSize()
+    # n == 5 takes the LU null space (stewenius.h:175-180): same models as the minimal solver up to normalisation
+    s5 = inl_idx[:5].astype(np.uint32)
+    a = oracle.refit_e(npts, s5)
+    b = oracle.solve_e5(npts, s5)
+    assert len(a) == len(b)
+    for E in a:
+        assert min(np.abs(_norm(E) - _norm(q)).max() for q in b) < 1e-6
