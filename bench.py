@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs]
 
 Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
 50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
@@ -26,7 +26,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "graph-cut-ransac_b200"))
 
-FLOP_PER_EVAL = {"h": 21.0, "f": 35.0}  # H-MSAC 21, Sampson-MSAC 35 (counted from the reference lines)
+# H-MSAC 21, Sampson-MSAC 35, Sampson-MAGSAC++ 43 flop per evaluation (counted from the reference lines)
+FLOP_PER_EVAL = {("h", "msac"): 21.0, ("f", "msac"): 35.0, ("e", "msac"): 35.0, ("e", "magsac"): 43.0,
+                 ("f", "magsac"): 43.0, ("h", "magsac"): 29.0}
 
 WORKLOADS = {
     # name: problem, n points, outlier ratio, threshold, samples per step, pairs per GPU
@@ -34,6 +36,16 @@ WORKLOADS = {
                 desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
     "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
                       desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 (configs[3])"),
+    # configs[2]: E, 5-point + MAGSAC++ on K-normalised correspondences (threshold / focal length), 85 % outliers
+    "e2k": dict(problem="e", scoring="magsac", n=2048, outliers=0.85, thr=0.75 / 1000.0, samples=65536, pairs=1,
+                desc="E 5-pt (Nister) + MAGSAC++, N=2048, 85% outliers, known K, thr 0.75 px / f, single pair (configs[2])"),
+    # full pipelines (adaptive stop, LO, graph-cut, IRLS, final fit) through pygcransac.find*: image pairs / s
+    "f4k_pairs": dict(problem="f", n=4096, outliers=0.5, thr=0.75, pairs=32, pipeline=True,
+                      desc="findFundamentalMatrix full pipeline (7-pt + MSAC, LO + graph-cut, conf 0.99), N=4096, 50% "
+                           "outliers, thr 0.75 px, distinct synthetic pairs one after the other (configs[1] pipeline)"),
+    "h2k_pairs": dict(problem="h", n=2048, outliers=0.3, thr=3.0, pairs=32, pipeline=True,
+                      desc="findHomography full pipeline (4-pt + MSAC, LO + graph-cut, conf 0.99), N=2048, 30% outliers, "
+                           "thr 3.0 px, distinct synthetic pairs one after the other"),
     # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL max all-reduce of the key
     "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps",
                         desc="single F problem, N=1048576 x K=1048576 7-pt samples sharded over the GPUs, MSAC, "
@@ -48,6 +60,11 @@ def make_points(wl, rank):
         seed = (0 if wl.get("shard") == "hyps" else 1000 * rank) + p + 1   # a sharded problem is the SAME on every rank
         if wl["problem"] == "f":
             pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])
+        elif wl["problem"] == "e":
+            # normalizeCorrespondences (py/gcransac_python.cpp:2519-2600): x' = K^-1 (x, y, 1)
+            px = synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0]
+            c, f = synth.SIZE / 2, synth.FOCAL
+            pts.append((px - c) / f)
         else:
             pts.append(synth.homography_pair(wl["n"], wl["outliers"], seed)[0])
     return np.ascontiguousarray(np.stack(pts))
@@ -116,19 +133,20 @@ _CPU_IMPL = {}
 
 def cpu_samples_per_core(wl):
     """Bounded CPU sample: ~1 s of single-core work per step (65536 7-point / 8192 4-point samples at N = 4096, scaled by N)."""
-    base = 65536 if wl["problem"] == "f" else 8192
+    base = 65536 if wl["problem"] == "f" else 8192                    # 5-point: ~10 models of FP64 Sturm solving per sample
     return max(8, int(base * 4096 / wl["n"]))
 
 
 def cpu_round_worker(args):
     """One CPU slice: `count` samples of the same workload through the reference scoring loop (or the port)."""
-    kind, problem, pts, seed, first, count, thr = args
+    kind, problem, pts, seed, first, count, thr, scoring = args
     if kind not in _CPU_IMPL:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
         _CPU_IMPL[kind] = (O, O.Ref() if kind == "reference" else O.Oracle())
     O, impl = _CPU_IMPL[kind]
-    score, idx, scored, _ = impl.round(O.F if problem == "f" else O.H, O.MSAC, pts, seed, first, count, thr)
+    score, idx, scored, _ = impl.round({"f": O.F, "h": O.H, "e": O.E}[problem], O.MAGSAC if scoring == "magsac" else O.MSAC,
+                                       pts, seed, first, count, thr)
     return scored, score, idx
 
 
@@ -153,7 +171,8 @@ class CpuArm:
     def run(self, samples_total, first=0):
         """Returns (evals, wall seconds, samples actually run)."""
         per = max(1, samples_total // (self.cores * 4))
-        jobs = [(self.kind, self.wl["problem"], self.pts0, 12345, first + c * per, per, self.wl["thr"])
+        jobs = [(self.kind, self.wl["problem"], self.pts0, 12345, first + c * per, per, self.wl["thr"],
+                 self.wl.get("scoring", "msac"))
                 for c in range(self.cores * 4)]
         t0 = time.perf_counter()
         out = self.pool.map(cpu_round_worker, jobs, chunksize=1)
@@ -188,11 +207,128 @@ def bench_reference(args, wl, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "samples_per_step": used},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
-                         "sample": "%d samples/step of the same pair (7-pt solve + MSAC over all %d points), sliced "
+                         "sample": "%d samples/step of the same pair (minimal solve + scoring over all %d points), sliced "
                                    "over the host cores" % (used, wl["n"])},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def _pairs_cpu_worker(args):
+    """One image pair through the reference's verbatim GCRANSAC<>::run on one host core."""
+    problem, pts, thr, weight, seed = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    if "ref" not in _CPU_IMPL:
+        _CPU_IMPL["ref"] = O.Ref()
+    eps = np.finfo(np.float64).eps if problem == "h" else 0.0
+    cs = np.array([(1024 + eps) / 4.0] * 4)
+    t0 = time.perf_counter()
+    out = _CPU_IMPL["ref"].run(O.H if problem == "h" else O.F, pts, cs, 4, thr, conf=0.99, spatial_weight=weight,
+                               max_iters=10000, min_iters=50, lo_number=50, seed=seed)
+    return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
+
+
+def bench_pairs(args, wl, rank, world):
+    """Full-pipeline workloads: image pairs / s through pygcransac.find* (batched GPU driver: adaptive stop, LO with the
+    reference's BK min-cut on the host, IRLS, final fit), one pair after the other per GPU; pairs shard over the ranks
+    with no collective.  The API takes host arrays, so every call includes its H2D / D2H: value == e2e.
+    --impl reference: the reference's verbatim GCRANSAC<>::run (oracle/_ref) on the same pairs, one pair per host core."""
+    weight = 0.975 if wl["problem"] == "h" else 0.0                  # the Python defaults (py/bindings.cpp:1147-1178)
+    n_pairs = wl["pairs"]
+    pts = make_points(wl, rank)
+    line = {"metric": "image pairs/s", "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "spatial_coherence_weight": weight}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        pool = mp.get_context("fork").Pool(cores)
+        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1) for p in range(n_pairs)]
+        for s in range(args.warmup):
+            pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
+        t0 = time.perf_counter()
+        outs = []
+        for s in range(args.steps):
+            outs += pool.map(_pairs_cpu_worker, jobs(args.warmup + s), chunksize=1)
+        wall = time.perf_counter() - t0
+        pool.close()
+        pool.join()
+        value = n_pairs * args.steps / wall
+        line.update({"impl": "reference", "value": value, "ms_per_step": 1e3 * wall / args.steps, "dtype": "f64",
+                     "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                      "sample": "%d pairs/step, one pair per host core; mean %.1f ms per pair on one core, "
+                                                "mean %d iterations" % (n_pairs, 1e3 * np.mean([o[2] for o in outs]),
+                                                                        np.mean([o[1] for o in outs]))},
+                     "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return
+    import torch
+    import torch.distributed as dist
+    import pygcransac
+    from pygcransac import _cabi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    find = pygcransac.findHomography if wl["problem"] == "h" else pygcransac.findFundamentalMatrix
+
+    def one_pass(s):
+        inl = its = 0
+        for p in range(n_pairs):
+            M, mask = find(pts[p], 1024, 1024, 1024, 1024, [], threshold=wl["thr"], conf=0.99,
+                           spatial_coherence_weight=weight, max_iters=10000, min_iters=50, use_sprt=False, sampler=1,
+                           neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank)
+            inl += int(mask.sum())
+            its += pygcransac.last_statistics["iteration_number"]
+        return inl, its
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        one_pass(s)
+    ctx = pygcransac._context(local_rank)
+    launches0 = ctx.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    inl = its = 0
+    for s in range(args.steps):
+        a, b = one_pass(args.warmup + s)
+        inl, its = inl + a, its + b
+    barrier()
+    wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    launches = ctx.launch_count() - launches0
+    total_pairs = n_pairs * args.steps
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = t.item()
+        w = torch.tensor([total_pairs, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        total_pairs, launches = w.tolist()
+    if rank == 0:
+        value = total_pairs / wall
+        line.update({"value": value, "ms_per_step": 1e3 * wall / args.steps, "dtype": "f32 ranking / f64 decisions",
+                     "clocks": clock_info, "gpu_launches": int(launches),
+                     "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": int(pts.nbytes),
+                             "d2h_bytes_per_step": int(n_pairs * (72 + wl["n"]))},
+                     "roofline": None})
+        line["config"].update({"mean_inliers": inl / (n_pairs * args.steps), "mean_iterations": its / (n_pairs * args.steps),
+                               "timing": "host wall clock around synchronous API calls (each returns host results), "
+                                         "max over ranks"})
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -217,6 +353,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if wl.get("pipeline"):
+        bench_pairs(args, wl, rank, world)
+        return
     if args.impl == "reference":
         bench_reference(args, wl, rank, world)
         return
@@ -231,7 +370,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    prob = _cabi.F if wl["problem"] == "f" else _cabi.H
+    prob = {"f": _cabi.F, "h": _cabi.H, "e": _cabi.E}[wl["problem"]]
+    scoring = _cabi.MAGSAC if wl.get("scoring") == "magsac" else _cabi.MSAC
+    mlen = 9
     flags = _cabi.SCORE_EXACT_COUNTS if args.exact_counts else 0
     ctx = _cabi.Context(local_rank)
     # a real (non-default) stream: handle 0 would mean "restore the context's own stream" to gcr_ctx_set_stream, and
@@ -263,9 +404,9 @@ def main():
     def one_round(i):
         if hyps_sharded:
             from pygcransac import sharded
-            return sharded.sharded_round(ctx, prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
+            return sharded.sharded_round(ctx, prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
                                          wl["thr"], flags, keys, best, 3 if wl["problem"] == "f" else 1, rank, world)
-        return ctx.round_device(prob, _cabi.MSAC, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
+        return ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
                                 flags, 0, keys.data_ptr(), best.data_ptr())
 
     def step_resident(i):
@@ -337,7 +478,7 @@ def main():
         evals, evals_e2e, launches, slot_evals = w.tolist()
 
     if rank == 0:
-        flop = FLOP_PER_EVAL[wl["problem"]]
+        flop = FLOP_PER_EVAL[(wl["problem"], wl.get("scoring", "msac"))]
         mhz, peak_src = fp32_peak_tflops(info["sm_count"])
         if mhz is None:
             mhz = info["sm_clock_khz"] / 1e3
