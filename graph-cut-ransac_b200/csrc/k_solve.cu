@@ -48,17 +48,9 @@ extern "C" int gcr_model_len(int problem) { return problem == GCR_PNP ? 12 : 9; 
 __device__ __forceinline__ void count_valid(unsigned long long *counters, uint32_t mine)
 {
 	const uint32_t active = __activemask();
-	// only the tail warp of a launch can be partial: per-thread atomics there, a shuffle reduction elsewhere
-	if (active == 0xffffffffu)
-	{
-		uint32_t total = mine;
-		for (int o = 16; o > 0; o >>= 1)
-			total += __shfl_xor_sync(0xffffffffu, total, o);
-		if ((threadIdx.x & 31) == 0 && total)
-			atomicAdd(&counters[0], (unsigned long long)total);
-	}
-	else if (mine)
-		atomicAdd(&counters[0], (unsigned long long)mine);
+	const uint32_t total = __reduce_add_sync(active, mine); // the converged lanes of this warp
+	if ((threadIdx.x & 31) == (uint32_t)(__ffs(active) - 1) && total)
+		atomicAdd(&counters[0], (unsigned long long)total);
 }
 
 // ---------------------------------------------------------------------------------------------------- H4 ----
@@ -87,35 +79,85 @@ __device__ bool h_valid_sample(const double *a, const double *b, const double *c
 	return true;
 }
 
-__global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts, int n,
-                                                  const GcrSampleSource src, int count,
-                                                  double *__restrict__ models, uint8_t *__restrict__ valid,
-                                                  unsigned long long *__restrict__ counters)
+// The oriented-constraint test rejects ~56 % of uniformly drawn 4-point samples (the "twisted quad" cases).  With one
+// sample per thread those lanes would idle through the whole elimination, so a CTA first tests H4_ROUNDS samples per
+// thread, packs the coordinates of the VALID ones into a shared-memory table (ballot + one shared atomic per warp; the
+// packing order does not matter, every result goes back to its own sample's slot), and then the threads solve the
+// packed samples: the FP64 work is issued for (nearly) full warps.
+#define H4_THREADS 128
+#define H4_ROUNDS 2
+#define H4_SAMPLES (H4_THREADS * H4_ROUNDS)
+__global__ void __launch_bounds__(H4_THREADS) k_solve_h4(const double *__restrict__ pts, int n,
+                                                         const GcrSampleSource src, int count,
+                                                         double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                         unsigned long long *__restrict__ counters)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
+	__shared__ double s_pt[16][H4_SAMPLES]; // coordinate e of packed sample q at [e][q]: conflict-free
+	__shared__ int s_owner[H4_SAMPLES];     // sample index of packed sample q
+	__shared__ int s_n;
+	const int tid = threadIdx.x;
 	const int pair = blockIdx.y;
 	const double *P = pts + (size_t)pair * n * 4;
-	uint32_t s[4];
-	gcr_load_sample<4>(src, pair, count, i, s);
-	double pt[4][4];
-#pragma unroll
-	for (int j = 0; j < 4; ++j)
+	if (tid == 0)
+		s_n = 0;
+	__syncthreads();
+#pragma unroll 1
+	for (int r = 0; r < H4_ROUNDS; ++r)
 	{
-		const double *p = P + (size_t)s[j] * 4;
-		pt[j][0] = p[0]; pt[j][1] = p[1]; pt[j][2] = p[2]; pt[j][3] = p[3];
+		const int i = blockIdx.x * H4_SAMPLES + r * H4_THREADS + tid;
+		double pt[4][4];
+		bool ok = false;
+		if (i < count)
+		{
+			uint32_t s[4];
+			gcr_load_sample<4>(src, pair, count, i, s);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+			{
+				const double *p = P + (size_t)s[j] * 4;
+				pt[j][0] = p[0]; pt[j][1] = p[1]; pt[j][2] = p[2]; pt[j][3] = p[3];
+			}
+			ok = h_valid_sample(pt[0], pt[1], pt[2], pt[3]);
+			if (!ok)
+			{
+				double *out = models + ((size_t)pair * count + i) * 9;
+#pragma unroll
+				for (int j = 0; j < 9; ++j)
+					out[j] = 0.0;
+				valid[(size_t)pair * count + i] = 0;
+			}
+		}
+		const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+		int base = 0;
+		if ((tid & 31) == 0 && ballot)
+			base = atomicAdd(&s_n, __popc(ballot));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (ok)
+		{
+			const int q = base + __popc(ballot & ((1u << (tid & 31)) - 1u));
+			s_owner[q] = i;
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+#pragma unroll
+				for (int c = 0; c < 4; ++c)
+					s_pt[4 * j + c][q] = pt[j][c];
+		}
 	}
-	double *out = models + ((size_t)pair * count + i) * 9;
-	bool ok = h_valid_sample(pt[0], pt[1], pt[2], pt[3]);
+	__syncthreads();
+	const int n_valid = s_n;
+#pragma unroll 1
+	for (int q = tid; q < n_valid; q += H4_THREADS)
+	{
+	const int owner = s_owner[q];
+	double *out = models + ((size_t)pair * count + owner) * 9;
+	bool ok = true;
 	double M[8][9];
-	if (ok)
 	{
 		int row = 0;
 #pragma unroll
 		for (int j = 0; j < 4; ++j)
 		{
-			const double x1 = pt[j][0], y1 = pt[j][1], x2 = pt[j][2], y2 = pt[j][3];
+			const double x1 = s_pt[4 * j][q], y1 = s_pt[4 * j + 1][q], x2 = s_pt[4 * j + 2][q], y2 = s_pt[4 * j + 3][q];
 			const double weight = 1.0;
 			const double mwx1 = -weight * x1, mwy1 = -weight * y1, wx2 = weight * x2, wy2 = weight * y2;
 			M[row][0] = mwx1; M[row][1] = mwy1; M[row][2] = -weight; M[row][3] = 0; M[row][4] = 0; M[row][5] = 0;
@@ -155,18 +197,13 @@ __global__ void __launch_bounds__(128) k_solve_h4(const double *__restrict__ pts
 		for (int j = 0; j < 8; ++j)
 			if (isnan(h[j]))
 				ok = false;
-		if (ok)
-		{
-			for (int j = 0; j < 8; ++j)
-				out[j] = h[j];
-			out[8] = 1.0;
-		}
+		for (int j = 0; j < 8; ++j)
+			out[j] = ok ? h[j] : 0.0;
+		out[8] = ok ? 1.0 : 0.0;
 	}
-	if (!ok)
-		for (int j = 0; j < 9; ++j)
-			out[j] = 0.0;
-	valid[(size_t)pair * count + i] = ok ? 1 : 0;
+	valid[(size_t)pair * count + owner] = ok ? 1 : 0;
 	count_valid(counters, ok ? 1u : 0u);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------- F7 ----
@@ -338,7 +375,7 @@ static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource 
 	switch (problem)
 	{
 	case GCR_H:
-		k_solve_h4<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
+		k_solve_h4<<<dim3((count + H4_SAMPLES - 1) / H4_SAMPLES, ctx->n_pairs), H4_THREADS, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_F:
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SMEM));

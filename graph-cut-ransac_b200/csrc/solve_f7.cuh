@@ -89,62 +89,92 @@ namespace gcr_f7
 	__device__ inline int solve(const PointFn &pt, const SmemMat &A, double *f1, double *f2, double *roots)
 	{
 		const double eps = 2.220446049250313e-16;
-#pragma unroll
-		for (int i = 0; i < 7; ++i)
+		// The full-pivot search of step k + 1 is folded into the elimination pass of step k (the updated entries are in
+		// registers when they are stored), one independent running maximum per COLUMN and a strict '>' merge of the
+		// columns in ascending order: the same element Eigen's column-major maxCoeff visitor picks, without the serial
+		// 196-element compare chain (and its 196 shared-memory reloads) of a separate search.
+		double biggest = 0.0;
+		int pr = 0, pc = 0;
 		{
-			const double x0 = pt(i, 0), y0 = pt(i, 1), x1 = pt(i, 2), y1 = pt(i, 3);
-			A(i, 0) = x1 * x0; A(i, 1) = x1 * y0; A(i, 2) = x1;
-			A(i, 3) = y1 * x0; A(i, 4) = y1 * y0; A(i, 5) = y1;
-			A(i, 6) = x0; A(i, 7) = y0; A(i, 8) = 1;
+			double colmax[9];
+			int colarg[9];
+#pragma unroll
+			for (int j = 0; j < 9; ++j) { colmax[j] = 0.0; colarg[j] = 0; }
+#pragma unroll
+			for (int i = 0; i < 7; ++i)
+			{
+				const double x0 = pt(i, 0), y0 = pt(i, 1), x1 = pt(i, 2), y1 = pt(i, 3);
+				double row[9];
+				row[0] = x1 * x0; row[1] = x1 * y0; row[2] = x1;
+				row[3] = y1 * x0; row[4] = y1 * y0; row[5] = y1;
+				row[6] = x0; row[7] = y0; row[8] = 1;
+#pragma unroll
+				for (int j = 0; j < 9; ++j)
+				{
+					A(i, j) = row[j];
+					const double a = fabs(row[j]);
+					if (a > colmax[j]) { colmax[j] = a; colarg[j] = i; }
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 9; ++j)
+				if (colmax[j] > biggest) { biggest = colmax[j]; pr = colarg[j]; pc = j; }
 		}
 		unsigned long long colperm = 0x876543210ull; // nibble j = original column now at position j
 		double maxpivot = 0.0;
-		int nonzero = 7;
+		double diag[7];
 #pragma unroll
 		for (int k = 0; k < 7; ++k)
 		{
-			if (k < nonzero)
+			if (biggest == 0.0) // FullPivLU stops here: fewer than 7 non-zero pivots, dimensionOfKernel() != 2
+				return 0;
+			if (biggest > maxpivot) maxpivot = biggest;
+			// rows k <-> pr on the columns still in play (the L part is never read: kernel() only needs U and the
+			// column permutation); unconditional, a swap with itself is harmless
 			{
-				int pr = k, pc = k;
-				double biggest = 0.0;
+				double rk[9], rp[9];
 #pragma unroll
-				for (int j = k; j < 9; ++j) // column-major search like Eigen's maxCoeff on a column-major block
+				for (int j = k; j < 9; ++j) { rk[j] = A(k, j); rp[j] = A(pr, j); }
 #pragma unroll
-					for (int i = k; i < 7; ++i)
-					{
-						const double a = fabs(A(i, j));
-						if (a > biggest) { biggest = a; pr = i; pc = j; }
-					}
-				if (biggest == 0.0)
-					nonzero = k;
-				else
+				for (int j = k; j < 9; ++j) { A(pr, j) = rk[j]; }
+#pragma unroll
+				for (int j = k; j < 9; ++j) { A(k, j) = rp[j]; }
+			}
+			// columns k <-> pc on every row (rows < k hold U)
+			double fac[7];
+			{
+				double ck[7], cp[7];
+#pragma unroll
+				for (int i = 0; i < 7; ++i) { ck[i] = A(i, k); cp[i] = A(i, pc); }
+#pragma unroll
+				for (int i = 0; i < 7; ++i) { A(i, pc) = ck[i]; }
+#pragma unroll
+				for (int i = 0; i <= k; ++i) { A(i, k) = cp[i]; } // below the diagonal: L, never read again
+				const unsigned long long a = (colperm >> (4 * k)) & 15ull, b = (colperm >> (4 * pc)) & 15ull;
+				colperm &= ~((15ull << (4 * k)) | (15ull << (4 * pc)));
+				colperm |= (b << (4 * k)) | (a << (4 * pc));
+				diag[k] = cp[k]; // the pivot
+#pragma unroll
+				for (int i = k + 1; i < 7; ++i)
+					fac[i] = cp[i] / cp[k];
+			}
+			biggest = 0.0;
+			pr = pc = k + 1;
+#pragma unroll
+			for (int j = k + 1; j < 9; ++j)
+			{
+				const double r = A(k, j);
+				double cm = 0.0;
+				int ci = k + 1;
+#pragma unroll
+				for (int i = k + 1; i < 7; ++i)
 				{
-					if (biggest > maxpivot) maxpivot = biggest;
-					if (pr != k)
-#pragma unroll
-						for (int j = 0; j < 9; ++j) { const double t = A(k, j); A(k, j) = A(pr, j); A(pr, j) = t; }
-					if (pc != k)
-					{
-#pragma unroll
-						for (int i = 0; i < 7; ++i) { const double t = A(i, k); A(i, k) = A(i, pc); A(i, pc) = t; }
-						const unsigned long long a = (colperm >> (4 * k)) & 15ull, b = (colperm >> (4 * pc)) & 15ull;
-						colperm &= ~((15ull << (4 * k)) | (15ull << (4 * pc)));
-						colperm |= (b << (4 * k)) | (a << (4 * pc));
-					}
-					const double piv = A(k, k);
-					double rowk[9];
-#pragma unroll
-					for (int j = k + 1; j < 9; ++j) rowk[j] = A(k, j);
-#pragma unroll
-					for (int i = k + 1; i < 7; ++i)
-					{
-						const double f = A(i, k) / piv;
-						A(i, k) = f;
-#pragma unroll
-						for (int j = k + 1; j < 9; ++j)
-							A(i, j) -= f * rowk[j];
-					}
+					const double v = A(i, j) - fac[i] * r;
+					A(i, j) = v;
+					const double a = fabs(v);
+					if (a > cm) { cm = a; ci = i; }
 				}
+				if (cm > biggest) { biggest = cm; pr = ci; pc = j; }
 			}
 		}
 		// dimensionOfKernel() == 2  <=>  all 7 pivots above eps * 7 * maxpivot (:161-163)
@@ -152,7 +182,7 @@ namespace gcr_f7
 		int rank = 0;
 #pragma unroll
 		for (int k = 0; k < 7; ++k)
-			if (k < nonzero && fabs(A(k, k)) > premult) ++rank;
+			if (fabs(diag[k]) > premult) ++rank;
 		if (rank != 7)
 			return 0;
 		double x[2][7];
@@ -166,7 +196,7 @@ namespace gcr_f7
 #pragma unroll
 				for (int j = i + 1; j < 7; ++j)
 					s -= A(i, j) * x[c][j];
-				x[c][i] = s / A(i, i);
+				x[c][i] = s / diag[i];
 			}
 		}
 		// the matrix is dead from here on: its first two rows become f1 / f2 (un-permuted)
