@@ -81,6 +81,10 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	}
 	if (ctx->h_pinned)
 		cudaFreeHost(ctx->h_pinned);
+	if (ctx->h_stage)
+		cudaFreeHost(ctx->h_stage);
+	for (auto &b : ctx->blocks)
+		cudaFree(b.p);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 	return GCR_OK;
@@ -116,26 +120,84 @@ extern "C" gcr_status gcr_device_info(gcr_ctx *ctx, int *sm_count, int *sm_clock
 
 extern "C" uint64_t gcr_launch_count(const gcr_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+static size_t bucket_of(size_t bytes)
+{
+	size_t b = 256;
+	while (b < bytes && b < ((size_t)1 << 20))
+		b <<= 1;
+	if (b >= bytes)
+		return b;
+	return (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1); // above 1 MiB: MiB granules
+}
 extern "C" gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out)
 {
 	if (!ctx || !d_out)
 		return GCR_ERR_ARG;
+	const size_t cap = bucket_of(bytes ? bytes : 1);
+	for (auto &b : ctx->blocks)
+		if (!b.used && b.cap == cap)
+		{
+			b.used = true;
+			*d_out = b.p;
+			return GCR_OK;
+		}
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-	GCR_CHECK_CUDA(ctx, cudaMalloc(d_out, bytes ? bytes : 1));
+	cudaError_t e = cudaMalloc(d_out, cap);
+	if (e != cudaSuccess)
+	{
+		// out of memory: give the cached free blocks back and try once more
+		cudaGetLastError();
+		cudaStreamSynchronize(ctx->stream);
+		for (size_t i = 0; i < ctx->blocks.size();)
+			if (!ctx->blocks[i].used)
+			{
+				cudaFree(ctx->blocks[i].p);
+				ctx->blocks[i] = ctx->blocks.back();
+				ctx->blocks.pop_back();
+			}
+			else
+				++i;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(d_out, cap));
+	}
+	ctx->blocks.push_back({*d_out, cap, true});
 	return GCR_OK;
 }
 extern "C" gcr_status gcr_free(gcr_ctx *ctx, void *d_ptr)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
-	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	GCR_CHECK_CUDA(ctx, cudaFree(d_ptr));
+	if (!d_ptr)
+		return GCR_OK;
+	for (auto &b : ctx->blocks)
+		if (b.p == d_ptr)
+		{
+			b.used = false; // kept for the next gcr_malloc of this size; released by gcr_ctx_destroy
+			return GCR_OK;
+		}
+	GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_free: pointer was not allocated by gcr_malloc on this context");
+}
+static gcr_status ensure_stage(gcr_ctx *ctx)
+{
+	if (ctx->h_stage)
+		return GCR_OK;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	GCR_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_stage, gcr_ctx::STAGE_BYTES));
 	return GCR_OK;
 }
 extern "C" gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
+	if (bytes == 0)
+		return GCR_OK;
+	if (bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	{
+		// every staged copy ends with a synchronise, so the bounce buffer is never in flight here
+		memcpy(ctx->h_stage, h_src, bytes);
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return GCR_OK;
+	}
 	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return GCR_OK;
@@ -144,6 +206,15 @@ extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_sr
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
+	if (bytes == 0)
+		return GCR_OK;
+	if (bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	{
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		memcpy(h_dst, ctx->h_stage, bytes);
+		return GCR_OK;
+	}
 	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return GCR_OK;
@@ -488,7 +559,18 @@ extern "C" gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, in
 		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts64_owned, bytes));
 		ctx->pts64_capacity = bytes;
 	}
-	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	cudaPointerAttributes attr;
+	const bool pinned = cudaPointerGetAttributes(&attr, h_points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned && bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	{
+		// pageable caller memory: bounce through the context's pinned buffer (a pinned source is copied asynchronously)
+		memcpy(ctx->h_stage, h_points, bytes);
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the bounce buffer is free again on return
+	}
+	else
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	ctx->d_pts64 = ctx->d_pts64_owned;
 	ctx->n = n;
 	ctx->cols = cols;

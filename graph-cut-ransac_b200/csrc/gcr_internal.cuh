@@ -3,6 +3,7 @@
 // (bit parity with the CPU build, which has no FMA contraction), and the FP32 hot loops state their FMAs
 // explicitly (fmaf / __ffma2_rn).
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -71,6 +72,17 @@ struct gcr_ctx
 	size_t scratch_capacity = 0;
 	void *h_pinned = nullptr;
 	size_t pinned_capacity = 0;
+
+	// gcr_malloc / gcr_free: size-bucketed cache of device blocks owned by this context.  cudaMalloc / cudaFree
+	// synchronise the whole device and serialise every host thread, so a driver that allocates its ~20 buffers per
+	// image pair would stall all other contexts; freed blocks are kept and handed out again (reuse is ordered by
+	// this context's stream, the only stream the block was used on).
+	struct CachedBlock { void *p; size_t cap; bool used; };
+	std::vector<CachedBlock> blocks;
+	// small host <-> device copies go through this pinned bounce buffer (pageable cudaMemcpyAsync takes the driver's
+	// global staging path); separate from h_pinned, which kernels' result read-backs use
+	void *h_stage = nullptr;
+	static const size_t STAGE_BYTES = 1 << 20;
 
 	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu
 	int score_variant = -1;    // -1 auto; else forces a kernel variant (bench / tests)

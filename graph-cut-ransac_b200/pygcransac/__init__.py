@@ -16,6 +16,7 @@ not part of this path.  `neighborhood` must be 0 (grid) when `spatial_coherence_
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -68,11 +69,17 @@ def _load_driver():
 
 
 def _context(device=0):
-    if device not in _contexts:
-        _contexts[device] = _cabi.Context(device)
-    return _contexts[device]
+    """One gcr_ctx (stream + workspaces) per (device, calling thread): independent image pairs can be processed from
+    several host threads at once -- ctypes drops the GIL during the driver call, the GPU overlaps their small kernels
+    and copies (the reference's counterpart is one problem per host core)."""
+    key = (device, threading.get_ident())
+    ctx = _contexts.get(key)
+    if ctx is None:
+        ctx = _contexts[key] = _cabi.Context(device)
+    return ctx
 
 
+_tls = threading.local()  # _tls.last_statistics: the calling thread's most recent RunStats
 last_statistics = None  # RunStats of the most recent call (the reference fills utils::RANSACStatistics; not returned by its API either)
 
 
@@ -115,7 +122,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
                                        model.ctypes.data, mask.ctypes.data, C.byref(stats))
     if n_inl < 0:
         raise _cabi.GcrError("gcr_find_model failed (%d): %s" % (n_inl, ctx.lib.gcr_last_error(ctx.h).decode()))
-    last_statistics = stats.as_dict()
+    last_statistics = _tls.last_statistics = stats.as_dict()
     if n_inl == 0:
         return None, mask.astype(bool)                                      # bindings.cpp:973-975
     return model.reshape(3, 3), mask.astype(bool)
