@@ -18,6 +18,7 @@
 
 #include "solve_f7.cuh"
 #include "solve_e5.cuh"
+#include "solve_e5_group.cuh"
 #include "solve_p3p.cuh"
 
 extern "C" int gcr_max_models(int problem)
@@ -265,49 +266,57 @@ __global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__rest
 }
 
 // ---------------------------------------------------------------------------------------------------- E5 ----
-// One thread per sample; the solver's working set (10 x 20 constraint matrix, Sturm chain, interval stack: ~6 KB) is
-// thread-local memory served from L1/L2.  O(K) work next to the O(K N) scoring.
-struct SamplePoints5
+// Ten lanes per sample, three samples per warp, the solver's working set (10 x 20 constraint matrix, Sturm chain,
+// interval stack: ~5 KB per sample) in shared memory: solve_e5_group.cuh.  Lanes 30 / 31 of every warp idle.
+#define E5_THREADS 128
+#define E5_SAMPLES_PER_CTA (3 * E5_THREADS / 32)
+#define E5_SMEM (E5_SAMPLES_PER_CTA * gcr_e5g::SAMPLE_DOUBLES * sizeof(double))
+
+struct GroupSync
 {
-	const double *P;
-	const uint32_t *s;
-	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 4 + c]; }
+	unsigned mask;      // the ten lanes of this group
+	unsigned warp_mask; // every lane of the warp that runs a group
+	int shift;          // first lane of the group
+	__device__ __forceinline__ void operator()() const { __syncwarp(mask); }
+	__device__ __forceinline__ bool any(bool x) const { return __any_sync(warp_mask, x) != 0; }
+	__device__ __forceinline__ unsigned ballot(bool x) const { return (__ballot_sync(mask, x) >> shift) & 0x3ffu; }
 };
 
-__global__ void __launch_bounds__(64) k_solve_e5(const double *__restrict__ pts, int n,
-                                                 const GcrSampleSource src, int count,
-                                                 double *__restrict__ models, uint8_t *__restrict__ valid,
-                                                 unsigned long long *__restrict__ counters)
+__global__ void __launch_bounds__(E5_THREADS) k_solve_e5(const double *__restrict__ pts, int n,
+                                                         const GcrSampleSource src, int count,
+                                                         double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                         unsigned long long *__restrict__ counters)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int pair = blockIdx.y;
-	uint32_t n_ok = 0;
-	if (i < count)
-	{
-		uint32_t sidx[5];
-		gcr_load_sample<5>(src, pair, count, i, sidx);
-		const SamplePoints5 pt{pts + (size_t)pair * n * 4, sidx};
-		double *out = models + ((size_t)pair * count + i) * 90;
-		uint8_t *v = valid + ((size_t)pair * count + i) * 10;
-		const int nm = gcr_e5::solve(pt, out); // models land in slots 0..nm-1 of the output row
-		for (int mdl = 0; mdl < 10; ++mdl)
-		{
-			bool ok = mdl < nm;
-			if (ok)
-				ok = gcr_f7::orientation_valid(out + 9 * mdl, pt, 5); // essential_estimator.h:165-171, 338-401
-			if (!ok)
-				for (int j = 0; j < 9; ++j)
-					out[9 * mdl + j] = 0.0;
-			v[mdl] = ok ? 1 : 0;
-			n_ok += ok ? 1u : 0u;
-		}
-	}
+	extern __shared__ double e5_smem[];
 	__shared__ uint32_t cnt;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int g = lane / 10, li = lane - 10 * g;
+	const int pair = blockIdx.y;
+	const int slot = warp * 3 + g;
+	const int i = blockIdx.x * E5_SAMPLES_PER_CTA + slot;
 	if (threadIdx.x == 0)
 		cnt = 0;
 	__syncthreads();
-	if (n_ok)
-		atomicAdd(&cnt, n_ok);
+	const unsigned warp_mask = __ballot_sync(0xffffffffu, g < 3 && i < count);
+	if (g < 3 && i < count)
+	{
+		double *S = e5_smem + (size_t)slot * gcr_e5g::SAMPLE_DOUBLES;
+		const GroupSync sync{0x3ffu << (10 * g), warp_mask, 10 * g};
+		uint32_t sidx[5];
+		gcr_load_sample<5>(src, pair, count, i, sidx); // every lane draws the same five indices
+		if (li < 5)
+		{
+			const double *p = pts + ((size_t)pair * n + sidx[li]) * 4;
+			double *d = S + gcr_e5g::OFF_PT + 4 * li;
+			d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+		}
+		sync();
+		double *out = models + ((size_t)pair * count + i) * 90;
+		uint8_t *v = valid + ((size_t)pair * count + i) * 10;
+		const int n_ok = gcr_e5g::solve_group(li, S, sync, out, v);
+		if (li == 0 && n_ok)
+			atomicAdd(&cnt, (uint32_t)n_ok);
+	}
 	__syncthreads();
 	if (threadIdx.x == 0 && cnt)
 		atomicAdd(&counters[0], (unsigned long long)cnt);
@@ -383,8 +392,9 @@ static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource 
 		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_E:
-		k_solve_e5<<<dim3((count + 63) / 64, ctx->n_pairs), 64, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models,
-		                                                                         d_valid, ctx->d_counters);
+		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_e5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E5_SMEM));
+		k_solve_e5<<<dim3((count + E5_SAMPLES_PER_CTA - 1) / E5_SAMPLES_PER_CTA, ctx->n_pairs), E5_THREADS, E5_SMEM, ctx->stream>>>(
+		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_PNP:
 		k_solve_p3p<<<grid, 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
