@@ -370,6 +370,81 @@ __global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pt
 		atomicAdd(&counters[0], (unsigned long long)cnt);
 }
 
+// ------------------------------------------------------------------------------------------ plane + parallax ----
+// FundamentalMatrixPlaneParallaxSolver::estimateModel (estimators/solver_fundamental_matrix_plane_and_parallax.h:109-160)
+// + the oriented epipolar constraint on the two sample points (fundamental_estimator.h:161-184): DEGENSAC's inner
+// minimal solver.  One sample (2 points) per thread; same statement order as oracle/gcr_oracle_f.cpp.
+struct PlaneHomography { double h[9]; };
+
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *c)
+{
+	c[0] = a[1] * b[2] - a[2] * b[1];
+	c[1] = a[2] * b[0] - a[0] * b[2];
+	c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__global__ void __launch_bounds__(128) k_solve_fpp(const double *__restrict__ pts, int n,
+                                                   const uint32_t *__restrict__ samples, int count, const PlaneHomography H,
+                                                   double *__restrict__ models, uint8_t *__restrict__ valid,
+                                                   unsigned long long *__restrict__ counters)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int pair = blockIdx.y;
+	if (i >= count)
+		return;
+	const uint32_t *sidx = samples + ((size_t)pair * count + i) * 2;
+	const SamplePoints pt{pts + (size_t)pair * n * 4, sidx};
+	double line[2][3];
+#pragma unroll
+	for (int q = 0; q < 2; ++q)
+	{
+		const double src[3] = {pt(q, 0), pt(q, 1), 1.0}, dst[3] = {pt(q, 2), pt(q, 3), 1.0};
+		double proj[3];
+#pragma unroll
+		for (int r = 0; r < 3; ++r)
+			proj[r] = H.h[3 * r] * src[0] + H.h[3 * r + 1] * src[1] + H.h[3 * r + 2] * src[2];
+		cross3(proj, dst, line[q]);
+	}
+	double e[3], F[9];
+	cross3(line[0], line[1], e);
+	bool ok = !(fabs(e[2]) < 2.220446049250313e-16);
+	if (ok)
+	{
+		const double ex[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+#pragma unroll
+		for (int r = 0; r < 3; ++r)
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+				F[3 * r + c] = ex[3 * r] * H.h[c] + ex[3 * r + 1] * H.h[3 + c] + ex[3 * r + 2] * H.h[6 + c];
+		ok = gcr_f7::orientation_valid(F, pt, 2);
+	}
+	double *out = models + ((size_t)pair * count + i) * 9;
+#pragma unroll
+	for (int j = 0; j < 9; ++j)
+		out[j] = ok ? F[j] : 0.0;
+	valid[(size_t)pair * count + i] = ok ? 1 : 0;
+	count_valid(counters, ok ? 1u : 0u);
+}
+
+extern "C" gcr_status gcr_solve_plane_parallax(gcr_ctx *ctx, const uint32_t *d_samples, int count, const double *h_homography,
+                                               double *d_models, uint8_t *d_valid)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_solve_plane_parallax: no points uploaded");
+	if (ctx->cols != 4 || !d_samples || !h_homography || !d_models || !d_valid || count <= 0)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_plane_parallax: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	PlaneHomography H;
+	for (int j = 0; j < 9; ++j)
+		H.h[j] = h_homography[j];
+	k_solve_fpp<<<dim3((count + 127) / 128, ctx->n_pairs), 128, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, d_samples, count, H,
+	                                                                             d_models, d_valid, ctx->d_counters);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
 static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource &src, int count, double *d_models,
                                uint8_t *d_valid)
 {

@@ -37,6 +37,15 @@ namespace
 	}
 
 	// fundamental_estimator.h:225-253
+	// homography_estimator.h:181-199
+	double sq_homography_transfer(const double *s, const double *H)
+	{
+		const double x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
+		const double t1 = H[0] * x1 + H[1] * y1 + H[2], t2 = H[3] * x1 + H[4] * y1 + H[5], t3 = H[6] * x1 + H[7] * y1 + H[8];
+		const double d1 = x2 - (t1 / t3), d2 = y2 - (t2 / t3);
+		return d1 * d1 + d2 * d2;
+	}
+
 	double sq_symmetric_epipolar(const double *s, const double *F)
 	{
 		const double x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
@@ -96,6 +105,13 @@ namespace
 		double T; // squared truncated threshold (GCRANSAC.h:253-254)
 		double truncated_threshold;
 		std::string error;
+		// DEGENSAC (fundamental_estimator.h:341-572).  The inner run is this same driver with the plane-and-parallax
+		// minimal solver (variant 1: 2-point samples + pp_H), on the points the outer run already uploaded.
+		int variant = 0;
+		bool nested = false;
+		double pp_H[9] = {0};
+		double f_min_ratio = 0.5; // minimum_inlier_ratio_in_validity_check (:91); the inner estimator is built with 0.0 (:540)
+		std::vector<uint32_t> h_samples;
 
 		// main-loop batch
 		int B = 0;
@@ -173,8 +189,12 @@ namespace
 		}
 
 		// ---- isValidModel ----
-		bool is_valid_model(const double *model, const std::vector<uint32_t> &inliers) const
+		// `model` may be replaced (DEGENSAC, F only): then `updated` is set and the caller re-scores it (GCRANSAC.h:446-454)
+		bool is_valid_model(double *model, const std::vector<uint32_t> &inliers, const uint32_t *minimal_sample, bool &updated,
+		                    bool &failed)
 		{
+			updated = false;
+			failed = false;
 			if (problem == GCR_H)
 			{
 				// homography_estimator.h:326-342: |det H| >= 1e-2
@@ -183,17 +203,160 @@ namespace
 				                   H[2] * (H[3] * H[7] - H[4] * H[6]);
 				return !(std::fabs(det) < 1e-2);
 			}
-			// fundamental_estimator.h:287-318 (symmetric-epipolar ratio test; DEGENSAC stays with the host estimator),
-			// essential_estimator.h:279-305 (ratio 0.1).  `const size_t x = MAX(size_t, double)`: truncated.
-			const double a = (double)m, b = inliers.size() * (problem == GCR_E ? 0.1 : 0.5);
+			// fundamental_estimator.h:287-318 (symmetric-epipolar ratio test), essential_estimator.h:279-305 (ratio 0.1).
+			// `const size_t x = MAX(size_t, double)`: truncated.
+			const double a = (double)m, b = inliers.size() * (problem == GCR_E ? 0.1 : f_min_ratio);
 			const size_t minimum_inlier_number = (size_t)(a > b ? a : b);
 			const double squared_threshold = truncated_threshold * truncated_threshold;
 			size_t inlier_number = 0;
+			bool passed = false;
 			for (uint32_t i : inliers)
 				if (sq_symmetric_epipolar(pts + 4 * (size_t)i, model) < squared_threshold)
 					if (++inlier_number >= minimum_inlier_number)
-						return true;
-			return false;
+					{
+						passed = true;
+						break;
+					}
+			if (!passed)
+				return false;
+			if (problem == GCR_F && variant == 0 && S.use_degensac && minimal_sample) // :325-333
+				return apply_degensac(model, inliers, minimal_sample, updated, failed);
+			return true;
+		}
+
+		// ---- applyDegensac (fundamental_estimator.h:341-572) ----
+		// H-degenerate sample test on the host (seven points, five triplets); when it fires: the plane homography is
+		// refitted on its inliers among the model's inliers (GPU, K6) and an inner GC-RANSAC with the plane-and-parallax
+		// solver runs as a nested driver on this context.  The reference seeds the inner sampler from random_device
+		// (:553); here inner run r draws from the counter-based streams of seed + r * 0xD1B54A32D192ED03.
+		bool apply_degensac(double *model, const std::vector<uint32_t> &inliers, const uint32_t *sample, bool &updated,
+		                    bool &failed)
+		{
+			static const int triplets[15] = {0, 1, 2, 3, 4, 5, 0, 1, 6, 3, 4, 6, 2, 5, 6};
+			const double squared_homography_threshold = 2.0 * 2.0; // homography_threshold_ = 2.0 (:93)
+			const double *F = model;
+			// epipole in the second image: e^T F = 0 (the reference takes JacobiSVD's U.col(2), :365-372).  F comes from
+			// the 7-point solver, rank 2 up to the cubic's polish: e = the largest cross product of two columns of F.
+			double e[3] = {0, 0, 0}, best = -1.0;
+			for (int c0 = 0; c0 < 3; ++c0)
+				for (int c1 = c0 + 1; c1 < 3; ++c1)
+				{
+					const double u[3] = {F[c0], F[3 + c0], F[6 + c0]}, v[3] = {F[c1], F[3 + c1], F[6 + c1]};
+					const double w[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+					const double nn = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+					if (nn > best) { best = nn; e[0] = w[0]; e[1] = w[1]; e[2] = w[2]; }
+				}
+			e[0] /= e[2]; e[1] /= e[2]; e[2] = 1.0;
+			auto cross = [](const double *x, const double *y, double *z) {
+				z[0] = x[1] * y[2] - x[2] * y[1]; z[1] = x[2] * y[0] - x[0] * y[2]; z[2] = x[0] * y[1] - x[1] * y[0];
+			};
+			const double ex[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+			double A[9];
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					A[3 * r + c] = ex[3 * r] * F[c] + ex[3 * r + 1] * F[3 + c] + ex[3 * r + 2] * F[6 + c];
+			bool h_degenerate = false;
+			double H[9];
+			for (int t = 0; t < 5 && !h_degenerate; ++t)
+			{
+				uint32_t idx[3];
+				double p1[3][3], b[3];
+				for (int q = 0; q < 3; ++q)
+				{
+					idx[q] = sample[triplets[3 * t + q]];
+					const double *p = pts + 4 * (size_t)idx[q];
+					p1[q][0] = p[0]; p1[q][1] = p[1]; p1[q][2] = 1;
+					const double p2[3] = {p[2], p[3], 1};
+					double pxe[3], Ap[3], pxAp[3];
+					cross(p2, e, pxe);
+					for (int r = 0; r < 3; ++r)
+						Ap[r] = A[3 * r] * p1[q][0] + A[3 * r + 1] * p1[q][1] + A[3 * r + 2] * p1[q][2];
+					cross(p2, Ap, pxAp);
+					b[q] = (pxAp[0] * pxe[0] + pxAp[1] * pxe[1] + pxAp[2] * pxe[2]) / (pxe[0] * pxe[0] + pxe[1] * pxe[1] + pxe[2] * pxe[2]);
+				}
+				// (M^-1 b) by cofactors, M = rows (x, y, 1) of the triplet in the first image
+				const double *M0 = p1[0], *M1 = p1[1], *M2 = p1[2];
+				const double c00 = M1[1] * M2[2] - M1[2] * M2[1], c01 = M1[2] * M2[0] - M1[0] * M2[2], c02 = M1[0] * M2[1] - M1[1] * M2[0];
+				const double det = M0[0] * c00 + M0[1] * c01 + M0[2] * c02;
+				const double id = 1.0 / det;
+				const double Mi[9] = {c00 * id, (M0[2] * M2[1] - M0[1] * M2[2]) * id, (M0[1] * M1[2] - M0[2] * M1[1]) * id,
+				                      c01 * id, (M0[0] * M2[2] - M0[2] * M2[0]) * id, (M0[2] * M1[0] - M0[0] * M1[2]) * id,
+				                      c02 * id, (M0[1] * M2[0] - M0[0] * M2[1]) * id, (M0[0] * M1[1] - M0[1] * M1[0]) * id};
+				double Mb[3];
+				for (int r = 0; r < 3; ++r)
+					Mb[r] = Mi[3 * r] * b[0] + Mi[3 * r + 1] * b[1] + Mi[3 * r + 2] * b[2];
+				for (int r = 0; r < 3; ++r)
+					for (int c = 0; c < 3; ++c)
+						H[3 * r + c] = A[3 * r + c] - e[r] * Mb[c];
+				int inlier_number = 3;
+				for (int i = 0; i < 7; ++i)
+				{
+					const uint32_t id7 = sample[i];
+					if (id7 == idx[0] || id7 == idx[1] || id7 == idx[2])
+						continue;
+					if (sq_homography_transfer(pts + 4 * (size_t)id7, H) < squared_homography_threshold)
+						++inlier_number;
+				}
+				if (inlier_number >= 5)
+					h_degenerate = true;
+			}
+			if (!h_degenerate)
+				return true; // :571
+			std::vector<uint32_t> h_inliers; // :501-509
+			for (uint32_t i : inliers)
+				if (sq_homography_transfer(pts + 4 * (size_t)i, H) < squared_homography_threshold)
+					h_inliers.push_back(i);
+			if (h_inliers.size() < 4) // homography_estimator.nonMinimalSampleSize()
+				return false;
+			std::vector<double> models;
+			std::vector<uint8_t> ok;
+			{
+				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)h_inliers.size());
+				if (!refit(h_inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, false, GCR_H))
+				{
+					failed = true;
+					return false;
+				}
+				if (!ok[0]) // :530-531
+					return false;
+			}
+			++st.degensac_runs;
+			Driver inner;
+			inner.ctx = ctx;
+			inner.problem = GCR_F;
+			inner.variant = 1;
+			inner.nested = true;
+			inner.f_min_ratio = 0.0;
+			memcpy(inner.pp_H, models.data(), sizeof(inner.pp_H));
+			inner.n = n;
+			inner.pts = pts;
+			gcr_run_settings_default(&inner.S); // a default-constructed GCRANSAC<> (settings.h:63-84) + :547-551
+			inner.S.threshold = truncated_threshold;
+			inner.S.spatial_coherence_weight = 0;
+			inner.S.confidence = 0.99;
+			inner.S.use_degensac = 0;
+			inner.S.seed = S.seed + st.degensac_runs * 0xD1B54A32D192ED03ull;
+			inner.S.batch = S.batch;
+			double inner_model[9];
+			std::vector<uint8_t> inner_mask(n);
+			const int r = inner.run(inner_model, inner_mask.data());
+			st.gpu_batches += inner.st.gpu_batches;
+			st.exact_rescores += inner.st.exact_rescores;
+			st.models_scored += inner.st.models_scored;
+			st.graph_cut_seconds += inner.st.graph_cut_seconds;
+			if (r < 0)
+			{
+				error = inner.error;
+				failed = true;
+				return false;
+			}
+			if ((size_t)r > inliers.size()) // :561-567
+			{
+				updated = true;
+				memcpy(model, inner_model, sizeof(inner_model));
+				++st.degensac_updates;
+			}
+			return true;
 		}
 
 		// ---- one GPU batch of the main loop: samples [first, first + B) -> models, valid flags, FP32 scores, exact counts ----
@@ -205,7 +368,12 @@ namespace
 				return fail("gcr_malloc");
 			if (gcr_sample(ctx, GCR_UNIFORM, m, first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_sample");
-			if (gcr_solve_minimal(ctx, problem, d_samples.as<uint32_t>(), B, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
+			if (variant == 1)
+			{
+				if (gcr_solve_plane_parallax(ctx, d_samples.as<uint32_t>(), B, pp_H, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
+					return fail("gcr_solve_plane_parallax");
+			}
+			else if (gcr_solve_minimal(ctx, problem, d_samples.as<uint32_t>(), B, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_solve_minimal");
 			if (gcr_score(ctx, problem, GCR_MSAC, d_models.as<double>(), d_valid.as<uint8_t>(), (int)K, S.threshold,
 			              GCR_SCORE_EXACT_COUNTS, d_scores.as<float>(), d_counts.as<uint32_t>()) != GCR_OK)
@@ -214,6 +382,13 @@ namespace
 			h_scores.resize(K);
 			h_counts.resize(K);
 			h_models.resize(K * 9);
+			if (S.use_degensac && problem == GCR_F && variant == 0)
+			{
+				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
+				h_samples.resize((size_t)B * m);
+				if (gcr_memcpy_d2h(ctx, h_samples.data(), d_samples.p, (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
+					return fail("gcr_memcpy_d2h");
+			}
 			if (gcr_memcpy_d2h(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
 			    gcr_memcpy_d2h(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
 			    gcr_memcpy_d2h(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
@@ -281,8 +456,10 @@ namespace
 		// ---- non-minimal refit of `count` index sets (one GPU launch) ----
 		bool refit(const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
 		           const double *weights_by_point, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
-		           bool sets_on_device = false)
+		           bool sets_on_device = false, int refit_problem = -1)
 		{
+			const int rp = refit_problem < 0 ? problem : refit_problem;
+			const int rm = refit_problem < 0 ? this->rm : gcr_max_refit_models(rp);
 			const int count = (int)sizes.size();
 			size_t total = 0;
 			for (uint32_t v : sizes) total += v;
@@ -308,7 +485,7 @@ namespace
 					return fail("gcr_memcpy_h2d");
 				d_w = d_weights.as<double>();
 			}
-			if (gcr_refit(ctx, problem, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
+			if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
 			              weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_refit");
 			models.resize((size_t)count * rm * 9);
@@ -511,13 +688,15 @@ namespace
 		int run(double *model_out, uint8_t *inlier_mask)
 		{
 			memset(&st, 0, sizeof(st));
-			m = gcr_sample_size(problem);
-			mm = gcr_max_models(problem);
+			m = variant == 1 ? 2 : gcr_sample_size(problem);
+			mm = variant == 1 ? 1 : gcr_max_models(problem);
 			B = S.batch > 0 ? S.batch : 1024;
 			truncated_threshold = 3.0 / 2.0 * S.threshold;
 			T = truncated_threshold * truncated_threshold;
 			rm = gcr_max_refit_models(problem);
-			if (grid_pts && grid_pts != pts)
+			if (nested)
+				have_grid = false; // spatial_coherence_weight = 0: no neighbourhood (the reference passes nullptr, :558)
+			else if (grid_pts && grid_pts != pts)
 			{
 				// findEssentialMatrix_ builds the grid on the pixel coordinates and runs on the K-normalised ones
 				// (py/gcransac_python.cpp:2592-2600, 2641-2645)
@@ -529,13 +708,16 @@ namespace
 				if (!build_grid())
 					return -1;
 			}
-			if (gcr_points_upload(ctx, pts, n, 4, 1) != GCR_OK)
+			if (!nested)
 			{
-				fail("gcr_points_upload");
-				return -1;
+				if (gcr_points_upload(ctx, pts, n, 4, 1) != GCR_OK)
+				{
+					fail("gcr_points_upload");
+					return -1;
+				}
+				if (!(grid_pts && grid_pts != pts) && !build_grid())
+					return -1;
 			}
-			if (!(grid_pts && grid_pts != pts) && !build_grid())
-				return -1;
 			const double log_probability = std::log(1.0 - S.confidence);
 			uint64_t max_iteration = iteration_number(1, n, m, log_probability);
 			uint64_t &it = st.iteration_number;
@@ -588,10 +770,25 @@ namespace
 						if (!exact(model, s, &cur.idx))
 							return -1;
 						cur.lazy = false;
-						if (best.value < s.value && is_valid_model(model, cur.idx)) // :440-446
+						if (!(best.value < s.value)) // :440
+							continue;
+						double candidate[9];
+						memcpy(candidate, model, sizeof(candidate));
+						bool updated = false, failed = false;
+						const bool valid_model = is_valid_model(candidate, cur.idx, h_samples.empty() ? nullptr : &h_samples[(size_t)success_at * m],
+						                                        updated, failed);
+						if (failed)
+							return -1;
+						if (valid_model) // :441-446
 						{
+							if (updated) // :449-456: the replaced model is scored again, into the same container
+							{
+								memcpy(cur.model, candidate, sizeof(cur.model));
+								if (!exact(candidate, s, &cur.idx))
+									return -1;
+							}
 							offset = (offset + 1) % 2;
-							memcpy(best_model, model, sizeof(best_model));
+							memcpy(best_model, candidate, sizeof(best_model));
 							best = s;
 							do_lo = it > S.min_iteration_number_before_lo && best.inliers > (uint64_t)m; // :463-464
 							max_iteration = iteration_number(best.inliers, n, m, log_probability);
@@ -707,6 +904,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->cells_per_axis = 4;
 	s->seed = 1;
 	s->batch = 1024;
+	s->use_degensac = 0;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

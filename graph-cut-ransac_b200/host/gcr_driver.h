@@ -47,6 +47,9 @@ typedef struct gcr_run_settings
 	/* driver */
 	uint64_t seed;  /* counter-based sample streams: main = stream 0, local optimisation = stream 1 */
 	int batch;      /* minimal samples per GPU batch (default 1024) */
+	/* FundamentalMatrixEstimator(minimum_inlier_ratio_in_validity_check = 0.5, use_degensac = true,
+	 * homography_threshold = 2.0) (fundamental_estimator.h:91-93); F only */
+	int use_degensac;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats
@@ -55,6 +58,7 @@ typedef struct gcr_run_stats
 	uint64_t gpu_batches, exact_rescores, models_scored;
 	double score;
 	double graph_cut_seconds; /* host min-cut, timed separately (north star) */
+	uint64_t degensac_runs, degensac_updates; /* inner plane-and-parallax runs / models they replaced */
 } gcr_run_stats;
 
 /* defaults of utils::Settings + the Python drivers */

@@ -26,6 +26,7 @@ EXPORTS = [
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
+    "gcr_solve_plane_parallax",
 ]
 
 _lib = None
@@ -65,6 +66,7 @@ def load_library():
         "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
         "gcr_sample_from_pool": (i32, [vp, vp, u32, i32, u64, i32, u64, u32, vp]),
         "gcr_solve_minimal": (i32, [vp, i32, vp, i32, vp, vp]),
+        "gcr_solve_plane_parallax": (i32, [vp, vp, i32, vp, vp, vp]),
         "gcr_max_models": (i32, [i32]),
         "gcr_max_refit_models": (i32, [i32]),
         "gcr_sample_size": (i32, [i32]),
@@ -247,6 +249,22 @@ class Context:
             self.check(self.lib.gcr_solve_minimal(self.h, problem, C.c_void_p(ds), count, C.c_void_p(dm), C.c_void_p(dv)))
             return (self.to_host(dm, (self.n_pairs, count, mm, ml), np.float64),
                     self.to_host(dv, (self.n_pairs, count, mm), np.uint8))
+        finally:
+            for d in (ds, dm, dv):
+                self.free(d)
+
+    def solve_plane_parallax(self, samples, homography):
+        """DEGENSAC's inner minimal solver: 2-point samples + the plane homography -> F (or invalid)."""
+        samples = np.ascontiguousarray(samples, dtype=np.uint32).reshape(self.n_pairs, -1, 2)
+        count = samples.shape[1]
+        Hm = np.ascontiguousarray(homography, dtype=np.float64).reshape(9)
+        ds = self.to_device(samples)
+        dm = self.malloc(self.n_pairs * count * 72)
+        dv = self.malloc(self.n_pairs * count)
+        try:
+            self.check(self.lib.gcr_solve_plane_parallax(self.h, C.c_void_p(ds), count, Hm.ctypes.data_as(C.c_void_p),
+                                                         C.c_void_p(dm), C.c_void_p(dv)))
+            return (self.to_host(dm, (self.n_pairs, count, 9), np.float64), self.to_host(dv, (self.n_pairs, count), np.uint8))
         finally:
             for d in (ds, dm, dv):
                 self.free(d)

@@ -83,6 +83,36 @@ def epipolar_pair(n, outlier_ratio, seed, sigma=0.5):
     return pts, Fm / Fm[2, 2], Em, K_MAT.copy(), inl[perm]
 
 
+def epipolar_pair_planar(n, outlier_ratio, plane_fraction, seed, sigma=0.5):
+    """As epipolar_pair, but `plane_fraction` of the inliers lie on ONE scene plane (a dominant plane: the case
+    DEGENSAC, fundamental_estimator.h:341-572, exists for).  Returns pixel correspondences, F, inlier mask, on-plane mask."""
+    rng = np.random.default_rng(seed)
+    R, t = relative_pose(rng)
+    x1 = rng.uniform(0, SIZE, size=(n, 2))
+    rays = np.c_[x1, np.ones(n)] @ np.linalg.inv(K_MAT).T
+    depth = rng.uniform(4, 8, size=n)
+    on_plane = rng.uniform(size=n) < plane_fraction
+    nrm = np.array([0.15, -0.1, 1.0])
+    nrm /= np.linalg.norm(nrm)
+    depth[on_plane] = 6.0 / (rays[on_plane] @ nrm)                 # n . (depth * ray) = 6
+    X = rays * depth[:, None]
+    X2 = X @ R.T + t
+    p2 = X2 @ K_MAT.T
+    x2 = p2[:, :2] / p2[:, 2:] + rng.normal(0, sigma, size=(n, 2))
+    n_out = int(round(n * outlier_ratio))
+    out = rng.permutation(n)[:n_out]
+    x1[out] = rng.uniform(0, SIZE, size=(n_out, 2))
+    x2[out] = rng.uniform(0, SIZE, size=(n_out, 2))
+    perm = rng.permutation(n)
+    pts = np.ascontiguousarray(np.c_[x1, x2][perm])
+    Ki = np.linalg.inv(K_MAT)
+    Fm = Ki.T @ (_skew(t) @ R) @ Ki
+    inl = np.ones(n, bool)
+    inl[out] = False
+    on_plane[out] = False
+    return pts, Fm / Fm[2, 2], inl[perm], on_plane[perm]
+
+
 def pnp_scene(n, outlier_ratio, seed, sigma=0.5 / FOCAL):
     """Rows u v X Y Z with (u, v) K-normalised; returns points, P = [R|t] (3x4), inlier mask."""
     rng = np.random.default_rng(seed)

@@ -104,6 +104,12 @@ gcr_status gcr_sample_from_pool(gcr_ctx *ctx, const uint32_t *d_pool, uint32_t p
  * present and passed the tests.  max_models = 1 (H), 3 (F), 10 (E), 4 (PnP). */
 gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_t *d_samples, int count, double *d_models,
                              uint8_t *d_valid);
+/* FundamentalMatrixPlaneParallaxSolver::estimateModel (estimators/solver_fundamental_matrix_plane_and_parallax.h
+ * :109-160) + the oriented epipolar constraint (estimators/fundamental_estimator.h:161-184): the minimal solver of
+ * DEGENSAC's inner GC-RANSAC (fundamental_estimator.h:538-543).  d_samples [n_pairs][count][2]; h_homography: the
+ * plane homography, 9 doubles row-major, HOST memory; d_models [n_pairs][count][9]; d_valid [n_pairs][count]. */
+gcr_status gcr_solve_plane_parallax(gcr_ctx *ctx, const uint32_t *d_samples, int count, const double *h_homography,
+                                    double *d_models, uint8_t *d_valid);
 int gcr_max_models(int problem);
 int gcr_sample_size(int problem);
 int gcr_model_len(int problem);

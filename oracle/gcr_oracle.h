@@ -98,6 +98,12 @@ int gcro_f_orientation_valid(const double *F9, const double *pts, const uint32_t
 int gcro_estimate_f7(const double *pts, const uint32_t *sample, double *F27);
 /* fundamental_estimator.h:574-618 + :637-734 + solver_fundamental_matrix_eight_point.h:93-182  [unpinned]      */
 int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9);
+/* DEGENSAC (fundamental_estimator.h:341-572): H-degenerate sample test -> 1 and the plane homography             */
+int gcro_degensac_sample_homography(const double *F9, const double *pts, const uint32_t *sample, double sq_h_threshold,
+                                    double *H9);
+/* solver_fundamental_matrix_plane_and_parallax.h:109-160 (2 points + H), and with the orientation test (:161-184)  */
+int gcro_solve_f_plane_parallax(const double *pts, const uint32_t *sample, const double *H9, double *F9);
+int gcro_estimate_f_plane_parallax(const double *pts, const uint32_t *sample, const double *H9, double *F9);
 /* fundamental_estimator.h:287-338 symmetric-epipolar ratio test part of isValidModel (no DEGENSAC)              */
 int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t *inl, int n_inl, int m,
                              double truncated_thr, double min_ratio);

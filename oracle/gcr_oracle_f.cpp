@@ -320,6 +320,102 @@ int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double
 	return 1;
 }
 
+// ---- DEGENSAC (fundamental_estimator.h:341-572) -------------------------------------------------------------------
+// First half, :341-500: is the minimal sample H-degenerate?  The epipole of the second image comes from
+// JacobiSVD(F).matrixU().col(2) / U(2,2) (:365-372) -- here the right null vector of F^T from a one-sided Jacobi SVD
+// (V is orthonormal by construction; U's column for the vanishing singular value is not).  For each of the five point
+// triplets (:349-355) the plane homography H = A - e (M^-1 b)^T with A = [e]_x F (:380-442) is tested on the other
+// sample points with the forward transfer error (:445-483); >= 5 consistent points of 7 make the sample H-degenerate.
+int gcro_degensac_sample_homography(const double *F9, const double *pts, const uint32_t *sample, double sq_h_threshold,
+                                    double *H9)
+{
+	static const int triplets[15] = {0, 1, 2, 3, 4, 5, 0, 1, 6, 3, 4, 6, 2, 5, 6};
+	double Ft[9], U[9], sv[3], V[9];
+	gcro::transpose3(F9, Ft);
+	gcro::jacobi_svd(Ft, 3, 3, U, sv, V);
+	const double e[3] = {V[2] / V[8], V[5] / V[8], V[8] / V[8]};
+	const double ex[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+	double A[9];
+	gcro::mul3(ex, F9, A);
+	for (int t = 0; t < 5; ++t)
+	{
+		uint32_t idx[3];
+		double p1[3][3], p2[3][3], b[3];
+		for (int q = 0; q < 3; ++q)
+		{
+			idx[q] = sample[triplets[3 * t + q]];
+			const double *p = pts + 4 * (size_t)idx[q];
+			p1[q][0] = p[0]; p1[q][1] = p[1]; p1[q][2] = 1;
+			p2[q][0] = p[2]; p2[q][1] = p[3]; p2[q][2] = 1;
+			double pxe[3], Ap[3], pxAp[3];
+			gcro::cross3(p2[q], e, pxe);
+			for (int r = 0; r < 3; ++r)
+				Ap[r] = A[3 * r] * p1[q][0] + A[3 * r + 1] * p1[q][1] + A[3 * r + 2] * p1[q][2];
+			gcro::cross3(p2[q], Ap, pxAp);
+			b[q] = (pxAp[0] * pxe[0] + pxAp[1] * pxe[1] + pxAp[2] * pxe[2]) / (pxe[0] * pxe[0] + pxe[1] * pxe[1] + pxe[2] * pxe[2]);
+		}
+		const double M[9] = {p1[0][0], p1[0][1], p1[0][2], p1[1][0], p1[1][1], p1[1][2], p1[2][0], p1[2][1], p1[2][2]};
+		double Mi[9], Mb[3], H[9];
+		gcro::inv3(M, Mi);
+		for (int r = 0; r < 3; ++r)
+			Mb[r] = Mi[3 * r] * b[0] + Mi[3 * r + 1] * b[1] + Mi[3 * r + 2] * b[2];
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c)
+				H[3 * r + c] = A[3 * r + c] - e[r] * Mb[c];
+		int inlier_number = 3;
+		for (int i = 0; i < 7; ++i)
+		{
+			const uint32_t id = sample[i];
+			if (id == idx[0] || id == idx[1] || id == idx[2])
+				continue;
+			const double *p = pts + 4 * (size_t)id;
+			const double t1 = H[0] * p[0] + H[1] * p[1] + H[2], t2 = H[3] * p[0] + H[4] * p[1] + H[5],
+			             t3 = H[6] * p[0] + H[7] * p[1] + H[8];
+			const double d1 = p[2] - (t1 / t3), d2 = p[3] - (t2 / t3);
+			if (d1 * d1 + d2 * d2 < sq_h_threshold)
+				++inlier_number;
+		}
+		if (inlier_number >= 5)
+		{
+			std::memcpy(H9, H, sizeof(H));
+			return 1;
+		}
+	}
+	return 0;
+}
+
+// FundamentalMatrixPlaneParallaxSolver::estimateModel (solver_fundamental_matrix_plane_and_parallax.h:109-160): the
+// epipole is the intersection of the two lines joining H x1 and x2; F = [e]_x H.
+int gcro_solve_f_plane_parallax(const double *pts, const uint32_t *sample, const double *H9, double *F9)
+{
+	double line[2][3];
+	for (int q = 0; q < 2; ++q)
+	{
+		const double *p = pts + 4 * (size_t)sample[q];
+		const double src[3] = {p[0], p[1], 1}, dst[3] = {p[2], p[3], 1};
+		double proj[3];
+		for (int r = 0; r < 3; ++r)
+			proj[r] = H9[3 * r] * src[0] + H9[3 * r + 1] * src[1] + H9[3 * r + 2] * src[2];
+		gcro::cross3(proj, dst, line[q]);
+	}
+	double e[3];
+	gcro::cross3(line[0], line[1], e);
+	if (std::fabs(e[2]) < 2.220446049250313e-16)
+		return 0;
+	const double ex[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+	gcro::mul3(ex, H9, F9);
+	return 1;
+}
+
+// FundamentalMatrixEstimator<PlaneParallax, EightPoint>::estimateModel (fundamental_estimator.h:161-184): the solver +
+// the oriented epipolar constraint on the two sample points
+int gcro_estimate_f_plane_parallax(const double *pts, const uint32_t *sample, const double *H9, double *F9)
+{
+	if (!gcro_solve_f_plane_parallax(pts, sample, H9, F9))
+		return 0;
+	return gcro_f_orientation_valid(F9, pts, sample, 2) ? 1 : 0;
+}
+
 // fundamental_estimator.h:287-318 (and essential_estimator.h:279-305): the symmetric-epipolar part of isValidModel
 int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t *inl, int n_inl, int m,
                              double truncated_thr, double min_ratio)

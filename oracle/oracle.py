@@ -94,6 +94,12 @@ class Oracle:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [_dp, _u32p, _dp]
+        lib.gcro_degensac_sample_homography.restype = C.c_int
+        lib.gcro_degensac_sample_homography.argtypes = [_dp, _dp, _u32p, C.c_double, _dp]
+        for name in ("gcro_solve_f_plane_parallax", "gcro_estimate_f_plane_parallax"):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = [_dp, _u32p, _dp, _dp]
         lib.gcro_solve_e5_stewenius.restype = C.c_int
         lib.gcro_solve_e5_stewenius.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
         lib.gcro_refit_e.restype = C.c_int
@@ -213,6 +219,19 @@ class Oracle:
     def estimate_f7(self, pts, sample):
         return self._multi(self.lib.gcro_estimate_f7, pts, sample, 3, 3, 3)
 
+    def degensac_sample_homography(self, F, pts, sample, sq_h_threshold=4.0):
+        """fundamental_estimator.h:341-500: None, or the plane homography the H-degenerate part of the sample implies."""
+        Hm = np.zeros(9)
+        ok = self.lib.gcro_degensac_sample_homography(_as_pts(F).ravel(), _as_pts(pts),
+                                                      np.ascontiguousarray(sample, dtype=np.uint32), sq_h_threshold, Hm)
+        return Hm.reshape(3, 3) if ok else None
+
+    def solve_f_plane_parallax(self, pts, sample, Hm, oriented=False):
+        Fm = np.zeros(9)
+        fn = self.lib.gcro_estimate_f_plane_parallax if oriented else self.lib.gcro_solve_f_plane_parallax
+        ok = fn(_as_pts(pts), np.ascontiguousarray(sample, dtype=np.uint32), _as_pts(Hm).ravel(), Fm)
+        return Fm.reshape(3, 3) if ok else None
+
     def solve_e5(self, pts, sample):
         return self._multi(self.lib.gcro_solve_e5_nister, pts, sample, 10, 3, 3)
 
@@ -310,28 +329,29 @@ class Ref:
         lib.ref_run.restype = C.c_int
         lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
-                                _u64p, C.POINTER(C.c_double), C.c_void_p]
+                                _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int]
 
     def round(self, problem, scoring, pts, seed, first, count, thr):
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
-            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None):
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
         model = np.zeros(9)
         mask = np.zeros(len(pts), dtype=np.uint8)
-        stats = np.zeros(8, dtype=np.uint64)
+        stats = np.zeros(10, dtype=np.uint64)
         score = C.c_double()
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
-                                 C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data)
+                                 C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data,
+                                 1 if use_degensac else 0)
         if n_inl < 0:
             raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
         names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",
-                 "main_samples", "lo_samples")
+                 "main_samples", "lo_samples", "degensac_runs", "degensac_updates")
         return dict(model=model.reshape(3, 3), mask=mask.astype(bool), inliers=n_inl, score=score.value,
                     stats=dict(zip(names, (int(v) for v in stats))))
 

@@ -28,6 +28,10 @@ namespace
 	template <> struct ProblemTraits<GCRO_H> { static constexpr size_t m = 4, nonmin = 4, maxsol = 1, rows = 3, cols = 3; static constexpr bool weighting = true; };
 	template <> struct ProblemTraits<GCRO_F> { static constexpr size_t m = 7, nonmin = 8, maxsol = 3, rows = 3, cols = 3; static constexpr bool weighting = true; };
 	template <> struct ProblemTraits<GCRO_E> { static constexpr size_t m = 5, nonmin = 5, maxsol = 10, rows = 3, cols = 3; static constexpr bool weighting = true; };
+	// DEGENSAC's inner estimator: plane-and-parallax minimal solver (2 points + H), 8-point non-minimal solver
+	// (fundamental_estimator.h:538-541)
+	constexpr int GCRO_FPP = 100;
+	template <> struct ProblemTraits<GCRO_FPP> { static constexpr size_t m = 2, nonmin = 8, maxsol = 1, rows = 3, cols = 3; static constexpr bool weighting = true; };
 	template <> struct ProblemTraits<GCRO_PNP> { static constexpr size_t m = 3, nonmin = 6, maxsol = 4, rows = 3, cols = 4; static constexpr bool weighting = false; };
 
 	inline void to_flat(const Eigen::MatrixXd &d, double *out)
@@ -45,14 +49,23 @@ namespace
 		return m;
 	}
 
+	template <int PROBLEM> class OracleEstimator;
+	// fundamental_estimator.h:341-572 (defined below, after the counter-based sampler it needs)
+	bool oracle_apply_degensac(const OracleEstimator<GCRO_F> &est, Model &model_, const cv::Mat &data_,
+	                           const std::vector<size_t> &inliers_, const size_t *minimal_sample_, double threshold_,
+	                           bool &model_updated_);
+
 	// Estimator concept (estimators/estimator.h:48-108) over the restated solvers.
 	template <int PROBLEM>
 	class OracleEstimator
 	{
 	public:
 		typedef ProblemTraits<PROBLEM> T;
-		double f_min_ratio = 0.5; // fundamental_estimator.h minimum_inlier_ratio_in_validity_check default
+		double f_min_ratio = PROBLEM == GCRO_FPP ? 0.0 : 0.5; // minimum_inlier_ratio_in_validity_check (:91; inner run: 0.0, :540)
 		bool use_degensac = false;
+		const double *pp_homography = nullptr; // GCRO_FPP: the plane homography (setHomography, :542)
+		uint64_t seed = 1;                      // DEGENSAC's inner run draws from streams keyed by (seed, inner run number)
+		mutable uint64_t degensac_runs = 0, degensac_updates = 0;
 
 		static constexpr size_t sampleSize() { return T::m; }
 		static constexpr size_t nonMinimalSampleSize() { return T::nonmin; }
@@ -100,6 +113,8 @@ namespace
 				count = gcro_estimate_f7(pts, s, out);
 			else if constexpr (PROBLEM == GCRO_E)
 				count = gcro_estimate_e5(pts, s, out);
+			else if constexpr (PROBLEM == GCRO_FPP)
+				count = gcro_estimate_f_plane_parallax(pts, s, pp_homography, out);
 			else
 				count = gcro_solve_p3p(pts, s, out);
 			for (int i = 0; i < count; ++i)
@@ -122,7 +137,7 @@ namespace
 			int count = 0;
 			if constexpr (PROBLEM == GCRO_H)
 				count = gcro_refit_h(pts, s.data(), (int)sample_number_, weights_, out);
-			else if constexpr (PROBLEM == GCRO_F)
+			else if constexpr (PROBLEM == GCRO_F || PROBLEM == GCRO_FPP)
 				count = gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
 			else if constexpr (PROBLEM == GCRO_E)
 				count = gcro_refit_e(pts, s.data(), (int)sample_number_, weights_, out);
@@ -141,14 +156,19 @@ namespace
 			to_flat(model.descriptor, flat);
 			if constexpr (PROBLEM == GCRO_H)
 				return gcro_h_valid_model(flat) != 0;
-			else if constexpr (PROBLEM == GCRO_F || PROBLEM == GCRO_E)
+			else if constexpr (PROBLEM == GCRO_F || PROBLEM == GCRO_E || PROBLEM == GCRO_FPP)
 			{
 				std::vector<uint32_t> inl(inliers.size());
 				for (size_t i = 0; i < inliers.size(); ++i)
 					inl[i] = (uint32_t)inliers[i];
-				const double ratio = PROBLEM == GCRO_F ? f_min_ratio : 0.1;
-				return gcro_f_valid_model_ratio(flat, reinterpret_cast<const double *>(data.data), inl.data(),
-				                                (int)inl.size(), (int)T::m, threshold_, ratio) != 0;
+				const double ratio = PROBLEM == GCRO_E ? 0.1 : f_min_ratio;
+				if (!gcro_f_valid_model_ratio(flat, reinterpret_cast<const double *>(data.data), inl.data(),
+				                              (int)inl.size(), (int)T::m, threshold_, ratio))
+					return false;
+				if constexpr (PROBLEM == GCRO_F) // :325-333 (sampleSize() >= 7)
+					if (use_degensac)
+						return oracle_apply_degensac(*this, model, data, inliers, minimal_sample_, threshold_, model_updated_);
+				return true;
 			}
 			return true;
 		}
@@ -384,14 +404,67 @@ namespace
 		}
 	};
 
+	// fundamental_estimator.h:341-572.  The H-degenerate sample test is the restated gcro_degensac_sample_homography;
+	// the inner GC-RANSAC is the reference's own GCRANSAC<> (verbatim) over the plane-and-parallax estimator with the
+	// settings of :547-551.  The reference draws the inner samples from a fresh random_device-seeded UniformSampler
+	// shared by the main loop and the local optimisation (:553, not reproducible); here run number r of a call uses
+	// the counter-based streams (seed + r * 0xD1B54A32D192ED03, 0 / 1).
+	bool oracle_apply_degensac(const OracleEstimator<GCRO_F> &est, Model &model_, const cv::Mat &data_,
+	                           const std::vector<size_t> &inliers_, const size_t *minimal_sample_, double threshold_,
+	                           bool &model_updated_)
+	{
+		model_updated_ = false;
+		const double squared_homography_threshold = 2.0 * 2.0; // homography_threshold_ = 2.0 (:93)
+		const double *pts = reinterpret_cast<const double *>(data_.data);
+		double F[9], H[9];
+		to_flat(model_.descriptor, F);
+		uint32_t s7[7];
+		for (int i = 0; i < 7; ++i)
+			s7[i] = (uint32_t)minimal_sample_[i];
+		if (!gcro_degensac_sample_homography(F, pts, s7, squared_homography_threshold, H))
+			return true; // not H-degenerate: the model stands (:571)
+		std::vector<uint32_t> h_inliers; // :501-509
+		for (const size_t &idx : inliers_)
+			if (gcro_sqres_h(pts + 4 * idx, H) < squared_homography_threshold)
+				h_inliers.push_back((uint32_t)idx);
+		if (h_inliers.size() < 4) // homography_estimator.nonMinimalSampleSize() (:512)
+			return false;
+		double Hn[9];
+		if (gcro_refit_h(pts, h_inliers.data(), (int)h_inliers.size(), nullptr, Hn) != 1) // :520-528
+			return false;
+		typedef OracleEstimator<GCRO_FPP> Inner;
+		Inner inner;
+		inner.pp_homography = Hn;
+		++est.degensac_runs;
+		const uint64_t inner_seed = est.seed + est.degensac_runs * 0xD1B54A32D192ED03ull;
+		CounterSampler main_sampler(&data_, inner_seed, 0u), lo_sampler(&data_, inner_seed, 1u);
+		GCRANSAC<Inner, neighborhood::GridNeighborhoodGraph<4>> gcransac;
+		gcransac.settings.threshold = threshold_;
+		gcransac.settings.spatial_coherence_weight = 0;
+		gcransac.settings.confidence = 0.99;
+		gcransac.settings.neighborhood_sphere_radius = 8;
+		Model model;
+		gcransac.run(data_, inner, &main_sampler, &lo_sampler, nullptr, model);
+		const utils::RANSACStatistics &statistics = gcransac.getRansacStatistics();
+		if (statistics.inliers.size() > inliers_.size()) // :561-567
+		{
+			model_updated_ = true;
+			model_ = model;
+			++est.degensac_updates;
+		}
+		return true;
+	}
+
 	template <int PROBLEM, class Scoring>
 	int run_reference(const cv::Mat &points, const cv::Mat &grid_points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
 	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
-	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out)
+	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0)
 	{
 		typedef OracleEstimator<PROBLEM> Est;
 		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
 		Est estimator;
+		estimator.use_degensac = use_degensac != 0;
+		estimator.seed = seed;
 		std::vector<double> cs(cell_sizes, cell_sizes + 4);
 		Grid graph(&grid_points, cs, (size_t)cells_per_axis); // E: built on the pixel coordinates (py/gcransac_python.cpp:2592-2600)
 		CounterSampler main_sampler(&points, seed, 0u), lo_sampler(&points, seed, 1u);
@@ -423,6 +496,8 @@ namespace
 			stats_out[5] = st.rejected_models;
 			stats_out[6] = main_sampler.drawn();
 			stats_out[7] = lo_sampler.drawn();
+			stats_out[8] = estimator.degensac_runs;
+			stats_out[9] = estimator.degensac_updates;
 		}
 		if (score_out)
 			*score_out = st.score;
@@ -441,11 +516,11 @@ extern "C" {
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
-            const double *grid_pts)
+            const double *grid_pts, int use_degensac)
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
 	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
-#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out)
+#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac)
 	if (scoring_kind == 0)
 	{
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);

@@ -74,7 +74,8 @@ def test_findfundamental_matches_reference_run(pyg, ref):
     pts, Fm, Em, K, inl = synth.epipolar_pair(2000, 0.5, seed=34)
     for seed, weight in ((7, 0.0), (8, 0.1)):
         F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
-                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed,
+                                            use_degensac=False)
         st = pyg.last_statistics
         cs = np.array([1024 / 4.0] * 4)
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50, seed=seed)
@@ -83,6 +84,31 @@ def test_findfundamental_matches_reference_run(pyg, ref):
         assert np.array_equal(mask, want["mask"])
         assert _up_to_scale(want["model"], F) < 1e-5
         assert (mask & inl).sum() > 0.95 * inl.sum()
+
+
+def test_findfundamental_degensac_matches_reference_run(pyg, ref):
+    """A scene dominated by one plane: the best 7-point samples are H-degenerate, DEGENSAC (fundamental_estimator.h
+    :341-572) refits the plane homography and runs the inner plane-and-parallax GC-RANSAC.  The driver's nested run
+    against the reference's verbatim GCRANSAC<> (outer AND inner) over the oracle estimators, same sample streams."""
+    cs = np.array([1024 / 4.0] * 4)
+    runs = updates = 0
+    for seed, plane in ((1, 0.8), (3, 0.8), (1, 0.95), (2, 0.95), (3, 0.95), (4, 0.0)):
+        pts, Fm, inl, on_plane = synth.epipolar_pair_planar(1000, 0.4, plane, seed + 10)
+        F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=0.0,
+                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+        st = pyg.last_statistics
+        want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50,
+                       seed=seed, use_degensac=True)
+        assert st["degensac_runs"] == want["stats"]["degensac_runs"], (seed, plane, st, want["stats"])
+        assert st["degensac_updates"] == want["stats"]["degensac_updates"]
+        assert st["iteration_number"] == want["stats"]["iterations"], (seed, plane, st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert np.array_equal(mask, want["mask"]), (seed, plane, int(mask.sum()), int(want["mask"].sum()))
+        assert _up_to_scale(want["model"], F) < 1e-5
+        assert (mask & inl).sum() > 0.9 * inl.sum()
+        runs += st["degensac_runs"]
+        updates += st["degensac_updates"]
+    assert runs >= 3 and updates >= 2      # the degenerate branch and the model replacement were both exercised
 
 
 def test_findessential_matches_reference_run(pyg, ref, oracle):

@@ -208,3 +208,21 @@ def test_round_f_matches_cpu_round(gcr_ctx, oracle):
     err = np.abs(best[0] / np.linalg.norm(best[0]) - want_model / np.linalg.norm(want_model)).max()
     assert err < 1e-9
     assert gcr_ctx.counters()[1] == 0
+
+
+def test_plane_parallax_models_bit_exact(gcr_ctx, oracle):
+    """DEGENSAC's inner minimal solver (solver_fundamental_matrix_plane_and_parallax.h:109-160 + the oriented
+    constraint): same statement order as the oracle, only + - * -> bit-exact."""
+    pts, Fm, inl, on_plane = synth.epipolar_pair_planar(600, 0.3, 0.6, seed=23)
+    Hm = oracle.refit(O.H, pts, np.flatnonzero(on_plane)[:50].astype(np.uint32))
+    gcr_ctx.points_upload(pts)
+    samples = oracle.sample_uniform(5, 0, 2000, 600, 2)
+    models, valid = gcr_ctx.solve_plane_parallax(samples, Hm)
+    n_valid = 0
+    for s, mdl, v in zip(samples, models[0], valid[0]):
+        want = oracle.solve_f_plane_parallax(pts, s, Hm, oriented=True)
+        assert bool(v) == (want is not None)
+        if want is not None:
+            n_valid += 1
+            assert np.array_equal(mdl.reshape(3, 3), want)
+    assert 200 < n_valid < 2000

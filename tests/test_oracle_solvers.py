@@ -174,3 +174,65 @@ def test_refit_e_stewenius_against_numpy(oracle):
     assert len(a) == len(b)
     for E in a:
         assert min(np.abs(_norm(E) - _norm(q)).max() for q in b) < 1e-6
+
+
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def test_plane_parallax_solver_against_numpy(oracle):
+    """solver_fundamental_matrix_plane_and_parallax.h:109-160 stated with numpy: e = (Hx1 x x1') x (Hx2 x x2'), F = [e]x H.
+    With the true plane homography and two off-plane points the result is the true F (up to scale)."""
+    pts, Fm, inl, on_plane = synth.epipolar_pair_planar(400, 0.0, 0.5, seed=21, sigma=0.0)
+    plane_idx = np.flatnonzero(on_plane)[:40].astype(np.uint32)
+    Hm = oracle.refit(O.H, pts, plane_idx)                      # exact plane homography (noise-free points)
+    off = np.flatnonzero(~on_plane)
+    for a, b in ((off[0], off[1]), (off[5], off[9]), (off[2], off[30])):
+        got = oracle.solve_f_plane_parallax(pts, [a, b], Hm)
+        l = [np.cross(Hm @ np.r_[pts[i, :2], 1], np.r_[pts[i, 2:], 1]) for i in (a, b)]
+        want = _skew(np.cross(l[0], l[1])) @ Hm
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        g, w = got / np.linalg.norm(got), Fm / np.linalg.norm(Fm)
+        assert min(np.abs(g - w).max(), np.abs(g + w).max()) < 1e-6
+    # two points ON the plane: H x = x', both lines vanish, no epipole -> no model
+
+
+def test_degensac_sample_test_against_numpy(oracle):
+    """fundamental_estimator.h:341-500 stated with numpy (SVD epipole, H = A - e (M^-1 b)^T): a 7-point sample with
+    >= 5 points on one plane is H-degenerate and the implied homography maps the plane's points; a general sample is not."""
+    pts, Fm, inl, on_plane = synth.epipolar_pair_planar(600, 0.0, 0.5, seed=22, sigma=0.05)
+    P, Q = np.flatnonzero(on_plane), np.flatnonzero(~on_plane)
+    rng = np.random.default_rng(3)
+    hits = 0
+    for trial in range(40):
+        k = [7, 6, 5, 2, 0][trial % 5]                          # points of the sample on the plane
+        sample = np.r_[rng.choice(P, k, replace=False), rng.choice(Q, 7 - k, replace=False)].astype(np.uint32)
+        rng.shuffle(sample)
+        models = oracle.solve_f7(pts, sample)
+        if len(models) == 0:
+            continue
+        F = models[trial % len(models)]
+        got = oracle.degensac_sample_homography(F, pts, sample)
+        # numpy statement
+        U = np.linalg.svd(F)[0]
+        e = U[:, 2] / U[2, 2]
+        A = _skew(e) @ F
+        want = None
+        for t in ((0, 1, 2), (3, 4, 5), (0, 1, 6), (3, 4, 6), (2, 5, 6)):
+            idx = sample[list(t)]
+            x1 = np.c_[pts[idx, :2], np.ones(3)]
+            x2 = np.c_[pts[idx, 2:], np.ones(3)]
+            c = [np.cross(x2[q], e) for q in range(3)]
+            b = np.array([np.cross(x2[q], A @ x1[q]) @ c[q] / (c[q] @ c[q]) for q in range(3)])
+            Hm = A - np.outer(e, np.linalg.inv(x1) @ b)
+            others = [i for i in sample if i not in idx]
+            proj = np.c_[pts[others, :2], np.ones(len(others))] @ Hm.T
+            r2 = ((proj[:, :2] / proj[:, 2:] - pts[others, 2:]) ** 2).sum(1)
+            if 3 + (r2 < 4.0).sum() >= 5:
+                want = Hm
+                break
+        assert (got is None) == (want is None), (trial, k)
+        if got is not None:
+            hits += 1
+            assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert hits >= 8
