@@ -98,6 +98,12 @@ int gcro_f_orientation_valid(const double *F9, const double *pts, const uint32_t
 int gcro_estimate_f7(const double *pts, const uint32_t *sample, double *F27);
 /* fundamental_estimator.h:574-618 + :637-734 + solver_fundamental_matrix_eight_point.h:93-182  [unpinned]      */
 int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9);
+/* LM bundle adjustment of F (relative_pose/bundle.cpp:253-339, jacobian_impl.h:472-606): refinement of F9 on n points
+ * in the working frame; the estimator's default non-minimal fit (fundamental_estimator.h:574-618 with the BA solver);
+ * the post-run polish of py/gcransac_python.cpp:1851-1858                                                        */
+int gcro_refine_f_lm(const double *np, int n, const double *weights, double *F9, int max_iterations);
+int gcro_refit_f_ba(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9);
+int gcro_polish_f_ba(const double *pts, const uint32_t *inliers, int n, const double *weights, double *F9);
 /* DEGENSAC (fundamental_estimator.h:341-572): H-degenerate sample test -> 1 and the plane homography             */
 int gcro_degensac_sample_homography(const double *F9, const double *pts, const uint32_t *sample, double sq_h_threshold,
                                     double *H9);

@@ -269,17 +269,14 @@ static void fullpiv_householder_q_lastcol(const double *M_in, int n, double *q)
 
 // fundamental_estimator.h:574-618 (+ normalizePoints :637-734) + solver_fundamental_matrix_eight_point.h:93-182.
 // The 8-point solver receives the normalised copy with sample_ == nullptr, so it reads weights_[i] by POSITION (:113-118).
-int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9)
+// FundamentalMatrixEightPointSolver::estimateModel (solver_fundamental_matrix_eight_point.h:93-182) on n points given
+// in the working frame (rows x0 y0 x1 y1), positional weights: the null vector of A^T A as a 3 x 3 matrix
+static void f8_in_frame(const double *np, int n, const double *weights, double *f)
 {
-	if (n < 8)
-		return 0;
-	std::vector<double> np((size_t)n * 4);
-	double T1[9], T2[9];
-	gcro_normalize_points(pts, 4, sample, n, np.data(), T1, T2);
 	std::vector<double> A((size_t)n * 9);
 	for (int i = 0; i < n; ++i)
 	{
-		const double *p = np.data() + 4 * (size_t)i;
+		const double *p = np + 4 * (size_t)i;
 		const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
 		double *r = A.data() + 9 * (size_t)i;
 		if (!weights)
@@ -303,9 +300,12 @@ int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double
 				s += A[9 * (size_t)i + a] * A[9 * (size_t)i + b];
 			AtA[9 * a + b] = s;
 		}
-	double f[9];
 	fullpiv_householder_q_lastcol(AtA, 9, f);
-	// fundamental_estimator.h:606-616: F = T2^T * Fn * T1, Frobenius-normalise, sign so that F(2,2) >= 0
+}
+
+// fundamental_estimator.h:606-616: F = T2^T * Fn * T1, Frobenius-normalise, sign so that F(2,2) >= 0
+static void f_denormalise(const double *f, const double *T1, const double *T2, double *F9)
+{
 	double T2t[9], tmp[9], F[9];
 	gcro::transpose3(T2, T2t);
 	gcro::mul3(T2t, f, tmp);
@@ -317,6 +317,260 @@ int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double
 	if (F[8] < 0)
 		for (int i = 0; i < 9; ++i) F[i] = -F[i];
 	std::memcpy(F9, F, sizeof(F));
+}
+
+int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9)
+{
+	if (n < 8)
+		return 0;
+	std::vector<double> np((size_t)n * 4);
+	double T1[9], T2[9], f[9];
+	gcro_normalize_points(pts, 4, sample, n, np.data(), T1, T2);
+	f8_in_frame(np.data(), n, weights, f);
+	f_denormalise(f, T1, T2, F9);
+	return 1;
+}
+
+// ---- LM bundle adjustment of F (relative_pose/bundle.cpp:253-339 lm_F_impl, relative_pose/jacobian_impl.h:472-606) ----
+// F = U diag(1, sigma, 0) V^T (FactorizedFundamentalMatrix: 7 parameters, rank 2 by construction), Sampson residual,
+// TRUNCATED loss with scale 1 (solver_fundamental_matrix_bundle_adjustment.h:56-62, bundle.h:106-118), lambda0 = 1e-3,
+// x / : 10, gradient / step tolerance 1e-8, <= 25 iterations, positional weights (jacobian_impl.h:525-528, 573-577).
+namespace
+{
+	struct FactorizedF
+	{
+		double U[9], V[9], sigma;
+		void F(double *out) const // :481-483
+		{
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					out[3 * r + c] = U[3 * r] * V[3 * c] + sigma * U[3 * r + 1] * V[3 * c + 1];
+		}
+	};
+
+	double lm_f_cost(const double *np, int n, const double *weights, const FactorizedF &FF)
+	{
+		double F[9];
+		FF.F(F);
+		double cost = 0.0;
+		for (int k = 0; k < n; ++k)
+		{
+			const double *p = np + 4 * (size_t)k;
+			const double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+			const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+			const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+			const double Ft0 = F[0] * x2 + F[3] * y2 + F[6], Ft1 = F[1] * x2 + F[4] * y2 + F[7];
+			const double nJc_sq = (Fx0 * Fx0 + Fx1 * Fx1) + (Ft0 * Ft0 + Ft1 * Ft1);
+			const double r2 = (C * C) / nJc_sq;
+			const double loss = std::min(r2, 1.0);
+			cost += weights ? weights[k] * loss : loss;
+		}
+		return cost;
+	}
+
+	void lm_f_accumulate(const double *np, int n, const double *weights, const FactorizedF &FF, double *JtJ /*7x7 lower*/,
+	                     double *Jtr)
+	{
+		double F[9];
+		FF.F(F);
+		double ds[9]; // d_sigma = U.col(1) * V.col(1)^T
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c)
+				ds[3 * r + c] = FF.U[3 * r + 1] * FF.V[3 * c + 1];
+#define F_(r, c) F[3 * (r) + (c)]
+#define D_(r, c) ds[3 * (r) + (c)]
+		const double dFdp[9][7] = {
+		    {0, F_(2, 0), -F_(1, 0), 0, F_(0, 2), -F_(0, 1), D_(0, 0)},
+		    {-F_(2, 0), 0, F_(0, 0), 0, F_(1, 2), -F_(1, 1), D_(1, 0)},
+		    {F_(1, 0), -F_(0, 0), 0, 0, F_(2, 2), -F_(2, 1), D_(2, 0)},
+		    {0, F_(2, 1), -F_(1, 1), -F_(0, 2), 0, F_(0, 0), D_(0, 1)},
+		    {-F_(2, 1), 0, F_(0, 1), -F_(1, 2), 0, F_(1, 0), D_(1, 1)},
+		    {F_(1, 1), -F_(0, 1), 0, -F_(2, 2), 0, F_(2, 0), D_(2, 1)},
+		    {0, F_(2, 2), -F_(1, 2), F_(0, 1), -F_(0, 0), 0, D_(0, 2)},
+		    {-F_(2, 2), 0, F_(0, 2), F_(1, 1), -F_(1, 0), 0, D_(1, 2)},
+		    {F_(1, 2), -F_(0, 2), 0, F_(2, 1), -F_(2, 0), 0, D_(2, 2)}};
+#undef F_
+#undef D_
+		for (int k = 0; k < n; ++k)
+		{
+			const double *p = np + 4 * (size_t)k;
+			const double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+			const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+			const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+			// J_C = [F(:, 0:1)^T x2h ; F(0:1, :) x1h]
+			const double JC[4] = {F[0] * x2 + F[3] * y2 + F[6], F[1] * x2 + F[4] * y2 + F[7], Fx0, Fx1};
+			const double nJ_C = std::sqrt(JC[0] * JC[0] + JC[1] * JC[1] + JC[2] * JC[2] + JC[3] * JC[3]);
+			const double inv_nJ_C = 1.0 / nJ_C;
+			const double r = C * inv_nJ_C;
+			double weight = ((r * r) < 1.0 ? 1.0 : 0.0) / n;
+			if (weights)
+				weight = weights[k] * weight;
+			if (weight == 0.0)
+				continue;
+			double dF[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0};
+			const double s = C * inv_nJ_C * inv_nJ_C;
+			dF[0] -= s * (JC[2] * x1 + JC[0] * x2);
+			dF[1] -= s * (JC[3] * x1 + JC[0] * y2);
+			dF[2] -= s * (JC[0]);
+			dF[3] -= s * (JC[2] * y1 + JC[1] * x2);
+			dF[4] -= s * (JC[3] * y1 + JC[1] * y2);
+			dF[5] -= s * (JC[1]);
+			dF[6] -= s * (JC[2]);
+			dF[7] -= s * (JC[3]);
+			for (int i = 0; i < 9; ++i) dF[i] *= inv_nJ_C;
+			double J[7];
+			for (int j = 0; j < 7; ++j)
+			{
+				double acc = 0.0;
+				for (int i = 0; i < 9; ++i) acc += dF[i] * dFdp[i][j];
+				J[j] = acc;
+			}
+			for (int i = 0; i < 7; ++i)
+			{
+				Jtr[i] += weight * C * inv_nJ_C * J[i];
+				for (int j = 0; j <= i; ++j)
+					JtJ[7 * i + j] += weight * (J[i] * J[j]);
+			}
+		}
+	}
+
+	// x = -(L L^T)^-1 b from the lower triangle of A (7 x 7); NaNs propagate when A is not positive definite, as with
+	// Eigen's unchecked llt().solve
+	void llt_solve7_neg(const double *A, const double *b, double *x)
+	{
+		double L[49];
+		for (int j = 0; j < 7; ++j)
+		{
+			double d = A[7 * j + j];
+			for (int k = 0; k < j; ++k) d -= L[7 * j + k] * L[7 * j + k];
+			d = std::sqrt(d);
+			L[7 * j + j] = d;
+			for (int i = j + 1; i < 7; ++i)
+			{
+				double s = A[7 * i + j];
+				for (int k = 0; k < j; ++k) s -= L[7 * i + k] * L[7 * j + k];
+				L[7 * i + j] = s / d;
+			}
+		}
+		double y[7];
+		for (int i = 0; i < 7; ++i)
+		{
+			double s = b[i];
+			for (int k = 0; k < i; ++k) s -= L[7 * i + k] * y[k];
+			y[i] = s / L[7 * i + i];
+		}
+		for (int i = 6; i >= 0; --i)
+		{
+			double s = y[i];
+			for (int k = i + 1; k < 7; ++k) s -= L[7 * k + i] * x[k];
+			x[i] = s / L[7 * i + i];
+		}
+		for (int i = 0; i < 7; ++i) x[i] = -x[i];
+	}
+
+	// M <- M + (a [w]x + (1 - b) [w]x^2) M   (:290-316)
+	void lie_update(const double *w3, const double *M, double *out)
+	{
+		double w[3] = {w3[0], w3[1], w3[2]};
+		const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+		for (int i = 0; i < 3; ++i) w[i] /= theta;
+		const double a = std::sin(theta), b = std::cos(theta);
+		const double sw[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+		double sw2[9], R[9], RM[9];
+		gcro::mul3(sw, sw, sw2);
+		for (int i = 0; i < 9; ++i) R[i] = a * sw[i] + (1 - b) * sw2[i];
+		gcro::mul3(R, M, RM);
+		for (int i = 0; i < 9; ++i) out[i] = M[i] + RM[i];
+	}
+}
+
+// refine_fundamental (bundle.cpp:454-499) with TruncatedLoss(1.0): F9 in / out, points in the working frame
+int gcro_refine_f_lm(const double *np, int n, const double *weights, double *F9, int max_iterations)
+{
+	FactorizedF F;
+	{
+		double s[3], Ucols[9], Vcols[9];
+		gcro::jacobi_svd(F9, 3, 3, Ucols, s, Vcols); // FactorizedFundamentalMatrix(F): JacobiSVD, sigma = s1 / s0 (:474-480)
+		std::memcpy(F.U, Ucols, sizeof(Ucols));
+		std::memcpy(F.V, Vcols, sizeof(Vcols));
+		F.sigma = s[1] / s[0];
+	}
+	double lambda = 1e-3;
+	double cost = lm_f_cost(np, n, weights, F);
+	bool recompute_jac = true;
+	double JtJ[49], Jtr[7];
+	int iter;
+	for (iter = 0; iter < max_iterations; ++iter)
+	{
+		if (recompute_jac)
+		{
+			for (int i = 0; i < 49; ++i) JtJ[i] = 0.0;
+			for (int i = 0; i < 7; ++i) Jtr[i] = 0.0;
+			lm_f_accumulate(np, n, weights, F, JtJ, Jtr);
+			double g = 0.0;
+			for (int i = 0; i < 7; ++i) g += Jtr[i] * Jtr[i];
+			if (std::sqrt(g) < 1e-8)
+				break;
+		}
+		for (int k = 0; k < 7; ++k) JtJ[7 * k + k] += lambda;
+		double sol[7];
+		llt_solve7_neg(JtJ, Jtr, sol);
+		double sn = 0.0;
+		for (int i = 0; i < 7; ++i) sn += sol[i] * sol[i];
+		if (std::sqrt(sn) < 1e-8)
+			break;
+		FactorizedF Fn;
+		lie_update(sol, F.U, Fn.U);
+		lie_update(sol + 3, F.V, Fn.V);
+		Fn.sigma = F.sigma + sol[6];
+		const double cost_new = lm_f_cost(np, n, weights, Fn);
+		if (cost_new < cost)
+		{
+			F = Fn;
+			lambda /= 10;
+			cost = cost_new;
+			recompute_jac = true;
+		}
+		else
+		{
+			for (int k = 0; k < 7; ++k) JtJ[7 * k + k] -= lambda;
+			lambda *= 10;
+			recompute_jac = false;
+		}
+	}
+	F.F(F9);
+	return iter;
+}
+
+// FundamentalMatrixEstimator<SevenPoint, FundamentalMatrixBundleAdjustmentSolver>::estimateModelNonminimal
+// (fundamental_estimator.h:574-618; the reference's DEFAULT F estimator, types.h:78-80): Hartley normalisation, the
+// 8-point initialisation and the LM refinement both in the normalised frame
+// (solver_fundamental_matrix_bundle_adjustment.h:113-177), then T2^T F T1.  n == 7 (the 7-point initialisation with up
+// to three models) is not restated: returns 0.
+int gcro_refit_f_ba(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9)
+{
+	if (n < 8)
+		return 0;
+	std::vector<double> np((size_t)n * 4);
+	double T1[9], T2[9], f[9];
+	gcro_normalize_points(pts, 4, sample, n, np.data(), T1, T2);
+	f8_in_frame(np.data(), n, weights, f);
+	gcro_refine_f_lm(np.data(), n, weights, f, 25);
+	f_denormalise(f, T1, T2, F9);
+	return 1;
+}
+
+// The post-run polish of findFundamentalMatrix_ (py/gcransac_python.cpp:1851-1858): the BA solver called directly on
+// the pixel coordinates of the inliers -- un-normalised 8-point initialisation, LM in pixels.  Output not rescaled.
+int gcro_polish_f_ba(const double *pts, const uint32_t *inliers, int n, const double *weights, double *F9)
+{
+	if (n < 8)
+		return 0;
+	std::vector<double> sel((size_t)n * 4);
+	for (int i = 0; i < n; ++i)
+		std::memcpy(sel.data() + 4 * (size_t)i, pts + 4 * (size_t)inliers[i], 4 * sizeof(double));
+	f8_in_frame(sel.data(), n, weights, F9);
+	gcro_refine_f_lm(sel.data(), n, weights, F9, 25);
 	return 1;
 }
 

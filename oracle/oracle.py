@@ -86,7 +86,9 @@ class Oracle:
         lib.gcro_h_valid_model.argtypes = [_dp]
         lib.gcro_normalize_points.restype = None
         lib.gcro_normalize_points.argtypes = [_dp, C.c_int, _u32p, C.c_int, _dp, _dp, _dp]
-        for name in ("gcro_refit_h", "gcro_refit_f8"):
+        lib.gcro_refine_f_lm.restype = C.c_int
+        lib.gcro_refine_f_lm.argtypes = [_dp, C.c_int, C.c_void_p, _dp, C.c_int]
+        for name in ("gcro_refit_h", "gcro_refit_f8", "gcro_refit_f_ba", "gcro_polish_f_ba"):
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
@@ -206,6 +208,32 @@ class Oracle:
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         fn = self.lib.gcro_refit_h if problem == H else self.lib.gcro_refit_f8
         ok = fn(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
+        return out.reshape(3, 3) if ok else None
+
+    def normalize_points(self, pts, sample):
+        """normalizePoints (fundamental_estimator.h:637-734 / homography_estimator.h:213-310): the selected points in the
+        Hartley frame and the two 3 x 3 transforms."""
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(sample), 4))
+        T1, T2 = np.zeros(9), np.zeros(9)
+        self.lib.gcro_normalize_points(_as_pts(pts), 4, sample, len(sample), out.reshape(-1), T1, T2)
+        return out, T1.reshape(3, 3), T2.reshape(3, 3)
+
+    def refine_f_lm(self, pts_in_frame, F, weights=None, max_iterations=25):
+        """relative_pose/bundle.cpp:253-339 on points already in the working frame; returns (F, iterations)."""
+        out = np.ascontiguousarray(F, dtype=np.float64).reshape(9).copy()
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        it = self.lib.gcro_refine_f_lm(_as_pts(pts_in_frame), len(pts_in_frame), None if w is None else w.ctypes.data, out,
+                                       max_iterations)
+        return out.reshape(3, 3), it
+
+    def refit_f_ba(self, pts, sample, weights=None, polish=False):
+        """The reference's default non-minimal F fit (8-point + LM in the Hartley frame), or with polish=True the
+        post-run bundle adjustment of py/gcransac_python.cpp:1851-1858 (pixel frame)."""
+        out = np.zeros(9)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        fn = self.lib.gcro_polish_f_ba if polish else self.lib.gcro_refit_f_ba
+        ok = fn(_as_pts(pts), np.ascontiguousarray(sample, dtype=np.uint32), len(sample), None if w is None else w.ctypes.data, out)
         return out.reshape(3, 3) if ok else None
 
     def _multi(self, fn, pts, sample, maxn, rows, cols):

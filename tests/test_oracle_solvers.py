@@ -236,3 +236,47 @@ def test_degensac_sample_test_against_numpy(oracle):
             hits += 1
             assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
     assert hits >= 8
+
+
+def _sampson_residuals(F, p):
+    x1 = np.c_[p[:, :2], np.ones(len(p))]
+    x2 = np.c_[p[:, 2:], np.ones(len(p))]
+    Fx, Ftx = x1 @ F.T, x2 @ F
+    return (x2 * Fx).sum(1) / np.sqrt(Fx[:, 0] ** 2 + Fx[:, 1] ** 2 + Ftx[:, 0] ** 2 + Ftx[:, 1] ** 2)
+
+
+def test_f_bundle_adjustment_against_scipy(oracle):
+    """relative_pose/bundle.cpp:253-339 (lm_F_impl) + jacobian_impl.h:472-606 restated; pinned against an independent
+    scipy least-squares minimisation of the same Sampson cost over rank-2 matrices U diag(1, s, 0) V^T."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    pts, Fm, Em, Kc, _ = synth.epipolar_pair(400, 0.0, seed=31, sigma=0.8)
+    idx = np.arange(150, dtype=np.uint32)
+    npts, T1, T2 = oracle.normalize_points(pts, idx)
+    F0 = np.linalg.inv(T2).T @ oracle.refit(O.F, pts, idx) @ np.linalg.inv(T1)               # 8-point result, Hartley frame
+    F1, iters = oracle.refine_f_lm(npts, F0)
+    r0, r1 = _sampson_residuals(F0, npts), _sampson_residuals(F1, npts)
+    assert 0 < iters <= 25 and (r1 ** 2).sum() < (r0 ** 2).sum()
+    assert abs(np.linalg.det(F1 / np.linalg.norm(F1))) < 1e-14                               # rank 2 by construction
+    U, s, Vt = np.linalg.svd(F1)
+
+    def unpack(x):
+        Ux = Rotation.from_rotvec(x[:3]).as_matrix() @ U
+        Vx = Rotation.from_rotvec(x[3:6]).as_matrix() @ Vt.T
+        return np.outer(Ux[:, 0], Vx[:, 0]) + (s[1] / s[0] + x[6]) * np.outer(Ux[:, 1], Vx[:, 1])
+
+    sol = least_squares(lambda x: _sampson_residuals(unpack(x), npts), np.zeros(7), xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    # the LM result is (numerically) a stationary point: scipy cannot lower the cost from it by more than 1e-9 relative
+    assert (sol.fun ** 2).sum() >= (r1 ** 2).sum() * (1 - 1e-6)
+    G, W = unpack(sol.x), F1 / s[0]
+    assert np.abs(G / np.linalg.norm(G) - W / np.linalg.norm(W)).max() < 1e-4
+    # weights: zero-weight points do not influence the fit
+    w = np.ones(len(idx))
+    w[100:] = 0.0
+    Fa = oracle.refit_f_ba(pts, idx, weights=w)
+    pts2 = pts.copy()
+    pts2[100:150, 2:] += 50.0
+    Fb = oracle.refit_f_ba(pts2, idx, weights=w)
+    # (the Hartley normalisation sees the moved points, so the frames differ: compare the fits on the weighted points)
+    ra, rb = _sampson_residuals(Fa, pts[:100]), _sampson_residuals(Fb, pts[:100])
+    assert abs((ra ** 2).sum() - (rb ** 2).sum()) < 0.05 * (ra ** 2).sum()
