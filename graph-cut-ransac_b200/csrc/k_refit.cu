@@ -47,6 +47,7 @@ struct RefitArgs
 	int weight_mode;
 	double *models; // [count][R][9], R = gcr_max_refit_models(problem)
 	uint8_t *ok;    // [count][R]
+	int ba_frame;   // F only: 0 = linear 8-point fit; GCR_BA_HARTLEY / GCR_BA_PIXEL = + LM bundle adjustment in that frame
 };
 
 // fixed-tree block sum of NV values per thread; result valid in out[] for every thread after the call
@@ -116,7 +117,9 @@ __device__ bool gauss8(double M[8][9], double *h)
 }
 
 // Eigen FullPivHouseholderQR(M).matrixQ().rightCols<1>() for a 9 x 9 row-major M (destroyed)
-__device__ void fullpiv_householder_q_lastcol9(double *M, double *q)
+// __noinline__: inlined into the bundle-adjustment instantiations of k_refit, nvcc 12.9 -O3 produced a kernel whose
+// Householder vectors were garbage for a correct A^T A (observed on B200; the stand-alone function is correct)
+__device__ __noinline__ void fullpiv_householder_q_lastcol9(double *M, double *q)
 {
 	const int n = 9;
 	int rowswap[9];
@@ -180,7 +183,314 @@ __device__ void fullpiv_householder_q_lastcol9(double *M, double *q)
 	}
 }
 
-template <int PROBLEM>
+// ---- LM bundle adjustment of F (relative_pose/bundle.cpp:253-339 lm_F_impl, relative_pose/jacobian_impl.h:472-606) ----
+// One CTA per index set: the point sums (cost; 28 + 7 entries of J^T J, J^T r) are strided over the threads and meet in
+// the fixed-tree block_sum; thread 0 does the 7 x 7 damped Cholesky step and the Lie update of U, V.  Same statements
+// as oracle/gcr_oracle_f.cpp (gcro_refine_f_lm), summation order aside.
+__device__ void jacobi_svd3(const double *A_in, double *U, double *s, double *V)
+{
+	// one-sided Jacobi, columns of A rotated until orthogonal: A = U diag(s) V^T, s descending (oracle/linalg.h jacobi_svd)
+	double A[9], Vt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	for (int i = 0; i < 9; ++i) A[i] = A_in[i];
+	for (int sweep = 0; sweep < 100; ++sweep)
+	{
+		bool rotated = false;
+		for (int p = 0; p < 2; ++p)
+			for (int q = p + 1; q < 3; ++q)
+			{
+				double alpha = 0, beta = 0, gamma = 0;
+				for (int i = 0; i < 3; ++i)
+				{
+					const double ap = A[3 * i + p], aq = A[3 * i + q];
+					alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
+				}
+				if (fabs(gamma) <= 1e-17 * sqrt(alpha * beta) || gamma == 0.0)
+					continue;
+				rotated = true;
+				const double zeta = (beta - alpha) / (2.0 * gamma);
+				const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+				const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+				for (int i = 0; i < 3; ++i)
+				{
+					const double ap = A[3 * i + p], aq = A[3 * i + q];
+					A[3 * i + p] = c * ap - sn * aq;
+					A[3 * i + q] = sn * ap + c * aq;
+					const double vp = Vt[3 * i + p], vq = Vt[3 * i + q];
+					Vt[3 * i + p] = c * vp - sn * vq;
+					Vt[3 * i + q] = sn * vp + c * vq;
+				}
+			}
+		if (!rotated)
+			break;
+	}
+	double sv[3];
+	int order[3] = {0, 1, 2};
+	for (int j = 0; j < 3; ++j)
+		sv[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+	for (int a = 0; a < 2; ++a) // stable descending sort of three
+		for (int b = 0; b < 2 - a; ++b)
+			if (sv[order[b]] < sv[order[b + 1]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+	for (int c = 0; c < 3; ++c)
+	{
+		const int o = order[c];
+		s[c] = sv[o];
+		for (int i = 0; i < 3; ++i)
+		{
+			U[3 * i + c] = sv[o] > 0 ? A[3 * i + o] / sv[o] : 0.0;
+			V[3 * i + c] = Vt[3 * i + o];
+		}
+	}
+}
+
+__device__ __forceinline__ void factorized_f(const double *U, const double *V, double sigma, double *F)
+{
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c)
+			F[3 * r + c] = U[3 * r] * V[3 * c] + sigma * U[3 * r + 1] * V[3 * c + 1];
+}
+
+// M <- M + (sin(t) [w]x + (1 - cos(t)) [w]x^2) M, t = |w| (bundle.cpp:290-316)
+__device__ void lie_update3(const double *w3, const double *M, double *out)
+{
+	double w[3] = {w3[0], w3[1], w3[2]};
+	const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+	for (int i = 0; i < 3; ++i) w[i] /= theta;
+	const double a = sin(theta), b = cos(theta);
+	const double sw[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+	double sw2[9], R[9], RM[9];
+	mul3(sw, sw, sw2);
+	for (int i = 0; i < 9; ++i) R[i] = a * sw[i] + (1 - b) * sw2[i];
+	mul3(R, M, RM);
+	for (int i = 0; i < 9; ++i) out[i] = M[i] + RM[i];
+}
+
+struct BaFrame { double msx, msy, mdx, mdy, rs, rd; };
+
+__device__ __forceinline__ double ba_weight_of(const RefitArgs &a, const uint32_t *idx, int i)
+{
+	return !a.weights ? 1.0 : a.weight_mode == GCR_WEIGHT_BY_POINT ? a.weights[idx[i]] : a.weights[i];
+}
+
+// sum over the set of w_k * min(r_k^2, 1) for the matrix F (shared memory); every thread gets the result
+__device__ double ba_cost(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, const double *F, double *red, double *tot)
+{
+	double v[1] = {0.0};
+	for (int i = threadIdx.x; i < n; i += RF_THREADS)
+	{
+		const double *p = a.pts + (size_t)idx[i] * 4;
+		const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
+		const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+		const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+		const double Ft0 = F[0] * x2 + F[3] * y2 + F[6], Ft1 = F[1] * x2 + F[4] * y2 + F[7];
+		const double nJc_sq = (Fx0 * Fx0 + Fx1 * Fx1) + (Ft0 * Ft0 + Ft1 * Ft1);
+		const double r2 = (C * C) / nJc_sq;
+		const double loss = fmin(r2, 1.0);
+		v[0] += a.weights ? ba_weight_of(a, idx, i) * loss : loss;
+	}
+	block_sum<1>(v, red, tot);
+	const double c = tot[0];
+	__syncthreads();
+	return c;
+}
+
+// refines sh->F in place (shared memory); all threads of the CTA call it
+struct BaShared
+{
+	double F[9], U[9], V[9], Un[9], Vn[9], Fn[9], JtJ[49], Jtr[7], sigma, sigman, lambda;
+	int flag; // 0 go on, 1 stop
+};
+
+__device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, BaShared *sh, double *red, double *tot,
+                            int max_iterations)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0)
+	{
+		double s[3];
+		jacobi_svd3(sh->F, sh->U, s, sh->V); // FactorizedFundamentalMatrix(F) (jacobian_impl.h:474-480)
+#ifdef GCR_BA_DEBUG
+		if (blockIdx.x == 0) printf("svd s %g %g %g U %g %g V %g %g\n", s[0], s[1], s[2], sh->U[0], sh->U[1], sh->V[0], sh->V[1]);
+#endif
+		sh->sigma = s[1] / s[0];
+		factorized_f(sh->U, sh->V, sh->sigma, sh->F);
+		sh->lambda = 1e-3;
+		sh->flag = 0;
+	}
+	__syncthreads();
+	double cost = ba_cost(a, idx, n, fr, sh->F, red, tot);
+#ifdef GCR_BA_DEBUG
+	if (tid == 0 && blockIdx.x == 0) printf("BA init: n %d sigma %g cost %g F %g %g %g\n", n, sh->sigma, cost, sh->F[0], sh->F[4], sh->F[8]);
+#endif
+	bool recompute_jac = true;
+	for (int iter = 0; iter < max_iterations; ++iter)
+	{
+		if (recompute_jac)
+		{
+			const double *F = sh->F;
+			double ds[9];
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c)
+					ds[3 * r + c] = sh->U[3 * r + 1] * sh->V[3 * c + 1];
+#define F_(r, c) F[3 * (r) + (c)]
+#define D_(r, c) ds[3 * (r) + (c)]
+			const double dFdp[9][7] = {
+			    {0, F_(2, 0), -F_(1, 0), 0, F_(0, 2), -F_(0, 1), D_(0, 0)},
+			    {-F_(2, 0), 0, F_(0, 0), 0, F_(1, 2), -F_(1, 1), D_(1, 0)},
+			    {F_(1, 0), -F_(0, 0), 0, 0, F_(2, 2), -F_(2, 1), D_(2, 0)},
+			    {0, F_(2, 1), -F_(1, 1), -F_(0, 2), 0, F_(0, 0), D_(0, 1)},
+			    {-F_(2, 1), 0, F_(0, 1), -F_(1, 2), 0, F_(1, 0), D_(1, 1)},
+			    {F_(1, 1), -F_(0, 1), 0, -F_(2, 2), 0, F_(2, 0), D_(2, 1)},
+			    {0, F_(2, 2), -F_(1, 2), F_(0, 1), -F_(0, 0), 0, D_(0, 2)},
+			    {-F_(2, 2), 0, F_(0, 2), F_(1, 1), -F_(1, 0), 0, D_(1, 2)},
+			    {F_(1, 2), -F_(0, 2), 0, F_(2, 1), -F_(2, 0), 0, D_(2, 2)}};
+#undef F_
+#undef D_
+			double acc[35]; // lower triangle of J^T J row by row (28), then J^T r (7)
+#pragma unroll
+			for (int j = 0; j < 35; ++j) acc[j] = 0.0;
+			for (int i = tid; i < n; i += RF_THREADS)
+			{
+				const double *p = a.pts + (size_t)idx[i] * 4;
+				const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
+				const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+				const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+				const double JC[4] = {F[0] * x2 + F[3] * y2 + F[6], F[1] * x2 + F[4] * y2 + F[7], Fx0, Fx1};
+				const double nJ_C = sqrt(JC[0] * JC[0] + JC[1] * JC[1] + JC[2] * JC[2] + JC[3] * JC[3]);
+				const double inv_nJ_C = 1.0 / nJ_C;
+				const double r = C * inv_nJ_C;
+				double weight = ((r * r) < 1.0 ? 1.0 : 0.0) / n;
+				if (a.weights)
+					weight = ba_weight_of(a, idx, i) * weight;
+				if (weight == 0.0)
+					continue;
+				double dF[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0};
+				const double s = C * inv_nJ_C * inv_nJ_C;
+				dF[0] -= s * (JC[2] * x1 + JC[0] * x2);
+				dF[1] -= s * (JC[3] * x1 + JC[0] * y2);
+				dF[2] -= s * (JC[0]);
+				dF[3] -= s * (JC[2] * y1 + JC[1] * x2);
+				dF[4] -= s * (JC[3] * y1 + JC[1] * y2);
+				dF[5] -= s * (JC[1]);
+				dF[6] -= s * (JC[2]);
+				dF[7] -= s * (JC[3]);
+#pragma unroll
+				for (int q = 0; q < 9; ++q) dF[q] *= inv_nJ_C;
+				double J[7];
+#pragma unroll
+				for (int j = 0; j < 7; ++j)
+				{
+					double t = 0.0;
+#pragma unroll
+					for (int q = 0; q < 9; ++q) t += dF[q] * dFdp[q][j];
+					J[j] = t;
+				}
+				int q = 0;
+#pragma unroll
+				for (int r7 = 0; r7 < 7; ++r7)
+#pragma unroll
+					for (int c7 = 0; c7 <= r7; ++c7)
+						acc[q++] += weight * (J[r7] * J[c7]);
+#pragma unroll
+				for (int r7 = 0; r7 < 7; ++r7)
+					acc[28 + r7] += weight * C * inv_nJ_C * J[r7];
+			}
+			block_sum<35>(acc, red, tot);
+			if (tid == 0)
+			{
+				int q = 0;
+				for (int r7 = 0; r7 < 7; ++r7)
+					for (int c7 = 0; c7 <= r7; ++c7)
+						sh->JtJ[7 * r7 + c7] = tot[q++];
+				double g = 0.0;
+				for (int r7 = 0; r7 < 7; ++r7)
+				{
+					sh->Jtr[r7] = tot[28 + r7];
+					g += tot[28 + r7] * tot[28 + r7];
+				}
+				if (sqrt(g) < 1e-8) // gradient_tol
+					sh->flag = 1;
+			}
+			__syncthreads();
+			if (sh->flag)
+				break;
+		}
+		if (tid == 0)
+		{
+			for (int k = 0; k < 7; ++k) sh->JtJ[7 * k + k] += sh->lambda;
+			// sol = -(L L^T)^-1 Jtr from the lower triangle; NaNs propagate if it is not positive definite (Eigen's llt().solve)
+			double L[49], y[7], sol[7];
+			for (int j = 0; j < 7; ++j)
+			{
+				double d = sh->JtJ[7 * j + j];
+				for (int k = 0; k < j; ++k) d -= L[7 * j + k] * L[7 * j + k];
+				d = sqrt(d);
+				L[7 * j + j] = d;
+				for (int i = j + 1; i < 7; ++i)
+				{
+					double t = sh->JtJ[7 * i + j];
+					for (int k = 0; k < j; ++k) t -= L[7 * i + k] * L[7 * j + k];
+					L[7 * i + j] = t / d;
+				}
+			}
+			for (int i = 0; i < 7; ++i)
+			{
+				double t = sh->Jtr[i];
+				for (int k = 0; k < i; ++k) t -= L[7 * i + k] * y[k];
+				y[i] = t / L[7 * i + i];
+			}
+			for (int i = 6; i >= 0; --i)
+			{
+				double t = y[i];
+				for (int k = i + 1; k < 7; ++k) t -= L[7 * k + i] * sol[k];
+				sol[i] = t / L[7 * i + i];
+			}
+			double sn = 0.0;
+			for (int i = 0; i < 7; ++i)
+			{
+				sol[i] = -sol[i];
+				sn += sol[i] * sol[i];
+			}
+			if (sqrt(sn) < 1e-8) // step_tol
+				sh->flag = 1;
+			else
+			{
+				lie_update3(sol, sh->U, sh->Un);
+				lie_update3(sol + 3, sh->V, sh->Vn);
+				sh->sigman = sh->sigma + sol[6];
+				factorized_f(sh->Un, sh->Vn, sh->sigman, sh->Fn);
+			}
+		}
+		__syncthreads();
+		if (sh->flag)
+			break;
+		const double cost_new = ba_cost(a, idx, n, fr, sh->Fn, red, tot);
+		const bool accept = cost_new < cost; // the same value in every thread
+#ifdef GCR_BA_DEBUG
+		if (tid == 0 && blockIdx.x == 0) printf("BA it %d: cost %g new %g lambda %g Jtr0 %g JtJ00 %g sigman %g\n", iter, cost, cost_new, sh->lambda, sh->Jtr[0], sh->JtJ[0], sh->sigman);
+#endif
+		if (tid == 0)
+		{
+			if (accept)
+			{
+				for (int i = 0; i < 9; ++i) { sh->U[i] = sh->Un[i]; sh->V[i] = sh->Vn[i]; sh->F[i] = sh->Fn[i]; }
+				sh->sigma = sh->sigman;
+				sh->lambda /= 10;
+			}
+			else
+			{
+				for (int k = 0; k < 7; ++k) sh->JtJ[7 * k + k] -= sh->lambda;
+				sh->lambda *= 10;
+			}
+		}
+		if (accept)
+			cost = cost_new;
+		recompute_jac = accept;
+		__syncthreads();
+	}
+	__syncthreads();
+}
+
+template <int PROBLEM, int BA = 0>
 __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 {
 	constexpr int NV = PROBLEM == GCR_H ? 44 : 45;
@@ -199,7 +509,9 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 		}
 		return;
 	}
+	constexpr bool pixel_frame = PROBLEM == GCR_F && BA == GCR_BA_PIXEL; // the post-run polish fits in pixels
 	// ---- normalizePoints: centroids ----
+	if (!pixel_frame)
 	{
 		double v[4] = {0, 0, 0, 0};
 		for (int i = tid; i < n; i += RF_THREADS)
@@ -209,9 +521,11 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 		}
 		block_sum<4>(v, red, tot);
 	}
-	const double msx = tot[0] / n, msy = tot[1] / n, mdx = tot[2] / n, mdy = tot[3] / n;
+	const double msx = pixel_frame ? 0.0 : tot[0] / n, msy = pixel_frame ? 0.0 : tot[1] / n, mdx = pixel_frame ? 0.0 : tot[2] / n,
+	             mdy = pixel_frame ? 0.0 : tot[3] / n;
 	__syncthreads();
 	// ---- mean distances ----
+	if (!pixel_frame)
 	{
 		double v[2] = {0, 0};
 		for (int i = tid; i < n; i += RF_THREADS)
@@ -223,7 +537,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 		}
 		block_sum<2>(v, red, tot);
 	}
-	const double rs = 1.4142135623730951 / (tot[0] / n), rd = 1.4142135623730951 / (tot[1] / n);
+	const double rs = pixel_frame ? 1.0 : 1.4142135623730951 / (tot[0] / n), rd = pixel_frame ? 1.0 : 1.4142135623730951 / (tot[1] / n);
 	__syncthreads();
 	const double T1[9] = {rs, 0, -rs * msx, 0, rs, -rs * msy, 0, 0, 1};
 	const double T2[9] = {rd, 0, -rd * mdx, 0, rd, -rd * mdy, 0, 0, 1};
@@ -295,6 +609,60 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 		}
 	}
 	block_sum<NV>(acc, red, tot);
+	if (PROBLEM == GCR_F && BA != 0)
+	{
+		// FundamentalMatrixBundleAdjustmentSolver::estimateModel (solver_fundamental_matrix_bundle_adjustment.h:113-177):
+		// the 8-point model initialises the LM refinement, in the same frame
+		__shared__ BaShared ba;
+		if (tid == 0)
+		{
+			double AtA[81];
+			int q = 0;
+			for (int r = 0; r < 9; ++r)
+				for (int c = r; c < 9; ++c)
+				{
+					AtA[9 * r + c] = tot[q];
+					AtA[9 * c + r] = tot[q];
+					++q;
+				}
+#ifdef GCR_BA_DEBUG
+			if (blockIdx.x == 0) printf("AtA %g %g %g tot44 %g n %d rs %g\n", AtA[0], AtA[1], AtA[80], tot[44], n, rs);
+#endif
+			double f[9];
+			fullpiv_householder_q_lastcol9(AtA, f);
+			for (int i = 0; i < 9; ++i) ba.F[i] = f[i];
+#ifdef GCR_BA_DEBUG
+			if (blockIdx.x == 0) printf("f %g %g %g %g\n", ba.F[0], ba.F[1], ba.F[4], ba.F[8]);
+#endif
+		}
+		__syncthreads();
+		const BaFrame fr = {msx, msy, mdx, mdy, rs, rd};
+		ba_refine_f(a, idx, n, fr, &ba, red, tot, 25);
+		if (tid != 0)
+			return;
+		double out[9];
+		bool ok = true;
+		if (pixel_frame)
+			for (int i = 0; i < 9; ++i) out[i] = ba.F[i];
+		else
+		{
+			const double T2t[9] = {T2[0], T2[3], T2[6], T2[1], T2[4], T2[7], T2[2], T2[5], T2[8]};
+			double tmp[9];
+			mul3(T2t, ba.F, tmp);
+			mul3(tmp, T1, out);
+			double nrm = 0.0;
+			for (int i = 0; i < 9; ++i) nrm += out[i] * out[i];
+			nrm = sqrt(nrm);
+			for (int i = 0; i < 9; ++i) out[i] /= nrm;
+			if (out[8] < 0)
+				for (int i = 0; i < 9; ++i) out[i] = -out[i];
+		}
+		for (int i = 0; i < 9; ++i)
+			if (isnan(out[i])) ok = false;
+		for (int j = 0; j < 9; ++j) a.models[(size_t)set * 9 + j] = ok ? out[j] : 0.0;
+		a.ok[set] = ok ? 1 : 0;
+		return;
+	}
 	if (tid != 0)
 		return;
 
@@ -581,9 +949,31 @@ extern "C" int gcr_max_refit_models(int problem)
 	return problem == GCR_E ? RF_E_MODELS : (problem == GCR_H || problem == GCR_F) ? 1 : 0;
 }
 
+static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets,
+                               const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count,
+                               const double *d_weights, int weight_mode, int ba_frame, double *d_models, uint8_t *d_ok);
+
 extern "C" gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets,
                                 const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count,
                                 const double *d_weights, int weight_mode, double *d_models, uint8_t *d_ok)
+{
+	return refit_launch(ctx, problem, pair, d_index_sets, d_set_offsets, d_set_sizes, count, d_weights, weight_mode, 0, d_models, d_ok);
+}
+
+extern "C" gcr_status gcr_refit_f_ba(gcr_ctx *ctx, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
+                                     const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode,
+                                     int frame, double *d_models, uint8_t *d_ok)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (frame != GCR_BA_HARTLEY && frame != GCR_BA_PIXEL)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_f_ba: frame must be GCR_BA_HARTLEY or GCR_BA_PIXEL");
+	return refit_launch(ctx, GCR_F, pair, d_index_sets, d_set_offsets, d_set_sizes, count, d_weights, weight_mode, frame, d_models, d_ok);
+}
+
+static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets,
+                               const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count,
+                               const double *d_weights, int weight_mode, int ba_frame, double *d_models, uint8_t *d_ok)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
@@ -605,10 +995,15 @@ extern "C" gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint3
 	a.weight_mode = weight_mode;
 	a.models = d_models;
 	a.ok = d_ok;
+	a.ba_frame = ba_frame;
 	if (problem == GCR_H)
 		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else if (problem == GCR_E)
 		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	else if (ba_frame == GCR_BA_HARTLEY)
+		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	else if (ba_frame == GCR_BA_PIXEL)
+		k_refit<GCR_F, GCR_BA_PIXEL><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else
 		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);

@@ -18,6 +18,8 @@ WEIGHT_NONE, WEIGHT_POSITIONAL, WEIGHT_BY_POINT = 0, 1, 2
 SCORE_EXACT_COUNTS = 1
 
 # every symbol include/gcr/gcr.h declares (tests check the library exports all of them)
+BA_HARTLEY, BA_PIXEL = 1, 2
+
 EXPORTS = [
     "gcr_ctx_create", "gcr_ctx_destroy", "gcr_ctx_set_stream", "gcr_sync", "gcr_last_error", "gcr_version",
     "gcr_device_info", "gcr_launch_count", "gcr_malloc", "gcr_free", "gcr_memcpy_h2d", "gcr_memcpy_d2h", "gcr_memset",
@@ -26,7 +28,7 @@ EXPORTS = [
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
-    "gcr_solve_plane_parallax",
+    "gcr_solve_plane_parallax", "gcr_refit_f_ba",
 ]
 
 _lib = None
@@ -79,6 +81,7 @@ def load_library():
         "gcr_key_score": (C.c_float, [u64]),
         "gcr_key_index": (u32, [u64]),
         "gcr_refit": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp]),
+        "gcr_refit_f_ba": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp]),
         "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
         "gcr_round_results": (i32, [vp, vp, vp]),
@@ -314,7 +317,8 @@ class Context:
         return float(self.lib.gcr_key_score(int(key))), int(self.lib.gcr_key_index(int(key)))
 
     # ---- K6 ----
-    def refit(self, problem, index_sets, weights=None, weight_mode=WEIGHT_NONE, pair=0):
+    def refit(self, problem, index_sets, weights=None, weight_mode=WEIGHT_NONE, pair=0, ba_frame=0):
+        """ba_frame (F only): 0 = the linear fit; BA_HARTLEY / BA_PIXEL = + the LM bundle adjustment (gcr_refit_f_ba)."""
         sizes = np.array([len(s) for s in index_sets], dtype=np.uint32)
         offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint32)
         flat = np.concatenate([np.asarray(s, dtype=np.uint32) for s in index_sets]).astype(np.uint32)
@@ -325,9 +329,14 @@ class Context:
         dm = self.malloc(count * R * 9 * 8)
         dok = self.malloc(count * R)
         try:
-            self.check(self.lib.gcr_refit(self.h, problem, pair, C.c_void_p(d_flat), C.c_void_p(d_off), C.c_void_p(d_sz),
-                                          count, C.c_void_p(d_w) if d_w else None, weight_mode, C.c_void_p(dm),
-                                          C.c_void_p(dok)))
+            if ba_frame:
+                self.check(self.lib.gcr_refit_f_ba(self.h, pair, C.c_void_p(d_flat), C.c_void_p(d_off), C.c_void_p(d_sz), count,
+                                                   C.c_void_p(d_w) if d_w else None, weight_mode, ba_frame, C.c_void_p(dm),
+                                                   C.c_void_p(dok)))
+            else:
+                self.check(self.lib.gcr_refit(self.h, problem, pair, C.c_void_p(d_flat), C.c_void_p(d_off), C.c_void_p(d_sz),
+                                              count, C.c_void_p(d_w) if d_w else None, weight_mode, C.c_void_p(dm),
+                                              C.c_void_p(dok)))
             if R == 1:
                 return self.to_host(dm, (count, 3, 3), np.float64), self.to_host(dok, (count,), np.uint8)
             return self.to_host(dm, (count, R, 3, 3), np.float64), self.to_host(dok, (count, R), np.uint8)

@@ -168,6 +168,18 @@ uint32_t gcr_key_index(uint64_t key);
 gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
                      const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode,
                      double *d_models, uint8_t *d_ok);
+/* The reference's DEFAULT non-minimal F fit (types.h:78-80): FundamentalMatrixBundleAdjustmentSolver
+ * (estimators/solver_fundamental_matrix_bundle_adjustment.h:113-177) -- the 8-point model refined by the LM bundle
+ * adjustment of relative_pose/bundle.cpp:253-339 (F = U diag(1, sigma, 0) V^T, Sampson residual, truncated loss,
+ * <= 25 iterations, relative_pose/jacobian_impl.h:472-606).  frame = GCR_BA_HARTLEY: as called through
+ * FundamentalMatrixEstimator::estimateModelNonminimal (fundamental_estimator.h:574-618: both steps on Hartley-normalised
+ * points, result de-normalised); GCR_BA_PIXEL: the solver called on pixel coordinates, the post-run polish of
+ * findFundamentalMatrix_ (py/gcransac_python.cpp:1851-1858; result not rescaled).  Sets with fewer than 8 points: ok = 0. */
+#define GCR_BA_HARTLEY 1
+#define GCR_BA_PIXEL 2
+gcr_status gcr_refit_f_ba(gcr_ctx *ctx, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
+                          const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode, int frame,
+                          double *d_models, uint8_t *d_ok);
 int gcr_max_refit_models(int problem);
 
 /* ---- K7 grid neighbourhood -------------------------------------------------------------------------------- */

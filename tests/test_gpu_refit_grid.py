@@ -76,6 +76,36 @@ def test_refit_f8_matches_oracle(gcr_ctx, oracle):
     assert ok[0] and _up_to_scale(oracle.refit(O.F, pts, sets[-1], weights=w), got[0]) < RTOL_MODEL
 
 
+def test_refit_f_bundle_adjustment_matches_oracle(gcr_ctx, oracle):
+    """K6 + LM bundle adjustment (gcr_refit_f_ba: the reference's default non-minimal F fit, 8-point + lm_F_impl) against
+    the oracle's restatement: Hartley frame as the estimator calls it, pixel frame as the post-run polish does, weights."""
+    pts, Fm, Em, Kc, inl = synth.epipolar_pair(2500, 0.4, seed=54)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(5)
+    inl_idx = np.nonzero(inl)[0]
+    sets = _index_sets(rng, inl_idx, [49] * 20 + [8, 9, 15, 300, len(inl_idx)])
+    sets.append(rng.choice(2500, size=49, replace=False).astype(np.uint32))                  # outliers mixed in
+    sets.append(inl_idx[:7].astype(np.uint32))                                               # n < 8: no model
+    models, ok = gcr_ctx.refit(_cabi.F, sets, ba_frame=_cabi.BA_HARTLEY)
+    plain, _ = gcr_ctx.refit(_cabi.F, sets)
+    worst, moved = 0.0, 0.0
+    for s, mdl, lin, k in zip(sets, models, plain, ok):
+        want = oracle.refit_f_ba(pts, s)
+        assert bool(k) == (want is not None)
+        if want is not None:
+            worst = max(worst, _up_to_scale(want, mdl))
+            moved = max(moved, _up_to_scale(lin, mdl))
+            assert abs(np.linalg.det(mdl / np.linalg.norm(mdl))) < 1e-12                      # rank 2 after the refinement
+    assert worst < RTOL_MODEL, worst
+    assert moved > 1e-6                                                                       # the refinement does something
+    w = rng.uniform(0.05, 1.0, size=2500)
+    got, ok = gcr_ctx.refit(_cabi.F, [sets[24]], weights=w, weight_mode=_cabi.WEIGHT_POSITIONAL, ba_frame=_cabi.BA_HARTLEY)
+    assert ok[0] and _up_to_scale(oracle.refit_f_ba(pts, sets[24], weights=w), got[0]) < RTOL_MODEL
+    # the post-run polish (py/gcransac_python.cpp:1832-1858): pixel frame, weights 1 - r^2 / T by inlier position
+    got, ok = gcr_ctx.refit(_cabi.F, [sets[24]], weights=w, weight_mode=_cabi.WEIGHT_POSITIONAL, ba_frame=_cabi.BA_PIXEL)
+    assert ok[0] and _up_to_scale(oracle.refit_f_ba(pts, sets[24], weights=w, polish=True), got[0]) < RTOL_MODEL
+
+
 def _e_set_distance(got, want):
     """every model of `got` has a partner in `want` (normalised, E33 >= 0 on both sides): worst partner distance"""
     return max(min(np.abs(E - q).max() for q in want) for E in got) if len(got) else 0.0
