@@ -41,7 +41,8 @@ WORKLOADS = {
                 desc="E 5-pt (Nister) + MAGSAC++, N=2048, 85% outliers, known K, thr 0.75 px / f, single pair (configs[2])"),
     # full pipelines (adaptive stop, LO, graph-cut, IRLS, final fit) through pygcransac.find*: image pairs / s
     "f4k_pairs": dict(problem="f", n=4096, outliers=0.5, thr=0.75, pairs=128, pipeline=True,
-                      desc="findFundamentalMatrix full pipeline (7-pt + MSAC, LO + graph-cut, conf 0.99), N=4096, 50% "
+                      desc="findFundamentalMatrix full default pipeline (7-pt + MSAC, LO + graph-cut with BA refits, DEGENSAC, "
+                           "post-run BA, conf 0.99), N=4096, 50% "
                            "outliers, thr 0.75 px, distinct synthetic pairs (configs[1] pipeline)"),
     "h2k_pairs": dict(problem="h", n=2048, outliers=0.3, thr=3.0, pairs=128, pipeline=True,
                       desc="findHomography full pipeline (4-pt + MSAC, LO + graph-cut, conf 0.99), N=2048, 30% outliers, "
@@ -224,8 +225,10 @@ def _pairs_cpu_worker(args):
     eps = np.finfo(np.float64).eps if problem == "h" else 0.0
     cs = np.array([(1024 + eps) / 4.0] * 4)
     t0 = time.perf_counter()
+    # F: the reference's default pipeline on both arms -- BA non-minimal solver, DEGENSAC, post-run bundle adjustment
     out = _CPU_IMPL["ref"].run(O.H if problem == "h" else O.F, pts, cs, 4, thr, conf=0.99, spatial_weight=weight,
-                               max_iters=10000, min_iters=50, lo_number=50, seed=seed)
+                               max_iters=10000, min_iters=50, lo_number=50, seed=seed, use_degensac=problem == "f",
+                               f_ba=3 if problem == "f" else 0)
     return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
 
 

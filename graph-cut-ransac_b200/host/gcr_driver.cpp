@@ -456,7 +456,7 @@ namespace
 		// ---- non-minimal refit of `count` index sets (one GPU launch) ----
 		bool refit(const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
 		           const double *weights_by_point, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
-		           bool sets_on_device = false, int refit_problem = -1)
+		           bool sets_on_device = false, int refit_problem = -1, int ba_frame_override = 0)
 		{
 			const int rp = refit_problem < 0 ? problem : refit_problem;
 			const int rm = refit_problem < 0 ? this->rm : gcr_max_refit_models(rp);
@@ -485,8 +485,18 @@ namespace
 					return fail("gcr_memcpy_h2d");
 				d_w = d_weights.as<double>();
 			}
-			if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
-			              weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
+			// the reference's default F estimator refines every non-minimal fit by bundle adjustment (types.h:78-80); DEGENSAC's
+			// inner estimator (variant 1) keeps the bare 8-point solver (fundamental_estimator.h:532-533)
+			const int ba_frame = ba_frame_override ? ba_frame_override
+			                                       : (rp == GCR_F && variant == 0 && (S.f_bundle_adjustment & 1)) ? GCR_BA_HARTLEY : 0;
+			if (ba_frame)
+			{
+				if (gcr_refit_f_ba(ctx, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w, weight_mode,
+				                   ba_frame, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
+					return fail("gcr_refit_f_ba");
+			}
+			else if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
+			                   weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_refit");
 			models.resize((size_t)count * rm * 9);
 			ok.resize((size_t)count * rm);
@@ -873,10 +883,39 @@ namespace
 					}
 				}
 			}
+			st.score = best.value;
+			if (problem == GCR_F && !nested && (S.f_bundle_adjustment & 2) && buf[offset].idx.size() > 7)
+			{
+				// the post-run bundle adjustment of findFundamentalMatrix_ (py/gcransac_python.cpp:1832-1887)
+				std::vector<uint32_t> &inl = buf[offset].idx;
+				std::vector<double> r2, weights(inl.size(), 0.0), models;
+				std::vector<uint8_t> ok;
+				Score s;
+				if (!exact(best_model, s, nullptr, &r2))
+					return -1;
+				for (size_t k = 0; k < inl.size(); ++k)
+					weights[k] = std::max(0.0, 1.0 - r2[inl[k]] / T);
+				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inl.size());
+				if (!refit(inl.data(), offsets, sizes, weights.data(), GCR_WEIGHT_POSITIONAL, models, ok, false, GCR_F, GCR_BA_PIXEL))
+					return -1;
+				if (ok[0])
+				{
+					const int idx2 = (offset + 1) % 2;
+					Score cur;
+					buf[idx2].lazy = false;
+					if (!exact(models.data(), cur, &buf[idx2].idx))
+						return -1;
+					if (st.score < cur.value) // :1877
+					{
+						memcpy(best_model, models.data(), 9 * sizeof(double));
+						st.score = cur.value;
+						offset = idx2;
+					}
+				}
+			}
 			for (uint32_t i : buf[offset].idx)
 				inlier_mask[i] = 1;
 			memcpy(model_out, best_model, sizeof(best_model));
-			st.score = best.value;
 			return (int)buf[offset].idx.size();
 		}
 	};
@@ -905,6 +944,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->seed = 1;
 	s->batch = 1024;
 	s->use_degensac = 0;
+	s->f_bundle_adjustment = 0;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

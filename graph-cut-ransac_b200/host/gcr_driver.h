@@ -50,6 +50,10 @@ typedef struct gcr_run_settings
 	/* FundamentalMatrixEstimator(minimum_inlier_ratio_in_validity_check = 0.5, use_degensac = true,
 	 * homography_threshold = 2.0) (fundamental_estimator.h:91-93); F only */
 	int use_degensac;
+	/* F: bit 0 = FundamentalMatrixBundleAdjustmentSolver as the non-minimal solver (the reference's default estimator,
+	 * types.h:78-80; gcr_refit_f_ba in the Hartley frame), bit 1 = the post-run polish of findFundamentalMatrix_
+	 * (py/gcransac_python.cpp:1832-1887; pixel frame) */
+	int f_bundle_adjustment;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats

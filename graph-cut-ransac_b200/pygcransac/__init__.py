@@ -35,7 +35,7 @@ class RunSettings(C.Structure):
                 ("max_graph_cut_number", C.c_uint64), ("max_least_squares_iterations", C.c_uint64),
                 ("max_unsuccessful_model_generations", C.c_uint64), ("do_local_optimization", C.c_int),
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
-                ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int)]
+                ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -85,7 +85,7 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
-          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False):
+          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
     min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
@@ -112,6 +112,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         s.cell_sizes[i] = (v + eps) / max(cells, 1)
     s.seed = seed
     s.use_degensac = 1 if use_degensac else 0
+    s.f_bundle_adjustment = f_bundle_adjustment
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()
@@ -143,14 +144,16 @@ def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=
 def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
                           spatial_coherence_weight=0.0, max_iters=10000, min_iters=50, use_sprt=True,
                           min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=1, neighborhood_size=20.0,
-                          lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, use_degensac=True):
-    """py/bindings.cpp:279-400, 1003-1022 -> findFundamentalMatrix_ (py/gcransac_python.cpp:1600-1921), with the
-    linear 8-point non-minimal solver (the reference's default wraps it in an LM polish: SURVEY.md 8f N2, out of
-    scope).  DEGENSAC (fundamental_estimator.h:341-572) is on, as in the reference's default-constructed estimator
-    (py/gcransac_python.cpp:1705); `use_degensac=False` (not a reference argument) switches it off."""
+                          lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, use_degensac=True,
+                          bundle_adjustment=True):
+    """py/bindings.cpp:279-400, 1003-1022 -> findFundamentalMatrix_ (py/gcransac_python.cpp:1600-1921) with the
+    reference's default estimator (types.h:78-80): 7-point minimal solver, non-minimal fits = 8-point + LM bundle
+    adjustment (gcr_refit_f_ba), DEGENSAC (fundamental_estimator.h:341-572), and the post-run bundle adjustment on the
+    inliers (py/gcransac_python.cpp:1832-1887).  `use_degensac=False` / `bundle_adjustment=False` (not reference
+    arguments) switch those parts off (linear 8-point non-minimal fits, no polish)."""
     return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device,
-                 use_degensac=use_degensac)
+                 use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0)
 
 
 def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,

@@ -63,6 +63,7 @@ namespace
 		typedef ProblemTraits<PROBLEM> T;
 		double f_min_ratio = PROBLEM == GCRO_FPP ? 0.0 : 0.5; // minimum_inlier_ratio_in_validity_check (:91; inner run: 0.0, :540)
 		bool use_degensac = false;
+		bool f_nonminimal_ba = false; // F: FundamentalMatrixBundleAdjustmentSolver instead of the bare 8-point solver (types.h:78-80)
 		const double *pp_homography = nullptr; // GCRO_FPP: the plane homography (setHomography, :542)
 		uint64_t seed = 1;                      // DEGENSAC's inner run draws from streams keyed by (seed, inner run number)
 		mutable uint64_t degensac_runs = 0, degensac_updates = 0;
@@ -137,7 +138,10 @@ namespace
 			int count = 0;
 			if constexpr (PROBLEM == GCRO_H)
 				count = gcro_refit_h(pts, s.data(), (int)sample_number_, weights_, out);
-			else if constexpr (PROBLEM == GCRO_F || PROBLEM == GCRO_FPP)
+			else if constexpr (PROBLEM == GCRO_F)
+				count = f_nonminimal_ba ? gcro_refit_f_ba(pts, s.data(), (int)sample_number_, weights_, out)
+				                        : gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
+			else if constexpr (PROBLEM == GCRO_FPP)
 				count = gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
 			else if constexpr (PROBLEM == GCRO_E)
 				count = gcro_refit_e(pts, s.data(), (int)sample_number_, weights_, out);
@@ -458,12 +462,13 @@ namespace
 	template <int PROBLEM, class Scoring>
 	int run_reference(const cv::Mat &points, const cv::Mat &grid_points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
 	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
-	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0)
+	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0, int f_ba = 0)
 	{
 		typedef OracleEstimator<PROBLEM> Est;
 		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
 		Est estimator;
 		estimator.use_degensac = use_degensac != 0;
+		estimator.f_nonminimal_ba = (f_ba & 1) != 0;
 		estimator.seed = seed;
 		std::vector<double> cs(cell_sizes, cell_sizes + 4);
 		Grid graph(&grid_points, cs, (size_t)cells_per_axis); // E: built on the pixel coordinates (py/gcransac_python.cpp:2592-2600)
@@ -479,7 +484,38 @@ namespace
 		gcransac.settings.min_iteration_number = min_iters;
 		gcransac.settings.neighborhood_sphere_radius = cells_per_axis;
 		gcransac.run(points, estimator, &main_sampler, &lo_sampler, &graph, model);
-		const utils::RANSACStatistics &st = gcransac.getRansacStatistics();
+		utils::RANSACStatistics st = gcransac.getRansacStatistics();
+		if constexpr (PROBLEM == GCRO_F)
+			if ((f_ba & 2) && st.inliers.size() > 7)
+			{
+				// the post-run bundle adjustment of findFundamentalMatrix_ (py/gcransac_python.cpp:1832-1887): weights
+				// 1 - r^2 / T by inlier position, the BA solver on the pixel coordinates, the reference's own MSAC score
+				const double truncated_threshold = 3.0 / 2.0 * threshold;
+				const double squared_truncated_threshold = truncated_threshold * truncated_threshold;
+				const size_t inlier_number = st.inliers.size();
+				std::vector<double> weights(inlier_number, 0.0);
+				std::vector<uint32_t> inl(inlier_number);
+				for (size_t k = 0; k < inlier_number; ++k)
+				{
+					inl[k] = (uint32_t)st.inliers[k];
+					weights[k] = MAX(0, 1.0 - estimator.squaredResidual(points.row((int)st.inliers[k]), model) / squared_truncated_threshold);
+				}
+				double polished[9];
+				if (gcro_polish_f_ba(reinterpret_cast<const double *>(points.data), inl.data(), (int)inlier_number, weights.data(), polished))
+				{
+					Model tmp_model = from_flat(polished, 3, 3);
+					MSACScoringFunction<Est> scoring;
+					scoring.initialize(squared_truncated_threshold, points.rows);
+					std::vector<size_t> current_inliers;
+					Score score = scoring.getScore(points, tmp_model, estimator, squared_truncated_threshold, current_inliers);
+					if (st.score < score.value)
+					{
+						model.descriptor = tmp_model.descriptor;
+						st.score = score.value;
+						st.inliers.swap(current_inliers);
+					}
+				}
+			}
 		for (int i = 0; i < points.rows; ++i)
 			inlier_mask[i] = 0;
 		for (size_t idx : st.inliers)
@@ -516,11 +552,11 @@ extern "C" {
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
-            const double *grid_pts, int use_degensac)
+            const double *grid_pts, int use_degensac, int f_ba)
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
 	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
-#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac)
+#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba)
 	if (scoring_kind == 0)
 	{
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);

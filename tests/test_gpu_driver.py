@@ -75,7 +75,7 @@ def test_findfundamental_matches_reference_run(pyg, ref):
     for seed, weight in ((7, 0.0), (8, 0.1)):
         F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
                                             neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed,
-                                            use_degensac=False)
+                                            use_degensac=False, bundle_adjustment=False)
         st = pyg.last_statistics
         cs = np.array([1024 / 4.0] * 4)
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50, seed=seed)
@@ -95,7 +95,8 @@ def test_findfundamental_degensac_matches_reference_run(pyg, ref):
     for seed, plane in ((1, 0.8), (3, 0.8), (1, 0.95), (2, 0.95), (3, 0.95), (4, 0.0)):
         pts, Fm, inl, on_plane = synth.epipolar_pair_planar(1000, 0.4, plane, seed + 10)
         F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=0.0,
-                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed,
+                                            bundle_adjustment=False)
         st = pyg.last_statistics
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50,
                        seed=seed, use_degensac=True)
@@ -109,6 +110,30 @@ def test_findfundamental_degensac_matches_reference_run(pyg, ref):
         runs += st["degensac_runs"]
         updates += st["degensac_updates"]
     assert runs >= 3 and updates >= 2      # the degenerate branch and the model replacement were both exercised
+
+
+def test_findfundamental_default_estimator_matches_reference_run(pyg, ref):
+    """The reference's DEFAULT F pipeline: non-minimal fits by 8-point + LM bundle adjustment (types.h:78-80), DEGENSAC,
+    and the post-run bundle adjustment of py/gcransac_python.cpp:1832-1887 -- the GPU driver against the verbatim
+    GCRANSAC<> over the oracle estimator with the same parts switched on.  The LM sums are ordered differently on the
+    two sides (block tree vs sequential), so masks may differ on points at the threshold: a few bits of slack."""
+    cs = np.array([1024 / 4.0] * 4)
+    general = lambda t: (t[0], t[1], t[4])                                  # (pts, F, E, K, inliers) -> (pts, F, inliers)
+    for seed, (pts, Fm, inl) in enumerate([general(synth.epipolar_pair(2000, 0.5, seed=36)),
+                                           synth.epipolar_pair_planar(1000, 0.4, 0.9, seed=12)[:3],
+                                           general(synth.epipolar_pair(1200, 0.3, seed=37))], start=1):
+        F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=0.0,
+                                            neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+        st = pyg.last_statistics
+        want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50,
+                       seed=seed, use_degensac=True, f_ba=3)
+        assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert st["degensac_runs"] == want["stats"]["degensac_runs"]
+        assert (mask != want["mask"]).sum() <= 2, (seed, int(mask.sum()), int(want["mask"].sum()))
+        assert _up_to_scale(want["model"], F) < 1e-5
+        assert abs(st["score"] - want["score"]) <= 1e-5 * want["score"]
+        assert (mask & inl).sum() > 0.9 * inl.sum()
 
 
 def test_findessential_matches_reference_run(pyg, ref, oracle):
