@@ -63,6 +63,7 @@ struct gcr_ctx
 	uint64_t score_launches = 0;
 	uint64_t score_evals = 0;
 
+	unsigned long long *d_score_trace = nullptr; // gcr_set_score_trace: per-CTA timeline of the next K3 launches
 	// workspace of gcr_score (compact model list, accumulators, FP64 work list)
 	void *d_score_ws = nullptr;
 	size_t score_ws_capacity = 0;

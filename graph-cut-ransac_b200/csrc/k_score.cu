@@ -217,6 +217,7 @@ struct ScoreArgs
 	int hyps_per_item, grid;
 	double thr;
 	float band_factor;
+	unsigned long long *trace; // optional [grid][4]: SM id, first / last globaltimer tick, segments of each K3 CTA
 };
 
 // ------------------------------------------------------------------------------------------------- prepare ----
@@ -424,8 +425,15 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 			s_lut[i] = a.lut[i];
 	__syncthreads();
 
+	unsigned long long t_begin = 0, n_segments = 0;
+	if (a.trace && tid == 0)
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 	const unsigned long long n_gran = (unsigned long long)(a.n_pad / GRAN);
 	const unsigned long long W = (unsigned long long)a.prefix[a.n_pairs] * n_gran;
+	// Static stream-K split.  (A dynamic chunk queue was tried after gcr_set_score_trace showed the 5 CTAs of an SM
+	// finishing one after the other, 76 ... 269 us for equal slices -- the warp schedulers favour the older CTAs.  With
+	// the queue every CTA ended within 10 % of the others and the kernel took exactly as long: the FMA pipe runs at
+	// the same rate whether 5 warps per scheduler are resident or 1, so the staircase costs nothing.)
 	unsigned long long pos = W * blockIdx.x / gridDim.x;
 	const unsigned long long pos_end = W * (blockIdx.x + 1ull) / gridDim.x;
 	uint32_t ring = 0; // ring tiles this CTA has consumed so far: stage = ring % STAGES, parity = (ring / STAGES) & 1
@@ -691,6 +699,18 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 		ring += (uint32_t)seg_tiles;
 		if (warp_active)
 			flush();
+		++n_segments;
+	}
+	if (a.trace && tid == 0)
+	{
+		unsigned long long t_end;
+		uint32_t smid;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		a.trace[4 * blockIdx.x + 0] = smid;
+		a.trace[4 * blockIdx.x + 1] = t_begin;
+		a.trace[4 * blockIdx.x + 2] = t_end;
+		a.trace[4 * blockIdx.x + 3] = n_segments;
 	}
 }
 
@@ -961,6 +981,7 @@ gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double 
 	a.n_pairs = ctx->n_pairs;
 	a.thr = threshold;
 	a.band_factor = (float)ctx->band_factor;
+	a.trace = ctx->d_score_trace;
 	const bool exact = (flags & GCR_SCORE_EXACT_COUNTS) != 0;
 #define GCR_DISPATCH(P)                                                                   \
 	(scoring == GCR_MSAC ? launch_problem<P, GCR_MSAC>(ctx, a, exact) : launch_problem<P, GCR_MAGSAC>(ctx, a, exact))

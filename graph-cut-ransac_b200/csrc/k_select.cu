@@ -81,6 +81,13 @@ extern "C" gcr_status gcr_set_band_factor(gcr_ctx *ctx, double f)
 	ctx->band_factor = f;
 	return GCR_OK;
 }
+extern "C" gcr_status gcr_set_score_trace(gcr_ctx *ctx, uint64_t *d_trace)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	ctx->d_score_trace = (unsigned long long *)d_trace;
+	return GCR_OK;
+}
 extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 {
 	if (!ctx)

@@ -28,7 +28,7 @@ EXPORTS = [
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
-    "gcr_solve_plane_parallax", "gcr_refit_f_ba",
+    "gcr_solve_plane_parallax", "gcr_refit_f_ba", "gcr_set_score_trace",
 ]
 
 _lib = None
@@ -93,6 +93,8 @@ def load_library():
         fn.argtypes = args
     lib.gcr_set_band_factor.restype = i32
     lib.gcr_set_band_factor.argtypes = [vp, f64]
+    lib.gcr_set_score_trace.restype = i32
+    lib.gcr_set_score_trace.argtypes = [vp, vp]
     lib.gcr_set_score_variant.restype = i32
     lib.gcr_set_score_variant.argtypes = [vp, i32]
     lib.gcr_profile_enable.restype = i32

@@ -56,6 +56,9 @@ uint64_t gcr_launch_count(const gcr_ctx *ctx);
 gcr_status gcr_set_band_factor(gcr_ctx *ctx, double factor);
 /* force a scoring-kernel variant (hypotheses per thread): -1 auto, 0 R=4, 1 R=6, 2 R=8 (PnP: 0 R=2, 1 R=4) */
 gcr_status gcr_set_score_variant(gcr_ctx *ctx, int variant);
+/* per-CTA timeline of the following K3 launches: d_trace (device, >= 4 * 148 * 8 uint64, or NULL to stop) receives per
+ * CTA its SM id, first and last %globaltimer tick (ns) and the number of segments it ran (tools/k3_trace.py) */
+gcr_status gcr_set_score_trace(gcr_ctx *ctx, uint64_t *d_trace);
 /* CUDA-event timing of every K3 launch made through gcr_round / gcr_score (on the context's stream) */
 gcr_status gcr_profile_enable(gcr_ctx *ctx, int on);
 /* total K3 device time (ms), number of K3 launches and hypothesis x point evaluations they covered; resets */
