@@ -217,6 +217,7 @@ struct ScoreArgs
 	int hyps_per_item, grid;
 	double thr;
 	float band_factor;
+	int no_counts; // the main kernel ran without inlier counting: accC is all zero, finalize must not read it as "no inliers"
 	unsigned long long *trace; // optional [grid][4]: SM id, first / last globaltimer tick, segments of each K3 CTA
 };
 
@@ -397,7 +398,10 @@ __device__ __forceinline__ void amb_record(const ScoreArgs &a, size_t gslot, int
 // and no scheduler atomics -- and partial sums meet in the integer accumulators.
 #define GRAN 32
 
-template <int PROBLEM, int SCORING, int R, bool EXACT, bool SC>
+// COUNT = false: the per-model inlier counts are not wanted (gcr_round: the winner's exact count comes from K4) -- the
+// hot loop sheds its two LEA.HI per pair of evaluations; every instruction of that loop costs the scheduler two
+// dispatch cycles (packed FP32, half-rate ALU / XU pipes), so 8 of ~100 instructions are ~8 % of the kernel.
+template <int PROBLEM, int SCORING, int R, bool EXACT, bool SC, bool COUNT = true>
 __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const ScoreArgs a)
 {
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
@@ -576,8 +580,11 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 								if (SCORING == GCR_MSAC)
 								{
 									T2[q] = padd<SC>(T2[q], make_float2(fminf(v.x, 0.f), fminf(v.y, 0.f)));
-									cnt[2 * q] += __float_as_uint(v.x) >> 31; // u < 0 (generated NaNs are the positive canonical NaN)
-									cnt[2 * q + 1] += __float_as_uint(v.y) >> 31;
+									if (COUNT)
+									{
+										cnt[2 * q] += __float_as_uint(v.x) >> 31; // u < 0 (generated NaNs are the positive canonical NaN)
+										cnt[2 * q + 1] += __float_as_uint(v.y) >> 31;
+									}
 									if (EXACT) mn = fminf(mn, fminf(fabsf(v.x), fabsf(v.y)));
 								}
 								else
@@ -586,8 +593,11 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 									const float wx = magsac_weight(s_lut, v.x, th.c_idx), wy = magsac_weight(s_lut, v.y, th.c_idx);
 									const bool inx = ux <= 0.f, iny = uy <= 0.f;
 									T2[q] = padd<SC>(T2[q], make_float2(inx ? wx : 0.f, iny ? wy : 0.f));
-									cnt[2 * q] += inx ? 1u : 0u;
-									cnt[2 * q + 1] += iny ? 1u : 0u;
+									if (COUNT)
+									{
+										cnt[2 * q] += inx ? 1u : 0u;
+										cnt[2 * q + 1] += iny ? 1u : 0u;
+									}
 									if (EXACT) mn = fminf(mn, fminf(fabsf(ux), fabsf(uy)));
 								}
 							}
@@ -601,7 +611,7 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 								if (SCORING == GCR_MSAC)
 								{
 									T1[q] += fminf(v, 0.f);
-									cnt[q] += __float_as_uint(v) >> 31;
+									if (COUNT) cnt[q] += __float_as_uint(v) >> 31;
 									if (EXACT) mn = fminf(mn, fabsf(v));
 								}
 								else
@@ -610,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 									const float w = magsac_weight(s_lut, v, th.c_idx);
 									const bool in = u <= 0.f;
 									T1[q] += in ? w : 0.f;
-									cnt[q] += in ? 1u : 0u;
+									if (COUNT) cnt[q] += in ? 1u : 0u;
 									if (EXACT) mn = fminf(mn, fabsf(u));
 								}
 							}
@@ -788,8 +798,8 @@ __global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 		float score;
 		if (!present)
 			score = -1.f;
-		else if (SCORING == GCR_MSAC && c == 0)
-			score = 0.f; // scoring_function.h:221-222
+		else if (SCORING == GCR_MSAC && c == 0 && !a.no_counts)
+			score = 0.f; // scoring_function.h:221-222 (without counts: the sum over no inliers is 0 as well)
 		else
 			score = (float)((double)(long long)a.accS[g] * (1.0 / FIX_ONE));
 		a.scores[g] = score;
@@ -881,7 +891,9 @@ static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 		return st;
 	a.hyps_per_item = THREADS * R;
 	const size_t smem = (size_t)STAGES * TILE * 2 * sizeof(float4) + 64 + (SCORING == GCR_MAGSAC ? 5008 * sizeof(float) : 0);
-	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true, SC> : k_score_main<PROBLEM, SCORING, R, false, SC>;
+	a.no_counts = !exact && a.inliers == nullptr ? 1 : 0;
+	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true, SC>
+	                  : (a.no_counts ? k_score_main<PROBLEM, SCORING, R, false, SC, false> : k_score_main<PROBLEM, SCORING, R, false, SC>);
 	GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
