@@ -291,7 +291,7 @@ def bench_pairs(args, wl, rank, world):
     def one_pair(job):
         s, p = job
         M, mask = find(pts[p], 1024, 1024, 1024, 1024, [], threshold=wl["thr"], conf=0.99,
-                       spatial_coherence_weight=weight, max_iters=10000, min_iters=50, use_sprt=False, sampler=1,
+                       spatial_coherence_weight=weight, max_iters=10000, min_iters=50, use_sprt=False, sampler=0,
                        neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank)
         st = pygcransac._tls.last_statistics
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):

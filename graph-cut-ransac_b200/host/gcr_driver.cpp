@@ -335,6 +335,7 @@ namespace
 			inner.S.spatial_coherence_weight = 0;
 			inner.S.confidence = 0.99;
 			inner.S.use_degensac = 0;
+			inner.S.sampler = 0; // sampler::UniformSampler (:546)
 			inner.S.seed = S.seed + st.degensac_runs * 0xD1B54A32D192ED03ull;
 			inner.S.batch = S.batch;
 			double inner_model[9];
@@ -366,7 +367,9 @@ namespace
 			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * 9 * sizeof(double)) ||
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
-			if (gcr_sample(ctx, GCR_UNIFORM, m, first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
+			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
+			if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : GCR_UNIFORM, m, S.sampler == 1 ? first + 1 : first, B, S.seed,
+			               d_samples.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_sample");
 			if (variant == 1)
 			{
@@ -535,7 +538,7 @@ namespace
 					if (gcr_memcpy_h2d(ctx, d_pool.p, inliers.data(), inliers.size() * sizeof(uint32_t)) != GCR_OK)
 						return fail("gcr_memcpy_h2d");
 					if (gcr_sample_from_pool(ctx, d_pool.as<uint32_t>(), (uint32_t)inliers.size(), (int)sample_size, st.lo_samples,
-					                         trials, S.seed, 1u, d_sets.as<uint32_t>()) != GCR_OK)
+					                         trials, S.seed, S.sampler == 1 ? 2u : 1u, d_sets.as<uint32_t>()) != GCR_OK)
 						return fail("gcr_sample_from_pool");
 					st.lo_samples += trials;
 					std::vector<uint32_t> offsets(trials), sizes(trials, (uint32_t)sample_size);
@@ -945,6 +948,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->batch = 1024;
 	s->use_degensac = 0;
 	s->f_bundle_adjustment = 0;
+	s->sampler = 0;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

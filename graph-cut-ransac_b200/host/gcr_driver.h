@@ -54,6 +54,9 @@ typedef struct gcr_run_settings
 	 * types.h:78-80; gcr_refit_f_ba in the Hartley frame), bit 1 = the post-run polish of findFundamentalMatrix_
 	 * (py/gcransac_python.cpp:1832-1887; pixel frame) */
 	int f_bundle_adjustment;
+	/* main sampler: 0 = uniform (samplers/uniform_sampler.h), 1 = PROSAC (samplers/prosac_sampler.h: the correspondences
+	 * are ordered by quality); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
+	int sampler;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats

@@ -10,9 +10,10 @@ max-flow on the host).  There is no CPU fallback: without a CUDA device / the bu
 
 Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
 tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
-so the flags are accepted and ignored.  `sampler` must be 0/1 (uniform; the counter-based stream) -- the stateful
-samplers (2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are host-side plug-ins of the reference's virtual Sampler interface and are
-not part of this path.  `neighborhood` must be 0 (grid) when `spatial_coherence_weight` > 0 (FLANN is out of scope).
+so the flags are accepted and ignored.  `sampler` is 0 (uniform) or 1 (PROSAC, the reference's default: the
+correspondences are taken to be ordered by quality), both on the counter-based stream -- the stateful samplers
+(2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are host-side plug-ins of the reference's virtual Sampler interface and are not part of
+this path.  `neighborhood` must be 0 (grid) when `spatial_coherence_weight` > 0 (FLANN is out of scope).
 """
 import ctypes as C
 import os
@@ -35,7 +36,8 @@ class RunSettings(C.Structure):
                 ("max_graph_cut_number", C.c_uint64), ("max_least_squares_iterations", C.c_uint64),
                 ("max_unsuccessful_model_generations", C.c_uint64), ("do_local_optimization", C.c_int),
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
-                ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int)]
+                ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
+                ("sampler", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -94,7 +96,8 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     if pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
     if sampler not in (0, 1):
-        raise NotImplementedError("sampler=%d: only the uniform sampler (0/1) runs on the counter-based GPU stream" % sampler)
+        raise NotImplementedError("sampler=%d: the uniform (0) and PROSAC (1) samplers run on the counter-based GPU stream; "
+                                  "P-NAPSAC / NG-RANSAC / AR are host-side plug-ins of the reference" % sampler)
     if spatial_coherence_weight > np.finfo(np.float64).eps and neighborhood != 0:
         raise NotImplementedError("neighborhood=%d: only the grid neighbourhood (0) is built on the GPU" % neighborhood)
     lib = _load_driver()
@@ -112,6 +115,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         s.cell_sizes[i] = (v + eps) / max(cells, 1)
     s.seed = seed
     s.use_degensac = 1 if use_degensac else 0
+    s.sampler = sampler
     s.f_bundle_adjustment = f_bundle_adjustment
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)

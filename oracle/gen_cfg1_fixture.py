@@ -44,6 +44,13 @@ def main():
         runs["mask_%d" % seed] = r["mask"]
         runs["stats_%d" % seed] = np.array(list(r["stats"].values()), dtype=np.uint64)
         print("seed", seed, "inliers", r["inliers"], r["stats"])
+        # BASELINE configs[0] passes sampler=1: PROSAC over the SNN-ratio order (py/gcransac_python.cpp:4320-4323)
+        r = ref.run(O.H, pts.astype(np.float64), cs, cells, 3.0, conf=0.99, spatial_weight=0.975, max_iters=10000,
+                    min_iters=50, lo_number=50, seed=seed, sampler=1)
+        runs["prosac_model_%d" % seed] = r["model"]
+        runs["prosac_mask_%d" % seed] = r["mask"]
+        runs["prosac_stats_%d" % seed] = np.array(list(r["stats"].values()), dtype=np.uint64)
+        print("seed", seed, "PROSAC inliers", r["inliers"], r["stats"])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cfg1_matches.npz"), pts=pts, size=np.array([h1, w1, h2, w2]),
                         cell_sizes=cs, **runs)
 

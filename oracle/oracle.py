@@ -357,16 +357,17 @@ class Ref:
         lib.ref_run.restype = C.c_int
         lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
-                                _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int]
+                                _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int]
 
     def round(self, problem, scoring, pts, seed, first, count, thr):
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
-            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0):
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  f_ba (F): bit 0 = the BA non-minimal solver (the reference's default estimator),
-        bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
+        bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  sampler: 0 = uniform, 1 = PROSAC (the points
+        are taken to be ordered by quality).  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
         model = np.zeros(9)
@@ -376,7 +377,7 @@ class Ref:
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
                                  C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data,
-                                 1 if use_degensac else 0, f_ba)
+                                 1 if use_degensac else 0, f_ba, sampler)
         if n_inl < 0:
             raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
         names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",

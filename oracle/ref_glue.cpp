@@ -408,6 +408,43 @@ namespace
 		}
 	};
 
+	// PROSAC (samplers/prosac_sampler.h:207-236) on the counter-based stream: call k (from 1) returns PROSAC sample k
+	// of gcro_sample_prosac -- the growth function, subset sizes and the k = 1 quirk are pinned against the reference's
+	// own ProsacSampler (tests/golden/prosac.npz); only its random_device-seeded draws are replaced.
+	class CounterProsacSampler : public sampler::Sampler<cv::Mat, size_t>
+	{
+		uint64_t seed, next;
+		uint32_t n;
+		std::vector<uint64_t> growth;
+		std::vector<uint32_t> tmp;
+
+	public:
+		CounterProsacSampler(const cv::Mat *c, uint64_t seed_) : sampler::Sampler<cv::Mat, size_t>(c), seed(seed_), next(0), n((uint32_t)c->rows)
+		{
+			initialized = true;
+		}
+		const std::string getName() const { return "Counter-based PROSAC sampler"; }
+		void reset() {}
+		void update(const size_t *const, const size_t &, const size_t &, const double &) {}
+		bool initialize(const cv::Mat *const) { return true; }
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &, size_t *const subset_, size_t sample_size_)
+		{
+			if (sample_size_ > n)
+				return false;
+			if (growth.empty())
+			{
+				growth.resize(n);
+				gcro_prosac_growth(n, (int)sample_size_, 100000, growth.data());
+			}
+			tmp.resize(sample_size_);
+			gcro_sample_prosac(seed, ++next, n, (int)sample_size_, growth.data(), 100000, tmp.data());
+			for (size_t i = 0; i < sample_size_; ++i)
+				subset_[i] = tmp[i];
+			return true;
+		}
+	};
+
 	// fundamental_estimator.h:341-572.  The H-degenerate sample test is the restated gcro_degensac_sample_homography;
 	// the inner GC-RANSAC is the reference's own GCRANSAC<> (verbatim) over the plane-and-parallax estimator with the
 	// settings of :547-551.  The reference draws the inner samples from a fresh random_device-seeded UniformSampler
@@ -462,7 +499,8 @@ namespace
 	template <int PROBLEM, class Scoring>
 	int run_reference(const cv::Mat &points, const cv::Mat &grid_points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
 	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
-	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0, int f_ba = 0)
+	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0, int f_ba = 0,
+	                  int sampler_id = 0)
 	{
 		typedef OracleEstimator<PROBLEM> Est;
 		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
@@ -472,7 +510,12 @@ namespace
 		estimator.seed = seed;
 		std::vector<double> cs(cell_sizes, cell_sizes + 4);
 		Grid graph(&grid_points, cs, (size_t)cells_per_axis); // E: built on the pixel coordinates (py/gcransac_python.cpp:2592-2600)
-		CounterSampler main_sampler(&points, seed, 0u), lo_sampler(&points, seed, 1u);
+		// sampler_id 1 = PROSAC main sampler (py/gcransac_python.cpp:4320-4323); the LO sampler is uniform either way
+		// (stream 2 then: PROSAC draws use stream 1)
+		CounterSampler uniform_sampler(&points, seed, 0u), lo_sampler(&points, seed, sampler_id == 1 ? 2u : 1u);
+		CounterProsacSampler prosac_sampler(&points, seed);
+		sampler::Sampler<cv::Mat, size_t> *main_sampler_ptr = sampler_id == 1 ? (sampler::Sampler<cv::Mat, size_t> *)&prosac_sampler
+		                                                                        : (sampler::Sampler<cv::Mat, size_t> *)&uniform_sampler;
 		Model model;
 		GCRANSAC<Est, Grid, Scoring> gcransac;
 		// py/gcransac_python.cpp:4498-4504
@@ -483,7 +526,7 @@ namespace
 		gcransac.settings.max_iteration_number = max_iters;
 		gcransac.settings.min_iteration_number = min_iters;
 		gcransac.settings.neighborhood_sphere_radius = cells_per_axis;
-		gcransac.run(points, estimator, &main_sampler, &lo_sampler, &graph, model);
+		gcransac.run(points, estimator, main_sampler_ptr, &lo_sampler, &graph, model);
 		utils::RANSACStatistics st = gcransac.getRansacStatistics();
 		if constexpr (PROBLEM == GCRO_F)
 			if ((f_ba & 2) && st.inliers.size() > 7)
@@ -530,7 +573,7 @@ namespace
 			stats_out[3] = st.neighbor_number;
 			stats_out[4] = st.accepted_models;
 			stats_out[5] = st.rejected_models;
-			stats_out[6] = main_sampler.drawn();
+			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : uniform_sampler.drawn();
 			stats_out[7] = lo_sampler.drawn();
 			stats_out[8] = estimator.degensac_runs;
 			stats_out[9] = estimator.degensac_updates;
@@ -552,11 +595,11 @@ extern "C" {
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
-            const double *grid_pts, int use_degensac, int f_ba)
+            const double *grid_pts, int use_degensac, int f_ba, int sampler_id)
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
 	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
-#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba)
+#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id)
 	if (scoring_kind == 0)
 	{
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);

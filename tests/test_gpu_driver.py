@@ -31,31 +31,36 @@ def pyg():
 
 
 def test_findhomography_cfg1_matches_reference_run(pyg, ref):
+    """BASELINE configs[0]: the bundled pair with the call of the reference's own test -- sampler=1 is PROSAC over the
+    SNN-ratio order (py/gcransac_python.cpp:4320-4323); sampler=0 (uniform) as well."""
     g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
     pts = g["pts"]                                   # float32 N x 4, like the reference's tests pass it
     h1, w1, h2, w2 = (int(v) for v in g["size"])
-    for seed in (1, 2, 3):
-        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, [], threshold=3.0, conf=0.99, spatial_coherence_weight=0.975,
-                                     max_iters=10000, min_iters=50, use_sprt=False, sampler=1, neighborhood=0,
-                                     neighborhood_size=4.0, use_space_partitioning=False, lo_number=50, seed=seed)
-        st = pyg.last_statistics
-        want = ref.run(O.H, pts.astype(np.float64), g["cell_sizes"], 4, 3.0, conf=0.99, spatial_weight=0.975, max_iters=10000,
-                       min_iters=50, lo_number=50, seed=seed)
-        assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
-        assert st["graph_cut_number"] == want["stats"]["graph_cuts"]
-        assert st["local_optimization_number"] == want["stats"]["local_optimizations"]
-        assert st["lo_samples"] == want["stats"]["lo_samples"]
-        assert np.array_equal(mask, want["mask"]), (seed, int(mask.sum()), int(want["mask"].sum()))
-        assert _up_to_scale(want["model"], H) < 1e-5
-        assert abs(st["score"] - want["score"]) <= 1e-9 * want["score"]
-        assert np.array_equal(mask, g["mask_%d" % seed])      # and the committed fixture
+    for sampler, prefix in ((1, "prosac_"), (0, "")):
+        for seed in (1, 2, 3):
+            H, mask = pyg.findHomography(pts, h1, w1, h2, w2, [], threshold=3.0, conf=0.99, spatial_coherence_weight=0.975,
+                                         max_iters=10000, min_iters=50, use_sprt=False, sampler=sampler, neighborhood=0,
+                                         neighborhood_size=4.0, use_space_partitioning=False, lo_number=50, seed=seed)
+            st = pyg.last_statistics
+            want = ref.run(O.H, pts.astype(np.float64), g["cell_sizes"], 4, 3.0, conf=0.99, spatial_weight=0.975,
+                           max_iters=10000, min_iters=50, lo_number=50, seed=seed, sampler=sampler)
+            assert st["iteration_number"] == want["stats"]["iterations"], (sampler, seed, st, want["stats"])
+            assert st["graph_cut_number"] == want["stats"]["graph_cuts"]
+            assert st["local_optimization_number"] == want["stats"]["local_optimizations"]
+            assert st["lo_samples"] == want["stats"]["lo_samples"]
+            assert np.array_equal(mask, want["mask"]), (sampler, seed, int(mask.sum()), int(want["mask"].sum()))
+            assert _up_to_scale(want["model"], H) < 1e-5
+            assert abs(st["score"] - want["score"]) <= 1e-9 * want["score"]
+            assert np.array_equal(mask, g["%smask_%d" % (prefix, seed)])      # and the committed fixture
+            assert mask.sum() > 250                                            # the reference's own floor (tests/test_homography.py:85)
 
 
 def test_findhomography_synthetic_and_errors(pyg, ref):
     pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)
     cs = np.array([(1024 + np.finfo(np.float64).eps) / 4] * 4)
-    want = ref.run(O.H, pts, cs, 4, 2.0, conf=0.99, spatial_weight=0.975, max_iters=10000, min_iters=50, lo_number=50, seed=5)
+    want = ref.run(O.H, pts, cs, 4, 2.0, conf=0.99, spatial_weight=0.975, max_iters=10000, min_iters=50, lo_number=50, seed=5,
+                   sampler=1)                                       # the Python default sampler is PROSAC
     assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5
     assert (mask & inl).sum() > 0.97 * inl.sum()
     with pytest.raises(ValueError):
@@ -75,7 +80,7 @@ def test_findfundamental_matches_reference_run(pyg, ref):
     for seed, weight in ((7, 0.0), (8, 0.1)):
         F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
                                             neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed,
-                                            use_degensac=False, bundle_adjustment=False)
+                                            use_degensac=False, bundle_adjustment=False, sampler=0)
         st = pyg.last_statistics
         cs = np.array([1024 / 4.0] * 4)
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50, seed=seed)
@@ -96,7 +101,7 @@ def test_findfundamental_degensac_matches_reference_run(pyg, ref):
         pts, Fm, inl, on_plane = synth.epipolar_pair_planar(1000, 0.4, plane, seed + 10)
         F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=0.0,
                                             neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed,
-                                            bundle_adjustment=False)
+                                            bundle_adjustment=False, sampler=0)
         st = pyg.last_statistics
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50,
                        seed=seed, use_degensac=True)
@@ -126,7 +131,7 @@ def test_findfundamental_default_estimator_matches_reference_run(pyg, ref):
                                             neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
         st = pyg.last_statistics
         want = ref.run(O.F, pts, cs, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50,
-                       seed=seed, use_degensac=True, f_ba=3)
+                       seed=seed, use_degensac=True, f_ba=3, sampler=1)  # every Python default: PROSAC, BA, DEGENSAC
         assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
         assert st["lo_samples"] == want["stats"]["lo_samples"]
         assert st["degensac_runs"] == want["stats"]["degensac_runs"]
@@ -143,7 +148,7 @@ def test_findessential_matches_reference_run(pyg, ref, oracle):
     npts = oracle.normalize_correspondences(pts, K, K)
     for seed, weight in ((7, 0.0), (8, 0.1)):
         E, mask = pyg.findEssentialMatrix(pts, K, K, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=weight,
-                                          neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed)
+                                          neighborhood=0, neighborhood_size=4.0, use_sprt=False, seed=seed, sampler=0)
         st = pyg.last_statistics
         cs = np.array([1024 / 4.0] * 4)
         thr = 0.75 / (0.25 * (K[0, 0] + K[1, 1] + K[0, 0] + K[1, 1]))          # py/gcransac_python.cpp:2624-2626, 2737
