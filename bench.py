@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs]
 
 Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
 50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
@@ -47,6 +47,9 @@ WORKLOADS = {
     "h2k_pairs": dict(problem="h", n=2048, outliers=0.3, thr=3.0, pairs=128, pipeline=True,
                       desc="findHomography full pipeline (4-pt + MSAC, LO + graph-cut, conf 0.99), N=2048, 30% outliers, "
                            "thr 3.0 px, distinct synthetic pairs"),
+    "e2k_pairs": dict(problem="e", n=2048, outliers=0.85, thr=0.75, pairs=64, pipeline=True, max_iters=100000,
+                      desc="findEssentialMatrix full pipeline (5-pt + MSAC, Stewenius refits in LO, conf 0.99, max_iters "
+                           "100000), N=2048, 85% outliers, known K, thr 0.75 px, distinct synthetic pairs (configs[2] pipeline)"),
     # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL max all-reduce of the key
     "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps",
                         desc="single F problem, N=1048576 x K=1048576 7-pt samples sharded over the GPUs, MSAC, "
@@ -61,6 +64,8 @@ def make_points(wl, rank):
         seed = (0 if wl.get("shard") == "hyps" else 1000 * rank) + p + 1   # a sharded problem is the SAME on every rank
         if wl["problem"] == "f":
             pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])
+        elif wl["problem"] == "e" and wl.get("pipeline"):
+            pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])       # pixels: the API normalises by K itself
         elif wl["problem"] == "e":
             # normalizeCorrespondences (py/gcransac_python.cpp:2519-2600): x' = K^-1 (x, y, 1)
             px = synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0]
@@ -217,7 +222,7 @@ def bench_reference(args, wl, rank, world):
 
 def _pairs_cpu_worker(args):
     """One image pair through the reference's verbatim GCRANSAC<>::run on one host core."""
-    problem, pts, thr, weight, seed = args
+    problem, pts, thr, weight, seed, max_iters = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     if "ref" not in _CPU_IMPL:
@@ -225,9 +230,16 @@ def _pairs_cpu_worker(args):
     eps = np.finfo(np.float64).eps if problem == "h" else 0.0
     cs = np.array([(1024 + eps) / 4.0] * 4)
     t0 = time.perf_counter()
+    if problem == "e":
+        from pygcransac import synth
+        K = synth.K_MAT
+        npts = (pts - synth.SIZE / 2) / synth.FOCAL                              # K^-1 normalisation (utils.h:65-110)
+        out = _CPU_IMPL["ref"].run(O.E, npts, cs, 4, thr / synth.FOCAL, conf=0.99, spatial_weight=weight, max_iters=max_iters,
+                                   min_iters=50, lo_number=50, seed=seed, grid_pts=pts)
+        return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
     # F: the reference's default pipeline on both arms -- BA non-minimal solver, DEGENSAC, post-run bundle adjustment
     out = _CPU_IMPL["ref"].run(O.H if problem == "h" else O.F, pts, cs, 4, thr, conf=0.99, spatial_weight=weight,
-                               max_iters=10000, min_iters=50, lo_number=50, seed=seed, use_degensac=problem == "f",
+                               max_iters=max_iters, min_iters=50, lo_number=50, seed=seed, use_degensac=problem == "f",
                                f_ba=3 if problem == "f" else 0)
     return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
 
@@ -238,7 +250,8 @@ def bench_pairs(args, wl, rank, world):
     taking pairs from a queue; pairs shard over the ranks
     with no collective.  The API takes host arrays, so every call includes its H2D / D2H: value == e2e.
     --impl reference: the reference's verbatim GCRANSAC<>::run (oracle/_ref) on the same pairs, one pair per host core."""
-    weight = 0.975 if wl["problem"] == "h" else 0.0                  # the Python defaults (py/bindings.cpp:1147-1178)
+    weight = {"h": 0.975, "f": 0.0, "e": 0.1}[wl["problem"]]          # the Python defaults (py/bindings.cpp:1147-1178)
+    max_iters = wl.get("max_iters", 10000)
     n_pairs = wl["pairs"]
     pts = make_points(wl, rank)
     line = {"metric": "image pairs/s", "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -250,7 +263,7 @@ def bench_pairs(args, wl, rank, world):
         import multiprocessing as mp
         cores = os.cpu_count() or 1
         pool = mp.get_context("fork").Pool(cores)
-        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1) for p in range(n_pairs)]
+        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters) for p in range(n_pairs)]
         for s in range(args.warmup):
             pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
         t0 = time.perf_counter()
@@ -279,7 +292,11 @@ def bench_pairs(args, wl, rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    find = pygcransac.findHomography if wl["problem"] == "h" else pygcransac.findFundamentalMatrix
+    from pygcransac import synth
+    if wl["problem"] == "e":
+        find = lambda c, *a, **kw: pygcransac.findEssentialMatrix(c, synth.K_MAT, synth.K_MAT, *a, **kw)
+    else:
+        find = pygcransac.findHomography if wl["problem"] == "h" else pygcransac.findFundamentalMatrix
 
     from concurrent.futures import ThreadPoolExecutor
     workers = args.workers if args.workers > 0 else max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
@@ -291,7 +308,7 @@ def bench_pairs(args, wl, rank, world):
     def one_pair(job):
         s, p = job
         M, mask = find(pts[p], 1024, 1024, 1024, 1024, [], threshold=wl["thr"], conf=0.99,
-                       spatial_coherence_weight=weight, max_iters=10000, min_iters=50, use_sprt=False, sampler=0,
+                       spatial_coherence_weight=weight, max_iters=max_iters, min_iters=50, use_sprt=False, sampler=0,
                        neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank)
         st = pygcransac._tls.last_statistics
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):

@@ -274,25 +274,37 @@ __global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
 		a.accS[g] = 0ull;
 		a.accC[g] = 0u;
 	}
+	// positions in the pair's compact list: warp ballots -> one shared prefix per CTA -> ONE global atomic per CTA
+	// (a per-warp atomic on the same counter serialises 24576 requests at the L2 for a 786432-slot pair)
+	__shared__ uint32_t s_warp_base[8];
+	__shared__ uint32_t s_cta_base;
 	const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
-	if (ballot != 0u)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0)
+		s_warp_base[warp] = (uint32_t)__popc(ballot);
+	__syncthreads();
+	if (threadIdx.x == 0)
 	{
-		const int lane = threadIdx.x & 31;
-		uint32_t base = 0;
-		if (lane == __ffs(ballot) - 1)
-			base = atomicAdd(&a.counts[pair], (uint32_t)__popc(ballot));
-		base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-		if (ok)
+		uint32_t run = 0;
+		for (int w = 0; w < 8; ++w)
 		{
-			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-			a.slots[(size_t)pair * a.k + pos] = (uint32_t)slot;
-			float m[ML];
-			normalise_model<PROBLEM>(a.models + g * ML, a.norm + (size_t)pair * 8, m);
-			float *o = a.m32 + ((size_t)pair * a.k + pos) * ML;
-#pragma unroll
-			for (int j = 0; j < ML; ++j)
-				o[j] = m[j];
+			const uint32_t c = s_warp_base[w];
+			s_warp_base[w] = run;
+			run += c;
 		}
+		s_cta_base = run ? atomicAdd(&a.counts[pair], run) : 0u;
+	}
+	__syncthreads();
+	if (ok)
+	{
+		const uint32_t pos = s_cta_base + s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u));
+		a.slots[(size_t)pair * a.k + pos] = (uint32_t)slot;
+		float m[ML];
+		normalise_model<PROBLEM>(a.models + g * ML, a.norm + (size_t)pair * 8, m);
+		float *o = a.m32 + ((size_t)pair * a.k + pos) * ML;
+#pragma unroll
+		for (int j = 0; j < ML; ++j)
+			o[j] = m[j];
 	}
 	// the last CTA to get here sees every pair's final count and builds the hypothesis-tile prefix (saves a launch)
 	__threadfence();

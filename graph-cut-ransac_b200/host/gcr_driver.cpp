@@ -112,6 +112,12 @@ namespace
 		double pp_H[9] = {0};
 		double f_min_ratio = 0.5; // minimum_inlier_ratio_in_validity_check (:91); the inner estimator is built with 0.0 (:540)
 		std::vector<uint32_t> h_samples;
+		// FP64 scores / inlier lists of the batch's record candidates, evaluated in ONE launch (prefetch_candidates)
+		std::vector<size_t> cand_slot;
+		std::vector<double> cand_score;
+		std::vector<uint32_t> cand_count;
+		std::vector<uint32_t> cand_idx; // [candidate][n]
+		DeviceBuffer d_cand_models, d_cand_scores, d_cand_counts, d_cand_idx;
 
 		// main-loop batch
 		int B = 0;
@@ -401,6 +407,65 @@ namespace
 			batch_count = B;
 			++st.gpu_batches;
 			return true;
+		}
+
+		// The sequential loop re-scores in FP64 every model whose FP32 score comes within 2e-4 of the best so far.  Only
+		// the running records of the batch can do that, O(log B) of them: they are found here from the FP32 scores
+		// (running maximum started at the current best) and evaluated in one launch instead of one launch + two
+		// synchronisations each.  A model the loop wants and this prediction missed (the best so far can lag behind the
+		// FP32 record when isValidModel rejects it) is evaluated on demand as before.
+		bool prefetch_candidates(double best_value, uint64_t from)
+		{
+			cand_slot.clear();
+			double record = best_value;
+			std::vector<double> models;
+			for (size_t j = (size_t)(from - batch_first); j < (size_t)batch_count; ++j)
+				for (int q = 0; q < mm; ++q)
+				{
+					const size_t slot = j * mm + q;
+					if (!h_valid[slot] || !((double)h_scores[slot] > record * (1.0 - 2e-4)))
+						continue;
+					cand_slot.push_back(slot);
+					models.insert(models.end(), &h_models[slot * 9], &h_models[slot * 9] + 9);
+					record = std::max(record, (double)h_scores[slot]);
+				}
+			const size_t C = cand_slot.size();
+			if (C < 2 || C > 64)
+			{
+				cand_slot.clear(); // nothing to gain / an implausible batch (pure noise): on demand
+				return true;
+			}
+			if (!d_cand_models.ensure(ctx, C * 9 * sizeof(double)) || !d_cand_scores.ensure(ctx, C * sizeof(double)) ||
+			    !d_cand_counts.ensure(ctx, C * sizeof(uint32_t)) || !d_cand_idx.ensure(ctx, C * (size_t)n * sizeof(uint32_t)))
+				return fail("gcr_malloc");
+			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models.data(), C * 9 * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_h2d");
+			if (gcr_score_exact(ctx, problem, GCR_MSAC, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
+			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), nullptr) != GCR_OK)
+				return fail("gcr_score_exact");
+			cand_score.resize(C);
+			cand_count.resize(C);
+			cand_idx.resize(C * (size_t)n);
+			if (gcr_memcpy_d2h(ctx, cand_score.data(), d_cand_scores.p, C * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, cand_count.data(), d_cand_counts.p, C * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h(ctx, cand_idx.data(), d_cand_idx.p, C * (size_t)n * sizeof(uint32_t)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			return true;
+		}
+
+		// exact() of slot `slot` of the current batch, from the prefetched candidates when it is one of them
+		bool exact_slot(size_t slot, const double *model, Score &s, std::vector<uint32_t> &inliers)
+		{
+			for (size_t c = 0; c < cand_slot.size(); ++c)
+				if (cand_slot[c] == slot)
+				{
+					++st.exact_rescores;
+					s.value = cand_score[c];
+					s.inliers = cand_count[c];
+					inliers.assign(cand_idx.begin() + c * (size_t)n, cand_idx.begin() + c * (size_t)n + cand_count[c]);
+					return true;
+				}
+			return exact(model, s, &inliers);
 		}
 
 		// ---- GCRANSAC::labeling (GCRANSAC.h:913-1021): unary terms from GPU residuals, BK min-cut on the host ----
@@ -751,7 +816,7 @@ namespace
 				{
 					const uint64_t g = cursor++;
 					if (batch_count == 0 || g < batch_first || g >= batch_first + (uint64_t)batch_count)
-						if (!run_batch(g))
+						if (!run_batch(g) || !prefetch_candidates(best.value, g))
 							return -1;
 					const size_t j = (size_t)(g - batch_first);
 					bool any = false;
@@ -780,7 +845,7 @@ namespace
 						if (!((double)h_scores[slot] > best.value * (1.0 - 2e-4)))
 							continue; // FP32 ranking: cannot beat the best so far (:440)
 						Score s;
-						if (!exact(model, s, &cur.idx))
+						if (!exact_slot(slot, model, s, cur.idx))
 							return -1;
 						cur.lazy = false;
 						if (!(best.value < s.value)) // :440
