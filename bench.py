@@ -448,11 +448,46 @@ def main():
     def step_resident(i):
         return one_round(i)
 
+    # e2e for a batch of pairs: the pairs are independent, so the upload of one chunk of pairs overlaps the scoring of
+    # the previous one -- two contexts (streams) take alternate chunks (the user-level pattern for host-resident batches)
+    E2E_CHUNKS = 8
+    overlap = n_pairs >= 8 * E2E_CHUNKS and not hyps_sharded
+    if overlap:
+        side = []
+        for _ in range(2):
+            c2 = _cabi.Context(local_rank)
+            s2 = torch.cuda.Stream()
+            c2.set_stream(s2.cuda_stream)
+            if args.variant >= 0:
+                c2.set_score_variant(args.variant)
+            side.append((c2, s2))
+        chunk = n_pairs // E2E_CHUNKS
+
     def step_e2e(i):
-        ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
-        ev = one_round(i)
-        keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
-        best_host.copy_(best, non_blocking=True)
+        if not overlap:
+            ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
+            ev = one_round(i)
+            keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
+            best_host.copy_(best, non_blocking=True)
+            return ev
+        start = torch.cuda.Event()
+        start.record(stream)
+        ev = 0
+        for c2, s2 in side:
+            s2.wait_event(start)
+        for c in range(E2E_CHUNKS):
+            c2, s2 = side[c & 1]
+            lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
+            with torch.cuda.stream(s2):
+                c2.check(c2.lib.gcr_points_upload(c2.h, pts_host[lo:hi].data_ptr(), n, 4, hi - lo))
+                ev += c2.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345 + c, wl["thr"], flags, 0,
+                                      keys[lo:hi].data_ptr(), best[lo:hi].data_ptr())
+                keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
+                best_host[lo:hi].copy_(best[lo:hi], non_blocking=True)
+        for c2, s2 in side:
+            done = torch.cuda.Event()
+            done.record(s2)
+            stream.wait_event(done)
         return ev
 
     def timed(step_fn, first):
@@ -499,10 +534,15 @@ def main():
         step_e2e(i)
     barrier()
     ctx.counters(reset=True)
+    if overlap:
+        for c2, _ in side:
+            c2.counters(reset=True)
     ms_e2e, _ = timed(step_e2e, args.warmup)
     barrier()
     clock_info = clocks.stop()
     evals_e2e = ctx.counters(reset=True)[0] * n
+    if overlap:
+        evals_e2e = sum(c2.counters(reset=True)[0] for c2, _ in side) * n
 
     # ---- max over ranks, sum of work ----
     if world > 1:
@@ -542,7 +582,8 @@ def main():
                                  "contraction, HBM traffic ~0): peak is the FP32 roofline, not hbm/tensor"},
             "clocks": clock_info,
             "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": "evals/s",
-                    "h2d_bytes_per_step": int(pts_host.numel() * 8), "d2h_bytes_per_step": int(n_pairs * (8 + 72))},
+                    "h2d_bytes_per_step": int(pts_host.numel() * 8), "d2h_bytes_per_step": int(n_pairs * (8 + 72)),
+                    "overlap": ("%d chunks of pairs on 2 contexts / streams: uploads overlap scoring" % E2E_CHUNKS) if overlap else "none"},
             "gpu_launches": int(launches),
         }
         if not args.no_cpu:
@@ -554,6 +595,9 @@ def main():
                                     "sample": "%d samples of pair 0 (solve + MSAC over all %d points), sliced over the "
                                               "host cores, %.1f s wall" % (used, n, c_wall)}
         print(json.dumps(line))
+    if overlap:
+        for c2, _ in side:
+            c2.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
