@@ -184,22 +184,34 @@ static gcr_status ensure_stage(gcr_ctx *ctx)
 	GCR_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_stage, gcr_ctx::STAGE_BYTES));
 	return GCR_OK;
 }
+// Small host -> device copies: the source is copied into a ring inside the pinned bounce buffer and the transfer is
+// queued WITHOUT a synchronise (the caller's buffer is free on return, the data is ordered on the context's stream like
+// any kernel).  The ring occupies the first half of the buffer and restarts after any stream synchronise of this file;
+// device -> host copies land in the second half and do synchronise (the host reads them).
 extern "C" gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
 	if (bytes == 0)
 		return GCR_OK;
-	if (bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	const size_t half = gcr_ctx::STAGE_BYTES / 2;
+	if (bytes <= half && ensure_stage(ctx) == GCR_OK)
 	{
-		// every staged copy ends with a synchronise, so the bounce buffer is never in flight here
-		memcpy(ctx->h_stage, h_src, bytes);
-		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
-		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		const size_t need = (bytes + 255) & ~(size_t)255;
+		if (ctx->stage_off + need > half)
+		{
+			GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the ring is full: wait for the queued copies
+			ctx->stage_off = 0;
+		}
+		char *slot = (char *)ctx->h_stage + ctx->stage_off;
+		memcpy(slot, h_src, bytes);
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->stage_off += need;
 		return GCR_OK;
 	}
 	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stage_off = 0;
 	return GCR_OK;
 }
 extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
@@ -208,15 +220,25 @@ extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_sr
 		return GCR_ERR_ARG;
 	if (bytes == 0)
 		return GCR_OK;
-	if (bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	const size_t half = gcr_ctx::STAGE_BYTES / 2;
+	if (ensure_stage(ctx) == GCR_OK)
 	{
-		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		memcpy(h_dst, ctx->h_stage, bytes);
+		// through the pinned buffer, in pieces if need be: a pageable destination would send the copy down the driver's
+		// own staging path, which serialises the host threads of a multi-context process
+		char *slot = (char *)ctx->h_stage + half;
+		for (size_t done = 0; done < bytes; done += half)
+		{
+			const size_t piece = bytes - done < half ? bytes - done : half;
+			GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(slot, (const char *)d_src + done, piece, cudaMemcpyDeviceToHost, ctx->stream));
+			GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			memcpy((char *)h_dst + done, slot, piece);
+		}
+		ctx->stage_off = 0; // everything queued before has completed
 		return GCR_OK;
 	}
 	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stage_off = 0;
 	return GCR_OK;
 }
 extern "C" gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes)
@@ -565,9 +587,15 @@ extern "C" gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, in
 	if (!pinned && bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
 	{
 		// pageable caller memory: bounce through the context's pinned buffer (a pinned source is copied asynchronously)
+		if (ctx->stage_off)
+		{
+			GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // queued ring copies still read the buffer
+			ctx->stage_off = 0;
+		}
 		memcpy(ctx->h_stage, h_points, bytes);
 		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
 		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the bounce buffer is free again on return
+		ctx->stage_off = 0;
 	}
 	else
 		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream));

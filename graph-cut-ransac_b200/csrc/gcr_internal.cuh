@@ -83,7 +83,8 @@ struct gcr_ctx
 	// small host <-> device copies go through this pinned bounce buffer (pageable cudaMemcpyAsync takes the driver's
 	// global staging path); separate from h_pinned, which kernels' result read-backs use
 	void *h_stage = nullptr;
-	static const size_t STAGE_BYTES = 1 << 20;
+	size_t stage_off = 0; // next free byte of the host -> device ring (first half of h_stage)
+	static const size_t STAGE_BYTES = 4 << 20;
 
 	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu
 	int score_variant = -1;    // -1 auto; else forces a kernel variant (bench / tests)
