@@ -12,6 +12,9 @@ timeout 600 python bench.py --steps 3 --warmup 1 --workload f4k_pairs > gpurun_o
 timeout 600 python bench.py --steps 3 --warmup 1 --workload h2k_pairs > gpurun_out/bench_h2k_pairs.log 2>&1
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 --workload f4k_pairs > gpurun_out/bench_f4k_pairs_ref.log 2>&1
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 --workload h2k_pairs > gpurun_out/bench_h2k_pairs_ref.log 2>&1
+timeout 600 python bench.py --steps 3 --warmup 1 --workload e2k_pairs > gpurun_out/bench_e2k_pairs.log 2>&1
+timeout 900 python bench.py --impl reference --steps 1 --warmup 0 --workload e2k_pairs > gpurun_out/bench_e2k_pairs_ref.log 2>&1
+timeout 300 python tools/k3_trace.py f4k > gpurun_out/k3_trace_f4k.txt 2>&1
 for w in f4k h2k_batch e2k; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$w.csv python bench.py --steps 2 --warmup 1 --no-cpu --workload $w > gpurun_out/ncu_launch_$w.log 2>&1
 done
