@@ -121,6 +121,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def k3_dram_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K3 launch, from the committed `ncu --set full` capture of this
+    workload (profiles/r1c_ncu_k3_*.txt; scripts/gpu_pass.sh regenerates it).  None if there is no capture."""
+    name = {"f4k": "f4k", "h2k_batch": "h2k", "e2k": "e2k"}.get(workload)
+    if name is None:
+        return None
+    try:
+        total = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r1c_ncu_k3_%s.txt" % name)):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+        return total
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def fp32_peak_tflops(sm_count):
     """FP32 FMA roofline: SMs x 128 lanes x 2 flop x max SM clock.  MEASURED_PEAKS.json carries HBM and bf16 tensor
     peaks but no FP32-pipe figure; its measured sm_max_mhz is used for the clock (else the device attribute)."""
@@ -575,7 +592,9 @@ def main():
                        "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs)",
                        "best_score_rank0": best_key_score},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": k3_dram_traffic(args.workload),
+                         "traffic_note": "DRAM bytes of one K3 launch from the committed ncu --set full capture (profiles/): the "
+                                         "points and models are L2-resident, the FMA pipe is the bound",
                          "kernel": "k_score (K3)", "flop_per_eval": flop, "k3_ms_per_launch": score_ms / max(1, score_launches),
                          "k3_share_of_step": score_ms / ms if world == 1 else None, "peak_source": peak_src,
                          "note": "FP32-FMA-pipe bound (projective divide / Sampson denominator; not a tensor-core "
