@@ -98,12 +98,12 @@ extern "C" gcr_status gcr_ctx_set_stream(gcr_ctx *ctx, void *cuda_stream)
 	return GCR_OK;
 }
 
+static gcr_status flush_d2h(gcr_ctx *ctx);
 extern "C" gcr_status gcr_sync(gcr_ctx *ctx)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
-	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return GCR_OK;
+	return flush_d2h(ctx); // synchronises the stream and delivers the copies queued by gcr_memcpy_d2h_async
 }
 
 extern "C" const char *gcr_last_error(const gcr_ctx *ctx) { return ctx ? ctx->err : "null context"; }
@@ -214,32 +214,57 @@ extern "C" gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_sr
 	ctx->stage_off = 0;
 	return GCR_OK;
 }
-extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+// completes the queued device -> host copies: one synchronise, then the pieces go to their destinations
+static gcr_status flush_d2h(gcr_ctx *ctx)
+{
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const size_t half = gcr_ctx::STAGE_BYTES / 2;
+	for (const auto &p : ctx->pending_d2h)
+		memcpy(p.dst, (char *)ctx->h_stage + half + p.off, p.bytes);
+	ctx->pending_d2h.clear();
+	ctx->d2h_off = 0;
+	ctx->stage_off = 0; // everything queued before has completed
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_memcpy_d2h_async(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
 	if (bytes == 0)
 		return GCR_OK;
 	const size_t half = gcr_ctx::STAGE_BYTES / 2;
-	if (ensure_stage(ctx) == GCR_OK)
+	if (ensure_stage(ctx) != GCR_OK)
+		return GCR_ERR_CUDA;
+	// through the pinned buffer, in pieces if need be: a pageable destination would send the copy down the driver's own
+	// staging path, which serialises the host threads of a multi-context process
+	for (size_t done = 0; done < bytes;)
 	{
-		// through the pinned buffer, in pieces if need be: a pageable destination would send the copy down the driver's
-		// own staging path, which serialises the host threads of a multi-context process
-		char *slot = (char *)ctx->h_stage + half;
-		for (size_t done = 0; done < bytes; done += half)
+		if (ctx->d2h_off >= half)
 		{
-			const size_t piece = bytes - done < half ? bytes - done : half;
-			GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(slot, (const char *)d_src + done, piece, cudaMemcpyDeviceToHost, ctx->stream));
-			GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			memcpy((char *)h_dst + done, slot, piece);
+			gcr_status st = flush_d2h(ctx);
+			if (st)
+				return st;
 		}
-		ctx->stage_off = 0; // everything queued before has completed
-		return GCR_OK;
+		const size_t room = half - ctx->d2h_off;
+		const size_t piece = bytes - done < room ? bytes - done : room;
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync((char *)ctx->h_stage + half + ctx->d2h_off, (const char *)d_src + done, piece,
+		                                    cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->pending_d2h.push_back({ctx->d2h_off, (char *)h_dst + done, piece});
+		ctx->d2h_off += (piece + 255) & ~(size_t)255;
+		done += piece;
 	}
-	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ctx->stage_off = 0;
 	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	gcr_status st = gcr_memcpy_d2h_async(ctx, h_dst, d_src, bytes);
+	if (st)
+		return st;
+	return flush_d2h(ctx);
 }
 extern "C" gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes)
 {
@@ -587,10 +612,11 @@ extern "C" gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, in
 	if (!pinned && bytes <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
 	{
 		// pageable caller memory: bounce through the context's pinned buffer (a pinned source is copied asynchronously)
-		if (ctx->stage_off)
+		if (ctx->stage_off || !ctx->pending_d2h.empty())
 		{
-			GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // queued ring copies still read the buffer
-			ctx->stage_off = 0;
+			gcr_status fs = flush_d2h(ctx); // queued copies still use the buffer
+			if (fs)
+				return fs;
 		}
 		memcpy(ctx->h_stage, h_points, bytes);
 		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));

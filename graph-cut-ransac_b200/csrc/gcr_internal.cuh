@@ -84,6 +84,11 @@ struct gcr_ctx
 	// global staging path); separate from h_pinned, which kernels' result read-backs use
 	void *h_stage = nullptr;
 	size_t stage_off = 0; // next free byte of the host -> device ring (first half of h_stage)
+	// device -> host copies queued by gcr_memcpy_d2h_async: they land in the second half of h_stage and are handed to
+	// their destinations by the next gcr_sync / gcr_memcpy_d2h (one stream synchronise for all of them)
+	struct PendingD2H { size_t off; void *dst; size_t bytes; };
+	std::vector<PendingD2H> pending_d2h;
+	size_t d2h_off = 0;
 	static const size_t STAGE_BYTES = 4 << 20;
 
 	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu

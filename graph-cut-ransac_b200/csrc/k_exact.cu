@@ -287,14 +287,13 @@ extern "C" gcr_status gcr_getscore_host(gcr_ctx *ctx, int problem, int scoring, 
 	                      (uint32_t *)(d + o_count), h_inlier_idx ? (uint32_t *)(d + o_idx) : nullptr, nullptr);
 	if (st)
 		return st;
-	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h + o_score, d + o_score, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	// score, count and the whole index buffer in ONE copy / synchronise (the list is at most n entries: 4 n bytes)
+	const size_t back = h_inlier_idx ? o_idx - o_score + n * sizeof(uint32_t) : 16;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h + o_score, d + o_score, back, cudaMemcpyDeviceToHost, ctx->stream));
 	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	*h_score = *(double *)(h + o_score);
 	*h_count = *(uint32_t *)(h + o_count);
 	if (h_inlier_idx && *h_count)
-	{
-		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(h_inlier_idx, d + o_idx, (size_t)*h_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	}
+		memcpy(h_inlier_idx, h + o_idx, (size_t)*h_count * sizeof(uint32_t));
 	return GCR_OK;
 }

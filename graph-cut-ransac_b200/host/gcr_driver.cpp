@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -93,6 +94,14 @@ namespace
 		size_t size() const { return lazy ? (size_t)lazy_count : idx.size(); }
 	};
 
+	struct PhaseTimer // adds the scope's wall clock to one slot of gcr_run_stats::phase_seconds
+	{
+		double &slot;
+		std::chrono::steady_clock::time_point t0;
+		explicit PhaseTimer(double &s) : slot(s), t0(std::chrono::steady_clock::now()) {}
+		~PhaseTimer() { slot += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+	};
+
 	class Driver
 	{
 	public:
@@ -167,19 +176,17 @@ namespace
 			                    d_one_count.as<uint32_t>(), d_idx.as<uint32_t>(), d_res.as<double>()) != GCR_OK)
 				return fail("gcr_score_exact");
 			uint32_t count = 0;
-			if (gcr_memcpy_d2h(ctx, &s.value, d_one_score.p, sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, &count, d_one_count.p, sizeof(uint32_t)) != GCR_OK)
+			residuals->resize(n);
+			if (inliers) inliers->resize(n);
+			// every read-back of the call is queued, one synchronise delivers them (the list is copied whole: 4 n bytes)
+			if (gcr_memcpy_d2h_async(ctx, &s.value, d_one_score.p, sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, &count, d_one_count.p, sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, residuals->data(), d_res.p, (size_t)n * sizeof(double)) != GCR_OK ||
+			    (inliers && gcr_memcpy_d2h_async(ctx, inliers->data(), d_idx.p, (size_t)n * sizeof(uint32_t)) != GCR_OK) ||
+			    gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			s.inliers = count;
-			residuals->resize(n);
-			if (gcr_memcpy_d2h(ctx, residuals->data(), d_res.p, (size_t)n * sizeof(double)) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			if (inliers)
-			{
-				inliers->resize(count);
-				if (count && gcr_memcpy_d2h(ctx, inliers->data(), d_idx.p, (size_t)count * sizeof(uint32_t)) != GCR_OK)
-					return fail("gcr_memcpy_d2h");
-			}
+			if (inliers) inliers->resize(count);
 			return true;
 		}
 
@@ -395,13 +402,13 @@ namespace
 			{
 				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
 				h_samples.resize((size_t)B * m);
-				if (gcr_memcpy_d2h(ctx, h_samples.data(), d_samples.p, (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
+				if (gcr_memcpy_d2h_async(ctx, h_samples.data(), d_samples.p, (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
 					return fail("gcr_memcpy_d2h");
 			}
-			if (gcr_memcpy_d2h(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK)
+			if (gcr_memcpy_d2h_async(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK || gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			batch_first = first;
 			batch_count = B;
@@ -435,21 +442,31 @@ namespace
 				cand_slot.clear(); // nothing to gain / an implausible batch (pure noise): on demand
 				return true;
 			}
+			return exact_many(models.data(), C, cand_score, cand_count, cand_idx);
+		}
+
+		// FP64 getScore of C models (host, 9 doubles each) in one launch and one synchronise: scores, inlier counts and
+		// the inlier lists ([C][n], the first count entries of each row)
+		bool exact_many(const double *models, size_t C, std::vector<double> &score, std::vector<uint32_t> &count,
+		                std::vector<uint32_t> &idx)
+		{
 			if (!d_cand_models.ensure(ctx, C * 9 * sizeof(double)) || !d_cand_scores.ensure(ctx, C * sizeof(double)) ||
 			    !d_cand_counts.ensure(ctx, C * sizeof(uint32_t)) || !d_cand_idx.ensure(ctx, C * (size_t)n * sizeof(uint32_t)))
 				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models.data(), C * 9 * sizeof(double)) != GCR_OK)
+			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models, C * 9 * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
 			if (gcr_score_exact(ctx, problem, GCR_MSAC, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
 			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), nullptr) != GCR_OK)
 				return fail("gcr_score_exact");
-			cand_score.resize(C);
-			cand_count.resize(C);
-			cand_idx.resize(C * (size_t)n);
-			if (gcr_memcpy_d2h(ctx, cand_score.data(), d_cand_scores.p, C * sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, cand_count.data(), d_cand_counts.p, C * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, cand_idx.data(), d_cand_idx.p, C * (size_t)n * sizeof(uint32_t)) != GCR_OK)
+			score.resize(C);
+			count.resize(C);
+			idx.resize(C * (size_t)n);
+			if (gcr_memcpy_d2h_async(ctx, score.data(), d_cand_scores.p, C * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, count.data(), d_cand_counts.p, C * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, idx.data(), d_cand_idx.p, C * (size_t)n * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
+			st.exact_rescores += C;
 			return true;
 		}
 
@@ -459,7 +476,6 @@ namespace
 			for (size_t c = 0; c < cand_slot.size(); ++c)
 				if (cand_slot[c] == slot)
 				{
-					++st.exact_rescores;
 					s.value = cand_score[c];
 					s.inliers = cand_count[c];
 					inliers.assign(cand_idx.begin() + c * (size_t)n, cand_idx.begin() + c * (size_t)n + cand_count[c]);
@@ -524,7 +540,7 @@ namespace
 		// ---- non-minimal refit of `count` index sets (one GPU launch) ----
 		bool refit(const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
 		           const double *weights_by_point, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
-		           bool sets_on_device = false, int refit_problem = -1, int ba_frame_override = 0)
+		           bool sets_on_device = false, int refit_problem = -1, int ba_frame_override = 0, bool defer_sync = false)
 		{
 			const int rp = refit_problem < 0 ? problem : refit_problem;
 			const int rm = refit_problem < 0 ? this->rm : gcr_max_refit_models(rp);
@@ -568,8 +584,13 @@ namespace
 				return fail("gcr_refit");
 			models.resize((size_t)count * rm * 9);
 			ok.resize((size_t)count * rm);
-			if (gcr_memcpy_d2h(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, ok.data(), d_lok.p, (size_t)count * rm) != GCR_OK)
+			if (defer_sync) // the caller queues more work on these models and synchronises once
+				return gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) == GCR_OK &&
+				               gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) == GCR_OK
+				           ? true
+				           : fail("gcr_memcpy_d2h");
+			if (gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) != GCR_OK || gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			return true;
 		}
@@ -608,8 +629,8 @@ namespace
 					st.lo_samples += trials;
 					std::vector<uint32_t> offsets(trials), sizes(trials, (uint32_t)sample_size);
 					for (int t = 0; t < trials; ++t) offsets[t] = (uint32_t)(t * sample_size);
-					if (!refit(nullptr, offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, true))
-						return false;
+					if (!refit(nullptr, offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, true, -1, 0, true))
+						return false; // (read-backs queued: delivered together with the scores below)
 					n_models = trials * rm; // trial-major, the solver's model order inside a trial (:866)
 				}
 				else if ((size_t)m < inliers.size() && trials > 0)
@@ -633,6 +654,28 @@ namespace
 					if (gcr_memcpy_d2h(ctx, scores32.data(), d_lscores.p, n_models * sizeof(float)) != GCR_OK)
 						return fail("gcr_memcpy_d2h");
 					st.models_scored += n_models;
+					// the trials that can become the round's best: running records of the FP32 scores, evaluated in FP64
+					// in one launch (the sequential loop below falls back to a single evaluation for anything else)
+					std::vector<int> rec;
+					std::vector<double> rec_models, rec_score;
+					std::vector<uint32_t> rec_count, rec_idx;
+					{
+						double record = max_score.value;
+						for (int t = 0; t < n_models && rec.size() < 64; ++t)
+							if (ok[t] && (double)scores32[t] > record * (1.0 - 2e-4))
+							{
+								rec.push_back(t);
+								rec_models.insert(rec_models.end(), &models[(size_t)t * 9], &models[(size_t)t * 9] + 9);
+								record = std::max(record, (double)scores32[t]);
+							}
+						if (rec.size() >= 2)
+						{
+							if (!exact_many(rec_models.data(), rec.size(), rec_score, rec_count, rec_idx))
+								return false;
+						}
+						else
+							rec.clear();
+					}
 					for (int t = 0; t < n_models; ++t)
 					{
 						if (!ok[t])
@@ -640,7 +683,15 @@ namespace
 						if (!((double)scores32[t] > max_score.value * (1.0 - 2e-4)))
 							continue; // FP32 ranking says it cannot beat the best so far
 						Score s;
-						if (!exact(&models[(size_t)t * 9], s, &tmp))
+						size_t c = 0;
+						while (c < rec.size() && rec[c] != t) ++c;
+						if (c < rec.size())
+						{
+							s.value = rec_score[c];
+							s.inliers = rec_count[c];
+							tmp.assign(rec_idx.begin() + c * (size_t)n, rec_idx.begin() + c * (size_t)n + rec_count[c]);
+						}
+						else if (!exact(&models[(size_t)t * 9], s, &tmp))
 							return false;
 						if (max_score.value < s.value) // :880
 						{
@@ -772,6 +823,7 @@ namespace
 			truncated_threshold = 3.0 / 2.0 * S.threshold;
 			T = truncated_threshold * truncated_threshold;
 			rm = gcr_max_refit_models(problem);
+			std::unique_ptr<PhaseTimer> setup_timer(new PhaseTimer(st.phase_seconds[0]));
 			if (nested)
 				have_grid = false; // spatial_coherence_weight = 0: no neighbourhood (the reference passes nullptr, :558)
 			else if (grid_pts && grid_pts != pts)
@@ -796,8 +848,11 @@ namespace
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
 					return -1;
 			}
+			setup_timer.reset();
 			const double log_probability = std::log(1.0 - S.confidence);
 			uint64_t max_iteration = iteration_number(1, n, m, log_probability);
+			const auto loop_t0 = std::chrono::steady_clock::now();
+			const double batch_before = st.phase_seconds[1], lo_before = st.phase_seconds[3];
 			uint64_t &it = st.iteration_number;
 			uint64_t cursor = 0; // next sample of the main stream
 			Score best;
@@ -816,8 +871,11 @@ namespace
 				{
 					const uint64_t g = cursor++;
 					if (batch_count == 0 || g < batch_first || g >= batch_first + (uint64_t)batch_count)
+					{
+						PhaseTimer t(st.phase_seconds[1]);
 						if (!run_batch(g) || !prefetch_candidates(best.value, g))
 							return -1;
+					}
 					const size_t j = (size_t)(g - batch_first);
 					bool any = false;
 					for (int q = 0; q < mm; ++q)
@@ -876,11 +934,14 @@ namespace
 				if (S.do_local_optimization && do_lo)
 				{
 					++st.local_optimization_number; // :485 (and once more inside, :805 -- the reference counts twice)
+					PhaseTimer t(st.phase_seconds[3]);
 					if (!local_optimization(buf[offset], best_model, best))
 						return -1;
 					max_iteration = iteration_number(best.inliers, n, m, log_probability);
 				}
 			}
+			st.phase_seconds[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - loop_t0).count() -
+			                       (st.phase_seconds[1] - batch_before) - (st.phase_seconds[3] - lo_before);
 
 			for (int i = 0; i < n; ++i)
 				inlier_mask[i] = 0;
@@ -889,6 +950,7 @@ namespace
 			if (S.do_local_optimization && st.local_optimization_number == 0) // :530-543
 			{
 				++st.local_optimization_number;
+				PhaseTimer t(st.phase_seconds[3]);
 				if (!local_optimization(buf[offset], best_model, best))
 					return -1;
 			}
@@ -907,6 +969,7 @@ namespace
 			bool iterative_refitting_applied = false;
 			if (S.do_final_iterated_least_squares) // :559-586
 			{
+				PhaseTimer t(st.phase_seconds[4]);
 				double model[9];
 				memcpy(model, best_model, sizeof(model));
 				bool success = false;
@@ -927,6 +990,7 @@ namespace
 					}
 				}
 			}
+			PhaseTimer final_timer(st.phase_seconds[5]);
 			if (!iterative_refitting_applied) // :588-617: one least-squares fit on the first best.inliers entries
 			{
 				std::vector<double> models;

@@ -66,6 +66,10 @@ typedef struct gcr_run_stats
 	double score;
 	double graph_cut_seconds; /* host min-cut, timed separately (north star) */
 	uint64_t degensac_runs, degensac_updates; /* inner plane-and-parallax runs / models they replaced */
+	/* host wall clock per phase (s): [0] upload + grid build, [1] GPU batches of the main loop (sample, solve, score,
+	 * read-back), [2] the rest of the main loop (FP64 re-scores, isValidModel / DEGENSAC), [3] local optimisation
+	 * (labeling, min-cut, inner batch), [4] iterated least squares, [5] final fit + post-run polish */
+	double phase_seconds[6];
 } gcr_run_stats;
 
 /* defaults of utils::Settings + the Python drivers */

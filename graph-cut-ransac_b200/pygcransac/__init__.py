@@ -45,10 +45,10 @@ class RunStats(C.Structure):
                 ("local_optimization_number", C.c_uint64), ("main_samples", C.c_uint64), ("lo_samples", C.c_uint64),
                 ("gpu_batches", C.c_uint64), ("exact_rescores", C.c_uint64), ("models_scored", C.c_uint64),
                 ("score", C.c_double), ("graph_cut_seconds", C.c_double), ("degensac_runs", C.c_uint64),
-                ("degensac_updates", C.c_uint64)]
+                ("degensac_updates", C.c_uint64), ("phase_seconds", C.c_double * 6)]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if name == "phase_seconds" else getattr(self, name)) for name, _ in self._fields_}
 
 
 def _load_driver():

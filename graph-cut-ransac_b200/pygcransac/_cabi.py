@@ -29,6 +29,7 @@ EXPORTS = [
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
     "gcr_solve_plane_parallax", "gcr_refit_f_ba", "gcr_set_score_trace",
+    "gcr_memcpy_d2h_async",
 ]
 
 _lib = None
@@ -61,6 +62,7 @@ def load_library():
         "gcr_free": (i32, [vp, vp]),
         "gcr_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
         "gcr_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+        "gcr_memcpy_d2h_async": (i32, [vp, vp, vp, C.c_size_t]),
         "gcr_memset": (i32, [vp, vp, i32, C.c_size_t]),
         "gcr_points_upload": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),

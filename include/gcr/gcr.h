@@ -72,6 +72,9 @@ gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out);
 gcr_status gcr_free(gcr_ctx *ctx, void *d_ptr);
 gcr_status gcr_memcpy_h2d(gcr_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* queues a device -> host copy on the context's stream; the data is in h_dst after the next gcr_sync or gcr_memcpy_d2h
+ * (several read-backs of one step then cost one synchronise) */
+gcr_status gcr_memcpy_d2h_async(gcr_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes);
 
 /* ---- points ----------------------------------------------------------------------------------------------- */
