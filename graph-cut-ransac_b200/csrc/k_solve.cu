@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__rest
 // ---------------------------------------------------------------------------------------------------- E5 ----
 // Ten lanes per sample, three samples per warp, the solver's working set (10 x 20 constraint matrix, Sturm chain,
 // interval stack: ~5 KB per sample) in shared memory: solve_e5_group.cuh.  Lanes 30 / 31 of every warp idle.
+#ifndef E5_MIN_BLOCKS
+#define E5_MIN_BLOCKS 5 // 3.7 KB of shared memory per sample: five CTAs (20 warps) per SM if the registers allow (<= 102)
+#endif
 #define E5_THREADS 128
 #define E5_SAMPLES_PER_CTA (3 * E5_THREADS / 32)
 #define E5_SMEM (E5_SAMPLES_PER_CTA * gcr_e5g::SAMPLE_DOUBLES * sizeof(double))
@@ -282,7 +285,7 @@ struct GroupSync
 	__device__ __forceinline__ unsigned ballot(bool x) const { return (__ballot_sync(mask, x) >> shift) & 0x3ffu; }
 };
 
-__global__ void __launch_bounds__(E5_THREADS) k_solve_e5(const double *__restrict__ pts, int n,
+__global__ void __launch_bounds__(E5_THREADS, E5_MIN_BLOCKS) k_solve_e5(const double *__restrict__ pts, int n,
                                                          const GcrSampleSource src, int count,
                                                          double *__restrict__ models, uint8_t *__restrict__ valid,
                                                          unsigned long long *__restrict__ counters)

@@ -24,16 +24,17 @@ namespace gcr_e5g
 	constexpr int OFF_PT = OFF_N + 36;            // PT[5][4] sample points
 	constexpr int OFF_EET = OFF_PT + 20;          // EET[9][10]; later T10[6][11]
 	constexpr int OFF_ABS = OFF_EET + 90;         // 11 scratch doubles (pivot candidates / remainder r[11])
+	constexpr int OFF_C = OFF_ABS + 11;           // C[10][21]; before it LU5[5][9]
+	constexpr int OFF_CHAIN = OFF_C + 10 * C_STRIDE - 121; // the Sturm chain p[11][11] takes the END of the dead matrix ...
 	constexpr int STACK_CAP = 62;                 // bisection depth <= 60: one pending sibling per level + the last pair
-	constexpr int OFF_STACK = OFF_EET;            // 62 x (a, b) + 62 x packed (sa, sb, depth): overlays EET / T10 / scratch,
-	constexpr int STACK_DOUBLES = 2 * STACK_CAP + STACK_CAP / 2; // all dead once the polynomial is formed
-	constexpr int OFF_C = OFF_STACK + STACK_DOUBLES; // C[10][21]; before it LU5[5][9]; after it the Sturm chain p[11][11]
+	constexpr int OFF_STACK = OFF_EET;            // ... so that the interval stack -- 62 x (a, b) + 62 x packed (sa, sb, depth)
+	constexpr int STACK_DOUBLES = 2 * STACK_CAP + STACK_CAP / 2; // -- can run over EET / T10, the scratch and its start
 	constexpr int OFF_P = OFF_C + 10 * C_STRIDE;  // px[3][4] py[3][4] pc[3][5]
-	constexpr int OFF_POLY = OFF_P + 39;          // c[11] f[11] df[11]
-	constexpr int OFF_DEG = OFF_POLY + 33;        // 12 ints: deg[11], len
+	constexpr int OFF_POLY = OFF_P + 39;          // c[11] -> f[11] in place, df[11]
+	constexpr int OFF_DEG = OFF_POLY + 22;        // 12 ints: deg[11], len
 	constexpr int OFF_IV = OFF_DEG + 6;           // isolated intervals (a, b) x 10, then the finite / valid flags
 	constexpr int SAMPLE_DOUBLES = OFF_IV + 30;
-	static_assert(STACK_DOUBLES >= 90 + 11, "the stack region must cover EET and the scratch");
+	static_assert(OFF_STACK + STACK_DOUBLES <= OFF_CHAIN, "the interval stack must end before the Sturm chain");
 
 	__device__ __forceinline__ int sgn_of(double v) { return v > 0.0 ? 1 : (v < 0.0 ? -1 : 0); }
 
@@ -193,7 +194,7 @@ namespace gcr_e5g
 		double *P = S + OFF_P;
 		double *poly = S + OFF_POLY; // c[11] f[11] df[11]
 		const int n = 10;
-		double *f = poly + 11, *df = poly + 22;
+		double *f = poly, *df = poly + 11; // f overwrites the raw coefficients in place
 		int n_roots = 0, top = 0;
 		bool go = false;
 		if (have)
@@ -337,6 +338,7 @@ namespace gcr_e5g
 			if (go)
 			{
 				const double inv = 1.0 / poly[n];
+				sync(); // everybody has read the leading coefficient before it becomes 1
 				f[li] = poly[li] * inv;
 				if (li == 0) f[n] = 1.0;
 				sync();
@@ -346,7 +348,7 @@ namespace gcr_e5g
 				df[li] = f[li + 1] * (double)(li + 1);
 				R = 1.0 + mx;
 				// ---- chain ----
-				double *chain = S + OFF_C; // p[11][11]  (the 10 x 20 system is dead)
+				double *chain = S + OFF_CHAIN; // p[11][11]  (the 10 x 20 system is dead)
 				int *deg = reinterpret_cast<int *>(S + OFF_DEG);
 				double *r = S + OFF_ABS;
 				sync(); // df complete, everybody is past the reads of C
@@ -416,7 +418,7 @@ namespace gcr_e5g
 		// (groups without a polynomial take part in the votes with nothing to do)
 		{
 			{
-				const double *chain = S + OFF_C;
+				const double *chain = S + OFF_CHAIN;
 				const int *deg = reinterpret_cast<const int *>(S + OFF_DEG);
 				double *stk = S + OFF_STACK;
 				int *stki = reinterpret_cast<int *>(S + OFF_STACK + 2 * STACK_CAP);
