@@ -38,6 +38,8 @@
 
 #define RF_THREADS 128
 #define RF_WARPS (RF_THREADS / 32)
+#define RF_MAX_THREADS 512 /* the single-set launches of the bundle adjustment (all inliers of a run) use 512 threads */
+#define RF_MAX_WARPS (RF_MAX_THREADS / 32)
 
 struct RefitArgs
 {
@@ -66,11 +68,11 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* RF_WA
 			smem[warp * NV + j] = x;
 	}
 	__syncthreads();
-	for (int j = threadIdx.x; j < NV; j += RF_THREADS)
+	const int n_warps = (int)blockDim.x >> 5;
+	for (int j = threadIdx.x; j < NV; j += (int)blockDim.x)
 	{
 		double s = 0.0;
-#pragma unroll
-		for (int w = 0; w < RF_WARPS; ++w)
+		for (int w = 0; w < n_warps; ++w)
 			s += smem[w * NV + j];
 		out[j] = s;
 	}
@@ -275,7 +277,7 @@ __device__ __forceinline__ double ba_weight_of(const RefitArgs &a, const uint32_
 __device__ double ba_cost(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, const double *F, double *red, double *tot)
 {
 	double v[1] = {0.0};
-	for (int i = threadIdx.x; i < n; i += RF_THREADS)
+	for (int i = threadIdx.x; i < n; i += (int)blockDim.x)
 	{
 		const double *p = a.pts + (size_t)idx[i] * 4;
 		const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
@@ -348,7 +350,7 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 			double acc[35]; // lower triangle of J^T J row by row (28), then J^T r (7)
 #pragma unroll
 			for (int j = 0; j < 35; ++j) acc[j] = 0.0;
-			for (int i = tid; i < n; i += RF_THREADS)
+			for (int i = tid; i < n; i += (int)blockDim.x)
 			{
 				const double *p = a.pts + (size_t)idx[i] * 4;
 				const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
@@ -491,10 +493,10 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 }
 
 template <int PROBLEM, int BA = 0>
-__global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
+__global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit(const RefitArgs a)
 {
 	constexpr int NV = PROBLEM == GCR_H ? 44 : 45;
-	__shared__ double red[RF_WARPS * 45];
+	__shared__ double red[(BA != 0 ? RF_MAX_WARPS : RF_WARPS) * 45];
 	__shared__ double tot[45];
 	const int set = blockIdx.x, tid = threadIdx.x;
 	const uint32_t *idx = a.sets + a.offsets[set];
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 	if (!pixel_frame)
 	{
 		double v[4] = {0, 0, 0, 0};
-		for (int i = tid; i < n; i += RF_THREADS)
+		for (int i = tid; i < n; i += (int)blockDim.x)
 		{
 			const double *p = a.pts + (size_t)idx[i] * 4;
 			v[0] += p[0]; v[1] += p[1]; v[2] += p[2]; v[3] += p[3];
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 	if (!pixel_frame)
 	{
 		double v[2] = {0, 0};
-		for (int i = tid; i < n; i += RF_THREADS)
+		for (int i = tid; i < n; i += (int)blockDim.x)
 		{
 			const double *p = a.pts + (size_t)idx[i] * 4;
 			const double dx1 = msx - p[0], dy1 = msy - p[1], dx2 = mdx - p[2], dy2 = mdy - p[3];
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit(const RefitArgs a)
 	double acc[NV];
 #pragma unroll
 	for (int j = 0; j < NV; ++j) acc[j] = 0.0;
-	for (int i = tid; i < n; i += RF_THREADS)
+	for (int i = tid; i < n; i += (int)blockDim.x)
 	{
 		const double *p = a.pts + (size_t)idx[i] * 4;
 		const double x1 = (p[0] - msx) * rs, y1 = (p[1] - msy) * rs, x2 = (p[2] - mdx) * rd, y2 = (p[3] - mdy) * rd;
@@ -1001,9 +1003,9 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 	else if (problem == GCR_E)
 		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_HARTLEY)
-		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, count == 1 ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_PIXEL)
-		k_refit<GCR_F, GCR_BA_PIXEL><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_PIXEL><<<count, count == 1 ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
 	else
 		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);
