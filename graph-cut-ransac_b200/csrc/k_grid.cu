@@ -262,3 +262,87 @@ extern "C" gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell
 		*h_neighbor_number = *(unsigned long long *)((char *)ctx->h_pinned + 8);
 	return GCR_OK;
 }
+
+
+// --------------------------------------------------------------------------------- radius neighbourhood graph ----
+// FlannNeighborhoodGraph::initialize (neighborhood/flann_neighborhood_graph.h:99-137): the points converted to FP32,
+// every point's neighbours within `matching_radius` (L2 in the 4-D correspondence space), the point itself dropped.
+// The reference asks OpenCV's FLANN for them (4 randomised kd-trees, 6 checks: an approximate, run-dependent answer);
+// here the graph is the EXACT one, by brute force: N^2 distance evaluations are nothing for the sizes the graph-cut can
+// handle at all (its edge bookkeeping is an N x N matrix, GCRANSAC.h:963).  One thread per point, the other points
+// staged through shared memory; pass 1 counts, pass 2 writes the neighbours in ascending index order (CSR).
+#define RG_THREADS 256
+template <bool FILL>
+__global__ void __launch_bounds__(RG_THREADS) k_radius_graph(const double *__restrict__ pts, int n, float r2,
+                                                             uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
+                                                             uint32_t *__restrict__ neighbors)
+{
+	__shared__ float4 tile[RG_THREADS];
+	const int i = blockIdx.x * RG_THREADS + threadIdx.x;
+	float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (i < n)
+	{
+		const double *p = pts + (size_t)i * 4;
+		me = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]); // convertTo(CV_32F) (:115)
+	}
+	uint32_t found = 0;
+	uint32_t *out = FILL && i < n ? neighbors + offsets[i] : nullptr;
+	for (int j0 = 0; j0 < n; j0 += RG_THREADS)
+	{
+		const int j = j0 + threadIdx.x;
+		if (j < n)
+		{
+			const double *p = pts + (size_t)j * 4;
+			tile[threadIdx.x] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+		}
+		__syncthreads();
+		const int m = min(RG_THREADS, n - j0);
+		if (i < n)
+			for (int q = 0; q < m; ++q)
+			{
+				const float4 o = tile[q];
+				const float dx = me.x - o.x, dy = me.y - o.y, dz = me.z - o.z, dw = me.w - o.w;
+				const float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+				if (d2 < r2 && j0 + q != i) // RadiusResultSet keeps dist < radius; the query point itself is dropped (:131-133)
+				{
+					if (FILL) out[found] = (uint32_t)(j0 + q);
+					++found;
+				}
+			}
+		__syncthreads();
+	}
+	if (!FILL && i < n)
+		counts[i] = found;
+}
+
+extern "C" gcr_status gcr_radius_graph_count(gcr_ctx *ctx, int pair, double radius, uint32_t *d_counts)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0 || ctx->cols != 4)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_count: no 4-column points uploaded");
+	if (pair < 0 || pair >= ctx->n_pairs || !d_counts || !(radius > 0.0))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_radius_graph_count: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const float r = (float)radius;
+	k_radius_graph<false><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+	    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, d_counts, nullptr, nullptr);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_radius_graph_fill(gcr_ctx *ctx, int pair, double radius, const uint32_t *d_offsets, uint32_t *d_neighbors)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0 || ctx->cols != 4)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_fill: no 4-column points uploaded");
+	if (pair < 0 || pair >= ctx->n_pairs || !d_offsets || !d_neighbors || !(radius > 0.0))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_radius_graph_fill: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const float r = (float)radius;
+	k_radius_graph<true><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+	    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, nullptr, d_offsets, d_neighbors);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}

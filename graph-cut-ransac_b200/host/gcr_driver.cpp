@@ -144,6 +144,9 @@ namespace
 		// grid
 		std::vector<uint32_t> cell_of_point, sorted_idx, cell_offsets;
 		bool have_grid = false;
+		// radius neighbourhood (S.neighborhood == 1): CSR, neighbours ascending
+		std::vector<uint32_t> nbr_offsets, nbr_idx;
+		bool have_radius_graph = false;
 
 		bool fail(const char *what)
 		{
@@ -509,7 +512,23 @@ namespace
 				else
 					problem_graph->add_term1(i, 0, one_minus_lambda * (1 - tmp_energy));
 			}
-			if (lambda > 0 && have_grid)
+			if (lambda > 0 && have_radius_graph)
+			{
+				// every unordered pair of neighbours once (the reference's used_edges matrix, :963, does the same for its lists)
+				for (int i = 0; i < n; ++i)
+				{
+					const double energy1 = distance_per_threshold[i];
+					for (uint32_t q = nbr_offsets[i]; q < nbr_offsets[i + 1]; ++q)
+					{
+						const uint32_t j = nbr_idx[q];
+						if ((int)j <= i)
+							continue;
+						const double e00 = 0.5 * (energy1 + distance_per_threshold[j]);
+						problem_graph->add_term2(i, j, e00 * lambda, lambda, lambda, 0 * lambda);
+					}
+				}
+			}
+			else if (lambda > 0 && have_grid)
 			{
 				// the reference walks point_idx ascending and, per point, its cell's list ascending, skipping pairs already
 				// used (the N x N used_edges matrix, :963): exactly the pairs (i, j > i) of a cell, in this order
@@ -787,8 +806,46 @@ namespace
 			return true;
 		}
 
+		bool build_radius_graph()
+		{
+			have_radius_graph = false;
+			DeviceBuffer dc, doff, dn;
+			if (!dc.ensure(ctx, (size_t)n * 4) || !doff.ensure(ctx, (size_t)n * 4))
+				return fail("gcr_malloc");
+			if (gcr_radius_graph_count(ctx, 0, S.neighborhood_radius, dc.as<uint32_t>()) != GCR_OK)
+				return fail("gcr_radius_graph_count");
+			std::vector<uint32_t> counts(n);
+			if (gcr_memcpy_d2h(ctx, counts.data(), dc.p, (size_t)n * 4) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			nbr_offsets.assign((size_t)n + 1, 0u);
+			for (int i = 0; i < n; ++i)
+				nbr_offsets[i + 1] = nbr_offsets[i] + counts[i];
+			const size_t total = nbr_offsets[n];
+			nbr_idx.resize(total);
+			if (total)
+			{
+				if (!dn.ensure(ctx, total * 4))
+					return fail("gcr_malloc");
+				if (gcr_memcpy_h2d(ctx, doff.p, nbr_offsets.data(), (size_t)n * 4) != GCR_OK)
+					return fail("gcr_memcpy_h2d");
+				if (gcr_radius_graph_fill(ctx, 0, S.neighborhood_radius, doff.as<uint32_t>(), dn.as<uint32_t>()) != GCR_OK)
+					return fail("gcr_radius_graph_fill");
+				if (gcr_memcpy_d2h(ctx, nbr_idx.data(), dn.p, total * 4) != GCR_OK)
+					return fail("gcr_memcpy_d2h");
+			}
+			have_radius_graph = true;
+			return true;
+		}
+
 		bool build_grid()
 		{
+			if (S.neighborhood == 1)
+			{
+				have_grid = false;
+				if (!(S.spatial_coherence_weight > 0.0) || !S.do_local_optimization)
+					return true;
+				return build_radius_graph();
+			}
 			have_grid = false;
 			if (!(S.spatial_coherence_weight > 0.0) || !S.do_local_optimization)
 				return true;
@@ -1084,6 +1141,8 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->use_degensac = 0;
 	s->f_bundle_adjustment = 0;
 	s->sampler = 0;
+	s->neighborhood = 0;
+	s->neighborhood_radius = 20.0;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

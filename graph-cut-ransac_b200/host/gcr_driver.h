@@ -57,6 +57,11 @@ typedef struct gcr_run_settings
 	/* main sampler: 0 = uniform (samplers/uniform_sampler.h), 1 = PROSAC (samplers/prosac_sampler.h: the correspondences
 	 * are ordered by quality); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
 	int sampler;
+	/* neighbourhood of the graph-cut: 0 = GridNeighborhoodGraph<4> (cell_sizes / cells_per_axis above), 1 = the radius
+	 * neighbourhood of FlannNeighborhoodGraph (neighborhood/flann_neighborhood_graph.h:99-137; exact instead of FLANN's
+	 * approximate search), points within neighborhood_radius in the 4-D correspondence space */
+	int neighborhood;
+	double neighborhood_radius;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats

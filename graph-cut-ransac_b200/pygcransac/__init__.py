@@ -13,7 +13,9 @@ tricks of the reference; the GPU scores every point of every model, which yields
 so the flags are accepted and ignored.  `sampler` is 0 (uniform) or 1 (PROSAC, the reference's default: the
 correspondences are taken to be ordered by quality), both on the counter-based stream -- the stateful samplers
 (2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are host-side plug-ins of the reference's virtual Sampler interface and are not part of
-this path.  `neighborhood` must be 0 (grid) when `spatial_coherence_weight` > 0 (FLANN is out of scope).
+this path.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
+`neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
+approximate, run-dependent one).
 """
 import ctypes as C
 import os
@@ -37,7 +39,7 @@ class RunSettings(C.Structure):
                 ("max_unsuccessful_model_generations", C.c_uint64), ("do_local_optimization", C.c_int),
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
-                ("sampler", C.c_int)]
+                ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double)]
 
 
 class RunStats(C.Structure):
@@ -98,8 +100,8 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     if sampler not in (0, 1):
         raise NotImplementedError("sampler=%d: the uniform (0) and PROSAC (1) samplers run on the counter-based GPU stream; "
                                   "P-NAPSAC / NG-RANSAC / AR are host-side plug-ins of the reference" % sampler)
-    if spatial_coherence_weight > np.finfo(np.float64).eps and neighborhood != 0:
-        raise NotImplementedError("neighborhood=%d: only the grid neighbourhood (0) is built on the GPU" % neighborhood)
+    if neighborhood not in (0, 1):
+        raise ValueError("neighborhood should be 0 (grid) or 1 (radius)")
     lib = _load_driver()
     ctx = _context(device)
     s = RunSettings()
@@ -116,6 +118,10 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.seed = seed
     s.use_degensac = 1 if use_degensac else 0
     s.sampler = sampler
+    # neighborhood=1: the reference builds a FLANN radius graph with radius neighborhood_size (py/gcransac_python.cpp
+    # :123-125); here the exact radius graph (gcr_radius_graph_*).  The grid settings below are then unused.
+    s.neighborhood = neighborhood
+    s.neighborhood_radius = float(neighborhood_size)
     s.f_bundle_adjustment = f_bundle_adjustment
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)

@@ -29,7 +29,7 @@ EXPORTS = [
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
     "gcr_solve_plane_parallax", "gcr_refit_f_ba", "gcr_set_score_trace",
-    "gcr_memcpy_d2h_async",
+    "gcr_memcpy_d2h_async", "gcr_radius_graph_count", "gcr_radius_graph_fill",
 ]
 
 _lib = None
@@ -85,6 +85,8 @@ def load_library():
         "gcr_refit": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp]),
         "gcr_refit_f_ba": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp]),
         "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
+        "gcr_radius_graph_count": (i32, [vp, i32, f64, vp]),
+        "gcr_radius_graph_fill": (i32, [vp, i32, f64, vp, vp]),
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
         "gcr_round_results": (i32, [vp, vp, vp]),
         "gcr_getscore_host": (i32, [vp, i32, i32, i32, vp, f64, f64, C.POINTER(f64), C.POINTER(u32), vp]),
@@ -365,6 +367,24 @@ class Context:
         finally:
             for d in (dk, ds, do):
                 self.free(d)
+
+    def radius_graph(self, radius, pair=0):
+        """The exact radius neighbourhood graph (neighborhood=1): CSR offsets [n + 1] and neighbours (ascending)."""
+        dc = self.malloc(self.n * 4)
+        try:
+            self.check(self.lib.gcr_radius_graph_count(self.h, pair, radius, C.c_void_p(dc)))
+            counts = self.to_host(dc, (self.n,), np.uint32)
+            offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+            total = int(offsets[-1])
+            do, dn = self.to_device(offsets[:-1].copy()), self.malloc(max(total, 1) * 4)
+            try:
+                self.check(self.lib.gcr_radius_graph_fill(self.h, pair, radius, C.c_void_p(do), C.c_void_p(dn)))
+                return offsets, self.to_host(dn, (total,), np.uint32)
+            finally:
+                self.free(do)
+                self.free(dn)
+        finally:
+            self.free(dc)
 
     def round_results(self):
         """FP64 score and exact inlier count of each pair's winner of the last round."""

@@ -196,6 +196,13 @@ int gcr_max_refit_models(int problem);
 gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell_sizes[4], uint64_t cells_per_axis,
                           uint64_t *d_keys, uint32_t *d_sorted_idx, uint32_t *d_cell_offsets, uint32_t *h_n_cells,
                           uint64_t *h_neighbor_number);
+/* FlannNeighborhoodGraph::initialize (neighborhood/flann_neighborhood_graph.h:99-137) -- the neighbourhood the Python
+ * entry points use for neighborhood=1: every point's neighbours within `radius` (L2 over the four FP32 coordinates,
+ * strict <, the point itself excluded).  The reference's answer comes from OpenCV's approximate FLANN search; this is
+ * the exact graph.  Two passes around a host prefix sum: d_counts [n] neighbours per point; then, with d_offsets [n]
+ * the exclusive prefix of the counts, d_neighbors receives every point's neighbours in ascending index order. */
+gcr_status gcr_radius_graph_count(gcr_ctx *ctx, int pair, double radius, uint32_t *d_counts);
+gcr_status gcr_radius_graph_fill(gcr_ctx *ctx, int pair, double radius, const uint32_t *d_offsets, uint32_t *d_neighbors);
 
 /* ---- fused fixed-K round (the benchmarked step) ------------------------------------------------------------ */
 /* One pass of the hot path over every pair on the context: K1 sample `count` minimal samples -> K2 solve -> K3

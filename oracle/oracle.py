@@ -357,17 +357,20 @@ class Ref:
         lib.ref_run.restype = C.c_int
         lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
-                                _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int]
+                                _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+        lib.ref_radius_graph.restype = C.c_uint64
+        lib.ref_radius_graph.argtypes = [_dp, C.c_int, C.c_double, _u32p, _u32p, C.c_uint64]
 
     def round(self, problem, scoring, pts, seed, first, count, thr):
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
-            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0):
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0, radius=0.0):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  f_ba (F): bit 0 = the BA non-minimal solver (the reference's default estimator),
         bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  sampler: 0 = uniform, 1 = PROSAC (the points
-        are taken to be ordered by quality).  scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
+        are taken to be ordered by quality).  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
+        scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
         model = np.zeros(9)
@@ -377,7 +380,7 @@ class Ref:
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
                                  C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data,
-                                 1 if use_degensac else 0, f_ba, sampler)
+                                 1 if use_degensac else 0, f_ba, sampler, radius)
         if n_inl < 0:
             raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
         names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",
@@ -418,6 +421,16 @@ class Ref:
 
     def iteration_number(self, inliers, n, m, log_probability):
         return self.lib.ref_iteration_number(inliers, n, m, log_probability)
+
+    def radius_graph(self, pts, radius):
+        """CSR (offsets [n + 1], neighbours) of the exact radius neighbourhood the verbatim driver runs on for radius > 0."""
+        pts = _as_pts(pts)
+        n = len(pts)
+        offsets = np.empty(n + 1, dtype=np.uint32)
+        total = self.lib.ref_radius_graph(pts, n, radius, offsets, np.empty(1, dtype=np.uint32), 0)
+        nbrs = np.empty(max(int(total), 1), dtype=np.uint32)
+        self.lib.ref_radius_graph(pts, n, radius, offsets, nbrs, total)
+        return offsets, nbrs[:total]
 
 
 class RefCuda(Ref):

@@ -365,6 +365,9 @@ void ref_round(int problem, int scoring, const double *pts, int n, uint64_t seed
 #undef GCR_RR
 }
 
+// the exact radius neighbourhood (ExactRadiusGraph below is the class the verbatim driver runs on): CSR
+uint64_t ref_radius_graph(const double *pts, int n, double radius, uint32_t *offsets /* n + 1 */, uint32_t *neighbors, uint64_t capacity);
+
 uint64_t ref_iteration_number(uint64_t inliers, uint64_t n, int m, double log_probability)
 {
 	IterProbe p;
@@ -496,20 +499,83 @@ namespace
 		return true;
 	}
 
+	// The neighbourhood of neighborhood=1 (neighborhood/flann_neighborhood_graph.h:99-137) without FLANN: every point's
+	// neighbours within `radius` (L2 over the four coordinates converted to FP32 as :115 does, strict <, the point itself
+	// dropped as :131-133 drop the first match).  The reference's lists are what OpenCV's approximate kd-tree search
+	// (4 trees, 6 checks) happens to return; this is the exact graph, in ascending index order.
+	class ExactRadiusGraph : public neighborhood::NeighborhoodGraph<cv::Mat>
+	{
+		double radius;
+		std::vector<std::vector<size_t>> neighbours;
+		std::vector<double> no_cell_sizes;
+		std::unordered_map<size_t, std::pair<std::vector<size_t>, std::vector<size_t>>> no_cells;
+
+	public:
+		ExactRadiusGraph(const cv::Mat *c, double r) : neighborhood::NeighborhoodGraph<cv::Mat>(c), radius(r) { initialized = initialize(c); }
+		bool initialize(const cv::Mat *const c)
+		{
+			const int n = c->rows;
+			const double *p = reinterpret_cast<const double *>(c->data);
+			std::vector<float> f((size_t)n * 4);
+			for (size_t i = 0; i < f.size(); ++i) f[i] = (float)p[i];
+			const float r = (float)radius, r2 = r * r;
+			neighbours.assign(n, std::vector<size_t>());
+			neighbor_number = 0;
+			for (int i = 0; i < n; ++i)
+			{
+				for (int j = 0; j < n; ++j)
+				{
+					const float dx = f[4 * i] - f[4 * j], dy = f[4 * i + 1] - f[4 * j + 1], dz = f[4 * i + 2] - f[4 * j + 2],
+					            dw = f[4 * i + 3] - f[4 * j + 3];
+					const float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+					if (d2 < r2 && j != i)
+						neighbours[i].push_back((size_t)j);
+				}
+				neighbor_number += neighbours[i].size();
+			}
+			return neighbor_number > 0;
+		}
+		const std::vector<size_t> &getNeighbors(size_t i) const { return neighbours[i]; }
+		const std::vector<double> &getCellSizes() const { return no_cell_sizes; }
+		const std::unordered_map<size_t, std::pair<std::vector<size_t>, std::vector<size_t>>> &getCells() const { return no_cells; }
+		size_t getDivisionNumber() const { return 0; }
+		size_t filledCellNumber() const { return neighbours.size(); }
+	};
+
+	template <int PROBLEM, class Scoring, class Graph>
+	int run_reference_on(Graph &graph, const cv::Mat &points, int cells_per_axis, double threshold, double conf,
+	                     double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
+	                     uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac, int f_ba, int sampler_id);
+
+	// radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid (neighborhood=0)
 	template <int PROBLEM, class Scoring>
 	int run_reference(const cv::Mat &points, const cv::Mat &grid_points, const double *cell_sizes, int cells_per_axis, double threshold, double conf,
 	                  double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
 	                  uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac = 0, int f_ba = 0,
-	                  int sampler_id = 0)
+	                  int sampler_id = 0, double radius = 0.0)
+	{
+		if (radius > 0.0)
+		{
+			ExactRadiusGraph graph(&grid_points, radius);
+			return run_reference_on<PROBLEM, Scoring>(graph, points, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters,
+			                                          lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id);
+		}
+		std::vector<double> cs(cell_sizes, cell_sizes + 4);
+		neighborhood::GridNeighborhoodGraph<4> graph(&grid_points, cs, (size_t)cells_per_axis);
+		return run_reference_on<PROBLEM, Scoring>(graph, points, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters,
+		                                          lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id);
+	}
+
+	template <int PROBLEM, class Scoring, class Grid>
+	int run_reference_on(Grid &graph, const cv::Mat &points, int cells_per_axis, double threshold, double conf,
+	                     double spatial_weight, int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out,
+	                     uint8_t *inlier_mask, uint64_t *stats_out, double *score_out, int use_degensac, int f_ba, int sampler_id)
 	{
 		typedef OracleEstimator<PROBLEM> Est;
-		typedef neighborhood::GridNeighborhoodGraph<4> Grid;
 		Est estimator;
 		estimator.use_degensac = use_degensac != 0;
 		estimator.f_nonminimal_ba = (f_ba & 1) != 0;
 		estimator.seed = seed;
-		std::vector<double> cs(cell_sizes, cell_sizes + 4);
-		Grid graph(&grid_points, cs, (size_t)cells_per_axis); // E: built on the pixel coordinates (py/gcransac_python.cpp:2592-2600)
 		// sampler_id 1 = PROSAC main sampler (py/gcransac_python.cpp:4320-4323); the LO sampler is uniform either way
 		// (stream 2 then: PROSAC draws use stream 1)
 		CounterSampler uniform_sampler(&points, seed, 0u), lo_sampler(&points, seed, sampler_id == 1 ? 2u : 1u);
@@ -595,11 +661,11 @@ extern "C" {
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
-            const double *grid_pts, int use_degensac, int f_ba, int sampler_id)
+            const double *grid_pts, int use_degensac, int f_ba, int sampler_id, double radius)
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
 	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
-#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id)
+#define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id, radius)
 	if (scoring_kind == 0)
 	{
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);
@@ -621,6 +687,24 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
 #endif
 #undef GCR_RUN
 	return -2;
+}
+
+uint64_t ref_radius_graph(const double *pts, int n, double radius, uint32_t *offsets, uint32_t *neighbors, uint64_t capacity)
+{
+	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
+	ExactRadiusGraph g(&points, radius);
+	uint64_t total = 0;
+	for (int i = 0; i < n; ++i)
+	{
+		offsets[i] = (uint32_t)total;
+		for (size_t j : g.getNeighbors(i))
+		{
+			if (total < capacity) neighbors[total] = (uint32_t)j;
+			++total;
+		}
+	}
+	offsets[n] = (uint32_t)total;
+	return total;
 }
 
 } // extern "C"

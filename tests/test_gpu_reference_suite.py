@@ -4,7 +4,7 @@ intrinsics for E -- SIFT tentatives extracted exactly as those tests do (committ
 oracle/gen_fountain_fixture.py).  Each test keeps the reference's inlier-count floor (> 250, > 380, > 450) and adds what
 the reference cannot check: equality with its verbatim GCRANSAC<> driver on the same sample streams.  Differences from
 the reference's calls: sampler=1 (PROSAC) where they pass 2 / 4 (P-NAPSAC / AR: host-side plug-ins, not on this path),
-and the grid neighbourhood where findEssentialMatrix defaults to FLANN."""
+and, for neighborhood=1, the exact radius graph where the reference asks FLANN for an approximate one."""
 import os
 
 import numpy as np
@@ -81,3 +81,22 @@ def test_find_essential_matrix(pyg, ref, oracle):
     assert st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2, (int(mask.sum()), int(want["mask"].sum()))
     assert _up_to_scale(want["model"], E) < 1e-5
+
+
+def test_find_essential_matrix_default_arguments(pyg, ref, oracle):
+    """The reference's call verbatim but for the sampler: every default of findEssentialMatrix, i.e. neighborhood=1 (radius
+    20 px around each correspondence in the 4-D space) with spatial_coherence_weight 0.1."""
+    g = np.load(os.path.join(GOLDEN, "fountain_matches.npz"))
+    pts, K1, K2 = np.ascontiguousarray(g["pts"]), g["K1"], g["K2"]
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    E, mask = pyg.findEssentialMatrix(pts, K1, K2, h1, w1, h2, w2, probabilities=[], threshold=0.75, conf=0.99, min_iters=50,
+                                      max_iters=5000, sampler=1)
+    st = pyg.last_statistics
+    assert E is not None and mask.sum() > 450
+    npts = oracle.normalize_correspondences(pts.astype(np.float64), K1, K2)
+    thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
+    want = ref.run(O.E, npts, np.ones(4), 20, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50,
+                   seed=1, grid_pts=pts.astype(np.float64), sampler=1, radius=20.0)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert st["graph_cut_number"] == want["stats"]["graph_cuts"] and st["lo_samples"] == want["stats"]["lo_samples"]
+    assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5

@@ -203,3 +203,22 @@ def test_grid_second_pair_and_errors(gcr_ctx, oracle):
     assert np.array_equal(got["sorted_idx"], want["sorted_idx"]) and got["neighbor_number"] == want["neighbor_number"]
     with pytest.raises(_cabi.GcrError):
         gcr_ctx.grid_build(np.array([0.0, 1.0, 1.0, 1.0]), 4)
+
+
+def test_radius_graph_bit_exact(gcr_ctx, ref):
+    """neighborhood=1: the exact radius neighbourhood (FlannNeighborhoodGraph's contract without FLANN's approximation)
+    against the graph class the verbatim reference driver runs on, and against numpy."""
+    for n, radius, seed in ((700, 20.0, 61), (3000, 35.0, 62), (257, 500.0, 63)):
+        pts, _, _ = synth.homography_pair(n, 0.4, seed=seed)
+        pts[5] = pts[6]                                              # a duplicate point is a neighbour at distance 0
+        gcr_ctx.points_upload(pts)
+        off, nbr = gcr_ctx.radius_graph(radius)
+        want_off, want_nbr = ref.radius_graph(pts, radius)
+        assert np.array_equal(off, want_off) and np.array_equal(nbr, want_nbr)
+        f = pts.astype(np.float32)
+        d = f[:, None, :] - f[None, :, :]
+        d2 = ((d[..., 0] ** 2 + d[..., 1] ** 2) + d[..., 2] ** 2) + d[..., 3] ** 2
+        A = (d2 < np.float32(radius) ** 2) & ~np.eye(n, dtype=bool)
+        assert np.array_equal(np.nonzero(A)[1].astype(np.uint32), nbr) and len(nbr) > 0
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.radius_graph(0.0)
