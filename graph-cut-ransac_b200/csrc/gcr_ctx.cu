@@ -442,20 +442,12 @@ __device__ __forceinline__ double pow2_scale(double half_extent)
 	return ldexp(1.0, -e);
 }
 
+// centre + power-of-two scale of the primed frame from the bounding box
 template <int COLS>
-__global__ void k_norm(const unsigned long long *bbox, double *norm, int n_pairs)
+__device__ __forceinline__ void norm_from_bbox(double (&mn)[COLS], double (&mx)[COLS], double *o)
 {
-	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-	if (pair >= n_pairs)
-		return;
-	double mn[COLS], mx[COLS];
 	for (int c = 0; c < COLS; ++c)
-	{
-		mn[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 0]);
-		mx[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 1]);
 		if (!(mn[c] <= mx[c])) { mn[c] = 0.0; mx[c] = 0.0; }
-	}
-	double *o = norm + (size_t)pair * 8;
 	if (COLS == 4)
 	{
 		double h = 0.0;
@@ -484,6 +476,125 @@ __global__ void k_norm(const unsigned long long *bbox, double *norm, int n_pairs
 }
 
 template <int COLS>
+__global__ void k_norm(const unsigned long long *bbox, double *norm, int n_pairs)
+{
+	const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pair >= n_pairs)
+		return;
+	double mn[COLS], mx[COLS];
+	for (int c = 0; c < COLS; ++c)
+	{
+		mn[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 0]);
+		mx[c] = gcr_from_ordered_u64(bbox[((size_t)pair * COLS + c) * 2 + 1]);
+	}
+	norm_from_bbox<COLS>(mn, mx, norm + (size_t)pair * 8);
+}
+
+// the operand-duplicated FP32 copy of point i of a pair (or the NaN padding row)
+template <int COLS>
+__device__ __forceinline__ void convert_point(const double *__restrict__ pts_pair, const double *nm, int n, int i, float4 *__restrict__ out_pair)
+{
+	const float nanv = __int_as_float(0x7fc00000);
+	if (COLS == 4)
+	{
+		float4 q = make_float4(nanv, nanv, nanv, nanv);
+		if (i < n)
+		{
+			const double *p = pts_pair + (size_t)i * 4;
+			const double s = nm[4];
+			q.x = (float)((p[0] - nm[0]) * s);
+			q.y = (float)((p[1] - nm[1]) * s);
+			q.z = (float)((p[2] - nm[2]) * s);
+			q.w = (float)((p[3] - nm[3]) * s);
+		}
+		out_pair[(size_t)i * 2 + 0] = make_float4(q.x, q.x, q.y, q.y);
+		out_pair[(size_t)i * 2 + 1] = make_float4(q.z, q.z, q.w, q.w);
+	}
+	else
+	{
+		float4 a = make_float4(nanv, nanv, 0.f, 0.f), b = make_float4(nanv, nanv, nanv, 0.f);
+		if (i < n)
+		{
+			const double *p = pts_pair + (size_t)i * 5;
+			a.x = (float)((p[0] - nm[0]) * nm[2]);
+			a.y = (float)((p[1] - nm[1]) * nm[2]);
+			b.x = (float)((p[2] - nm[3]) * nm[6]);
+			b.y = (float)((p[3] - nm[4]) * nm[6]);
+			b.z = (float)((p[4] - nm[5]) * nm[6]);
+		}
+		out_pair[(size_t)i * 2 + 0] = a;
+		out_pair[(size_t)i * 2 + 1] = b;
+	}
+}
+
+// K0 in ONE launch for pairs of up to 32768 points: one CTA per pair finds the bounding box (min / max are exact and
+// order-independent: the same box as the atomic version), derives the frame and converts the pair's points.  The four
+// separate launches below cost ~12 us of launch latency on a 128 KB upload.
+#define K0_FUSED_THREADS 1024
+#define K0_FUSED_MAX_POINTS 32768
+template <int COLS>
+__global__ void __launch_bounds__(K0_FUSED_THREADS) k_prepare_fused(const double *__restrict__ pts, int n, int n_pad,
+                                                                  double *__restrict__ norm, float4 *__restrict__ out32)
+{
+	__shared__ double s_mn[32][COLS], s_mx[32][COLS];
+	__shared__ double s_nm[8];
+	const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const double *p = pts + (size_t)pair * n * COLS;
+	double mn[COLS], mx[COLS];
+#pragma unroll
+	for (int c = 0; c < COLS; ++c)
+	{
+		mn[c] = INFINITY;
+		mx[c] = -INFINITY;
+	}
+	for (int i = tid; i < n; i += K0_FUSED_THREADS)
+#pragma unroll
+		for (int c = 0; c < COLS; ++c)
+		{
+			const double v = p[(size_t)i * COLS + c];
+			if (v < mn[c]) mn[c] = v;
+			if (v > mx[c]) mx[c] = v;
+		}
+#pragma unroll
+	for (int c = 0; c < COLS; ++c)
+	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			const double a = __shfl_xor_sync(0xffffffffu, mn[c], o), b = __shfl_xor_sync(0xffffffffu, mx[c], o);
+			if (a < mn[c]) mn[c] = a;
+			if (b > mx[c]) mx[c] = b;
+		}
+		if (lane == 0)
+		{
+			s_mn[warp][c] = mn[c];
+			s_mx[warp][c] = mx[c];
+		}
+	}
+	__syncthreads();
+	if (tid == 0)
+	{
+		for (int w = 1; w < K0_FUSED_THREADS / 32; ++w)
+			for (int c = 0; c < COLS; ++c)
+			{
+				if (s_mn[w][c] < mn[c]) mn[c] = s_mn[w][c];
+				if (s_mx[w][c] > mx[c]) mx[c] = s_mx[w][c];
+			}
+		double o[8];
+		norm_from_bbox<COLS>(mn, mx, o);
+		for (int j = 0; j < 8; ++j)
+		{
+			s_nm[j] = o[j];
+			norm[(size_t)pair * 8 + j] = o[j];
+		}
+	}
+	__syncthreads();
+	float4 *out_pair = out32 + (size_t)pair * n_pad * 2;
+	for (int i = tid; i < n_pad; i += K0_FUSED_THREADS)
+		convert_point<COLS>(p, s_nm, n, i, out_pair);
+}
+
+template <int COLS>
 __global__ void __launch_bounds__(256) k_convert(const double *__restrict__ pts, const double *__restrict__ norm,
                                                   int n, int n_pad, float4 *__restrict__ out32)
 {
@@ -491,38 +602,7 @@ __global__ void __launch_bounds__(256) k_convert(const double *__restrict__ pts,
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_pad)
 		return;
-	const double *nm = norm + (size_t)pair * 8;
-	const float nanv = __int_as_float(0x7fc00000);
-	if (COLS == 4)
-	{
-		float4 q = make_float4(nanv, nanv, nanv, nanv);
-		if (i < n)
-		{
-			const double *p = pts + ((size_t)pair * n + i) * 4;
-			const double s = nm[4];
-			q.x = (float)((p[0] - nm[0]) * s);
-			q.y = (float)((p[1] - nm[1]) * s);
-			q.z = (float)((p[2] - nm[2]) * s);
-			q.w = (float)((p[3] - nm[3]) * s);
-		}
-		out32[((size_t)pair * n_pad + i) * 2 + 0] = make_float4(q.x, q.x, q.y, q.y);
-		out32[((size_t)pair * n_pad + i) * 2 + 1] = make_float4(q.z, q.z, q.w, q.w);
-	}
-	else
-	{
-		float4 a = make_float4(nanv, nanv, 0.f, 0.f), b = make_float4(nanv, nanv, nanv, 0.f);
-		if (i < n)
-		{
-			const double *p = pts + ((size_t)pair * n + i) * 5;
-			a.x = (float)((p[0] - nm[0]) * nm[2]);
-			a.y = (float)((p[1] - nm[1]) * nm[2]);
-			b.x = (float)((p[2] - nm[3]) * nm[6]);
-			b.y = (float)((p[3] - nm[4]) * nm[6]);
-			b.z = (float)((p[4] - nm[5]) * nm[6]);
-		}
-		out32[((size_t)pair * n_pad + i) * 2 + 0] = a;
-		out32[((size_t)pair * n_pad + i) * 2 + 1] = b;
-	}
+	convert_point<COLS>(pts + (size_t)pair * n * COLS, norm + (size_t)pair * 8, n, i, out32 + (size_t)pair * n_pad * 2);
 }
 
 static gcr_status prepare_points(gcr_ctx *ctx)
@@ -549,6 +629,15 @@ static gcr_status prepare_points(gcr_ctx *ctx)
 		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_norm, (size_t)n_pairs * 8 * sizeof(double)));
 		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_bbox, (size_t)n_pairs * 5 * 2 * sizeof(unsigned long long)));
 		ctx->norm_capacity = n_pairs;
+	}
+	if (n <= K0_FUSED_MAX_POINTS)
+	{
+		if (cols == 4)
+			k_prepare_fused<4><<<n_pairs, K0_FUSED_THREADS, 0, ctx->stream>>>(ctx->d_pts64, n, ctx->n_pad, ctx->d_norm, ctx->d_pts32);
+		else
+			k_prepare_fused<5><<<n_pairs, K0_FUSED_THREADS, 0, ctx->stream>>>(ctx->d_pts64, n, ctx->n_pad, ctx->d_norm, ctx->d_pts32);
+		GCR_LAUNCHED(ctx);
+		return GCR_OK;
 	}
 	const int entries = n_pairs * cols * 2;
 	k_bbox_init<<<(entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_bbox, entries);
