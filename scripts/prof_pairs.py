@@ -1,3 +1,4 @@
+"""Per-phase latency of the full pipelines on one host thread (gcr_run_stats.phase_seconds): F plain / F default / H / E."""
 import sys, time
 sys.path.insert(0,'graph-cut-ransac_b200')
 import numpy as np
