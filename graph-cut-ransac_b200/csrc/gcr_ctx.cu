@@ -90,15 +90,21 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	return GCR_OK;
 }
 
+static gcr_status flush_d2h(gcr_ctx *ctx);
 extern "C" gcr_status gcr_ctx_set_stream(gcr_ctx *ctx, void *cuda_stream)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
+	if (ctx->stage_off || !ctx->pending_d2h.empty())
+	{
+		gcr_status st = flush_d2h(ctx); // copies queued on the old stream are completed on it
+		if (st)
+			return st;
+	}
 	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
 	return GCR_OK;
 }
 
-static gcr_status flush_d2h(gcr_ctx *ctx);
 extern "C" gcr_status gcr_sync(gcr_ctx *ctx)
 {
 	if (!ctx)
