@@ -35,7 +35,8 @@ WORKLOADS = {
     "f4k": dict(problem="f", n=4096, outliers=0.5, thr=0.75, samples=262144, pairs=1,
                 desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
     "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
-                      desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 (configs[3])"),
+                      desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 + argmax + final "
+                           "least-squares refit per pair (configs[3])"),
     # configs[2]: E, 5-point + MAGSAC++ on K-normalised correspondences (threshold / focal length), 85 % outliers
     "e2k": dict(problem="e", scoring="magsac", n=2048, outliers=0.85, thr=0.75 / 1000.0, samples=65536, pairs=1,
                 desc="E 5-pt (Nister) + MAGSAC++, N=2048, 85% outliers, known K, thr 0.75 px / f, single pair (configs[2])"),
@@ -454,7 +455,26 @@ def main():
 
     hyps_sharded = wl.get("shard") == "hyps"
 
+    # configs[3] = "fixed K hypotheses per pair + argmax + one final least-squares refit" (SURVEY.md 8d): the refit tail
+    # for every pair of the batch, device-resident, two launches (inliers of the winners, one fit per pair)
+    refit_tail = n_pairs > 1 and not wl.get("shard")
+    if refit_tail:
+        t_idx = torch.empty(n_pairs, n, dtype=torch.int32, device="cuda")
+        t_cnt = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
+        t_sc = torch.empty(n_pairs, dtype=torch.float64, device="cuda")
+        t_refit = torch.empty(n_pairs, 9, dtype=torch.float64, device="cuda")
+        t_ok = torch.empty(n_pairs, dtype=torch.uint8, device="cuda")
+
+    def tail(c, lo, hi):
+        c.final_refit_pairs(prob, best[lo:hi].data_ptr(), wl["thr"], t_idx[lo:hi].data_ptr(), t_cnt[lo:hi].data_ptr(),
+                            t_sc[lo:hi].data_ptr(), t_refit[lo:hi].data_ptr(), t_ok[lo:hi].data_ptr())
+
     def one_round(i):
+        if refit_tail:
+            ev = ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"], flags, 0,
+                                  keys.data_ptr(), best.data_ptr())
+            tail(ctx, 0, n_pairs)
+            return ev
         if hyps_sharded:
             from pygcransac import sharded
             return sharded.sharded_round(ctx, prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
@@ -499,8 +519,9 @@ def main():
                 c2.check(c2.lib.gcr_points_upload(c2.h, pts_host[lo:hi].data_ptr(), n, 4, hi - lo))
                 ev += c2.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345 + c, wl["thr"], flags, 0,
                                       keys[lo:hi].data_ptr(), best[lo:hi].data_ptr())
+                tail(c2, lo, hi)
                 keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
-                best_host[lo:hi].copy_(best[lo:hi], non_blocking=True)
+                best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
         for c2, s2 in side:
             done = torch.cuda.Event()
             done.record(s2)
@@ -587,6 +608,10 @@ def main():
             "higher_is_better": True, "scaling": "strong" if hyps_sharded else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
+                       "pairs_per_s": (world * n_pairs * args.steps / (ms * 1e-3)) if n_pairs > 1 else None,
+                       "pairs_per_s_e2e": (world * n_pairs * args.steps / (ms_e2e * 1e-3)) if n_pairs > 1 else None,
+                       "step": "gcr_round (K1-K4)" + (" + inliers of every pair's winner + one least-squares refit per pair"
+                                                       if refit_tail else ""),
                        "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
                        "k3_exact_counts": bool(args.exact_counts), "winner": "FP64 re-score of the near-best candidates (K4)", "k3_variant": args.variant,
                        "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs)",

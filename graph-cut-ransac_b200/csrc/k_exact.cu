@@ -24,6 +24,7 @@ struct ExactArgs
 	int n, k;
 	double thr;
 	double T_override; // > 0: squared truncated threshold handed over as is (ScoringFunction::initialize), else from thr
+	size_t pair_stride; // 0: every model against the selected pair; n * cols: model m against pair m (one model per pair)
 };
 
 template <int PROBLEM, int SCORING>
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_score_exact(const ExactArgs a)
 		{
 			double pt[COLS];
 			for (int c = 0; c < COLS; ++c)
-				pt[c] = a.pts[(size_t)i * COLS + c];
+				pt[c] = a.pts[(size_t)model * a.pair_stride + (size_t)i * COLS + c];
 			const double r2 = gcr_sqres64<PROBLEM>(pt, M);
 			if (a.residuals)
 				a.residuals[(size_t)model * a.n + i] = r2;
@@ -173,6 +174,14 @@ extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, in
 	                        d_residuals);
 }
 
+extern "C" gcr_status gcr_score_exact_pairs(gcr_ctx *ctx, int problem, int scoring, const double *d_models, double threshold,
+                                            double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	return score_exact_impl(ctx, problem, scoring, -1, d_models, ctx->n_pairs, threshold, 0.0, d_scores, d_counts, d_inlier_idx, nullptr);
+}
+
 static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                    double threshold, double T_override, double *d_scores, uint32_t *d_counts,
                                    uint32_t *d_inlier_idx, double *d_residuals)
@@ -183,7 +192,8 @@ static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int p
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_score_exact: no points uploaded");
 	if (problem < GCR_H || problem > GCR_PNP || gcr_cols_of(problem) != ctx->cols)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: problem does not match the uploaded points");
-	if (pair < 0 || pair >= ctx->n_pairs || k <= 0 || !d_models || !d_scores || !d_counts)
+	// pair == -1 (internal, gcr_score_exact_pairs): k == n_pairs models, model m scored against pair m
+	if (pair < -1 || pair >= ctx->n_pairs || (pair == -1 && k != ctx->n_pairs) || k <= 0 || !d_models || !d_scores || !d_counts)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (scoring == GCR_MAGSAC)
@@ -193,7 +203,7 @@ static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int p
 			return lst;
 	}
 	ExactArgs a;
-	a.pts = ctx->d_pts64 + (size_t)pair * ctx->n * ctx->cols;
+	a.pts = pair < 0 ? ctx->d_pts64 : ctx->d_pts64 + (size_t)pair * ctx->n * ctx->cols;
 	a.models = d_models;
 	a.lut64 = ctx->d_magsac_lut64;
 	a.scores = d_scores;
@@ -204,6 +214,12 @@ static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int p
 	a.k = k;
 	a.thr = threshold;
 	a.T_override = T_override;
+	a.pair_stride = 0;
+	if (pair < 0) // gcr_score_exact_pairs: model m belongs to pair m
+	{
+		a.pts = ctx->d_pts64;
+		a.pair_stride = (size_t)ctx->n * ctx->cols;
+	}
 #define GCR_EX(P)                                                                                        \
 	do                                                                                                   \
 	{                                                                                                    \

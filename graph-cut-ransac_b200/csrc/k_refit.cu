@@ -50,6 +50,9 @@ struct RefitArgs
 	double *models; // [count][R][9], R = gcr_max_refit_models(problem)
 	uint8_t *ok;    // [count][R]
 	int ba_frame;   // F only: 0 = linear 8-point fit; GCR_BA_HARTLEY / GCR_BA_PIXEL = + LM bundle adjustment in that frame
+	// gcr_refit_pairs: set s belongs to pair s -- its indices start at sets + s * set_stride (offsets == null) and point into
+	// pts + s * pair_stride
+	size_t pair_stride, set_stride;
 };
 
 // fixed-tree block sum of NV values per thread; result valid in out[] for every thread after the call
@@ -493,13 +496,15 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 }
 
 template <int PROBLEM, int BA = 0>
-__global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit(const RefitArgs a)
+__global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit(const RefitArgs a_in)
 {
+	RefitArgs a = a_in;
+	a.pts += (size_t)blockIdx.x * a_in.pair_stride;
 	constexpr int NV = PROBLEM == GCR_H ? 44 : 45;
 	__shared__ double red[(BA != 0 ? RF_MAX_WARPS : RF_WARPS) * 45];
 	__shared__ double tot[45];
 	const int set = blockIdx.x, tid = threadIdx.x;
-	const uint32_t *idx = a.sets + a.offsets[set];
+	const uint32_t *idx = a.offsets ? a.sets + a.offsets[set] : a.sets + (size_t)set * a.set_stride;
 	const int n = (int)a.sizes[set];
 	const int min_n = PROBLEM == GCR_H ? 4 : 8;
 	if (n < min_n)
@@ -998,6 +1003,7 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 	a.models = d_models;
 	a.ok = d_ok;
 	a.ba_frame = ba_frame;
+	a.pair_stride = a.set_stride = 0;
 	if (problem == GCR_H)
 		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else if (problem == GCR_E)
@@ -1008,6 +1014,38 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 		k_refit<GCR_F, GCR_BA_PIXEL><<<count, count == 1 ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
 	else
 		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+// One non-minimal fit per pair of the context, all pairs in one launch: set p = the first d_sizes[p] entries of
+// d_index_sets[p][n] (e.g. the inlier lists gcr_score_exact_pairs wrote), fitted to pair p's points.  H and F (8-point).
+extern "C" gcr_status gcr_refit_pairs(gcr_ctx *ctx, int problem, const uint32_t *d_index_sets, const uint32_t *d_sizes,
+                                      double *d_models, uint8_t *d_ok)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_refit_pairs: no points uploaded");
+	if (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F) || !d_index_sets || !d_sizes || !d_models || !d_ok)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_pairs: H or F (8-point) on 4-column points");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	RefitArgs a;
+	a.pts = ctx->d_pts64;
+	a.sets = d_index_sets;
+	a.offsets = nullptr;
+	a.sizes = d_sizes;
+	a.weights = nullptr;
+	a.weight_mode = GCR_WEIGHT_NONE;
+	a.models = d_models;
+	a.ok = d_ok;
+	a.ba_frame = 0;
+	a.pair_stride = (size_t)ctx->n * 4;
+	a.set_stride = (size_t)ctx->n;
+	if (problem == GCR_H)
+		k_refit<GCR_H><<<ctx->n_pairs, RF_THREADS, 0, ctx->stream>>>(a);
+	else
+		k_refit<GCR_F><<<ctx->n_pairs, RF_THREADS, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }

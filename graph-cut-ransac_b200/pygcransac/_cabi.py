@@ -30,6 +30,7 @@ EXPORTS = [
     "gcr_profile_read", "gcr_counters_read", "gcr_round_results", "gcr_getscore_host", "gcr_max_refit_models",
     "gcr_solve_plane_parallax", "gcr_refit_f_ba", "gcr_set_score_trace",
     "gcr_memcpy_d2h_async", "gcr_radius_graph_count", "gcr_radius_graph_fill",
+    "gcr_score_exact_pairs", "gcr_refit_pairs",
 ]
 
 _lib = None
@@ -87,6 +88,8 @@ def load_library():
         "gcr_grid_build": (i32, [vp, i32, vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64)]),
         "gcr_radius_graph_count": (i32, [vp, i32, f64, vp]),
         "gcr_radius_graph_fill": (i32, [vp, i32, f64, vp, vp]),
+        "gcr_score_exact_pairs": (i32, [vp, i32, i32, vp, f64, vp, vp, vp]),
+        "gcr_refit_pairs": (i32, [vp, i32, vp, vp, vp, vp]),
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
         "gcr_round_results": (i32, [vp, vp, vp]),
         "gcr_getscore_host": (i32, [vp, i32, i32, i32, vp, f64, f64, C.POINTER(f64), C.POINTER(u32), vp]),
@@ -385,6 +388,13 @@ class Context:
                 self.free(dn)
         finally:
             self.free(dc)
+
+    def final_refit_pairs(self, problem, d_models, thr, d_idx, d_counts, d_scores, d_refit, d_ok):
+        """Device-resident tail of the batched configuration: inliers of every pair's model, then one refit per pair."""
+        self.check(self.lib.gcr_score_exact_pairs(self.h, problem, MSAC, C.c_void_p(d_models), thr, C.c_void_p(d_scores),
+                                                  C.c_void_p(d_counts), C.c_void_p(d_idx)))
+        self.check(self.lib.gcr_refit_pairs(self.h, problem, C.c_void_p(d_idx), C.c_void_p(d_counts), C.c_void_p(d_refit),
+                                            C.c_void_p(d_ok)))
 
     def round_results(self):
         """FP64 score and exact inlier count of each pair's winner of the last round."""

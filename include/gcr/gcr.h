@@ -135,6 +135,11 @@ gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const double *d_mod
 gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                            double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
                            double *d_residuals);
+/* the same for a batch of pairs: one model per pair (d_models [n_pairs][9|12]), every pair in one launch; outputs
+ * [n_pairs], d_inlier_idx [n_pairs][n] or NULL.  With gcr_refit_pairs: the "argmax + one final least-squares refit" tail
+ * of the batched configuration (SURVEY.md 8d cfg 4; GCRANSAC.h:588-617 per pair) */
+gcr_status gcr_score_exact_pairs(gcr_ctx *ctx, int problem, int scoring, const double *d_models, double threshold,
+                                 double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx);
 /* host-pointer convenience wrappers (H2D of models, D2H of results inside) */
 gcr_status gcr_score_host(gcr_ctx *ctx, int problem, int scoring, const double *h_models, const uint8_t *h_valid,
                           int k, double threshold, int flags, float *h_scores, uint32_t *h_inliers);
@@ -186,6 +191,10 @@ gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_inde
 gcr_status gcr_refit_f_ba(gcr_ctx *ctx, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
                           const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode, int frame,
                           double *d_models, uint8_t *d_ok);
+/* one non-minimal fit per pair, all pairs in one launch: set p = the first d_sizes[p] entries of d_index_sets[p][n],
+ * fitted to pair p's points (H: homography_estimator.h:136-173; F: 8-point, fundamental_estimator.h:574-618) */
+gcr_status gcr_refit_pairs(gcr_ctx *ctx, int problem, const uint32_t *d_index_sets, const uint32_t *d_sizes,
+                           double *d_models, uint8_t *d_ok);
 int gcr_max_refit_models(int problem);
 
 /* ---- K7 grid neighbourhood -------------------------------------------------------------------------------- */

@@ -54,6 +54,27 @@ def test_cfg4_batched_h_2048_pairs(gcr_ctx, oracle):
         assert idx == want, (p, idx, want)
         assert abs(r64[p] - scores[want]) <= 1e-12 * scores[want]
         assert np.array_equal(best[p].reshape(3, 3), oracle.solve_h4(pts[p], samples[want]))
+    # the tail of configs[3]: inliers of every pair's winner and one least-squares refit per pair, two launches
+    d_best = gcr_ctx.to_device(best)
+    d_idx, d_cnt = gcr_ctx.malloc(n_pairs * n * 4), gcr_ctx.malloc(n_pairs * 4)
+    d_sc, d_refit, d_ok = gcr_ctx.malloc(n_pairs * 8), gcr_ctx.malloc(n_pairs * 72), gcr_ctx.malloc(n_pairs)
+    try:
+        gcr_ctx.final_refit_pairs(_cabi.H, d_best, 3.0, d_idx, d_cnt, d_sc, d_refit, d_ok)
+        cnt = gcr_ctx.to_host(d_cnt, (n_pairs,), np.uint32)
+        sc = gcr_ctx.to_host(d_sc, (n_pairs,), np.float64)
+        refit = gcr_ctx.to_host(d_refit, (n_pairs, 3, 3), np.float64)
+        ok = gcr_ctx.to_host(d_ok, (n_pairs,), np.uint8)
+        idx_all = gcr_ctx.to_host(d_idx, (n_pairs, n), np.uint32)
+    finally:
+        for d in (d_best, d_idx, d_cnt, d_sc, d_refit, d_ok):
+            gcr_ctx.free(d)
+    assert ok.all() and np.array_equal(cnt, rc) and np.allclose(sc, r64, rtol=1e-12)
+    for p in (0, 1, 777, 2047):
+        s_p, c_p, inl = oracle.score(O.H, O.MSAC, pts[p], best[p].reshape(3, 3), 3.0, want_inliers=True)
+        assert c_p == cnt[p] and np.array_equal(inl, idx_all[p, : cnt[p]])
+        want = oracle.refit(O.H, pts[p], inl)
+        g, w = refit[p] / np.linalg.norm(refit[p]), want / np.linalg.norm(want)
+        assert min(np.abs(g - w).max(), np.abs(g + w).max()) < 1e-5
     dec = [gcr_ctx.key_decode(kk) for kk in keys]
     assert all(0 <= i < k for _, i in dec) and min(s for s, _ in dec) > 0.5 * 0.7 * n   # 70 % inliers: every pair found a model
     keys2, best2, _ = gcr_ctx.round(O.H, _cabi.MSAC, _cabi.UNIFORM, 0, k, seed=77, thr=3.0)
