@@ -10,7 +10,7 @@ REF=${GCR_REFERENCE_DIR:-/root/reference}/src/pygcransac/include
 if [ ! -f "$REF/energy.h" ]; then echo "reference tree not present; skipping host/_ref/libgcr_driver.so"; exit 0; fi
 if [ ! -f ../libgcr_b200.so ]; then echo "build libgcr_b200.so first (python graph-cut-ransac_b200/build.py)"; exit 1; fi
 mkdir -p _ref
-g++ -O2 -std=c++17 -w -fPIC -shared -ffp-contract=off -I"$REF" -I../../include -I. \
+g++ -O2 -DNDEBUG -std=c++17 -w -fPIC -shared -ffp-contract=off -I"$REF" -I../../include -I. \
     -o _ref/libgcr_driver.so gcr_driver.cpp \
     -L.. -lgcr_b200 -Wl,-rpath,'$ORIGIN/../..'
 echo "built graph-cut-ransac_b200/host/_ref/libgcr_driver.so"

@@ -505,7 +505,9 @@ namespace
 			for (int i = 0; i < n; ++i)
 			{
 				const double d = r2[i] / squared_truncated_threshold;
-				distance_per_threshold[i] = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : d); // utils::clamp
+				// utils::clamp; a NaN residual (NaN / inf coordinates in the input) counts as a full-cost outlier -- the
+				// reference would feed NaN capacities to the max-flow (its assert(B + C >= 0), energy.h:228, or worse)
+				distance_per_threshold[i] = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : (d == d ? d : 1.0));
 				const double tmp_energy = 1 - distance_per_threshold[i];
 				if (r2[i] <= squared_truncated_threshold)
 					problem_graph->add_term1(i, one_minus_lambda * tmp_energy, 0);
