@@ -106,6 +106,7 @@ extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 #define SEL_BUCKETS GCR_SEL_BUCKETS
 #define SEL_MARGIN 2e-4f
 #define SEL_THREADS 256
+#define SEL_MAX_THREADS 1024 /* few pairs: one big CTA per pair re-scores a candidate over all points in ~1 us */
 
 struct SelectArgs
 {
@@ -123,7 +124,7 @@ struct SelectArgs
 };
 
 template <int PROBLEM, int SCORING>
-__global__ void __launch_bounds__(SEL_THREADS) k_select_exact(const SelectArgs a)
+__global__ void __launch_bounds__(SEL_MAX_THREADS) k_select_exact(const SelectArgs a)
 {
 	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_exact(const SelectArgs a
 	__shared__ int s_cand[SEL_BUCKETS];
 	__shared__ int s_ncand;
 	__shared__ double s_model[ML];
-	__shared__ double warp_sum[SEL_THREADS / 32];
-	__shared__ uint32_t warp_cnt[SEL_THREADS / 32];
+	__shared__ double warp_sum[SEL_MAX_THREADS / 32];
+	__shared__ uint32_t warp_cnt[SEL_MAX_THREADS / 32];
 	__shared__ double s_best_score;
 	__shared__ uint32_t s_best_slot, s_best_count;
 	const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_exact(const SelectArgs a
 		for (int j = 0; j < ML; ++j) M[j] = s_model[j];
 		double sum = 0.0;
 		uint32_t cnt = 0;
-		for (int i = tid; i < a.n; i += SEL_THREADS)
+		for (int i = tid; i < a.n; i += (int)blockDim.x)
 		{
 			double pt[COLS];
 			for (int j = 0; j < COLS; ++j) pt[j] = P[(size_t)i * COLS + j];
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_exact(const SelectArgs a
 		{
 			double value = 0.0;
 			uint32_t inl = 0;
-			for (int w = 0; w < SEL_THREADS / 32; ++w) { value += warp_sum[w]; inl += warp_cnt[w]; }
+			for (int w = 0; w < (int)blockDim.x / 32; ++w) { value += warp_sum[w]; inl += warp_cnt[w]; }
 			const double score = SCORING == GCR_MSAC ? (inl == 0 ? 0.0 : (value + inl * T) / T) : value;
 			if (score > s_best_score || (score == s_best_score && gidx < s_best_slot))
 			{
@@ -323,13 +324,14 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	sa.k = (int)K;
 	sa.index_base = index_base;
 	sa.thr = threshold;
+	const int sel_threads = ctx->n_pairs < 2 * ctx->sm_count ? SEL_MAX_THREADS : SEL_THREADS;
 #define GCR_SEL(PR)                                                                                          \
 	do                                                                                                       \
 	{                                                                                                        \
 		if (scoring == GCR_MSAC)                                                                             \
-			k_select_exact<PR, GCR_MSAC><<<ctx->n_pairs, SEL_THREADS, 0, ctx->stream>>>(sa);                  \
+			k_select_exact<PR, GCR_MSAC><<<ctx->n_pairs, sel_threads, 0, ctx->stream>>>(sa);                  \
 		else                                                                                                 \
-			k_select_exact<PR, GCR_MAGSAC><<<ctx->n_pairs, SEL_THREADS, 0, ctx->stream>>>(sa);                \
+			k_select_exact<PR, GCR_MAGSAC><<<ctx->n_pairs, sel_threads, 0, ctx->stream>>>(sa);                \
 	} while (0)
 	if (problem == GCR_H) GCR_SEL(GCR_H);
 	else if (problem == GCR_PNP) GCR_SEL(GCR_PNP);
