@@ -11,15 +11,16 @@ max-flow on the host).  There is no CPU fallback: without a CUDA device / the bu
 Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
 tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
 so the flags are accepted and ignored.  `sampler` is 0 (uniform) or 1 (PROSAC, the reference's default: the
-correspondences are taken to be ordered by quality), both on the counter-based stream -- the stateful samplers
-(2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are host-side plug-ins of the reference's virtual Sampler interface and are not part of
-this path.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
+correspondences are taken to be ordered by quality), both on the counter-based stream.  The stateful samplers
+(2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are sequential host-side samplers of the reference and cannot be drawn ahead in batches:
+such calls run with PROSAC over the same quality order (for 3 / 4: descending `probabilities`) and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
 `neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
 approximate, run-dependent one).
 """
 import ctypes as C
 import os
 import threading
+import warnings
 
 import numpy as np
 
@@ -89,7 +90,8 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
-          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0):
+          neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0,
+          probabilities=()):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
     min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
@@ -97,9 +99,24 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)
     if pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
+    order = None
     if sampler not in (0, 1):
-        raise NotImplementedError("sampler=%d: the uniform (0) and PROSAC (1) samplers run on the counter-based GPU stream; "
-                                  "P-NAPSAC / NG-RANSAC / AR are host-side plug-ins of the reference" % sampler)
+        # 2 P-NAPSAC, 3 NG-RANSAC, 4 AR-Sampler: stateful host-side samplers of the reference whose next sample depends on
+        # the verdict on the previous one -- not drawable ahead in batches.  They are all "guided by a quality order":
+        # the call runs with PROSAC over that order (the given one for P-NAPSAC; descending inlier probability for
+        # NG-RANSAC / AR, bindings.cpp:262-277) and says so.
+        if sampler not in (2, 3, 4):
+            raise NotImplementedError("sampler=%d is not a sampler of the three entry points (0-4)" % sampler)
+        if sampler in (3, 4):
+            prob = np.asarray(probabilities, dtype=np.float64).ravel()
+            if len(prob) != len(pts):
+                raise ValueError("The number of correspondences and inlier probabilities should be the same")   # bindings.cpp
+            order = np.argsort(-prob, kind="stable")
+            pts = np.ascontiguousarray(pts[order])
+        warnings.warn("sampler=%d (%s) is a sequential host-side sampler of the reference; running PROSAC over the same "
+                      "quality order instead" % (sampler, {2: "P-NAPSAC", 3: "NG-RANSAC", 4: "AR-Sampler"}[sampler]),
+                      RuntimeWarning, stacklevel=3)
+        sampler = 1
     if neighborhood not in (0, 1):
         raise ValueError("neighborhood should be 0 (grid) or 1 (radius)")
     lib = _load_driver()
@@ -136,9 +153,14 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     if n_inl < 0:
         raise _cabi.GcrError("gcr_find_model failed (%d): %s" % (n_inl, ctx.lib.gcr_last_error(ctx.h).decode()))
     last_statistics = _tls.last_statistics = stats.as_dict()
+    mask = mask.astype(bool)
+    if order is not None:                                                   # back to the caller's order
+        unsorted = np.zeros_like(mask)
+        unsorted[order] = mask
+        mask = unsorted
     if n_inl == 0:
-        return None, mask.astype(bool)                                      # bindings.cpp:973-975
-    return model.reshape(3, 3), mask.astype(bool)
+        return None, mask                                                   # bindings.cpp:973-975
+    return model.reshape(3, 3), mask
 
 
 def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -148,7 +170,7 @@ def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=
     """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
     None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
     return _find(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
-                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device)
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device, probabilities=probabilities)
 
 
 def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -163,7 +185,7 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
     arguments) switch those parts off (linear 8-point non-minimal fits, no polish)."""
     return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device,
-                 use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0)
+                 use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, probabilities=probabilities)
 
 
 def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -183,4 +205,5 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
     if K2.shape != (3, 3):
         raise ValueError("K2 shape should be [3x3]")
     return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
-                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2))
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2),
+                 probabilities=probabilities)

@@ -100,3 +100,34 @@ def test_find_essential_matrix_default_arguments(pyg, ref, oracle):
     assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
     assert st["graph_cut_number"] == want["stats"]["graph_cuts"] and st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
+
+
+def test_reference_calls_with_their_own_samplers(pyg):
+    """The reference's tests verbatim, sampler ids included: P-NAPSAC (2) for H, AR-Sampler (4) with rank-based inlier
+    probabilities for F and E (tests/test_*.py: get_probabilities).  Those samplers are sequential host-side code; the
+    calls run with PROSAC over the same quality order, say so in a RuntimeWarning, and keep the reference's floors."""
+    g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
+    pts = np.ascontiguousarray(g["pts"])
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    prob = [1.0 - i / len(pts) for i in range(len(pts))]
+    with pytest.warns(RuntimeWarning, match="P-NAPSAC"):
+        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, threshold=3.0, sampler=2, max_iters=5000, min_iters=50, probabilities=[])
+    assert mask.sum() > 250
+    with pytest.warns(RuntimeWarning, match="AR-Sampler"):
+        F, mask = pyg.findFundamentalMatrix(pts, h1, w1, h2, w2, threshold=0.75, sampler=4, max_iters=5000, min_iters=50,
+                                            probabilities=prob)
+    assert mask.sum() > 380
+    # a shuffled input with the probabilities telling the order: the mask comes back in the caller's order
+    perm = np.random.default_rng(1).permutation(len(pts))
+    with pytest.warns(RuntimeWarning):
+        F2, mask2 = pyg.findFundamentalMatrix(np.ascontiguousarray(pts[perm]), h1, w1, h2, w2, threshold=0.75, sampler=4,
+                                              max_iters=5000, min_iters=50, probabilities=list(np.asarray(prob)[perm]))
+    assert np.array_equal(mask2, mask[perm]) and np.allclose(F2, F)
+    g = np.load(os.path.join(GOLDEN, "fountain_matches.npz"))
+    pts, K1, K2 = np.ascontiguousarray(g["pts"]), g["K1"], g["K2"]
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    prob = [1.0 - i / len(pts) for i in range(len(pts))]
+    with pytest.warns(RuntimeWarning, match="AR-Sampler"):
+        E, mask = pyg.findEssentialMatrix(pts, K1, K2, h1, w1, h2, w2, probabilities=prob, threshold=0.75, conf=0.99, min_iters=50,
+                                          max_iters=5000, sampler=4)
+    assert mask.sum() > 450
