@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(H4_THREADS) k_solve_h4(const double *__restric
 }
 
 // ---------------------------------------------------------------------------------------------------- F7 ----
+#ifndef F7_THREADS
 #define F7_THREADS 64
+#define F7_MIN_BLOCKS 6
+#endif
 #define F7_SMEM (63 * F7_THREADS * sizeof(double))
 
 struct SamplePoints // sample point i, column c, straight from the (L2-resident) FP64 point array
@@ -218,7 +221,7 @@ struct SamplePoints // sample point i, column c, straight from the (L2-resident)
 	__device__ __forceinline__ double operator()(int i, int c) const { return P[(size_t)s[i] * 4 + c]; }
 };
 
-__global__ void __launch_bounds__(F7_THREADS, 6) k_solve_f7(const double *__restrict__ pts, int n,
+__global__ void __launch_bounds__(F7_THREADS, F7_MIN_BLOCKS) k_solve_f7(const double *__restrict__ pts, int n,
                                                          const GcrSampleSource src, int count,
                                                          double *__restrict__ models, uint8_t *__restrict__ valid,
                                                          unsigned long long *__restrict__ counters)
