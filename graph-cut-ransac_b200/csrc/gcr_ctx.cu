@@ -72,6 +72,7 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	cudaFree(ctx->d_magsac_lut64);
 	cudaFree(ctx->d_scratch);
 	cudaFree(ctx->d_prosac_growth);
+	cudaFree(ctx->d_importance_cdf);
 	cudaFree(ctx->d_round);
 	cudaFree(ctx->d_counters);
 	for (int i = 0; i < gcr_ctx::EV_RING; ++i)

@@ -42,6 +42,9 @@ struct gcr_ctx
 	// PROSAC growth function T'_n (prosac_sampler.h:129-160) for the current (n, m)
 	unsigned long long *d_prosac_growth = nullptr;
 	int prosac_n = 0, prosac_m = 0;
+	// cumulative table of the importance sampler's std::discrete_distribution (importance_sampler.h:76-78), n entries
+	double *d_importance_cdf = nullptr;
+	int importance_n = 0;
 
 	// per-round buffers of gcr_round (samples, models, valid flags, scores)
 	void *d_round = nullptr;
@@ -230,8 +233,9 @@ struct GcrSampleSource
 {
 	const uint32_t *samples;            // [n_pairs][count][m], or nullptr = generate
 	unsigned long long seed, first_index;
-	int sampler;                        // GCR_UNIFORM / GCR_PROSAC
+	int sampler;                        // GCR_UNIFORM / GCR_PROSAC / GCR_IMPORTANCE
 	const unsigned long long *growth;   // PROSAC growth function
+	const double *cdf;                  // importance sampler: cumulative probabilities (n entries)
 	uint32_t n;                         // pool size = number of points
 };
 
@@ -278,6 +282,35 @@ __device__ __forceinline__ void gcr_gen_prosac(unsigned long long seed, int pair
 				v[j] = subset - 1;
 	}
 }
+// importance_sampler.h:134-135: m independent draws of std::discrete_distribution<int> (libstdc++: p =
+// generate_canonical<double, 53>(urng) = (w0 + w1 * 2^32) / 2^64 in FP64, clamped below 1; index = lower_bound(cdf, p)).
+// With replacement: a sample may contain a point twice, as in the reference.
+__device__ __forceinline__ void gcr_gen_importance(unsigned long long seed, int pair, unsigned long long index, int m, uint32_t n,
+                                                   const double *__restrict__ cdf, uint32_t *v)
+{
+	GcrDrawStream s(seed + (unsigned long long)pair * GCR_PAIR_SEED_STRIDE, index, 3u);
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+	{
+		if (j < m)
+		{
+			const uint32_t w0 = s.next(), w1 = s.next();
+			double p = ((double)w0 + (double)w1 * 4294967296.0) / 18446744073709551616.0;
+			if (p >= 1.0)
+				p = 0.99999999999999988898; // nextafter(1, 0)
+			uint32_t lo = 0, hi = n; // first i with cdf[i] >= p (cdf[n-1] = 1 > p)
+			while (lo < hi)
+			{
+				const uint32_t mid = lo + (hi - lo) / 2;
+				if (cdf[mid] < p)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			v[j] = lo;
+		}
+	}
+}
 // the M indices of sample i of pair `pair` for a solver kernel
 template <int M>
 __device__ __forceinline__ void gcr_load_sample(const GcrSampleSource &src, int pair, int count, int i, uint32_t *sidx)
@@ -293,6 +326,8 @@ __device__ __forceinline__ void gcr_load_sample(const GcrSampleSource &src, int 
 	uint32_t v[8];
 	if (src.sampler == GCR_PROSAC)
 		gcr_gen_prosac(src.seed, pair, src.first_index + (unsigned long long)i, M, src.n, src.growth, 100000ull, v);
+	else if (src.sampler == GCR_IMPORTANCE)
+		gcr_gen_importance(src.seed, pair, src.first_index + (unsigned long long)i, M, src.n, src.cdf, v);
 	else
 		gcr_gen_uniform(src.seed, pair, src.first_index + (unsigned long long)i, M, src.n, v);
 #pragma unroll

@@ -10,6 +10,7 @@
 #include "gcr_internal.cuh"
 
 #include <math.h>
+#include <cmath>
 #include <vector>
 
 
@@ -41,6 +42,24 @@ __global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ ou
 	const unsigned long long k = first_k + (unsigned long long)i;
 	uint32_t v[8];
 	gcr_gen_prosac(seed, pair, k, m, n, growth, convergence, v);
+	uint32_t *o = out + ((size_t)pair * count + i) * m;
+#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		if (j < m)
+			o[j] = v[j];
+}
+
+// importance_sampler.h:126-137 (NG-RANSAC): m independent draws from the point-probability distribution
+__global__ void __launch_bounds__(256) k_sample_importance(uint32_t *__restrict__ out, int count, int m, uint32_t n,
+                                                            uint64_t first_index, uint64_t seed,
+                                                            const double *__restrict__ cdf)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const int pair = blockIdx.y;
+	uint32_t v[8];
+	gcr_gen_importance(seed, pair, first_index + (uint64_t)i, m, n, cdf, v);
 	uint32_t *o = out + ((size_t)pair * count + i) * m;
 #pragma unroll
 	for (int j = 0; j < 8; ++j)
@@ -142,9 +161,59 @@ extern "C" gcr_status gcr_sample(gcr_ctx *ctx, int sampler, int m, uint64_t firs
 		k_sample_prosac<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed,
 		                                                ctx->d_prosac_growth, 100000ull);
 	}
+	else if (sampler == GCR_IMPORTANCE)
+	{
+		if (!ctx->d_importance_cdf || ctx->importance_n != ctx->n)
+			GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_sample: GCR_IMPORTANCE needs gcr_set_point_probabilities for the %d points", ctx->n);
+		k_sample_importance<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed,
+		                                                    ctx->d_importance_cdf);
+	}
 	else
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: unknown sampler %d", sampler);
 	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+// The table std::discrete_distribution<int>::param_type::_M_initialize builds from the weights (libstdc++
+// bits/random.tcc, the library the reference's ImportanceSampler is compiled against, importance_sampler.h:76-78):
+// sum = accumulate(w), p_i = w_i / sum, cp = partial_sum(p), cp.back() = 1.  Sequential FP64 on the host, in that
+// order, so that the device draws select exactly the indices the reference's distribution object would.
+extern "C" gcr_status gcr_set_point_probabilities(gcr_ctx *ctx, const double *h_probabilities, int n)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!h_probabilities || n < 1)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_point_probabilities: need n >= 1 probabilities");
+	if (n != ctx->n)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_point_probabilities: %d probabilities for %d points (importance_sampler.h:72-73)", n, ctx->n);
+	double sum = 0.0;
+	for (int i = 0; i < n; ++i)
+	{
+		if (!(h_probabilities[i] >= 0.0) || !std::isfinite(h_probabilities[i]))
+			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_point_probabilities: probability %d is negative or not finite", i);
+		sum += h_probabilities[i];
+	}
+	if (!(sum > 0.0))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_point_probabilities: the probabilities sum to zero");
+	std::vector<double> cp((size_t)n);
+	double run = 0.0;
+	for (int i = 0; i < n; ++i)
+	{
+		run = (i == 0) ? h_probabilities[0] / sum : run + h_probabilities[i] / sum;
+		cp[i] = run;
+	}
+	cp[n - 1] = 1.0;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->importance_n != n)
+	{
+		cudaFree(ctx->d_importance_cdf);
+		ctx->d_importance_cdf = nullptr;
+		ctx->importance_n = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_importance_cdf, (size_t)n * sizeof(double)));
+	}
+	GCR_CHECK_CUDA(ctx, cudaMemcpy(ctx->d_importance_cdf, cp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+	ctx->importance_n = n;
 	return GCR_OK;
 }
 

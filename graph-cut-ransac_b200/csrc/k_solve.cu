@@ -499,6 +499,7 @@ extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_
 	src.seed = src.first_index = 0;
 	src.sampler = GCR_UNIFORM;
 	src.growth = nullptr;
+	src.cdf = nullptr;
 	src.n = (uint32_t)ctx->n;
 	return solve_launch(ctx, problem, src, count, d_models, d_valid);
 }
@@ -519,6 +520,7 @@ gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, u
 	src.first_index = first_index;
 	src.sampler = sampler;
 	src.growth = nullptr;
+	src.cdf = nullptr;
 	src.n = (uint32_t)ctx->n;
 	if (sampler == GCR_PROSAC)
 	{
@@ -528,6 +530,12 @@ gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, u
 		if (st)
 			return st;
 		src.growth = ctx->d_prosac_growth;
+	}
+	else if (sampler == GCR_IMPORTANCE)
+	{
+		if (!ctx->d_importance_cdf || ctx->importance_n != ctx->n)
+			GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_round: GCR_IMPORTANCE needs gcr_set_point_probabilities for the %d points", ctx->n);
+		src.cdf = ctx->d_importance_cdf;
 	}
 	else if (sampler != GCR_UNIFORM)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: unknown sampler %d", sampler);

@@ -384,8 +384,9 @@ namespace
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
 			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
-			if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : GCR_UNIFORM, m, S.sampler == 1 ? first + 1 : first, B, S.seed,
-			               d_samples.as<uint32_t>()) != GCR_OK)
+			// sampler 3 = ImportanceSampler (NG-RANSAC, py/gcransac_python.cpp:4343-4346): draw g = sample g of stream 3
+			if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : S.sampler == 3 ? GCR_IMPORTANCE : GCR_UNIFORM, m,
+			               S.sampler == 1 ? first + 1 : first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_sample");
 			if (variant == 1)
 			{
@@ -906,6 +907,20 @@ namespace
 				}
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
 					return -1;
+				if (S.sampler == 3)
+				{
+					// ImportanceSampler's constructor (samplers/importance_sampler.h:67-82): one probability per point
+					if (!S.point_probabilities)
+					{
+						error = "sampler 3 (importance sampler) needs gcr_run_settings.point_probabilities";
+						return -1;
+					}
+					if (gcr_set_point_probabilities(ctx, S.point_probabilities, n) != GCR_OK)
+					{
+						fail("gcr_set_point_probabilities");
+						return -1;
+					}
+				}
 			}
 			setup_timer.reset();
 			const double log_probability = std::log(1.0 - S.confidence);
@@ -1145,6 +1160,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->sampler = 0;
 	s->neighborhood = 0;
 	s->neighborhood_radius = 20.0;
+	s->point_probabilities = nullptr;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

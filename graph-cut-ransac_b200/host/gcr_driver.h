@@ -55,13 +55,16 @@ typedef struct gcr_run_settings
 	 * (py/gcransac_python.cpp:1832-1887; pixel frame) */
 	int f_bundle_adjustment;
 	/* main sampler: 0 = uniform (samplers/uniform_sampler.h), 1 = PROSAC (samplers/prosac_sampler.h: the correspondences
-	 * are ordered by quality); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
+	 * are ordered by quality), 3 = the importance sampler of NG-RANSAC (samplers/importance_sampler.h; needs
+	 * point_probabilities below); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
 	int sampler;
 	/* neighbourhood of the graph-cut: 0 = GridNeighborhoodGraph<4> (cell_sizes / cells_per_axis above), 1 = the radius
 	 * neighbourhood of FlannNeighborhoodGraph (neighborhood/flann_neighborhood_graph.h:99-137; exact instead of FLANN's
 	 * approximate search), points within neighborhood_radius in the 4-D correspondence space */
 	int neighborhood;
 	double neighborhood_radius;
+	/* sampler 3: the inlier probability of each of the n correspondences (host memory, read during the call) */
+	const double *point_probabilities;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats

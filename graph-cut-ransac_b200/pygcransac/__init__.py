@@ -10,10 +10,11 @@ max-flow on the host).  There is no CPU fallback: without a CUDA device / the bu
 
 Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
 tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
-so the flags are accepted and ignored.  `sampler` is 0 (uniform) or 1 (PROSAC, the reference's default: the
-correspondences are taken to be ordered by quality), both on the counter-based stream.  The stateful samplers
-(2 P-NAPSAC, 3 NG-RANSAC, 4 AR) are sequential host-side samplers of the reference and cannot be drawn ahead in batches:
-such calls run with PROSAC over the same quality order (for 3 / 4: descending `probabilities`) and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
+so the flags are accepted and ignored.  `sampler` is 0 (uniform), 1 (PROSAC, the reference's default: the
+correspondences are taken to be ordered by quality) or 3 (the importance sampler of NG-RANSAC: independent draws from
+`probabilities`, samplers/importance_sampler.h), all on the counter-based stream.  The stateful samplers
+(2 P-NAPSAC, 4 AR) are sequential host-side samplers of the reference and cannot be drawn ahead in batches:
+such calls run with PROSAC over the same quality order (for 4: descending `probabilities`) and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
 `neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
 approximate, run-dependent one).
 """
@@ -40,7 +41,8 @@ class RunSettings(C.Structure):
                 ("max_unsuccessful_model_generations", C.c_uint64), ("do_local_optimization", C.c_int),
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
-                ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double)]
+                ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
+                ("point_probabilities", C.c_void_p)]
 
 
 class RunStats(C.Structure):
@@ -100,21 +102,28 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     if pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
     order = None
-    if sampler not in (0, 1):
-        # 2 P-NAPSAC, 3 NG-RANSAC, 4 AR-Sampler: stateful host-side samplers of the reference whose next sample depends on
-        # the verdict on the previous one -- not drawable ahead in batches.  They are all "guided by a quality order":
-        # the call runs with PROSAC over that order (the given one for P-NAPSAC; descending inlier probability for
-        # NG-RANSAC / AR, bindings.cpp:262-277) and says so.
-        if sampler not in (2, 3, 4):
+    prob = None
+    if sampler in (3, 4):
+        prob = np.ascontiguousarray(probabilities, dtype=np.float64).ravel()
+        if len(prob) != len(pts):
+            raise ValueError("The number of correspondences and inlier probabilities should be the same")   # bindings.cpp
+    if sampler == 3:
+        # NG-RANSAC's ImportanceSampler (py/gcransac_python.cpp:4343-4346): stateless, m independent draws from the
+        # probabilities per sample -- drawn on the GPU (GCR_IMPORTANCE)
+        if not (np.all(np.isfinite(prob)) and np.all(prob >= 0) and prob.sum() > 0):
+            raise ValueError("probabilities should be finite, non-negative and not all zero")
+    elif sampler not in (0, 1):
+        # 2 P-NAPSAC, 4 AR-Sampler: stateful host-side samplers of the reference whose next sample depends on the verdict
+        # on the previous one -- not drawable ahead in batches.  Both are "guided by a quality order": the call runs
+        # with PROSAC over that order (the given one for P-NAPSAC; descending inlier probability for AR,
+        # bindings.cpp:262-277) and says so.
+        if sampler not in (2, 4):
             raise NotImplementedError("sampler=%d is not a sampler of the three entry points (0-4)" % sampler)
-        if sampler in (3, 4):
-            prob = np.asarray(probabilities, dtype=np.float64).ravel()
-            if len(prob) != len(pts):
-                raise ValueError("The number of correspondences and inlier probabilities should be the same")   # bindings.cpp
+        if sampler == 4:
             order = np.argsort(-prob, kind="stable")
             pts = np.ascontiguousarray(pts[order])
         warnings.warn("sampler=%d (%s) is a sequential host-side sampler of the reference; running PROSAC over the same "
-                      "quality order instead" % (sampler, {2: "P-NAPSAC", 3: "NG-RANSAC", 4: "AR-Sampler"}[sampler]),
+                      "quality order instead" % (sampler, {2: "P-NAPSAC", 4: "AR-Sampler"}[sampler]),
                       RuntimeWarning, stacklevel=3)
         sampler = 1
     if neighborhood not in (0, 1):
@@ -140,6 +149,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.neighborhood = neighborhood
     s.neighborhood_radius = float(neighborhood_size)
     s.f_bundle_adjustment = f_bundle_adjustment
+    s.point_probabilities = prob.ctypes.data if sampler == 3 else None
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libgcr_b200.so")
 
 H, F, E, PNP = 0, 1, 2, 3
 MSAC, MAGSAC = 0, 1
-UNIFORM, PROSAC = 0, 1
+UNIFORM, PROSAC, IMPORTANCE = 0, 1, 2
 WEIGHT_NONE, WEIGHT_POSITIONAL, WEIGHT_BY_POINT = 0, 1, 2
 SCORE_EXACT_COUNTS = 1
 
@@ -23,7 +23,7 @@ BA_HARTLEY, BA_PIXEL = 1, 2
 EXPORTS = [
     "gcr_ctx_create", "gcr_ctx_destroy", "gcr_ctx_set_stream", "gcr_sync", "gcr_last_error", "gcr_version",
     "gcr_device_info", "gcr_launch_count", "gcr_malloc", "gcr_free", "gcr_memcpy_h2d", "gcr_memcpy_d2h", "gcr_memset",
-    "gcr_points_upload", "gcr_points_set_device", "gcr_points_get_norm", "gcr_sample", "gcr_sample_from_pool",
+    "gcr_points_upload", "gcr_points_set_device", "gcr_points_get_norm", "gcr_sample", "gcr_set_point_probabilities", "gcr_sample_from_pool",
     "gcr_solve_minimal", "gcr_max_models", "gcr_sample_size", "gcr_model_len", "gcr_score", "gcr_score_exact",
     "gcr_score_host", "gcr_score_exact_host", "gcr_argmax", "gcr_key_score", "gcr_key_index", "gcr_refit",
     "gcr_grid_build", "gcr_round", "gcr_set_band_factor", "gcr_set_score_variant", "gcr_profile_enable",
@@ -69,6 +69,7 @@ def load_library():
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_get_norm": (i32, [vp, vp]),
         "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
+        "gcr_set_point_probabilities": (i32, [vp, vp, i32]),
         "gcr_sample_from_pool": (i32, [vp, vp, u32, i32, u64, i32, u64, u32, vp]),
         "gcr_solve_minimal": (i32, [vp, i32, vp, i32, vp, vp]),
         "gcr_solve_plane_parallax": (i32, [vp, vp, i32, vp, vp, vp]),
@@ -236,6 +237,11 @@ class Context:
             return self.to_host(d, (self.n_pairs, count, m), np.uint32)
         finally:
             self.free(d)
+
+    def set_point_probabilities(self, probabilities):
+        """The distribution GCR_IMPORTANCE samples draw from (samplers/importance_sampler.h:67-82)."""
+        p = np.ascontiguousarray(probabilities, dtype=np.float64).ravel()
+        self.check(self.lib.gcr_set_point_probabilities(self.h, _ptr(p), len(p)))
 
     def sample_from_pool(self, pool, m, first_index, count, seed, stream):
         pool = np.ascontiguousarray(pool, dtype=np.uint32)

@@ -32,7 +32,7 @@ typedef int gcr_status;
 enum { GCR_OK = 0, GCR_ERR_CUDA = 1, GCR_ERR_ARG = 2, GCR_ERR_STATE = 3, GCR_ERR_NOMEM = 4 };
 enum { GCR_H = 0, GCR_F = 1, GCR_E = 2, GCR_PNP = 3 };          /* problem */
 enum { GCR_MSAC = 0, GCR_MAGSAC = 1 };                          /* scoring function */
-enum { GCR_UNIFORM = 0, GCR_PROSAC = 1 };                       /* sampler */
+enum { GCR_UNIFORM = 0, GCR_PROSAC = 1, GCR_IMPORTANCE = 2 };   /* sampler */
 enum { GCR_WEIGHT_NONE = 0, GCR_WEIGHT_POSITIONAL = 1, GCR_WEIGHT_BY_POINT = 2 }; /* refit weight indexing */
 /* gcr_score flags */
 enum { GCR_SCORE_EXACT_COUNTS = 1 /* FP64 re-check of points within the FP32 error band of the threshold */ };
@@ -93,6 +93,14 @@ gcr_status gcr_points_get_norm(gcr_ctx *ctx, double *h_out /* 8 * n_pairs */);
  * d_out: [n_pairs][count][m] uint32.  For PROSAC first_index is the 1-based k of the first draw. */
 gcr_status gcr_sample(gcr_ctx *ctx, int sampler, int m, uint64_t first_index, int count, uint64_t seed,
                       uint32_t *d_out);
+/* ImportanceSampler (samplers/importance_sampler.h:67-82, the NG-RANSAC sampler, `sampler=3` of the Python entry
+ * points): the inlier probabilities of the n uploaded points become the cumulative table of the reference's
+ * std::discrete_distribution<int> (normalise by the sum, partial sums, last entry 1).  GCR_IMPORTANCE samples are then
+ * m INDEPENDENT draws from that distribution (importance_sampler.h:134-135: with replacement, a sample may repeat a
+ * point), draw j of sample i = two 32-bit words of stream 3 of (seed, first_index + i, pair) -> the 53-bit uniform of
+ * std::generate_canonical -> lower bound in the table.  All pairs of the context share the table.
+ * Call after gcr_points_upload; n must equal the number of points. */
+gcr_status gcr_set_point_probabilities(gcr_ctx *ctx, const double *h_probabilities, int n);
 /* Uniform draws from explicit pools (GCRANSAC.h:842-846, the LO inner sampler): pool p has pool_sizes[p] entries
  * at d_pool + pool_offsets[p]; out[i] = pool[draw_i].  stream distinguishes independent uses of one seed. */
 gcr_status gcr_sample_from_pool(gcr_ctx *ctx, const uint32_t *d_pool, uint32_t pool_size, int m,

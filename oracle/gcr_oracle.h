@@ -75,6 +75,15 @@ uint32_t gcro_prosac_subset_size(const uint64_t *growth, uint32_t n, int m, uint
 void gcro_sample_prosac(uint64_t seed, uint64_t k, uint32_t n, int m, const uint64_t *growth,
                         uint64_t convergence_iters, uint32_t *out);
 
+/* importance_sampler.h:67-82: the cumulative table of the reference's std::discrete_distribution<int> (libstdc++
+ * bits/random.tcc: normalise by the sum, partial sums, last entry 1); n entries
+ * [pinned: std::discrete_distribution over the same word stream, oracle/_ref ref_sample_importance]            */
+void gcro_importance_cdf(const double *probabilities, uint32_t n, double *cdf);
+/* importance_sampler.h:126-137: m independent draws (with replacement) of that distribution; draw j of sample
+ * `sample_index` takes two words of stream 3: p = generate_canonical<double, 53> = (w0 + w1 * 2^32) / 2^64,
+ * index = lower_bound(cdf, p)                                                                                  */
+void gcro_sample_importance(uint64_t seed, uint64_t sample_index, uint32_t n, int m, const double *cdf, uint32_t *out);
+
 /* ---- homography (a4, a5, a7, a21) ------------------------------------------------------------------------- */
 /* homography_estimator.h:346-381 */
 int gcro_h_valid_sample(const double *pts, const uint32_t *sample);

@@ -347,6 +347,49 @@ void gcro_sample_prosac(uint64_t seed, uint64_t k, uint32_t n, int m, const uint
 	out[m - 1] = subset - 1;
 }
 
+// importance_sampler.h:76-78: std::discrete_distribution<int>(begin(probabilities), end(probabilities)); libstdc++'s
+// param_type::_M_initialize: sum = accumulate, p_i /= sum, cp = partial_sum(p), cp.back() = 1.
+void gcro_importance_cdf(const double *probabilities, uint32_t n, double *cdf)
+{
+	double sum = 0.0;
+	for (uint32_t i = 0; i < n; ++i)
+		sum += probabilities[i];
+	double value = 0.0;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const double p = probabilities[i] / sum;
+		value = i == 0 ? p : value + p;
+		cdf[i] = value;
+	}
+	if (n)
+		cdf[n - 1] = 1.0;
+}
+
+// importance_sampler.h:134-135: subset_[i] = multinomial_distribution(generator), i.e. independent draws.  libstdc++'s
+// operator(): p = generate_canonical<double, 53>(urng) -- for a 32-bit generator two calls, (w0 + w1 * 2^32) / 2^64
+// in FP64, nextafter(1, 0) if that rounds to 1 -- then lower_bound over the cumulative table.
+void gcro_sample_importance(uint64_t seed, uint64_t sample_index, uint32_t n, int m, const double *cdf, uint32_t *out)
+{
+	DrawStream s(seed, sample_index, 3u);
+	for (int j = 0; j < m; ++j)
+	{
+		const uint32_t w0 = s.next(), w1 = s.next();
+		double p = ((double)w0 + (double)w1 * 4294967296.0) / 18446744073709551616.0;
+		if (p >= 1.0)
+			p = std::nextafter(1.0, 0.0);
+		uint32_t lo = 0, hi = n;
+		while (lo < hi)
+		{
+			const uint32_t mid = lo + (hi - lo) / 2;
+			if (cdf[mid] < p)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		out[j] = lo;
+	}
+}
+
 // --------------------------------------------------------------------------------------------- homography ----
 // homography_estimator.h:312-322 ("cross_product" with st_ = 1) and :346-381
 static inline void h_cross(double *r, const double *v1, const double *v2)

@@ -22,9 +22,35 @@ from pygcransac import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
+IMPORTANCE_CASES = ((762, 4), (4096, 7), (2048, 5), (2, 4), (1, 4))
+
+
+def importance_probabilities(n):
+    """Skewed inlier probabilities with a fifth of the points at exactly zero (never drawn)."""
+    r = np.random.default_rng(1000 + n)
+    p = r.random(n) ** 3
+    if n > 10:
+        p[r.integers(0, n, n // 5)] = 0.0
+    return p
+
+
+def importance(ref):
+    # ---- importance sampler (importance_sampler.h verbatim: its own std::discrete_distribution object) ----
+    imp = {}
+    for n, m in IMPORTANCE_CASES:
+        imp["samples_%d_%d" % (n, m)] = ref.sample_importance(importance_probabilities(n), m, 11, 0, 3000)
+    imp["provenance"] = np.array("ImportanceSampler::multinomial_distribution (built by the reference's constructor, "
+                                 "compiled verbatim) drawn with the Philox word stream (seed 11, stream 3)")
+    np.savez_compressed(os.path.join(OUT, "importance.npz"), **imp)
+
+
 def main():
     ref = O.Ref()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "importance":   # only this fixture (the others stay byte-identical)
+        importance(ref)
+        return
+    importance(ref)
     rng = np.random.default_rng(2024)
 
     # ---- scoring (scoring_function.h verbatim) ----

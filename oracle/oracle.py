@@ -76,6 +76,10 @@ class Oracle:
         lib.gcro_prosac_growth.argtypes = [C.c_uint32, C.c_int, C.c_uint64, _u64p]
         lib.gcro_prosac_subset_size.restype = C.c_uint32
         lib.gcro_prosac_subset_size.argtypes = [_u64p, C.c_uint32, C.c_int, C.c_uint64]
+        lib.gcro_importance_cdf.restype = None
+        lib.gcro_importance_cdf.argtypes = [_dp, C.c_uint32, _dp]
+        lib.gcro_sample_importance.restype = None
+        lib.gcro_sample_importance.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _dp, _u32p]
         lib.gcro_sample_prosac.restype = None
         lib.gcro_sample_prosac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _u64p, C.c_uint64, _u32p]
         lib.gcro_h_valid_sample.restype = C.c_int
@@ -186,6 +190,19 @@ class Oracle:
         out = np.empty((count, m), dtype=np.uint32)
         for i in range(count):
             self.lib.gcro_sample_prosac(seed, first_k + i, n, m, growth, conv, out[i])
+        return out
+
+    def importance_cdf(self, probabilities):
+        p = np.ascontiguousarray(probabilities, dtype=np.float64)
+        cdf = np.empty(len(p))
+        self.lib.gcro_importance_cdf(p, len(p), cdf)
+        return cdf
+
+    def sample_importance(self, seed, first, count, m, cdf):
+        out = np.empty((count, m), dtype=np.uint32)
+        cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+        for i in range(count):
+            self.lib.gcro_sample_importance(seed, first + i, len(cdf), m, cdf, out[i])
         return out
 
     # ---- solvers ----
@@ -358,6 +375,10 @@ class Ref:
         lib.ref_run.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                 C.c_int, C.c_int, C.c_uint64, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
                                 _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+        lib.ref_sample_importance.restype = None
+        lib.ref_sample_importance.argtypes = [_dp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u32p]
+        lib.ref_set_point_probabilities.restype = None
+        lib.ref_set_point_probabilities.argtypes = [_dp, C.c_int]
         lib.ref_radius_graph.restype = C.c_uint64
         lib.ref_radius_graph.argtypes = [_dp, C.c_int, C.c_double, _u32p, _u32p, C.c_uint64]
 
@@ -365,11 +386,12 @@ class Ref:
         return _round(self.lib.ref_round, problem, scoring, pts, seed, first, count, thr)
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
-            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0, radius=0.0):
+            min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0, radius=0.0,
+            probabilities=None):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  f_ba (F): bit 0 = the BA non-minimal solver (the reference's default estimator),
         bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  sampler: 0 = uniform, 1 = PROSAC (the points
-        are taken to be ordered by quality).  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
+        are taken to be ordered by quality), 3 = the reference's ImportanceSampler over `probabilities`.  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
         scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
@@ -377,6 +399,10 @@ class Ref:
         mask = np.zeros(len(pts), dtype=np.uint8)
         stats = np.zeros(10, dtype=np.uint64)
         score = C.c_double()
+        if sampler == 3:
+            prob = np.ascontiguousarray(probabilities, dtype=np.float64)
+            assert len(prob) == len(pts)
+            self.lib.ref_set_point_probabilities(prob, len(prob))
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
                                  C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data,
@@ -407,6 +433,14 @@ class Ref:
         last = np.empty(calls, dtype=np.uint32)
         self.lib.ref_prosac(n, m, conv, growth, calls, sizes, last)
         return growth, sizes, last
+
+    def sample_importance(self, probabilities, m, seed, first, count):
+        """Samples [first, first + count) of the reference's own ImportanceSampler distribution object
+        (samplers/importance_sampler.h:76-78, 134-135) on the counter-based word stream."""
+        p = np.ascontiguousarray(probabilities, dtype=np.float64)
+        out = np.empty((count, m), dtype=np.uint32)
+        self.lib.ref_sample_importance(p, len(p), m, seed, first, count, out)
+        return out
 
     def grid(self, pts, cell_sizes, cells_per_axis):
         pts = _as_pts(pts)

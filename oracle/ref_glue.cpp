@@ -11,6 +11,7 @@
 
 #include "GCRANSAC.h"
 #include "neighborhood/grid_neighborhood_graph.h"
+#include "samplers/importance_sampler.h"
 #include "samplers/prosac_sampler.h"
 #include "samplers/uniform_sampler.h"
 
@@ -216,6 +217,47 @@ namespace
 		size_t kth() const { return kth_sample_number; }
 	};
 
+	// The reference's ImportanceSampler (samplers/importance_sampler.h) draws `multinomial_distribution(mt19937 seeded
+	// from random_device)`.  The probe reaches the distribution object the reference's own constructor built (:76-78)
+	// and draws from it with the counter-based word stream instead: the std::discrete_distribution semantics (table
+	// construction, generate_canonical, lower bound) are the library's, only the words differ.
+	struct PhiloxWords
+	{
+		typedef uint32_t result_type;
+		static constexpr result_type min() { return 0u; }
+		static constexpr result_type max() { return 0xFFFFFFFFu; }
+		uint32_t ctr[4], key[2], buf[4];
+		int pos;
+		PhiloxWords(uint64_t seed, uint64_t index, uint32_t stream) : pos(4)
+		{
+			ctr[0] = (uint32_t)index; ctr[1] = (uint32_t)(index >> 32); ctr[2] = 0; ctr[3] = stream;
+			key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+		}
+		result_type operator()()
+		{
+			if (pos == 4)
+			{
+				gcro_philox4x32(ctr, key, buf);
+				++ctr[2];
+				pos = 0;
+			}
+			return buf[pos++];
+		}
+	};
+	class ImportanceProbe : public sampler::ImportanceSampler
+	{
+	public:
+		ImportanceProbe(const cv::Mat *c, const std::vector<double> &p, size_t m) : sampler::ImportanceSampler(c, p, m) {}
+		// importance_sampler.h:134-135 with the generator swapped
+		void draw(uint64_t seed, uint64_t index, size_t m, size_t *subset)
+		{
+			PhiloxWords words(seed, index, 3u);
+			for (size_t j = 0; j < m; ++j)
+				subset[j] = (size_t)multinomial_distribution(words);
+		}
+	};
+	std::vector<double> g_point_probabilities; // ref_set_point_probabilities -> sampler_id 3 of ref_run
+
 	// exposes GCRANSAC<>::getIterationNumber (protected)
 	struct IterProbe : public GCRANSAC<OracleEstimator<GCRO_H>, neighborhood::GridNeighborhoodGraph<4>>
 	{
@@ -243,6 +285,27 @@ void ref_score(int problem, int scoring, const double *pts, int n, const double 
 // gamma_values.cpp:2012 table entry
 double ref_gamma_value(int k) { return stored_gamma_values[k]; }
 int ref_gamma_table_size() { return (int)(sizeof(stored_gamma_values) / sizeof(double)); }
+
+// samples [first, first + count) of the reference's ImportanceSampler on the counter-based word stream; out [count][m]
+void ref_sample_importance(const double *probabilities, int n, int m, uint64_t seed, uint64_t first, int count, uint32_t *out)
+{
+	cv::Mat dummy(n, 4, CV_64F);
+	std::vector<double> p(probabilities, probabilities + n);
+	ImportanceProbe probe(&dummy, p, (size_t)m);
+	std::vector<size_t> subset(m);
+	for (int i = 0; i < count; ++i)
+	{
+		probe.draw(seed, first + (uint64_t)i, (size_t)m, subset.data());
+		for (int j = 0; j < m; ++j)
+			out[(size_t)i * m + j] = (uint32_t)subset[j];
+	}
+}
+
+// the point probabilities sampler_id 3 of ref_run hands to the reference's ImportanceSampler
+void ref_set_point_probabilities(const double *probabilities, int n)
+{
+	g_point_probabilities.assign(probabilities, probabilities + n);
+}
 
 // prosac_sampler.h growth function and the subset size used by each of the first `calls` sample() calls
 void ref_prosac(int n, int m, uint64_t conv, uint64_t *growth, int calls, uint32_t *subset_sizes, uint32_t *last_index)
@@ -448,6 +511,34 @@ namespace
 		}
 	};
 
+	// ImportanceSampler (samplers/importance_sampler.h) on the counter-based stream: call k (from 0) returns sample k
+	// drawn from the reference's own distribution object (ImportanceProbe above).
+	class CounterImportanceSampler : public sampler::Sampler<cv::Mat, size_t>
+	{
+		uint64_t seed, next;
+		std::unique_ptr<ImportanceProbe> probe;
+
+	public:
+		CounterImportanceSampler(const cv::Mat *c, uint64_t seed_, const std::vector<double> &p, size_t m) : sampler::Sampler<cv::Mat, size_t>(c), seed(seed_), next(0)
+		{
+			if (p.size() == (size_t)c->rows)
+				probe.reset(new ImportanceProbe(c, p, m));
+			initialized = (bool)probe;
+		}
+		const std::string getName() const { return "Counter-based importance sampler"; }
+		void reset() {}
+		void update(const size_t *const, const size_t &, const size_t &, const double &) {}
+		bool initialize(const cv::Mat *const) { return true; }
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &, size_t *const subset_, size_t sample_size_)
+		{
+			if (!probe)
+				return false;
+			probe->draw(seed, next++, sample_size_, subset_);
+			return true;
+		}
+	};
+
 	// fundamental_estimator.h:341-572.  The H-degenerate sample test is the restated gcro_degensac_sample_homography;
 	// the inner GC-RANSAC is the reference's own GCRANSAC<> (verbatim) over the plane-and-parallax estimator with the
 	// settings of :547-551.  The reference draws the inner samples from a fresh random_device-seeded UniformSampler
@@ -580,7 +671,12 @@ namespace
 		// (stream 2 then: PROSAC draws use stream 1)
 		CounterSampler uniform_sampler(&points, seed, 0u), lo_sampler(&points, seed, sampler_id == 1 ? 2u : 1u);
 		CounterProsacSampler prosac_sampler(&points, seed);
-		sampler::Sampler<cv::Mat, size_t> *main_sampler_ptr = sampler_id == 1 ? (sampler::Sampler<cv::Mat, size_t> *)&prosac_sampler
+		// sampler_id 3 = the importance sampler of NG-RANSAC (py/gcransac_python.cpp:4343-4346)
+		CounterImportanceSampler importance_sampler(&points, seed, sampler_id == 3 ? g_point_probabilities : std::vector<double>(), Est::sampleSize());
+		if (sampler_id == 3 && !importance_sampler.isInitialized())
+			return -3;
+		sampler::Sampler<cv::Mat, size_t> *main_sampler_ptr = sampler_id == 1   ? (sampler::Sampler<cv::Mat, size_t> *)&prosac_sampler
+		                                                      : sampler_id == 3 ? (sampler::Sampler<cv::Mat, size_t> *)&importance_sampler
 		                                                                        : (sampler::Sampler<cv::Mat, size_t> *)&uniform_sampler;
 		Model model;
 		GCRANSAC<Est, Grid, Scoring> gcransac;
@@ -639,7 +735,7 @@ namespace
 			stats_out[3] = st.neighbor_number;
 			stats_out[4] = st.accepted_models;
 			stats_out[5] = st.rejected_models;
-			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : uniform_sampler.drawn();
+			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : sampler_id == 3 ? importance_sampler.drawn() : uniform_sampler.drawn();
 			stats_out[7] = lo_sampler.drawn();
 			stats_out[8] = estimator.degensac_runs;
 			stats_out[9] = estimator.degensac_updates;

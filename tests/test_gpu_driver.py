@@ -55,6 +55,45 @@ def test_findhomography_cfg1_matches_reference_run(pyg, ref):
             assert mask.sum() > 250                                            # the reference's own floor (tests/test_homography.py:85)
 
 
+def test_importance_sampler_matches_reference_run(pyg, ref):
+    """sampler=3 (NG-RANSAC's ImportanceSampler, py/gcransac_python.cpp:4343-4346): the same run as the verbatim reference
+    driver over the reference's own sampler distribution, on the bundled pair (rank-based probabilities like the
+    reference's tests build them) and on synthetic F with noisy inlier probabilities."""
+    g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
+    pts = g["pts"]
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    n = len(pts)
+    prob = 1.0 - np.arange(n) / n                    # SNN-ratio rank -> probability (tests/test_*.py: get_probabilities)
+    for seed in (1, 2):
+        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, prob, threshold=3.0, conf=0.99, spatial_coherence_weight=0.975,
+                                     max_iters=10000, min_iters=50, use_sprt=False, sampler=3, neighborhood=0,
+                                     neighborhood_size=4.0, use_space_partitioning=False, lo_number=50, seed=seed)
+        st = pyg.last_statistics
+        want = ref.run(O.H, pts.astype(np.float64), g["cell_sizes"], 4, 3.0, conf=0.99, spatial_weight=0.975,
+                       max_iters=10000, min_iters=50, lo_number=50, seed=seed, sampler=3, probabilities=prob)
+        assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert np.array_equal(mask, want["mask"]), (seed, int(mask.sum()), int(want["mask"].sum()))
+        assert _up_to_scale(want["model"], H) < 1e-5
+        assert mask.sum() > 250
+    pts, Fm, Em, K, inl = synth.epipolar_pair(2000, 0.6, seed=8)
+    rng = np.random.default_rng(4)
+    prob = np.clip(np.where(inl, 0.7, 0.3) + rng.normal(0, 0.2, len(pts)), 0.0, 1.0)
+    F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, prob, threshold=0.75, spatial_coherence_weight=0.1,
+                                        neighborhood=0, neighborhood_size=8.0, use_sprt=False, seed=6, sampler=3,
+                                        use_degensac=False, bundle_adjustment=False)
+    st = pyg.last_statistics
+    want = ref.run(O.F, pts, np.array([1024 / 8] * 4), 8, 0.75, conf=0.99, spatial_weight=0.1, max_iters=10000, min_iters=50,
+                   lo_number=50, seed=6, sampler=3, probabilities=prob)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], F) < 1e-5
+    assert (mask & inl).sum() > 0.9 * inl.sum()
+    with pytest.raises(ValueError):
+        pyg.findHomography(pts, 1024, 1024, 1024, 1024, prob[:-1], sampler=3)      # one probability per correspondence
+    with pytest.raises(ValueError):
+        pyg.findHomography(pts, 1024, 1024, 1024, 1024, np.zeros(len(pts)), sampler=3)
+
+
 def test_findhomography_synthetic_and_errors(pyg, ref):
     pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)

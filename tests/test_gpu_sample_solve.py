@@ -42,6 +42,58 @@ def test_prosac_samples_bit_exact(gcr_ctx, oracle):
         assert np.array_equal(got, oracle.sample_prosac(9, 99990, 30, n, m, growth)), (n, m)
 
 
+def test_importance_samples_bit_exact(gcr_ctx, oracle):
+    """GCR_IMPORTANCE (samplers/importance_sampler.h, NG-RANSAC): the device draws select the indices the reference's own
+    std::discrete_distribution object selects from the same word stream (fixture from oracle/_ref) and the oracle's."""
+    import os
+    from conftest import GOLDEN
+    sys_path_gen = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "gen_golden.py")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden", sys_path_gen)
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(GOLDEN, "importance.npz"))
+    for n, m in gen.IMPORTANCE_CASES:
+        if n < m:
+            continue                                   # gcr_sample refuses m > n like the uniform sampler
+        p = gen.importance_probabilities(n)
+        pts = np.stack([synth.homography_pair(n, 0.3, seed=s)[0] for s in (1, 2)])
+        gcr_ctx.points_upload(pts, n_pairs=2)
+        with pytest.raises(_cabi.GcrError):
+            gcr_ctx.sample(_cabi.IMPORTANCE, m, 0, 10, seed=11)         # no probabilities for these points yet
+        gcr_ctx.set_point_probabilities(p)
+        got = gcr_ctx.sample(_cabi.IMPORTANCE, m, 0, 3000, seed=11)
+        assert np.array_equal(got[0], g["samples_%d_%d" % (n, m)]), (n, m)
+        cdf = oracle.importance_cdf(p)
+        assert np.array_equal(got[1], oracle.sample_importance((11 + PAIR_STRIDE) & MASK, 0, 3000, m, cdf)), (n, m)
+        got = gcr_ctx.sample(_cabi.IMPORTANCE, m, 123456789012, 100, seed=5)[0]     # 64-bit sample counters
+        assert np.array_equal(got, oracle.sample_importance(5, 123456789012, 100, m, cdf))
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.set_point_probabilities(np.ones(5))                     # importance_sampler.h:72-73: one per point
+    with pytest.raises(_cabi.GcrError):
+        gcr_ctx.set_point_probabilities(np.zeros(gcr_ctx.n))
+
+
+def test_round_with_importance_sampler(gcr_ctx, oracle):
+    """gcr_round draws the importance samples inside the solver kernel: the winner is the sample gcr_sample returns for
+    that index, solved and scored like any other."""
+    pts, Hm, inl = synth.homography_pair(1500, 0.4, seed=21)
+    prob = np.where(inl, 0.9, 0.1) * np.random.default_rng(0).uniform(0.5, 1.0, len(pts))
+    gcr_ctx.points_upload(pts)
+    gcr_ctx.set_point_probabilities(prob)
+    keys, best, evals = gcr_ctx.round(_cabi.H, _cabi.MSAC, _cabi.IMPORTANCE, 0, 2048, seed=3, thr=3.0)
+    score, idx = gcr_ctx.key_decode(keys[0])
+    sample = oracle.sample_importance(3, idx, 1, 4, oracle.importance_cdf(prob))[0]
+    want = oracle.solve_h4(pts, sample)
+    assert want is not None and np.array_equal(best[0].reshape(3, 3), want)
+    want_score, _ = oracle.score(O.H, O.MSAC, pts, want, 3.0)
+    assert abs(score - want_score) <= 1e-5 * want_score
+    # guided sampling pays: far more all-inlier samples than uniform draws give
+    s = gcr_ctx.sample(_cabi.IMPORTANCE, 4, 0, 2048, seed=3)[0]
+    u = gcr_ctx.sample(_cabi.UNIFORM, 4, 0, 2048, seed=3)[0]
+    assert inl[s].all(axis=1).mean() > 3 * inl[u].all(axis=1).mean()
+
+
 def test_pool_sampler(gcr_ctx, oracle):
     pool = np.arange(10, 500, 3, dtype=np.uint32)
     got = gcr_ctx.sample_from_pool(pool, 28, 0, 50, seed=4, stream=2)

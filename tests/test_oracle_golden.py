@@ -61,6 +61,30 @@ def test_prosac_first_draw_quirk(oracle):
     assert any((r[:-1] == m - 1).any() for r in firsts)
 
 
+def test_importance_sampler_matches_reference_fixture(oracle):
+    """samplers/importance_sampler.h: the restated table + draw against the reference's own std::discrete_distribution
+    object (fixture from oracle/_ref), bit-exact; draws are with replacement and never hit a zero-probability point."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "gen_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = _load("importance.npz")
+    for n, m in gen.IMPORTANCE_CASES:
+        p = gen.importance_probabilities(n)
+        cdf = oracle.importance_cdf(p)
+        assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0)
+        got = oracle.sample_importance(11, 0, 3000, m, cdf)
+        assert np.array_equal(got, g["samples_%d_%d" % (n, m)]), (n, m)
+        assert np.all(p[got] > 0)
+        # counter based: any sub-range reproduces
+        assert np.array_equal(oracle.sample_importance(11, 1000, 10, m, cdf), got[1000:1010])
+    p = gen.importance_probabilities(762)
+    s = oracle.sample_importance(3, 0, 50000, 4, oracle.importance_cdf(p))
+    assert any(len(set(r)) < 4 for r in s)                       # with replacement (importance_sampler.h:134-135)
+    freq = np.bincount(s.ravel(), minlength=762) / s.size
+    assert np.abs(freq - p / p.sum()).max() < 2e-3
+
+
 def test_grid(oracle):
     g = _load("grid.npz")
     for Cn in (3, 4, 8):
