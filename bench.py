@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs]
 
 Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
 50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
@@ -34,6 +34,9 @@ WORKLOADS = {
     # name: problem, n points, outlier ratio, threshold, samples per step, pairs per GPU
     "f4k": dict(problem="f", n=4096, outliers=0.5, thr=0.75, samples=262144, pairs=1,
                 desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
+    # the north star's other scoring target ("0.5 of FP32 peak on 4k-point homography and fundamental scoring")
+    "h4k": dict(problem="h", n=4096, outliers=0.5, thr=3.0, samples=262144, pairs=1,
+                desc="H 4-pt + MSAC, N=4096, 50% outliers, thr 3.0 px, single pair (the homography twin of configs[1])"),
     "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
                       desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 + argmax + final "
                            "least-squares refit per pair (configs[3])"),

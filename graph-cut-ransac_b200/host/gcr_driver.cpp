@@ -1,6 +1,7 @@
 // gcr_driver.cpp -- see gcr_driver.h.  Host C++; the only compile-time dependency on the reference tree is its
 // vendored Boykov-Kolmogorov max-flow (energy.h / graph.h + graph.cpp / maxflow.cpp), which stays the reference's code.
 #include "gcr_driver.h"
+#include "gcr_host_samplers.h"
 
 #include <algorithm>
 #include <chrono>
@@ -128,6 +129,8 @@ namespace
 		std::vector<uint32_t> cand_idx; // [candidate][n]
 		DeviceBuffer d_cand_models, d_cand_scores, d_cand_counts, d_cand_idx;
 
+		// sampler 4: the AR-Sampler's sequence, drawn ahead on the host (gcr_host_samplers.h)
+		gcr_host::AdaptiveReordering ar_sampler;
 		// main-loop batch
 		int B = 0;
 		uint64_t batch_first = 0;
@@ -384,8 +387,17 @@ namespace
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
 			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
+			if (S.sampler == 4)
+			{
+				// AdaptiveReorderingSampler (py/gcransac_python.cpp:4348-4359): the heap recurrence runs on the host, the
+				// batch's index sets go up in one copy
+				h_samples.resize((size_t)B * m);
+				ar_sampler.samples(first, (size_t)B, h_samples.data());
+				if (gcr_memcpy_h2d(ctx, d_samples.p, h_samples.data(), (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
+					return fail("gcr_memcpy_h2d");
+			}
 			// sampler 3 = ImportanceSampler (NG-RANSAC, py/gcransac_python.cpp:4343-4346): draw g = sample g of stream 3
-			if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : S.sampler == 3 ? GCR_IMPORTANCE : GCR_UNIFORM, m,
+			else if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : S.sampler == 3 ? GCR_IMPORTANCE : GCR_UNIFORM, m,
 			               S.sampler == 1 ? first + 1 : first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_sample");
 			if (variant == 1)
@@ -402,7 +414,7 @@ namespace
 			h_scores.resize(K);
 			h_counts.resize(K);
 			h_models.resize(K * 9);
-			if (S.use_degensac && problem == GCR_F && variant == 0)
+			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4)
 			{
 				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
 				h_samples.resize((size_t)B * m);
@@ -907,6 +919,15 @@ namespace
 				}
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
 					return -1;
+				if (S.sampler == 4)
+				{
+					if (!S.point_probabilities ||
+					    !ar_sampler.initialize(S.point_probabilities, (size_t)n, m, S.sampler_variance, S.seed))
+					{
+						error = "sampler 4 (AR-Sampler) needs gcr_run_settings.point_probabilities";
+						return -1;
+					}
+				}
 				if (S.sampler == 3)
 				{
 					// ImportanceSampler's constructor (samplers/importance_sampler.h:67-82): one probability per point
@@ -965,6 +986,12 @@ namespace
 				}
 				st.main_samples = cursor;
 				it += unsuccessful;
+				if (success_at < 0 && S.sampler == 4)
+				{
+					// GCRANSAC.h:297-339 gave up: the end-of-iteration update (:474) runs on the last sample once more
+					ar_sampler.repeat_update(cursor - 1);
+					batch_count = 0;
+				}
 				if (success_at >= 0)
 				{
 					for (int q = 0; q < mm; ++q)
@@ -1161,6 +1188,22 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->neighborhood = 0;
 	s->neighborhood_radius = 20.0;
 	s->point_probabilities = nullptr;
+	s->sampler_variance = 0.1;
+}
+
+// samples [first, first + count) of the host-side AR-Sampler sequence (gcr_host_samplers.h) -- what the driver uploads
+// for sampler 4; repeat_at >= 0: that sample's update ran twice.  No GPU involved: the CPU tests check it against the
+// reference's own class.
+extern "C" int gcr_host_sample_adaptive_reordering(const double *probabilities, int n, int m, double variance, uint64_t seed,
+                                                   uint64_t first, int count, long long repeat_at, uint32_t *out)
+{
+	gcr_host::AdaptiveReordering s;
+	if (!out || count < 0 || !s.initialize(probabilities, (size_t)n, m, variance, seed))
+		return -1;
+	if (repeat_at >= 0)
+		s.repeat_update((uint64_t)repeat_at);
+	s.samples(first, (size_t)count, out);
+	return 0;
 }
 
 extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,

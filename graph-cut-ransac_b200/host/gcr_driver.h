@@ -56,7 +56,8 @@ typedef struct gcr_run_settings
 	int f_bundle_adjustment;
 	/* main sampler: 0 = uniform (samplers/uniform_sampler.h), 1 = PROSAC (samplers/prosac_sampler.h: the correspondences
 	 * are ordered by quality), 3 = the importance sampler of NG-RANSAC (samplers/importance_sampler.h; needs
-	 * point_probabilities below); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
+	 * point_probabilities below), 4 = the AR-Sampler (samplers/adaptive_reordering_sampler.h; point_probabilities and
+	 * sampler_variance below; its heap recurrence runs on the host, gcr_host_samplers.h); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
 	int sampler;
 	/* neighbourhood of the graph-cut: 0 = GridNeighborhoodGraph<4> (cell_sizes / cells_per_axis above), 1 = the radius
 	 * neighbourhood of FlannNeighborhoodGraph (neighborhood/flann_neighborhood_graph.h:99-137; exact instead of FLANN's
@@ -65,6 +66,8 @@ typedef struct gcr_run_settings
 	double neighborhood_radius;
 	/* sampler 3: the inlier probability of each of the n correspondences (host memory, read during the call) */
 	const double *point_probabilities;
+	/* sampler 4: estimator_variance_ of AdaptiveReorderingSampler (`sampler_variance` of the Python calls, default 0.1) */
+	double sampler_variance;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats
@@ -94,6 +97,10 @@ int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, con
  * settings->threshold / mean focal length.  K1, K2: row-major 3 x 3 intrinsics.  model_out: E, 9 doubles. */
 int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, const double *K1, const double *K2,
                        const gcr_run_settings *settings, double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
+
+/* samples [first, first + count) of the AR-Sampler sequence the driver uploads for sampler 4 (host only) */
+int gcr_host_sample_adaptive_reordering(const double *probabilities, int n, int m, double variance, uint64_t seed,
+                                        uint64_t first, int count, long long repeat_at, uint32_t *out);
 
 #ifdef __cplusplus
 }

@@ -11,10 +11,11 @@ max-flow on the host).  There is no CPU fallback: without a CUDA device / the bu
 Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
 tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
 so the flags are accepted and ignored.  `sampler` is 0 (uniform), 1 (PROSAC, the reference's default: the
-correspondences are taken to be ordered by quality) or 3 (the importance sampler of NG-RANSAC: independent draws from
-`probabilities`, samplers/importance_sampler.h), all on the counter-based stream.  The stateful samplers
-(2 P-NAPSAC, 4 AR) are sequential host-side samplers of the reference and cannot be drawn ahead in batches:
-such calls run with PROSAC over the same quality order (for 4: descending `probabilities`) and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
+correspondences are taken to be ordered by quality), 3 (the importance sampler of NG-RANSAC: independent draws from
+`probabilities`, samplers/importance_sampler.h) or 4 (the AR-Sampler, samplers/adaptive_reordering_sampler.h: a heap
+recurrence over `probabilities` / `sampler_variance` that does not depend on any verdict, drawn ahead on the host and
+uploaded per batch), all on the counter-based stream.  P-NAPSAC (2) is not built: such calls run with PROSAC over the
+same quality order and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
 `neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
 approximate, run-dependent one).
 """
@@ -42,7 +43,7 @@ class RunSettings(C.Structure):
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
                 ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
-                ("point_probabilities", C.c_void_p)]
+                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double)]
 
 
 class RunStats(C.Structure):
@@ -93,7 +94,7 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
           neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0,
-          probabilities=()):
+          probabilities=(), sampler_variance=0.1):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
     min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
@@ -101,29 +102,21 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)
     if pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
-    order = None
     prob = None
     if sampler in (3, 4):
         prob = np.ascontiguousarray(probabilities, dtype=np.float64).ravel()
         if len(prob) != len(pts):
             raise ValueError("The number of correspondences and inlier probabilities should be the same")   # bindings.cpp
-    if sampler == 3:
-        # NG-RANSAC's ImportanceSampler (py/gcransac_python.cpp:4343-4346): stateless, m independent draws from the
-        # probabilities per sample -- drawn on the GPU (GCR_IMPORTANCE)
+        # 3: NG-RANSAC's ImportanceSampler (py/gcransac_python.cpp:4343-4346): stateless, m independent draws from the
+        # probabilities per sample -- drawn on the GPU (GCR_IMPORTANCE).  4: the AR-Sampler (:4348-4359): probabilities
+        # divided by their maximum, heap recurrence on the host (host/gcr_host_samplers.h)
         if not (np.all(np.isfinite(prob)) and np.all(prob >= 0) and prob.sum() > 0):
             raise ValueError("probabilities should be finite, non-negative and not all zero")
     elif sampler not in (0, 1):
-        # 2 P-NAPSAC, 4 AR-Sampler: stateful host-side samplers of the reference whose next sample depends on the verdict
-        # on the previous one -- not drawable ahead in batches.  Both are "guided by a quality order": the call runs
-        # with PROSAC over that order (the given one for P-NAPSAC; descending inlier probability for AR,
-        # bindings.cpp:262-277) and says so.
-        if sampler not in (2, 4):
+        # 2 P-NAPSAC: not built; guided by the given quality order, so the call runs with PROSAC over that order and says so
+        if sampler != 2:
             raise NotImplementedError("sampler=%d is not a sampler of the three entry points (0-4)" % sampler)
-        if sampler == 4:
-            order = np.argsort(-prob, kind="stable")
-            pts = np.ascontiguousarray(pts[order])
-        warnings.warn("sampler=%d (%s) is a sequential host-side sampler of the reference; running PROSAC over the same "
-                      "quality order instead" % (sampler, {2: "P-NAPSAC", 4: "AR-Sampler"}[sampler]),
+        warnings.warn("sampler=2 (P-NAPSAC) is not built; running PROSAC over the same quality order instead",
                       RuntimeWarning, stacklevel=3)
         sampler = 1
     if neighborhood not in (0, 1):
@@ -149,7 +142,8 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.neighborhood = neighborhood
     s.neighborhood_radius = float(neighborhood_size)
     s.f_bundle_adjustment = f_bundle_adjustment
-    s.point_probabilities = prob.ctypes.data if sampler == 3 else None
+    s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
+    s.sampler_variance = float(sampler_variance)
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()
@@ -164,10 +158,6 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         raise _cabi.GcrError("gcr_find_model failed (%d): %s" % (n_inl, ctx.lib.gcr_last_error(ctx.h).decode()))
     last_statistics = _tls.last_statistics = stats.as_dict()
     mask = mask.astype(bool)
-    if order is not None:                                                   # back to the caller's order
-        unsorted = np.zeros_like(mask)
-        unsorted[order] = mask
-        mask = unsorted
     if n_inl == 0:
         return None, mask                                                   # bindings.cpp:973-975
     return model.reshape(3, 3), mask
@@ -180,7 +170,8 @@ def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=
     """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
     None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
     return _find(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
-                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device, probabilities=probabilities)
+                 min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device, probabilities=probabilities,
+                 sampler_variance=sampler_variance)
 
 
 def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -195,7 +186,8 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
     arguments) switch those parts off (linear 8-point non-minimal fits, no polish)."""
     return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device,
-                 use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, probabilities=probabilities)
+                 use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, probabilities=probabilities,
+                 sampler_variance=sampler_variance)
 
 
 def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -216,4 +208,4 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
         raise ValueError("K2 shape should be [3x3]")
     return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2),
-                 probabilities=probabilities)
+                 probabilities=probabilities, sampler_variance=sampler_variance)

@@ -377,6 +377,10 @@ class Ref:
                                 _u64p, C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
         lib.ref_sample_importance.restype = None
         lib.ref_sample_importance.argtypes = [_dp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u32p]
+        lib.ref_sample_adaptive_reordering.restype = None
+        lib.ref_sample_adaptive_reordering.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_longlong, _u32p]
+        lib.ref_set_sampler_variance.restype = None
+        lib.ref_set_sampler_variance.argtypes = [C.c_double]
         lib.ref_set_point_probabilities.restype = None
         lib.ref_set_point_probabilities.argtypes = [_dp, C.c_int]
         lib.ref_radius_graph.restype = C.c_uint64
@@ -387,11 +391,12 @@ class Ref:
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
             min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0, radius=0.0,
-            probabilities=None):
+            probabilities=None, sampler_variance=0.1):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  f_ba (F): bit 0 = the BA non-minimal solver (the reference's default estimator),
         bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  sampler: 0 = uniform, 1 = PROSAC (the points
-        are taken to be ordered by quality), 3 = the reference's ImportanceSampler over `probabilities`.  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
+        are taken to be ordered by quality), 3 = the reference's ImportanceSampler over `probabilities`, 4 = its
+        AdaptiveReorderingSampler (probabilities / their maximum, `sampler_variance`).  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
         scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
@@ -399,10 +404,11 @@ class Ref:
         mask = np.zeros(len(pts), dtype=np.uint8)
         stats = np.zeros(10, dtype=np.uint64)
         score = C.c_double()
-        if sampler == 3:
+        if sampler in (3, 4):
             prob = np.ascontiguousarray(probabilities, dtype=np.float64)
             assert len(prob) == len(pts)
             self.lib.ref_set_point_probabilities(prob, len(prob))
+            self.lib.ref_set_sampler_variance(sampler_variance)
         n_inl = self.lib.ref_run(problem, scoring_kind, pts, len(pts), _as_pts(cell_sizes), cells_per_axis, threshold,
                                  conf, spatial_weight, max_iters, min_iters, lo_number, seed, model, mask, stats,
                                  C.byref(score), None if grid_pts is None else _as_pts(grid_pts).ctypes.data,
@@ -440,6 +446,15 @@ class Ref:
         p = np.ascontiguousarray(probabilities, dtype=np.float64)
         out = np.empty((count, m), dtype=np.uint32)
         self.lib.ref_sample_importance(p, len(p), m, seed, first, count, out)
+        return out
+
+    def sample_adaptive_reordering(self, probabilities, m, variance, seed, count, repeat_at=-1):
+        """The first `count` samples of the reference's own AdaptiveReorderingSampler (samplers/
+        adaptive_reordering_sampler.h, verbatim; rand() redirected to the counter-based stream) driven sample / update /
+        sample / ... as GCRANSAC::run drives it."""
+        p = np.ascontiguousarray(probabilities, dtype=np.float64)
+        out = np.empty((count, m), dtype=np.uint32)
+        self.lib.ref_sample_adaptive_reordering(p, len(p), m, variance, seed, count, repeat_at, out)
         return out
 
     def grid(self, pts, cell_sizes, cells_per_axis):

@@ -17,6 +17,40 @@
 
 #include "gcr_oracle.h"
 
+// The reference's AR-Sampler (samplers/adaptive_reordering_sampler.h) takes its noise from C rand() -- process-global
+// state.  The header is compiled UNMODIFIED, with the one call redirected to the counter-based word stream the product
+// uses for the same update (stream 4 of (seed, sample index)); everything else -- the heap, the Beta update, the
+// clamping -- is the reference's own code.  <cmath> / <cstdlib> / <math.h> first, as in the reference's own build, so
+// that its unqualified abs() is the floating-point overload.
+#include <cmath>
+#include <cstdlib>
+#include <math.h>
+#include <tuple>
+namespace gcr_ref_noise
+{
+	static uint32_t ctr[4], key[2], buf[4];
+	static int pos = 4;
+	inline void begin(uint64_t seed, uint64_t index, uint32_t stream)
+	{
+		ctr[0] = (uint32_t)index; ctr[1] = (uint32_t)(index >> 32); ctr[2] = 0; ctr[3] = stream;
+		key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+		pos = 4;
+	}
+	inline int next_rand() // in [0, RAND_MAX] like rand()
+	{
+		if (pos == 4)
+		{
+			gcro_philox4x32(ctr, key, buf);
+			++ctr[2];
+			pos = 0;
+		}
+		return (int)(buf[pos++] >> 1);
+	}
+}
+#define rand() gcr_ref_noise::next_rand()
+#include "samplers/adaptive_reordering_sampler.h"
+#undef rand
+
 #include <cstdint>
 #include <cstring>
 
@@ -256,7 +290,37 @@ namespace
 				subset[j] = (size_t)multinomial_distribution(words);
 		}
 	};
-	std::vector<double> g_point_probabilities; // ref_set_point_probabilities -> sampler_id 3 of ref_run
+	std::vector<double> g_point_probabilities; // ref_set_point_probabilities -> sampler_id 3 / 4 of ref_run
+	double g_sampler_variance = 0.1;           // ref_set_sampler_variance -> sampler_id 4
+
+	// The reference's AdaptiveReorderingSampler verbatim behind the Sampler interface; sample() / update() number k take
+	// their noise from stream 4 of (seed, k).  run() calls update() once after every sample() (GCRANSAC.h:304-474).
+	class CounterARSampler : public sampler::AdaptiveReorderingSampler
+	{
+		uint64_t seed, next;
+
+	public:
+		CounterARSampler(const cv::Mat *c, const std::vector<double> &p, size_t m, double variance, uint64_t seed_)
+		    : sampler::AdaptiveReorderingSampler(c, p, m, variance), seed(seed_), next(0)
+		{
+		}
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &pool_, size_t *const subset_, size_t sample_size_)
+		{
+			gcr_ref_noise::begin(seed, next++, 4u); // the update(s) that follow this sample
+			return sampler::AdaptiveReorderingSampler::sample(pool_, subset_, sample_size_);
+		}
+	};
+	// py/gcransac_python.cpp:4350-4354
+	std::vector<double> normalized_by_max(std::vector<double> p)
+	{
+		double max_prob = 0;
+		for (const auto &prob : p)
+			max_prob = MAX(max_prob, prob);
+		for (auto &prob : p)
+			prob /= max_prob;
+		return p;
+	}
 
 	// exposes GCRANSAC<>::getIterationNumber (protected)
 	struct IterProbe : public GCRANSAC<OracleEstimator<GCRO_H>, neighborhood::GridNeighborhoodGraph<4>>
@@ -300,6 +364,26 @@ void ref_sample_importance(const double *probabilities, int n, int m, uint64_t s
 			out[(size_t)i * m + j] = (uint32_t)subset[j];
 	}
 }
+
+// samples [0, count) of the reference's AdaptiveReorderingSampler driven as GCRANSAC::run drives it (sample, update,
+// sample, ...); repeat_at >= 0: that sample is followed by a second update (GCRANSAC.h:297-339 falling through to :474)
+void ref_sample_adaptive_reordering(const double *probabilities, int n, int m, double variance, uint64_t seed, int count,
+                                    long long repeat_at, uint32_t *out)
+{
+	cv::Mat dummy(n, 4, CV_64F);
+	CounterARSampler s(&dummy, normalized_by_max(std::vector<double>(probabilities, probabilities + n)), (size_t)m, variance, seed);
+	std::vector<size_t> pool, subset(m);
+	for (int i = 0; i < count; ++i)
+	{
+		s.sample(pool, subset.data(), (size_t)m);
+		s.update(subset.data(), (size_t)m, (size_t)i, 0.0);
+		if (i == repeat_at)
+			s.update(subset.data(), (size_t)m, (size_t)i, 0.0);
+		for (int j = 0; j < m; ++j)
+			out[(size_t)i * m + j] = (uint32_t)subset[j];
+	}
+}
+void ref_set_sampler_variance(double v) { g_sampler_variance = v; }
 
 // the point probabilities sampler_id 3 of ref_run hands to the reference's ImportanceSampler
 void ref_set_point_probabilities(const double *probabilities, int n)
@@ -675,7 +759,16 @@ namespace
 		CounterImportanceSampler importance_sampler(&points, seed, sampler_id == 3 ? g_point_probabilities : std::vector<double>(), Est::sampleSize());
 		if (sampler_id == 3 && !importance_sampler.isInitialized())
 			return -3;
+		// sampler_id 4 = the AR-Sampler over the max-normalised probabilities (py/gcransac_python.cpp:4348-4359)
+		std::unique_ptr<CounterARSampler> ar_sampler;
+		if (sampler_id == 4)
+		{
+			if (g_point_probabilities.size() != (size_t)points.rows)
+				return -3;
+			ar_sampler.reset(new CounterARSampler(&points, normalized_by_max(g_point_probabilities), Est::sampleSize(), g_sampler_variance, seed));
+		}
 		sampler::Sampler<cv::Mat, size_t> *main_sampler_ptr = sampler_id == 1   ? (sampler::Sampler<cv::Mat, size_t> *)&prosac_sampler
+		                                                      : sampler_id == 4 ? (sampler::Sampler<cv::Mat, size_t> *)ar_sampler.get()
 		                                                      : sampler_id == 3 ? (sampler::Sampler<cv::Mat, size_t> *)&importance_sampler
 		                                                                        : (sampler::Sampler<cv::Mat, size_t> *)&uniform_sampler;
 		Model model;
@@ -735,7 +828,7 @@ namespace
 			stats_out[3] = st.neighbor_number;
 			stats_out[4] = st.accepted_models;
 			stats_out[5] = st.rejected_models;
-			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : sampler_id == 3 ? importance_sampler.drawn() : uniform_sampler.drawn();
+			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : sampler_id == 3 ? importance_sampler.drawn() : sampler_id == 4 ? ar_sampler->drawn() : uniform_sampler.drawn();
 			stats_out[7] = lo_sampler.drawn();
 			stats_out[8] = estimator.degensac_runs;
 			stats_out[9] = estimator.degensac_updates;

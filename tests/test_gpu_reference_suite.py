@@ -102,10 +102,11 @@ def test_find_essential_matrix_default_arguments(pyg, ref, oracle):
     assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
 
 
-def test_reference_calls_with_their_own_samplers(pyg):
+def test_reference_calls_with_their_own_samplers(pyg, ref, oracle):
     """The reference's tests verbatim, sampler ids included: P-NAPSAC (2) for H, AR-Sampler (4) with rank-based inlier
-    probabilities for F and E (tests/test_*.py: get_probabilities).  Those samplers are sequential host-side code; the
-    calls run with PROSAC over the same quality order, say so in a RuntimeWarning, and keep the reference's floors."""
+    probabilities for F and E (tests/test_*.py: get_probabilities).  The AR calls run the reference's own sampler
+    sequence (host/gcr_host_samplers.h) and are compared with the verbatim reference driver over the reference's own
+    AdaptiveReorderingSampler class; P-NAPSAC is not built: PROSAC over the same order, with a RuntimeWarning."""
     g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
     pts = np.ascontiguousarray(g["pts"])
     h1, w1, h2, w2 = (int(v) for v in g["size"])
@@ -113,21 +114,40 @@ def test_reference_calls_with_their_own_samplers(pyg):
     with pytest.warns(RuntimeWarning, match="P-NAPSAC"):
         H, mask = pyg.findHomography(pts, h1, w1, h2, w2, threshold=3.0, sampler=2, max_iters=5000, min_iters=50, probabilities=[])
     assert mask.sum() > 250
-    with pytest.warns(RuntimeWarning, match="AR-Sampler"):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                                       # sampler 4 is native: no substitution warning
         F, mask = pyg.findFundamentalMatrix(pts, h1, w1, h2, w2, threshold=0.75, sampler=4, max_iters=5000, min_iters=50,
                                             probabilities=prob)
-    assert mask.sum() > 380
-    # a shuffled input with the probabilities telling the order: the mask comes back in the caller's order
-    perm = np.random.default_rng(1).permutation(len(pts))
-    with pytest.warns(RuntimeWarning):
-        F2, mask2 = pyg.findFundamentalMatrix(np.ascontiguousarray(pts[perm]), h1, w1, h2, w2, threshold=0.75, sampler=4,
-                                              max_iters=5000, min_iters=50, probabilities=list(np.asarray(prob)[perm]))
-    assert np.array_equal(mask2, mask[perm]) and np.allclose(F2, F)
+    st = pyg.last_statistics
+    assert mask.sum() > 380                                                  # tests/test_fundamental_matrix.py:90
+    cells = 20
+    cs = np.array([w1 / cells, h1 / cells, w2 / cells, h2 / cells])
+    want = ref.run(O.F, pts.astype(np.float64), cs, cells, 0.75, conf=0.99, spatial_weight=0.0, max_iters=5000, min_iters=50,
+                   lo_number=50, seed=1, use_degensac=True, f_ba=3, sampler=4, probabilities=prob, sampler_variance=0.1)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], F) < 1e-5
+    # H on the same pair with the AR-Sampler, linear pipeline: exact masks
+    Hm, mask = pyg.findHomography(pts, h1, w1, h2, w2, prob, threshold=3.0, sampler=4, max_iters=5000, min_iters=50,
+                                  neighborhood=0, neighborhood_size=4.0, sampler_variance=0.3, seed=2)
+    st = pyg.last_statistics
+    want = ref.run(O.H, pts.astype(np.float64), g["cell_sizes"], 4, 3.0, conf=0.99, spatial_weight=0.975, max_iters=5000,
+                   min_iters=50, lo_number=50, seed=2, sampler=4, probabilities=prob, sampler_variance=0.3)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert st["lo_samples"] == want["stats"]["lo_samples"]
+    assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], Hm) < 1e-5 and mask.sum() > 250
     g = np.load(os.path.join(GOLDEN, "fountain_matches.npz"))
     pts, K1, K2 = np.ascontiguousarray(g["pts"]), g["K1"], g["K2"]
     h1, w1, h2, w2 = (int(v) for v in g["size"])
     prob = [1.0 - i / len(pts) for i in range(len(pts))]
-    with pytest.warns(RuntimeWarning, match="AR-Sampler"):
-        E, mask = pyg.findEssentialMatrix(pts, K1, K2, h1, w1, h2, w2, probabilities=prob, threshold=0.75, conf=0.99, min_iters=50,
-                                          max_iters=5000, sampler=4)
-    assert mask.sum() > 450
+    E, mask = pyg.findEssentialMatrix(pts, K1, K2, h1, w1, h2, w2, probabilities=prob, threshold=0.75, conf=0.99, min_iters=50,
+                                      max_iters=5000, sampler=4)
+    st = pyg.last_statistics
+    assert mask.sum() > 450                                                  # tests/test_essential_matrix.py:98
+    npts = oracle.normalize_correspondences(pts.astype(np.float64), K1, K2)
+    thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
+    want = ref.run(O.E, npts, np.ones(4), 20, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50,
+                   seed=1, grid_pts=pts.astype(np.float64), sampler=4, radius=20.0, probabilities=prob, sampler_variance=0.1)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert st["lo_samples"] == want["stats"]["lo_samples"]
+    assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
