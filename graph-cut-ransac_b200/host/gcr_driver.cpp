@@ -131,6 +131,8 @@ namespace
 
 		// sampler 4: the AR-Sampler's sequence, drawn ahead on the host (gcr_host_samplers.h)
 		gcr_host::AdaptiveReordering ar_sampler;
+		// sampler 2: Progressive NAPSAC's sequence (its four grid layers are built on the GPU, gcr_grid_build)
+		gcr_host::ProgressiveNapsac pnapsac_sampler;
 		// main-loop batch
 		int B = 0;
 		uint64_t batch_first = 0;
@@ -387,12 +389,15 @@ namespace
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
 			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
-			if (S.sampler == 4)
+			if (S.sampler == 4 || S.sampler == 2)
 			{
-				// AdaptiveReorderingSampler (py/gcransac_python.cpp:4348-4359): the heap recurrence runs on the host, the
-				// batch's index sets go up in one copy
+				// AdaptiveReorderingSampler / ProgressiveNapsacSampler (py/gcransac_python.cpp:4334-4359): the recurrence
+				// over the sample number runs on the host, the batch's index sets go up in one copy
 				h_samples.resize((size_t)B * m);
-				ar_sampler.samples(first, (size_t)B, h_samples.data());
+				if (S.sampler == 4)
+					ar_sampler.samples(first, (size_t)B, h_samples.data());
+				else
+					pnapsac_sampler.samples(first, (size_t)B, h_samples.data());
 				if (gcr_memcpy_h2d(ctx, d_samples.p, h_samples.data(), (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
 					return fail("gcr_memcpy_h2d");
 			}
@@ -414,7 +419,7 @@ namespace
 			h_scores.resize(K);
 			h_counts.resize(K);
 			h_models.resize(K * 9);
-			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4)
+			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4 && S.sampler != 2)
 			{
 				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
 				h_samples.resize((size_t)B * m);
@@ -852,6 +857,44 @@ namespace
 			return true;
 		}
 
+		// ProgressiveNapsacSampler<4>(&points, {16, 8, 4, 2}, m, {w1, h1, w2, h2}, 0.5) (py/gcransac_python.cpp:4335-4343):
+		// one GridNeighborhoodGraph<4> per layer over the points currently uploaded, cell size = image size / cells
+		bool build_pnapsac()
+		{
+			static const uint64_t layer_cells[4] = {16, 8, 4, 2};
+			std::vector<gcr_host::GridLayer> layers(4);
+			DeviceBuffer dk, ds, dof;
+			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
+				return fail("gcr_malloc");
+			for (int l = 0; l < 4; ++l)
+			{
+				double cell_sizes[4];
+				for (int d = 0; d < 4; ++d)
+					cell_sizes[d] = S.image_sizes[d] / layer_cells[l];
+				uint32_t n_cells = 0;
+				uint64_t neighbor_number = 0;
+				if (gcr_grid_build(ctx, 0, cell_sizes, layer_cells[l], dk.as<uint64_t>(), ds.as<uint32_t>(), dof.as<uint32_t>(),
+				                   &n_cells, &neighbor_number) != GCR_OK)
+					return fail("gcr_grid_build");
+				gcr_host::GridLayer &g = layers[l];
+				g.sorted_idx.resize(n);
+				g.cell_offsets.resize((size_t)n_cells + 1);
+				if (gcr_memcpy_d2h(ctx, g.sorted_idx.data(), ds.p, (size_t)n * 4) != GCR_OK ||
+				    gcr_memcpy_d2h(ctx, g.cell_offsets.data(), dof.p, ((size_t)n_cells + 1) * 4) != GCR_OK)
+					return fail("gcr_memcpy_d2h");
+				g.cell_of_point.resize(n);
+				for (uint32_t c = 0; c < n_cells; ++c)
+					for (uint32_t q = g.cell_offsets[c]; q < g.cell_offsets[c + 1]; ++q)
+						g.cell_of_point[g.sorted_idx[q]] = c;
+			}
+			if (!pnapsac_sampler.initialize(std::move(layers), (size_t)n, m, 0.5, S.seed))
+			{
+				error = "sampler 2 (Progressive NAPSAC): bad sample size / point number";
+				return false;
+			}
+			return true;
+		}
+
 		bool build_grid()
 		{
 			if (S.neighborhood == 1)
@@ -909,6 +952,8 @@ namespace
 				}
 				if (!build_grid())
 					return -1;
+				if (S.sampler == 2 && !build_pnapsac()) // on the pixel coordinates (py/gcransac_python.cpp:2650)
+					return -1;
 			}
 			if (!nested)
 			{
@@ -918,6 +963,8 @@ namespace
 					return -1;
 				}
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
+					return -1;
+				if (S.sampler == 2 && !(grid_pts && grid_pts != pts) && !build_pnapsac())
 					return -1;
 				if (S.sampler == 4)
 				{
@@ -1189,6 +1236,52 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->neighborhood_radius = 20.0;
 	s->point_probabilities = nullptr;
 	s->sampler_variance = 0.1;
+	for (int d = 0; d < 4; ++d)
+		s->image_sizes[d] = 0.0;
+}
+
+// samples [first, first + count) of the host-side Progressive NAPSAC sequence over n x 4 host points; the grid layers are
+// built here on the host (the driver builds them with gcr_grid_build): no GPU involved, for the CPU tests.
+extern "C" int gcr_host_sample_progressive_napsac(const double *points, int n, int m, const double *image_sizes, uint64_t seed,
+                                                  uint64_t first, int count, uint32_t *out)
+{
+	if (!points || !image_sizes || !out || n < 1 || count < 0)
+		return -1;
+	static const size_t layer_cells[4] = {16, 8, 4, 2};
+	std::vector<gcr_host::GridLayer> layers(4);
+	for (int l = 0; l < 4; ++l)
+	{
+		// grid_neighborhood_graph.h:229-292: key = sum_d floor(x_d / cell_d) * cells^d
+		std::vector<std::pair<uint64_t, uint32_t>> keyed((size_t)n);
+		for (int i = 0; i < n; ++i)
+		{
+			uint64_t key = 0, offset = 1;
+			for (int d = 0; d < 4; ++d)
+			{
+				const size_t idx = (size_t)std::floor(points[4 * (size_t)i + d] / (image_sizes[d] / layer_cells[l]));
+				key += offset * idx;
+				offset *= layer_cells[l];
+			}
+			keyed[i] = std::make_pair(key, (uint32_t)i);
+		}
+		std::sort(keyed.begin(), keyed.end());
+		gcr_host::GridLayer &g = layers[l];
+		g.cell_of_point.resize(n);
+		g.sorted_idx.resize(n);
+		for (int q = 0; q < n; ++q)
+		{
+			if (q == 0 || keyed[q].first != keyed[q - 1].first)
+				g.cell_offsets.push_back((uint32_t)q);
+			g.sorted_idx[q] = keyed[q].second;
+			g.cell_of_point[keyed[q].second] = (uint32_t)g.cell_offsets.size() - 1;
+		}
+		g.cell_offsets.push_back((uint32_t)n);
+	}
+	gcr_host::ProgressiveNapsac s;
+	if (!s.initialize(std::move(layers), (size_t)n, m, 0.5, seed))
+		return -2;
+	s.samples(first, (size_t)count, out);
+	return 0;
 }
 
 // samples [first, first + count) of the host-side AR-Sampler sequence (gcr_host_samplers.h) -- what the driver uploads

@@ -55,7 +55,7 @@ typedef struct gcr_run_settings
 	 * (py/gcransac_python.cpp:1832-1887; pixel frame) */
 	int f_bundle_adjustment;
 	/* main sampler: 0 = uniform (samplers/uniform_sampler.h), 1 = PROSAC (samplers/prosac_sampler.h: the correspondences
-	 * are ordered by quality), 3 = the importance sampler of NG-RANSAC (samplers/importance_sampler.h; needs
+	 * are ordered by quality), 2 = Progressive NAPSAC (image_sizes below; host recurrence like 4), 3 = the importance sampler of NG-RANSAC (samplers/importance_sampler.h; needs
 	 * point_probabilities below), 4 = the AR-Sampler (samplers/adaptive_reordering_sampler.h; point_probabilities and
 	 * sampler_variance below; its heap recurrence runs on the host, gcr_host_samplers.h); the local-optimisation sampler is uniform either way (py/gcransac_python.cpp:4316-4330) */
 	int sampler;
@@ -68,6 +68,9 @@ typedef struct gcr_run_settings
 	const double *point_probabilities;
 	/* sampler 4: estimator_variance_ of AdaptiveReorderingSampler (`sampler_variance` of the Python calls, default 0.1) */
 	double sampler_variance;
+	/* sampler 2 (Progressive NAPSAC, samplers/progressive_napsac_sampler.h): w1, h1, w2, h2 -- its grid layers have
+	 * 16 / 8 / 4 / 2 cells per axis of these sizes (py/gcransac_python.cpp:4335-4343) */
+	double image_sizes[4];
 } gcr_run_settings;
 
 typedef struct gcr_run_stats
@@ -101,6 +104,10 @@ int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, const double
 /* samples [first, first + count) of the AR-Sampler sequence the driver uploads for sampler 4 (host only) */
 int gcr_host_sample_adaptive_reordering(const double *probabilities, int n, int m, double variance, uint64_t seed,
                                         uint64_t first, int count, long long repeat_at, uint32_t *out);
+
+/* samples [first, first + count) of the Progressive NAPSAC sequence the driver uploads for sampler 2 (host only) */
+int gcr_host_sample_progressive_napsac(const double *points, int n, int m, const double *image_sizes, uint64_t seed,
+                                       uint64_t first, int count, uint32_t *out);
 
 #ifdef __cplusplus
 }

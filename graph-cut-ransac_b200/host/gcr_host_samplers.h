@@ -1,4 +1,5 @@
-// gcr_host_samplers.h -- the reference's SEQUENTIAL main samplers, drawn ahead on the host for the batched driver.
+// gcr_host_samplers.h -- the reference's SEQUENTIAL main samplers, drawn ahead on the host for the batched driver:
+// AdaptiveReordering (sampler 4) and ProgressiveNapsac (sampler 2, see the class).
 //
 // AdaptiveReorderingSampler (samplers/adaptive_reordering_sampler.h, `sampler=4`, the AR-Sampler the reference's F / E
 // tests use) keeps a priority queue of (inlier probability, point): sample() pops the m best points (:205-215),
@@ -58,6 +59,213 @@ namespace gcr_host
 				pos = 0;
 			}
 			return buf[pos++];
+		}
+	};
+
+	// unbiased integer in [lo, hi]: Lemire's multiply-shift with rejection, as GcrDrawStream::bounded on the device
+	inline size_t in_range(WordStream &w, size_t lo, size_t hi)
+	{
+		const uint32_t range = (uint32_t)(hi - lo + 1);
+		for (;;)
+		{
+			const uint64_t p = (uint64_t)w.next() * range;
+			const uint32_t l = (uint32_t)p;
+			if (l < range)
+			{
+				const uint32_t thresh = (uint32_t)(0u - range) % range;
+				if (l < thresh)
+					continue;
+			}
+			return lo + (size_t)(p >> 32);
+		}
+	}
+
+	// ProsacSampler (samplers/prosac_sampler.h) as a state machine: the subset size, the sample counter and the range of
+	// its generator (which the reference only resets when the subset grows, :65-88, 178-203) -- the two PROSAC samplers
+	// inside Progressive NAPSAC are built with other arguments than the stand-alone one (sample size 1; convergence
+	// after n samples), and set to arbitrary sample numbers.
+	struct ProsacState
+	{
+		size_t m = 0, n = 0, convergence = 0, kth = 1, subset_size = 0, range_lo = 0, range_hi = 0;
+		std::vector<size_t> growth;
+		void initialize(size_t sample_size, size_t point_number, size_t convergence_iterations)
+		{
+			m = sample_size; n = point_number; convergence = convergence_iterations; kth = 1;
+			growth.assign(n, 0); // :129-160
+			double T_n = (double)convergence;
+			for (size_t i = 0; i < m; i++)
+				T_n *= static_cast<double>(m - i) / (n - i);
+			size_t T_n_prime = 1;
+			for (size_t i = 0; i < n; ++i)
+			{
+				if (i + 1 <= m) { growth[i] = T_n_prime; continue; }
+				const double Tn_plus1 = static_cast<double>(i + 1) * T_n / (i + 1 - m);
+				growth[i] = T_n_prime + (unsigned int)std::ceil(Tn_plus1 - T_n);
+				T_n = Tn_plus1;
+				T_n_prime = growth[i];
+			}
+			subset_size = m;
+			range_lo = 0; range_hi = m - 1; // :171-172
+		}
+		void grow()
+		{
+			++subset_size;
+			if (subset_size > n)
+				subset_size = n;
+			range_lo = 0; range_hi = subset_size - 2;
+		}
+		void increment() // :65-88
+		{
+			++kth;
+			if (kth > convergence) { range_lo = 0; range_hi = n - 1; }
+			else if (kth > growth[subset_size - 1])
+				grow();
+		}
+		void set_sample_number(size_t k) // :178-203
+		{
+			kth = k;
+			if (kth > convergence) { range_lo = 0; range_hi = n - 1; }
+			else
+				while (kth > growth[subset_size - 1] && subset_size != n)
+					grow();
+		}
+		void unique_set(WordStream &w, size_t *out, size_t count) const // uniform_random_generator.h:75-88
+		{
+			for (size_t i = 0; i < count; i++)
+			{
+				out[i] = in_range(w, range_lo, range_hi);
+				for (int j = (int)i - 1; j >= 0; j--)
+					if (out[i] == out[j]) { i--; break; }
+			}
+		}
+		void sample(WordStream &w, size_t *out) // :207-236
+		{
+			if (kth > convergence) { unique_set(w, out, m); return; }
+			unique_set(w, out, m - 1);
+			out[m - 1] = subset_size - 1;
+			increment();
+		}
+	};
+
+	// one layer of Progressive NAPSAC's grids: GridNeighborhoodGraph<4> as gcr_grid_build returns it -- the points sorted
+	// by cell (ascending index inside a cell = the reference's insertion order) and each point's cell
+	struct GridLayer
+	{
+		std::vector<uint32_t> cell_of_point, sorted_idx, cell_offsets;
+		size_t cell_size(uint32_t point) const { const uint32_t c = cell_of_point[point]; return cell_offsets[c + 1] - cell_offsets[c]; }
+		const uint32_t *cell_points(uint32_t point) const { return &sorted_idx[cell_offsets[cell_of_point[point]]]; }
+	};
+
+	// ProgressiveNapsacSampler<4> (samplers/progressive_napsac_sampler.h, `sampler=2`, the sampler of the reference's H
+	// test).  Sample k takes its centre from a one-point PROSAC sampler (the k-th best point), the rest from the centre's
+	// cell in the finest grid layer that holds enough points, the neighbourhood growing with the number of times each
+	// point has been hit (:246-310); after 0.5 n samples it is PROSAC over all points (:236-242).  Its update() is empty
+	// (:111-118): the sequence depends on the points, the layers and the random words only -- a sequential recurrence over
+	// k (the hit counters), drawn ahead on the host like the AR-Sampler's.  Sample k (from 1) takes stream 5 of (seed, k).
+	class ProgressiveNapsac
+	{
+		std::vector<GridLayer> layers;
+		std::vector<size_t> layer_of_point, hits, subset_size_of_point, growth;
+		ProsacState one_point, prosac;
+		size_t n = 0, m = 0, max_iterations = 0, kth = 0;
+		uint64_t seed = 0;
+		std::vector<uint32_t> drawn;
+
+		void generate_one()
+		{
+			++kth;
+			WordStream words(seed, kth, 5u);
+			size_t subset[16];
+			auto emit = [&]() { for (size_t i = 0; i < m; ++i) drawn.push_back((uint32_t)subset[i]); };
+			if (kth > max_iterations) // :236-242
+			{
+				prosac.set_sample_number(kth);
+				prosac.sample(words, subset);
+				emit();
+				return;
+			}
+			size_t centre[1];
+			one_point.sample(words, centre);
+			const size_t initial_point = centre[0];
+			const size_t hit_count = ++hits[initial_point];
+			size_t &subset_size = subset_size_of_point[initial_point]; // :259-262
+			while (hit_count > growth[subset_size - 1] && subset_size < n)
+				subset_size = std::min(subset_size + 1, n);
+			size_t &layer = layer_of_point[initial_point]; // :265-290
+			bool is_last_layer = false;
+			for (;;)
+			{
+				if (layer >= layers.size()) { is_last_layer = true; break; }
+				if (layers[layer].cell_size((uint32_t)initial_point) < subset_size) { ++layer; continue; }
+				break;
+			}
+			if (!is_last_layer) // :293-318
+			{
+				const uint32_t *neighbors = layers[layer].cell_points((uint32_t)initial_point);
+				subset[m - 1] = initial_point;
+				subset[m - 2] = neighbors[subset_size - 1];
+				// uniform_random_generator.h:105-124: m - 2 distinct POSITIONS in [0, subset_size - 2], never the value
+				// `initial_point` (the reference skips the centre's INDEX among neighbour positions; kept)
+				for (size_t i = 0; i < m - 2; i++)
+				{
+					subset[i] = in_range(words, 0, subset_size - 2);
+					if (subset[i] == initial_point) { i--; continue; }
+					for (int j = (int)i - 1; j >= 0; j--)
+						if (subset[i] == subset[j]) { i--; break; }
+				}
+				for (size_t i = 0; i < m - 2; ++i)
+				{
+					subset[i] = neighbors[subset[i]];
+					++hits[subset[i]];
+				}
+				++hits[subset[m - 2]];
+			}
+			else // :321-329
+			{
+				prosac.set_sample_number(kth);
+				prosac.sample(words, subset);
+				subset[m - 1] = initial_point;
+			}
+			emit();
+		}
+
+	public:
+		// grid_layers: finest first (the drivers use 16, 8, 4, 2 cells per axis); sampler_length 0.5 (py/gcransac_python.cpp:4343)
+		bool initialize(std::vector<GridLayer> grid_layers, size_t point_number, int sample_size, double sampler_length, uint64_t seed_)
+		{
+			if (sample_size < 3 || sample_size > 16 || point_number < (size_t)sample_size)
+				return false;
+			layers = std::move(grid_layers);
+			n = point_number; m = (size_t)sample_size; seed = seed_; kth = 0;
+			drawn.clear();
+			layer_of_point.assign(n, 0);
+			hits.assign(n, 0);
+			subset_size_of_point.assign(n, m);
+			one_point.initialize(1, n, n);
+			prosac.initialize(m, n, n);
+			max_iterations = static_cast<size_t>(sampler_length * n);
+			growth.assign(n, 0); // :179-199
+			const size_t local_sample_size = m - 1;
+			double T_n = (double)max_iterations;
+			for (size_t i = 0; i < local_sample_size; ++i)
+				T_n *= static_cast<double>(local_sample_size - i) / (n - i);
+			unsigned int T_n_prime = 1;
+			for (size_t i = 0; i < n; ++i)
+			{
+				if (i + 1 <= local_sample_size) { growth[i] = T_n_prime; continue; }
+				const double Tn_plus1 = static_cast<double>(i + 1) * T_n / (i + 1 - local_sample_size);
+				growth[i] = T_n_prime + static_cast<size_t>(std::ceil(Tn_plus1 - T_n));
+				T_n = Tn_plus1;
+				T_n_prime = (unsigned int)growth[i];
+			}
+			return true;
+		}
+		// samples [first, first + count) (0-based: sample g is the reference's call g + 1) -> out [count][m]
+		void samples(uint64_t first, size_t count, uint32_t *out)
+		{
+			while (drawn.size() / m < first + count)
+				generate_one();
+			std::copy(drawn.begin() + first * m, drawn.begin() + (first + count) * m, out);
 		}
 	};
 

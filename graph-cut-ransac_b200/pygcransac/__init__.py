@@ -10,19 +10,18 @@ max-flow on the host).  There is no CPU fallback: without a CUDA device / the bu
 
 Accepted-but-mapped arguments: `use_sprt` and `use_space_partitioning` are CPU early-exit / pruning
 tricks of the reference; the GPU scores every point of every model, which yields the scores those tricks approximate,
-so the flags are accepted and ignored.  `sampler` is 0 (uniform), 1 (PROSAC, the reference's default: the
-correspondences are taken to be ordered by quality), 3 (the importance sampler of NG-RANSAC: independent draws from
-`probabilities`, samplers/importance_sampler.h) or 4 (the AR-Sampler, samplers/adaptive_reordering_sampler.h: a heap
-recurrence over `probabilities` / `sampler_variance` that does not depend on any verdict, drawn ahead on the host and
-uploaded per batch), all on the counter-based stream.  P-NAPSAC (2) is not built: such calls run with PROSAC over the
-same quality order and emit a RuntimeWarning.  `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
+so the flags are accepted and ignored.  `sampler` takes every id of the reference: 0 uniform, 1 PROSAC (the
+reference's default: the correspondences are taken to be ordered by quality), 3 the importance sampler of NG-RANSAC
+(independent draws from `probabilities`) -- these three drawn on the GPU -- and 2 Progressive NAPSAC / 4 the AR-Sampler,
+whose sample k depends on samples 1..k-1 (hit counters resp. a heap) but on no verdict: their sequences are drawn ahead
+on the host (host/gcr_host_samplers.h) and uploaded per batch.  All on the counter-based word stream.
+`neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
 `neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
 approximate, run-dependent one).
 """
 import ctypes as C
 import os
 import threading
-import warnings
 
 import numpy as np
 
@@ -43,7 +42,7 @@ class RunSettings(C.Structure):
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
                 ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
-                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double)]
+                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4)]
 
 
 class RunStats(C.Structure):
@@ -112,13 +111,8 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         # divided by their maximum, heap recurrence on the host (host/gcr_host_samplers.h)
         if not (np.all(np.isfinite(prob)) and np.all(prob >= 0) and prob.sum() > 0):
             raise ValueError("probabilities should be finite, non-negative and not all zero")
-    elif sampler not in (0, 1):
-        # 2 P-NAPSAC: not built; guided by the given quality order, so the call runs with PROSAC over that order and says so
-        if sampler != 2:
-            raise NotImplementedError("sampler=%d is not a sampler of the three entry points (0-4)" % sampler)
-        warnings.warn("sampler=2 (P-NAPSAC) is not built; running PROSAC over the same quality order instead",
-                      RuntimeWarning, stacklevel=3)
-        sampler = 1
+    elif sampler not in (0, 1, 2):
+        raise NotImplementedError("sampler=%d is not a sampler of the three entry points (0-4)" % sampler)
     if neighborhood not in (0, 1):
         raise ValueError("neighborhood should be 0 (grid) or 1 (radius)")
     lib = _load_driver()
@@ -144,6 +138,8 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.f_bundle_adjustment = f_bundle_adjustment
     s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
     s.sampler_variance = float(sampler_variance)
+    for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
+        s.image_sizes[i] = float(v)
     model = np.zeros(9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()

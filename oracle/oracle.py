@@ -379,6 +379,10 @@ class Ref:
         lib.ref_sample_importance.argtypes = [_dp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u32p]
         lib.ref_sample_adaptive_reordering.restype = None
         lib.ref_sample_adaptive_reordering.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_longlong, _u32p]
+        lib.ref_set_image_sizes.restype = None
+        lib.ref_set_image_sizes.argtypes = [C.c_double] * 4
+        lib.ref_sample_pnapsac.restype = C.c_int
+        lib.ref_sample_pnapsac.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_uint64, C.c_int, _u32p]
         lib.ref_set_sampler_variance.restype = None
         lib.ref_set_sampler_variance.argtypes = [C.c_double]
         lib.ref_set_point_probabilities.restype = None
@@ -391,12 +395,13 @@ class Ref:
 
     def run(self, problem, pts, cell_sizes, cells_per_axis, threshold, conf=0.99, spatial_weight=0.975, max_iters=10000,
             min_iters=50, lo_number=50, seed=1, scoring_kind=0, grid_pts=None, use_degensac=False, f_ba=0, sampler=0, radius=0.0,
-            probabilities=None, sampler_variance=0.1):
+            probabilities=None, sampler_variance=0.1, image_sizes=None):
         """GCRANSAC<>::run (GCRANSAC.h:202-627, verbatim) with the settings of py/gcransac_python.cpp:4498-4504 on the
         counter-based sample stream.  f_ba (F): bit 0 = the BA non-minimal solver (the reference's default estimator),
         bit 1 = the post-run polish of py/gcransac_python.cpp:1832-1887.  sampler: 0 = uniform, 1 = PROSAC (the points
         are taken to be ordered by quality), 3 = the reference's ImportanceSampler over `probabilities`, 4 = its
-        AdaptiveReorderingSampler (probabilities / their maximum, `sampler_variance`).  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
+        AdaptiveReorderingSampler (probabilities / their maximum, `sampler_variance`), 2 = its ProgressiveNapsacSampler<4>
+        (layers 16 / 8 / 4 / 2 over `image_sizes` = (w1, h1, w2, h2), on grid_pts when given).  radius > 0: the exact radius neighbourhood (neighborhood=1) instead of the grid.
         scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
@@ -404,6 +409,8 @@ class Ref:
         mask = np.zeros(len(pts), dtype=np.uint8)
         stats = np.zeros(10, dtype=np.uint64)
         score = C.c_double()
+        if sampler == 2:
+            self.lib.ref_set_image_sizes(*[float(v) for v in image_sizes])   # (w1, h1, w2, h2)
         if sampler in (3, 4):
             prob = np.ascontiguousarray(probabilities, dtype=np.float64)
             assert len(prob) == len(pts)
@@ -446,6 +453,16 @@ class Ref:
         p = np.ascontiguousarray(probabilities, dtype=np.float64)
         out = np.empty((count, m), dtype=np.uint32)
         self.lib.ref_sample_importance(p, len(p), m, seed, first, count, out)
+        return out
+
+    def sample_pnapsac(self, pts, m, image_sizes, seed, count):
+        """The first `count` samples of the reference's own ProgressiveNapsacSampler<4> (verbatim; layers 16 / 8 / 4 / 2,
+        blending length 0.5 as the drivers construct it) on the counter-based word stream."""
+        pts = _as_pts(pts)
+        out = np.empty((count, m), dtype=np.uint32)
+        rc = self.lib.ref_sample_pnapsac(pts, len(pts), m, np.ascontiguousarray(image_sizes, dtype=np.float64), seed, count, out)
+        if rc != 0:
+            raise ValueError("ref_sample_pnapsac failed (%d)" % rc)
         return out
 
     def sample_adaptive_reordering(self, probabilities, m, variance, seed, count, repeat_at=-1):

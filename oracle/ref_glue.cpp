@@ -9,10 +9,110 @@
 // restated estimators"; stated wherever results of this library are quoted).
 #include <opencv2/core/core.hpp>
 
+#include <cstdint>
+#include <cstddef>
+// The reference's samplers draw through utils::UniformRandomGenerator<size_t> (uniform_random_generator.h): a
+// std::mt19937 seeded from std::random_device.  For the samplers whose own code has to run verbatim on a reproducible
+// stream (ProgressiveNapsacSampler and the two ProsacSamplers inside it), the member functions that consume random
+// numbers are explicitly specialised HERE, before anything instantiates them: same contracts (values uniform in the
+// range of the last resetGenerator, draw-and-reject for distinct sets, the `to_skip_` value never returned), the words
+// taken from the counter-based stream gcr_ref_words, which the sampler wrappers below point at (seed, sample number,
+// stream) before every sample() call.  Everything else in uniform_random_generator.h and every sampler header is the
+// reference's text.  (The counter-based uniform / PROSAC adapters of this file do not go through this class at all.)
+extern "C" void gcro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+namespace gcr_ref_words
+{
+	static uint32_t ctr[4], key[2], buf[4];
+	static int pos = 4;
+	inline void begin(uint64_t seed, uint64_t index, uint32_t stream)
+	{
+		ctr[0] = (uint32_t)index; ctr[1] = (uint32_t)(index >> 32); ctr[2] = 0; ctr[3] = stream;
+		key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+		pos = 4;
+	}
+	inline uint32_t next()
+	{
+		if (pos == 4)
+		{
+			gcro_philox4x32(ctr, key, buf);
+			++ctr[2];
+			pos = 0;
+		}
+		return buf[pos++];
+	}
+	// unbiased integer in [lo, hi] (Lemire's multiply-shift with rejection; the product's GcrDrawStream::bounded)
+	inline size_t in_range(size_t lo, size_t hi)
+	{
+		const uint32_t range = (uint32_t)(hi - lo + 1);
+		for (;;)
+		{
+			const uint64_t p = (uint64_t)next() * range;
+			const uint32_t l = (uint32_t)p;
+			if (l < range)
+			{
+				const uint32_t thresh = (uint32_t)(0u - range) % range;
+				if (l < thresh)
+					continue;
+			}
+			return lo + (size_t)(p >> 32);
+		}
+	}
+}
+#ifndef OLGA_INLINE
+#define OLGA_INLINE inline
+#define GCR_REF_DEFINED_OLGA_INLINE
+#endif
+#include "uniform_random_generator.h"
+namespace gcransac
+{
+	namespace utils
+	{
+		template <> inline int UniformRandomGenerator<size_t>::getRandomNumber() { return (int)gcr_ref_words::in_range(generate.a(), generate.b()); }
+		// uniform_random_generator.h:75-88
+		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_)
+		{
+			for (size_t i = 0; i < sample_size_; i++)
+			{
+				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
+				for (int j = (int)i - 1; j >= 0; j--)
+					if (sample_[i] == sample_[j]) { i--; break; }
+			}
+		}
+		// :90-103
+		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_, size_t max_)
+		{
+			resetGenerator(0, max_);
+			for (size_t i = 0; i < sample_size_; i++)
+			{
+				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
+				for (int j = (int)i - 1; j >= 0; j--)
+					if (sample_[i] == sample_[j]) { i--; break; }
+			}
+		}
+		// :105-124
+		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_, size_t max_, size_t to_skip_)
+		{
+			resetGenerator(0, max_);
+			for (size_t i = 0; i < sample_size_; i++)
+			{
+				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
+				if (sample_[i] == to_skip_) { i--; continue; }
+				for (int j = (int)i - 1; j >= 0; j--)
+					if (sample_[i] == sample_[j]) { i--; break; }
+			}
+		}
+	}
+}
+#ifdef GCR_REF_DEFINED_OLGA_INLINE
+#undef OLGA_INLINE
+#undef GCR_REF_DEFINED_OLGA_INLINE
+#endif
+
 #include "GCRANSAC.h"
 #include "neighborhood/grid_neighborhood_graph.h"
 #include "samplers/importance_sampler.h"
 #include "samplers/prosac_sampler.h"
+#include "samplers/progressive_napsac_sampler.h"
 #include "samplers/uniform_sampler.h"
 
 #include "gcr_oracle.h"
@@ -311,6 +411,29 @@ namespace
 			return sampler::AdaptiveReorderingSampler::sample(pool_, subset_, sample_size_);
 		}
 	};
+	double g_image_sizes[4] = {0, 0, 0, 0};    // ref_set_image_sizes (w1, h1, w2, h2) -> sampler_id 2
+	const cv::Mat *g_pnapsac_points = nullptr; // E: the pixel coordinates (the run itself is on the K-normalised points)
+
+	// The reference's ProgressiveNapsacSampler<4> verbatim (with the two ProsacSamplers inside it), constructed as the
+	// drivers construct it (py/gcransac_python.cpp:4335-4343: layers 16 / 8 / 4 / 2, blending length 0.5); sample()
+	// number k (from 1) draws from stream 5 of (seed, k) through the specialised generator members at the top of this file.
+	class CounterPNapsacSampler : public sampler::ProgressiveNapsacSampler<4>
+	{
+		uint64_t seed, next;
+
+	public:
+		CounterPNapsacSampler(const cv::Mat *c, size_t m, const double *sizes, uint64_t seed_)
+		    : sampler::ProgressiveNapsacSampler<4>(c, {16, 8, 4, 2}, m, {sizes[0], sizes[1], sizes[2], sizes[3]}, 0.5), seed(seed_), next(0)
+		{
+		}
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &pool_, size_t *const subset_, size_t sample_size_)
+		{
+			gcr_ref_words::begin(seed, ++next, 5u);
+			return sampler::ProgressiveNapsacSampler<4>::sample(pool_, subset_, sample_size_);
+		}
+	};
+
 	// py/gcransac_python.cpp:4350-4354
 	std::vector<double> normalized_by_max(std::vector<double> p)
 	{
@@ -384,6 +507,29 @@ void ref_sample_adaptive_reordering(const double *probabilities, int n, int m, d
 	}
 }
 void ref_set_sampler_variance(double v) { g_sampler_variance = v; }
+void ref_set_image_sizes(double w1, double h1, double w2, double h2)
+{
+	g_image_sizes[0] = w1; g_image_sizes[1] = h1; g_image_sizes[2] = w2; g_image_sizes[3] = h2;
+}
+// the first `count` samples of the reference's ProgressiveNapsacSampler<4> over the n x 4 points (pool = all points)
+int ref_sample_pnapsac(const double *pts, int n, int m, const double *sizes, uint64_t seed, int count, uint32_t *out)
+{
+	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
+	CounterPNapsacSampler s(&points, (size_t)m, sizes, seed);
+	if (!s.isInitialized())
+		return -1;
+	std::vector<size_t> pool(n), subset(m);
+	for (int i = 0; i < n; ++i)
+		pool[i] = (size_t)i;
+	for (int i = 0; i < count; ++i)
+	{
+		if (!s.sample(pool, subset.data(), (size_t)m))
+			return -2 - i;
+		for (int j = 0; j < m; ++j)
+			out[(size_t)i * m + j] = (uint32_t)subset[j];
+	}
+	return 0;
+}
 
 // the point probabilities sampler_id 3 of ref_run hands to the reference's ImportanceSampler
 void ref_set_point_probabilities(const double *probabilities, int n)
@@ -767,7 +913,16 @@ namespace
 				return -3;
 			ar_sampler.reset(new CounterARSampler(&points, normalized_by_max(g_point_probabilities), Est::sampleSize(), g_sampler_variance, seed));
 		}
+		// sampler_id 2 = Progressive NAPSAC over the points the grids are built on (py/gcransac_python.cpp:4334-4343)
+		std::unique_ptr<CounterPNapsacSampler> pnapsac_sampler;
+		if (sampler_id == 2)
+		{
+			pnapsac_sampler.reset(new CounterPNapsacSampler(g_pnapsac_points ? g_pnapsac_points : &points, Est::sampleSize(), g_image_sizes, seed));
+			if (!pnapsac_sampler->isInitialized())
+				return -3;
+		}
 		sampler::Sampler<cv::Mat, size_t> *main_sampler_ptr = sampler_id == 1   ? (sampler::Sampler<cv::Mat, size_t> *)&prosac_sampler
+		                                                      : sampler_id == 2 ? (sampler::Sampler<cv::Mat, size_t> *)pnapsac_sampler.get()
 		                                                      : sampler_id == 4 ? (sampler::Sampler<cv::Mat, size_t> *)ar_sampler.get()
 		                                                      : sampler_id == 3 ? (sampler::Sampler<cv::Mat, size_t> *)&importance_sampler
 		                                                                        : (sampler::Sampler<cv::Mat, size_t> *)&uniform_sampler;
@@ -828,7 +983,7 @@ namespace
 			stats_out[3] = st.neighbor_number;
 			stats_out[4] = st.accepted_models;
 			stats_out[5] = st.rejected_models;
-			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : sampler_id == 3 ? importance_sampler.drawn() : sampler_id == 4 ? ar_sampler->drawn() : uniform_sampler.drawn();
+			stats_out[6] = sampler_id == 1 ? prosac_sampler.drawn() : sampler_id == 3 ? importance_sampler.drawn() : sampler_id == 4 ? ar_sampler->drawn() : sampler_id == 2 ? pnapsac_sampler->drawn() : uniform_sampler.drawn();
 			stats_out[7] = lo_sampler.drawn();
 			stats_out[8] = estimator.degensac_runs;
 			stats_out[9] = estimator.degensac_updates;
@@ -854,6 +1009,11 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
 {
 	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
 	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
+	struct PNapsacPoints // findEssentialMatrix_ hands P-NAPSAC the pixel coordinates (py/gcransac_python.cpp:2650)
+	{
+		PNapsacPoints(const cv::Mat *p) { g_pnapsac_points = p; }
+		~PNapsacPoints() { g_pnapsac_points = nullptr; }
+	} pnapsac_points_guard(&grid_points);
 #define GCR_RUN(P, S) run_reference<P, S>(points, grid_points, cell_sizes, cells_per_axis, threshold, conf, spatial_weight, max_iters, min_iters, lo_number, seed, model_out, inlier_mask, stats_out, score_out, use_degensac, f_ba, sampler_id, radius)
 	if (scoring_kind == 0)
 	{

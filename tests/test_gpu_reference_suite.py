@@ -104,19 +104,27 @@ def test_find_essential_matrix_default_arguments(pyg, ref, oracle):
 
 def test_reference_calls_with_their_own_samplers(pyg, ref, oracle):
     """The reference's tests verbatim, sampler ids included: P-NAPSAC (2) for H, AR-Sampler (4) with rank-based inlier
-    probabilities for F and E (tests/test_*.py: get_probabilities).  The AR calls run the reference's own sampler
-    sequence (host/gcr_host_samplers.h) and are compared with the verbatim reference driver over the reference's own
-    AdaptiveReorderingSampler class; P-NAPSAC is not built: PROSAC over the same order, with a RuntimeWarning."""
+    probabilities for F and E (tests/test_*.py: get_probabilities).  The calls run the reference's own sampler sequences
+    (host/gcr_host_samplers.h) and are compared with the verbatim reference driver over the reference's own
+    ProgressiveNapsacSampler<4> / AdaptiveReorderingSampler classes."""
     g = np.load(os.path.join(GOLDEN, "cfg1_matches.npz"))
     pts = np.ascontiguousarray(g["pts"])
     h1, w1, h2, w2 = (int(v) for v in g["size"])
     prob = [1.0 - i / len(pts) for i in range(len(pts))]
-    with pytest.warns(RuntimeWarning, match="P-NAPSAC"):
-        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, threshold=3.0, sampler=2, max_iters=5000, min_iters=50, probabilities=[])
-    assert mask.sum() > 250
     import warnings
     with warnings.catch_warnings():
-        warnings.simplefilter("error")                                       # sampler 4 is native: no substitution warning
+        warnings.simplefilter("error")                                       # every sampler id is native: nothing is substituted
+        # tests/test_homography.py:75-85
+        H, mask = pyg.findHomography(pts, h1, w1, h2, w2, threshold=3.0, sampler=2, max_iters=5000, min_iters=50, probabilities=[])
+        st = pyg.last_statistics
+        assert mask.sum() > 250                                              # tests/test_homography.py:85
+        eps = np.finfo(np.float64).eps
+        cs = np.array([(w1 + eps) / 4, (h1 + eps) / 4, (w2 + eps) / 4, (h2 + eps) / 4])
+        want = ref.run(O.H, pts.astype(np.float64), cs, 4, 3.0, conf=0.99, spatial_weight=0.975, max_iters=5000, min_iters=50,
+                       lo_number=50, seed=1, sampler=2, image_sizes=(w1, h1, w2, h2))
+        assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5
         F, mask = pyg.findFundamentalMatrix(pts, h1, w1, h2, w2, threshold=0.75, sampler=4, max_iters=5000, min_iters=50,
                                             probabilities=prob)
     st = pyg.last_statistics
