@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs|cfg1_pairs]
 
 Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
 50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
@@ -51,6 +51,12 @@ WORKLOADS = {
     "h2k_pairs": dict(problem="h", n=2048, outliers=0.3, thr=3.0, pairs=128, pipeline=True,
                       desc="findHomography full pipeline (4-pt + MSAC, LO + graph-cut, conf 0.99), N=2048, 30% outliers, "
                            "thr 3.0 px, distinct synthetic pairs"),
+    # BASELINE configs[0]: the reference's own test call on its bundled image pair (tests/test_homography.py:75-85:
+    # threshold 3.0, P-NAPSAC sampler, max_iters 5000), every call a fresh seed; the SIFT matches are the committed fixture
+    "cfg1_pairs": dict(problem="h", n=762, outliers=None, thr=3.0, pairs=128, pipeline=True, max_iters=5000, sampler=2,
+                       fixture="cfg1_matches.npz",
+                       desc="findHomography on the bundled tests/test_data pair (762 SIFT matches), threshold 3.0 px, the "
+                            "reference's test call (P-NAPSAC sampler, max_iters 5000, conf 0.99), one call per seed (configs[0])"),
     "e2k_pairs": dict(problem="e", n=2048, outliers=0.85, thr=0.75, pairs=64, pipeline=True, max_iters=100000,
                       desc="findEssentialMatrix full pipeline (5-pt + MSAC, Stewenius refits in LO, conf 0.99, max_iters "
                            "100000), N=2048, 85% outliers, known K, thr 0.75 px, distinct synthetic pairs (configs[2] pipeline)"),
@@ -61,8 +67,20 @@ WORKLOADS = {
 }
 
 
+def fixture_sizes(wl):
+    """(h1, w1, h2, w2) of a fixture workload's image pair, else the synthetic 1024 x 1024."""
+    if wl.get("fixture"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", wl["fixture"]))
+        return tuple(int(v) for v in g["size"])
+    return (1024, 1024, 1024, 1024)
+
+
 def make_points(wl, rank):
     from pygcransac import synth
+    if wl.get("fixture"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", wl["fixture"]))
+        one = np.ascontiguousarray(g["pts"], dtype=np.float64)
+        return np.ascontiguousarray(np.stack([one] * wl["pairs"]))
     pts = []
     for p in range(wl["pairs"]):
         seed = (0 if wl.get("shard") == "hyps" else 1000 * rank) + p + 1   # a sharded problem is the SAME on every rank
@@ -127,13 +145,14 @@ class ClockSampler:
 
 def k3_dram_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE K3 launch, from the committed `ncu --set full` capture of this
-    workload (profiles/r1c_ncu_k3_*.txt; scripts/gpu_pass.sh regenerates it).  None if there is no capture."""
-    name = {"f4k": "f4k", "h2k_batch": "h2k", "e2k": "e2k"}.get(workload)
+    workload (the newest profiles/r*_ncu_k3_*.txt; scripts/gpu_pass.sh regenerates it).  None if there is no capture."""
+    name = {"f4k": "f4k", "h4k": "h4k", "h2k_batch": "h2k", "e2k": "e2k"}.get(workload)
     if name is None:
         return None
     try:
         total = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r1c_ncu_k3_%s.txt" % name)):
+        import glob
+        for line in open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k3_%s.txt" % name)))[-1]):
             f = line.split()
             if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 total += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
@@ -243,14 +262,19 @@ def bench_reference(args, wl, rank, world):
 
 def _pairs_cpu_worker(args):
     """One image pair through the reference's verbatim GCRANSAC<>::run on one host core."""
-    problem, pts, thr, weight, seed, max_iters = args
+    problem, pts, thr, weight, seed, max_iters, sampler, sizes = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     if "ref" not in _CPU_IMPL:
         _CPU_IMPL["ref"] = O.Ref()
     eps = np.finfo(np.float64).eps if problem == "h" else 0.0
-    cs = np.array([(1024 + eps) / 4.0] * 4)
+    h1, w1, h2, w2 = sizes
+    cs = np.array([(w1 + eps) / 4.0, (h1 + eps) / 4.0, (w2 + eps) / 4.0, (h2 + eps) / 4.0])
     t0 = time.perf_counter()
+    if sampler == 2:                                                             # configs[0]: the reference's own P-NAPSAC class
+        out = _CPU_IMPL["ref"].run(O.H, pts, cs, 4, thr, conf=0.99, spatial_weight=weight, max_iters=max_iters, min_iters=50,
+                                   lo_number=50, seed=seed, sampler=2, image_sizes=(w1, h1, w2, h2))
+        return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
     if problem == "e":
         from pygcransac import synth
         K = synth.K_MAT
@@ -276,7 +300,8 @@ def bench_pairs(args, wl, rank, world):
     n_pairs = wl["pairs"]
     pts = make_points(wl, rank)
     line = {"metric": "image pairs/s", "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "data": "real (the reference's bundled image pair, committed SIFT matches)" if wl.get("fixture") else "synthetic",
             "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "spatial_coherence_weight": weight}}
     if args.impl == "reference":
         if rank != 0:
@@ -284,7 +309,8 @@ def bench_pairs(args, wl, rank, world):
         import multiprocessing as mp
         cores = os.cpu_count() or 1
         pool = mp.get_context("fork").Pool(cores)
-        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters) for p in range(n_pairs)]
+        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters, wl.get("sampler", 0),
+                           fixture_sizes(wl)) for p in range(n_pairs)]
         for s in range(args.warmup):
             pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
         t0 = time.perf_counter()
@@ -325,11 +351,12 @@ def bench_pairs(args, wl, rank, world):
     pool = ThreadPoolExecutor(workers)
 
     extra = {}
+    sizes = fixture_sizes(wl)
 
     def one_pair(job):
         s, p = job
-        M, mask = find(pts[p], 1024, 1024, 1024, 1024, [], threshold=wl["thr"], conf=0.99,
-                       spatial_coherence_weight=weight, max_iters=max_iters, min_iters=50, use_sprt=False, sampler=0,
+        M, mask = find(pts[p], *sizes, [], threshold=wl["thr"], conf=0.99,
+                       spatial_coherence_weight=weight, max_iters=max_iters, min_iters=50, use_sprt=False, sampler=wl.get("sampler", 0),
                        neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank)
         st = pygcransac._tls.last_statistics
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):
