@@ -204,15 +204,19 @@ extern "C" gcr_status gcr_set_point_probabilities(gcr_ctx *ctx, const double *h_
 	}
 	cp[n - 1] = 1.0;
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (ctx->importance_n != n)
 	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // kernels still reading the old table
 		cudaFree(ctx->d_importance_cdf);
 		ctx->d_importance_cdf = nullptr;
 		ctx->importance_n = 0;
 		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_importance_cdf, (size_t)n * sizeof(double)));
 	}
-	GCR_CHECK_CUDA(ctx, cudaMemcpy(ctx->d_importance_cdf, cp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+	// stream-ordered, through the context's pinned ring (a pageable copy would serialise the host threads of a
+	// multi-context process)
+	const gcr_status st = gcr_memcpy_h2d(ctx, ctx->d_importance_cdf, cp.data(), (size_t)n * sizeof(double));
+	if (st != GCR_OK)
+		return st;
 	ctx->importance_n = n;
 	return GCR_OK;
 }
