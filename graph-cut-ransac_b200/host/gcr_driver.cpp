@@ -863,6 +863,19 @@ namespace
 		{
 			static const uint64_t layer_cells[4] = {16, 8, 4, 2};
 			std::vector<gcr_host::GridLayer> layers(4);
+			if (n <= 16384)
+			{
+				// a few thousand points: four sorts on the host take less than the four round trips of the GPU build
+				const double *p = (grid_pts && grid_pts != pts) ? grid_pts : pts;
+				for (int l = 0; l < 4; ++l)
+					gcr_host::build_grid_layer(p, (size_t)n, S.image_sizes, (size_t)layer_cells[l], layers[l]);
+				if (!pnapsac_sampler.initialize(std::move(layers), (size_t)n, m, 0.5, S.seed))
+				{
+					error = "sampler 2 (Progressive NAPSAC): bad sample size / point number";
+					return false;
+				}
+				return true;
+			}
 			DeviceBuffer dk, ds, dof;
 			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
 				return fail("gcr_malloc");
@@ -1250,33 +1263,7 @@ extern "C" int gcr_host_sample_progressive_napsac(const double *points, int n, i
 	static const size_t layer_cells[4] = {16, 8, 4, 2};
 	std::vector<gcr_host::GridLayer> layers(4);
 	for (int l = 0; l < 4; ++l)
-	{
-		// grid_neighborhood_graph.h:229-292: key = sum_d floor(x_d / cell_d) * cells^d
-		std::vector<std::pair<uint64_t, uint32_t>> keyed((size_t)n);
-		for (int i = 0; i < n; ++i)
-		{
-			uint64_t key = 0, offset = 1;
-			for (int d = 0; d < 4; ++d)
-			{
-				const size_t idx = (size_t)std::floor(points[4 * (size_t)i + d] / (image_sizes[d] / layer_cells[l]));
-				key += offset * idx;
-				offset *= layer_cells[l];
-			}
-			keyed[i] = std::make_pair(key, (uint32_t)i);
-		}
-		std::sort(keyed.begin(), keyed.end());
-		gcr_host::GridLayer &g = layers[l];
-		g.cell_of_point.resize(n);
-		g.sorted_idx.resize(n);
-		for (int q = 0; q < n; ++q)
-		{
-			if (q == 0 || keyed[q].first != keyed[q - 1].first)
-				g.cell_offsets.push_back((uint32_t)q);
-			g.sorted_idx[q] = keyed[q].second;
-			g.cell_of_point[keyed[q].second] = (uint32_t)g.cell_offsets.size() - 1;
-		}
-		g.cell_offsets.push_back((uint32_t)n);
-	}
+		gcr_host::build_grid_layer(points, (size_t)n, image_sizes, layer_cells[l], layers[l]);
 	gcr_host::ProgressiveNapsac s;
 	if (!s.initialize(std::move(layers), (size_t)n, m, 0.5, seed))
 		return -2;

@@ -156,6 +156,37 @@ namespace gcr_host
 		const uint32_t *cell_points(uint32_t point) const { return &sorted_idx[cell_offsets[cell_of_point[point]]]; }
 	};
 
+	// GridNeighborhoodGraph<4>::initialize (neighborhood/grid_neighborhood_graph.h:229-292) on the host, for point sets
+	// too small to be worth a GPU round trip: key = sum_d floor(x_d / cell_d) * cells^d, cells in ascending key order,
+	// points in ascending index order inside a cell (what gcr_grid_build returns for larger sets)
+	inline void build_grid_layer(const double *points, size_t n, const double *image_sizes, size_t cells, GridLayer &g)
+	{
+		std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
+		for (size_t i = 0; i < n; ++i)
+		{
+			uint64_t key = 0, offset = 1;
+			for (int d = 0; d < 4; ++d)
+			{
+				const size_t idx = (size_t)std::floor(points[4 * i + d] / (image_sizes[d] / cells));
+				key += offset * idx;
+				offset *= cells;
+			}
+			keyed[i] = std::make_pair(key, (uint32_t)i);
+		}
+		std::sort(keyed.begin(), keyed.end());
+		g.cell_of_point.assign(n, 0);
+		g.sorted_idx.assign(n, 0);
+		g.cell_offsets.clear();
+		for (size_t q = 0; q < n; ++q)
+		{
+			if (q == 0 || keyed[q].first != keyed[q - 1].first)
+				g.cell_offsets.push_back((uint32_t)q);
+			g.sorted_idx[q] = keyed[q].second;
+			g.cell_of_point[keyed[q].second] = (uint32_t)g.cell_offsets.size() - 1;
+		}
+		g.cell_offsets.push_back((uint32_t)n);
+	}
+
 	// ProgressiveNapsacSampler<4> (samplers/progressive_napsac_sampler.h, `sampler=2`, the sampler of the reference's H
 	// test).  Sample k takes its centre from a one-point PROSAC sampler (the k-th best point), the rest from the centre's
 	// cell in the finest grid layer that holds enough points, the neighbourhood growing with the number of times each

@@ -94,6 +94,22 @@ def test_importance_sampler_matches_reference_run(pyg, ref):
         pyg.findHomography(pts, 1024, 1024, 1024, 1024, np.zeros(len(pts)), sampler=3)
 
 
+def test_progressive_napsac_gpu_built_layers_match_reference_run(pyg, ref):
+    """sampler=2 on a point set large enough for the four grid layers to come from gcr_grid_build (smaller sets build
+    them on the host): the same run as the verbatim reference driver over the reference's own P-NAPSAC class."""
+    pts, Hm, inl = synth.homography_pair(20000, 0.5, seed=41)
+    H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, spatial_coherence_weight=0.0, max_iters=2000,
+                                 use_sprt=False, use_space_partitioning=False, sampler=2, seed=3)
+    st = pyg.last_statistics
+    cs = np.array([(1024 + np.finfo(np.float64).eps) / 4] * 4)
+    want = ref.run(O.H, pts, cs, 4, 2.0, conf=0.99, spatial_weight=0.0, max_iters=2000, min_iters=50, lo_number=50, seed=3,
+                   sampler=2, image_sizes=(1024, 1024, 1024, 1024))
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert st["lo_samples"] == want["stats"]["lo_samples"]
+    assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5
+    assert (mask & inl).sum() > 0.97 * inl.sum()
+
+
 def test_findhomography_synthetic_and_errors(pyg, ref):
     pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)
