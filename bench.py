@@ -57,9 +57,10 @@ WORKLOADS = {
                        fixture="cfg1_matches.npz",
                        desc="findHomography on the bundled tests/test_data pair (762 SIFT matches), threshold 3.0 px, the "
                             "reference's test call (P-NAPSAC sampler, max_iters 5000, conf 0.99), one call per seed (configs[0])"),
-    "e2k_pairs": dict(problem="e", n=2048, outliers=0.85, thr=0.75, pairs=64, pipeline=True, max_iters=100000,
-                      desc="findEssentialMatrix full pipeline (5-pt + MSAC, Stewenius refits in LO, conf 0.99, max_iters "
-                           "100000), N=2048, 85% outliers, known K, thr 0.75 px, distinct synthetic pairs (configs[2] pipeline)"),
+    "e2k_pairs": dict(problem="e", n=2048, outliers=0.85, thr=0.75, pairs=64, pipeline=True, max_iters=100000, scoring="magsac",
+                      desc="findEssentialMatrix full pipeline with MAGSAC++ scoring (GCRANSAC<E estimator, grid, "
+                           "MAGSACScoringFunction>: 5-pt, Stewenius refits in LO, conf 0.99, max_iters 100000), N=2048, 85% "
+                           "outliers, known K, thr 0.75 px, distinct synthetic pairs (configs[2] pipeline)"),
     # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL max all-reduce of the key
     "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps",
                         desc="single F problem, N=1048576 x K=1048576 7-pt samples sharded over the GPUs, MSAC, "
@@ -262,7 +263,7 @@ def bench_reference(args, wl, rank, world):
 
 def _pairs_cpu_worker(args):
     """One image pair through the reference's verbatim GCRANSAC<>::run on one host core."""
-    problem, pts, thr, weight, seed, max_iters, sampler, sizes = args
+    problem, pts, thr, weight, seed, max_iters, sampler, sizes, magsac = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     if "ref" not in _CPU_IMPL:
@@ -280,7 +281,7 @@ def _pairs_cpu_worker(args):
         K = synth.K_MAT
         npts = (pts - synth.SIZE / 2) / synth.FOCAL                              # K^-1 normalisation (utils.h:65-110)
         out = _CPU_IMPL["ref"].run(O.E, npts, cs, 4, thr / synth.FOCAL, conf=0.99, spatial_weight=weight, max_iters=max_iters,
-                                   min_iters=50, lo_number=50, seed=seed, grid_pts=pts)
+                                   min_iters=50, lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2 if magsac else 0)
         return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
     # F: the reference's default pipeline on both arms -- BA non-minimal solver, DEGENSAC, post-run bundle adjustment
     out = _CPU_IMPL["ref"].run(O.H if problem == "h" else O.F, pts, cs, 4, thr, conf=0.99, spatial_weight=weight,
@@ -310,7 +311,7 @@ def bench_pairs(args, wl, rank, world):
         cores = os.cpu_count() or 1
         pool = mp.get_context("fork").Pool(cores)
         jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters, wl.get("sampler", 0),
-                           fixture_sizes(wl)) for p in range(n_pairs)]
+                           fixture_sizes(wl), wl.get("scoring") == "magsac") for p in range(n_pairs)]
         for s in range(args.warmup):
             pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
         t0 = time.perf_counter()
@@ -357,7 +358,8 @@ def bench_pairs(args, wl, rank, world):
         s, p = job
         M, mask = find(pts[p], *sizes, [], threshold=wl["thr"], conf=0.99,
                        spatial_coherence_weight=weight, max_iters=max_iters, min_iters=50, use_sprt=False, sampler=wl.get("sampler", 0),
-                       neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank)
+                       neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank,
+                       scoring=1 if wl.get("scoring") == "magsac" else 0)
         st = pygcransac._tls.last_statistics
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):
             extra[k] = extra.get(k, 0) + st[k]                          # (approximate under threads: diagnostics only)

@@ -112,6 +112,11 @@ namespace
 		const double *grid_pts = nullptr; // points the neighbourhood grid is built on (E: pixel coordinates; else = pts)
 		gcr_run_settings S;
 		gcr_run_stats st;
+		// the _ScoringFunction template argument of GCRANSAC<>: GCR_MSAC (every Python entry point) or GCR_MAGSAC
+		// (scoring_function.h:237-349; BASELINE configs[2]).  FP32 ranking error: 2e-5 (MSAC), up to 2e-4 (MAGSAC: the
+		// step-function LUT index flips under FP32 residual error) -- rank_slack is what "may beat the best so far" allows
+		int scoring = GCR_MSAC;
+		double rank_slack = 2e-4;
 		double T; // squared truncated threshold (GCRANSAC.h:253-254)
 		double truncated_threshold;
 		std::string error;
@@ -167,7 +172,7 @@ namespace
 			{
 				uint32_t count = 0;
 				if (inliers) inliers->resize(n);
-				if (gcr_getscore_host(ctx, problem, GCR_MSAC, 0, model, T, S.threshold, &s.value, &count,
+				if (gcr_getscore_host(ctx, problem, scoring, 0, model, T, S.threshold, &s.value, &count,
 				                      inliers ? inliers->data() : nullptr) != GCR_OK)
 					return fail("gcr_getscore_host");
 				s.inliers = count;
@@ -180,7 +185,7 @@ namespace
 				return fail("gcr_malloc");
 			if (gcr_memcpy_h2d(ctx, d_one_model.p, model, 9 * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
-			if (gcr_score_exact(ctx, problem, GCR_MSAC, 0, d_one_model.as<double>(), 1, S.threshold, d_one_score.as<double>(),
+			if (gcr_score_exact(ctx, problem, scoring, 0, d_one_model.as<double>(), 1, S.threshold, d_one_score.as<double>(),
 			                    d_one_count.as<uint32_t>(), d_idx.as<uint32_t>(), d_res.as<double>()) != GCR_OK)
 				return fail("gcr_score_exact");
 			uint32_t count = 0;
@@ -412,7 +417,7 @@ namespace
 			}
 			else if (gcr_solve_minimal(ctx, problem, d_samples.as<uint32_t>(), B, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_solve_minimal");
-			if (gcr_score(ctx, problem, GCR_MSAC, d_models.as<double>(), d_valid.as<uint8_t>(), (int)K, S.threshold,
+			if (gcr_score(ctx, problem, scoring, d_models.as<double>(), d_valid.as<uint8_t>(), (int)K, S.threshold,
 			              GCR_SCORE_EXACT_COUNTS, d_scores.as<float>(), d_counts.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_score");
 			h_valid.resize(K);
@@ -451,7 +456,7 @@ namespace
 				for (int q = 0; q < mm; ++q)
 				{
 					const size_t slot = j * mm + q;
-					if (!h_valid[slot] || !((double)h_scores[slot] > record * (1.0 - 2e-4)))
+					if (!h_valid[slot] || !((double)h_scores[slot] > record * (1.0 - rank_slack)))
 						continue;
 					cand_slot.push_back(slot);
 					models.insert(models.end(), &h_models[slot * 9], &h_models[slot * 9] + 9);
@@ -476,7 +481,7 @@ namespace
 				return fail("gcr_malloc");
 			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models, C * 9 * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
-			if (gcr_score_exact(ctx, problem, GCR_MSAC, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
+			if (gcr_score_exact(ctx, problem, scoring, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
 			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), nullptr) != GCR_OK)
 				return fail("gcr_score_exact");
 			score.resize(C);
@@ -686,7 +691,7 @@ namespace
 				{
 					if (!d_lscores.ensure(ctx, n_models * sizeof(float)))
 						return fail("gcr_malloc");
-					if (gcr_score(ctx, problem, GCR_MSAC, d_lmodels.as<double>(), d_lok.as<uint8_t>(), n_models, S.threshold, 0,
+					if (gcr_score(ctx, problem, scoring, d_lmodels.as<double>(), d_lok.as<uint8_t>(), n_models, S.threshold, 0,
 					              d_lscores.as<float>(), nullptr) != GCR_OK)
 						return fail("gcr_score");
 					scores32.resize(n_models);
@@ -701,7 +706,7 @@ namespace
 					{
 						double record = max_score.value;
 						for (int t = 0; t < n_models && rec.size() < 64; ++t)
-							if (ok[t] && (double)scores32[t] > record * (1.0 - 2e-4))
+							if (ok[t] && (double)scores32[t] > record * (1.0 - rank_slack))
 							{
 								rec.push_back(t);
 								rec_models.insert(rec_models.end(), &models[(size_t)t * 9], &models[(size_t)t * 9] + 9);
@@ -719,7 +724,7 @@ namespace
 					{
 						if (!ok[t])
 							continue;
-						if (!((double)scores32[t] > max_score.value * (1.0 - 2e-4)))
+						if (!((double)scores32[t] > max_score.value * (1.0 - rank_slack)))
 							continue; // FP32 ranking says it cannot beat the best so far
 						Score s;
 						size_t c = 0;
@@ -950,6 +955,8 @@ namespace
 			B = S.batch > 0 ? S.batch : 1024;
 			truncated_threshold = 3.0 / 2.0 * S.threshold;
 			T = truncated_threshold * truncated_threshold;
+			scoring = S.scoring == GCR_MAGSAC ? GCR_MAGSAC : GCR_MSAC;
+			rank_slack = scoring == GCR_MAGSAC ? 1e-3 : 2e-4;
 			rm = gcr_max_refit_models(problem);
 			std::unique_ptr<PhaseTimer> setup_timer(new PhaseTimer(st.phase_seconds[0]));
 			if (nested)
@@ -1067,7 +1074,7 @@ namespace
 						memcpy(cur.model, model, sizeof(cur.model));
 						cur.lazy_count = h_counts[slot];
 						cur.idx.clear();
-						if (!((double)h_scores[slot] > best.value * (1.0 - 2e-4)))
+						if (!((double)h_scores[slot] > best.value * (1.0 - rank_slack)))
 							continue; // FP32 ranking: cannot beat the best so far (:440)
 						Score s;
 						if (!exact_slot(slot, model, s, cur.idx))
@@ -1249,6 +1256,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->neighborhood_radius = 20.0;
 	s->point_probabilities = nullptr;
 	s->sampler_variance = 0.1;
+	s->scoring = GCR_MSAC;
 	for (int d = 0; d < 4; ++d)
 		s->image_sizes[d] = 0.0;
 }

@@ -71,6 +71,9 @@ typedef struct gcr_run_settings
 	/* sampler 2 (Progressive NAPSAC, samplers/progressive_napsac_sampler.h): w1, h1, w2, h2 -- its grid layers have
 	 * 16 / 8 / 4 / 2 cells per axis of these sizes (py/gcransac_python.cpp:4335-4343) */
 	double image_sizes[4];
+	/* the scoring function GCRANSAC<> is instantiated with: GCR_MSAC (MSACScoringFunction, the default template argument
+	 * and what every Python entry point uses) or GCR_MAGSAC (MAGSACScoringFunction, scoring_function.h:237-349) */
+	int scoring;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats

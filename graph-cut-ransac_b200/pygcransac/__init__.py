@@ -17,7 +17,9 @@ whose sample k depends on samples 1..k-1 (hit counters resp. a heap) but on no v
 on the host (host/gcr_host_samplers.h) and uploaded per batch.  All on the counter-based word stream.
 `neighborhood` is 0 (grid, `neighborhood_size` cells per axis) or 1 (the reference's FLANN radius graph,
 `neighborhood_size` = radius in pixels: built here as the EXACT radius graph on the GPU, where OpenCV's FLANN returns an
-approximate, run-dependent one).
+approximate, run-dependent one).  Not reference arguments: `seed` (the counter-based sample streams), `device`, and
+`scoring` (0 = MSAC, what the reference's entry points instantiate; 1 = MAGSAC++, the reference's
+MAGSACScoringFunction template argument, scoring_function.h:237-349).
 """
 import ctypes as C
 import os
@@ -42,7 +44,7 @@ class RunSettings(C.Structure):
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
                 ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
-                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4)]
+                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4), ("scoring", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -93,7 +95,7 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
           neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0,
-          probabilities=(), sampler_variance=0.1):
+          probabilities=(), sampler_variance=0.1, scoring=0):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
     min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
@@ -138,6 +140,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.f_bundle_adjustment = f_bundle_adjustment
     s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
     s.sampler_variance = float(sampler_variance)
+    s.scoring = int(scoring)
     for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
         s.image_sizes[i] = float(v)
     model = np.zeros(9)
@@ -162,19 +165,19 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
 def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
                    spatial_coherence_weight=0.975, max_iters=10000, min_iters=50, use_sprt=True,
                    min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=0, neighborhood_size=4.0,
-                   use_space_partitioning=True, lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0):
+                   use_space_partitioning=True, lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0):
     """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
     None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
     return _find(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device, probabilities=probabilities,
-                 sampler_variance=sampler_variance)
+                 sampler_variance=sampler_variance, scoring=scoring)
 
 
 def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
                           spatial_coherence_weight=0.0, max_iters=10000, min_iters=50, use_sprt=True,
                           min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=1, neighborhood_size=20.0,
                           lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, use_degensac=True,
-                          bundle_adjustment=True):
+                          bundle_adjustment=True, scoring=0):
     """py/bindings.cpp:279-400, 1003-1022 -> findFundamentalMatrix_ (py/gcransac_python.cpp:1600-1921) with the
     reference's default estimator (types.h:78-80): 7-point minimal solver, non-minimal fits = 8-point + LM bundle
     adjustment (gcr_refit_f_ba), DEGENSAC (fundamental_estimator.h:341-572), and the post-run bundle adjustment on the
@@ -183,13 +186,13 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
     return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device,
                  use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, probabilities=probabilities,
-                 sampler_variance=sampler_variance)
+                 sampler_variance=sampler_variance, scoring=scoring)
 
 
 def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
                         spatial_coherence_weight=0.1, max_iters=10000, min_iters=50, use_sprt=True,
                         min_inlier_ratio_for_sprt=0.01, sampler=1, neighborhood=1, neighborhood_size=20.0, lo_number=50,
-                        sampler_variance=0.1, solver=0, seed=1, device=0):
+                        sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0):
     """py/bindings.cpp:710-857, 1091-1112 -> findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855): 5-point (Nister)
     minimal solver, Stewenius non-minimal refits, MSAC on the K-normalised points with threshold / mean focal length,
     grid neighbourhood on the pixel coordinates.  Without the reference's final LM bundle-adjustment polish
@@ -204,4 +207,4 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
         raise ValueError("K2 shape should be [3x3]")
     return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2),
-                 probabilities=probabilities, sampler_variance=sampler_variance)
+                 probabilities=probabilities, sampler_variance=sampler_variance, scoring=scoring)

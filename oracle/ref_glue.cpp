@@ -1000,8 +1000,8 @@ namespace
 
 extern "C" {
 
-// scoring_kind: 0 = reference MSACScoringFunction (verbatim CPU), 1 = gcr::CudaMSACScoringFunction (library built with
-// GCR_REF_WITH_CUDA only).  Returns the inlier count.
+// scoring_kind: 0 = reference MSACScoringFunction (verbatim CPU), 2 = reference MAGSACScoringFunction (verbatim CPU),
+// 1 = gcr::CudaMSACScoringFunction (library built with GCR_REF_WITH_CUDA only).  Returns the inlier count.
 int ref_run(int problem, int scoring_kind, const double *pts, int n, const double *cell_sizes, int cells_per_axis,
             double threshold, double conf, double spatial_weight, int max_iters, int min_iters, int lo_number,
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
@@ -1020,6 +1020,13 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);
 		if (problem == GCRO_F) return GCR_RUN(GCRO_F, MSACScoringFunction<OracleEstimator<GCRO_F>>);
 		if (problem == GCRO_E) return GCR_RUN(GCRO_E, MSACScoringFunction<OracleEstimator<GCRO_E>>);
+		return -1;
+	}
+	if (scoring_kind == 2) // GCRANSAC<Estimator, Graph, MAGSACScoringFunction<Estimator>> (scoring_function.h:237-349)
+	{
+		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MAGSACScoringFunction<OracleEstimator<GCRO_H>>);
+		if (problem == GCRO_F) return GCR_RUN(GCRO_F, MAGSACScoringFunction<OracleEstimator<GCRO_F>>);
+		if (problem == GCRO_E) return GCR_RUN(GCRO_E, MAGSACScoringFunction<OracleEstimator<GCRO_E>>);
 		return -1;
 	}
 #ifdef GCR_REF_WITH_CUDA

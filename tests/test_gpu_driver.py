@@ -110,6 +110,37 @@ def test_progressive_napsac_gpu_built_layers_match_reference_run(pyg, ref):
     assert (mask & inl).sum() > 0.97 * inl.sum()
 
 
+def test_magsac_scoring_pipeline_matches_reference_run(pyg, ref, oracle):
+    """GCRANSAC<Estimator, Graph, MAGSACScoringFunction<Estimator>> (scoring_function.h:237-349; BASELINE configs[2] is
+    E + MAGSAC++): the driver with gcr_run_settings.scoring = GCR_MAGSAC against the verbatim reference driver
+    instantiated with the reference's own MAGSACScoringFunction, E and H.  The mask marks residual <= threshold
+    (MAGSAC's inlier rule, :338-344), not MSAC's 1.5 x threshold."""
+    from pygcransac import _cabi
+    K = synth.K_MAT
+    for seed, outliers in ((6, 0.5), (7, 0.7)):
+        pts, Fm, Em, Kc, inl = synth.epipolar_pair(1500, outliers, seed=seed + 2)
+        E, mask = pyg.findEssentialMatrix(pts, K, K, 1024, 1024, 1024, 1024, [], threshold=0.75, max_iters=5000, sampler=0,
+                                          neighborhood=0, neighborhood_size=4.0, seed=seed, scoring=_cabi.MAGSAC)
+        st = pyg.last_statistics
+        npts = oracle.normalize_correspondences(pts, K, K)
+        thr = 0.75 / (0.25 * (K[0, 0] + K[1, 1] + K[0, 0] + K[1, 1]))
+        want = ref.run(O.E, npts, np.array([256.0] * 4), 4, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50,
+                       lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2)
+        assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
+        assert abs(st["score"] - want["score"]) <= 1e-6 * want["score"]
+        assert (mask & inl).sum() > 0.8 * inl.sum()
+    pts, Hm, inl = synth.homography_pair(2000, 0.4, seed=8)
+    H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, seed=6, scoring=_cabi.MAGSAC)
+    st = pyg.last_statistics
+    cs = np.array([(1024 + np.finfo(np.float64).eps) / 4] * 4)
+    want = ref.run(O.H, pts, cs, 4, 2.0, seed=6, scoring_kind=2, sampler=1)
+    assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+    assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5
+    assert abs(st["score"] - want["score"]) <= 1e-9 * want["score"]
+
+
 def test_findhomography_synthetic_and_errors(pyg, ref):
     pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)
