@@ -14,3 +14,7 @@ g++ -O2 -DNDEBUG -std=c++17 -w -fPIC -shared -ffp-contract=off -I"$REF" -I../../
     -o _ref/libgcr_driver.so gcr_driver.cpp \
     -L.. -lgcr_b200 -Wl,-rpath,'$ORIGIN/../..'
 echo "built graph-cut-ransac_b200/host/_ref/libgcr_driver.so"
+# the reference's C++ driver signatures (gcr_gcransac_python.h) called from a C++ translation unit, for the tests
+g++ -O2 -std=c++17 -fPIC -shared -I../../include -I. -o _ref/libgcr_cpp_api_shim.so ../../tests/cpp/cpp_api_shim.cpp \
+    -L_ref -lgcr_driver -L.. -lgcr_b200 -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../..'
+echo "built graph-cut-ransac_b200/host/_ref/libgcr_cpp_api_shim.so"

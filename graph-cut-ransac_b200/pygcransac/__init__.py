@@ -168,6 +168,10 @@ def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=
                    use_space_partitioning=True, lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0):
     """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
     None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
+    if use_space_partitioning and neighborhood != 0:
+        # py/gcransac_python.cpp:4282-4286: "Space Partitioning only works with Grid neighorbood yet. Thus, setting
+        # neighborhood_id = 0." -- the flag itself has no effect here, its side effect on the graph is kept
+        neighborhood = 0
     return _find(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, True, seed, device, probabilities=probabilities,
                  sampler_variance=sampler_variance, scoring=scoring)
