@@ -925,6 +925,18 @@ namespace
 			have_grid = false;
 			if (!(S.spatial_coherence_weight > 0.0) || !S.do_local_optimization)
 				return true;
+			if (n <= 16384)
+			{
+				// a few thousand points: binning + one sort on the host costs less than the ~10 launches and two
+				// synchronising read-backs of the GPU build (which every host thread's pair would queue on the context)
+				gcr_host::GridLayer g;
+				gcr_host::build_grid_cells((grid_pts && grid_pts != pts) ? grid_pts : pts, (size_t)n, S.cell_sizes, (size_t)S.cells_per_axis, g);
+				cell_of_point.swap(g.cell_of_point);
+				sorted_idx.swap(g.sorted_idx);
+				cell_offsets.swap(g.cell_offsets);
+				have_grid = true;
+				return true;
+			}
 			DeviceBuffer dk, ds, dof;
 			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
 				return fail("gcr_malloc");
@@ -964,8 +976,11 @@ namespace
 			else if (grid_pts && grid_pts != pts)
 			{
 				// findEssentialMatrix_ builds the grid on the pixel coordinates and runs on the K-normalised ones
-				// (py/gcransac_python.cpp:2592-2600, 2641-2645)
-				if (gcr_points_upload(ctx, grid_pts, n, 4, 1) != GCR_OK)
+				// (py/gcransac_python.cpp:2592-2600, 2641-2645).  The pixel coordinates only go to the GPU when a GPU build
+				// will read them: the radius graph, or grids over more than 16384 points.
+				const bool graph_wanted = S.spatial_coherence_weight > 0.0 && S.do_local_optimization;
+				if (((graph_wanted && S.neighborhood == 1) || ((graph_wanted || S.sampler == 2) && n > 16384)) &&
+				    gcr_points_upload(ctx, grid_pts, n, 4, 1) != GCR_OK)
 				{
 					fail("gcr_points_upload");
 					return -1;

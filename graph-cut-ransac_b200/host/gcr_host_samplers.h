@@ -159,7 +159,15 @@ namespace gcr_host
 	// GridNeighborhoodGraph<4>::initialize (neighborhood/grid_neighborhood_graph.h:229-292) on the host, for point sets
 	// too small to be worth a GPU round trip: key = sum_d floor(x_d / cell_d) * cells^d, cells in ascending key order,
 	// points in ascending index order inside a cell (what gcr_grid_build returns for larger sets)
+	inline void build_grid_cells(const double *points, size_t n, const double *cell_sizes, size_t cells, GridLayer &g);
 	inline void build_grid_layer(const double *points, size_t n, const double *image_sizes, size_t cells, GridLayer &g)
+	{
+		double cell_sizes[4];
+		for (int d = 0; d < 4; ++d)
+			cell_sizes[d] = image_sizes[d] / cells; // progressive_napsac_sampler.h:171-173
+		build_grid_cells(points, n, cell_sizes, cells, g);
+	}
+	inline void build_grid_cells(const double *points, size_t n, const double *cell_sizes, size_t cells, GridLayer &g)
 	{
 		std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
 		for (size_t i = 0; i < n; ++i)
@@ -167,7 +175,7 @@ namespace gcr_host
 			uint64_t key = 0, offset = 1;
 			for (int d = 0; d < 4; ++d)
 			{
-				const size_t idx = (size_t)std::floor(points[4 * i + d] / (image_sizes[d] / cells));
+				const size_t idx = (size_t)std::floor(points[4 * i + d] / cell_sizes[d]);
 				key += offset * idx;
 				offset *= cells;
 			}
