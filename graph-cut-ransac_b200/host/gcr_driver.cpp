@@ -1006,7 +1006,8 @@ namespace
 					if (!S.point_probabilities ||
 					    !ar_sampler.initialize(S.point_probabilities, (size_t)n, m, S.sampler_variance, S.seed))
 					{
-						error = "sampler 4 (AR-Sampler) needs gcr_run_settings.point_probabilities";
+						error = "sampler 4 (AR-Sampler) needs gcr_run_settings.point_probabilities: one finite, non-negative value per "
+						        "correspondence, not all zero";
 						return -1;
 					}
 				}

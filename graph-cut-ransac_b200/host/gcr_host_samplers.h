@@ -380,7 +380,13 @@ namespace gcr_host
 				return false;
 			double max_prob = 0;
 			for (size_t i = 0; i < n; ++i)
+			{
+				if (!std::isfinite(probabilities[i]) || probabilities[i] < 0.0)
+					return false; // (the reference does not check: NaN keys would break its heap's ordering)
 				max_prob = std::max(max_prob, probabilities[i]);
+			}
+			if (!(max_prob > 0.0))
+				return false;
 			initial.resize(n);
 			for (size_t i = 0; i < n; ++i)
 				initial[i] = probabilities[i] / max_prob;

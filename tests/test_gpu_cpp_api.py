@@ -82,6 +82,13 @@ def test_cpp_entry_points_failure_conventions(shim):
     assert count == 0 and len(H) == 0 and len(mask) == 0
     count, H, mask = call(_cabi.H, pts, [0.5] * 10, sizes, 0.975, 3.0, 4, 0, 4.0, 1)   # AR-Sampler: one probability per point
     assert count == 0 and len(H) == 0
+    bad = np.full(len(pts), 0.5)
+    bad[7] = np.nan
+    for sampler in (3, 4):                                                             # probabilities that are no probabilities
+        count, H, mask = call(_cabi.H, pts, bad, sizes, 0.975, 3.0, sampler, 0, 4.0, 1)
+        assert count == 0 and len(H) == 0
+        count, H, mask = call(_cabi.H, pts, np.zeros(len(pts)), sizes, 0.975, 3.0, sampler, 0, 4.0, 1)
+        assert count == 0 and len(H) == 0
     count, H, mask = call(_cabi.H, pts, [], sizes, 0.975, 3.0, 1, 5, 4.0, 1, use_sp=False)     # unknown neighbourhood
     assert count == 0
     count, H, mask = call(_cabi.H, pts[:3], [], sizes, 0.975, 3.0, 1, 0, 4.0, 1)       # fewer points than a minimal sample
