@@ -89,6 +89,7 @@ namespace
 	struct InlierBuffer
 	{
 		bool lazy = false;      // holds "the inliers of `model`", not fetched yet
+		long long slot = -1;    // lazy: `model` itself is still slot `slot` of the current batch on the device (>= 0), not in `model`
 		double model[9] = {0};
 		uint64_t lazy_count = 0;
 		std::vector<uint32_t> idx;
@@ -146,7 +147,12 @@ namespace
 		std::vector<uint8_t> h_valid;
 		std::vector<float> h_scores;
 		std::vector<uint32_t> h_counts;
+		// the models of a batch stay on the device (72 B per slot, 2.9 MB per 4096 five-point samples): the host fetches the
+		// few it looks at -- record candidates, the model behind a lazy inlier container -- into this cache
 		std::vector<double> h_models;
+		std::vector<uint8_t> h_model_have;
+		InlierBuffer *live_buffers = nullptr; // the two containers of the run in progress (their lazy models are resolved
+		                                      // before a new batch overwrites d_models)
 		// exact scoring
 		DeviceBuffer d_one_model, d_one_score, d_one_count, d_idx, d_res;
 		// LO batch
@@ -203,10 +209,52 @@ namespace
 			return true;
 		}
 
+		// model of slot `slot` of the current batch, fetched on first use (one 72-byte read-back)
+		const double *model_of(size_t slot)
+		{
+			if (!h_model_have[slot])
+			{
+				if (gcr_memcpy_d2h(ctx, &h_models[slot * 9], d_models.as<double>() + slot * 9, 9 * sizeof(double)) != GCR_OK)
+				{
+					fail("gcr_memcpy_d2h");
+					return nullptr;
+				}
+				h_model_have[slot] = 1;
+			}
+			return &h_models[slot * 9];
+		}
+		// several at once: the copies are queued, one synchronise delivers them
+		bool fetch_models(const std::vector<size_t> &slots)
+		{
+			bool queued = false;
+			for (size_t slot : slots)
+				if (!h_model_have[slot])
+				{
+					if (gcr_memcpy_d2h_async(ctx, &h_models[slot * 9], d_models.as<double>() + slot * 9, 9 * sizeof(double)) != GCR_OK)
+						return fail("gcr_memcpy_d2h");
+					h_model_have[slot] = 1;
+					queued = true;
+				}
+			return !queued || gcr_sync(ctx) == GCR_OK || fail("gcr_sync");
+		}
+		bool resolve_model(InlierBuffer &b)
+		{
+			if (b.slot < 0)
+				return true;
+			const double *model = model_of((size_t)b.slot);
+			if (!model)
+				return false;
+			memcpy(b.model, model, sizeof(b.model));
+			b.slot = -1;
+			return true;
+		}
+
 		bool materialise(InlierBuffer &b)
 		{
 			if (!b.lazy)
 				return true;
+			if (!resolve_model(b))
+				return false;
 			Score s;
 			if (!exact(b.model, s, &b.idx))
 				return false;
@@ -390,6 +438,10 @@ namespace
 		bool run_batch(uint64_t first)
 		{
 			const size_t K = (size_t)B * mm;
+			if (live_buffers && !h_model_have.empty()) // a lazy container may still point into the batch about to be overwritten
+				for (int b = 0; b < 2; ++b)
+					if (live_buffers[b].lazy && !resolve_model(live_buffers[b]))
+						return false;
 			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * 9 * sizeof(double)) ||
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
@@ -424,6 +476,12 @@ namespace
 			h_scores.resize(K);
 			h_counts.resize(K);
 			h_models.resize(K * 9);
+			// small batches (H, F: up to a few hundred KB) come back whole with the flags and scores -- one more queued copy,
+			// no later round trip; large ones (five-point batches: 0.7-2.9 MB) stay on the device and are fetched on demand
+			const bool models_with_batch = K * 9 * sizeof(double) <= (size_t)(256 << 10);
+			h_model_have.assign(K, models_with_batch ? 1 : 0);
+			if (models_with_batch && gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
 			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4 && S.sampler != 2)
 			{
 				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
@@ -433,8 +491,7 @@ namespace
 			}
 			if (gcr_memcpy_d2h_async(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
 			    gcr_memcpy_d2h_async(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK || gcr_sync(ctx) != GCR_OK)
+			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK || gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			batch_first = first;
 			batch_count = B;
@@ -451,7 +508,6 @@ namespace
 		{
 			cand_slot.clear();
 			double record = best_value;
-			std::vector<double> models;
 			for (size_t j = (size_t)(from - batch_first); j < (size_t)batch_count; ++j)
 				for (int q = 0; q < mm; ++q)
 				{
@@ -459,7 +515,6 @@ namespace
 					if (!h_valid[slot] || !((double)h_scores[slot] > record * (1.0 - rank_slack)))
 						continue;
 					cand_slot.push_back(slot);
-					models.insert(models.end(), &h_models[slot * 9], &h_models[slot * 9] + 9);
 					record = std::max(record, (double)h_scores[slot]);
 				}
 			const size_t C = cand_slot.size();
@@ -468,6 +523,11 @@ namespace
 				cand_slot.clear(); // nothing to gain / an implausible batch (pure noise): on demand
 				return true;
 			}
+			if (!fetch_models(cand_slot))
+				return false;
+			std::vector<double> models;
+			for (size_t slot : cand_slot)
+				models.insert(models.end(), &h_models[slot * 9], &h_models[slot * 9] + 9);
 			return exact_many(models.data(), C, cand_score, cand_count, cand_idx);
 		}
 
@@ -1036,6 +1096,7 @@ namespace
 			Score best;
 			double best_model[9] = {0};
 			InlierBuffer buf[2];
+			live_buffers = buf;
 			int offset = 0;
 			batch_count = 0;
 
@@ -1083,15 +1144,19 @@ namespace
 						if (!h_valid[slot])
 							continue;
 						++st.models_scored;
-						const double *model = &h_models[slot * 9];
 						// the reference's getScore writes this model's inliers into the current container
 						InlierBuffer &cur = buf[offset];
 						cur.lazy = true;
-						memcpy(cur.model, model, sizeof(cur.model));
+						cur.slot = (long long)slot; // the model stays on the device unless somebody asks for it
 						cur.lazy_count = h_counts[slot];
 						cur.idx.clear();
 						if (!((double)h_scores[slot] > best.value * (1.0 - rank_slack)))
 							continue; // FP32 ranking: cannot beat the best so far (:440)
+						const double *model = model_of(slot);
+						if (!model)
+							return -1;
+						memcpy(cur.model, model, sizeof(cur.model));
+						cur.slot = -1;
 						Score s;
 						if (!exact_slot(slot, model, s, cur.idx))
 							return -1;
