@@ -156,7 +156,7 @@ namespace
 		// exact scoring
 		DeviceBuffer d_one_model, d_one_score, d_one_count, d_idx, d_res;
 		// LO batch
-		DeviceBuffer d_pool, d_sets, d_offsets, d_sizes, d_lmodels, d_lok, d_lscores, d_lcounts, d_weights;
+		DeviceBuffer d_pool, d_sets, d_offsets, d_lmodels, d_lok, d_lscores, d_lcounts, d_weights;
 		// grid
 		std::vector<uint32_t> cell_of_point, sorted_idx, cell_offsets;
 		bool have_grid = false;
@@ -658,12 +658,15 @@ namespace
 				if (gcr_memcpy_h2d(ctx, d_sets.p, flat, total * sizeof(uint32_t)) != GCR_OK)
 					return fail("gcr_memcpy_h2d");
 			}
-			if (!d_offsets.ensure(ctx, count * sizeof(uint32_t)) || !d_sizes.ensure(ctx, count * sizeof(uint32_t)) ||
+			// offsets and sizes travel as one array (one copy instead of two): [offsets | sizes]
+			if (!d_offsets.ensure(ctx, 2 * count * sizeof(uint32_t)) ||
 			    !d_lmodels.ensure(ctx, (size_t)count * rm * 9 * sizeof(double)) || !d_lok.ensure(ctx, (size_t)count * rm))
 				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_offsets.p, offsets.data(), count * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_h2d(ctx, d_sizes.p, sizes.data(), count * sizeof(uint32_t)) != GCR_OK)
+			std::vector<uint32_t> offsets_sizes(offsets.begin(), offsets.begin() + count);
+			offsets_sizes.insert(offsets_sizes.end(), sizes.begin(), sizes.begin() + count);
+			if (gcr_memcpy_h2d(ctx, d_offsets.p, offsets_sizes.data(), 2 * count * sizeof(uint32_t)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
+			const uint32_t *d_set_offsets = d_offsets.as<uint32_t>(), *d_set_sizes = d_offsets.as<uint32_t>() + count;
 			const double *d_w = nullptr;
 			if (weights_by_point)
 			{
@@ -679,11 +682,11 @@ namespace
 			                                       : (rp == GCR_F && variant == 0 && (S.f_bundle_adjustment & 1)) ? GCR_BA_HARTLEY : 0;
 			if (ba_frame)
 			{
-				if (gcr_refit_f_ba(ctx, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w, weight_mode,
+				if (gcr_refit_f_ba(ctx, 0, d_sets.as<uint32_t>(), d_set_offsets, d_set_sizes, count, d_w, weight_mode,
 				                   ba_frame, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 					return fail("gcr_refit_f_ba");
 			}
-			else if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_offsets.as<uint32_t>(), d_sizes.as<uint32_t>(), count, d_w,
+			else if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_set_offsets, d_set_sizes, count, d_w,
 			                   weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_refit");
 			models.resize((size_t)count * rm * 9);
@@ -928,6 +931,12 @@ namespace
 		{
 			static const uint64_t layer_cells[4] = {16, 8, 4, 2};
 			std::vector<gcr_host::GridLayer> layers(4);
+			for (int d = 0; d < 4; ++d)
+				if (!(S.image_sizes[d] > 0.0) || !std::isfinite(S.image_sizes[d]))
+				{
+					error = "sampler 2 (Progressive NAPSAC) needs gcr_run_settings.image_sizes = (w1, h1, w2, h2), all positive";
+					return false;
+				}
 			if (n <= 16384)
 			{
 				// a few thousand points: four sorts on the host take less than the four round trips of the GPU build

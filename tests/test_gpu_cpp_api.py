@@ -89,6 +89,8 @@ def test_cpp_entry_points_failure_conventions(shim):
         assert count == 0 and len(H) == 0
         count, H, mask = call(_cabi.H, pts, np.zeros(len(pts)), sizes, 0.975, 3.0, sampler, 0, 4.0, 1)
         assert count == 0 and len(H) == 0
+    count, H, mask = call(_cabi.H, pts, [], (0, 1024, 1024, 1024), 0.975, 3.0, 2, 0, 4.0, 1)   # P-NAPSAC without an image size
+    assert count == 0
     count, H, mask = call(_cabi.H, pts, [], sizes, 0.975, 3.0, 1, 5, 4.0, 1, use_sp=False)     # unknown neighbourhood
     assert count == 0
     count, H, mask = call(_cabi.H, pts[:3], [], sizes, 0.975, 3.0, 1, 0, 4.0, 1)       # fewer points than a minimal sample
