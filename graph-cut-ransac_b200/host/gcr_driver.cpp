@@ -1121,11 +1121,13 @@ namespace
 					if (batch_count == 0 || g < batch_first || g >= batch_first + (uint64_t)batch_count)
 					{
 						PhaseTimer t(st.phase_seconds[1]);
-						// batch size: the configured one, four times that while the loop still has far to go (the samples
-						// are a function of their index, so batch boundaries do not change any result)
+						// batch size: the configured one, 4 x / 16 x that while the loop still has far to go -- a 5-point run at
+						// 85 % outliers needs ~60 000 samples, and 4096 of them fill a third of the GPU (the samples are a
+						// function of their index, so batch boundaries do not change any result)
 						const uint64_t horizon = std::min<uint64_t>(max_iteration, S.max_iteration_number);
 						const int base = S.batch > 0 ? S.batch : 1024;
-						B = (st.gpu_batches > 0 && horizon > it && horizon - it > 8ull * (uint64_t)base) ? 4 * base : base; // (the first
+						const uint64_t far = (st.gpu_batches > 0 && horizon > it) ? horizon - it : 0;
+						B = far > 64ull * (uint64_t)base ? 16 * base : far > 8ull * (uint64_t)base ? 4 * base : base; // (the first
 						// batch usually finds a model that shortens the horizon from "unbounded" to a few hundred samples)
 						if (!run_batch(g) || !prefetch_candidates(best.value, g))
 							return -1;

@@ -168,6 +168,8 @@ def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=
                    use_space_partitioning=True, lo_number=50, sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0):
     """py/bindings.cpp:859-983, 1158-1178 -> findHomography_ (py/gcransac_python.cpp:4221-4550).  Returns (H 3x3 or
     None, mask bool[N]); the mask marks points within 1.5 x threshold (MSAC's truncated threshold)."""
+    if solver != 0:
+        raise NotImplementedError("solver=%d: only point correspondences (solver 0) are on this path" % solver)
     if use_space_partitioning and neighborhood != 0:
         # py/gcransac_python.cpp:4282-4286: "Space Partitioning only works with Grid neighorbood yet. Thus, setting
         # neighborhood_id = 0." -- the flag itself has no effect here, its side effect on the graph is kept
@@ -187,6 +189,8 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
     adjustment (gcr_refit_f_ba), DEGENSAC (fundamental_estimator.h:341-572), and the post-run bundle adjustment on the
     inliers (py/gcransac_python.cpp:1832-1887).  `use_degensac=False` / `bundle_adjustment=False` (not reference
     arguments) switch those parts off (linear 8-point non-minimal fits, no polish)."""
+    if solver != 0:
+        raise NotImplementedError("solver=%d: only point correspondences (solver 0) are on this path" % solver)
     return _find(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device,
                  use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, probabilities=probabilities,

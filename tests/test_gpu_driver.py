@@ -155,6 +155,8 @@ def test_findhomography_synthetic_and_errors(pyg, ref):
         pyg.findHomography(np.zeros((10, 3)), 10, 10, 10, 10, [])
     with pytest.raises(NotImplementedError):
         pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], sampler=7)
+    with pytest.raises(NotImplementedError):                         # SIFT / affine correspondence solvers are other estimators
+        pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], solver=1)
     with pytest.raises(ValueError):                                  # NG-RANSAC / AR need one probability per correspondence
         pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], sampler=4)
     # no model: pure noise, tiny threshold -> (None, all-false mask) like bindings.cpp:973-975
