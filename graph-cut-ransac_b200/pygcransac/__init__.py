@@ -216,3 +216,17 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
     return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2),
                  probabilities=probabilities, sampler_variance=sampler_variance, scoring=scoring)
+
+
+def find6DPose(x1y1, x2y2z2, probabilities=(), threshold=0.001, conf=0.99, spatial_coherence_weight=0.975, max_iters=10000,
+               min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood_size=20.0, lo_number=50,
+               sampler_variance=0.1):
+    """py/bindings.cpp:203-277 -> find6DPose_ (py/gcransac_python.cpp:1026-1272).  Not wired: the P3P minimal solver and the
+    PnP scoring run on the GPU (gcr_solve_minimal / gcr_score with GCR_PNP), but every non-minimal fit of the reference's
+    DefaultPnPEstimator goes through PnPBundleAdjustment, whose behaviour is undefined in the reference itself (the
+    accumulator is constructed with the loss where its camera belongs, loops over all rows while indexing the sample, and
+    multiplies by weights that find6DPose_ passes as nullptr; relative_pose/bundle.cpp:589-594, jacobian_impl.h:12-18,
+    32-37, 56) and starts from OpenCV's EPnP, a dependency outside the tree -- there is no result to match."""
+    raise NotImplementedError("find6DPose: the reference's non-minimal PnP solver has no defined behaviour to match "
+                              "(DESIGN.md section 8); P3P solving and PnP scoring are available through the C ABI "
+                              "(gcr_solve_minimal / gcr_score with GCR_PNP)")
