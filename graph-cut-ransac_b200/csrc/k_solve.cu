@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(F7_THREADS, F7_MIN_BLOCKS) k_solve_f7(const do
 #ifndef E5_MIN_BLOCKS
 #define E5_MIN_BLOCKS 5 // 3.7 KB of shared memory per sample: five CTAs (20 warps) per SM if the registers allow (<= 102)
 #endif
-#define E5_THREADS 128
+#ifndef E5_THREADS
+#define E5_THREADS 128 // overridable at build time (GCR_NVCC_EXTRA=-DE5_THREADS=64 -DE5_MIN_BLOCKS=10) for launch-shape experiments
+#endif
 #define E5_SAMPLES_PER_CTA (3 * E5_THREADS / 32)
 #define E5_SMEM (E5_SAMPLES_PER_CTA * gcr_e5g::SAMPLE_DOUBLES * sizeof(double))
 
