@@ -141,6 +141,29 @@ def test_magsac_scoring_pipeline_matches_reference_run(pyg, ref, oracle):
     assert abs(st["score"] - want["score"]) <= 1e-9 * want["score"]
 
 
+def test_ar_sampler_when_model_generation_gives_up(pyg, ref):
+    """Two thirds of the correspondences are one and the same point and carry the highest probabilities: the AR-Sampler
+    keeps proposing degenerate samples, GCRANSAC::run gives up after 100 of them in a row (GCRANSAC.h:297-339) and its
+    end-of-iteration update() then runs on the last sample a second time (:474) -- which changes every later sample.  The
+    driver rebuilds its drawn-ahead sequence at that point; several such events, then a model is found."""
+    n = 600
+    cs = np.array([(1024 + np.finfo(np.float64).eps) / 4] * 4)
+    prob = 1.0 - np.arange(n) / n
+    for degenerate, variance in ((400, 0.1), (500, 0.9765)):
+        pts, Hm, inl = synth.homography_pair(n, 0.2, seed=5)
+        pts[:degenerate] = pts[0]
+        H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, prob, threshold=3.0, max_iters=5000, use_sprt=False,
+                                     use_space_partitioning=False, sampler=4, sampler_variance=variance, seed=3)
+        st = pyg.last_statistics
+        want = ref.run(O.H, pts, cs, 4, 3.0, conf=0.99, spatial_weight=0.975, max_iters=5000, min_iters=50, lo_number=50, seed=3,
+                       sampler=4, probabilities=prob, sampler_variance=variance)
+        give_ups = want["stats"]["iterations"] - want["stats"]["main_samples"]     # an exhausted iteration counts 101 for 100 samples
+        assert give_ups >= 5, want["stats"]
+        assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+        assert st["main_samples"] == want["stats"]["main_samples"]
+        assert np.array_equal(mask, want["mask"]) and _up_to_scale(want["model"], H) < 1e-5 and mask.sum() > 500
+
+
 def test_findhomography_synthetic_and_errors(pyg, ref):
     pts, Hm, inl = synth.homography_pair(3000, 0.5, seed=33)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, use_sprt=False, use_space_partitioning=False, seed=5)
