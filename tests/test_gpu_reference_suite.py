@@ -159,3 +159,27 @@ def test_reference_calls_with_their_own_samplers(pyg, ref, oracle):
     assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
     assert st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
+
+
+def test_essential_with_progressive_napsac_and_importance_sampler(pyg, ref, oracle):
+    """findEssentialMatrix with the two samplers the reference's E test does not use: P-NAPSAC builds its grid layers on the
+    PIXEL coordinates while the run is on the K-normalised ones (py/gcransac_python.cpp:2650); the importance sampler
+    draws from rank-based probabilities.  Both against the verbatim reference driver."""
+    g = np.load(os.path.join(GOLDEN, "fountain_matches.npz"))
+    pts, K1, K2 = np.ascontiguousarray(g["pts"]), g["K1"], g["K2"]
+    h1, w1, h2, w2 = (int(v) for v in g["size"])
+    prob = 1.0 - np.arange(len(pts)) / len(pts)
+    npts = oracle.normalize_correspondences(pts.astype(np.float64), K1, K2)
+    thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
+    cells = 8
+    cs = np.array([w1 / cells, h1 / cells, w2 / cells, h2 / cells])
+    for sampler in (2, 3):
+        E, mask = pyg.findEssentialMatrix(pts, K1, K2, h1, w1, h2, w2, probabilities=prob, threshold=0.75, conf=0.99, min_iters=50,
+                                          max_iters=5000, sampler=sampler, neighborhood=0, neighborhood_size=float(cells), seed=2)
+        st = pyg.last_statistics
+        want = ref.run(O.E, npts, cs, cells, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50, seed=2,
+                       grid_pts=pts.astype(np.float64), sampler=sampler, probabilities=prob, image_sizes=(w1, h1, w2, h2))
+        assert st["iteration_number"] == want["stats"]["iterations"], (sampler, st, want["stats"])
+        assert st["lo_samples"] == want["stats"]["lo_samples"]
+        assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5, sampler
+        assert mask.sum() > 450
