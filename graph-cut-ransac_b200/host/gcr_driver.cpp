@@ -1301,7 +1301,13 @@ namespace
 					const int idx2 = (offset + 1) % 2;
 					Score cur;
 					buf[idx2].lazy = false;
-					if (!exact(models.data(), cur, &buf[idx2].idx))
+					// the driver code scores the polished model with an MSACScoringFunction of its own (:1866-1875), whatever
+					// scoring function the run was instantiated with
+					const int run_scoring = scoring;
+					scoring = GCR_MSAC;
+					const bool scored = exact(models.data(), cur, &buf[idx2].idx);
+					scoring = run_scoring;
+					if (!scored)
 						return -1;
 					if (st.score < cur.value) // :1877
 					{

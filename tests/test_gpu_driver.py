@@ -131,6 +131,18 @@ def test_magsac_scoring_pipeline_matches_reference_run(pyg, ref, oracle):
         assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
         assert abs(st["score"] - want["score"]) <= 1e-6 * want["score"]
         assert (mask & inl).sum() > 0.8 * inl.sum()
+    # F, plain (8-point refits) and the default estimator (BA refits, DEGENSAC with its MSAC-scored inner run, post-run BA)
+    pts, Fm, Em, Kc, inl = synth.epipolar_pair(2000, 0.5, seed=36)
+    cs4 = np.array([1024 / 4.0] * 4)
+    for full in (False, True):
+        F, mask = pyg.findFundamentalMatrix(pts, 1024, 1024, 1024, 1024, [], threshold=0.75, spatial_coherence_weight=0.0,
+                                            neighborhood=0, neighborhood_size=4.0, seed=4, sampler=0, use_degensac=full,
+                                            bundle_adjustment=full, scoring=_cabi.MAGSAC)
+        st = pyg.last_statistics
+        want = ref.run(O.F, pts, cs4, 4, 0.75, conf=0.99, spatial_weight=0.0, max_iters=10000, min_iters=50, lo_number=50, seed=4,
+                       use_degensac=full, f_ba=3 if full else 0, scoring_kind=2)
+        assert st["iteration_number"] == want["stats"]["iterations"], (full, st, want["stats"])
+        assert (mask != want["mask"]).sum() <= (2 if full else 0) and _up_to_scale(want["model"], F) < 1e-5, full
     pts, Hm, inl = synth.homography_pair(2000, 0.4, seed=8)
     H, mask = pyg.findHomography(pts, 1024, 1024, 1024, 1024, [], threshold=2.0, seed=6, scoring=_cabi.MAGSAC)
     st = pyg.last_statistics
