@@ -3,8 +3,9 @@ its own images, through the same Python calls: the bundled 004520/004523 pair fo
 intrinsics for E -- SIFT tentatives extracted exactly as those tests do (committed fixtures: oracle/gen_cfg1_fixture.py,
 oracle/gen_fountain_fixture.py).  Each test keeps the reference's inlier-count floor (> 250, > 380, > 450) and adds what
 the reference cannot check: equality with its verbatim GCRANSAC<> driver on the same sample streams.  Differences from
-the reference's calls: sampler=1 (PROSAC) where they pass 2 / 4 (P-NAPSAC / AR: host-side plug-ins, not on this path),
-and, for neighborhood=1, the exact radius graph where the reference asks FLANN for an approximate one."""
+the reference's calls: the first tests pass sampler=1 (PROSAC); test_reference_calls_with_their_own_samplers makes the
+calls with the reference's own sampler ids (2 P-NAPSAC for H, 4 AR-Sampler for F and E); for neighborhood=1 the exact
+radius graph stands where the reference asks FLANN for an approximate one."""
 import os
 
 import numpy as np
