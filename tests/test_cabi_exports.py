@@ -38,3 +38,27 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(_cabi.GcrError):
         _cabi.Context(0)
+
+
+def test_driver_library_exports_every_declared_symbol():
+    """libgcr_driver.so (host/gcr_driver.h: the batched driver behind the Python and C++ entry points) exports what its
+    header declares, and its settings structure is the one pygcransac mirrors (same size, same defaults)."""
+    import ctypes as C
+    import pygcransac
+    path = os.path.join(ROOT, "graph-cut-ransac_b200", "host", "_ref", "libgcr_driver.so")
+    if not os.path.exists(path):
+        pytest.skip("host driver not built (needs the reference tree for its BK max-flow)")
+    from pygcransac import _cabi
+    _cabi.load_library()
+    lib = C.CDLL(path)
+    header = open(os.path.join(ROOT, "graph-cut-ransac_b200", "host", "gcr_driver.h")).read()
+    declared = set(re.findall(r"\b(gcr_[a-z0-9_]+)\s*\(", header)) - {"gcr_ctx"}
+    assert {"gcr_find_model", "gcr_find_essential", "gcr_run_settings_default"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    s = pygcransac.RunSettings()
+    lib.gcr_run_settings_default.argtypes = [C.POINTER(pygcransac.RunSettings)]
+    C.memset(C.byref(s), 0xFF, C.sizeof(s))               # every byte must be written by the default initialiser
+    lib.gcr_run_settings_default(C.byref(s))
+    assert (s.threshold, s.confidence, s.batch, s.sampler, s.scoring, s.sampler_variance) == (2.0, 0.95, 1024, 0, 0, 0.1)
+    assert not s.point_probabilities and list(s.image_sizes) == [0.0] * 4 and s.neighborhood_radius == 20.0
