@@ -486,6 +486,10 @@ def main():
         torch.cuda.synchronize()
 
     hyps_sharded = wl.get("shard") == "hyps"
+    if hyps_sharded:
+        from pygcransac import sharded
+        winners = torch.zeros(n_pairs, 16, dtype=torch.int64, device="cuda")      # gcr_winner records (128 B each)
+        sharded.init_comm(ctx, rank, world)
 
     # configs[3] = "fixed K hypotheses per pair + argmax + one final least-squares refit" (SURVEY.md 8d): the refit tail
     # for every pair of the batch, device-resident, two launches (inliers of the winners, one fit per pair)
@@ -508,9 +512,8 @@ def main():
             tail(ctx, 0, n_pairs)
             return ev
         if hyps_sharded:
-            from pygcransac import sharded
-            return sharded.sharded_round(ctx, prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
-                                         wl["thr"], flags, keys, best, 3 if wl["problem"] == "f" else 1, rank, world)
+            return ctx.round_sharded_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
+                                            wl["thr"], flags, 65536, winners.data_ptr())
         return ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
                                 flags, 0, keys.data_ptr(), best.data_ptr())
 

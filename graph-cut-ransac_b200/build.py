@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stdout.write(out)
     if failed:
         raise RuntimeError("CUDA build failed")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -47,8 +47,8 @@ extern "C" gcr_status gcr_ctx_create(int device, gcr_ctx **out)
 	int khz = 0;
 	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
 	ctx->sm_clock_khz = khz;
-	if (cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
+	if (cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)
 	{
 		delete ctx;
 		return GCR_ERR_CUDA;
@@ -63,6 +63,8 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 		return GCR_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	gcr_comm_destroy(ctx);
+	cudaFree(ctx->d_gather);
 	cudaFree(ctx->d_pts64_owned);
 	cudaFree(ctx->d_pts32);
 	cudaFree(ctx->d_score_ws);
@@ -381,14 +383,31 @@ extern "C" gcr_status gcr_profile_read(gcr_ctx *ctx, double *score_ms, uint64_t 
 	return GCR_OK;
 }
 
-extern "C" gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[4], int reset)
+extern "C" gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[8], int reset)
 {
 	if (!ctx || !out)
 		return GCR_ERR_ARG;
-	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_counters, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	gcr_status st = gcr_memcpy_d2h_async(ctx, out, ctx->d_counters, 8 * sizeof(uint64_t));
+	if (st)
+		return st;
 	if (reset)
-		GCR_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint64_t), ctx->stream));
-	GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(uint64_t), ctx->stream));
+	return gcr_sync(ctx);
+}
+
+extern "C" gcr_status gcr_cache_stats(gcr_ctx *ctx, uint64_t *blocks, uint64_t *blocks_in_use, uint64_t *bytes)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	uint64_t used = 0, total = 0;
+	for (const auto &b : ctx->blocks)
+	{
+		used += b.used ? 1 : 0;
+		total += b.cap;
+	}
+	if (blocks) *blocks = ctx->blocks.size();
+	if (blocks_in_use) *blocks_in_use = used;
+	if (bytes) *bytes = total;
 	return GCR_OK;
 }
 

@@ -55,7 +55,8 @@ struct gcr_ctx
 	uint32_t *d_round_best_counts = nullptr;
 
 	// counters (device, u64): [0] valid models produced by K2, [1] FP64 re-check entries dropped (work list full),
-	// [2] FP64 re-check entries queued -- since the last reset
+	// [2] FP64 re-check entries queued, [3] K4 FP64 re-scores, [4] max relative FP32 score error seen by K4 (float bits)
+	// -- since the last reset
 	unsigned long long *d_counters = nullptr;
 	// optional per-launch timing of the scoring kernel (bench.py's roofline leg)
 	bool profile = false;
@@ -94,6 +95,12 @@ struct gcr_ctx
 	size_t d2h_off = 0;
 	static const size_t STAGE_BYTES = 4 << 20;
 
+	// hypothesis-sharded mode (gcr_comm.cu): NCCL communicator of the ranks that share one problem
+	void *nccl_comm = nullptr;
+	int comm_rank = 0, comm_world = 1;
+	gcr_winner *d_gather = nullptr; // [world][n_pairs] all-gather buffer (this rank's record accumulates in place)
+	size_t gather_capacity = 0;     // in records
+
 	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu
 	int score_variant = -1;    // -1 auto; else forces a kernel variant (bench / tests)
 };
@@ -130,11 +137,10 @@ gcr_status gcr_profile_begin(gcr_ctx *ctx);
 gcr_status gcr_profile_end(gcr_ctx *ctx, uint64_t evals);
 gcr_status gcr_ensure_prosac_growth(gcr_ctx *ctx, int m);
 gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx);
-#define GCR_SEL_BUCKETS 64 /* index classes of K4's first stage */
-// gcr_score with K4's first stage fused into the finalize kernel (d_buckets may be null)
+// gcr_score with K4's first stage fused into the finalize kernel: d_pairbest [n_pairs] (zeroed by the caller, may be
+// null) receives each pair's best FP32 key (orderedBits(score) << 32 | ~slot)
 gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid, int k,
-                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_buckets,
-                           uint32_t index_base);
+                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_pairbest);
 // K2 with the sample drawn inside the solver kernel (gcr_round's fused K1 + K2)
 gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, uint64_t first_index, int count, uint64_t seed,
                                        double *d_models, uint8_t *d_valid);

@@ -257,16 +257,19 @@ extern "C" gcr_status gcr_score_exact_host(gcr_ctx *ctx, int problem, int scorin
 	if (!st)
 		st = gcr_score_exact(ctx, problem, scoring, pair, (const double *)d_m, k, threshold, (double *)d_s,
 		                     (uint32_t *)d_c, (uint32_t *)d_i, (double *)d_r);
-	if (!st) st = gcr_memcpy_d2h(ctx, h_scores, d_s, k * sizeof(double));
-	if (!st) st = gcr_memcpy_d2h(ctx, h_counts, d_c, k * sizeof(uint32_t));
-	if (!st && h_inlier_idx) st = gcr_memcpy_d2h(ctx, h_inlier_idx, d_i, (size_t)k * n * sizeof(uint32_t));
-	if (!st && h_residuals) st = gcr_memcpy_d2h(ctx, h_residuals, d_r, (size_t)k * n * sizeof(double));
-	cudaStreamSynchronize(ctx->stream);
-	cudaFree(d_m);
-	cudaFree(d_s);
-	cudaFree(d_c);
-	cudaFree(d_i);
-	cudaFree(d_r);
+	// the four read-backs are queued and delivered by ONE synchronise; the temporaries go back to the context's block
+	// cache (gcr_free, on every path: a raw cudaFree would leave their cache entries dangling)
+	if (!st) st = gcr_memcpy_d2h_async(ctx, h_scores, d_s, k * sizeof(double));
+	if (!st) st = gcr_memcpy_d2h_async(ctx, h_counts, d_c, k * sizeof(uint32_t));
+	if (!st && h_inlier_idx) st = gcr_memcpy_d2h_async(ctx, h_inlier_idx, d_i, (size_t)k * n * sizeof(uint32_t));
+	if (!st && h_residuals) st = gcr_memcpy_d2h_async(ctx, h_residuals, d_r, (size_t)k * n * sizeof(double));
+	const gcr_status sync_st = gcr_sync(ctx); // also orders the reuse of the blocks after the kernels that wrote them
+	if (!st) st = sync_st;
+	gcr_free(ctx, d_m);
+	gcr_free(ctx, d_s);
+	gcr_free(ctx, d_c);
+	gcr_free(ctx, d_i);
+	gcr_free(ctx, d_r);
 	return st;
 }
 

@@ -211,8 +211,7 @@ struct ScoreArgs
 	// outputs
 	float *scores;
 	uint32_t *inliers;
-	unsigned long long *buckets; // optional [n_pairs][GCR_SEL_BUCKETS]: finalize also keeps the best key per index class
-	uint32_t index_base;
+	unsigned long long *pairbest; // optional [n_pairs]: finalize also keeps the pair's best FP32 key (score << 32 | ~slot)
 	int n, n_pad, k, n_pairs;
 	int hyps_per_item, grid;
 	double thr;
@@ -790,18 +789,15 @@ __global__ void __launch_bounds__(256) k_score_fixup(const ScoreArgs a)
 template <int SCORING>
 __global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 {
-	__shared__ unsigned long long sb[GCR_SEL_BUCKETS];
+	__shared__ unsigned long long s_warp_best[8];
 	const int pair = blockIdx.y;
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (a.buckets && threadIdx.x < GCR_SEL_BUCKETS)
-		sb[threadIdx.x] = 0ull;
-	if (a.buckets)
-		__syncthreads();
 	if (slot == 0 && pair == 0 && a.plan->amb_count)
 	{
 		atomicAdd(&a.counters[1], (unsigned long long)a.plan->amb_dropped);
 		atomicAdd(&a.counters[2], (unsigned long long)a.plan->amb_count);
 	}
+	unsigned long long key = 0ull;
 	if (slot < a.k)
 	{
 		const size_t g = (size_t)pair * a.k + slot;
@@ -817,16 +813,28 @@ __global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 		a.scores[g] = score;
 		if (a.inliers)
 			a.inliers[g] = present ? c : 0u;
-		if (a.buckets && score > 0.f) // K4's first stage, fused: best key per index class (see k_select.cu)
-			atomicMax(&sb[slot % GCR_SEL_BUCKETS],
-			          ((unsigned long long)gcr_ordered_u32(score) << 32) | (unsigned long long)(0xFFFFFFFFu - ((uint32_t)slot + a.index_base)));
+		if (score > 0.f)
+			key = ((unsigned long long)gcr_ordered_u32(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot);
 	}
-	if (a.buckets)
+	if (a.pairbest) // K4's first stage, fused: the pair's best FP32 key (the anchor of k_select_exact's candidate margin)
 	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+			if (other > key) key = other;
+		}
+		if ((threadIdx.x & 31) == 0)
+			s_warp_best[threadIdx.x >> 5] = key;
 		__syncthreads();
-		// most CTAs cannot raise the class maximum: look before the (contended) atomic
-		if (threadIdx.x < GCR_SEL_BUCKETS && sb[threadIdx.x] > __ldcg(&a.buckets[(size_t)pair * GCR_SEL_BUCKETS + threadIdx.x]))
-			atomicMax(&a.buckets[(size_t)pair * GCR_SEL_BUCKETS + threadIdx.x], sb[threadIdx.x]);
+		if (threadIdx.x == 0)
+		{
+			for (int w = 1; w < 8; ++w)
+				if (s_warp_best[w] > key) key = s_warp_best[w];
+			// most CTAs cannot raise the maximum: look before the (contended) atomic
+			if (key > __ldcg(&a.pairbest[pair]))
+				atomicMax(&a.pairbest[pair], key);
+		}
 	}
 }
 
@@ -957,12 +965,11 @@ static gcr_status launch_problem(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 extern "C" gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid,
                                 int k, double threshold, int flags, float *d_scores, uint32_t *d_inliers)
 {
-	return gcr_score_fused(ctx, problem, scoring, d_models, d_valid, k, threshold, flags, d_scores, d_inliers, nullptr, 0);
+	return gcr_score_fused(ctx, problem, scoring, d_models, d_valid, k, threshold, flags, d_scores, d_inliers, nullptr);
 }
 
 gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid, int k,
-                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_buckets,
-                           uint32_t index_base)
+                           double threshold, int flags, float *d_scores, uint32_t *d_inliers, unsigned long long *d_pairbest)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
@@ -997,8 +1004,7 @@ gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double 
 	a.counters = ctx->d_counters;
 	a.scores = d_scores;
 	a.inliers = d_inliers;
-	a.buckets = d_buckets;
-	a.index_base = index_base;
+	a.pairbest = d_pairbest;
 	a.n = ctx->n;
 	a.n_pad = ctx->n_pad;
 	a.k = k;
@@ -1036,12 +1042,14 @@ extern "C" gcr_status gcr_score_host(gcr_ctx *ctx, int problem, int scoring, con
 	if (!st)
 		st = gcr_score(ctx, problem, scoring, (const double *)d_m, h_valid ? (const uint8_t *)d_v : nullptr, k, threshold,
 		               flags, (float *)d_s, (uint32_t *)d_i);
-	if (!st) st = gcr_memcpy_d2h(ctx, h_scores, d_s, total * sizeof(float));
-	if (!st && h_inliers) st = gcr_memcpy_d2h(ctx, h_inliers, d_i, total * sizeof(uint32_t));
-	cudaStreamSynchronize(ctx->stream);
-	cudaFree(d_m);
-	cudaFree(d_v);
-	cudaFree(d_s);
-	cudaFree(d_i);
+	if (!st) st = gcr_memcpy_d2h_async(ctx, h_scores, d_s, total * sizeof(float));
+	if (!st && h_inliers) st = gcr_memcpy_d2h_async(ctx, h_inliers, d_i, total * sizeof(uint32_t));
+	const gcr_status sync_st = gcr_sync(ctx); // one synchronise delivers both read-backs
+	if (!st) st = sync_st;
+	// back to the context's block cache on every path (never a raw cudaFree: the cache entry would dangle)
+	gcr_free(ctx, d_m);
+	gcr_free(ctx, d_v);
+	gcr_free(ctx, d_s);
+	gcr_free(ctx, d_i);
 	return st;
 }

@@ -98,29 +98,50 @@ extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 
 // ------------------------------------------------------------------------------- exact winner selection ---
 // The FP32 scores of K3 rank the hypotheses, but FP32 cannot separate two models whose scores differ by less than its
-// own error (~2e-5 relative for Sampson: the model coefficients themselves are rounded to FP32).  gcr_round therefore
-// keeps, per pair, the best FP32 key of each of SEL_BUCKETS index classes (slot % SEL_BUCKETS; max is order-independent,
-// so this is deterministic; done inside K3's finalize kernel, k_score.cu), re-scores in FP64 -- reference operation order per point -- every bucket winner within
-// SEL_MARGIN of the best, and picks the winner by (FP64 score, lowest index): the strict '<' first-wins rule of
-// GCRANSAC.h:440 evaluated in the reference's precision.
-#define SEL_BUCKETS GCR_SEL_BUCKETS
-#define SEL_MARGIN 2e-4f
+// own error (~2e-5 relative for Sampson: the model coefficients themselves are rounded to FP32).  K3's finalize kernel
+// leaves each pair's best FP32 key; k_select_exact then re-scores in FP64 -- reference operation order per point --
+// EVERY slot whose FP32 score lies within a relative margin of that best (no bucketing: the candidate set is complete),
+// and picks the winner by (FP64 score, lowest index): the strict '<' first-wins rule of GCRANSAC.h:440 /
+// scoring_function.h:63-66 evaluated in the reference's precision.  With FP32 score errors of at most e, the true FP64
+// winner W satisfies s32(W) >= s32(top) (1 - 2e), so the margin must be >= 2e: MSAC 2e-4 (measured e <= 2e-5), MAGSAC++
+// 1e-3 (e <= 2e-4).  Every re-score also records |s32 - s64| / s64 (counters[4], the largest seen), so the tests can
+// assert the premise instead of trusting it.
+//
+// Grid: (cx, n_pairs).  CTA (b, p) scans slots [b k / cx, (b + 1) k / cx) of pair p, keeps its own best and leaves it in
+// partials[p][b]; the last CTA of a pair to finish reduces the cx partials by the same (score, index) rule -- the result
+// does not depend on which CTA that is -- merges with the running winner record when asked to (chunks of one problem:
+// the running best never leaves the device, and stays FP64), and writes every output.
+#define SEL_MARGIN_MSAC 2e-4f
+#define SEL_MARGIN_MAGSAC 1e-3f
 #define SEL_THREADS 256
-#define SEL_MAX_THREADS 1024 /* few pairs: one big CTA per pair re-scores a candidate over all points in ~1 us */
+#define SEL_MAX_THREADS 1024 /* few pairs: big CTAs re-score a candidate over all points in ~1 us */
+
+struct SelPartial
+{
+	double score;
+	uint32_t slot;
+	uint32_t count;
+};
 
 struct SelectArgs
 {
 	const double *pts; // [n_pairs][n][cols]
 	const double *models; // [n_pairs][k][ML]
 	const double *lut64;
-	const unsigned long long *buckets; // [n_pairs][SEL_BUCKETS]
-	unsigned long long *keys;          // [n_pairs]
-	double *best_models;               // [n_pairs][ML] or null
-	double *best_scores;               // [n_pairs] or null (FP64 score of the winner)
-	uint32_t *best_counts;             // [n_pairs] or null (exact inlier count of the winner)
-	int n, k;
-	uint32_t index_base;
+	const float *scores32;               // [n_pairs][k] K3's FP32 scores
+	const unsigned long long *pairbest;  // [n_pairs] best FP32 key of each pair (finalize)
+	SelPartial *partials;                // [n_pairs][gridDim.x]
+	uint32_t *done;                      // [n_pairs] CTAs finished (zeroed with pairbest)
+	unsigned long long *keys;            // [n_pairs] legacy packed key of THIS round's winner, or null
+	double *best_models;                 // [n_pairs][ML] or null
+	double *best_scores;                 // [n_pairs] FP64 score of this round's winner
+	uint32_t *best_counts;               // [n_pairs] its exact inlier count
+	gcr_winner *winners;                 // [n_pairs] winner records, or null
+	unsigned long long *counters;
+	int n, k, accumulate;
+	unsigned long long index_base;
 	double thr;
+	float margin;
 };
 
 template <int PROBLEM, int SCORING>
@@ -128,38 +149,24 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) k_select_exact(const SelectAr
 {
 	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
 	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
-	__shared__ unsigned long long s_keys[SEL_BUCKETS];
-	__shared__ int s_cand[SEL_BUCKETS];
-	__shared__ int s_ncand;
+	__shared__ uint32_t s_cand[SEL_MAX_THREADS];
+	__shared__ uint32_t s_ncand;
 	__shared__ double s_model[ML];
 	__shared__ double warp_sum[SEL_MAX_THREADS / 32];
-	__shared__ uint32_t warp_cnt[SEL_MAX_THREADS / 32];
+	__shared__ uint32_t warp_cnt[SEL_MAX_THREADS / 32], warp_slot[SEL_MAX_THREADS / 32];
 	__shared__ double s_best_score;
-	__shared__ uint32_t s_best_slot, s_best_count;
-	const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid < SEL_BUCKETS)
-		s_keys[tid] = a.buckets[(size_t)pair * SEL_BUCKETS + tid];
-	__syncthreads();
+	__shared__ uint32_t s_best_slot, s_best_count, s_last, s_take, s_rescored;
+	__shared__ float s_max_err;
+	const int pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x >> 5;
+	const unsigned long long top_key = a.pairbest[pair];
 	if (tid == 0)
 	{
-		unsigned long long best = 0ull;
-		for (int b = 0; b < SEL_BUCKETS; ++b)
-			if (s_keys[b] > best) best = s_keys[b];
-		int nc = 0;
-		if (best)
-		{
-			const float top = gcr_from_ordered_u32((uint32_t)(best >> 32));
-			const float floor_score = top - SEL_MARGIN * top;
-			for (int b = 0; b < SEL_BUCKETS; ++b)
-				if (s_keys[b] && gcr_from_ordered_u32((uint32_t)(s_keys[b] >> 32)) >= floor_score)
-					s_cand[nc++] = b;
-		}
-		s_ncand = nc;
 		s_best_score = -1.0;
 		s_best_slot = 0xFFFFFFFFu;
 		s_best_count = 0;
+		s_rescored = 0;
+		s_max_err = 0.f;
 	}
-	__syncthreads();
 	const double *P = a.pts + (size_t)pair * a.n * COLS;
 	// thresholds / MAGSAC constants exactly as the reference forms them (GCRANSAC.h:253-254, scoring_function.h:257-296)
 	const double truncated_threshold = 3.0 / 2.0 * a.thr;
@@ -169,117 +176,214 @@ __global__ void __launch_bounds__(SEL_MAX_THREADS) k_select_exact(const SelectAr
 	const double one_over_sigma = 0.25 * 2.8284271247461903 / a.thr;
 	const double weight_zero = one_over_sigma * gamma_difference;
 	const double squared_sigma_max_2 = a.thr * a.thr * 2.0;
-	for (int c = 0; c < s_ncand; ++c)
+	if (top_key)
 	{
-		const uint32_t gidx = 0xFFFFFFFFu - (uint32_t)(s_keys[s_cand[c]] & 0xFFFFFFFFull);
-		const uint32_t slot = gidx - a.index_base;
-		if (tid < ML)
-			s_model[tid] = a.models[((size_t)pair * a.k + slot) * ML + tid];
-		__syncthreads();
-		double M[ML];
-		for (int j = 0; j < ML; ++j) M[j] = s_model[j];
-		double sum = 0.0;
-		uint32_t cnt = 0;
-		for (int i = tid; i < a.n; i += (int)blockDim.x)
+		const float top = gcr_from_ordered_u32((uint32_t)(top_key >> 32));
+		const float floor_score = top - a.margin * top;
+		const int per = (a.k + (int)gridDim.x - 1) / (int)gridDim.x;
+		const int lo = (int)blockIdx.x * per, hi = min(a.k, lo + per);
+		const float *sc = a.scores32 + (size_t)pair * a.k;
+		for (int base = lo; base < hi; base += (int)blockDim.x)
 		{
-			double pt[COLS];
-			for (int j = 0; j < COLS; ++j) pt[j] = P[(size_t)i * COLS + j];
-			const double r2 = gcr_sqres64<PROBLEM>(pt, M);
-			if (SCORING == GCR_MSAC)
+			__syncthreads();
+			if (tid == 0)
+				s_ncand = 0;
+			__syncthreads();
+			const int slot = base + tid;
+			if (slot < hi && sc[slot] >= floor_score)
+				s_cand[atomicAdd(&s_ncand, 1u)] = (uint32_t)slot; // order is irrelevant: the rule below is symmetric
+			__syncthreads();
+			const int nc = (int)s_ncand;
+			for (int c = 0; c < nc; ++c)
 			{
-				if (r2 < T) { sum -= r2; ++cnt; }
-			}
-			else
-			{
-				const double residual = sqrt(r2);
-				if (!(residual > a.thr))
+				const uint32_t slot_c = s_cand[c];
+				if (tid < ML)
+					s_model[tid] = a.models[((size_t)pair * a.k + slot_c) * ML + tid];
+				__syncthreads();
+				double M[ML];
+				for (int j = 0; j < ML; ++j) M[j] = s_model[j];
+				double sum = 0.0;
+				uint32_t cnt = 0;
+				for (int i = tid; i < a.n; i += (int)blockDim.x)
 				{
-					double weight;
-					if (residual < 2.220446049250313e-16)
-						weight = weight_zero;
+					double pt[COLS];
+					for (int j = 0; j < COLS; ++j) pt[j] = P[(size_t)i * COLS + j];
+					const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+					if (SCORING == GCR_MSAC)
+					{
+						if (r2 < T) { sum -= r2; ++cnt; }
+					}
 					else
 					{
-						const double squared_residual = residual * residual;
-						unsigned long long x = (unsigned long long)round(1e4 * squared_residual / squared_sigma_max_2);
-						if (x > 5000) x = 5000;
-						weight = one_over_sigma * (a.lut64[x] - gamma_k);
+						const double residual = sqrt(r2);
+						if (!(residual > a.thr))
+						{
+							double weight;
+							if (residual < 2.220446049250313e-16)
+								weight = weight_zero;
+							else
+							{
+								const double squared_residual = residual * residual;
+								unsigned long long x = (unsigned long long)round(1e4 * squared_residual / squared_sigma_max_2);
+								if (x > 5000) x = 5000;
+								weight = one_over_sigma * (a.lut64[x] - gamma_k);
+							}
+							sum += weight / weight_zero;
+							++cnt;
+						}
 					}
-					sum += weight / weight_zero;
-					++cnt;
 				}
+				for (int o = 16; o > 0; o >>= 1)
+				{
+					sum += __shfl_xor_sync(0xffffffffu, sum, o);
+					cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+				}
+				if (lane == 0) { warp_sum[warp] = sum; warp_cnt[warp] = cnt; }
+				__syncthreads();
+				if (tid == 0)
+				{
+					double value = 0.0;
+					uint32_t inl = 0;
+					for (int w = 0; w < nwarps; ++w) { value += warp_sum[w]; inl += warp_cnt[w]; }
+					const double score = SCORING == GCR_MSAC ? (inl == 0 ? 0.0 : (value + inl * T) / T) : value;
+					if (score > s_best_score || (score == s_best_score && slot_c < s_best_slot))
+					{
+						s_best_score = score;
+						s_best_slot = slot_c;
+						s_best_count = inl;
+					}
+					++s_rescored;
+					if (score > 0.0)
+						s_max_err = fmaxf(s_max_err, (float)(fabs((double)sc[slot_c] - score) / score));
+				}
+				__syncthreads();
 			}
 		}
-		for (int o = 16; o > 0; o >>= 1)
-		{
-			sum += __shfl_xor_sync(0xffffffffu, sum, o);
-			cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-		}
-		if (lane == 0) { warp_sum[warp] = sum; warp_cnt[warp] = cnt; }
-		__syncthreads();
-		if (tid == 0)
-		{
-			double value = 0.0;
-			uint32_t inl = 0;
-			for (int w = 0; w < (int)blockDim.x / 32; ++w) { value += warp_sum[w]; inl += warp_cnt[w]; }
-			const double score = SCORING == GCR_MSAC ? (inl == 0 ? 0.0 : (value + inl * T) / T) : value;
-			if (score > s_best_score || (score == s_best_score && gidx < s_best_slot))
-			{
-				s_best_score = score;
-				s_best_slot = gidx;
-				s_best_count = inl;
-			}
-		}
-		__syncthreads();
 	}
-	if (s_ncand == 0)
-	{
-		if (tid == 0)
-		{
-			a.keys[pair] = 0ull;
-			if (a.best_scores) a.best_scores[pair] = 0.0;
-			if (a.best_counts) a.best_counts[pair] = 0;
-		}
-		if (a.best_models && tid < ML)
-			a.best_models[(size_t)pair * ML + tid] = 0.0;
-		return;
-	}
+	// ---- this CTA's best -> partials; the last CTA of the pair reduces them ----
+	__syncthreads();
 	if (tid == 0)
 	{
-		a.keys[pair] = ((unsigned long long)gcr_ordered_u32((float)s_best_score) << 32) | (unsigned long long)(0xFFFFFFFFu - s_best_slot);
-		if (a.best_scores) a.best_scores[pair] = s_best_score;
-		if (a.best_counts) a.best_counts[pair] = s_best_count;
+		SelPartial sp;
+		sp.score = s_best_score;
+		sp.slot = s_best_slot;
+		sp.count = s_best_count;
+		a.partials[(size_t)pair * gridDim.x + blockIdx.x] = sp;
+		if (s_rescored)
+		{
+			atomicAdd(&a.counters[3], (unsigned long long)s_rescored);
+			atomicMax(&a.counters[4], (unsigned long long)__float_as_uint(s_max_err)); // non-negative floats order like their bits
+		}
+		__threadfence();
+		s_last = atomicAdd(&a.done[pair], 1u) == gridDim.x - 1 ? 1u : 0u;
 	}
-	if (a.best_models && tid < ML)
-		a.best_models[(size_t)pair * ML + tid] = a.models[((size_t)pair * a.k + (s_best_slot - a.index_base)) * ML + tid];
+	__syncthreads();
+	if (!s_last)
+		return;
+	__threadfence();
+	double bs = -1.0;
+	uint32_t bslot = 0xFFFFFFFFu, bcnt = 0;
+	for (int b = tid; b < (int)gridDim.x; b += (int)blockDim.x)
+	{
+		const SelPartial *sp = &a.partials[(size_t)pair * gridDim.x + b];
+		const double s = __ldcg(&sp->score);
+		const uint32_t sl = __ldcg(&sp->slot), c = __ldcg(&sp->count);
+		if (s > bs || (s == bs && sl < bslot)) { bs = s; bslot = sl; bcnt = c; }
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		const double s = __shfl_xor_sync(0xffffffffu, bs, o);
+		const uint32_t sl = __shfl_xor_sync(0xffffffffu, bslot, o), c = __shfl_xor_sync(0xffffffffu, bcnt, o);
+		if (s > bs || (s == bs && sl < bslot)) { bs = s; bslot = sl; bcnt = c; }
+	}
+	if (lane == 0) { warp_sum[warp] = bs; warp_slot[warp] = bslot; warp_cnt[warp] = bcnt; }
+	__syncthreads();
+	if (tid == 0)
+	{
+		for (int w = 1; w < nwarps; ++w)
+			if (warp_sum[w] > bs || (warp_sum[w] == bs && warp_slot[w] < bslot)) { bs = warp_sum[w]; bslot = warp_slot[w]; bcnt = warp_cnt[w]; }
+		const bool have = bslot != 0xFFFFFFFFu && bs > 0.0;
+		const unsigned long long gidx = a.index_base + (unsigned long long)bslot;
+		if (a.keys)
+			a.keys[pair] = have ? (((unsigned long long)gcr_ordered_u32((float)bs) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)gidx)) : 0ull;
+		a.best_scores[pair] = have ? bs : 0.0;
+		a.best_counts[pair] = have ? bcnt : 0u;
+		uint32_t take = have ? 1u : 0u; // does this round's winner replace the record?
+		if (a.winners)
+		{
+			gcr_winner *w = &a.winners[pair];
+			if (a.accumulate && w->valid)
+			{
+				// running best over the chunks of one problem: strict '<' on the FP64 score, ties to the lower global index
+				if (!have || !(bs > w->score || (bs == w->score && gidx < w->index)))
+					take = 0u;
+			}
+			else if (!have)
+			{
+				w->score = 0.0;
+				w->index = 0ull;
+				w->count = 0u;
+				w->valid = 0u;
+				w->reserved = 0ull;
+			}
+			if (take)
+			{
+				w->score = bs;
+				w->index = gidx;
+				w->count = bcnt;
+				w->valid = 1u;
+				w->reserved = 0ull;
+			}
+		}
+		s_take = take;
+		s_best_slot = have ? bslot : 0xFFFFFFFFu;
+	}
+	__syncthreads();
+	const bool have = s_best_slot != 0xFFFFFFFFu;
+	if (tid < 12)
+	{
+		const double v = have && tid < ML ? a.models[((size_t)pair * a.k + s_best_slot) * ML + tid] : 0.0;
+		if (a.best_models && tid < ML)
+			a.best_models[(size_t)pair * ML + tid] = v;
+		if (a.winners && (s_take || !(a.accumulate && a.winners[pair].valid)))
+			a.winners[pair].model[tid] = v;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ gcr_round ---
-extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
-                                uint64_t seed, double threshold, int flags, uint32_t index_base, uint64_t *d_keys,
-                                double *d_best_models, uint64_t *evals_out)
+// index_base: global slot index of (sample first_index, model 0) -- what the keys / winner records report.
+static gcr_status round_impl(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
+                             uint64_t seed, double threshold, int flags, uint64_t index_base, uint64_t *d_keys,
+                             double *d_best_models, gcr_winner *d_winners, int accumulate, uint64_t *evals_out)
 {
-	if (!ctx)
-		return GCR_ERR_ARG;
 	if (!ctx->d_pts64 || ctx->n == 0)
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_round: no points uploaded");
-	if (count <= 0 || !d_keys)
+	if (count <= 0 || (!d_keys && !d_winners))
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: bad arguments");
 	const int m = gcr_sample_size(problem), mm = gcr_max_models(problem), ml = gcr_model_len(problem);
 	if (m == 0)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: unknown problem %d", problem);
 	const size_t P = (size_t)ctx->n_pairs, K = (size_t)count * mm;
-	// carve the round buffer: samples | models | valid | scores
+	if (K >= (1ull << 31))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: count * max_models must stay below 2^31 model slots per call (walk the samples in chunks)");
+	// grid of the selection kernel: many CTAs per pair when there are few pairs
+	const int sel_threads = ctx->n_pairs < 2 * ctx->sm_count ? SEL_MAX_THREADS : SEL_THREADS;
+	int cx = (int)((K + sel_threads - 1) / sel_threads);
+	const int cx_cap = ctx->n_pairs >= 2 * ctx->sm_count ? 1 : (2 * ctx->sm_count + ctx->n_pairs - 1) / ctx->n_pairs;
+	if (cx > cx_cap) cx = cx_cap;
+	if (cx < 1) cx = 1;
+	// carve the round buffer
 	size_t off = 0;
 	auto take = [&](size_t bytes) {
 		const size_t o = off;
 		off += (bytes + 255) & ~(size_t)255;
 		return o;
 	};
-	const size_t o_samples = take(P * count * m * sizeof(uint32_t));
 	const size_t o_models = take(P * K * ml * sizeof(double));
 	const size_t o_valid = take(P * K);
 	const size_t o_scores = take(P * K * sizeof(float));
-	const size_t o_buckets = take(P * SEL_BUCKETS * sizeof(unsigned long long));
+	const size_t o_pairbest = take(P * sizeof(unsigned long long) + P * sizeof(uint32_t)); // pairbest | done: one memset
+	const size_t o_partials = take(P * cx * sizeof(SelPartial));
 	const size_t o_best_scores = take(P * sizeof(double));
 	const size_t o_best_counts = take(P * sizeof(uint32_t));
 	if (off > ctx->round_capacity)
@@ -292,20 +396,19 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 		ctx->round_capacity = off;
 	}
 	char *base = (char *)ctx->d_round;
-	uint32_t *d_samples = (uint32_t *)(base + o_samples);
 	double *d_models = (double *)(base + o_models);
 	uint8_t *d_valid = (uint8_t *)(base + o_valid);
 	float *d_scores = (float *)(base + o_scores);
 
-	(void)d_samples; // K1 is fused into K2: the solver kernel draws its sample in registers
+	// K1 is fused into K2: the solver kernel draws its sample in registers
 	gcr_status st = gcr_solve_minimal_generated(ctx, problem, sampler, first_index, count, seed, d_models, d_valid);
 	if (st) return st;
-	// K3 (+ K4's first stage inside its finalize kernel: best FP32 key per index class)
-	unsigned long long *d_buckets = (unsigned long long *)(base + o_buckets);
-	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_buckets, 0, P * SEL_BUCKETS * sizeof(unsigned long long), ctx->stream));
-	st = gcr_score_fused(ctx, problem, scoring, d_models, d_valid, (int)K, threshold, flags, d_scores, nullptr, d_buckets, index_base);
+	// K3 (+ K4's first stage inside its finalize kernel: the pair's best FP32 key)
+	unsigned long long *d_pairbest = (unsigned long long *)(base + o_pairbest);
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_pairbest, 0, P * sizeof(unsigned long long) + P * sizeof(uint32_t), ctx->stream));
+	st = gcr_score_fused(ctx, problem, scoring, d_models, d_valid, (int)K, threshold, flags, d_scores, nullptr, d_pairbest);
 	if (st) return st;
-	// K4: FP64 re-score of the near-best candidates -> winner (see k_select_exact)
+	// K4: FP64 re-score of every near-best candidate -> winner (see k_select_exact)
 	if (scoring == GCR_MAGSAC)
 	{
 		st = gcr_ensure_magsac_lut64(ctx);
@@ -315,23 +418,30 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	sa.pts = ctx->d_pts64;
 	sa.models = d_models;
 	sa.lut64 = ctx->d_magsac_lut64;
-	sa.buckets = d_buckets;
+	sa.scores32 = d_scores;
+	sa.pairbest = d_pairbest;
+	sa.partials = (SelPartial *)(base + o_partials);
+	sa.done = (uint32_t *)(base + o_pairbest + P * sizeof(unsigned long long));
 	sa.keys = (unsigned long long *)d_keys;
 	sa.best_models = d_best_models;
 	sa.best_scores = (double *)(base + o_best_scores);
 	sa.best_counts = (uint32_t *)(base + o_best_counts);
+	sa.winners = d_winners;
+	sa.counters = ctx->d_counters;
 	sa.n = ctx->n;
 	sa.k = (int)K;
+	sa.accumulate = accumulate;
 	sa.index_base = index_base;
 	sa.thr = threshold;
-	const int sel_threads = ctx->n_pairs < 2 * ctx->sm_count ? SEL_MAX_THREADS : SEL_THREADS;
+	sa.margin = scoring == GCR_MSAC ? SEL_MARGIN_MSAC : SEL_MARGIN_MAGSAC;
+	const dim3 grid(cx, ctx->n_pairs);
 #define GCR_SEL(PR)                                                                                          \
 	do                                                                                                       \
 	{                                                                                                        \
 		if (scoring == GCR_MSAC)                                                                             \
-			k_select_exact<PR, GCR_MSAC><<<ctx->n_pairs, sel_threads, 0, ctx->stream>>>(sa);                  \
+			k_select_exact<PR, GCR_MSAC><<<grid, sel_threads, 0, ctx->stream>>>(sa);                          \
 		else                                                                                                 \
-			k_select_exact<PR, GCR_MAGSAC><<<ctx->n_pairs, sel_threads, 0, ctx->stream>>>(sa);                \
+			k_select_exact<PR, GCR_MAGSAC><<<grid, sel_threads, 0, ctx->stream>>>(sa);                        \
 	} while (0)
 	if (problem == GCR_H) GCR_SEL(GCR_H);
 	else if (problem == GCR_PNP) GCR_SEL(GCR_PNP);
@@ -345,6 +455,32 @@ extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int samp
 	return GCR_OK;
 }
 
+extern "C" gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
+                                uint64_t seed, double threshold, int flags, uint32_t index_base, uint64_t *d_keys,
+                                double *d_best_models, uint64_t *evals_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_keys)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round: d_keys is required");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	return round_impl(ctx, problem, scoring, sampler, first_index, count, seed, threshold, flags, (uint64_t)index_base, d_keys,
+	                  d_best_models, nullptr, 0, evals_out);
+}
+
+extern "C" gcr_status gcr_round_winners(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
+                                        uint64_t seed, double threshold, int flags, uint64_t index_base, int accumulate,
+                                        gcr_winner *d_winners, uint64_t *evals_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_winners)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_round_winners: d_winners is required");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	return round_impl(ctx, problem, scoring, sampler, first_index, count, seed, threshold, flags, index_base, nullptr, nullptr,
+	                  d_winners, accumulate, evals_out);
+}
+
 extern "C" gcr_status gcr_round_results(gcr_ctx *ctx, double *h_best_scores, uint32_t *h_best_counts)
 {
 	if (!ctx)
@@ -353,8 +489,9 @@ extern "C" gcr_status gcr_round_results(gcr_ctx *ctx, double *h_best_scores, uin
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_round_results: no round has run on this context");
 	gcr_status st = GCR_OK;
 	if (h_best_scores)
-		st = gcr_memcpy_d2h(ctx, h_best_scores, ctx->d_round_best_scores, (size_t)ctx->n_pairs * sizeof(double));
+		st = gcr_memcpy_d2h_async(ctx, h_best_scores, ctx->d_round_best_scores, (size_t)ctx->n_pairs * sizeof(double));
 	if (!st && h_best_counts)
-		st = gcr_memcpy_d2h(ctx, h_best_counts, ctx->d_round_best_counts, (size_t)ctx->n_pairs * sizeof(uint32_t));
-	return st;
+		st = gcr_memcpy_d2h_async(ctx, h_best_counts, ctx->d_round_best_counts, (size_t)ctx->n_pairs * sizeof(uint32_t));
+	const gcr_status sync_st = gcr_sync(ctx);
+	return st ? st : sync_st;
 }

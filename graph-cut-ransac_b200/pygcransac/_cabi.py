@@ -31,7 +31,20 @@ EXPORTS = [
     "gcr_solve_plane_parallax", "gcr_refit_f_ba", "gcr_set_score_trace",
     "gcr_memcpy_d2h_async", "gcr_radius_graph_count", "gcr_radius_graph_fill",
     "gcr_score_exact_pairs", "gcr_refit_pairs",
+    "gcr_cache_stats", "gcr_round_winners", "gcr_comm_unique_id", "gcr_comm_init", "gcr_comm_destroy", "gcr_round_sharded",
+    "gcr_winners_reduce", "gcr_ubench_fp32",
 ]
+
+
+class Winner(C.Structure):
+    """gcr_winner (include/gcr/gcr.h): the 128-byte per-pair winner record of gcr_round_winners / gcr_round_sharded."""
+    _fields_ = [("score", C.c_double), ("index", C.c_uint64), ("count", C.c_uint32), ("valid", C.c_uint32),
+                ("model", C.c_double * 12), ("reserved", C.c_uint64)]
+
+
+WINNER_DTYPE = np.dtype([("score", "<f8"), ("index", "<u8"), ("count", "<u4"), ("valid", "<u4"), ("model", "<f8", (12,)),
+                         ("reserved", "<u8")])
+assert C.sizeof(Winner) == 128 and WINNER_DTYPE.itemsize == 128
 
 _lib = None
 
@@ -94,6 +107,14 @@ def load_library():
         "gcr_round": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u32, vp, vp, C.POINTER(u64)]),
         "gcr_round_results": (i32, [vp, vp, vp]),
         "gcr_getscore_host": (i32, [vp, i32, i32, i32, vp, f64, f64, C.POINTER(f64), C.POINTER(u32), vp]),
+        "gcr_cache_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "gcr_round_winners": (i32, [vp, i32, i32, i32, u64, i32, u64, f64, i32, u64, i32, vp, C.POINTER(u64)]),
+        "gcr_comm_unique_id": (i32, [vp]),
+        "gcr_comm_init": (i32, [vp, vp, i32, i32]),
+        "gcr_comm_destroy": (i32, [vp]),
+        "gcr_round_sharded": (i32, [vp, i32, i32, i32, u64, u64, u64, f64, i32, i32, vp, C.POINTER(u64)]),
+        "gcr_winners_reduce": (i32, [vp, vp, i32, vp]),
+        "gcr_ubench_fp32": (i32, [vp, i32, f64, C.POINTER(f64 * 2), C.POINTER(f64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -110,7 +131,7 @@ def load_library():
     lib.gcr_profile_read.restype = i32
     lib.gcr_profile_read.argtypes = [vp, C.POINTER(f64), C.POINTER(u64), C.POINTER(u64)]
     lib.gcr_counters_read.restype = i32
-    lib.gcr_counters_read.argtypes = [vp, C.POINTER(u64 * 4), i32]
+    lib.gcr_counters_read.argtypes = [vp, C.POINTER(u64 * 8), i32]
     _lib = lib
     return lib
 
@@ -121,6 +142,15 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return C.c_void_p(a.ctypes.data)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id for gcr_comm_init (create on rank 0, hand to every rank)."""
+    buf = (C.c_char * 128)()
+    st = load_library().gcr_comm_unique_id(C.byref(buf))
+    if st != 0:
+        raise GcrError("gcr_comm_unique_id failed with status %d (is libnccl.so.2 loadable?)" % st)
+    return bytes(buf)
 
 
 class Context:
@@ -200,9 +230,58 @@ class Context:
         return ms.value, n.value, ev.value
 
     def counters(self, reset=False):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 8)()
         self.check(self.lib.gcr_counters_read(self.h, C.byref(out), 1 if reset else 0))
         return list(out)
+
+    def select_stats(self, reset=False):
+        """(FP64 re-scores made by gcr_round's selection, largest relative FP32-vs-FP64 score error seen among them)."""
+        c = self.counters(reset)
+        return int(c[3]), float(np.array([c[4] & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0])
+
+    def ubench_fp32(self, mode=0, min_ms=200.0):
+        """Measured FP32 FMA roofline of this device: (sustained TFLOP/s over >= min_ms, best single launch, ms run)."""
+        tf, ms = (C.c_double * 2)(), C.c_double()
+        self.check(self.lib.gcr_ubench_fp32(self.h, mode, min_ms, C.byref(tf), C.byref(ms)))
+        return tf[0], tf[1], ms.value
+
+    def cache_stats(self):
+        b, u, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.check(self.lib.gcr_cache_stats(self.h, C.byref(b), C.byref(u), C.byref(n)))
+        return dict(blocks=b.value, in_use=u.value, bytes=n.value)
+
+    # ---- winner records / hypothesis-sharded mode ----
+    def round_winners_device(self, problem, scoring, sampler, first_index, count, seed, thr, flags, index_base, accumulate,
+                             d_winners):
+        ev = C.c_uint64()
+        self.check(self.lib.gcr_round_winners(self.h, problem, scoring, sampler, first_index, count, seed, thr, flags,
+                                              index_base, 1 if accumulate else 0, C.c_void_p(d_winners), C.byref(ev)))
+        return ev.value
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self.check(self.lib.gcr_comm_init(self.h, C.byref(buf), rank, world))
+
+    def comm_destroy(self):
+        self.check(self.lib.gcr_comm_destroy(self.h))
+
+    def round_sharded_device(self, problem, scoring, sampler, first_index, total_samples, seed, thr, flags, chunk_samples,
+                             d_winners):
+        """gcr_round_sharded with a caller-owned device record array; returns this rank's slot evaluations."""
+        ev = C.c_uint64()
+        self.check(self.lib.gcr_round_sharded(self.h, problem, scoring, sampler, first_index, total_samples, seed, thr, flags,
+                                              chunk_samples, C.c_void_p(d_winners), C.byref(ev)))
+        return ev.value
+
+    def round_sharded(self, problem, scoring, sampler, first_index, total_samples, seed, thr, flags=0, chunk_samples=65536):
+        """Host-output convenience: the winner records as a numpy structured array [n_pairs] (WINNER_DTYPE)."""
+        d = self.malloc(self.n_pairs * 128)
+        try:
+            ev = self.round_sharded_device(problem, scoring, sampler, first_index, total_samples, seed, thr, flags,
+                                           chunk_samples, d)
+            return self.to_host(d, (self.n_pairs,), WINNER_DTYPE), ev
+        finally:
+            self.free(d)
 
     def round_device(self, problem, scoring, sampler, first_index, count, seed, thr, flags, index_base, d_keys, d_best):
         """gcr_round with caller-owned device outputs (no host copies); returns the slot evaluations."""

@@ -64,8 +64,19 @@ gcr_status gcr_profile_enable(gcr_ctx *ctx, int on);
 /* total K3 device time (ms), number of K3 launches and hypothesis x point evaluations they covered; resets */
 gcr_status gcr_profile_read(gcr_ctx *ctx, double *score_ms, uint64_t *score_launches, uint64_t *score_evals);
 /* device counters since the last reset: out[0] = valid models produced by gcr_solve_minimal, out[1] = FP64
- * re-check evaluations dropped because the work list was full (must stay 0), out[2] = FP64 re-checks queued */
-gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[4], int reset);
+ * re-check evaluations dropped because the work list was full (must stay 0), out[2] = FP64 re-checks queued,
+ * out[3] = candidates gcr_round's selection re-scored in FP64, out[4] = the largest |FP32 score - FP64 score| / FP64 score
+ * seen among them, as the bit pattern of a float (the premise of the selection margin: must stay below margin / 2),
+ * out[5..7] reserved */
+gcr_status gcr_counters_read(gcr_ctx *ctx, uint64_t out[8], int reset);
+/* the context's device-block cache (gcr_malloc / gcr_free): blocks held, blocks handed out, bytes held */
+gcr_status gcr_cache_stats(gcr_ctx *ctx, uint64_t *blocks, uint64_t *blocks_in_use, uint64_t *bytes);
+
+/* Measures the FP32-FMA-pipe roofline of the context's device (the bound of the scoring kernels): runs a
+ * kernel of dependent packed-FFMA chains back to back for at least min_ms.  mode 0: pure FFMA2 (the pipe's peak);
+ * mode 1: FFMA2 with K3's side work (2 MUFU.RCP + compare / count / add per 19 FFMA2: the ceiling of K3's instruction
+ * mix).  tflops_out[0] = sustained over the interval, tflops_out[1] = best single launch (2 flop per FMA lane). */
+gcr_status gcr_ubench_fp32(gcr_ctx *ctx, int mode, double min_ms, double tflops_out[2], double *ms_out);
 
 /* device memory helpers so that C / ctypes callers need no other CUDA binding */
 gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out);
@@ -234,6 +245,45 @@ gcr_status gcr_round(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64
 
 /* FP64 score and exact inlier count of each pair's winner of the last gcr_round (host outputs, [n_pairs]). */
 gcr_status gcr_round_results(gcr_ctx *ctx, double *h_best_scores, uint32_t *h_best_counts);
+
+/* The winner of a round as ONE 128-byte device record per pair: what the chunks of a large problem accumulate and what
+ * the hypothesis-sharded mode exchanges between GPUs.  Unlike the packed key of gcr_round it carries the score in FP64
+ * and a 64-bit index, so GCRANSAC.h:440's strict '<' (scoring_function.h:63-66) is decided in the reference's precision
+ * across chunks and ranks too, and 2^20 samples x 3 models cannot wrap. */
+typedef struct gcr_winner
+{
+	double score;      /* FP64 score (reference arithmetic); 0 when valid == 0 */
+	uint64_t index;    /* global model-slot index: index_base + sample * max_models + model slot */
+	uint32_t count;    /* exact inlier count */
+	uint32_t valid;    /* 1 = some model scored > 0 */
+	double model[12];  /* row-major, 9 (H / F / E) or 12 (PnP) entries, the rest 0 */
+	uint64_t reserved; /* 0 */
+} gcr_winner;
+/* gcr_round writing winner records: d_winners [n_pairs].  accumulate != 0: the record is only replaced by a strictly
+ * better winner -- (FP64 score, then lower index) -- so a problem walked in chunks keeps its running best on the device. */
+gcr_status gcr_round_winners(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index, int count,
+                             uint64_t seed, double threshold, int flags, uint64_t index_base, int accumulate,
+                             gcr_winner *d_winners, uint64_t *evals_out);
+
+/* ---- hypothesis-sharded mode: one process (or thread) per GPU, NCCL over NVLink ------------------------------ */
+/* 128-byte NCCL unique id (ncclGetUniqueId): rank 0 creates it, the caller hands it to every rank (MPI, torch.distributed,
+ * a socket: host plumbing).  NCCL is loaded with dlopen("libnccl.so.2") -- inside a torch process that is torch's copy. */
+gcr_status gcr_comm_unique_id(void *h_out_128);
+/* joins the communicator of `world` contexts (blocking collective call: every rank must make it) */
+gcr_status gcr_comm_init(gcr_ctx *ctx, const void *h_unique_id_128, int rank, int world);
+gcr_status gcr_comm_destroy(gcr_ctx *ctx);
+/* One fixed-K pass with the samples [0, total_samples) of the counter-based stream sharded over the ranks of the
+ * context's communicator (rank g owns a contiguous, balanced range; sample i is a pure function of
+ * (seed, first_index + i), so no rank needs another's samples).  Each rank walks its range in chunks of chunk_samples
+ * (bounds the workspace), accumulating its winner record on the device; the records are then all-gathered (ncclAllGather,
+ * 128 bytes per pair per rank) and every rank reduces them by the same rule -- larger FP64 score, then lower index -- so
+ * all ranks end with the identical record, model included, with no host synchronisation and no second collective.
+ * Without a communicator (or world = 1) it is the chunked single-GPU pass.  d_winners [n_pairs] device. */
+gcr_status gcr_round_sharded(gcr_ctx *ctx, int problem, int scoring, int sampler, uint64_t first_index,
+                             uint64_t total_samples, uint64_t seed, double threshold, int flags, int chunk_samples,
+                             gcr_winner *d_winners, uint64_t *evals_out);
+/* the reduction rule on its own: d_all [world][n_pairs] records -> d_out [n_pairs] */
+gcr_status gcr_winners_reduce(gcr_ctx *ctx, const gcr_winner *d_all, int world, gcr_winner *d_out);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,10 @@
 """The N > 1 host logic on CPU: world_size-2 gloo process groups (no GPU).
 
-Covers shard ranges (pairs / hypotheses), the packed-key all-reduce that carries the (score, index) argmax across ranks
-(first-wins on ties, uint64 order preserved through the int64 transport) and the owner lookup for the model broadcast."""
+Covers shard ranges (pairs / hypotheses) and the winner-record reduction that carries the (FP64 score, index) argmax
+across ranks: strictly larger FP64 score wins -- also when the two scores round to the SAME float, the case the round-1
+packed key lost --, equal scores go to the lower 64-bit index, ranks without a model are ignored, and every rank ends up
+with the identical record (model included).  The device kernel k_winners_reduce applies the same rule
+(tests/test_gpu_sharded.py compares the two)."""
 import os
 import struct
 import sys
@@ -52,19 +55,32 @@ def test_key_packing_matches_library():
     assert pack_key(2.0, 900) > pack_key(1.0, 3) and pack_key(1.0, 3) > pack_key(1.0, 4) > pack_key(-1.0, 0)
 
 
+def rec(score, index, count=0, model=None, valid=1):
+    from pygcransac import _cabi
+    r = np.zeros((), dtype=_cabi.WINNER_DTYPE)
+    if valid:
+        r["score"], r["index"], r["count"], r["valid"] = score, index, count, 1
+        r["model"][:9] = np.arange(9) + index if model is None else model
+    return r
+
+
+# pair 0: rank 1 better; pair 1: tie -> lower global index (rank 0, even though rank 1's index is > 2^32 apart);
+# pair 2: rank 1 has no model; pair 3: scores 1 ulp of FP64 apart that round to the same float -> FP64 decides;
+# pair 4: nobody has a model
+_S = 524288.0
+LOCAL = {0: [rec(10.0, 40), rec(7.5, 90), rec(3.0, 5), rec(_S, 7), rec(0, 0, valid=0)],
+         1: [rec(11.0, 1040), rec(7.5, 5 * 2 ** 32 + 1), rec(0, 0, valid=0), rec(np.nextafter(_S, 2 * _S), 2 ** 33), rec(0, 0, valid=0)]}
+EXPECT = [LOCAL[1][0], LOCAL[0][1], LOCAL[0][2], LOCAL[1][3], rec(0, 0, valid=0)]
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # three "pairs": rank-local winners; pair 1 is a cross-rank tie (lower global index must win), pair 2 has no model on rank 1
-        local = {0: [pack_key(10.0, 40), pack_key(7.5, 90), pack_key(3.0, 5)],
-                 1: [pack_key(11.0, 1040), pack_key(7.5, 1001), 0]}[rank]
-        keys = torch.tensor([as_i64(k) for k in local], dtype=torch.int64)
-        sharded.reduce_keys(keys)
-        got = [int(k) & ((1 << 64) - 1) for k in keys]
-        if rank == 0:
-            out.put(got)
+        local = np.stack(LOCAL[rank])
+        got = sharded.reduce_winner_records(sharded.pack_records(local))
+        out.put((rank, got.tobytes()))
         # sharded sample ranges: every sample has exactly one owner and the owners agree with the ranges
         lo, hi = sharded.shard_range(1001, rank, world)
         mine = torch.zeros(1001, dtype=torch.int64)
@@ -76,16 +92,17 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_key_allreduce_first_wins_two_ranks():
+def test_winner_record_reduce_two_ranks():
+    assert np.float32(LOCAL[0][3]["score"]) == np.float32(LOCAL[1][3]["score"])      # an FP32 key could not tell them apart
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    got = out.get(timeout=120)
+    got = dict(out.get(timeout=120) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert got == [pack_key(11.0, 1040), pack_key(7.5, 90), pack_key(3.0, 5)]
-    assert sharded.key_index(as_i64(got[1])) == 90
+    want = np.stack(EXPECT).tobytes()
+    assert got[0] == want and got[1] == want                                        # bit-identical on both ranks
