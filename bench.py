@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- hypothesis x point evaluations / s of the GC-RANSAC hypothesise-and-verify hot path on B200.
+"""bench.py -- hypothesis x point evaluations / s (and image pairs / s) of the GC-RANSAC hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload f4k|h4k|h2k_batch|e2k|f1m_sharded|f4k_pairs|h2k_pairs|e2k_pairs|cfg1_pairs]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--no-extras]
 
-Workload at N = 1 (BASELINE.json configs[1]): fundamental matrix, 7-point + MSAC, synthetic N = 4096 correspondences,
-50 % outliers, threshold 0.75 px, single image pair.  One "step" = one fixed-K pass of the hot path: K1 draw `--samples`
-minimal samples -> K2 7-point solve + oriented-constraint test -> K3 MSAC scoring of every model against all points ->
-K4 argmax.  `value` counts only REAL models (valid model count x N), not empty root slots.
-At N > 1 every rank runs the same per-GPU workload on its own image pair (pairs shard with no collective: weak scaling).
+Default (what the driver runs): the headline line is BASELINE.json configs[1] -- fundamental matrix, 7-point + MSAC,
+synthetic N = 4096 correspondences, 50 % outliers, threshold 0.75 px, single image pair -- and the SAME JSON line carries an
+`extra` block with the other BASELINE configurations measured in the same process: h4k (the homography twin), e2k
+(configs[2]), h2k_batch (configs[3]: 2048 pairs per GPU, pairs/s resident and end to end), f1m_sharded (configs[4]:
+hypotheses sharded, NCCL all-gather of the FP64 winner records; asserts N-rank result == 1-rank result bit for bit) and the
+full pipelines through pygcransac.find* (pairs/s) with their reference CPU arms.
 
-The JSON line follows the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches).
+One "step" = `rounds_per_step` consecutive fixed-K passes of the hot path (gcr_round: K1 draw the minimal samples -> K2
+solve + validity tests -> K3 score every model against all points -> K4 FP64 winner), each over FRESH samples of the
+counter-based stream, so that K steps make a timed region of >= 1 s (clocks are sampled during it).  `value` counts only
+REAL models (valid model count x N), not empty root slots.  At N > 1 every rank runs the per-GPU workload on its own
+pairs (pairs shard with no collective: weak scaling); f1m_sharded is strong scaling.
+
+The JSON line follows the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches, extra).
 --impl reference times the reference's CPU implementation of the same pass (oracle/_ref: the reference's scoring /
 driver headers compiled verbatim + restated estimators; falls back to the oracle port) on all host cores.
 """
@@ -31,17 +38,17 @@ FLOP_PER_EVAL = {("h", "msac"): 21.0, ("f", "msac"): 35.0, ("e", "msac"): 35.0, 
                  ("f", "magsac"): 43.0, ("h", "magsac"): 29.0}
 
 WORKLOADS = {
-    # name: problem, n points, outlier ratio, threshold, samples per step, pairs per GPU
-    "f4k": dict(problem="f", n=4096, outliers=0.5, thr=0.75, samples=262144, pairs=1,
+    # name: problem, n points, outlier ratio, threshold, samples per round, pairs per GPU, rounds per step
+    "f4k": dict(problem="f", n=4096, outliers=0.5, thr=0.75, samples=262144, pairs=1, rounds=128,
                 desc="F 7-pt + MSAC, N=4096, 50% outliers, thr 0.75 px, single pair (BASELINE configs[1])"),
     # the north star's other scoring target ("0.5 of FP32 peak on 4k-point homography and fundamental scoring")
-    "h4k": dict(problem="h", n=4096, outliers=0.5, thr=3.0, samples=262144, pairs=1,
+    "h4k": dict(problem="h", n=4096, outliers=0.5, thr=3.0, samples=262144, pairs=1, rounds=256,
                 desc="H 4-pt + MSAC, N=4096, 50% outliers, thr 3.0 px, single pair (the homography twin of configs[1])"),
-    "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048,
+    "h2k_batch": dict(problem="h", n=2048, outliers=0.3, thr=3.0, samples=1024, pairs=2048, rounds=16,
                       desc="batched H 4-pt + MSAC, 2048 pairs/GPU x N=2048, 30% outliers, thr 3.0 px, K=1024 + argmax + final "
                            "least-squares refit per pair (configs[3])"),
     # configs[2]: E, 5-point + MAGSAC++ on K-normalised correspondences (threshold / focal length), 85 % outliers
-    "e2k": dict(problem="e", scoring="magsac", n=2048, outliers=0.85, thr=0.75 / 1000.0, samples=65536, pairs=1,
+    "e2k": dict(problem="e", scoring="magsac", n=2048, outliers=0.85, thr=0.75 / 1000.0, samples=65536, pairs=1, rounds=64,
                 desc="E 5-pt (Nister) + MAGSAC++, N=2048, 85% outliers, known K, thr 0.75 px / f, single pair (configs[2])"),
     # full pipelines (adaptive stop, LO, graph-cut, IRLS, final fit) through pygcransac.find*: image pairs / s
     "f4k_pairs": dict(problem="f", n=4096, outliers=0.5, thr=0.75, pairs=128, pipeline=True,
@@ -61,11 +68,14 @@ WORKLOADS = {
                       desc="findEssentialMatrix full pipeline with MAGSAC++ scoring (GCRANSAC<E estimator, grid, "
                            "MAGSACScoringFunction>: 5-pt, Stewenius refits in LO, conf 0.99, max_iters 100000), N=2048, 85% "
                            "outliers, known K, thr 0.75 px, distinct synthetic pairs (configs[2] pipeline)"),
-    # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL max all-reduce of the key
-    "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps",
+    # configs[4]: ONE problem, its hypotheses sharded over the ranks (strong scaling), NCCL all-gather of the winner records
+    "f1m_sharded": dict(problem="f", n=1048576, outliers=0.5, thr=0.75, samples=1048576, pairs=1, shard="hyps", rounds=1,
                         desc="single F problem, N=1048576 x K=1048576 7-pt samples sharded over the GPUs, MSAC, "
-                             "NCCL max all-reduce of the (score, index) key (configs[4])"),
+                             "NCCL all-gather of the (FP64 score, index, model) winner records (configs[4])"),
 }
+# what the default run adds to the headline line's `extra` block: (workload, steps cap)
+EXTRA_ROUNDS = [("h4k", 8), ("e2k", 8), ("h2k_batch", 8), ("f1m_sharded", 3)]
+EXTRA_PIPELINES = ["cfg1_pairs", "f4k_pairs", "h2k_pairs", "e2k_pairs"]
 
 
 def fixture_sizes(wl):
@@ -83,7 +93,8 @@ def make_points(wl, rank):
         one = np.ascontiguousarray(g["pts"], dtype=np.float64)
         return np.ascontiguousarray(np.stack([one] * wl["pairs"]))
     pts = []
-    for p in range(wl["pairs"]):
+    distinct = min(wl["pairs"], 128)         # a larger batch repeats 128 distinct synthetic pairs with a small per-copy shift
+    for p in range(distinct):
         seed = (0 if wl.get("shard") == "hyps" else 1000 * rank) + p + 1   # a sharded problem is the SAME on every rank
         if wl["problem"] == "f":
             pts.append(synth.epipolar_pair(wl["n"], wl["outliers"], seed)[0])
@@ -96,7 +107,10 @@ def make_points(wl, rank):
             pts.append((px - c) / f)
         else:
             pts.append(synth.homography_pair(wl["n"], wl["outliers"], seed)[0])
-    return np.ascontiguousarray(np.stack(pts))
+    out = np.empty((wl["pairs"],) + pts[0].shape)
+    for p in range(wl["pairs"]):
+        out[p] = pts[p % distinct] + (p // distinct) * 1e-3
+    return out
 
 
 class ClockSampler:
@@ -104,7 +118,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.rows = []
@@ -114,11 +128,12 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -127,21 +142,26 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, sm_load, mx, power, reasons = [], [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                power.append(float(r[3]))
+                if len(r) > 9 and float(r[9]) >= 50.0:
+                    sm_load.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
                               ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = sm_load if sm_load else sm
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(sm_load),
+                "power_w_max": max(power) if power else None}
 
 
 def k3_dram_traffic(workload):
@@ -162,19 +182,7 @@ def k3_dram_traffic(workload):
         return None
 
 
-def fp32_peak_tflops(sm_count):
-    """FP32 FMA roofline: SMs x 128 lanes x 2 flop x max SM clock.  MEASURED_PEAKS.json carries HBM and bf16 tensor
-    peaks but no FP32-pipe figure; its measured sm_max_mhz is used for the clock (else the device attribute)."""
-    mhz, src = None, None
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            mhz = float(json.load(f)["sm_max_mhz"])
-            src = "derived: %d SMs x 128 x 2 x sm_max_mhz %.0f (MEASURED_PEAKS.json)" % (sm_count, mhz)
-    except (OSError, KeyError, ValueError):
-        pass
-    return mhz, src
-
-
+# ---------------------------------------------------------------------------------------------- CPU arms ---------
 _CPU_IMPL = {}
 
 
@@ -231,14 +239,21 @@ class CpuArm:
         self.pool.join()
 
 
-def bench_reference(args, wl, rank, world):
-    """--impl reference: the CPU arm on this box's host cores (rank 0 only)."""
-    if rank != 0:
-        return
+def cpu_baseline_rounds(wl, pts0, seconds_scale=10):
+    """cpu_baseline object of a round workload: the reference scoring loop on a bounded sample, all host cores."""
+    arm = CpuArm(wl, pts0)
+    c_evals, c_wall, used = arm.run(cpu_samples_per_core(wl) * arm.cores * seconds_scale)
+    arm.close()
+    return {"value": c_evals / c_wall, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
+            "sample": "%d samples of pair 0 (solve + %s over all %d points), sliced over the host cores, %.1f s wall" % (
+                used, wl.get("scoring", "msac").upper(), wl["n"], c_wall)}
+
+
+def reference_rounds(args, wl):
+    """--impl reference for a round workload: the CPU arm on this box's host cores."""
     pts0 = make_points(dict(wl, pairs=1), 0)[0]
     arm = CpuArm(wl, pts0)
-    # bounded sample per step: ~1 s of all-core CPU work on an 8-core host
-    per_step = cpu_samples_per_core(wl) * arm.cores
+    per_step = cpu_samples_per_core(wl) * arm.cores                 # ~1 s of all-core CPU work per step
     for s in range(args.warmup):
         arm.run(per_step // 8)
     t_total, evals_total, used = 0.0, 0, 0
@@ -248,7 +263,7 @@ def bench_reference(args, wl, rank, world):
         evals_total += evals
     arm.close()
     value = evals_total / t_total
-    line = {
+    return {
         "impl": "reference", "metric": "hypothesis x point evals/s", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -258,7 +273,6 @@ def bench_reference(args, wl, rank, world):
                                    "over the host cores" % (used, wl["n"])},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
 
 
 def _pairs_cpu_worker(args):
@@ -278,7 +292,6 @@ def _pairs_cpu_worker(args):
         return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
     if problem == "e":
         from pygcransac import synth
-        K = synth.K_MAT
         npts = (pts - synth.SIZE / 2) / synth.FOCAL                              # K^-1 normalisation (utils.h:65-110)
         out = _CPU_IMPL["ref"].run(O.E, npts, cs, 4, thr / synth.FOCAL, conf=0.99, spatial_weight=weight, max_iters=max_iters,
                                    min_iters=50, lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2 if magsac else 0)
@@ -290,57 +303,383 @@ def _pairs_cpu_worker(args):
     return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
 
 
-def bench_pairs(args, wl, rank, world):
-    """Full-pipeline workloads: image pairs / s through pygcransac.find* (batched GPU driver: adaptive stop, LO with the
-    reference's BK min-cut on the host, IRLS, final fit), a few host threads per GPU each with its own context / stream
-    taking pairs from a queue; pairs shard over the ranks
-    with no collective.  The API takes host arrays, so every call includes its H2D / D2H: value == e2e.
-    --impl reference: the reference's verbatim GCRANSAC<>::run (oracle/_ref) on the same pairs, one pair per host core."""
-    weight = {"h": 0.975, "f": 0.0, "e": 0.1}[wl["problem"]]          # the Python defaults (py/bindings.cpp:1147-1178)
-    max_iters = wl.get("max_iters", 10000)
-    n_pairs = wl["pairs"]
-    pts = make_points(wl, rank)
-    line = {"metric": "image pairs/s", "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+PIPELINE_WEIGHT = {"h": 0.975, "f": 0.0, "e": 0.1}          # the Python defaults (py/bindings.cpp:1147-1178)
+
+
+def pairs_line_base(args, wl, world):
+    return {"metric": "image pairs/s", "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "data": "real (the reference's bundled image pair, committed SIFT matches)" if wl.get("fixture") else "synthetic",
-            "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": n_pairs, "spatial_coherence_weight": weight}}
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        import multiprocessing as mp
-        cores = os.cpu_count() or 1
-        pool = mp.get_context("fork").Pool(cores)
-        jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters, wl.get("sampler", 0),
-                           fixture_sizes(wl), wl.get("scoring") == "magsac") for p in range(n_pairs)]
-        for s in range(args.warmup):
-            pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
-        t0 = time.perf_counter()
-        outs = []
-        for s in range(args.steps):
-            outs += pool.map(_pairs_cpu_worker, jobs(args.warmup + s), chunksize=1)
-        wall = time.perf_counter() - t0
-        pool.close()
-        pool.join()
-        value = n_pairs * args.steps / wall
-        line.update({"impl": "reference", "value": value, "ms_per_step": 1e3 * wall / args.steps, "dtype": "f64",
-                     "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                                      "sample": "%d pairs/step, one pair per host core; mean %.1f ms per pair on one core, "
-                                                "mean %d iterations" % (n_pairs, 1e3 * np.mean([o[2] for o in outs]),
-                                                                        np.mean([o[1] for o in outs]))},
-                     "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
-        return
-    import torch
-    import torch.distributed as dist
-    import pygcransac
+            "config": {"workload": wl["desc"], "pairs_per_step_per_gpu": wl["pairs"],
+                       "spatial_coherence_weight": PIPELINE_WEIGHT[wl["problem"]]}}
+
+
+def reference_pairs(args, wl, steps=None, warmup=None):
+    """The reference's verbatim GCRANSAC<>::run (oracle/_ref) on the workload's pairs, one pair per host core."""
+    import multiprocessing as mp
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
+    weight, max_iters, n_pairs = PIPELINE_WEIGHT[wl["problem"]], wl.get("max_iters", 10000), wl["pairs"]
+    pts = make_points(wl, 0)
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("fork").Pool(cores)
+    jobs = lambda s: [(wl["problem"], pts[p], wl["thr"], weight, 100 * s + p + 1, max_iters, wl.get("sampler", 0),
+                       fixture_sizes(wl), wl.get("scoring") == "magsac") for p in range(n_pairs)]
+    for s in range(warmup):
+        pool.map(_pairs_cpu_worker, jobs(s)[:cores], chunksize=1)
+    t0 = time.perf_counter()
+    outs = []
+    for s in range(steps):
+        outs += pool.map(_pairs_cpu_worker, jobs(warmup + s), chunksize=1)
+    wall = time.perf_counter() - t0
+    pool.close()
+    pool.join()
+    value = n_pairs * steps / wall
+    line = pairs_line_base(args, wl, args.gpus)
+    line.update({"impl": "reference", "value": value, "ms_per_step": 1e3 * wall / steps, "dtype": "f64", "steps": steps,
+                 "warmup": warmup,
+                 "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                  "sample": "%d pairs/step, one pair per host core; mean %.1f ms per pair on one core, "
+                                            "mean %d iterations" % (n_pairs, 1e3 * np.mean([o[2] for o in outs]),
+                                                                    np.mean([o[1] for o in outs]))},
+                 "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return line
+
+
+# ---------------------------------------------------------------------------------------------- GPU session ------
+class Session:
+    """torch / torch.distributed plumbing, set up once per process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+        self._peak = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def fp32_peak(self, ctx):
+        """Measured FP32-FMA roofline of this GPU (gcr_ubench_fp32, pure FFMA2 chains for >= 300 ms right before the timed
+        regions) + the ceiling of K3's own instruction mix; the derived figure beside it."""
+        if self._peak is None:
+            info = ctx.device_info()
+            sustained, burst, ms = ctx.ubench_fp32(0, 300.0)
+            mix_sustained, _, _ = ctx.ubench_fp32(1, 100.0)
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    mhz = float(json.load(f)["sm_max_mhz"])
+            except (OSError, KeyError, ValueError):
+                mhz = info["sm_clock_khz"] / 1e3
+            self._peak = {"sustained": sustained, "burst": burst, "k3_mix_sustained": mix_sustained,
+                          "derived": info["sm_count"] * 128 * 2 * mhz * 1e6 / 1e12,
+                          "source": "measured in this process: gcr_ubench_fp32 (dependent FFMA2 chains, 4 CTAs x 256 threads per "
+                                    "SM) back to back for %.0f ms -- the sustained figure; best single launch %.2f; derived %d SMs x "
+                                    "128 x 2 x %.0f MHz beside it (MEASURED_PEAKS.json has no FP32 figure)" % (
+                                        ms, burst, info["sm_count"], mhz)}
+        return self._peak
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
+    """A fixed-K round workload on this rank's GPU: resident leg, e2e leg, K3 roofline.  Returns the JSON line (rank 0) or None."""
+    torch = sess.torch
     from pygcransac import _cabi
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world, local_rank = sess.rank, sess.world, sess.local_rank
+    prob = {"f": _cabi.F, "h": _cabi.H, "e": _cabi.E}[wl["problem"]]
+    scoring = _cabi.MAGSAC if wl.get("scoring") == "magsac" else _cabi.MSAC
+    flags = _cabi.SCORE_EXACT_COUNTS if args.exact_counts else 0
+    rounds = args.rounds if args.rounds > 0 else wl["rounds"]
+    ctx = _cabi.Context(local_rank)
+    # a real (non-default) stream: handle 0 would mean "restore the context's own stream" to gcr_ctx_set_stream, and
+    # the CUDA events below must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    if args.variant >= 0:
+        ctx.set_score_variant(args.variant)
+    peak = sess.fp32_peak(ctx)
+
+    pts_host = torch.from_numpy(make_points(wl, rank)).pin_memory()          # [pairs, n, 4] f64, pinned
+    pts_dev = pts_host.cuda(non_blocking=True)
+    n_pairs, n = wl["pairs"], wl["n"]
+    keys = torch.zeros(n_pairs, dtype=torch.int64, device="cuda")
+    best = torch.zeros(n_pairs, 9, dtype=torch.float64, device="cuda")
+    keys_host = torch.zeros(n_pairs, dtype=torch.int64).pin_memory()
+    best_host = torch.zeros(n_pairs, 9, dtype=torch.float64).pin_memory()
+    flush = sess.flush
+    torch.cuda.synchronize()
+
+    hyps_sharded = wl.get("shard") == "hyps"
+    if hyps_sharded:
+        from pygcransac import sharded
+        winners = torch.zeros(n_pairs, 16, dtype=torch.int64, device="cuda")      # gcr_winner records (128 B each)
+        winners_host = torch.zeros(n_pairs, 16, dtype=torch.int64).pin_memory()
+        sharded.init_comm(ctx, rank, world)
+
+    # configs[3] = "fixed K hypotheses per pair + argmax + one final least-squares refit" (SURVEY.md 8d): the refit tail
+    # for every pair of the batch, device-resident, two launches (inliers of the winners, one fit per pair)
+    refit_tail = n_pairs > 1 and not wl.get("shard")
+    if refit_tail:
+        t_idx = torch.empty(n_pairs, n, dtype=torch.int32, device="cuda")
+        t_cnt = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
+        t_sc = torch.empty(n_pairs, dtype=torch.float64, device="cuda")
+        t_refit = torch.empty(n_pairs, 9, dtype=torch.float64, device="cuda")
+        t_ok = torch.empty(n_pairs, dtype=torch.uint8, device="cuda")
+
+    def tail(c, lo, hi):
+        c.final_refit_pairs(prob, best[lo:hi].data_ptr(), wl["thr"], t_idx[lo:hi].data_ptr(), t_cnt[lo:hi].data_ptr(),
+                            t_sc[lo:hi].data_ptr(), t_refit[lo:hi].data_ptr(), t_ok[lo:hi].data_ptr())
+
+    def one_round(i, fl=None):
+        fl = flags if fl is None else fl
+        if refit_tail:
+            ev = ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"], fl, 0,
+                                  keys.data_ptr(), best.data_ptr())
+            tail(ctx, 0, n_pairs)
+            return ev
+        if hyps_sharded:
+            return ctx.round_sharded_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
+                                            wl["thr"], fl, 65536, winners.data_ptr())
+        return ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
+                                fl, 0, keys.data_ptr(), best.data_ptr())
+
+    def step_resident(i, fl=None):
+        return sum(one_round(i * rounds + r, fl) for r in range(rounds))
+
+    # e2e for a batch of pairs: the pairs are independent, so the upload of one chunk of pairs overlaps the scoring of
+    # the previous ones -- E2E_SIDE contexts (streams) take the chunks in turn (the user-level pattern for host-resident
+    # batches); the FP32 upload entry point halves the bytes (the reference's own tests hand over float32 arrays)
+    E2E_CHUNKS, E2E_SIDE = 16, 4
+    overlap = n_pairs >= 8 * E2E_CHUNKS and not hyps_sharded
+    use_f32 = overlap and args.upload == "f32"
+    if overlap:
+        side = []
+        for _ in range(E2E_SIDE):
+            c2 = _cabi.Context(local_rank)
+            s2 = torch.cuda.Stream()
+            c2.set_stream(s2.cuda_stream)
+            if args.variant >= 0:
+                c2.set_score_variant(args.variant)
+            side.append((c2, s2))
+        chunk = n_pairs // E2E_CHUNKS
+        pts_host32 = pts_host.to(torch.float32).pin_memory() if use_f32 else None
+    h2d_bytes_per_round = int(pts_host.numel() * (4 if use_f32 else 8))
+
+    def upload(c, lo, hi):
+        if use_f32:
+            c.check(c.lib.gcr_points_upload_f32(c.h, pts_host32[lo:hi].data_ptr(), n, 4, hi - lo))
+        else:
+            c.check(c.lib.gcr_points_upload(c.h, pts_host[lo:hi].data_ptr(), n, 4, hi - lo))
+
+    def round_e2e(i):
+        """one round through the C ABI with HOST buffers: H2D of the points, the round, D2H of the result"""
+        if not overlap:
+            upload(ctx, 0, n_pairs)
+            ev = one_round(i)
+            if hyps_sharded:
+                winners_host.copy_(winners, non_blocking=True)
+            else:
+                keys_host.copy_(keys, non_blocking=True)
+                best_host.copy_(best, non_blocking=True)
+            return ev
+        start = torch.cuda.Event()
+        start.record(stream)
+        ev = 0
+        for c2, s2 in side:
+            s2.wait_event(start)
+        for c in range(E2E_CHUNKS):
+            c2, s2 = side[c % E2E_SIDE]
+            lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
+            with torch.cuda.stream(s2):
+                upload(c2, lo, hi)
+                ev += c2.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345 + c, wl["thr"], flags, 0,
+                                      keys[lo:hi].data_ptr(), best[lo:hi].data_ptr())
+                tail(c2, lo, hi)
+                keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
+                best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
+        for c2, s2 in side:
+            done = torch.cuda.Event()
+            done.record(s2)
+            stream.wait_event(done)
+        return ev
+
+    def step_e2e(i):
+        return sum(round_e2e(i * rounds + r) for r in range(rounds))
+
+    def timed(step_fn, first, nsteps):
+        """nsteps steps, each bracketed by its own CUDA event pair on the launching stream; the L2 flush (a 256 MiB device
+        memset) runs BETWEEN steps, outside the event pairs.  Returns (sum of step times in ms, slot evaluations)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        slot = 0
+        for i, (a, b) in enumerate(evs):
+            flush.zero_()
+            a.record()
+            slot += step_fn(first + i)
+            b.record()
+        stream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs), slot
+
+    # ---- resident leg: inputs in HBM before the timed region ----
+    ctx.points_set_device(pts_dev.data_ptr(), n, 4, n_pairs)
+    for i in range(warmup):
+        flush.zero_()
+        step_resident(i)
+    sess.barrier()
+    ctx.counters(reset=True)
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count()
+    clocks = ClockSampler(local_rank).start()
+    sess.barrier()
+    ms, slot_evals = timed(step_resident, warmup, steps)
+    sess.barrier()
+    launches = ctx.launch_count() - launches0
+    score_ms, score_launches, _ = ctx.profile_read()
+    rescored, max_err = ctx.select_stats()
+    counters = ctx.counters(reset=True)
+    valid_models, dropped = counters[0], counters[1]
+    if dropped:
+        raise SystemExit("bench.py: %d FP64 re-check evaluations were dropped (work list full)" % dropped)
+    evals = valid_models * n
+
+    # ---- K3 with FP64-exact per-model inlier counts (threshold-band re-check): the same kernel family, one short leg ----
+    frac_counts = None
+    if headline and not args.exact_counts and not hyps_sharded:
+        ctx.profile_read()
+        timed(lambda i: step_resident(i, _cabi.SCORE_EXACT_COUNTS), warmup + steps, max(1, min(steps, 3)))
+        c_ms, _, _ = ctx.profile_read()
+        c_valid = ctx.counters(reset=True)[0]
+        frac_counts = (c_valid * n, c_ms)
+    ctx.profile_enable(False)
+
+    # ---- hardware proof of SURVEY 8(e) row 2: the N-rank winner record == the 1-rank record, bit for bit ----
+    sharded_equal, rec = None, None
+    if hyps_sharded:
+        one_round(0)
+        got = winners.clone()
+        ctx.comm_destroy()                                              # without a communicator: the chunked 1-GPU pass
+        one_round(0)
+        stream.synchronize()
+        sharded_equal = bool(torch.equal(got, winners))
+        rec = got.cpu().numpy().reshape(-1).view(_cabi.WINNER_DTYPE)[0]
+        if not sharded_equal:
+            raise SystemExit("bench.py: rank %d: the %d-rank winner record differs from the single-GPU record" % (rank, world))
+        sharded.init_comm(ctx, rank, world)
+
+    # ---- e2e leg: host buffers, H2D + D2H inside the timed region ----
+    for i in range(warmup):
+        flush.zero_()
+        step_e2e(i)
+    sess.barrier()
+    ctx.counters(reset=True)
+    if overlap:
+        for c2, _ in side:
+            c2.counters(reset=True)
+    ms_e2e, _ = timed(step_e2e, warmup, steps)
+    sess.barrier()
+    clock_info = clocks.stop()
+    evals_e2e = ctx.counters(reset=True)[0] * n
+    if overlap:
+        evals_e2e = sum(c2.counters(reset=True)[0] for c2, _ in side) * n
+
+    # ---- max over ranks, sum of work ----
+    ms, ms_e2e = sess.reduce([ms, ms_e2e], "max")
+    evals_all, evals_e2e, launches, slot_evals = sess.reduce([evals, evals_e2e, launches, slot_evals], "sum")
+
+    line = None
+    if rank == 0:
+        flop = FLOP_PER_EVAL[(wl["problem"], wl.get("scoring", "msac"))]
+        # dominant kernel = K3 (k_score_main): algorithmic flops of the REAL models this rank scored / its own event time
+        achieved = evals * flop / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
+        total_rounds = steps * rounds
+        line = {
+            "metric": "hypothesis x point evals/s", "value": evals_all / (ms * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "strong" if hyps_sharded else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": name, "samples_per_round_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
+                       "rounds_per_step": rounds, "ms_per_round": ms / total_rounds, "timed_region_s": ms * 1e-3,
+                       "pairs_per_s": (world * n_pairs * total_rounds / (ms * 1e-3)) if n_pairs > 1 else None,
+                       "pairs_per_s_e2e": (world * n_pairs * total_rounds / (ms_e2e * 1e-3)) if n_pairs > 1 else None,
+                       "step": "%d x gcr_round (K1-K4) over fresh samples" % rounds +
+                               (" + inliers of every pair's winner + one least-squares refit per pair" if refit_tail else "") +
+                               (" (gcr_round_sharded: chunks of 65536 samples, FP64 winner records, ncclAllGather)" if hyps_sharded else ""),
+                       "models_scored_per_round": evals_all / n / total_rounds, "model_slots_per_round": slot_evals / n / total_rounds,
+                       "k3_exact_counts": bool(args.exact_counts),
+                       "winner": "every slot within the FP32 margin of the top re-scored in FP64 (K4): %d re-scores in the timed "
+                                 "region, max FP32 score error seen %.1e" % (rescored, max_err),
+                       "k3_variant": args.variant,
+                       "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs); inside a step the "
+                                   "points (<= 128 KB per pair) stay L2-resident by design"},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak["sustained"], "unit": "TFLOP/s",
+                         "frac": (achieved / peak["sustained"]) if achieved else None,
+                         "frac_of_derived_peak": (achieved / peak["derived"]) if achieved else None,
+                         "peak_burst": peak["burst"], "peak_derived": peak["derived"], "k3_mix_ceiling": peak["k3_mix_sustained"],
+                         "traffic": k3_dram_traffic(name),
+                         "traffic_note": "DRAM bytes of one K3 launch from the committed ncu --set full capture (profiles/): the "
+                                         "points and models are L2-resident, the FMA pipe is the bound",
+                         "kernel": "k_score_main (K3), without per-model inlier counts (the winner's exact count comes from K4)",
+                         "flop_per_eval": flop, "k3_ms_per_launch": score_ms / max(1, score_launches),
+                         "k3_share_of_step": score_ms / ms if world == 1 else None, "peak_source": peak["source"],
+                         "note": "FP32-FMA-pipe bound (projective divide / Sampson denominator; not a tensor-core "
+                                 "contraction, HBM traffic ~0): peak is the FP32 roofline, not hbm/tensor"},
+            "clocks": clock_info,
+            "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": h2d_bytes_per_round * rounds,
+                    "d2h_bytes_per_step": int(n_pairs * (128 if hyps_sharded else 8 + 72)) * rounds,
+                    "ms_per_round": ms_e2e / total_rounds,
+                    "h2d_gbs": h2d_bytes_per_round * total_rounds / (ms_e2e * 1e-3) / 1e9,
+                    "overlap": ("%d chunks of pairs on %d contexts / streams: uploads overlap scoring; %s upload" % (
+                        E2E_CHUNKS, E2E_SIDE, args.upload)) if overlap else "none"},
+            "gpu_launches": int(launches),
+        }
+        if frac_counts:
+            a_c = frac_counts[0] * flop / (frac_counts[1] * 1e-3) / 1e12 if frac_counts[1] > 0 else None
+            line["roofline"]["frac_with_exact_counts"] = a_c / peak["sustained"] if a_c else None
+        if hyps_sharded:
+            line["config"]["sharded_equals_single_gpu"] = sharded_equal
+            line["config"]["winner_record"] = {"score": float(rec["score"]), "index": int(rec["index"]), "count": int(rec["count"])}
+        if with_cpu:
+            line["cpu_baseline"] = cpu_baseline_rounds(wl, pts_host[0].numpy().copy(), 10 if headline else 3)
+    if overlap:
+        for c2, _ in side:
+            c2.close()
+    ctx.close()
+    return line
+
+
+def gpu_pairs(sess, args, name, wl, steps, warmup):
+    """Full-pipeline workloads: image pairs / s through pygcransac.find* (batched GPU driver: adaptive stop, LO with the
+    reference's BK min-cut on the host, IRLS, final fit), a few host threads per GPU each with its own context / stream
+    taking pairs from a queue; pairs shard over the ranks with no collective.  The API takes host arrays, so every call
+    includes its H2D / D2H: value == e2e."""
+    import pygcransac
     from pygcransac import synth
+    rank, world, local_rank = sess.rank, sess.world, sess.local_rank
+    weight, max_iters, n_pairs = PIPELINE_WEIGHT[wl["problem"]], wl.get("max_iters", 10000), wl["pairs"]
+    pts = make_points(wl, rank)
     if wl["problem"] == "e":
         find = lambda c, *a, **kw: pygcransac.findEssentialMatrix(c, synth.K_MAT, synth.K_MAT, *a, **kw)
     else:
@@ -350,7 +689,6 @@ def bench_pairs(args, wl, rank, world):
     workers = args.workers if args.workers > 0 else max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     pygcransac._load_driver()
     pool = ThreadPoolExecutor(workers)
-
     extra = {}
     sizes = fixture_sizes(wl)
 
@@ -371,49 +709,61 @@ def bench_pairs(args, wl, rank, world):
         out = list(pool.map(one_pair, [(s, p) for p in range(n_pairs)]))
         return sum(o[0] for o in out), sum(o[1] for o in out)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for s in range(args.warmup):
+    for s in range(warmup):
         one_pass(s)
     launch_total = lambda: sum(c.launch_count() for (d, _), c in list(pygcransac._contexts.items()) if d == local_rank)
     launches0 = launch_total()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
+    clocks = ClockSampler(local_rank).start()
+    sess.barrier()
     t0 = time.perf_counter()
     inl = its = 0
-    for s in range(args.steps):
-        a, b = one_pass(args.warmup + s)
+    for s in range(steps):
+        a, b = one_pass(warmup + s)
         inl, its = inl + a, its + b
-    barrier()
+    sess.barrier()
     wall = time.perf_counter() - t0
     clock_info = clocks.stop()
     launches = launch_total() - launches0
-    total_pairs = n_pairs * args.steps
-    if world > 1:
-        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = t.item()
-        w = torch.tensor([total_pairs, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        total_pairs, launches = w.tolist()
-    if rank == 0:
-        value = total_pairs / wall
-        line.update({"value": value, "ms_per_step": 1e3 * wall / args.steps, "dtype": "f32 ranking / f64 decisions",
-                     "clocks": clock_info, "gpu_launches": int(launches),
-                     "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": int(pts.nbytes),
-                             "d2h_bytes_per_step": int(n_pairs * (72 + wl["n"]))},
-                     "roofline": None})
-        line["config"].update({"per_pair_mean": {k: v / (n_pairs * (args.steps + args.warmup)) for k, v in extra.items()}})
-        line["config"].update({"host_threads_per_gpu": workers, "mean_inliers": inl / (n_pairs * args.steps), "mean_iterations": its / (n_pairs * args.steps),
-                               "timing": "host wall clock around synchronous API calls (each returns host results), "
-                                         "max over ranks"})
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    pool.shutdown()
+    wall, = sess.reduce([wall], "max")
+    total_pairs, launches = sess.reduce([n_pairs * steps, launches], "sum")
+    if rank != 0:
+        return None
+    value = total_pairs / wall
+    line = pairs_line_base(args, wl, world)
+    line.update({"value": value, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * wall / steps,
+                 "dtype": "f32 ranking / f64 decisions", "clocks": clock_info, "gpu_launches": int(launches),
+                 "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": int(pts.nbytes),
+                         "d2h_bytes_per_step": int(n_pairs * (72 + wl["n"]))},
+                 "roofline": None})
+    line["config"].update({"name": name, "per_pair_mean": {k: v / (n_pairs * (steps + warmup)) for k, v in extra.items()}})
+    line["config"].update({"host_threads_per_gpu": workers, "mean_inliers": inl / (n_pairs * steps), "mean_iterations": its / (n_pairs * steps),
+                           "timing": "host wall clock around synchronous API calls (each returns host results), "
+                                     "max over ranks"})
+    return line
+
+
+def compact(line):
+    """What an `extra` entry keeps of a workload's full line."""
+    out = {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"],
+           "steps": line["steps"], "scaling": line["scaling"], "e2e": line["e2e"]["value"], "workload": line["config"]["workload"],
+           "gpu_launches": line.get("gpu_launches")}
+    cfg = line["config"]
+    for k in ("rounds_per_step", "ms_per_round", "timed_region_s", "pairs_per_s", "pairs_per_s_e2e", "sharded_equals_single_gpu",
+              "winner_record", "mean_inliers", "mean_iterations", "host_threads_per_gpu", "models_scored_per_round"):
+        if cfg.get(k) is not None:
+            out[k] = cfg[k]
+    if line["e2e"].get("h2d_gbs") is not None:
+        out["e2e_h2d_gbs"] = line["e2e"]["h2d_gbs"]
+    if line.get("roofline"):
+        r = line["roofline"]
+        out["roofline"] = {k: r[k] for k in ("achieved", "peak", "frac", "frac_of_derived_peak", "k3_ms_per_launch", "k3_share_of_step",
+                                             "flop_per_eval")}
+    if line.get("clocks"):
+        out["clocks"] = {k: line["clocks"].get(k) for k in ("sm_mhz", "reasons", "samples_under_load")}
+    if line.get("cpu_baseline"):
+        out["cpu_baseline"] = line["cpu_baseline"]
+    return out
 
 
 def main():
@@ -422,264 +772,64 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="f4k", choices=sorted(WORKLOADS))
-    ap.add_argument("--samples", type=int, default=0, help="minimal samples per step per pair (default: workload's)")
+    ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
+                    help="one workload only; default: the f4k headline + every other configuration in `extra`")
+    ap.add_argument("--no-extras", action="store_true", help="default run without the `extra` block")
+    ap.add_argument("--samples", type=int, default=0, help="minimal samples per round per pair (default: workload's)")
+    ap.add_argument("--rounds", type=int, default=0, help="rounds per step (default: workload's, sized for a >= 1 s timed region)")
     ap.add_argument("--variant", type=int, default=-1, help="force a K3 kernel variant (see gcr_set_score_variant)")
+    ap.add_argument("--upload", default="f32", choices=["f32", "f64"], help="batched e2e leg: host array type handed to the C ABI")
     ap.add_argument("--exact-counts", action="store_true",
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")
-    ap.add_argument("--no-exact", action="store_true", help=argparse.SUPPRESS)  # old spelling of the default
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--workers", type=int, default=0, help="pipeline workloads: host threads (one gcr_ctx each) per GPU")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
+    name = args.workload or "f4k"
+    wl = dict(WORKLOADS[name])
     if args.samples:
         wl["samples"] = args.samples
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if wl.get("pipeline"):
-        bench_pairs(args, wl, rank, world)
-        return
     if args.impl == "reference":
-        bench_reference(args, wl, rank, world)
+        if rank != 0:
+            return
+        line = reference_pairs(args, wl) if wl.get("pipeline") else reference_rounds(args, wl)
+        print(json.dumps(line))
         return
 
-    import torch
-    import torch.distributed as dist
-    from pygcransac import _cabi
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    prob = {"f": _cabi.F, "h": _cabi.H, "e": _cabi.E}[wl["problem"]]
-    scoring = _cabi.MAGSAC if wl.get("scoring") == "magsac" else _cabi.MSAC
-    mlen = 9
-    flags = _cabi.SCORE_EXACT_COUNTS if args.exact_counts else 0
-    ctx = _cabi.Context(local_rank)
-    # a real (non-default) stream: handle 0 would mean "restore the context's own stream" to gcr_ctx_set_stream, and
-    # the CUDA events below must sit on the stream the kernels are launched on
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    if args.variant >= 0:
-        ctx.set_score_variant(args.variant)
-    info = ctx.device_info()
-
-    pts_host = torch.from_numpy(make_points(wl, rank)).pin_memory()          # [pairs, n, 4] f64, pinned
-    pts_dev = pts_host.cuda(non_blocking=True)
-    n_pairs, n = wl["pairs"], wl["n"]
-    keys = torch.zeros(n_pairs, dtype=torch.int64, device="cuda")
-    best = torch.zeros(n_pairs, 9, dtype=torch.float64, device="cuda")
-    keys_host = torch.zeros(n_pairs, dtype=torch.int64).pin_memory()
-    best_host = torch.zeros(n_pairs, 9, dtype=torch.float64).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    hyps_sharded = wl.get("shard") == "hyps"
-    if hyps_sharded:
-        from pygcransac import sharded
-        winners = torch.zeros(n_pairs, 16, dtype=torch.int64, device="cuda")      # gcr_winner records (128 B each)
-        sharded.init_comm(ctx, rank, world)
-
-    # configs[3] = "fixed K hypotheses per pair + argmax + one final least-squares refit" (SURVEY.md 8d): the refit tail
-    # for every pair of the batch, device-resident, two launches (inliers of the winners, one fit per pair)
-    refit_tail = n_pairs > 1 and not wl.get("shard")
-    if refit_tail:
-        t_idx = torch.empty(n_pairs, n, dtype=torch.int32, device="cuda")
-        t_cnt = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
-        t_sc = torch.empty(n_pairs, dtype=torch.float64, device="cuda")
-        t_refit = torch.empty(n_pairs, 9, dtype=torch.float64, device="cuda")
-        t_ok = torch.empty(n_pairs, dtype=torch.uint8, device="cuda")
-
-    def tail(c, lo, hi):
-        c.final_refit_pairs(prob, best[lo:hi].data_ptr(), wl["thr"], t_idx[lo:hi].data_ptr(), t_cnt[lo:hi].data_ptr(),
-                            t_sc[lo:hi].data_ptr(), t_refit[lo:hi].data_ptr(), t_ok[lo:hi].data_ptr())
-
-    def one_round(i):
-        if refit_tail:
-            ev = ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"], flags, 0,
-                                  keys.data_ptr(), best.data_ptr())
-            tail(ctx, 0, n_pairs)
-            return ev
-        if hyps_sharded:
-            return ctx.round_sharded_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345,
-                                            wl["thr"], flags, 65536, winners.data_ptr())
-        return ctx.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"],
-                                flags, 0, keys.data_ptr(), best.data_ptr())
-
-    def step_resident(i):
-        return one_round(i)
-
-    # e2e for a batch of pairs: the pairs are independent, so the upload of one chunk of pairs overlaps the scoring of
-    # the previous one -- two contexts (streams) take alternate chunks (the user-level pattern for host-resident batches)
-    E2E_CHUNKS = 8
-    overlap = n_pairs >= 8 * E2E_CHUNKS and not hyps_sharded
-    if overlap:
-        side = []
-        for _ in range(2):
-            c2 = _cabi.Context(local_rank)
-            s2 = torch.cuda.Stream()
-            c2.set_stream(s2.cuda_stream)
-            if args.variant >= 0:
-                c2.set_score_variant(args.variant)
-            side.append((c2, s2))
-        chunk = n_pairs // E2E_CHUNKS
-
-    def step_e2e(i):
-        if not overlap:
-            ctx.check(ctx.lib.gcr_points_upload(ctx.h, pts_host.data_ptr(), n, 4, n_pairs))   # H2D inside the timed region
-            ev = one_round(i)
-            keys_host.copy_(keys, non_blocking=True)                             # D2H of the step's result
-            best_host.copy_(best, non_blocking=True)
-            return ev
-        start = torch.cuda.Event()
-        start.record(stream)
-        ev = 0
-        for c2, s2 in side:
-            s2.wait_event(start)
-        for c in range(E2E_CHUNKS):
-            c2, s2 = side[c & 1]
-            lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
-            with torch.cuda.stream(s2):
-                c2.check(c2.lib.gcr_points_upload(c2.h, pts_host[lo:hi].data_ptr(), n, 4, hi - lo))
-                ev += c2.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345 + c, wl["thr"], flags, 0,
-                                      keys[lo:hi].data_ptr(), best[lo:hi].data_ptr())
-                tail(c2, lo, hi)
-                keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
-                best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
-        for c2, s2 in side:
-            done = torch.cuda.Event()
-            done.record(s2)
-            stream.wait_event(done)
-        return ev
-
-    def timed(step_fn, first):
-        """K steps, each bracketed by its own CUDA event pair on the launching stream; the L2 flush (a 256 MiB device
-        memset) runs BETWEEN steps, outside the event pairs.  Returns (sum of step times in ms, slot evaluations)."""
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        slot = 0
-        for i, (a, b) in enumerate(evs):
-            flush.zero_()
-            a.record()
-            slot += step_fn(first + i)
-            b.record()
-        stream.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs), slot
-
-    # ---- resident leg: inputs in HBM before the timed region ----
-    ctx.points_set_device(pts_dev.data_ptr(), n, 4, n_pairs)
-    for i in range(args.warmup):
-        flush.zero_()
-        step_resident(i)
-    barrier()
-    ctx.counters(reset=True)
-    ctx.profile_enable(True)
-    ctx.profile_read()
-    launches0 = ctx.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
-    ms, slot_evals = timed(step_resident, args.warmup)
-    barrier()
-    launches = ctx.launch_count() - launches0
-    score_ms, score_launches, score_slot_evals = ctx.profile_read()
-    ctx.profile_enable(False)
-    counters = ctx.counters(reset=True)
-    valid_models, dropped = counters[0], counters[1]
-    if dropped:
-        raise SystemExit("bench.py: %d FP64 re-check evaluations were dropped (work list full)" % dropped)
-    evals = valid_models * n
-    best_key_score, best_key_index = ctx.key_decode(int(keys[0].item()) & ((1 << 64) - 1))
-
-    # ---- e2e leg: host buffers, H2D + D2H inside the timed region ----
-    for i in range(args.warmup):
-        flush.zero_()
-        step_e2e(i)
-    barrier()
-    ctx.counters(reset=True)
-    if overlap:
-        for c2, _ in side:
-            c2.counters(reset=True)
-    ms_e2e, _ = timed(step_e2e, args.warmup)
-    barrier()
-    clock_info = clocks.stop()
-    evals_e2e = ctx.counters(reset=True)[0] * n
-    if overlap:
-        evals_e2e = sum(c2.counters(reset=True)[0] for c2, _ in side) * n
-
-    # ---- max over ranks, sum of work ----
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([evals, evals_e2e, launches, slot_evals], dtype=torch.float64, device="cuda")
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        ms, ms_e2e = t.tolist()
-        evals, evals_e2e, launches, slot_evals = w.tolist()
-
+    sess = Session()
+    with_cpu = not args.no_cpu and sess.world == 1            # the CPU legs run on rank 0 at N = 1 only (contract)
+    if wl.get("pipeline"):
+        line = gpu_pairs(sess, args, name, wl, args.steps, args.warmup)
+    else:
+        line = gpu_rounds(sess, args, name, wl, args.steps, args.warmup, with_cpu=with_cpu, headline=True)
+    if not args.workload and not args.no_extras:
+        extra = {}
+        for ename, cap in EXTRA_ROUNDS:
+            t0 = time.perf_counter()
+            l2 = gpu_rounds(sess, args, ename, dict(WORKLOADS[ename]), max(1, min(args.steps, cap)), min(args.warmup, 2),
+                            with_cpu=with_cpu, headline=False)
+            if rank == 0:
+                extra[ename] = compact(l2)
+                extra[ename]["bench_wall_s"] = time.perf_counter() - t0
+        for ename in EXTRA_PIPELINES:
+            t0 = time.perf_counter()
+            ewl = dict(WORKLOADS[ename])
+            l2 = gpu_pairs(sess, args, ename, ewl, 2, 1)
+            if rank == 0:
+                extra[ename] = compact(l2)
+                if with_cpu:
+                    ref = reference_pairs(args, ewl, steps=1, warmup=0)
+                    extra[ename]["cpu_baseline"] = ref["cpu_baseline"]
+                    extra[ename]["speedup_vs_cpu_baseline"] = l2["value"] / ref["value"]
+                extra[ename]["bench_wall_s"] = time.perf_counter() - t0
+            sess.barrier()
+        if rank == 0:
+            line["extra"] = extra
     if rank == 0:
-        flop = FLOP_PER_EVAL[(wl["problem"], wl.get("scoring", "msac"))]
-        mhz, peak_src = fp32_peak_tflops(info["sm_count"])
-        if mhz is None:
-            mhz = info["sm_clock_khz"] / 1e3
-            peak_src = "derived: %d SMs x 128 x 2 x device clock %.0f MHz (MEASURED_PEAKS.json absent: fallback)" % (
-                info["sm_count"], mhz)
-        peak = info["sm_count"] * 128 * 2 * mhz * 1e6 / 1e12
-        # dominant kernel = K3 (k_score): algorithmic flops of the REAL models it scored / its own event time
-        k3_real_evals = (evals / world) if world > 1 else evals
-        achieved = k3_real_evals * flop / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
-        line = {
-            "metric": "hypothesis x point evals/s", "value": evals / (ms * 1e-3), "unit": "evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong" if hyps_sharded else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wl["desc"], "samples_per_step_per_pair": wl["samples"], "pairs_per_gpu": n_pairs,
-                       "pairs_per_s": (world * n_pairs * args.steps / (ms * 1e-3)) if n_pairs > 1 else None,
-                       "pairs_per_s_e2e": (world * n_pairs * args.steps / (ms_e2e * 1e-3)) if n_pairs > 1 else None,
-                       "step": "gcr_round (K1-K4)" + (" + inliers of every pair's winner + one least-squares refit per pair"
-                                                       if refit_tail else ""),
-                       "models_scored_per_step": evals / n / args.steps, "model_slots_per_step": slot_evals / n / args.steps,
-                       "k3_exact_counts": bool(args.exact_counts), "winner": "FP64 re-score of the near-best candidates (K4)", "k3_variant": args.variant,
-                       "l2_flush": "256 MiB device memset between steps (outside the per-step event pairs)",
-                       "best_score_rank0": best_key_score},
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": k3_dram_traffic(args.workload),
-                         "traffic_note": "DRAM bytes of one K3 launch from the committed ncu --set full capture (profiles/): the "
-                                         "points and models are L2-resident, the FMA pipe is the bound",
-                         "kernel": "k_score (K3)", "flop_per_eval": flop, "k3_ms_per_launch": score_ms / max(1, score_launches),
-                         "k3_share_of_step": score_ms / ms if world == 1 else None, "peak_source": peak_src,
-                         "note": "FP32-FMA-pipe bound (projective divide / Sampson denominator; not a tensor-core "
-                                 "contraction, HBM traffic ~0): peak is the FP32 roofline, not hbm/tensor"},
-            "clocks": clock_info,
-            "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": "evals/s",
-                    "h2d_bytes_per_step": int(pts_host.numel() * 8), "d2h_bytes_per_step": int(n_pairs * (8 + 72)),
-                    "overlap": ("%d chunks of pairs on 2 contexts / streams: uploads overlap scoring" % E2E_CHUNKS) if overlap else "none"},
-            "gpu_launches": int(launches),
-        }
-        if not args.no_cpu:
-            arm = CpuArm(wl, pts_host[0].numpy().copy())
-            cpu_samples = cpu_samples_per_core(wl) * arm.cores * 10
-            c_evals, c_wall, used = arm.run(cpu_samples)
-            arm.close()
-            line["cpu_baseline"] = {"value": c_evals / c_wall, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
-                                    "sample": "%d samples of pair 0 (solve + MSAC over all %d points), sliced over the "
-                                              "host cores, %.1f s wall" % (used, n, c_wall)}
         print(json.dumps(line))
-    if overlap:
-        for c2, _ in side:
-            c2.close()
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    sess.close()
 
 
 if __name__ == "__main__":

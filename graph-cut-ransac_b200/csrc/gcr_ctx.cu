@@ -66,6 +66,7 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	gcr_comm_destroy(ctx);
 	cudaFree(ctx->d_gather);
 	cudaFree(ctx->d_pts64_owned);
+	cudaFree(ctx->d_upload32);
 	cudaFree(ctx->d_pts32);
 	cudaFree(ctx->d_score_ws);
 	cudaFree(ctx->d_norm);
@@ -740,6 +741,68 @@ extern "C" gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, in
 	}
 	else
 		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts64_owned, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->d_pts64 = ctx->d_pts64_owned;
+	ctx->n = n;
+	ctx->cols = cols;
+	ctx->n_pairs = n_pairs;
+	return prepare_points(ctx);
+}
+
+// float32 host array -> the FP64 device copy (exact widening: what pybind's py::array_t<double> conversion does on the host
+// for the float32 arrays the reference's own tests pass, tests/test_homography.py:52-60) -- half the bytes over PCIe
+__global__ void __launch_bounds__(256) k_widen_f32(const float *__restrict__ in, double *__restrict__ out, size_t count)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+		out[i] = (double)in[i];
+}
+
+extern "C" gcr_status gcr_points_upload_f32(gcr_ctx *ctx, const float *h_points, int n, int cols, int n_pairs)
+{
+	gcr_status st = check_shape(ctx, h_points, n, cols, n_pairs);
+	if (st)
+		return st;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t count = (size_t)n * cols * n_pairs, bytes = count * sizeof(double), bytes32 = count * sizeof(float);
+	if (bytes > ctx->pts64_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_pts64_owned);
+		ctx->d_pts64_owned = nullptr;
+		ctx->pts64_capacity = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pts64_owned, bytes));
+		ctx->pts64_capacity = bytes;
+	}
+	if (bytes32 > ctx->upload32_capacity)
+	{
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_upload32);
+		ctx->d_upload32 = nullptr;
+		ctx->upload32_capacity = 0;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_upload32, bytes32));
+		ctx->upload32_capacity = bytes32;
+	}
+	cudaPointerAttributes attr;
+	const bool pinned = cudaPointerGetAttributes(&attr, h_points) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned && bytes32 <= gcr_ctx::STAGE_BYTES && ensure_stage(ctx) == GCR_OK)
+	{
+		if (ctx->stage_off || !ctx->pending_d2h.empty())
+		{
+			gcr_status fs = flush_d2h(ctx);
+			if (fs)
+				return fs;
+		}
+		memcpy(ctx->h_stage, h_points, bytes32);
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_upload32, ctx->h_stage, bytes32, cudaMemcpyHostToDevice, ctx->stream));
+		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->stage_off = 0;
+	}
+	else
+		GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->d_upload32, h_points, bytes32, cudaMemcpyHostToDevice, ctx->stream));
+	size_t blocks = (count + 255) / 256;
+	if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+	k_widen_f32<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->d_upload32, ctx->d_pts64_owned, count);
+	GCR_LAUNCHED(ctx);
 	ctx->d_pts64 = ctx->d_pts64_owned;
 	ctx->n = n;
 	ctx->cols = cols;

@@ -26,6 +26,8 @@ struct gcr_ctx
 	const double *d_pts64 = nullptr; // [n_pairs][n][cols]
 	double *d_pts64_owned = nullptr;
 	size_t pts64_capacity = 0;
+	float *d_upload32 = nullptr; // staging of gcr_points_upload_f32
+	size_t upload32_capacity = 0;
 	// [n_pairs][n_pad][2] float4: (x1 x1 y1 y1)(x2 x2 y2 y2) operand-duplicated for the packed f32x2 scoring path
 	// (cols == 4), or (u v 0 0)(X Y Z 0) (cols == 5)
 	float4 *d_pts32 = nullptr;

@@ -32,7 +32,7 @@ EXPORTS = [
     "gcr_memcpy_d2h_async", "gcr_radius_graph_count", "gcr_radius_graph_fill",
     "gcr_score_exact_pairs", "gcr_refit_pairs",
     "gcr_cache_stats", "gcr_round_winners", "gcr_comm_unique_id", "gcr_comm_init", "gcr_comm_destroy", "gcr_round_sharded",
-    "gcr_winners_reduce", "gcr_ubench_fp32",
+    "gcr_winners_reduce", "gcr_ubench_fp32", "gcr_points_upload_f32",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
         "gcr_memset": (i32, [vp, vp, i32, C.c_size_t]),
         "gcr_points_upload": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
+        "gcr_points_upload_f32": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_get_norm": (i32, [vp, vp]),
         "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
         "gcr_set_point_probabilities": (i32, [vp, vp, i32]),
@@ -297,6 +298,14 @@ class Context:
         n = pts.size // cols // n_pairs
         self._pts_keepalive = pts
         self.check(self.lib.gcr_points_upload(self.h, _ptr(pts), n, cols, n_pairs))
+        self.n, self.cols, self.n_pairs = n, cols, n_pairs
+
+    def points_upload_f32(self, pts, n_pairs=1):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        cols = pts.shape[-1]
+        n = pts.size // cols // n_pairs
+        self._pts_keepalive = pts
+        self.check(self.lib.gcr_points_upload_f32(self.h, _ptr(pts), n, cols, n_pairs))
         self.n, self.cols, self.n_pairs = n, cols, n_pairs
 
     def points_set_device(self, dptr, n, cols, n_pairs=1):

@@ -92,6 +92,10 @@ gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes);
 /* Replaces the cv::Mat view the drivers build (py/gcransac_python.cpp:4274).  Copies host points to the device,
  * keeps the FP64 copy and derives the centred / power-of-two-scaled FP32 copies the scoring kernels stream. */
 gcr_status gcr_points_upload(gcr_ctx *ctx, const double *h_points, int n, int cols, int n_pairs);
+/* The same for a float32 host array -- what the reference's own tests hand to the Python entry points
+ * (tests/test_homography.py:52-60; pybind's py::array_t<double> widens it on the host, py/bindings.cpp:859-893): half the
+ * bytes cross PCIe and the exact widening to FP64 happens on the device. */
+gcr_status gcr_points_upload_f32(gcr_ctx *ctx, const float *h_points, int n, int cols, int n_pairs);
 /* Same, for points already resident in HBM (no copy; the caller keeps d_points alive). */
 gcr_status gcr_points_set_device(gcr_ctx *ctx, const double *d_points, int n, int cols, int n_pairs);
 /* per-pair normalisation the FP32 copy uses: out[8*pair + 0..4] = c1x c1y c2x c2y s (PnP: cu cv su cX cY cZ sX) */

@@ -210,3 +210,18 @@ def test_host_wrappers_keep_the_block_cache_consistent():
         assert st["in_use"] == 0 and st["blocks"] <= base["blocks"] + 8 and st["bytes"] <= base["bytes"] + (1 << 20), (base, st)
     finally:
         ctx.close()                                                     # a double free would fail here (compute-sanitizer clean)
+
+
+def test_float32_upload_equals_widened_float64_upload(gcr_ctx):
+    """gcr_points_upload_f32 (the float32 arrays the reference's tests pass; widened on the device) gives bit-identical
+    rounds to uploading the same values as float64 (pybind's host-side widening in the reference), batched pairs included."""
+    n_pairs, n = 6, 777
+    pts = np.stack([synth.homography_pair(n, 0.3, seed=s + 40)[0] for s in range(n_pairs)]).astype(np.float32)
+    gcr_ctx.points_upload(pts.astype(np.float64), n_pairs=n_pairs)
+    want = gcr_ctx.round(_cabi.H, _cabi.MSAC, _cabi.UNIFORM, 0, 512, seed=3, thr=3.0)
+    want_r = gcr_ctx.round_results()
+    gcr_ctx.points_upload_f32(pts, n_pairs=n_pairs)
+    got = gcr_ctx.round(_cabi.H, _cabi.MSAC, _cabi.UNIFORM, 0, 512, seed=3, thr=3.0)
+    got_r = gcr_ctx.round_results()
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
+    assert np.array_equal(want_r[0], got_r[0]) and np.array_equal(want_r[1], got_r[1])
