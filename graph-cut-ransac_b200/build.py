@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libgcr_b200.so")
+OUT = os.environ.get("GCR_LIB_OUT") or os.path.join(HERE, "libgcr_b200.so")   # GCR_LIB_OUT + GCR_NVCC_EXTRA: A/B variants
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-O3", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -34,7 +34,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + os.path.basename(OUT).replace(".so", "") if os.environ.get("GCR_LIB_OUT") else ""))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []

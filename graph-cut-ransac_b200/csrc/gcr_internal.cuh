@@ -3,6 +3,7 @@
 // (bit parity with the CPU build, which has no FMA contraction), and the FP32 hot loops state their FMAs
 // explicitly (fmaf / __ffma2_rn).
 #pragma once
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -105,6 +106,9 @@ struct gcr_ctx
 
 	double band_factor = 16.0; // FP32 error band in units of eps32 (normalised coordinates), see k_score.cu
 	int score_variant = -1;    // -1 auto; else forces a kernel variant (bench / tests)
+	std::vector<std::pair<const void *, int>> k3_occupancy; // scoring kernel -> resident CTAs per SM (queried once)
+	int tune_k3_ctas = 0;      // GCR_TUNE_K3_CTAS_PER_SM
+	int tune_round_prefetch = 1; // GCR_TUNE_ROUND_PREFETCH
 };
 
 #define GCR_CHECK_CUDA(ctx, expr)                                                                              \

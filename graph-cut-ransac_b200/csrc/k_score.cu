@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
 	__shared__ uint32_t s_last;
 	const int pair = blockIdx.y;
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+
 	const size_t g = (size_t)pair * a.k + slot;
 	const bool in_range = slot < a.k;
 	const bool ok = in_range && (a.valid == nullptr || a.valid[g] != 0);
@@ -334,6 +335,9 @@ template <bool SC> __device__ __forceinline__ float2 padd(float2 a, float2 b)
 }
 
 // u = r'^2 - t'^2 (MSAC) or r'^2 (MAGSAC) for two hypotheses side by side; point operands are duplicated pairs
+// (Tried for H and dropped: ONE MUFU.RCP of the product per packed pair, (1 / a, 1 / b) = (b, a) / (a b).  The XU pipe is not
+// what binds -- every instruction costs the scheduler dispatch cycles, and 1 MUFU + 3 FMUL is more of them than 2 MUFU:
+// h4k 0.571 -> 0.550 of FP32 peak.)
 template <int PROBLEM, int SCORING, bool SC = false>
 __device__ __forceinline__ float2 eval2(const float2 (&h)[9], const float2 X1, const float2 Y1, const float2 X2,
                                         const float2 Y2, const float2 NEGT)
@@ -488,8 +492,10 @@ __global__ void __launch_bounds__(THREADS, R >= 6 ? 4 : 5) k_score_main(const Sc
 		}
 
 		// ---- prologue: this thread's R hypotheses (compact order; a warp owns 32 R consecutive ones, lane = hypothesis) ----
-		const double *nm = a.norm + (size_t)pair * 8;
-		const Thresholds th = make_thresholds<PROBLEM, SCORING>(nm, a.thr, a.band_factor);
+		// (Hoisting this into k_score_prepare -- one 24-byte record per pair, loaded here -- was measured and dropped: the
+		// FP64 sqrt / divides overlap the first TMA tile in flight, while the dependent global load delayed every segment:
+		// K3 0.251 -> 0.277 ms on configs[1], 0.972 -> 0.984 ms on the batched workload, identical inner loops.)
+		const Thresholds th = make_thresholds<PROBLEM, SCORING>(a.norm + (size_t)pair * 8, a.thr, a.band_factor);
 		const int hyp0 = (int)(ht - a.prefix[pair]) * (THREADS * R) + warp * (32 * R) + lane; // + 32 * (HQ * q + e)
 		const float *mbase = a.m32 + (size_t)pair * a.k * ML;
 		// warps whose block of hypotheses lies beyond the pair's list idle through the segment; inside an active warp every
@@ -875,6 +881,7 @@ static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
 	};
 	const size_t o_head = take(sizeof(ScorePlan) + (size_t)a.n_pairs * sizeof(uint32_t)); // plan | counts: one memset
 	const size_t o_prefix = take(((size_t)a.n_pairs + 1) * sizeof(uint32_t));
+
 	const size_t o_slots = take(PK * sizeof(uint32_t));
 	const size_t o_m32 = take(PK * ml * sizeof(float));
 	const size_t o_accS = take(PK * sizeof(unsigned long long));
@@ -893,6 +900,7 @@ static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
 	a.plan = (ScorePlan *)(base + o_head);
 	a.counts = (uint32_t *)(base + o_head + sizeof(ScorePlan));
 	a.prefix = (uint32_t *)(base + o_prefix);
+
 	a.slots = (uint32_t *)(base + o_slots);
 	a.m32 = (float *)(base + o_m32);
 	a.accS = (unsigned long long *)(base + o_accS);
@@ -914,11 +922,22 @@ static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 	a.no_counts = !exact && a.inliers == nullptr ? 1 : 0;
 	auto kern = exact ? k_score_main<PROBLEM, SCORING, R, true, SC>
 	                  : (a.no_counts ? k_score_main<PROBLEM, SCORING, R, false, SC, false> : k_score_main<PROBLEM, SCORING, R, false, SC>);
-	GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	// the shared-memory opt-in and the occupancy query are per kernel, not per call (two driver calls on a path the
+	// pipelines take ~50 times per image pair)
 	int per_sm = 0;
-	GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-	if (per_sm < 1)
-		GCR_FAIL(ctx, GCR_ERR_CUDA, "gcr_score: scoring kernel does not fit on an SM");
+	for (const auto &e : ctx->k3_occupancy)
+		if (e.first == (const void *)kern)
+			per_sm = e.second;
+	if (per_sm == 0)
+	{
+		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+		if (per_sm < 1)
+			GCR_FAIL(ctx, GCR_ERR_CUDA, "gcr_score: scoring kernel does not fit on an SM");
+		ctx->k3_occupancy.push_back({(const void *)kern, per_sm});
+	}
+	if (ctx->tune_k3_ctas > 0 && per_sm > ctx->tune_k3_ctas)
+		per_sm = ctx->tune_k3_ctas;
 	a.grid = per_sm * ctx->sm_count;
 
 	const dim3 gslots((a.k + 255) / 256, a.n_pairs);

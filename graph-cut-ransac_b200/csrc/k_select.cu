@@ -88,6 +88,17 @@ extern "C" gcr_status gcr_set_score_trace(gcr_ctx *ctx, uint64_t *d_trace)
 	ctx->d_score_trace = (unsigned long long *)d_trace;
 	return GCR_OK;
 }
+extern "C" gcr_status gcr_set_tuning(gcr_ctx *ctx, int knob, int value)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	switch (knob)
+	{
+	case GCR_TUNE_K3_CTAS_PER_SM: ctx->tune_k3_ctas = value < 0 ? 0 : value; return GCR_OK;
+	case GCR_TUNE_ROUND_PREFETCH: ctx->tune_round_prefetch = value != 0; return GCR_OK;
+	default: GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_tuning: unknown knob %d", knob);
+	}
+}
 extern "C" gcr_status gcr_set_score_variant(gcr_ctx *ctx, int v)
 {
 	if (!ctx)

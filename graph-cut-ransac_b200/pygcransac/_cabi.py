@@ -9,13 +9,14 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libgcr_b200.so")
+LIB_PATH = os.environ.get("GCR_LIB_PATH") or os.path.join(_PKG, "libgcr_b200.so")   # GCR_LIB_PATH: A/B builds of the same ABI
 
 H, F, E, PNP = 0, 1, 2, 3
 MSAC, MAGSAC = 0, 1
 UNIFORM, PROSAC, IMPORTANCE = 0, 1, 2
 WEIGHT_NONE, WEIGHT_POSITIONAL, WEIGHT_BY_POINT = 0, 1, 2
 SCORE_EXACT_COUNTS = 1
+TUNE_K3_CTAS_PER_SM, TUNE_ROUND_PREFETCH = 0, 1
 
 # every symbol include/gcr/gcr.h declares (tests check the library exports all of them)
 BA_HARTLEY, BA_PIXEL = 1, 2
@@ -32,7 +33,7 @@ EXPORTS = [
     "gcr_memcpy_d2h_async", "gcr_radius_graph_count", "gcr_radius_graph_fill",
     "gcr_score_exact_pairs", "gcr_refit_pairs",
     "gcr_cache_stats", "gcr_round_winners", "gcr_comm_unique_id", "gcr_comm_init", "gcr_comm_destroy", "gcr_round_sharded",
-    "gcr_winners_reduce", "gcr_ubench_fp32", "gcr_points_upload_f32",
+    "gcr_winners_reduce", "gcr_ubench_fp32", "gcr_points_upload_f32", "gcr_set_tuning",
 ]
 
 
@@ -81,6 +82,7 @@ def load_library():
         "gcr_points_upload": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_upload_f32": (i32, [vp, vp, i32, i32, i32]),
+        "gcr_set_tuning": (i32, [vp, i32, i32]),
         "gcr_points_get_norm": (i32, [vp, vp]),
         "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
         "gcr_set_point_probabilities": (i32, [vp, vp, i32]),
@@ -218,6 +220,9 @@ class Context:
 
     def set_band_factor(self, f):
         self.check(self.lib.gcr_set_band_factor(self.h, f))
+
+    def set_tuning(self, knob, value):
+        self.check(self.lib.gcr_set_tuning(self.h, knob, value))
 
     def set_score_variant(self, v):
         self.check(self.lib.gcr_set_score_variant(self.h, v))

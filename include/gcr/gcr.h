@@ -56,6 +56,12 @@ uint64_t gcr_launch_count(const gcr_ctx *ctx);
 gcr_status gcr_set_band_factor(gcr_ctx *ctx, double factor);
 /* force a scoring-kernel variant (hypotheses per thread): -1 auto, 0 R=4, 1 R=6, 2 R=8 (PnP: 0 R=2, 1 R=4) */
 gcr_status gcr_set_score_variant(gcr_ctx *ctx, int variant);
+/* generic tuning knobs (experiments / benches; every knob has a sane default) */
+enum {
+	GCR_TUNE_K3_CTAS_PER_SM = 0, /* cap on the resident CTAs per SM of the scoring kernel (0 = as many as fit) */
+	GCR_TUNE_ROUND_PREFETCH = 1  /* gcr_round: solve the NEXT round's samples on a side stream while this round is scored (default 1) */
+};
+gcr_status gcr_set_tuning(gcr_ctx *ctx, int knob, int value);
 /* per-CTA timeline of the following K3 launches: d_trace (device, >= 4 * 148 * 8 uint64, or NULL to stop) receives per
  * CTA its SM id, first and last %globaltimer tick (ns) and the number of segments it ran (tools/k3_trace.py) */
 gcr_status gcr_set_score_trace(gcr_ctx *ctx, uint64_t *d_trace);
