@@ -294,7 +294,7 @@ def _pairs_cpu_worker(args):
         from pygcransac import synth
         npts = (pts - synth.SIZE / 2) / synth.FOCAL                              # K^-1 normalisation (utils.h:65-110)
         out = _CPU_IMPL["ref"].run(O.E, npts, cs, 4, thr / synth.FOCAL, conf=0.99, spatial_weight=weight, max_iters=max_iters,
-                                   min_iters=50, lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2 if magsac else 0)
+                                   min_iters=50, lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2 if magsac else 0, f_ba=4)
         return out["inliers"], out["stats"]["iterations"], time.perf_counter() - t0
     # F: the reference's default pipeline on both arms -- BA non-minimal solver, DEGENSAC, post-run bundle adjustment
     out = _CPU_IMPL["ref"].run(O.H if problem == "h" else O.F, pts, cs, 4, thr, conf=0.99, spatial_weight=weight,
@@ -471,7 +471,7 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
     # e2e for a batch of pairs: the pairs are independent, so the upload of one chunk of pairs overlaps the scoring of
     # the previous ones -- E2E_SIDE contexts (streams) take the chunks in turn (the user-level pattern for host-resident
     # batches); the FP32 upload entry point halves the bytes (the reference's own tests hand over float32 arrays)
-    E2E_CHUNKS, E2E_SIDE = 16, 4
+    E2E_CHUNKS, E2E_SIDE = args.e2e_chunks, args.e2e_streams
     overlap = n_pairs >= 8 * E2E_CHUNKS and not hyps_sharded
     use_f32 = overlap and args.upload == "f32"
     if overlap:
@@ -504,11 +504,7 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
                 keys_host.copy_(keys, non_blocking=True)
                 best_host.copy_(best, non_blocking=True)
             return ev
-        start = torch.cuda.Event()
-        start.record(stream)
         ev = 0
-        for c2, s2 in side:
-            s2.wait_event(start)
         for c in range(E2E_CHUNKS):
             c2, s2 = side[c % E2E_SIDE]
             lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
@@ -519,14 +515,24 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
                 tail(c2, lo, hi)
                 keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
                 best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
+        return ev
+
+    def step_e2e(i):
+        if not overlap:
+            return sum(round_e2e(i * rounds + r) for r in range(rounds))
+        # the side streams start after the step's start event and the step's end event waits for all of them; inside the
+        # step every stream works through its chunks of every round back to back (a chunk's buffers are only ever touched
+        # by its own stream, in order), so the upload of the next round's chunk overlaps the scoring of this round's
+        start = torch.cuda.Event()
+        start.record(stream)
+        for c2, s2 in side:
+            s2.wait_event(start)
+        ev = sum(round_e2e(i * rounds + r) for r in range(rounds))
         for c2, s2 in side:
             done = torch.cuda.Event()
             done.record(s2)
             stream.wait_event(done)
         return ev
-
-    def step_e2e(i):
-        return sum(round_e2e(i * rounds + r) for r in range(rounds))
 
     def timed(step_fn, first, nsteps):
         """nsteps steps, each bracketed by its own CUDA event pair on the launching stream; the L2 flush (a 256 MiB device
@@ -779,6 +785,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=0, help="rounds per step (default: workload's, sized for a >= 1 s timed region)")
     ap.add_argument("--variant", type=int, default=-1, help="force a K3 kernel variant (see gcr_set_score_variant)")
     ap.add_argument("--upload", default="f32", choices=["f32", "f64"], help="batched e2e leg: host array type handed to the C ABI")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="batched e2e leg: chunks of pairs per round")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="batched e2e leg: contexts / streams taking the chunks in turn")
     ap.add_argument("--exact-counts", action="store_true",
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")

@@ -346,3 +346,221 @@ extern "C" gcr_status gcr_radius_graph_fill(gcr_ctx *ctx, int pair, double radiu
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }
+
+// ------------------------------------------------------------------- labeling(): edge list + energy terms on the GPU ----
+// GCRANSAC::labeling (GCRANSAC.h:925-1020) walks point_idx ascending and, per point, its neighbour list ascending, adding
+// one pairwise term per unordered pair -- it remembers the pairs already used in an N x N matrix (`used_edges`, :963), the
+// reference's memory wall at N >> 10^4.  The pairs it ends up with are exactly (i, j > i) with j in i's list, in the order
+// (i ascending, j ascending): built here from K7's sorted cells (or the radius graph's CSR) by count -> scan -> fill, once
+// per run; per labeling call the unary terms and the pairwise weights come from the model's FP64 residuals in one pass.
+__global__ void __launch_bounds__(GT) k_edge_count_grid(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ cell_offsets,
+                                                        uint32_t n_cells, int n, uint32_t *__restrict__ counts)
+{
+	const int q = blockIdx.x * GT + threadIdx.x;
+	if (q >= n)
+		return;
+	uint32_t lo = 0, hi = n_cells; // cell_offsets[lo] <= q < cell_offsets[hi]
+	while (hi - lo > 1)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (cell_offsets[mid] <= (uint32_t)q) lo = mid;
+		else hi = mid;
+	}
+	// inside a cell the indices are ascending: the later entries of the cell are this point's partners j > i
+	counts[sorted_idx[q]] = cell_offsets[lo + 1] - (uint32_t)q - 1u;
+}
+
+__global__ void __launch_bounds__(GT) k_edge_fill_grid(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ cell_offsets,
+                                                       uint32_t n_cells, int n, const uint32_t *__restrict__ edge_offsets,
+                                                       uint32_t *__restrict__ edges)
+{
+	const int q = blockIdx.x * GT + threadIdx.x;
+	if (q >= n)
+		return;
+	uint32_t lo = 0, hi = n_cells;
+	while (hi - lo > 1)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (cell_offsets[mid] <= (uint32_t)q) lo = mid;
+		else hi = mid;
+	}
+	const uint32_t i = sorted_idx[q], end = cell_offsets[lo + 1];
+	uint32_t *out = edges + 2 * (size_t)edge_offsets[i];
+	for (uint32_t t = (uint32_t)q + 1; t < end; ++t)
+	{
+		*out++ = i;
+		*out++ = sorted_idx[t];
+	}
+}
+
+// CSR neighbour lists (ascending): the partners j > i of point i
+__global__ void __launch_bounds__(GT) k_edge_count_csr(const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ neighbors, int n,
+                                                       uint32_t *__restrict__ counts)
+{
+	const int i = blockIdx.x * GT + threadIdx.x;
+	if (i >= n)
+		return;
+	uint32_t c = 0;
+	for (uint32_t q = offsets[i]; q < offsets[i + 1]; ++q)
+		c += neighbors[q] > (uint32_t)i ? 1u : 0u;
+	counts[i] = c;
+}
+__global__ void __launch_bounds__(GT) k_edge_fill_csr(const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ neighbors, int n,
+                                                      const uint32_t *__restrict__ edge_offsets, uint32_t *__restrict__ edges)
+{
+	const int i = blockIdx.x * GT + threadIdx.x;
+	if (i >= n)
+		return;
+	uint32_t *out = edges + 2 * (size_t)edge_offsets[i];
+	for (uint32_t q = offsets[i]; q < offsets[i + 1]; ++q)
+		if (neighbors[q] > (uint32_t)i)
+		{
+			*out++ = (uint32_t)i;
+			*out++ = neighbors[q];
+		}
+}
+
+static gcr_status edges_common(gcr_ctx *ctx, const char *who, uint32_t *d_edge_offsets, uint32_t *d_edges, uint64_t capacity)
+{
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "%s: no points uploaded", who);
+	if (!d_edge_offsets || (!d_edges && capacity))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "%s: bad arguments", who);
+	if (capacity >= (1ull << 31))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "%s: more than 2^31 edges (a neighbourhood this dense is not a sparse graph)", who);
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_grid_edges(gcr_ctx *ctx, const uint32_t *d_sorted_idx, const uint32_t *d_cell_offsets, uint32_t n_cells,
+                                     uint32_t *d_edge_offsets, uint32_t *d_edges, uint64_t capacity)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	gcr_status st = edges_common(ctx, "gcr_grid_edges", d_edge_offsets, d_edges, capacity);
+	if (st)
+		return st;
+	if (!d_sorted_idx || !d_cell_offsets || n_cells == 0)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_grid_edges: bad arguments");
+	const int n = ctx->n, nb = (n + GT - 1) / GT;
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_edge_offsets + n, 0, sizeof(uint32_t), ctx->stream));
+	k_edge_count_grid<<<nb, GT, 0, ctx->stream>>>(d_sorted_idx, d_cell_offsets, n_cells, n, d_edge_offsets);
+	GCR_LAUNCHED(ctx);
+	k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(d_edge_offsets, (size_t)n + 1, nullptr);
+	GCR_LAUNCHED(ctx);
+	if (capacity)
+	{
+		k_edge_fill_grid<<<nb, GT, 0, ctx->stream>>>(d_sorted_idx, d_cell_offsets, n_cells, n, d_edge_offsets, d_edges);
+		GCR_LAUNCHED(ctx);
+	}
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_csr_edges(gcr_ctx *ctx, const uint32_t *d_offsets, const uint32_t *d_neighbors, uint32_t *d_edge_offsets,
+                                    uint32_t *d_edges, uint64_t capacity)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	gcr_status st = edges_common(ctx, "gcr_csr_edges", d_edge_offsets, d_edges, capacity);
+	if (st)
+		return st;
+	if (!d_offsets || (!d_neighbors && capacity))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_csr_edges: bad arguments");
+	const int n = ctx->n, nb = (n + GT - 1) / GT;
+	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_edge_offsets + n, 0, sizeof(uint32_t), ctx->stream));
+	k_edge_count_csr<<<nb, GT, 0, ctx->stream>>>(d_offsets, d_neighbors, n, d_edge_offsets);
+	GCR_LAUNCHED(ctx);
+	k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(d_edge_offsets, (size_t)n + 1, nullptr);
+	GCR_LAUNCHED(ctx);
+	if (capacity)
+	{
+		k_edge_fill_csr<<<nb, GT, 0, ctx->stream>>>(d_offsets, d_neighbors, n, d_edge_offsets, d_edges);
+		GCR_LAUNCHED(ctx);
+	}
+	return GCR_OK;
+}
+
+// unary terms: (to source, to sink) per point (GCRANSAC.h:933-957); dist = clamp(r^2 / T, 0, 1) kept for the pairwise pass
+template <int PROBLEM>
+__global__ void __launch_bounds__(GT) k_labeling_unary(const double *__restrict__ pts, int n, const double *__restrict__ model, double T,
+                                                       double one_minus_lambda, double *__restrict__ dist, double *__restrict__ unary)
+{
+	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	double M[ML];
+	for (int j = 0; j < ML; ++j) M[j] = model[j];
+	for (int i = blockIdx.x * GT + threadIdx.x; i < n; i += gridDim.x * GT)
+	{
+		double pt[COLS];
+		for (int j = 0; j < COLS; ++j) pt[j] = pts[(size_t)i * COLS + j];
+		const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+		const double d = r2 / T;
+		// utils::clamp; a NaN residual counts as a full-cost outlier (the reference would feed NaN capacities to the max-flow)
+		const double dc = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : (d == d ? d : 1.0));
+		dist[i] = dc;
+		const double tmp_energy = 1 - dc;
+		if (r2 <= T)
+		{
+			unary[2 * (size_t)i] = one_minus_lambda * tmp_energy;
+			unary[2 * (size_t)i + 1] = 0.0;
+		}
+		else
+		{
+			unary[2 * (size_t)i] = 0.0;
+			unary[2 * (size_t)i + 1] = one_minus_lambda * (1 - tmp_energy);
+		}
+	}
+}
+// pairwise weights e00 * lambda = 0.5 (dist_i + dist_j) * lambda (GCRANSAC.h:996-1003)
+__global__ void __launch_bounds__(GT) k_labeling_pairwise(const uint32_t *__restrict__ edges, size_t n_edges, const double *__restrict__ dist,
+                                                          double lambda, double *__restrict__ pairwise)
+{
+	for (size_t e = (size_t)blockIdx.x * GT + threadIdx.x; e < n_edges; e += (size_t)gridDim.x * GT)
+	{
+		const double e00 = 0.5 * (dist[edges[2 * e]] + dist[edges[2 * e + 1]]);
+		pairwise[e] = e00 * lambda;
+	}
+}
+
+extern "C" gcr_status gcr_labeling_terms(gcr_ctx *ctx, int problem, int pair, const double *d_model, double threshold, double lambda,
+                                         const uint32_t *d_edges, uint64_t n_edges, double *d_unary, double *d_pairwise,
+                                         double *d_dist)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_labeling_terms: no points uploaded");
+	if (!d_model || !d_unary || !(threshold > 0.0) || pair < 0 || pair >= ctx->n_pairs || (n_edges && d_pairwise && !d_edges))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_labeling_terms: bad arguments");
+	if (gcr_cols_of(problem) != ctx->cols)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_labeling_terms: problem / point columns mismatch");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int n = ctx->n;
+	double *dist = d_dist;
+	if (!dist)
+	{
+		gcr_status st = gcr_ensure_scratch(ctx, (size_t)n * sizeof(double));
+		if (st)
+			return st;
+		dist = (double *)ctx->d_scratch;
+	}
+	const double T = threshold * threshold * 9 / 4; // squared_truncated_threshold (GCRANSAC.h:929)
+	const double *pts = ctx->d_pts64 + (size_t)pair * n * ctx->cols;
+	int nb = (n + GT - 1) / GT;
+	if (nb > 8 * ctx->sm_count) nb = 8 * ctx->sm_count;
+	if (problem == GCR_H)
+		k_labeling_unary<GCR_H><<<nb, GT, 0, ctx->stream>>>(pts, n, d_model, T, 1.0 - lambda, dist, d_unary);
+	else if (problem == GCR_PNP)
+		k_labeling_unary<GCR_PNP><<<nb, GT, 0, ctx->stream>>>(pts, n, d_model, T, 1.0 - lambda, dist, d_unary);
+	else
+		k_labeling_unary<GCR_F><<<nb, GT, 0, ctx->stream>>>(pts, n, d_model, T, 1.0 - lambda, dist, d_unary);
+	GCR_LAUNCHED(ctx);
+	if (n_edges && d_pairwise)
+	{
+		size_t eb = (n_edges + GT - 1) / GT;
+		if (eb > (size_t)16 * ctx->sm_count) eb = (size_t)16 * ctx->sm_count;
+		k_labeling_pairwise<<<(unsigned)eb, GT, 0, ctx->stream>>>(d_edges, (size_t)n_edges, dist, lambda, d_pairwise);
+		GCR_LAUNCHED(ctx);
+	}
+	return GCR_OK;
+}

@@ -34,6 +34,7 @@
 #include "gcr_internal.cuh"
 
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 #define TILE 256
@@ -1041,6 +1042,17 @@ gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double 
 	default: return GCR_DISPATCH(GCR_F); // F and E share the Sampson residual
 	}
 #undef GCR_DISPATCH
+}
+
+// FP64 re-check evaluations the LAST gcr_score call of this context could not queue (work list full): queued read-back,
+// delivered by the next gcr_sync.  Non-zero means that call's GCR_SCORE_EXACT_COUNTS counts are not exact.
+extern "C" gcr_status gcr_score_dropped_async(gcr_ctx *ctx, uint32_t *h_dropped)
+{
+	if (!ctx || !h_dropped)
+		return GCR_ERR_ARG;
+	if (!ctx->d_score_ws)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_score_dropped_async: gcr_score has not run on this context");
+	return gcr_memcpy_d2h_async(ctx, h_dropped, (const char *)ctx->d_score_ws + offsetof(ScorePlan, amb_dropped), sizeof(uint32_t));
 }
 
 extern "C" gcr_status gcr_score_host(gcr_ctx *ctx, int problem, int scoring, const double *h_models,

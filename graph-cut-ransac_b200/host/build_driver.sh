@@ -7,7 +7,13 @@
 set -e
 cd "$(dirname "$0")"
 REF=${GCR_REFERENCE_DIR:-/root/reference}/src/pygcransac/include
-if [ ! -f "$REF/energy.h" ]; then echo "reference tree not present; skipping host/_ref/libgcr_driver.so"; exit 0; fi
+if [ ! -f "$REF/energy.h" ]; then
+  # no reference tree (the GPU box): the prebuilt driver must have travelled with the snapshot -- fail loudly otherwise, the
+  # Python / C++ entry points cannot work without it (the min-cut is the reference's own Boykov-Kolmogorov code, north star)
+  if [ -f _ref/libgcr_driver.so ]; then echo "reference tree not present; using the prebuilt host/_ref/libgcr_driver.so"; exit 0; fi
+  echo "ERROR: $REF/energy.h not found and no prebuilt host/_ref/libgcr_driver.so: set GCR_REFERENCE_DIR to a checkout of danini/graph-cut-ransac" >&2
+  exit 1
+fi
 if [ ! -f ../libgcr_b200.so ]; then echo "build libgcr_b200.so first (python graph-cut-ransac_b200/build.py)"; exit 1; fi
 mkdir -p _ref
 g++ -O2 -DNDEBUG -std=c++17 -w -fPIC -shared -ffp-contract=off -I"$REF" -I../../include -I. \

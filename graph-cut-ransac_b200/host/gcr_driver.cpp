@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -163,6 +164,13 @@ namespace
 		// radius neighbourhood (S.neighborhood == 1): CSR, neighbours ascending
 		std::vector<uint32_t> nbr_offsets, nbr_idx;
 		bool have_radius_graph = false;
+		// labeling()'s pairwise structure: every unordered pair of neighbours once, (i, j > i), i ascending then j ascending
+		// -- enumerated once per run (on the GPU from the grid cells / radius CSR when those were built there), kept on both
+		// sides: the device copy feeds gcr_labeling_terms, the host copy the max-flow graph
+		std::vector<uint32_t> edges; // [n_edges][2]
+		size_t n_edges = 0;
+		DeviceBuffer d_edges, d_edge_offsets, d_unary, d_pairwise, d_lab_model;
+		std::vector<double> h_unary, h_pairwise;
 
 		bool fail(const char *what)
 		{
@@ -489,10 +497,26 @@ namespace
 				if (gcr_memcpy_d2h_async(ctx, h_samples.data(), d_samples.p, (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
 					return fail("gcr_memcpy_d2h");
 			}
+			uint32_t dropped = 0;
 			if (gcr_memcpy_d2h_async(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
 			    gcr_memcpy_d2h_async(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK || gcr_sync(ctx) != GCR_OK)
+			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_score_dropped_async(ctx, &dropped) != GCR_OK || gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
+			if (dropped)
+			{
+				// the FP64 re-check list overflowed (N x batch very large): these counts feed the inlier-container bookkeeping
+				// (lazy_count, the size check before IRLS), so they must be exact -- the same samples again, half at a time
+				// (a sample is a function of its index: batch boundaries change no result)
+				if (B <= 1)
+				{
+					error = "gcr_score: the FP64 re-check list overflows for a single sample";
+					return false;
+				}
+				B = (B + 1) / 2;
+				h_model_have.clear();
+				return run_batch(first);
+			}
 			batch_first = first;
 			batch_count = B;
 			++st.gpu_batches;
@@ -570,66 +594,44 @@ namespace
 			return exact(model, s, &inliers);
 		}
 
-		// ---- GCRANSAC::labeling (GCRANSAC.h:913-1021): unary terms from GPU residuals, BK min-cut on the host ----
+		// ---- GCRANSAC::labeling (GCRANSAC.h:913-1021): the energy terms on the GPU (unary from the model's FP64
+		// residuals, pairwise over the run's edge list: gcr_labeling_terms), the BK min-cut on the host ----
 		bool labeling(const double *model, std::vector<uint32_t> &inliers)
 		{
-			Score s;
-			std::vector<double> r2;
-			if (!exact(model, s, nullptr, &r2))
-				return false;
-			const auto t0 = std::chrono::steady_clock::now();
 			const double lambda = S.spatial_coherence_weight;
+			const size_t E = lambda > 0 ? n_edges : 0;
+			// pairwise weights: 8 bytes per edge read back from the device kernel when the graph came from the device anyway
+			// (n > 16384), else formed here from the per-point clamped distances (24 n bytes come back instead of 16 n + 8 E)
+			static const bool force_device_pairwise = getenv("GCR_DEVICE_PAIRWISE") != nullptr;
+			const bool device_pairwise = E > 0 && (n > 16384 || force_device_pairwise);
+			if (!d_lab_model.ensure(ctx, 9 * sizeof(double)) || !d_unary.ensure(ctx, (size_t)n * 3 * sizeof(double)) ||
+			    !d_pairwise.ensure(ctx, std::max<size_t>(device_pairwise ? E : 0, 1) * sizeof(double)))
+				return fail("gcr_malloc");
+			h_unary.resize((size_t)n * 3); // [n][2] capacities, then [n] clamped distances
+			h_pairwise.resize(device_pairwise ? E : 0);
+			double *d_dist = d_unary.as<double>() + 2 * (size_t)n;
+			if (gcr_memcpy_h2d(ctx, d_lab_model.p, model, 9 * sizeof(double)) != GCR_OK)
+				return fail("gcr_memcpy_h2d");
+			if (gcr_labeling_terms(ctx, problem, 0, d_lab_model.as<double>(), S.threshold, lambda, d_edges.as<uint32_t>(), E,
+			                       d_unary.as<double>(), device_pairwise ? d_pairwise.as<double>() : nullptr, d_dist) != GCR_OK)
+				return fail("gcr_labeling_terms");
+			if (gcr_memcpy_d2h_async(ctx, h_unary.data(), d_unary.p, (size_t)n * 3 * sizeof(double)) != GCR_OK ||
+			    (device_pairwise && gcr_memcpy_d2h_async(ctx, h_pairwise.data(), d_pairwise.p, E * sizeof(double)) != GCR_OK) ||
+			    gcr_sync(ctx) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			++st.exact_rescores; // (one FP64 pass over the points, as the residual read-back it replaces)
+			const auto t0 = std::chrono::steady_clock::now();
+			const double *dist = h_unary.data() + 2 * (size_t)n;
 			Energy<double, double, double> *problem_graph = new Energy<double, double, double>(n, 0, NULL);
 			for (int i = 0; i < n; ++i)
 				problem_graph->add_node();
-			std::vector<double> distance_per_threshold(n);
-			const double squared_truncated_threshold = S.threshold * S.threshold * 9 / 4;
-			const double one_minus_lambda = 1.0 - lambda;
 			for (int i = 0; i < n; ++i)
+				problem_graph->add_term1(i, h_unary[2 * (size_t)i], h_unary[2 * (size_t)i + 1]);
+			for (size_t e = 0; e < E; ++e)
 			{
-				const double d = r2[i] / squared_truncated_threshold;
-				// utils::clamp; a NaN residual (NaN / inf coordinates in the input) counts as a full-cost outlier -- the
-				// reference would feed NaN capacities to the max-flow (its assert(B + C >= 0), energy.h:228, or worse)
-				distance_per_threshold[i] = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : (d == d ? d : 1.0));
-				const double tmp_energy = 1 - distance_per_threshold[i];
-				if (r2[i] <= squared_truncated_threshold)
-					problem_graph->add_term1(i, one_minus_lambda * tmp_energy, 0);
-				else
-					problem_graph->add_term1(i, 0, one_minus_lambda * (1 - tmp_energy));
-			}
-			if (lambda > 0 && have_radius_graph)
-			{
-				// every unordered pair of neighbours once (the reference's used_edges matrix, :963, does the same for its lists)
-				for (int i = 0; i < n; ++i)
-				{
-					const double energy1 = distance_per_threshold[i];
-					for (uint32_t q = nbr_offsets[i]; q < nbr_offsets[i + 1]; ++q)
-					{
-						const uint32_t j = nbr_idx[q];
-						if ((int)j <= i)
-							continue;
-						const double e00 = 0.5 * (energy1 + distance_per_threshold[j]);
-						problem_graph->add_term2(i, j, e00 * lambda, lambda, lambda, 0 * lambda);
-					}
-				}
-			}
-			else if (lambda > 0 && have_grid)
-			{
-				// the reference walks point_idx ascending and, per point, its cell's list ascending, skipping pairs already
-				// used (the N x N used_edges matrix, :963): exactly the pairs (i, j > i) of a cell, in this order
-				for (int i = 0; i < n; ++i)
-				{
-					const uint32_t c = cell_of_point[i];
-					const double energy1 = distance_per_threshold[i];
-					for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
-					{
-						const uint32_t j = sorted_idx[q];
-						if ((int)j <= i)
-							continue;
-						const double e00 = 0.5 * (energy1 + distance_per_threshold[j]);
-						problem_graph->add_term2(i, j, e00 * lambda, lambda, lambda, 0 * lambda);
-					}
-				}
+				const uint32_t i = edges[2 * e], j = edges[2 * e + 1];
+				const double w = device_pairwise ? h_pairwise[e] : 0.5 * (dist[i] + dist[j]) * lambda; // e00 * lambda (:996-1003)
+				problem_graph->add_term2((int)i, (int)j, w, lambda, lambda, 0 * lambda);
 			}
 			problem_graph->minimize();
 			inliers.clear();
@@ -638,6 +640,29 @@ namespace
 					inliers.push_back((uint32_t)i);
 			delete problem_graph;
 			st.graph_cut_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			return true;
+		}
+
+		// the run's edge list from a host-side structure (grids / radius graphs of up to 16384 points are built on the host)
+		bool upload_edges()
+		{
+			n_edges = edges.size() / 2;
+			if (n_edges == 0)
+				return true;
+			if (!d_edges.ensure(ctx, edges.size() * sizeof(uint32_t)))
+				return fail("gcr_malloc");
+			// (larger than the pinned ring when the neighbourhood is dense: gcr_memcpy_h2d then copies synchronously)
+			if (gcr_memcpy_h2d(ctx, d_edges.p, edges.data(), edges.size() * sizeof(uint32_t)) != GCR_OK)
+				return fail("gcr_memcpy_h2d");
+			return true;
+		}
+		// ... or built on the device next to the structure it comes from; the host keeps a copy for the max-flow graph
+		bool fetch_edges(uint64_t count)
+		{
+			n_edges = (size_t)count;
+			edges.resize(2 * n_edges);
+			if (n_edges && gcr_memcpy_d2h(ctx, edges.data(), d_edges.p, edges.size() * sizeof(uint32_t)) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
 			return true;
 		}
 
@@ -898,7 +923,7 @@ namespace
 		{
 			have_radius_graph = false;
 			DeviceBuffer dc, doff, dn;
-			if (!dc.ensure(ctx, (size_t)n * 4) || !doff.ensure(ctx, (size_t)n * 4))
+			if (!dc.ensure(ctx, (size_t)n * 4) || !doff.ensure(ctx, ((size_t)n + 1) * 4))
 				return fail("gcr_malloc");
 			if (gcr_radius_graph_count(ctx, 0, S.neighborhood_radius, dc.as<uint32_t>()) != GCR_OK)
 				return fail("gcr_radius_graph_count");
@@ -906,21 +931,42 @@ namespace
 			if (gcr_memcpy_d2h(ctx, counts.data(), dc.p, (size_t)n * 4) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			nbr_offsets.assign((size_t)n + 1, 0u);
+			uint64_t total64 = 0;
 			for (int i = 0; i < n; ++i)
-				nbr_offsets[i + 1] = nbr_offsets[i] + counts[i];
-			const size_t total = nbr_offsets[n];
+			{
+				total64 += counts[i];
+				nbr_offsets[i + 1] = (uint32_t)total64;
+			}
+			if (total64 >= (1ull << 31))
+			{
+				// (a radius this large against the point spread is not a sparse neighbourhood: the reference's own N x N edge
+				// matrix would not fit either)
+				error = "neighborhood_radius gives more than 2^31 neighbour entries: choose a smaller radius";
+				return false;
+			}
+			const size_t total = (size_t)total64;
 			nbr_idx.resize(total);
 			if (total)
 			{
 				if (!dn.ensure(ctx, total * 4))
 					return fail("gcr_malloc");
-				if (gcr_memcpy_h2d(ctx, doff.p, nbr_offsets.data(), (size_t)n * 4) != GCR_OK)
+				if (gcr_memcpy_h2d(ctx, doff.p, nbr_offsets.data(), ((size_t)n + 1) * 4) != GCR_OK)
 					return fail("gcr_memcpy_h2d");
 				if (gcr_radius_graph_fill(ctx, 0, S.neighborhood_radius, doff.as<uint32_t>(), dn.as<uint32_t>()) != GCR_OK)
 					return fail("gcr_radius_graph_fill");
+				// labeling()'s edges (i, j > i) straight from the CSR on the device (the distance test is symmetric: half the entries)
+				if (!d_edge_offsets.ensure(ctx, ((size_t)n + 1) * 4) || !d_edges.ensure(ctx, std::max<size_t>(total / 2, 1) * 8))
+					return fail("gcr_malloc");
+				if (gcr_csr_edges(ctx, doff.as<uint32_t>(), dn.as<uint32_t>(), d_edge_offsets.as<uint32_t>(), d_edges.as<uint32_t>(),
+				                  total / 2) != GCR_OK)
+					return fail("gcr_csr_edges");
 				if (gcr_memcpy_d2h(ctx, nbr_idx.data(), dn.p, total * 4) != GCR_OK)
 					return fail("gcr_memcpy_d2h");
+				if (!fetch_edges(total / 2))
+					return false;
 			}
+			else
+				n_edges = 0;
 			have_radius_graph = true;
 			return true;
 		}
@@ -1004,7 +1050,19 @@ namespace
 				sorted_idx.swap(g.sorted_idx);
 				cell_offsets.swap(g.cell_offsets);
 				have_grid = true;
-				return true;
+				// the pairs (i, j > i) of every cell, i ascending, the cell's list ascending: once per run
+				edges.clear();
+				for (int i = 0; i < n; ++i)
+				{
+					const uint32_t c = cell_of_point[i];
+					for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
+						if ((int)sorted_idx[q] > i)
+						{
+							edges.push_back((uint32_t)i);
+							edges.push_back(sorted_idx[q]);
+						}
+				}
+				return upload_edges();
 			}
 			DeviceBuffer dk, ds, dof;
 			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
@@ -1024,7 +1082,18 @@ namespace
 				for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
 					cell_of_point[sorted_idx[q]] = c;
 			have_grid = true;
-			return true;
+			// labeling()'s edge list from the sorted cells, on the device (neighbor_number = sum over cells of s (s - 1) / 2)
+			if (neighbor_number >= (1ull << 31))
+			{
+				error = "the grid neighbourhood has more than 2^31 point pairs: use more cells per axis";
+				return false;
+			}
+			if (!d_edge_offsets.ensure(ctx, ((size_t)n + 1) * 4) || !d_edges.ensure(ctx, std::max<size_t>((size_t)neighbor_number, 1) * 8))
+				return fail("gcr_malloc");
+			if (gcr_grid_edges(ctx, ds.as<uint32_t>(), dof.as<uint32_t>(), n_cells, d_edge_offsets.as<uint32_t>(), d_edges.as<uint32_t>(),
+			                   neighbor_number) != GCR_OK)
+				return fail("gcr_grid_edges");
+			return fetch_edges(neighbor_number);
 		}
 
 		// ---- GCRANSAC::run ----
@@ -1317,6 +1386,60 @@ namespace
 					}
 				}
 			}
+			if (problem == GCR_E && !nested && S.e_bundle_adjustment && buf[offset].idx.size() > 5)
+			{
+				// the post-run bundle adjustment of findEssentialMatrix_ (py/gcransac_python.cpp:2766-2821): weights 1 - r^2 / T by
+				// inlier POSITION, EssentialMatrixBundleAdjustmentSolver on the inliers (gcr_refit_e_ba: Stewenius -> poses -> LM),
+				// every model it returns scored by an MSAC scoring function of the driver's own, in order, strict '<'
+				std::vector<uint32_t> &inl = buf[offset].idx;
+				std::vector<double> r2, weights(inl.size(), 0.0);
+				Score s;
+				if (!exact(best_model, s, nullptr, &r2))
+					return -1;
+				for (size_t k = 0; k < inl.size(); ++k)
+					weights[k] = std::max(0.0, 1.0 - r2[inl[k]] / T);
+				const int R = gcr_max_e_ba_models();
+				if (!d_sets.ensure(ctx, inl.size() * sizeof(uint32_t)) || !d_weights.ensure(ctx, std::max(inl.size(), (size_t)n) * sizeof(double)) ||
+				    !d_lmodels.ensure(ctx, (size_t)R * 9 * sizeof(double)) || !d_lok.ensure(ctx, (size_t)R))
+				{
+					fail("gcr_malloc");
+					return -1;
+				}
+				std::vector<double> models((size_t)R * 9);
+				std::vector<uint8_t> ok(R);
+				if (gcr_memcpy_h2d(ctx, d_sets.p, inl.data(), inl.size() * sizeof(uint32_t)) != GCR_OK ||
+				    gcr_memcpy_h2d(ctx, d_weights.p, weights.data(), inl.size() * sizeof(double)) != GCR_OK ||
+				    gcr_refit_e_ba(ctx, 0, d_sets.as<uint32_t>(), (uint32_t)inl.size(), d_weights.as<double>(), d_lmodels.as<double>(),
+				                   d_lok.as<uint8_t>()) != GCR_OK ||
+				    gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, models.size() * sizeof(double)) != GCR_OK ||
+				    gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, ok.size()) != GCR_OK || gcr_sync(ctx) != GCR_OK)
+				{
+					fail("gcr_refit_e_ba");
+					return -1;
+				}
+				const int run_scoring = scoring;
+				scoring = GCR_MSAC; // (:2797-2798, whatever scoring function the run was instantiated with)
+				for (int q = 0; q < R; ++q)
+				{
+					if (!ok[q])
+						continue;
+					const int idx2 = (offset + 1) % 2;
+					Score cur;
+					buf[idx2].lazy = false;
+					if (!exact(&models[(size_t)q * 9], cur, &buf[idx2].idx))
+					{
+						scoring = run_scoring;
+						return -1;
+					}
+					if (st.score < cur.value) // :2813
+					{
+						memcpy(best_model, &models[(size_t)q * 9], 9 * sizeof(double));
+						st.score = cur.value;
+						offset = idx2;
+					}
+				}
+				scoring = run_scoring;
+			}
 			for (uint32_t i : buf[offset].idx)
 				inlier_mask[i] = 1;
 			memcpy(model_out, best_model, sizeof(best_model));
@@ -1355,6 +1478,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->point_probabilities = nullptr;
 	s->sampler_variance = 0.1;
 	s->scoring = GCR_MSAC;
+	s->e_bundle_adjustment = 0;
 	for (int d = 0; d < 4; ++d)
 		s->image_sizes[d] = 0.0;
 }

@@ -74,6 +74,9 @@ typedef struct gcr_run_settings
 	/* the scoring function GCRANSAC<> is instantiated with: GCR_MSAC (MSACScoringFunction, the default template argument
 	 * and what every Python entry point uses) or GCR_MAGSAC (MAGSACScoringFunction, scoring_function.h:237-349) */
 	int scoring;
+	/* E: the post-run relative-pose bundle adjustment of findEssentialMatrix_ (py/gcransac_python.cpp:2766-2821;
+	 * gcr_refit_e_ba) -- 0 = off (GCRANSAC<>::run alone), 1 = on (what the Python entry point does) */
+	int e_bundle_adjustment;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats
@@ -98,9 +101,9 @@ void gcr_run_settings_default(gcr_run_settings *s);
 int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,
                    double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
 
-/* findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855) without its final LM bundle-adjustment polish (SURVEY 8f
- * N2): the neighbourhood grid is built on the pixel coordinates, the run uses K^-1-normalised points and
- * settings->threshold / mean focal length.  K1, K2: row-major 3 x 3 intrinsics.  model_out: E, 9 doubles. */
+/* findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855): the neighbourhood grid is built on the pixel coordinates, the
+ * run uses K^-1-normalised points and settings->threshold / mean focal length; with settings->e_bundle_adjustment its
+ * final relative-pose bundle adjustment on the inliers (:2766-2821).  K1, K2: row-major 3 x 3 intrinsics.  model_out: E. */
 int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, const double *K1, const double *K2,
                        const gcr_run_settings *settings, double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);
 

@@ -98,6 +98,7 @@ namespace gcr_api
 		s.max_iteration_number = (uint64_t)max_iters;
 		s.min_iteration_number = (uint64_t)min_iters;
 		s.max_local_optimization_number = (uint64_t)lo_number;
+		s.e_bundle_adjustment = problem == GCR_E ? 1 : 0; // findEssentialMatrix_ ends with its relative-pose BA (py/gcransac_python.cpp:2766-2821)
 		const size_t cells = static_cast<size_t>(neighborhood_size);
 		s.cells_per_axis = cells > 0 ? cells : 1;
 		const double eps = problem == GCR_H ? std::numeric_limits<double>::epsilon() : 0.0;

@@ -44,7 +44,8 @@ class RunSettings(C.Structure):
                 ("do_final_iterated_least_squares", C.c_int), ("cell_sizes", C.c_double * 4),
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
                 ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
-                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4), ("scoring", C.c_int)]
+                ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4), ("scoring", C.c_int),
+                ("e_bundle_adjustment", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -95,7 +96,7 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
           neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0,
-          probabilities=(), sampler_variance=0.1, scoring=0):
+          probabilities=(), sampler_variance=0.1, scoring=0, e_bundle_adjustment=0):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
     min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
@@ -141,6 +142,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
     s.sampler_variance = float(sampler_variance)
     s.scoring = int(scoring)
+    s.e_bundle_adjustment = int(e_bundle_adjustment)
     for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
         s.image_sizes[i] = float(v)
     model = np.zeros(9)
@@ -200,11 +202,11 @@ def findFundamentalMatrix(correspondences, h1, w1, h2, w2, probabilities=(), thr
 def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
                         spatial_coherence_weight=0.1, max_iters=10000, min_iters=50, use_sprt=True,
                         min_inlier_ratio_for_sprt=0.01, sampler=1, neighborhood=1, neighborhood_size=20.0, lo_number=50,
-                        sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0):
+                        sampler_variance=0.1, solver=0, seed=1, device=0, scoring=0, bundle_adjustment=True):
     """py/bindings.cpp:710-857, 1091-1112 -> findEssentialMatrix_ (py/gcransac_python.cpp:2519-2855): 5-point (Nister)
     minimal solver, Stewenius non-minimal refits, MSAC on the K-normalised points with threshold / mean focal length,
-    grid neighbourhood on the pixel coordinates.  Without the reference's final LM bundle-adjustment polish
-    (out of scope) -- the returned E is GC-RANSAC's own result."""
+    grid neighbourhood on the pixel coordinates, and the final relative-pose bundle adjustment on the inliers
+    (:2766-2821; gcr_refit_e_ba).  `bundle_adjustment=False` (not a reference argument) returns GC-RANSAC's own result."""
     if solver != 0:
         raise NotImplementedError("solver=%d: only point correspondences (solver 0) are on this path" % solver)
     K1 = np.ascontiguousarray(K1, dtype=np.float64)
@@ -215,7 +217,8 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
         raise ValueError("K2 shape should be [3x3]")
     return _find(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters,
                  min_iters, sampler, neighborhood, neighborhood_size, lo_number, False, seed, device, intrinsics=(K1, K2),
-                 probabilities=probabilities, sampler_variance=sampler_variance, scoring=scoring)
+                 probabilities=probabilities, sampler_variance=sampler_variance, scoring=scoring,
+                 e_bundle_adjustment=1 if bundle_adjustment else 0)
 
 
 def find6DPose(x1y1, x2y2z2, probabilities=(), threshold=0.001, conf=0.99, spatial_coherence_weight=0.975, max_iters=10000,

@@ -34,6 +34,8 @@ EXPORTS = [
     "gcr_score_exact_pairs", "gcr_refit_pairs",
     "gcr_cache_stats", "gcr_round_winners", "gcr_comm_unique_id", "gcr_comm_init", "gcr_comm_destroy", "gcr_round_sharded",
     "gcr_winners_reduce", "gcr_ubench_fp32", "gcr_points_upload_f32", "gcr_set_tuning",
+    "gcr_grid_edges", "gcr_csr_edges", "gcr_labeling_terms", "gcr_score_dropped_async",
+    "gcr_refit_e_ba", "gcr_max_e_ba_models",
 ]
 
 
@@ -83,6 +85,12 @@ def load_library():
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_upload_f32": (i32, [vp, vp, i32, i32, i32]),
         "gcr_set_tuning": (i32, [vp, i32, i32]),
+        "gcr_score_dropped_async": (i32, [vp, vp]),
+        "gcr_refit_e_ba": (i32, [vp, i32, vp, u32, vp, vp, vp]),
+        "gcr_max_e_ba_models": (i32, []),
+        "gcr_grid_edges": (i32, [vp, vp, vp, u32, vp, vp, u64]),
+        "gcr_csr_edges": (i32, [vp, vp, vp, vp, vp, u64]),
+        "gcr_labeling_terms": (i32, [vp, i32, i32, vp, f64, f64, vp, u64, vp, vp, vp]),
         "gcr_points_get_norm": (i32, [vp, vp]),
         "gcr_sample": (i32, [vp, i32, i32, u64, i32, u64, vp]),
         "gcr_set_point_probabilities": (i32, [vp, vp, i32]),
@@ -454,6 +462,23 @@ class Context:
             if d_w:
                 self.free(d_w)
 
+    def refit_e_ba(self, index_set, weights=None, pair=0):
+        """gcr_refit_e_ba: the relative-pose bundle adjustment on one index set; (models [40, 3, 3], ok [40])."""
+        idx = np.ascontiguousarray(index_set, dtype=np.uint32)
+        d_idx = self.to_device(idx)
+        d_w = None if weights is None else self.to_device(np.ascontiguousarray(weights, dtype=np.float64))
+        R = self.lib.gcr_max_e_ba_models()
+        dm, dok = self.malloc(R * 72), self.malloc(R)
+        try:
+            self.check(self.lib.gcr_refit_e_ba(self.h, pair, C.c_void_p(d_idx), len(idx), C.c_void_p(d_w) if d_w else None,
+                                               C.c_void_p(dm), C.c_void_p(dok)))
+            return self.to_host(dm, (R, 3, 3), np.float64), self.to_host(dok, (R,), np.uint8)
+        finally:
+            for d in (d_idx, dm, dok):
+                self.free(d)
+            if d_w:
+                self.free(d_w)
+
     # ---- K7 ----
     def grid_build(self, cell_sizes, cells_per_axis, pair=0):
         cs = np.ascontiguousarray(cell_sizes, dtype=np.float64)
@@ -468,6 +493,56 @@ class Context:
                         neighbor_number=nn.value)
         finally:
             for d in (dk, ds, do):
+                self.free(d)
+
+    def grid_edges(self, cell_sizes, cells_per_axis, pair=0):
+        """labeling()'s edge list of the grid neighbourhood, built on the device: (edges [E, 2], edge_offsets [n + 1])."""
+        cs = np.ascontiguousarray(cell_sizes, dtype=np.float64)
+        n = self.n
+        dk, ds, do, deo = self.malloc(n * 8), self.malloc(n * 4), self.malloc((n + 1) * 4), self.malloc((n + 1) * 4)
+        nc, nn = C.c_uint32(), C.c_uint64()
+        de = None
+        try:
+            self.check(self.lib.gcr_grid_build(self.h, pair, _ptr(cs), cells_per_axis, C.c_void_p(dk), C.c_void_p(ds),
+                                               C.c_void_p(do), C.byref(nc), C.byref(nn)))
+            de = self.malloc(max(nn.value, 1) * 8)
+            self.check(self.lib.gcr_grid_edges(self.h, C.c_void_p(ds), C.c_void_p(do), nc.value, C.c_void_p(deo), C.c_void_p(de),
+                                               nn.value))
+            return self.to_host(de, (nn.value, 2), np.uint32), self.to_host(deo, (n + 1,), np.uint32)
+        finally:
+            for d in (dk, ds, do, deo, de):
+                if d:
+                    self.free(d)
+
+    def csr_edges(self, offsets, neighbors):
+        """labeling()'s edge list of a CSR neighbourhood (radius graph): the (i, j > i) entries, on the device."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        neighbors = np.ascontiguousarray(neighbors, dtype=np.uint32)
+        E = len(neighbors) // 2
+        do, dn = self.to_device(offsets), self.to_device(neighbors if len(neighbors) else np.zeros(1, np.uint32))
+        deo, de = self.malloc((self.n + 1) * 4), self.malloc(max(E, 1) * 8)
+        try:
+            self.check(self.lib.gcr_csr_edges(self.h, C.c_void_p(do), C.c_void_p(dn), C.c_void_p(deo), C.c_void_p(de), E))
+            return self.to_host(de, (E, 2), np.uint32), self.to_host(deo, (self.n + 1,), np.uint32)
+        finally:
+            for d in (do, dn, deo, de):
+                self.free(d)
+
+    def labeling_terms(self, problem, model, thr, lam, edges, pair=0):
+        """(unary [n, 2], pairwise [E]) of labeling()'s energy for one model."""
+        ml = self.lib.gcr_model_len(problem)
+        edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+        E = len(edges)
+        dm = self.to_device(np.ascontiguousarray(model, dtype=np.float64).reshape(ml))
+        de = self.to_device(edges if E else np.zeros((1, 2), np.uint32))
+        du, dp, dd = self.malloc(self.n * 16), self.malloc(max(E, 1) * 8), self.malloc(self.n * 8)
+        try:
+            self.check(self.lib.gcr_labeling_terms(self.h, problem, pair, C.c_void_p(dm), thr, lam, C.c_void_p(de), E,
+                                                   C.c_void_p(du), C.c_void_p(dp), C.c_void_p(dd)))
+            return (self.to_host(du, (self.n, 2), np.float64), self.to_host(dp, (E,), np.float64),
+                    self.to_host(dd, (self.n,), np.float64))
+        finally:
+            for d in (dm, de, du, dp, dd):
                 self.free(d)
 
     def radius_graph(self, radius, pair=0):

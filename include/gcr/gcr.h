@@ -158,6 +158,10 @@ int gcr_model_len(int problem);
  * d_scores [n_pairs][k] float, d_inliers [n_pairs][k] uint32 (may be NULL). */
 gcr_status gcr_score(gcr_ctx *ctx, int problem, int scoring, const double *d_models, const uint8_t *d_valid,
                      int k, double threshold, int flags, float *d_scores, uint32_t *d_inliers);
+/* GCR_SCORE_EXACT_COUNTS queues its FP64 re-checks in a bounded work list (4 Mi entries); what did not fit in the LAST
+ * gcr_score call of the context is reported here (a queued read-back: valid after the next gcr_sync).  Non-zero = that
+ * call's counts are not exact -- score fewer models per call. */
+gcr_status gcr_score_dropped_async(gcr_ctx *ctx, uint32_t *h_dropped);
 /* The same arithmetic in FP64, reference operation order, for a few models of pair `pair`: exact score, exact
  * inlier count and (optionally) the ascending inlier index list -- the side output of getScore
  * (scoring_function.h:166-167).  d_inlier_idx: [k][n] uint32 or NULL; d_residuals: [k][n] FP64 or NULL. */
@@ -220,6 +224,17 @@ gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_inde
 gcr_status gcr_refit_f_ba(gcr_ctx *ctx, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
                           const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode, int frame,
                           double *d_models, uint8_t *d_ok);
+/* EssentialMatrixBundleAdjustmentSolver::estimateModel (estimators/solver_essential_matrix_bundle_adjustment.h:113-186), the
+ * post-run polish of findEssentialMatrix_ (py/gcransac_python.cpp:2766-2821), on ONE index set of pair `pair`: the
+ * Stewenius non-minimal fit (up to 10 models) -> motion_from_essential + cheirality on the set's first point
+ * (relative_pose/essential.cpp:44-117: up to 4 poses each) -> the 5-dof LM of refine_relpose (relative_pose/bundle.cpp
+ * :176-250, Sampson error, TruncatedLoss(1.0), <= 25 iterations) -> E = [t]_x R.  d_weights: one weight per set ENTRY (by
+ * position: what the reference's driver fills and its LM accumulator reads; its Stewenius initialiser indexes the same
+ * vector by point, past its end -- here position everywhere) or NULL.  d_models [40][9], d_ok [40] in the order the
+ * reference emits them (initial model major, then pose); sets of fewer than 6 points: every ok = 0. */
+gcr_status gcr_refit_e_ba(gcr_ctx *ctx, int pair, const uint32_t *d_index_set, uint32_t set_size, const double *d_weights,
+                          double *d_models, uint8_t *d_ok);
+int gcr_max_e_ba_models(void); /* 40 */
 /* one non-minimal fit per pair, all pairs in one launch: set p = the first d_sizes[p] entries of d_index_sets[p][n],
  * fitted to pair p's points (H: homography_estimator.h:136-173; F: 8-point, fundamental_estimator.h:574-618) */
 gcr_status gcr_refit_pairs(gcr_ctx *ctx, int problem, const uint32_t *d_index_sets, const uint32_t *d_sizes,
@@ -241,6 +256,25 @@ gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell_sizes[4], 
  * the exclusive prefix of the counts, d_neighbors receives every point's neighbours in ascending index order. */
 gcr_status gcr_radius_graph_count(gcr_ctx *ctx, int pair, double radius, uint32_t *d_counts);
 gcr_status gcr_radius_graph_fill(gcr_ctx *ctx, int pair, double radius, const uint32_t *d_offsets, uint32_t *d_neighbors);
+
+/* The pairwise structure of GCRANSAC::labeling (GCRANSAC.h:963-1008) on the device: every unordered pair of points that
+ * share a grid cell (gcr_grid_edges, from gcr_grid_build's outputs) or are radius neighbours (gcr_csr_edges, from the
+ * CSR of gcr_radius_graph_*: d_offsets [n + 1]), once, as (i, j > i) in the order the reference visits them -- i
+ * ascending, j ascending -- without its N x N `used_edges` matrix.  d_edge_offsets [n + 1] receives the first edge of
+ * every point (its last entry = the edge count, which equals gcr_grid_build's neighbor_number / half the CSR length);
+ * d_edges [capacity][2] uint32, capacity >= that count (capacity 0: offsets only).  No host synchronisation. */
+gcr_status gcr_grid_edges(gcr_ctx *ctx, const uint32_t *d_sorted_idx, const uint32_t *d_cell_offsets, uint32_t n_cells,
+                          uint32_t *d_edge_offsets, uint32_t *d_edges, uint64_t capacity);
+gcr_status gcr_csr_edges(gcr_ctx *ctx, const uint32_t *d_offsets, const uint32_t *d_neighbors, uint32_t *d_edge_offsets,
+                         uint32_t *d_edges, uint64_t capacity);
+/* The energy terms of labeling() for one model of pair `pair` (d_model: device, 9 | 12 doubles): d_unary [n][2] = the
+ * (source, sink) capacities of add_term1 (GCRANSAC.h:933-957, truncation at (1.5 threshold)^2), d_pairwise [n_edges] =
+ * e00 * lambda of add_term2 for every edge of d_edges (:996-1003; the other three terms are lambda, lambda, 0), or NULL;
+ * d_dist [n] = clamp(r^2 / T, 0, 1) per point, or NULL (a caller that feeds a host max-flow can form e00 = 0.5 (dist_i +
+ * dist_j) while it adds the edge instead of reading 8 bytes per edge back).  The min-cut itself stays with the
+ * reference's Boykov-Kolmogorov solver on the host. */
+gcr_status gcr_labeling_terms(gcr_ctx *ctx, int problem, int pair, const double *d_model, double threshold, double lambda,
+                              const uint32_t *d_edges, uint64_t n_edges, double *d_unary, double *d_pairwise, double *d_dist);
 
 /* ---- fused fixed-K round (the benchmarked step) ------------------------------------------------------------ */
 /* One pass of the hot path over every pair on the context: K1 sample `count` minimal samples -> K2 solve -> K3

@@ -133,6 +133,9 @@ int gcro_solve_e5_stewenius(const double *pts, const uint32_t *sample, int n, co
 int gcro_refit_e(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
 /* essential_estimator.h:152-175 estimateModel = nister + orientation filter (:338-401) */
 int gcro_estimate_e5(const double *pts, const uint32_t *sample, double *E90);
+/* relative-pose bundle adjustment (gcr_oracle_eba.cpp): solver_essential_matrix_bundle_adjustment.h:113-186 */
+int gcro_refine_e_lm(const double *pts, const uint32_t *sample, int n, const double *weights, const double *E9, double *out36);
+int gcro_polish_e_ba(const double *pts, int n_points, const uint32_t *inliers, int n, const double *weights, double *out360);
 /* utils.h:65-110 normalizeCorrespondences: K^-1 on both images (K row-major 3x3) */
 void gcro_normalize_correspondences(const double *pts, int n, const double *K1, const double *K2, double *out);
 

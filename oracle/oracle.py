@@ -298,6 +298,30 @@ class Oracle:
         cnt = self.lib.gcro_refit_e(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data, out)
         return out[: cnt * 9].reshape(cnt, 3, 3).copy()
 
+    def refine_e_lm(self, pts, sample, E, weights=None):
+        """motion_from_essential (cheirality on sample[0]) + the 5-dof LM of refine_relpose for every surviving pose:
+        refined essential matrices [cnt <= 4, 3, 3].  weights: by position in `sample`."""
+        out = np.empty(36)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self.lib.gcro_refine_e_lm.restype = C.c_int
+        self.lib.gcro_refine_e_lm.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp, _dp]
+        cnt = self.lib.gcro_refine_e_lm(_as_pts(pts), s, len(s), None if w is None else w.ctypes.data,
+                                        np.ascontiguousarray(E, dtype=np.float64).reshape(9), out)
+        return out[: cnt * 9].reshape(cnt, 3, 3).copy()
+
+    def polish_e_ba(self, pts, inliers, weights=None):
+        """The post-run BA of findEssentialMatrix_ (EssentialMatrixBundleAdjustmentSolver::estimateModel on the inliers):
+        models [cnt <= 40, 3, 3].  weights: by position in `inliers`."""
+        out = np.empty(360)
+        p = _as_pts(pts)
+        s = np.ascontiguousarray(inliers, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self.lib.gcro_polish_e_ba.restype = C.c_int
+        self.lib.gcro_polish_e_ba.argtypes = [_dp, C.c_int, _u32p, C.c_int, C.c_void_p, _dp]
+        cnt = self.lib.gcro_polish_e_ba(p, len(p), s, len(s), None if w is None else w.ctypes.data, out)
+        return out[: cnt * 9].reshape(cnt, 3, 3).copy()
+
     def colpiv_q(self, A):
         A = np.ascontiguousarray(A, dtype=np.float64)
         Q = np.empty_like(A)

@@ -969,11 +969,54 @@ namespace
 					}
 				}
 			}
+		if constexpr (PROBLEM == GCRO_E)
+			if (f_ba & 4)
+			{
+				// the post-run bundle adjustment of findEssentialMatrix_ (py/gcransac_python.cpp:2766-2821): weights 1 - r^2 / T by
+				// inlier position, EssentialMatrixBundleAdjustmentSolver on the normalised points (restated:
+				// gcr_oracle_eba.cpp), every returned model scored by the reference's own MSAC in order; fewer than six
+				// inliers: the identity (:2822-2823)
+				if (st.inliers.size() > 5)
+				{
+					const double truncated_threshold = 3.0 / 2.0 * threshold;
+					const double squared_truncated_threshold = truncated_threshold * truncated_threshold;
+					const size_t inlier_number = st.inliers.size();
+					std::vector<double> weights(inlier_number, 0.0);
+					std::vector<uint32_t> inl(inlier_number);
+					for (size_t k = 0; k < inlier_number; ++k)
+					{
+						inl[k] = (uint32_t)st.inliers[k];
+						weights[k] = MAX(0, 1.0 - estimator.squaredResidual(points.row((int)st.inliers[k]), model) / squared_truncated_threshold);
+					}
+					double polished[360];
+					const int n_models = gcro_polish_e_ba(reinterpret_cast<const double *>(points.data), points.rows, inl.data(),
+					                                      (int)inlier_number, weights.data(), polished);
+					MSACScoringFunction<Est> scoring;
+					scoring.initialize(squared_truncated_threshold, points.rows);
+					for (int q = 0; q < n_models; ++q)
+					{
+						Model tmp_model = from_flat(polished + 9 * q, 3, 3);
+						std::vector<size_t> current_inliers;
+						Score score = scoring.getScore(points, tmp_model, estimator, squared_truncated_threshold, current_inliers);
+						if (st.score < score.value)
+						{
+							model.descriptor = tmp_model.descriptor;
+							st.score = score.value;
+							st.inliers.swap(current_inliers);
+						}
+					}
+				}
+				else
+				{
+					const double identity[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+					model = from_flat(identity, 3, 3);
+				}
+			}
 		for (int i = 0; i < points.rows; ++i)
 			inlier_mask[i] = 0;
 		for (size_t idx : st.inliers)
 			inlier_mask[idx] = 1;
-		if (st.inliers.size() > 0)
+		if (st.inliers.size() > 0 || (PROBLEM == GCRO_E && (f_ba & 4)))
 			to_flat(model.descriptor, model_out);
 		if (stats_out)
 		{

@@ -125,7 +125,7 @@ def test_magsac_scoring_pipeline_matches_reference_run(pyg, ref, oracle):
         npts = oracle.normalize_correspondences(pts, K, K)
         thr = 0.75 / (0.25 * (K[0, 0] + K[1, 1] + K[0, 0] + K[1, 1]))
         want = ref.run(O.E, npts, np.array([256.0] * 4), 4, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50,
-                       lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2)
+                       lo_number=50, seed=seed, grid_pts=pts, scoring_kind=2, f_ba=4)
         assert st["iteration_number"] == want["stats"]["iterations"], (seed, st, want["stats"])
         assert st["lo_samples"] == want["stats"]["lo_samples"]
         assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
@@ -278,7 +278,7 @@ def test_findessential_matches_reference_run(pyg, ref, oracle):
         cs = np.array([1024 / 4.0] * 4)
         thr = 0.75 / (0.25 * (K[0, 0] + K[1, 1] + K[0, 0] + K[1, 1]))          # py/gcransac_python.cpp:2624-2626, 2737
         want = ref.run(O.E, npts, cs, 4, thr, conf=0.99, spatial_weight=weight, max_iters=10000, min_iters=50, lo_number=50,
-                       seed=seed, grid_pts=pts)
+                       seed=seed, grid_pts=pts, f_ba=4)
         assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
         assert st["graph_cut_number"] == want["stats"]["graph_cuts"]
         assert st["lo_samples"] == want["stats"]["lo_samples"]

@@ -77,7 +77,7 @@ def test_find_essential_matrix(pyg, ref, oracle):
     cs = np.array([w1 / cells, h1 / cells, w2 / cells, h2 / cells])
     thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
     want = ref.run(O.E, npts, cs, cells, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50,
-                   seed=1, grid_pts=pts.astype(np.float64), sampler=1)
+                   seed=1, grid_pts=pts.astype(np.float64), sampler=1, f_ba=4)
     assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
     assert st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2, (int(mask.sum()), int(want["mask"].sum()))
@@ -97,7 +97,7 @@ def test_find_essential_matrix_default_arguments(pyg, ref, oracle):
     npts = oracle.normalize_correspondences(pts.astype(np.float64), K1, K2)
     thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
     want = ref.run(O.E, npts, np.ones(4), 20, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50,
-                   seed=1, grid_pts=pts.astype(np.float64), sampler=1, radius=20.0)
+                   seed=1, grid_pts=pts.astype(np.float64), sampler=1, radius=20.0, f_ba=4)
     assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
     assert st["graph_cut_number"] == want["stats"]["graph_cuts"] and st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
@@ -156,7 +156,7 @@ def test_reference_calls_with_their_own_samplers(pyg, ref, oracle):
     npts = oracle.normalize_correspondences(pts.astype(np.float64), K1, K2)
     thr = 0.75 / (0.25 * (K1[0, 0] + K1[1, 1] + K2[0, 0] + K2[1, 1]))
     want = ref.run(O.E, npts, np.ones(4), 20, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50,
-                   seed=1, grid_pts=pts.astype(np.float64), sampler=4, radius=20.0, probabilities=prob, sampler_variance=0.1)
+                   seed=1, grid_pts=pts.astype(np.float64), sampler=4, radius=20.0, probabilities=prob, sampler_variance=0.1, f_ba=4)
     assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
     assert st["lo_samples"] == want["stats"]["lo_samples"]
     assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5
@@ -179,7 +179,7 @@ def test_essential_with_progressive_napsac_and_importance_sampler(pyg, ref, orac
                                           max_iters=5000, sampler=sampler, neighborhood=0, neighborhood_size=float(cells), seed=2)
         st = pyg.last_statistics
         want = ref.run(O.E, npts, cs, cells, thr, conf=0.99, spatial_weight=0.1, max_iters=5000, min_iters=50, lo_number=50, seed=2,
-                       grid_pts=pts.astype(np.float64), sampler=sampler, probabilities=prob, image_sizes=(w1, h1, w2, h2))
+                       grid_pts=pts.astype(np.float64), sampler=sampler, probabilities=prob, image_sizes=(w1, h1, w2, h2), f_ba=4)
         assert st["iteration_number"] == want["stats"]["iterations"], (sampler, st, want["stats"])
         assert st["lo_samples"] == want["stats"]["lo_samples"]
         assert (mask != want["mask"]).sum() <= 2 and _up_to_scale(want["model"], E) < 1e-5, sampler

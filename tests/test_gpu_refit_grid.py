@@ -222,3 +222,72 @@ def test_radius_graph_bit_exact(gcr_ctx, ref):
         assert np.array_equal(np.nonzero(A)[1].astype(np.uint32), nbr) and len(nbr) > 0
     with pytest.raises(_cabi.GcrError):
         gcr_ctx.radius_graph(0.0)
+
+
+def _grid_edges_numpy(key):
+    """labeling()'s pairs: for i ascending, the points j > i of i's cell, ascending (GCRANSAC.h:963-1008 with the grid);
+    `key` = the reference's cell key per point (points outside the image can share a key across cells: kept as it is)."""
+    edges = []
+    members = {}
+    for i in range(len(key)):
+        members.setdefault(int(key[i]), []).append(int(i))
+    for i in range(len(key)):
+        for j in members[int(key[i])]:
+            if j > i:
+                edges.append((i, j))
+    return np.array(edges, dtype=np.uint32).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("n", [700, 20000])
+def test_grid_edge_list_matches_reference_order(gcr_ctx, oracle, n):
+    """gcr_grid_edges: every unordered pair of one cell once, (i, j > i), i ascending then j ascending -- the pairs and the
+    order the reference's labeling() produces with its N x N used_edges matrix."""
+    pts = synth.homography_pair(n, 0.3, seed=8)[0]
+    gcr_ctx.points_upload(pts)
+    cs = np.array([synth.SIZE / 8] * 4)
+    edges, off = gcr_ctx.grid_edges(cs, 8)
+    want = _grid_edges_numpy(oracle.grid_build(pts, cs, 8)["keys"])
+    assert np.array_equal(edges, want)
+    assert off[-1] == len(want) and np.array_equal(np.diff(off.astype(np.int64)), np.bincount(want[:, 0], minlength=n))
+
+
+def test_csr_edge_list_and_labeling_terms(gcr_ctx, oracle):
+    """gcr_csr_edges over the radius graph, and gcr_labeling_terms: unary / pairwise capacities bit-identical to the host
+    statement of GCRANSAC.h:933-1003 on the oracle's FP64 residuals."""
+    pts, Hm, _ = synth.homography_pair(1500, 0.3, seed=9)
+    gcr_ctx.points_upload(pts)
+    offsets, nbrs = gcr_ctx.radius_graph(40.0)
+    edges, eoff = gcr_ctx.csr_edges(offsets, nbrs)
+    want = np.array([(i, j) for i in range(len(pts)) for j in nbrs[offsets[i]:offsets[i + 1]] if j > i], dtype=np.uint32).reshape(-1, 2)
+    assert len(want) > 1000 and np.array_equal(edges, want) and eoff[-1] == len(want)
+    thr, lam = 2.0, 0.975
+    unary, pairwise, dist = gcr_ctx.labeling_terms(_cabi.H, Hm, thr, lam, edges)
+    r2 = oracle.residuals(O.H, pts, Hm)
+    T = thr * thr * 9 / 4
+    d = np.clip(r2 / T, 0.0, 1.0)
+    tmp = 1 - d
+    src = np.where(r2 <= T, (1.0 - lam) * tmp, 0.0)
+    snk = np.where(r2 <= T, 0.0, (1.0 - lam) * (1 - tmp))
+    assert np.array_equal(unary[:, 0], src) and np.array_equal(unary[:, 1], snk)
+    assert np.array_equal(pairwise, 0.5 * (d[want[:, 0]] + d[want[:, 1]]) * lam) and np.array_equal(dist, d)
+
+
+def test_refit_e_bundle_adjustment_matches_oracle(gcr_ctx, oracle):
+    """gcr_refit_e_ba (post-run polish of findEssentialMatrix_: Stewenius -> motion_from_essential + cheirality -> 5-dof LM)
+    against the oracle restatement: the same models in the same slots, <= 1e-6 up to scale (tolerance 1e-5), with and
+    without weights; fewer than 6 points: nothing."""
+    px, Fm, Em, Kc, inl = synth.epipolar_pair(900, 0.3, seed=44)
+    pts = oracle.normalize_correspondences(px, Kc, Kc)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(3)
+    idx = np.nonzero(inl)[0].astype(np.uint32)
+    for weights in (None, rng.uniform(0.1, 1.0, size=len(idx))):
+        got, ok = gcr_ctx.refit_e_ba(idx, weights)
+        want = oracle.polish_e_ba(pts, idx, weights)
+        assert ok.sum() == len(want) and len(want) >= 1
+        for M, Wm in zip(got[ok.astype(bool)], want):
+            assert _up_to_scale(Wm, M) < 1e-6, _up_to_scale(Wm, M)
+        Et = Em / np.linalg.norm(Em)
+        assert min(_up_to_scale(Et, M) for M in got[ok.astype(bool)]) < 5e-3
+    got, ok = gcr_ctx.refit_e_ba(idx[:5])
+    assert not ok.any()

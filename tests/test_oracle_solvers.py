@@ -280,3 +280,60 @@ def test_f_bundle_adjustment_against_scipy(oracle):
     # (the Hartley normalisation sees the moved points, so the frames differ: compare the fits on the weighted points)
     ra, rb = _sampson_residuals(Fa, pts[:100]), _sampson_residuals(Fb, pts[:100])
     assert abs((ra ** 2).sum() - (rb ** 2).sum()) < 0.05 * (ra ** 2).sum()
+
+
+def test_e_bundle_adjustment_against_scipy(oracle):
+    """relative_pose/bundle.cpp:176-250 (lm_5dof_impl) + jacobian_impl.h:307-460 + essential.cpp:44-117 restated
+    (oracle/gcr_oracle_eba.cpp); pinned against an independent scipy least-squares minimisation of the same Sampson cost over
+    essential matrices [t]_x R (rotation vector + translation), started from the oracle's result."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    px, Fm, Em, Kc, _ = synth.epipolar_pair(500, 0.0, seed=33, sigma=0.8)
+    pts = oracle.normalize_correspondences(px, Kc, Kc)
+    idx = np.arange(200, dtype=np.uint32)
+    init = oracle.refit_e(pts, idx)
+    assert len(init) >= 1
+    costs0 = [(_sampson_residuals(E, pts[:200]) ** 2).sum() for E in init]
+    E0 = init[int(np.argmin(costs0))]
+    refined = oracle.refine_e_lm(pts, idx, E0)
+    assert 1 <= len(refined) <= 4
+    costs = [(_sampson_residuals(E, pts[:200]) ** 2).sum() for E in refined]
+    E1 = refined[int(np.argmin(costs))]
+    assert min(costs) <= min(costs0) * (1 + 1e-12)
+    # an essential matrix by construction: two equal singular values, one zero
+    sv = np.linalg.svd(E1, compute_uv=False)
+    assert abs(sv[0] - sv[1]) < 1e-9 * sv[0] and sv[2] < 1e-12 * sv[0]
+    # scipy from the oracle's optimum: E = [t]_x R with R = exp(w) R1 and t on the sphere
+    U, s, Vt = np.linalg.svd(E1)
+    W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    best = None
+    for R1 in (U @ W @ Vt, U @ W.T @ Vt):
+        R1 = R1 * np.sign(np.linalg.det(R1))
+        for t1 in (U[:, 2], -U[:, 2]):
+            tx = np.array([[0, -t1[2], t1[1]], [t1[2], 0, -t1[0]], [-t1[1], t1[0], 0]])
+            Ec = tx @ R1
+            err = min(np.abs(Ec / np.linalg.norm(Ec) - E1 / np.linalg.norm(E1)).max(),
+                      np.abs(Ec / np.linalg.norm(Ec) + E1 / np.linalg.norm(E1)).max())
+            if best is None or err < best[0]:
+                best = (err, R1, t1)
+    assert best[0] < 1e-9
+    _, R1, t1 = best
+
+    def unpack(x):
+        R = Rotation.from_rotvec(x[:3]).as_matrix() @ R1
+        t = t1 + x[3:6]
+        return np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+
+    sol = least_squares(lambda x: _sampson_residuals(unpack(x), pts[:200]), np.zeros(6), xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    assert (sol.fun ** 2).sum() >= min(costs) * (1 - 1e-6)                  # the LM result is a stationary point
+    G = unpack(sol.x)
+    assert min(np.abs(G / np.linalg.norm(G) - E1 / np.linalg.norm(E1)).max(),
+               np.abs(G / np.linalg.norm(G) + E1 / np.linalg.norm(E1)).max()) < 1e-4
+    # ... close to the ground truth, and the whole post-run polish returns it among its models
+    Et = Em / np.linalg.norm(Em)
+    assert min(np.abs(E1 / np.linalg.norm(E1) - Et).max(), np.abs(E1 / np.linalg.norm(E1) + Et).max()) < 5e-3
+    w = np.linspace(1.0, 0.2, len(idx))
+    models = oracle.polish_e_ba(pts, idx, weights=w)
+    assert 1 <= len(models) <= 40
+    assert min(min(np.abs(M / np.linalg.norm(M) - Et).max(), np.abs(M / np.linalg.norm(M) + Et).max()) for M in models) < 5e-3
+    assert len(oracle.polish_e_ba(pts, idx[:5])) == 0                       # sampleSize() of the BA solver is 6
