@@ -151,6 +151,11 @@ gcr_status gcr_score_fused(gcr_ctx *ctx, int problem, int scoring, const double 
 gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, uint64_t first_index, int count, uint64_t seed,
                                        double *d_models, uint8_t *d_valid);
 
+// K6 for GCR_PNP (k_refit_pnp.cu): normalised DLT + the LM of refine_pnp, one CTA per index set
+gcr_status gcr_refit_pnp_launch(gcr_ctx *ctx, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
+                                const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode, double *d_models,
+                                uint8_t *d_ok);
+
 static inline int gcr_cols_of(int problem) { return problem == GCR_PNP ? 5 : 4; }
 
 // ---- device helpers -------------------------------------------------------------------------------------------

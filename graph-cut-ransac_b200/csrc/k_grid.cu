@@ -272,18 +272,24 @@ extern "C" gcr_status gcr_grid_build(gcr_ctx *ctx, int pair, const double h_cell
 // handle at all (its edge bookkeeping is an N x N matrix, GCRANSAC.h:963).  One thread per point, the other points
 // staged through shared memory; pass 1 counts, pass 2 writes the neighbours in ascending index order (CSR).
 #define RG_THREADS 256
-template <bool FILL>
+// COLS = 4 (correspondences) or 5 (2D-3D matches of find6DPose_: FlannNeighborhoodGraph over the whole 5-column row,
+// py/gcransac_python.cpp:1090-1092)
+struct RgPoint { float v[5]; };
+template <bool FILL, int COLS>
 __global__ void __launch_bounds__(RG_THREADS) k_radius_graph(const double *__restrict__ pts, int n, float r2,
                                                              uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ neighbors)
 {
-	__shared__ float4 tile[RG_THREADS];
+	__shared__ RgPoint tile[RG_THREADS];
 	const int i = blockIdx.x * RG_THREADS + threadIdx.x;
-	float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+	RgPoint me;
+#pragma unroll
+	for (int c = 0; c < 5; ++c) me.v[c] = 0.f;
 	if (i < n)
 	{
-		const double *p = pts + (size_t)i * 4;
-		me = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]); // convertTo(CV_32F) (:115)
+		const double *p = pts + (size_t)i * COLS;
+#pragma unroll
+		for (int c = 0; c < COLS; ++c) me.v[c] = (float)p[c]; // convertTo(CV_32F) (:115)
 	}
 	uint32_t found = 0;
 	uint32_t *out = FILL && i < n ? neighbors + offsets[i] : nullptr;
@@ -292,17 +298,25 @@ __global__ void __launch_bounds__(RG_THREADS) k_radius_graph(const double *__res
 		const int j = j0 + threadIdx.x;
 		if (j < n)
 		{
-			const double *p = pts + (size_t)j * 4;
-			tile[threadIdx.x] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+			const double *p = pts + (size_t)j * COLS;
+			RgPoint o;
+#pragma unroll
+			for (int c = 0; c < 5; ++c) o.v[c] = c < COLS ? (float)p[c < COLS ? c : 0] : 0.f;
+			tile[threadIdx.x] = o;
 		}
 		__syncthreads();
 		const int m = min(RG_THREADS, n - j0);
 		if (i < n)
 			for (int q = 0; q < m; ++q)
 			{
-				const float4 o = tile[q];
-				const float dx = me.x - o.x, dy = me.y - o.y, dz = me.z - o.z, dw = me.w - o.w;
-				const float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+				const RgPoint o = tile[q];
+				const float dx = me.v[0] - o.v[0], dy = me.v[1] - o.v[1], dz = me.v[2] - o.v[2], dw = me.v[3] - o.v[3];
+				float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+				if (COLS == 5)
+				{
+					const float dv = me.v[4] - o.v[4];
+					d2 = d2 + dv * dv;
+				}
 				if (d2 < r2 && j0 + q != i) // RadiusResultSet keeps dist < radius; the query point itself is dropped (:131-133)
 				{
 					if (FILL) out[found] = (uint32_t)(j0 + q);
@@ -319,14 +333,18 @@ extern "C" gcr_status gcr_radius_graph_count(gcr_ctx *ctx, int pair, double radi
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
-	if (!ctx->d_pts64 || ctx->n == 0 || ctx->cols != 4)
-		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_count: no 4-column points uploaded");
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_count: no points uploaded");
 	if (pair < 0 || pair >= ctx->n_pairs || !d_counts || !(radius > 0.0))
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_radius_graph_count: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	const float r = (float)radius;
-	k_radius_graph<false><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
-	    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, d_counts, nullptr, nullptr);
+	if (ctx->cols == 5)
+		k_radius_graph<false, 5><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+		    ctx->d_pts64 + (size_t)pair * ctx->n * 5, ctx->n, r * r, d_counts, nullptr, nullptr);
+	else
+		k_radius_graph<false, 4><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+		    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, d_counts, nullptr, nullptr);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }
@@ -335,14 +353,18 @@ extern "C" gcr_status gcr_radius_graph_fill(gcr_ctx *ctx, int pair, double radiu
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
-	if (!ctx->d_pts64 || ctx->n == 0 || ctx->cols != 4)
-		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_fill: no 4-column points uploaded");
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_radius_graph_fill: no points uploaded");
 	if (pair < 0 || pair >= ctx->n_pairs || !d_offsets || !d_neighbors || !(radius > 0.0))
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_radius_graph_fill: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	const float r = (float)radius;
-	k_radius_graph<true><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
-	    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, nullptr, d_offsets, d_neighbors);
+	if (ctx->cols == 5)
+		k_radius_graph<true, 5><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+		    ctx->d_pts64 + (size_t)pair * ctx->n * 5, ctx->n, r * r, nullptr, d_offsets, d_neighbors);
+	else
+		k_radius_graph<true, 4><<<(ctx->n + RG_THREADS - 1) / RG_THREADS, RG_THREADS, 0, ctx->stream>>>(
+		    ctx->d_pts64 + (size_t)pair * ctx->n * 4, ctx->n, r * r, nullptr, d_offsets, d_neighbors);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }

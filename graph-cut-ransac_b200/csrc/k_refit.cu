@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a)
 
 extern "C" int gcr_max_refit_models(int problem)
 {
-	return problem == GCR_E ? RF_E_MODELS : (problem == GCR_H || problem == GCR_F) ? 1 : 0;
+	return problem == GCR_E ? RF_E_MODELS : (problem == GCR_H || problem == GCR_F || problem == GCR_PNP) ? 1 : 0;
 }
 
 static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets,
@@ -986,13 +986,15 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 		return GCR_ERR_ARG;
 	if (!ctx->d_pts64 || ctx->n == 0)
 		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_refit: no points uploaded");
-	if (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F && problem != GCR_E))
-		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: non-minimal refits exist for H, F (8-point) and E (Stewenius) on 4-column points");
+	if (problem == GCR_PNP ? ctx->cols != 5 : (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F && problem != GCR_E)))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: non-minimal refits exist for H, F (8-point), E (Stewenius) on 4-column points and PnP (DLT + LM) on 5-column points");
 	if (pair < 0 || pair >= ctx->n_pairs || count <= 0 || !d_index_sets || !d_set_offsets || !d_set_sizes || !d_models || !d_ok)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: bad arguments");
 	if (d_weights && weight_mode != GCR_WEIGHT_POSITIONAL && weight_mode != GCR_WEIGHT_BY_POINT)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit: weights given but weight_mode is %d", weight_mode);
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (problem == GCR_PNP)
+		return gcr_refit_pnp_launch(ctx, pair, d_index_sets, d_set_offsets, d_set_sizes, count, d_weights, weight_mode, d_models, d_ok);
 	RefitArgs a;
 	a.pts = ctx->d_pts64 + (size_t)pair * ctx->n * 4;
 	a.sets = d_index_sets;

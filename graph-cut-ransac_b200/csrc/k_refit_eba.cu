@@ -54,32 +54,54 @@ __device__ double sqn(const double *v) { return v[0] * v[0] + v[1] * v[1] + v[2]
 // Eigen::Quaterniond(R) + normalize (CameraPose::rotmat_to_quat, relative_pose/bundle.h:35-41); q = (w, x, y, z)
 __device__ void rotmat_to_quat(const double *R, double *q)
 {
-	double t = R[0] + R[4] + R[8];
-	double w, v[3];
-	if (t > 0.0)
+	// Eigen::Quaterniond(R) (QuaternionBase::operator=(MatrixBase), quaternionbase_assign_impl<Other, 3, 3>) + normalize();
+	// the three cases of its largest-diagonal branch written out (no runtime-indexed local array)
+	const double trace = R[0] + R[4] + R[8];
+	double w, x, y, z;
+	if (trace > 0.0)
 	{
-		t = sqrt(t + 1.0);
+		double t = sqrt(trace + 1.0);
 		w = 0.5 * t;
 		t = 0.5 / t;
-		v[0] = (R[7] - R[5]) * t;
-		v[1] = (R[2] - R[6]) * t;
-		v[2] = (R[3] - R[1]) * t;
+		x = (R[7] - R[5]) * t;
+		y = (R[2] - R[6]) * t;
+		z = (R[3] - R[1]) * t;
 	}
 	else
 	{
 		int i = 0;
 		if (R[4] > R[0]) i = 1;
-		if (R[8] > R[4 * i]) i = 2;
-		const int j = (i + 1) % 3, k = (j + 1) % 3;
-		t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-		v[i] = 0.5 * t;
-		t = 0.5 / t;
-		w = (R[3 * k + j] - R[3 * j + k]) * t;
-		v[j] = (R[3 * j + i] + R[3 * i + j]) * t;
-		v[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+		if (R[8] > (i == 1 ? R[4] : R[0])) i = 2;
+		if (i == 0) // j = 1, k = 2
+		{
+			double t = sqrt(R[0] - R[4] - R[8] + 1.0);
+			x = 0.5 * t;
+			t = 0.5 / t;
+			w = (R[7] - R[5]) * t;
+			y = (R[3] + R[1]) * t;
+			z = (R[6] + R[2]) * t;
+		}
+		else if (i == 1) // j = 2, k = 0
+		{
+			double t = sqrt(R[4] - R[8] - R[0] + 1.0);
+			y = 0.5 * t;
+			t = 0.5 / t;
+			w = (R[2] - R[6]) * t;
+			z = (R[7] + R[5]) * t;
+			x = (R[1] + R[3]) * t;
+		}
+		else // j = 0, k = 1
+		{
+			double t = sqrt(R[8] - R[0] - R[4] + 1.0);
+			z = 0.5 * t;
+			t = 0.5 / t;
+			w = (R[3] - R[1]) * t;
+			x = (R[2] + R[6]) * t;
+			y = (R[5] + R[7]) * t;
+		}
 	}
-	const double nrm = sqrt(w * w + v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-	q[0] = w / nrm; q[1] = v[0] / nrm; q[2] = v[1] / nrm; q[3] = v[2] / nrm;
+	const double nrm = sqrt(w * w + x * x + y * y + z * z);
+	q[0] = w / nrm; q[1] = x / nrm; q[2] = y / nrm; q[3] = z / nrm;
 }
 __device__ void quat_to_rotmat(const double *q, double *R)
 {

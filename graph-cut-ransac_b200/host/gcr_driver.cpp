@@ -91,7 +91,7 @@ namespace
 	{
 		bool lazy = false;      // holds "the inliers of `model`", not fetched yet
 		long long slot = -1;    // lazy: `model` itself is still slot `slot` of the current batch on the device (>= 0), not in `model`
-		double model[9] = {0};
+		double model[12] = {0}; // 9 (H / F / E) or 12 (PnP) entries
 		uint64_t lazy_count = 0;
 		std::vector<uint32_t> idx;
 		size_t size() const { return lazy ? (size_t)lazy_count : idx.size(); }
@@ -109,7 +109,8 @@ namespace
 	{
 	public:
 		gcr_ctx *ctx;
-		int problem, n, m, mm, rm; // rm = models per non-minimal refit (1: H, F; up to 10: E)
+		int problem, n, m, mm, rm; // rm = models per non-minimal refit (1: H, F, PnP; up to 10: E)
+		int ml = 9, cols = 4;      // model length (12: PnP's 3 x 4 pose) and point columns (5: PnP's u v X Y Z)
 		const double *pts;
 		const double *grid_pts = nullptr; // points the neighbourhood grid is built on (E: pixel coordinates; else = pts)
 		gcr_run_settings S;
@@ -193,11 +194,11 @@ namespace
 				if (inliers) inliers->resize(count);
 				return true;
 			}
-			if (!d_one_model.ensure(ctx, 9 * sizeof(double)) || !d_one_score.ensure(ctx, sizeof(double)) ||
+			if (!d_one_model.ensure(ctx, ml * sizeof(double)) || !d_one_score.ensure(ctx, sizeof(double)) ||
 			    !d_one_count.ensure(ctx, sizeof(uint32_t)) || !d_idx.ensure(ctx, (size_t)n * sizeof(uint32_t)) ||
 			    !d_res.ensure(ctx, (size_t)n * sizeof(double)))
 				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_one_model.p, model, 9 * sizeof(double)) != GCR_OK)
+			if (gcr_memcpy_h2d(ctx, d_one_model.p, model, ml * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
 			if (gcr_score_exact(ctx, problem, scoring, 0, d_one_model.as<double>(), 1, S.threshold, d_one_score.as<double>(),
 			                    d_one_count.as<uint32_t>(), d_idx.as<uint32_t>(), d_res.as<double>()) != GCR_OK)
@@ -222,14 +223,14 @@ namespace
 		{
 			if (!h_model_have[slot])
 			{
-				if (gcr_memcpy_d2h(ctx, &h_models[slot * 9], d_models.as<double>() + slot * 9, 9 * sizeof(double)) != GCR_OK)
+				if (gcr_memcpy_d2h(ctx, &h_models[slot * ml], d_models.as<double>() + slot * ml, ml * sizeof(double)) != GCR_OK)
 				{
 					fail("gcr_memcpy_d2h");
 					return nullptr;
 				}
 				h_model_have[slot] = 1;
 			}
-			return &h_models[slot * 9];
+			return &h_models[slot * ml];
 		}
 		// several at once: the copies are queued, one synchronise delivers them
 		bool fetch_models(const std::vector<size_t> &slots)
@@ -238,7 +239,7 @@ namespace
 			for (size_t slot : slots)
 				if (!h_model_have[slot])
 				{
-					if (gcr_memcpy_d2h_async(ctx, &h_models[slot * 9], d_models.as<double>() + slot * 9, 9 * sizeof(double)) != GCR_OK)
+					if (gcr_memcpy_d2h_async(ctx, &h_models[slot * ml], d_models.as<double>() + slot * ml, ml * sizeof(double)) != GCR_OK)
 						return fail("gcr_memcpy_d2h");
 					h_model_have[slot] = 1;
 					queued = true;
@@ -252,7 +253,7 @@ namespace
 			const double *model = model_of((size_t)b.slot);
 			if (!model)
 				return false;
-			memcpy(b.model, model, sizeof(b.model));
+			memcpy(b.model, model, ml * sizeof(double));
 			b.slot = -1;
 			return true;
 		}
@@ -277,6 +278,8 @@ namespace
 		{
 			updated = false;
 			failed = false;
+			if (problem == GCR_PNP) // perspective_n_point_estimator.h:219-227: every pose is a valid model
+				return true;
 			if (problem == GCR_H)
 			{
 				// homography_estimator.h:326-342: |det H| >= 1e-2
@@ -450,7 +453,7 @@ namespace
 				for (int b = 0; b < 2; ++b)
 					if (live_buffers[b].lazy && !resolve_model(live_buffers[b]))
 						return false;
-			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * 9 * sizeof(double)) ||
+			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * ml * sizeof(double)) ||
 			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
 				return fail("gcr_malloc");
 			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
@@ -483,12 +486,12 @@ namespace
 			h_valid.resize(K);
 			h_scores.resize(K);
 			h_counts.resize(K);
-			h_models.resize(K * 9);
+			h_models.resize(K * ml);
 			// small batches (H, F: up to a few hundred KB) come back whole with the flags and scores -- one more queued copy,
 			// no later round trip; large ones (five-point batches: 0.7-2.9 MB) stay on the device and are fetched on demand
-			const bool models_with_batch = K * 9 * sizeof(double) <= (size_t)(256 << 10);
+			const bool models_with_batch = K * ml * sizeof(double) <= (size_t)(256 << 10);
 			h_model_have.assign(K, models_with_batch ? 1 : 0);
-			if (models_with_batch && gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * 9 * sizeof(double)) != GCR_OK)
+			if (models_with_batch && gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * ml * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4 && S.sampler != 2)
 			{
@@ -551,7 +554,7 @@ namespace
 				return false;
 			std::vector<double> models;
 			for (size_t slot : cand_slot)
-				models.insert(models.end(), &h_models[slot * 9], &h_models[slot * 9] + 9);
+				models.insert(models.end(), &h_models[slot * ml], &h_models[slot * ml] + ml);
 			return exact_many(models.data(), C, cand_score, cand_count, cand_idx);
 		}
 
@@ -560,10 +563,10 @@ namespace
 		bool exact_many(const double *models, size_t C, std::vector<double> &score, std::vector<uint32_t> &count,
 		                std::vector<uint32_t> &idx)
 		{
-			if (!d_cand_models.ensure(ctx, C * 9 * sizeof(double)) || !d_cand_scores.ensure(ctx, C * sizeof(double)) ||
+			if (!d_cand_models.ensure(ctx, C * ml * sizeof(double)) || !d_cand_scores.ensure(ctx, C * sizeof(double)) ||
 			    !d_cand_counts.ensure(ctx, C * sizeof(uint32_t)) || !d_cand_idx.ensure(ctx, C * (size_t)n * sizeof(uint32_t)))
 				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models, C * 9 * sizeof(double)) != GCR_OK)
+			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models, C * ml * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
 			if (gcr_score_exact(ctx, problem, scoring, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
 			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), nullptr) != GCR_OK)
@@ -604,13 +607,13 @@ namespace
 			// (n > 16384), else formed here from the per-point clamped distances (24 n bytes come back instead of 16 n + 8 E)
 			static const bool force_device_pairwise = getenv("GCR_DEVICE_PAIRWISE") != nullptr;
 			const bool device_pairwise = E > 0 && (n > 16384 || force_device_pairwise);
-			if (!d_lab_model.ensure(ctx, 9 * sizeof(double)) || !d_unary.ensure(ctx, (size_t)n * 3 * sizeof(double)) ||
+			if (!d_lab_model.ensure(ctx, ml * sizeof(double)) || !d_unary.ensure(ctx, (size_t)n * 3 * sizeof(double)) ||
 			    !d_pairwise.ensure(ctx, std::max<size_t>(device_pairwise ? E : 0, 1) * sizeof(double)))
 				return fail("gcr_malloc");
 			h_unary.resize((size_t)n * 3); // [n][2] capacities, then [n] clamped distances
 			h_pairwise.resize(device_pairwise ? E : 0);
 			double *d_dist = d_unary.as<double>() + 2 * (size_t)n;
-			if (gcr_memcpy_h2d(ctx, d_lab_model.p, model, 9 * sizeof(double)) != GCR_OK)
+			if (gcr_memcpy_h2d(ctx, d_lab_model.p, model, ml * sizeof(double)) != GCR_OK)
 				return fail("gcr_memcpy_h2d");
 			if (gcr_labeling_terms(ctx, problem, 0, d_lab_model.as<double>(), S.threshold, lambda, d_edges.as<uint32_t>(), E,
 			                       d_unary.as<double>(), device_pairwise ? d_pairwise.as<double>() : nullptr, d_dist) != GCR_OK)
@@ -673,6 +676,7 @@ namespace
 		{
 			const int rp = refit_problem < 0 ? problem : refit_problem;
 			const int rm = refit_problem < 0 ? this->rm : gcr_max_refit_models(rp);
+			const int rml = gcr_model_len(rp);
 			const int count = (int)sizes.size();
 			size_t total = 0;
 			for (uint32_t v : sizes) total += v;
@@ -685,7 +689,7 @@ namespace
 			}
 			// offsets and sizes travel as one array (one copy instead of two): [offsets | sizes]
 			if (!d_offsets.ensure(ctx, 2 * count * sizeof(uint32_t)) ||
-			    !d_lmodels.ensure(ctx, (size_t)count * rm * 9 * sizeof(double)) || !d_lok.ensure(ctx, (size_t)count * rm))
+			    !d_lmodels.ensure(ctx, (size_t)count * rm * rml * sizeof(double)) || !d_lok.ensure(ctx, (size_t)count * rm))
 				return fail("gcr_malloc");
 			std::vector<uint32_t> offsets_sizes(offsets.begin(), offsets.begin() + count);
 			offsets_sizes.insert(offsets_sizes.end(), sizes.begin(), sizes.begin() + count);
@@ -714,14 +718,14 @@ namespace
 			else if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_set_offsets, d_set_sizes, count, d_w,
 			                   weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
 				return fail("gcr_refit");
-			models.resize((size_t)count * rm * 9);
+			models.resize((size_t)count * rm * rml);
 			ok.resize((size_t)count * rm);
 			if (defer_sync) // the caller queues more work on these models and synchronises once
-				return gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) == GCR_OK &&
+				return gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * rml * sizeof(double)) == GCR_OK &&
 				               gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) == GCR_OK
 				           ? true
 				           : fail("gcr_memcpy_d2h");
-			if (gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * 9 * sizeof(double)) != GCR_OK ||
+			if (gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * rml * sizeof(double)) != GCR_OK ||
 			    gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) != GCR_OK || gcr_sync(ctx) != GCR_OK)
 				return fail("gcr_memcpy_d2h");
 			return true;
@@ -733,8 +737,8 @@ namespace
 			const size_t inlier_limit = 7 * (size_t)m; // estimator.inlierLimit()
 			const int trials = (int)S.max_local_optimization_number;
 			Score max_score = best_score;
-			double lbest_model[9];
-			memcpy(lbest_model, best_model, sizeof(lbest_model));
+			double lbest_model[12];
+			memcpy(lbest_model, best_model, ml * sizeof(double));
 			std::vector<uint32_t> lbest_inliers, inliers, tmp;
 			++st.local_optimization_number;
 			while (++st.graph_cut_number < S.max_graph_cut_number)
@@ -797,7 +801,7 @@ namespace
 							if (ok[t] && (double)scores32[t] > record * (1.0 - rank_slack))
 							{
 								rec.push_back(t);
-								rec_models.insert(rec_models.end(), &models[(size_t)t * 9], &models[(size_t)t * 9] + 9);
+								rec_models.insert(rec_models.end(), &models[(size_t)t * ml], &models[(size_t)t * ml] + ml);
 								record = std::max(record, (double)scores32[t]);
 							}
 						if (rec.size() >= 2)
@@ -823,13 +827,13 @@ namespace
 							s.inliers = rec_count[c];
 							tmp.assign(rec_idx.begin() + c * (size_t)n, rec_idx.begin() + c * (size_t)n + rec_count[c]);
 						}
-						else if (!exact(&models[(size_t)t * 9], s, &tmp))
+						else if (!exact(&models[(size_t)t * ml], s, &tmp))
 							return false;
 						if (max_score.value < s.value) // :880
 						{
 							updated = true;
 							max_score = s;
-							memcpy(lbest_model, &models[(size_t)t * 9], sizeof(lbest_model));
+							memcpy(lbest_model, &models[(size_t)t * ml], ml * sizeof(double));
 							lbest_inliers.swap(tmp);
 						}
 					}
@@ -840,7 +844,7 @@ namespace
 			if (best_score.value < max_score.value) // :900
 			{
 				best_score = max_score;
-				memcpy(best_model, lbest_model, sizeof(lbest_model));
+				memcpy(best_model, lbest_model, ml * sizeof(double));
 				best_inliers_out.lazy = false;
 				best_inliers_out.idx.swap(lbest_inliers);
 			}
@@ -861,24 +865,30 @@ namespace
 			while (++iterations < S.max_least_squares_iterations)
 			{
 				Score s;
-				if (!exact(model, s, nullptr, &r2))
-					return false;
-				for (uint32_t idx : inliers) // Tukey bisquare weights, written by POINT index (:657-668)
-				{
-					const double w = std::max(0.0, 1.0 - r2[idx] / T);
-					weights[idx] = w * w;
-				}
-				// ... and read by POSITION by the H / 8-point solvers, by POINT by the Stewenius solver
-				// (solver_essential_matrix_five_point_stewenius.h:143): reproduced literally
+				const bool weighting = problem != GCR_PNP; // _ModelEstimator::isWeightingApplicable() (:652): false for PnP
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
-				if (!refit(inliers.data(), offsets, sizes, weights.data(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
-				           models, ok))
+				if (weighting)
+				{
+					if (!exact(model, s, nullptr, &r2))
+						return false;
+					for (uint32_t idx : inliers) // Tukey bisquare weights, written by POINT index (:657-668)
+					{
+						const double w = std::max(0.0, 1.0 - r2[idx] / T);
+						weights[idx] = w * w;
+					}
+					// ... and read by POSITION by the H / 8-point solvers, by POINT by the Stewenius solver
+					// (solver_essential_matrix_five_point_stewenius.h:143): reproduced literally
+					if (!refit(inliers.data(), offsets, sizes, weights.data(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
+					           models, ok))
+						return false;
+					for (uint32_t idx : inliers)
+						weights[idx] = 0;
+				}
+				else if (!refit(inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok)) // :682-688
 					return false;
-				for (uint32_t idx : inliers)
-					weights[idx] = 0;
 				std::vector<const double *> found;
 				for (int q = 0; q < rm; ++q)
-					if (ok[q]) found.push_back(&models[(size_t)q * 9]);
+					if (ok[q]) found.push_back(&models[(size_t)q * ml]);
 				if (found.empty()) // :690
 					break;
 				if (found.size() == 1) // :692-714
@@ -889,7 +899,7 @@ namespace
 						break;
 					if (s.inliers <= inliers.size())
 						break;
-					memcpy(model, found[0], 9 * sizeof(double));
+					memcpy(model, found[0], ml * sizeof(double));
 					inliers.swap(tmp);
 				}
 				else // :715-748 several models: the best by inlier count, `best_score` lives across the rounds
@@ -907,7 +917,7 @@ namespace
 						{
 							updated = true;
 							irls_best = s;
-							memcpy(model, cand, 9 * sizeof(double));
+							memcpy(model, cand, ml * sizeof(double));
 							inliers.swap(tmp);
 						}
 					}
@@ -1030,6 +1040,12 @@ namespace
 
 		bool build_grid()
 		{
+			if (problem == GCR_PNP && S.neighborhood != 1 && S.spatial_coherence_weight > 0.0 && S.do_local_optimization)
+			{
+				// find6DPose_ knows one neighbourhood: FlannNeighborhoodGraph over the 5-column rows (py/gcransac_python.cpp:1087-1098)
+				error = "the absolute-pose problem uses the radius neighbourhood (gcr_run_settings.neighborhood = 1)";
+				return false;
+			}
 			if (S.neighborhood == 1)
 			{
 				have_grid = false;
@@ -1100,6 +1116,8 @@ namespace
 		int run(double *model_out, uint8_t *inlier_mask)
 		{
 			memset(&st, 0, sizeof(st));
+			ml = gcr_model_len(problem);
+			cols = problem == GCR_PNP ? 5 : 4;
 			m = variant == 1 ? 2 : gcr_sample_size(problem);
 			mm = variant == 1 ? 1 : gcr_max_models(problem);
 			B = S.batch > 0 ? S.batch : 1024;
@@ -1118,7 +1136,7 @@ namespace
 				// will read them: the radius graph, or grids over more than 16384 points.
 				const bool graph_wanted = S.spatial_coherence_weight > 0.0 && S.do_local_optimization;
 				if (((graph_wanted && S.neighborhood == 1) || ((graph_wanted || S.sampler == 2) && n > 16384)) &&
-				    gcr_points_upload(ctx, grid_pts, n, 4, 1) != GCR_OK)
+				    gcr_points_upload(ctx, grid_pts, n, cols, 1) != GCR_OK)
 				{
 					fail("gcr_points_upload");
 					return -1;
@@ -1130,13 +1148,18 @@ namespace
 			}
 			if (!nested)
 			{
-				if (gcr_points_upload(ctx, pts, n, 4, 1) != GCR_OK)
+				if (gcr_points_upload(ctx, pts, n, cols, 1) != GCR_OK)
 				{
 					fail("gcr_points_upload");
 					return -1;
 				}
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
 					return -1;
+				if (S.sampler == 2 && problem == GCR_PNP)
+				{
+					error = "Progressive NAPSAC is not usable for the absolute pose problem."; // py/gcransac_python.cpp:1113-1120
+					return -1;
+				}
 				if (S.sampler == 2 && !(grid_pts && grid_pts != pts) && !build_pnapsac())
 					return -1;
 				if (S.sampler == 4)
@@ -1172,7 +1195,7 @@ namespace
 			uint64_t &it = st.iteration_number;
 			uint64_t cursor = 0; // next sample of the main stream
 			Score best;
-			double best_model[9] = {0};
+			double best_model[12] = {0};
 			InlierBuffer buf[2];
 			live_buffers = buf;
 			int offset = 0;
@@ -1235,7 +1258,7 @@ namespace
 						const double *model = model_of(slot);
 						if (!model)
 							return -1;
-						memcpy(cur.model, model, sizeof(cur.model));
+						memcpy(cur.model, model, ml * sizeof(double));
 						cur.slot = -1;
 						Score s;
 						if (!exact_slot(slot, model, s, cur.idx))
@@ -1243,8 +1266,8 @@ namespace
 						cur.lazy = false;
 						if (!(best.value < s.value)) // :440
 							continue;
-						double candidate[9];
-						memcpy(candidate, model, sizeof(candidate));
+						double candidate[12];
+						memcpy(candidate, model, ml * sizeof(double));
 						bool updated = false, failed = false;
 						const bool valid_model = is_valid_model(candidate, cur.idx, h_samples.empty() ? nullptr : &h_samples[(size_t)success_at * m],
 						                                        updated, failed);
@@ -1254,12 +1277,12 @@ namespace
 						{
 							if (updated) // :449-456: the replaced model is scored again, into the same container
 							{
-								memcpy(cur.model, candidate, sizeof(cur.model));
+								memcpy(cur.model, candidate, ml * sizeof(double));
 								if (!exact(candidate, s, &cur.idx))
 									return -1;
 							}
 							offset = (offset + 1) % 2;
-							memcpy(best_model, candidate, sizeof(best_model));
+							memcpy(best_model, candidate, ml * sizeof(double));
 							best = s;
 							do_lo = it > S.min_iteration_number_before_lo && best.inliers > (uint64_t)m; // :463-464
 							max_iteration = iteration_number(best.inliers, n, m, log_probability);
@@ -1305,8 +1328,8 @@ namespace
 			if (S.do_final_iterated_least_squares) // :559-586
 			{
 				PhaseTimer t(st.phase_seconds[4]);
-				double model[9];
-				memcpy(model, best_model, sizeof(model));
+				double model[12];
+				memcpy(model, best_model, ml * sizeof(double));
 				bool success = false;
 				if (!iterated_least_squares(buf[offset].idx, model, success))
 					return -1;
@@ -1320,7 +1343,7 @@ namespace
 					if (best.value < cur.value)
 					{
 						iterative_refitting_applied = true;
-						memcpy(best_model, model, sizeof(model));
+						memcpy(best_model, model, ml * sizeof(double));
 						offset = idx2;
 					}
 				}
@@ -1341,11 +1364,11 @@ namespace
 					const int idx2 = (offset + 1) % 2;
 					Score cur;
 					buf[idx2].lazy = false;
-					if (!exact(&models[(size_t)q * 9], cur, &buf[idx2].idx))
+					if (!exact(&models[(size_t)q * ml], cur, &buf[idx2].idx))
 						return -1;
 					if (best.value < cur.value)
 					{
-						memcpy(best_model, &models[(size_t)q * 9], 9 * sizeof(double));
+						memcpy(best_model, &models[(size_t)q * ml], ml * sizeof(double));
 						offset = idx2;
 					}
 				}
@@ -1385,6 +1408,18 @@ namespace
 						offset = idx2;
 					}
 				}
+			}
+			if (problem == GCR_PNP && S.pnp_bundle_adjustment && buf[offset].idx.size() > 3)
+			{
+				// find6DPose_ (py/gcransac_python.cpp:1227-1238): PnPBundleAdjustment on the inliers, its result REPLACES the model
+				// (no score comparison, the inlier set stays)
+				std::vector<double> models;
+				std::vector<uint8_t> ok;
+				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)buf[offset].idx.size());
+				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
+					return -1;
+				if (ok[0])
+					memcpy(best_model, models.data(), ml * sizeof(double));
 			}
 			if (problem == GCR_E && !nested && S.e_bundle_adjustment && buf[offset].idx.size() > 5)
 			{
@@ -1442,7 +1477,7 @@ namespace
 			}
 			for (uint32_t i : buf[offset].idx)
 				inlier_mask[i] = 1;
-			memcpy(model_out, best_model, sizeof(best_model));
+			memcpy(model_out, best_model, ml * sizeof(double));
 			return (int)buf[offset].idx.size();
 		}
 	};
@@ -1479,6 +1514,7 @@ extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 	s->sampler_variance = 0.1;
 	s->scoring = GCR_MSAC;
 	s->e_bundle_adjustment = 0;
+	s->pnp_bundle_adjustment = 0;
 	for (int d = 0; d < 4; ++d)
 		s->image_sizes[d] = 0.0;
 }
@@ -1521,8 +1557,8 @@ extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points,
 {
 	if (!ctx || !h_points || !settings || !model_out || !inlier_mask || n <= 0)
 		return -2;
-	if (problem != GCR_H && problem != GCR_F && problem != GCR_E)
-		return -3; // PnP is not wired into this driver (find6DPose: SURVEY 8f N4)
+	if (problem != GCR_H && problem != GCR_F && problem != GCR_E && problem != GCR_PNP)
+		return -3;
 	Driver d;
 	d.ctx = ctx;
 	d.problem = problem;

@@ -77,6 +77,9 @@ typedef struct gcr_run_settings
 	/* E: the post-run relative-pose bundle adjustment of findEssentialMatrix_ (py/gcransac_python.cpp:2766-2821;
 	 * gcr_refit_e_ba) -- 0 = off (GCRANSAC<>::run alone), 1 = on (what the Python entry point does) */
 	int e_bundle_adjustment;
+	/* PnP: find6DPose_'s post-run step (py/gcransac_python.cpp:1227-1238): the non-minimal fit on the inliers replaces the
+	 * model -- 0 = off, 1 = on (what the Python entry point does) */
+	int pnp_bundle_adjustment;
 } gcr_run_settings;
 
 typedef struct gcr_run_stats
@@ -95,8 +98,10 @@ typedef struct gcr_run_stats
 /* defaults of utils::Settings + the Python drivers */
 void gcr_run_settings_default(gcr_run_settings *s);
 
-/* GCRANSAC<>::run for problem GCR_H, GCR_F or GCR_E (points already K-normalised) on `n` correspondences (row-major FP64 n x 4, host memory).
- * model_out: 9 doubles; inlier_mask: n bytes (1 = inlier).  Returns the inlier count (0 = no model), < 0 on error
+/* GCRANSAC<>::run for problem GCR_H, GCR_F, GCR_E (points already K-normalised) on `n` correspondences (row-major FP64
+ * n x 4, host memory), or GCR_PNP (find6DPose_, py/gcransac_python.cpp:1026-1272: rows u v X Y Z, n x 5, image points
+ * K-normalised; P3P minimal solver, non-minimal fits = normalised DLT + the LM of refine_pnp, radius neighbourhood).
+ * model_out: 9 doubles (PnP: 12, the 3 x 4 pose); inlier_mask: n bytes (1 = inlier).  Returns the inlier count (0 = no model), < 0 on error
  * (gcr_last_error(ctx)). */
 int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points, int n, const gcr_run_settings *settings,
                    double *model_out, uint8_t *inlier_mask, gcr_run_stats *stats);

@@ -183,3 +183,73 @@ inline int findEssentialMatrix_(std::vector<double> &correspondences, std::vecto
 	                     device);
 }
 #endif
+
+// include/gcransac_python.h:177-211 (py/gcransac_python.cpp:1026-1272): absolute pose from 2D-3D matches, rows u v X Y Z
+// with K-normalised image points; pose = 12 doubles, the row-major 3 x 4 [R | t].  neighborhood_id 0 = the radius
+// neighbourhood over the 5-column rows (FLANN in the reference, exact here).  Non-minimal fits: normalised DLT + the LM of
+// refine_pnp (the reference's EPnP initialiser is OpenCV's; its accumulator as written has no defined behaviour).
+inline int find6DPose_(std::vector<double> &correspondences, std::vector<double> &point_probabilities, std::vector<bool> &inliers,
+                       std::vector<double> &pose, double spatial_coherence_weight, double threshold, double conf, int max_iters,
+                       int min_iters, bool use_sprt, double min_inlier_ratio_for_sprt, int sampler_id, int neighborhood_id,
+                       double neighborhood_size, double sampler_variance, int lo_number, uint64_t seed = 1, int device = 0)
+{
+	(void)use_sprt; (void)min_inlier_ratio_for_sprt;
+	const size_t num_tents = correspondences.size() / 5;
+	if (num_tents < 4)
+	{
+		fprintf(stderr, "find6DPose_: %zu correspondences, at least 4 are needed\n", num_tents);
+		return 0;
+	}
+	if (neighborhood_id != 0) // py/gcransac_python.cpp:1093-1098
+	{
+		fprintf(stderr, "Unknown neighborhood-graph identifier: %d. The accepted values are 0 (FLANN-based neighborhood)\n", neighborhood_id);
+		return 0;
+	}
+	if (sampler_id == 2) // :1113-1120
+	{
+		fprintf(stderr, "Progressive NAPSAC is not usable for the absolute pose problem.\n");
+		return 0;
+	}
+	if (sampler_id < 0 || sampler_id > 4)
+	{
+		fprintf(stderr, "Unknown sampler identifier: %d. The accepted samplers are 0 (uniform sampling), 1 (PROSAC sampling), 2 (P-NAPSAC sampling)\n", sampler_id);
+		return 0;
+	}
+	if ((sampler_id == 3 || sampler_id == 4) && point_probabilities.size() != num_tents)
+	{
+		fprintf(stderr, "The number of correspondences (%zu) and the number of provided probabilities (%zu) do not match.\n", num_tents,
+		        point_probabilities.size());
+		return 0;
+	}
+	gcr_ctx *ctx = gcr_api::context(device);
+	if (!ctx)
+	{
+		fprintf(stderr, "find6DPose_: no usable CUDA device %d (there is no CPU fallback)\n", device);
+		return 0;
+	}
+	gcr_run_settings s;
+	gcr_run_settings_default(&s);
+	s.threshold = threshold;
+	s.confidence = conf;
+	s.spatial_coherence_weight = spatial_coherence_weight;
+	s.max_iteration_number = (uint64_t)max_iters;
+	s.min_iteration_number = (uint64_t)min_iters;
+	s.max_local_optimization_number = (uint64_t)lo_number;
+	s.seed = seed;
+	s.sampler = sampler_id;
+	s.sampler_variance = sampler_variance;
+	s.point_probabilities = (sampler_id == 3 || sampler_id == 4) ? point_probabilities.data() : nullptr;
+	s.neighborhood = 1;
+	s.neighborhood_radius = neighborhood_size;
+	s.pnp_bundle_adjustment = 1; // :1227-1238
+	std::vector<uint8_t> mask(num_tents, 0);
+	double m[12] = {0};
+	const int n_inl = gcr_find_model(ctx, GCR_PNP, correspondences.data(), (int)num_tents, &s, m, mask.data(), nullptr);
+	if (n_inl < 0)
+		return 0;
+	inliers.resize(num_tents);
+	for (size_t i = 0; i < num_tents; ++i)
+		inliers[i] = mask[i] != 0;
+	pose.assign(m, m + 12);
+	return n_inl;
+}

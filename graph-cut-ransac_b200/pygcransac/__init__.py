@@ -45,7 +45,7 @@ class RunSettings(C.Structure):
                 ("cells_per_axis", C.c_uint64), ("seed", C.c_uint64), ("batch", C.c_int), ("use_degensac", C.c_int), ("f_bundle_adjustment", C.c_int),
                 ("sampler", C.c_int), ("neighborhood", C.c_int), ("neighborhood_radius", C.c_double),
                 ("point_probabilities", C.c_void_p), ("sampler_variance", C.c_double), ("image_sizes", C.c_double * 4), ("scoring", C.c_int),
-                ("e_bundle_adjustment", C.c_int)]
+                ("e_bundle_adjustment", C.c_int), ("pnp_bundle_adjustment", C.c_int)]
 
 
 class RunStats(C.Structure):
@@ -96,13 +96,16 @@ last_statistics = None  # RunStats of the most recent call (the reference fills 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
           neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seed, device, intrinsics=None, use_degensac=False, f_bundle_adjustment=0,
-          probabilities=(), sampler_variance=0.1, scoring=0, e_bundle_adjustment=0):
+          probabilities=(), sampler_variance=0.1, scoring=0, e_bundle_adjustment=0, pnp_bundle_adjustment=0):
     global last_statistics
     pts = np.ascontiguousarray(correspondences, dtype=np.float64)           # bindings.cpp: py::array_t<double>
-    min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
-    if pts.ndim != 2 or pts.shape[1] != 4:
+    min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5, _cabi.PNP: 4}[problem]
+    if problem == _cabi.PNP:
+        if pts.ndim != 2 or pts.shape[1] != 5 or pts.shape[0] < min_n:
+            raise ValueError("x1y1x2y2z2 should be an array with dims [n,5], n>=4")                   # bindings.cpp:223-228
+    elif pts.ndim != 2 or pts.shape[1] != 4:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)
-    if pts.shape[0] < min_n:
+    elif pts.shape[0] < min_n:
         raise ValueError("correspondences should be an array with dims [n,4], n>=%d" % min_n)        # bindings.cpp:881-889
     prob = None
     if sampler in (3, 4):
@@ -143,9 +146,10 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     s.sampler_variance = float(sampler_variance)
     s.scoring = int(scoring)
     s.e_bundle_adjustment = int(e_bundle_adjustment)
+    s.pnp_bundle_adjustment = int(pnp_bundle_adjustment)
     for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
         s.image_sizes[i] = float(v)
-    model = np.zeros(9)
+    model = np.zeros(12 if problem == _cabi.PNP else 9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()
     if intrinsics is None:
@@ -161,7 +165,7 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
     mask = mask.astype(bool)
     if n_inl == 0:
         return None, mask                                                   # bindings.cpp:973-975
-    return model.reshape(3, 3), mask
+    return model.reshape(3, -1), mask
 
 
 def findHomography(correspondences, h1, w1, h2, w2, probabilities=(), threshold=1.0, conf=0.99,
@@ -221,15 +225,25 @@ def findEssentialMatrix(correspondences, K1, K2, h1, w1, h2, w2, probabilities=(
                  e_bundle_adjustment=1 if bundle_adjustment else 0)
 
 
-def find6DPose(x1y1, x2y2z2, probabilities=(), threshold=0.001, conf=0.99, spatial_coherence_weight=0.975, max_iters=10000,
-               min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood_size=20.0, lo_number=50,
-               sampler_variance=0.1):
-    """py/bindings.cpp:203-277 -> find6DPose_ (py/gcransac_python.cpp:1026-1272).  Not wired: the P3P minimal solver and the
-    PnP scoring run on the GPU (gcr_solve_minimal / gcr_score with GCR_PNP), but every non-minimal fit of the reference's
-    DefaultPnPEstimator goes through PnPBundleAdjustment, whose behaviour is undefined in the reference itself (the
-    accumulator is constructed with the loss where its camera belongs, loops over all rows while indexing the sample, and
-    multiplies by weights that find6DPose_ passes as nullptr; relative_pose/bundle.cpp:589-594, jacobian_impl.h:12-18,
-    32-37, 56) and starts from OpenCV's EPnP, a dependency outside the tree -- there is no result to match."""
-    raise NotImplementedError("find6DPose: the reference's non-minimal PnP solver has no defined behaviour to match "
-                              "(DESIGN.md section 8); P3P solving and PnP scoring are available through the C ABI "
-                              "(gcr_solve_minimal / gcr_score with GCR_PNP)")
+def find6DPose(correspondences, probabilities=(), threshold=0.001, conf=0.99, spatial_coherence_weight=0.975, max_iters=10000,
+               min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=0, neighborhood_size=8.0,
+               lo_number=50, sampler_variance=0.1, seed=1, device=0, scoring=0, bundle_adjustment=True):
+    """py/bindings.cpp:203-277, 1058-1072 -> find6DPose_ (py/gcransac_python.cpp:1026-1272): absolute pose [R | t] from
+    2D-3D matches, rows (u, v, X, Y, Z) with K-normalised image points.  GCRANSAC<DefaultPnPEstimator> = P3P minimal solver
+    (Lambda-Twist, estimators/solver_p3p.h) + PnPBundleAdjustment non-minimal fits; the neighbourhood (id 0) is the radius
+    graph over the 5-column rows (FLANN in the reference, the exact graph here); after the run the non-minimal fit on the
+    inliers replaces the pose (:1227-1238; `bundle_adjustment=False`, not a reference argument, skips it).
+    Returns (pose 3x4 or None, mask bool[N]).
+
+    The reference's non-minimal solver has no defined behaviour to match (its LM accumulator is constructed with the loss
+    where its camera belongs, loops over all rows while indexing the sample and multiplies by weights passed as nullptr;
+    its initialiser is OpenCV's EPnP, outside the tree) -- stated here as: normalised DLT on the index set (>= 6 points)
+    + the LM of refine_pnp over the index set (gcr_refit with GCR_PNP)."""
+    if neighborhood != 0:
+        # py/gcransac_python.cpp:1093-1098: "Unknown neighborhood-graph identifier ... accepted values are 0 (FLANN-based)"
+        return None, np.zeros(len(correspondences), dtype=bool)
+    if sampler == 2:
+        return None, np.zeros(len(correspondences), dtype=bool)            # :1113-1120 P-NAPSAC is not usable for PnP
+    return _find(_cabi.PNP, correspondences, (0, 0, 0, 0), threshold, conf, spatial_coherence_weight, max_iters, min_iters,
+                 sampler, 1, neighborhood_size, lo_number, False, seed, device, probabilities=probabilities,
+                 sampler_variance=sampler_variance, scoring=scoring, pnp_bundle_adjustment=1 if bundle_adjustment else 0)

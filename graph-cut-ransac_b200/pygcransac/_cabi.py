@@ -441,8 +441,9 @@ class Context:
         count = len(index_sets)
         d_flat, d_off, d_sz = self.to_device(flat), self.to_device(offsets), self.to_device(sizes)
         d_w = None if weights is None else self.to_device(np.ascontiguousarray(weights, dtype=np.float64))
-        R = self.lib.gcr_max_refit_models(problem)          # 1 (H, F) or 10 (E: Stewenius returns up to 10 models)
-        dm = self.malloc(count * R * 9 * 8)
+        R = self.lib.gcr_max_refit_models(problem)          # 1 (H, F, PnP) or 10 (E: Stewenius returns up to 10 models)
+        ml = self.lib.gcr_model_len(problem)
+        dm = self.malloc(count * R * ml * 8)
         dok = self.malloc(count * R)
         try:
             if ba_frame:
@@ -454,7 +455,7 @@ class Context:
                                               count, C.c_void_p(d_w) if d_w else None, weight_mode, C.c_void_p(dm),
                                               C.c_void_p(dok)))
             if R == 1:
-                return self.to_host(dm, (count, 3, 3), np.float64), self.to_host(dok, (count,), np.uint8)
+                return self.to_host(dm, (count, 3, ml // 3), np.float64), self.to_host(dok, (count,), np.uint8)
             return self.to_host(dm, (count, R, 3, 3), np.float64), self.to_host(dok, (count, R), np.uint8)
         finally:
             for d in (d_flat, d_off, d_sz, dm, dok):

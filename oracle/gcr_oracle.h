@@ -147,6 +147,9 @@ void gcro_test_eigenvector(const double *A, int n, double lambda, double *v);
 /* ---- absolute pose (a15) ---------------------------------------------------------------------------------- */
 /* solver_p3p.h:177-385 Lambda-Twist; returns #models (0..4), 3x4 row-major each  [unpinned] */
 int gcro_solve_p3p(const double *pts5, const uint32_t *sample, double *P48);
+/* non-minimal absolute pose (gcr_oracle_pba.cpp): normalised DLT + the LM of refine_pnp; weights by position or NULL */
+int gcro_refit_pnp(const double *pts5, const uint32_t *sample, int n, const double *weights, double *P12);
+int gcro_refine_pnp_lm(const double *pts5, const uint32_t *sample, int n, const double *weights, double *P12);
 
 /* ---- neighbourhood (a24) ---------------------------------------------------------------------------------- */
 /* grid_neighborhood_graph.h:229-292: keys[i] = cell key of point i; returns neighbor_number; *n_cells = filled

@@ -322,6 +322,27 @@ class Oracle:
         cnt = self.lib.gcro_polish_e_ba(p, len(p), s, len(s), None if w is None else w.ctypes.data, out)
         return out[: cnt * 9].reshape(cnt, 3, 3).copy()
 
+    def refit_pnp(self, pts5, sample, weights=None):
+        """Non-minimal absolute pose: normalised DLT + refine_pnp's LM; P [3, 4] or None.  weights: by position."""
+        out = np.empty(12)
+        p = np.ascontiguousarray(pts5, dtype=np.float64)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self.lib.gcro_refit_pnp.restype = C.c_int
+        self.lib.gcro_refit_pnp.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        cnt = self.lib.gcro_refit_pnp(p, s, len(s), None if w is None else w.ctypes.data, out)
+        return out.reshape(3, 4).copy() if cnt else None
+
+    def refine_pnp_lm(self, pts5, sample, P, weights=None):
+        out = np.ascontiguousarray(P, dtype=np.float64).reshape(12).copy()
+        p = np.ascontiguousarray(pts5, dtype=np.float64)
+        s = np.ascontiguousarray(sample, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self.lib.gcro_refine_pnp_lm.restype = C.c_int
+        self.lib.gcro_refine_pnp_lm.argtypes = [_dp, _u32p, C.c_int, C.c_void_p, _dp]
+        it = self.lib.gcro_refine_pnp_lm(p, s, len(s), None if w is None else w.ctypes.data, out)
+        return out.reshape(3, 4), it
+
     def colpiv_q(self, A):
         A = np.ascontiguousarray(A, dtype=np.float64)
         Q = np.empty_like(A)
@@ -429,7 +450,7 @@ class Ref:
         scoring_kind 0 = the reference's MSACScoringFunction, 1 = the CUDA adapter
         (RefCuda only).  Returns dict(model, mask, inliers, score, stats)."""
         pts = _as_pts(pts)
-        model = np.zeros(9)
+        model = np.zeros(12 if problem == PNP else 9)
         mask = np.zeros(len(pts), dtype=np.uint8)
         stats = np.zeros(10, dtype=np.uint64)
         score = C.c_double()
@@ -448,7 +469,7 @@ class Ref:
             raise ValueError("ref_run: unsupported problem / scoring kind (%d)" % n_inl)
         names = ("iterations", "graph_cuts", "local_optimizations", "neighbor_number", "accepted", "rejected",
                  "main_samples", "lo_samples", "degensac_runs", "degensac_updates")
-        return dict(model=model.reshape(3, 3), mask=mask.astype(bool), inliers=n_inl, score=score.value,
+        return dict(model=model.reshape(3, -1), mask=mask.astype(bool), inliers=n_inl, score=score.value,
                     stats=dict(zip(names, (int(v) for v in stats))))
 
     def score(self, problem, scoring, pts, model, thr, want_inliers=False):

@@ -280,8 +280,8 @@ namespace
 				count = gcro_refit_f8(pts, s.data(), (int)sample_number_, weights_, out);
 			else if constexpr (PROBLEM == GCRO_E)
 				count = gcro_refit_e(pts, s.data(), (int)sample_number_, weights_, out);
-			else
-				count = 0;
+			else // PnP: the stated non-minimal solver (gcr_oracle_pba.cpp); isWeightingApplicable() is false: never weighted
+				count = gcro_refit_pnp(pts, s.data(), (int)sample_number_, nullptr, out);
 			for (int i = 0; i < count; ++i)
 				models_->emplace_back(from_flat(out + i * T::rows * T::cols, T::rows, T::cols));
 			return count > 0;
@@ -835,9 +835,9 @@ namespace
 		ExactRadiusGraph(const cv::Mat *c, double r) : neighborhood::NeighborhoodGraph<cv::Mat>(c), radius(r) { initialized = initialize(c); }
 		bool initialize(const cv::Mat *const c)
 		{
-			const int n = c->rows;
+			const int n = c->rows, cols = c->cols; // 4 (correspondences) or 5 (find6DPose_'s u v X Y Z rows)
 			const double *p = reinterpret_cast<const double *>(c->data);
-			std::vector<float> f((size_t)n * 4);
+			std::vector<float> f((size_t)n * cols);
 			for (size_t i = 0; i < f.size(); ++i) f[i] = (float)p[i];
 			const float r = (float)radius, r2 = r * r;
 			neighbours.assign(n, std::vector<size_t>());
@@ -846,9 +846,14 @@ namespace
 			{
 				for (int j = 0; j < n; ++j)
 				{
-					const float dx = f[4 * i] - f[4 * j], dy = f[4 * i + 1] - f[4 * j + 1], dz = f[4 * i + 2] - f[4 * j + 2],
-					            dw = f[4 * i + 3] - f[4 * j + 3];
-					const float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+					const float dx = f[cols * i] - f[cols * j], dy = f[cols * i + 1] - f[cols * j + 1], dz = f[cols * i + 2] - f[cols * j + 2],
+					            dw = f[cols * i + 3] - f[cols * j + 3];
+					float d2 = ((dx * dx + dy * dy) + dz * dz) + dw * dw;
+					if (cols == 5)
+					{
+						const float dv = f[cols * i + 4] - f[cols * j + 4];
+						d2 = d2 + dv * dv;
+					}
 					if (d2 < r2 && j != i)
 						neighbours[i].push_back((size_t)j);
 				}
@@ -1012,6 +1017,15 @@ namespace
 					model = from_flat(identity, 3, 3);
 				}
 			}
+		if constexpr (PROBLEM == GCRO_PNP)
+			if ((f_ba & 8) && st.inliers.size() > 3)
+			{
+				// find6DPose_ (py/gcransac_python.cpp:1227-1238): the non-minimal solver on the inliers replaces the model
+				std::vector<uint32_t> inl(st.inliers.begin(), st.inliers.end());
+				double refined[12];
+				if (gcro_refit_pnp(reinterpret_cast<const double *>(points.data), inl.data(), (int)inl.size(), nullptr, refined))
+					model = from_flat(refined, 3, 4);
+			}
 		for (int i = 0; i < points.rows; ++i)
 			inlier_mask[i] = 0;
 		for (size_t idx : st.inliers)
@@ -1050,8 +1064,9 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
             uint64_t seed, double *model_out, uint8_t *inlier_mask, uint64_t *stats_out, double *score_out,
             const double *grid_pts, int use_degensac, int f_ba, int sampler_id, double radius)
 {
-	cv::Mat points(n, 4, CV_64F, const_cast<double *>(pts));
-	cv::Mat grid_points(n, 4, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
+	const int cols = gcro_point_cols(problem);
+	cv::Mat points(n, cols, CV_64F, const_cast<double *>(pts));
+	cv::Mat grid_points(n, cols, CV_64F, const_cast<double *>(grid_pts ? grid_pts : pts));
 	struct PNapsacPoints // findEssentialMatrix_ hands P-NAPSAC the pixel coordinates (py/gcransac_python.cpp:2650)
 	{
 		PNapsacPoints(const cv::Mat *p) { g_pnapsac_points = p; }
@@ -1063,6 +1078,7 @@ int ref_run(int problem, int scoring_kind, const double *pts, int n, const doubl
 		if (problem == GCRO_H) return GCR_RUN(GCRO_H, MSACScoringFunction<OracleEstimator<GCRO_H>>);
 		if (problem == GCRO_F) return GCR_RUN(GCRO_F, MSACScoringFunction<OracleEstimator<GCRO_F>>);
 		if (problem == GCRO_E) return GCR_RUN(GCRO_E, MSACScoringFunction<OracleEstimator<GCRO_E>>);
+		if (problem == GCRO_PNP) return GCR_RUN(GCRO_PNP, MSACScoringFunction<OracleEstimator<GCRO_PNP>>);
 		return -1;
 	}
 	if (scoring_kind == 2) // GCRANSAC<Estimator, Graph, MAGSACScoringFunction<Estimator>> (scoring_function.h:237-349)

@@ -10,11 +10,15 @@ extern "C" int shim_find(int problem, const double *pts, int n, const double *pr
                          int use_space_partitioning, double sampler_variance, int lo_number, unsigned long long seed,
                          double *model_out, unsigned char *mask_out, int *model_len, int *mask_len)
 {
-	std::vector<double> correspondences(pts, pts + 4 * (size_t)n), point_probabilities(probabilities, probabilities + n_probabilities);
+	const size_t cols = problem == GCR_PNP ? 5 : 4;
+	std::vector<double> correspondences(pts, pts + cols * (size_t)n), point_probabilities(probabilities, probabilities + n_probabilities);
 	std::vector<bool> inliers;
 	std::vector<double> model;
 	int count;
-	if (problem == GCR_H)
+	if (problem == GCR_PNP)
+		count = find6DPose_(correspondences, point_probabilities, inliers, model, spatial_coherence_weight, threshold, conf, max_iters,
+		                    min_iters, true, 0.00001, sampler_id, neighborhood_id, neighborhood_size, sampler_variance, lo_number, seed);
+	else if (problem == GCR_H)
 		count = findHomography_(correspondences, point_probabilities, inliers, model, h1, w1, h2, w2, spatial_coherence_weight, threshold,
 		                        conf, max_iters, min_iters, true, 0.00001, sampler_id, neighborhood_id, neighborhood_size,
 		                        use_space_partitioning != 0, sampler_variance, lo_number, seed);

@@ -32,7 +32,7 @@ def shim():
              use_sp=True, variance=0.1):
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         prob = np.ascontiguousarray(prob, dtype=np.float64)
-        model, mask = np.full(9, np.nan), np.zeros(len(pts) + 1, dtype=np.uint8)
+        model, mask = np.full(12, np.nan), np.zeros(len(pts) + 1, dtype=np.uint8)
         ml, kl = C.c_int(), C.c_int()
         K1 = np.ascontiguousarray(K1 if K1 is not None else np.eye(3), dtype=np.float64)
         K2 = np.ascontiguousarray(K2 if K2 is not None else np.eye(3), dtype=np.float64)
@@ -98,3 +98,15 @@ def test_cpp_entry_points_failure_conventions(shim):
     rng = np.random.default_rng(0)                                                     # no model: count 0, all-false mask
     count, H, mask = call(_cabi.H, rng.uniform(0, 1000, (50, 4)), [], (1000,) * 4, 0.975, 1e-6, 1, 0, 4.0, 1, max_iters=200)
     assert count == 0 and len(mask) == 50 and not mask.any()
+
+
+def test_cpp_find6dpose_equals_python(shim):
+    """find6DPose_ (include/gcransac_python.h:177-211) called from the C++ translation unit == pygcransac.find6DPose."""
+    pyg, call = shim
+    from pygcransac import _cabi, synth
+    pts, P0, inl = synth.pnp_scene(600, 0.5, seed=9)
+    count, P, mask = call(_cabi.PNP, pts, [], (0, 0, 0, 0), 0.975, 2.0 / synth.FOCAL, 0, 0, 0.6, 3)
+    Pp, maskp = pyg.find6DPose(pts, [], threshold=2.0 / synth.FOCAL, sampler=0, neighborhood_size=0.6, max_iters=5000, seed=3)
+    assert count == mask.sum() == maskp.sum() > 0.9 * inl.sum() and np.array_equal(mask, maskp)
+    assert P.shape == (12,) and np.array_equal(P.reshape(3, 4), Pp) and np.abs(Pp - P0).max() < 5e-3
+    assert call(_cabi.PNP, pts, [], (0, 0, 0, 0), 0.975, 2.0 / synth.FOCAL, 0, 1, 0.6, 3)[0] == 0      # unknown neighbourhood id

@@ -290,3 +290,38 @@ def test_findessential_matches_reference_run(pyg, ref, oracle):
         pyg.findEssentialMatrix(pts, np.eye(2), K, 10, 10, 10, 10, [])
     with pytest.raises(ValueError):
         pyg.findEssentialMatrix(np.zeros((4, 4)), K, K, 10, 10, 10, 10, [])
+
+
+def test_find6dpose_matches_reference_run(pyg, ref, oracle):
+    """find6DPose (py/gcransac_python.cpp:1026-1272: GCRANSAC<DefaultPnPEstimator>, P3P minimal solver, radius neighbourhood
+    over the 5-column rows, the non-minimal fit on the inliers replacing the pose at the end) against the reference's
+    verbatim GCRANSAC<>::run over the oracle's PnP estimator (same stated non-minimal solver: DLT + the LM of refine_pnp):
+    iteration / graph-cut / LO-sample counts, masks, poses -- a synthetic scene (with and without the spatial term) and
+    the reference's own example scene with the notebook's 75 % outliers."""
+    import os
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(GOLDEN, "pose6dscene.npz"))
+    spts, P0, sinl = synth.pnp_scene(800, 0.5, seed=21)
+    cases = [(spts, 2.0 / synth.FOCAL, 0.975, 0.6, 3, P0, sinl, 5e-3),
+             (spts, 2.0 / synth.FOCAL, 0.0, 0.6, 4, P0, sinl, 5e-3),
+             (g["pts"], float(g["threshold"]), 0.975, 8.0, 5, g["gt_pose"], g["inlier"], 2e-2)]
+    for pts, thr, weight, radius, seed, P_true, inl, tol in cases:
+        P, mask = pyg.find6DPose(pts, [], threshold=thr, conf=0.99, spatial_coherence_weight=weight, max_iters=5000,
+                                 min_iters=50, sampler=0, neighborhood=0, neighborhood_size=radius, seed=seed)
+        st = pyg.last_statistics
+        want = ref.run(O.PNP, pts, np.ones(4), 1, thr, conf=0.99, spatial_weight=weight, max_iters=5000, min_iters=50,
+                       lo_number=50, seed=seed, radius=radius if weight > 0 else 0.0, f_ba=8)
+        assert P is not None and P.shape == (3, 4)
+        assert st["iteration_number"] == want["stats"]["iterations"], (st, want["stats"])
+        assert st["graph_cut_number"] == want["stats"]["graph_cuts"] and st["lo_samples"] == want["stats"]["lo_samples"]
+        assert (mask != want["mask"]).sum() <= 2, (int(mask.sum()), int(want["mask"].sum()))
+        W = want["model"].reshape(3, 4)
+        assert np.abs(P[:, :3] - W[:, :3]).max() < 1e-5 and np.abs(P[:, 3] - W[:, 3]).max() < 1e-5 * max(1.0, np.abs(W[:, 3]).max())
+        assert (mask & inl).sum() > 0.9 * inl.sum()
+        assert np.abs(P[:, :3] - P_true[:, :3]).max() < tol
+    # binding behaviour: shape errors, unknown neighbourhood id, P-NAPSAC
+    with pytest.raises(ValueError):
+        pyg.find6DPose(np.zeros((10, 4)), [])
+    with pytest.raises(ValueError):
+        pyg.find6DPose(np.zeros((3, 5)), [])
+    assert pyg.find6DPose(spts, [], neighborhood=1)[0] is None and pyg.find6DPose(spts, [], sampler=2)[0] is None

@@ -291,3 +291,48 @@ def test_refit_e_bundle_adjustment_matches_oracle(gcr_ctx, oracle):
         assert min(_up_to_scale(Et, M) for M in got[ok.astype(bool)]) < 5e-3
     got, ok = gcr_ctx.refit_e_ba(idx[:5])
     assert not ok.any()
+
+
+def test_refit_pnp_matches_oracle(gcr_ctx, oracle):
+    """gcr_refit with GCR_PNP (normalised DLT + the LM of refine_pnp, one CTA per index set) against the oracle: synthetic
+    scenes with noise, several sets per launch, weights in both index modes, the reference's example scene; < 6 points: none."""
+    import os
+    from conftest import GOLDEN
+    pts, P0, inl = synth.pnp_scene(1200, 0.3, seed=17)
+    gcr_ctx.points_upload(pts)
+    rng = np.random.default_rng(2)
+    inl_idx = np.nonzero(inl)[0]
+    sets = _index_sets(rng, inl_idx, [21, 21, 60, 400, 6, 5])
+    got, ok = gcr_ctx.refit(_cabi.PNP, sets)
+    assert list(ok) == [1, 1, 1, 1, 1, 0]
+    for s, M in zip(sets[:5], got):
+        want = oracle.refit_pnp(pts, s)
+        assert np.abs(M - want).max() < 1e-7, np.abs(M - want).max()
+    assert np.abs(got[3] - P0).max() < 5e-3
+    w = rng.uniform(0.2, 1.0, size=len(pts))
+    s = sets[3]
+    got_p, _ = gcr_ctx.refit(_cabi.PNP, [s], weights=w[: len(s)], weight_mode=_cabi.WEIGHT_POSITIONAL)
+    got_b, _ = gcr_ctx.refit(_cabi.PNP, [s], weights=w, weight_mode=_cabi.WEIGHT_BY_POINT)
+    assert np.abs(got_p[0] - oracle.refit_pnp(pts, s, weights=w[: len(s)])).max() < 1e-7
+    assert np.abs(got_b[0] - oracle.refit_pnp(pts, s, weights=w[s])).max() < 1e-7
+    g = np.load(os.path.join(GOLDEN, "pose6dscene.npz"))
+    gcr_ctx.points_upload(g["pts"])
+    idx = np.nonzero(g["inlier"])[0].astype(np.uint32)
+    got, ok = gcr_ctx.refit(_cabi.PNP, [idx, idx[:21]])
+    assert ok.all()
+    for M, key in zip(got, ("epnp_lm_all", "epnp_lm_21")):
+        G = g[key]
+        assert np.abs(M[:, :3] - G[:, :3]).max() < 1e-4 and np.abs(M[:, 3] - G[:, 3]).max() < 1e-4 * np.abs(G[:, 3]).max()
+
+
+def test_radius_graph_five_columns(gcr_ctx):
+    """find6DPose_'s neighbourhood: the radius graph over the whole 5-column row (u v X Y Z)."""
+    pts, _, _ = synth.pnp_scene(900, 0.3, seed=5)
+    gcr_ctx.points_upload(pts)
+    off, nbr = gcr_ctx.radius_graph(0.8)
+    f = pts.astype(np.float32)
+    d = f[:, None, :] - f[None, :, :]
+    d2 = (((d[..., 0] ** 2 + d[..., 1] ** 2) + d[..., 2] ** 2) + d[..., 3] ** 2) + d[..., 4] ** 2
+    A = (d2 < np.float32(0.8) ** 2) & ~np.eye(len(pts), dtype=bool)
+    assert np.array_equal(np.nonzero(A)[1].astype(np.uint32), nbr) and len(nbr) > 1000
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(A.sum(1))]).astype(np.uint32))

@@ -337,3 +337,39 @@ def test_e_bundle_adjustment_against_scipy(oracle):
     assert 1 <= len(models) <= 40
     assert min(min(np.abs(M / np.linalg.norm(M) - Et).max(), np.abs(M / np.linalg.norm(M) + Et).max()) for M in models) < 5e-3
     assert len(oracle.polish_e_ba(pts, idx[:5])) == 0                       # sampleSize() of the BA solver is 6
+
+
+def test_pnp_nonminimal_against_opencv_epnp_golden(oracle):
+    """The stated non-minimal absolute-pose solver (oracle/gcr_oracle_pba.cpp: normalised DLT + the LM of refine_pnp) against
+    golden poses made WITHOUT this repository's code (oracle/gen_pnp_fixture.py: OpenCV's EPnP -- the reference's
+    initialiser -- refined by scipy least-squares) on the reference's own example scene.  The LM stops on the reference's
+    tolerances (gradient / step 1e-8), hence 1e-4 rather than 1e-9."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "pose6dscene.npz"))
+    pts, idx = g["pts"], np.nonzero(g["inlier"])[0].astype(np.uint32)
+
+    def cost(P, ii):
+        Z = pts[ii, 2:5] @ P[:, :3].T + P[:, 3]
+        return ((Z[:, :2] / Z[:, 2:] - pts[ii, :2]) ** 2).sum()
+
+    for ii, key in ((idx, "epnp_lm_all"), (idx[:21], "epnp_lm_21")):
+        P, G = oracle.refit_pnp(pts, ii), g[key]
+        assert np.abs(P[:, :3] - G[:, :3]).max() < 1e-4 and np.abs(P[:, 3] - G[:, 3]).max() < 1e-4 * np.abs(G[:, 3]).max()
+        assert abs(np.linalg.det(P[:, :3]) - 1) < 1e-12 and np.abs(P[:, :3] @ P[:, :3].T - np.eye(3)).max() < 1e-12
+        assert cost(P, ii) < 1e-10                                         # (the scene is noise-free: both sit in the minimum)
+        P2, iters = oracle.refine_pnp_lm(pts, ii, G)                       # the golden pose is a fixed point of the LM
+        assert iters == 0 and np.abs(P2 - G).max() < 1e-12
+    assert np.abs(oracle.refit_pnp(pts, idx)[:, :3] - g["gt_pose"][:, :3]).max() < 1e-4
+    assert oracle.refit_pnp(pts, idx[:5]) is None                          # fewer than six points: no model (stated)
+    # noisy synthetic scene: DLT + LM and EPnP-like start + LM meet in the same minimum; weights (by position) act
+    spts, P0, inl = synth.pnp_scene(400, 0.0, seed=12)
+    si = np.arange(120, dtype=np.uint32)
+    Pa = oracle.refit_pnp(spts, si)
+    Pb, _ = oracle.refine_pnp_lm(spts, si, P0)
+    assert np.abs(Pa - Pb).max() < 1e-7 and np.abs(Pa - P0).max() < 5e-3
+    w = np.ones(len(si))
+    w[60:] = 0.0
+    moved = spts.copy()
+    moved[60:120, :2] += 0.3
+    assert np.abs(oracle.refit_pnp(moved, si, weights=w) - oracle.refit_pnp(spts, si[:60])).max() < 1e-6
