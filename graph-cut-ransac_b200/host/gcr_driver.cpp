@@ -1,6 +1,7 @@
 // gcr_driver.cpp -- see gcr_driver.h.  Host C++; the only compile-time dependency on the reference tree is its
 // vendored Boykov-Kolmogorov max-flow (energy.h / graph.h + graph.cpp / maxflow.cpp), which stays the reference's code.
 #include "gcr_driver.h"
+#include "gcr_backend.h"
 #include "gcr_host_samplers.h"
 
 #include <algorithm>
@@ -63,27 +64,11 @@ namespace
 		return r * r * (a + b) / (a * b);
 	}
 
-	struct DeviceBuffer
-	{
-		gcr_ctx *ctx = nullptr;
-		void *p = nullptr;
-		size_t bytes = 0;
-		~DeviceBuffer() { if (p) gcr_free(ctx, p); }
-		bool ensure(gcr_ctx *c, size_t need)
-		{
-			ctx = c;
-			if (need <= bytes)
-				return true;
-			if (p) gcr_free(ctx, p);
-			p = nullptr;
-			bytes = 0;
-			if (gcr_malloc(ctx, need, &p) != GCR_OK)
-				return false;
-			bytes = need;
-			return true;
-		}
-		template <class T> T *as() const { return reinterpret_cast<T *>(p); }
-	};
+	using gcr_host::Backend;
+	using gcr_host::BatchOut;
+	using gcr_host::BatchSpec;
+	using gcr_host::DirectBackend;
+	using gcr_host::LoSpec;
 
 	// One of the two inlier containers of GCRANSAC::run (temp_inner_inliers, GCRANSAC.h:245-247).  Every getScore of the
 	// reference overwrites the current container; here the contents are only materialised when somebody reads them.
@@ -108,7 +93,7 @@ namespace
 	class Driver
 	{
 	public:
-		gcr_ctx *ctx;
+		Backend *be = nullptr; // the device operations: one pair on its own context, or a seat in the batch engine
 		int problem, n, m, mm, rm; // rm = models per non-minimal refit (1: H, F, PnP; up to 10: E)
 		int ml = 9, cols = 4;      // model length (12: PnP's 3 x 4 pose) and point columns (5: PnP's u v X Y Z)
 		const double *pts;
@@ -129,13 +114,13 @@ namespace
 		bool nested = false;
 		double pp_H[9] = {0};
 		double f_min_ratio = 0.5; // minimum_inlier_ratio_in_validity_check (:91); the inner estimator is built with 0.0 (:540)
-		std::vector<uint32_t> h_samples;
+		std::vector<uint32_t> &h_samples = batch.samples;
+		std::vector<uint32_t> explicit_samples; // samplers 2 / 4: the batch's index sets, drawn on the host
 		// FP64 scores / inlier lists of the batch's record candidates, evaluated in ONE launch (prefetch_candidates)
 		std::vector<size_t> cand_slot;
 		std::vector<double> cand_score;
 		std::vector<uint32_t> cand_count;
 		std::vector<uint32_t> cand_idx; // [candidate][n]
-		DeviceBuffer d_cand_models, d_cand_scores, d_cand_counts, d_cand_idx;
 
 		// sampler 4: the AR-Sampler's sequence, drawn ahead on the host (gcr_host_samplers.h)
 		gcr_host::AdaptiveReordering ar_sampler;
@@ -145,20 +130,17 @@ namespace
 		int B = 0;
 		uint64_t batch_first = 0;
 		int batch_count = 0;
-		DeviceBuffer d_samples, d_models, d_valid, d_scores, d_counts;
-		std::vector<uint8_t> h_valid;
-		std::vector<float> h_scores;
-		std::vector<uint32_t> h_counts;
-		// the models of a batch stay on the device (72 B per slot, 2.9 MB per 4096 five-point samples): the host fetches the
-		// few it looks at -- record candidates, the model behind a lazy inlier container -- into this cache
-		std::vector<double> h_models;
-		std::vector<uint8_t> h_model_have;
+		// the current batch: flags, FP32 scores, exact counts of every slot; the models of a large batch stay on the device
+		// (72 B per slot, 2.9 MB per 4096 five-point samples) and the host fetches the few it looks at -- record candidates,
+		// the model behind a lazy inlier container -- into batch.models
+		BatchOut batch;
+		std::vector<uint8_t> &h_valid = batch.valid;
+		std::vector<float> &h_scores = batch.scores;
+		std::vector<uint32_t> &h_counts = batch.counts;
+		std::vector<double> &h_models = batch.models;
+		std::vector<uint8_t> &h_model_have = batch.model_have;
 		InlierBuffer *live_buffers = nullptr; // the two containers of the run in progress (their lazy models are resolved
 		                                      // before a new batch overwrites d_models)
-		// exact scoring
-		DeviceBuffer d_one_model, d_one_score, d_one_count, d_idx, d_res;
-		// LO batch
-		DeviceBuffer d_pool, d_sets, d_offsets, d_lmodels, d_lok, d_lscores, d_lcounts, d_weights;
 		// grid
 		std::vector<uint32_t> cell_of_point, sorted_idx, cell_offsets;
 		bool have_grid = false;
@@ -170,12 +152,15 @@ namespace
 		// sides: the device copy feeds gcr_labeling_terms, the host copy the max-flow graph
 		std::vector<uint32_t> edges; // [n_edges][2]
 		size_t n_edges = 0;
-		DeviceBuffer d_edges, d_edge_offsets, d_unary, d_pairwise, d_lab_model;
 		std::vector<double> h_unary, h_pairwise;
 
-		bool fail(const char *what)
+		// DEGENSAC's inner run needs the same points on a backend of its own when the outer one is a seat of the batch engine
+		// (its minimal solver is not one of the engine's batched operations): null = the inner run shares `be`
+		Backend *(*nested_backend)(Driver *) = nullptr;
+		void *owner = nullptr; // the batch engine's per-worker state, for nested_backend
+		bool fail(const char *)
 		{
-			error = std::string(what) + ": " + gcr_last_error(ctx);
+			error = be->error;
 			return false;
 		}
 
@@ -183,36 +168,12 @@ namespace
 		bool exact(const double *model, Score &s, std::vector<uint32_t> *inliers, std::vector<double> *residuals = nullptr)
 		{
 			++st.exact_rescores;
-			if (!residuals)
-			{
-				uint32_t count = 0;
-				if (inliers) inliers->resize(n);
-				if (gcr_getscore_host(ctx, problem, scoring, 0, model, T, S.threshold, &s.value, &count,
-				                      inliers ? inliers->data() : nullptr) != GCR_OK)
-					return fail("gcr_getscore_host");
-				s.inliers = count;
-				if (inliers) inliers->resize(count);
-				return true;
-			}
-			if (!d_one_model.ensure(ctx, ml * sizeof(double)) || !d_one_score.ensure(ctx, sizeof(double)) ||
-			    !d_one_count.ensure(ctx, sizeof(uint32_t)) || !d_idx.ensure(ctx, (size_t)n * sizeof(uint32_t)) ||
-			    !d_res.ensure(ctx, (size_t)n * sizeof(double)))
-				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_one_model.p, model, ml * sizeof(double)) != GCR_OK)
-				return fail("gcr_memcpy_h2d");
-			if (gcr_score_exact(ctx, problem, scoring, 0, d_one_model.as<double>(), 1, S.threshold, d_one_score.as<double>(),
-			                    d_one_count.as<uint32_t>(), d_idx.as<uint32_t>(), d_res.as<double>()) != GCR_OK)
-				return fail("gcr_score_exact");
 			uint32_t count = 0;
-			residuals->resize(n);
 			if (inliers) inliers->resize(n);
-			// every read-back of the call is queued, one synchronise delivers them (the list is copied whole: 4 n bytes)
-			if (gcr_memcpy_d2h_async(ctx, &s.value, d_one_score.p, sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, &count, d_one_count.p, sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, residuals->data(), d_res.p, (size_t)n * sizeof(double)) != GCR_OK ||
-			    (inliers && gcr_memcpy_d2h_async(ctx, inliers->data(), d_idx.p, (size_t)n * sizeof(uint32_t)) != GCR_OK) ||
-			    gcr_sync(ctx) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
+			if (residuals) residuals->resize(n);
+			if (!be->exact(model, scoring, T, S.threshold, s.value, count, inliers ? inliers->data() : nullptr,
+			               residuals ? residuals->data() : nullptr))
+				return fail("exact");
 			s.inliers = count;
 			if (inliers) inliers->resize(count);
 			return true;
@@ -221,30 +182,14 @@ namespace
 		// model of slot `slot` of the current batch, fetched on first use (one 72-byte read-back)
 		const double *model_of(size_t slot)
 		{
-			if (!h_model_have[slot])
-			{
-				if (gcr_memcpy_d2h(ctx, &h_models[slot * ml], d_models.as<double>() + slot * ml, ml * sizeof(double)) != GCR_OK)
-				{
-					fail("gcr_memcpy_d2h");
-					return nullptr;
-				}
-				h_model_have[slot] = 1;
-			}
+			if (!h_model_have[slot] && !fetch_models(std::vector<size_t>(1, slot)))
+				return nullptr;
 			return &h_models[slot * ml];
 		}
-		// several at once: the copies are queued, one synchronise delivers them
+		// several at once: one round trip
 		bool fetch_models(const std::vector<size_t> &slots)
 		{
-			bool queued = false;
-			for (size_t slot : slots)
-				if (!h_model_have[slot])
-				{
-					if (gcr_memcpy_d2h_async(ctx, &h_models[slot * ml], d_models.as<double>() + slot * ml, ml * sizeof(double)) != GCR_OK)
-						return fail("gcr_memcpy_d2h");
-					h_model_have[slot] = 1;
-					queued = true;
-				}
-			return !queued || gcr_sync(ctx) == GCR_OK || fail("gcr_sync");
+			return be->fetch_models(slots, batch) || fail("fetch_models");
 		}
 		bool resolve_model(InlierBuffer &b)
 		{
@@ -397,7 +342,7 @@ namespace
 			std::vector<uint8_t> ok;
 			{
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)h_inliers.size());
-				if (!refit(h_inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, false, GCR_H))
+				if (!refit(h_inliers.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok, GCR_H))
 				{
 					failed = true;
 					return false;
@@ -407,7 +352,13 @@ namespace
 			}
 			++st.degensac_runs;
 			Driver inner;
-			inner.ctx = ctx;
+			Backend *inner_be = nested_backend ? nested_backend(this) : be; // the inner run works on the points the outer run uploaded
+			if (!inner_be)
+			{
+				failed = true;
+				return false;
+			}
+			inner.be = inner_be;
 			inner.problem = GCR_F;
 			inner.variant = 1;
 			inner.nested = true;
@@ -448,78 +399,40 @@ namespace
 		// ---- one GPU batch of the main loop: samples [first, first + B) -> models, valid flags, FP32 scores, exact counts ----
 		bool run_batch(uint64_t first)
 		{
-			const size_t K = (size_t)B * mm;
 			if (live_buffers && !h_model_have.empty()) // a lazy container may still point into the batch about to be overwritten
 				for (int b = 0; b < 2; ++b)
 					if (live_buffers[b].lazy && !resolve_model(live_buffers[b]))
 						return false;
-			if (!d_samples.ensure(ctx, (size_t)B * m * sizeof(uint32_t)) || !d_models.ensure(ctx, K * ml * sizeof(double)) ||
-			    !d_valid.ensure(ctx, K) || !d_scores.ensure(ctx, K * sizeof(float)) || !d_counts.ensure(ctx, K * sizeof(uint32_t)))
-				return fail("gcr_malloc");
-			// PROSAC draws are numbered from k = 1 (prosac_sampler.h:207-236); draw g of the run is PROSAC sample g + 1
+			BatchSpec spec;
+			spec.variant = variant;
+			spec.pp_H = pp_H;
+			spec.sampler = S.sampler;
+			spec.first = first;
+			spec.B = B;
+			spec.m = m;
+			spec.mm = mm;
+			spec.seed = S.seed;
+			spec.scoring = scoring;
+			spec.threshold = S.threshold;
 			if (S.sampler == 4 || S.sampler == 2)
 			{
 				// AdaptiveReorderingSampler / ProgressiveNapsacSampler (py/gcransac_python.cpp:4334-4359): the recurrence
 				// over the sample number runs on the host, the batch's index sets go up in one copy
-				h_samples.resize((size_t)B * m);
+				explicit_samples.resize((size_t)B * m);
 				if (S.sampler == 4)
-					ar_sampler.samples(first, (size_t)B, h_samples.data());
+					ar_sampler.samples(first, (size_t)B, explicit_samples.data());
 				else
-					pnapsac_sampler.samples(first, (size_t)B, h_samples.data());
-				if (gcr_memcpy_h2d(ctx, d_samples.p, h_samples.data(), (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
-					return fail("gcr_memcpy_h2d");
+					pnapsac_sampler.samples(first, (size_t)B, explicit_samples.data());
+				spec.explicit_samples = explicit_samples.data();
 			}
-			// sampler 3 = ImportanceSampler (NG-RANSAC, py/gcransac_python.cpp:4343-4346): draw g = sample g of stream 3
-			else if (gcr_sample(ctx, S.sampler == 1 ? GCR_PROSAC : S.sampler == 3 ? GCR_IMPORTANCE : GCR_UNIFORM, m,
-			               S.sampler == 1 ? first + 1 : first, B, S.seed, d_samples.as<uint32_t>()) != GCR_OK)
-				return fail("gcr_sample");
-			if (variant == 1)
-			{
-				if (gcr_solve_plane_parallax(ctx, d_samples.as<uint32_t>(), B, pp_H, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
-					return fail("gcr_solve_plane_parallax");
-			}
-			else if (gcr_solve_minimal(ctx, problem, d_samples.as<uint32_t>(), B, d_models.as<double>(), d_valid.as<uint8_t>()) != GCR_OK)
-				return fail("gcr_solve_minimal");
-			if (gcr_score(ctx, problem, scoring, d_models.as<double>(), d_valid.as<uint8_t>(), (int)K, S.threshold,
-			              GCR_SCORE_EXACT_COUNTS, d_scores.as<float>(), d_counts.as<uint32_t>()) != GCR_OK)
-				return fail("gcr_score");
-			h_valid.resize(K);
-			h_scores.resize(K);
-			h_counts.resize(K);
-			h_models.resize(K * ml);
-			// small batches (H, F: up to a few hundred KB) come back whole with the flags and scores -- one more queued copy,
-			// no later round trip; large ones (five-point batches: 0.7-2.9 MB) stay on the device and are fetched on demand
-			const bool models_with_batch = K * ml * sizeof(double) <= (size_t)(256 << 10);
-			h_model_have.assign(K, models_with_batch ? 1 : 0);
-			if (models_with_batch && gcr_memcpy_d2h_async(ctx, h_models.data(), d_models.p, K * ml * sizeof(double)) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			if (S.use_degensac && problem == GCR_F && variant == 0 && S.sampler != 4 && S.sampler != 2)
-			{
-				// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
-				h_samples.resize((size_t)B * m);
-				if (gcr_memcpy_d2h_async(ctx, h_samples.data(), d_samples.p, (size_t)B * m * sizeof(uint32_t)) != GCR_OK)
-					return fail("gcr_memcpy_d2h");
-			}
-			uint32_t dropped = 0;
-			if (gcr_memcpy_d2h_async(ctx, h_valid.data(), d_valid.p, K) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, h_scores.data(), d_scores.p, K * sizeof(float)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, h_counts.data(), d_counts.p, K * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_score_dropped_async(ctx, &dropped) != GCR_OK || gcr_sync(ctx) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			if (dropped)
-			{
-				// the FP64 re-check list overflowed (N x batch very large): these counts feed the inlier-container bookkeeping
-				// (lazy_count, the size check before IRLS), so they must be exact -- the same samples again, half at a time
-				// (a sample is a function of its index: batch boundaries change no result)
-				if (B <= 1)
-				{
-					error = "gcr_score: the FP64 re-check list overflows for a single sample";
-					return false;
-				}
-				B = (B + 1) / 2;
-				h_model_have.clear();
-				return run_batch(first);
-			}
+			// applyDegensac needs the minimal sample behind a candidate model (fundamental_estimator.h:344)
+			spec.want_samples = S.use_degensac && problem == GCR_F && variant == 0;
+			batch.samples.clear();
+			if (!be->run_batch(spec, batch))
+				return fail("run_batch");
+			if (spec.want_samples && spec.explicit_samples)
+				batch.samples.assign(explicit_samples.begin(), explicit_samples.begin() + (size_t)batch.B * m);
+			B = batch.B;
 			batch_first = first;
 			batch_count = B;
 			++st.gpu_batches;
@@ -563,22 +476,8 @@ namespace
 		bool exact_many(const double *models, size_t C, std::vector<double> &score, std::vector<uint32_t> &count,
 		                std::vector<uint32_t> &idx)
 		{
-			if (!d_cand_models.ensure(ctx, C * ml * sizeof(double)) || !d_cand_scores.ensure(ctx, C * sizeof(double)) ||
-			    !d_cand_counts.ensure(ctx, C * sizeof(uint32_t)) || !d_cand_idx.ensure(ctx, C * (size_t)n * sizeof(uint32_t)))
-				return fail("gcr_malloc");
-			if (gcr_memcpy_h2d(ctx, d_cand_models.p, models, C * ml * sizeof(double)) != GCR_OK)
-				return fail("gcr_memcpy_h2d");
-			if (gcr_score_exact(ctx, problem, scoring, 0, d_cand_models.as<double>(), (int)C, S.threshold, d_cand_scores.as<double>(),
-			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), nullptr) != GCR_OK)
-				return fail("gcr_score_exact");
-			score.resize(C);
-			count.resize(C);
-			idx.resize(C * (size_t)n);
-			if (gcr_memcpy_d2h_async(ctx, score.data(), d_cand_scores.p, C * sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, count.data(), d_cand_counts.p, C * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, idx.data(), d_cand_idx.p, C * (size_t)n * sizeof(uint32_t)) != GCR_OK ||
-			    gcr_sync(ctx) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
+			if (!be->exact_many(models, C, scoring, S.threshold, score, count, idx))
+				return fail("exact_many");
 			st.exact_rescores += C;
 			return true;
 		}
@@ -606,22 +505,9 @@ namespace
 			// pairwise weights: 8 bytes per edge read back from the device kernel when the graph came from the device anyway
 			// (n > 16384), else formed here from the per-point clamped distances (24 n bytes come back instead of 16 n + 8 E)
 			static const bool force_device_pairwise = getenv("GCR_DEVICE_PAIRWISE") != nullptr;
-			const bool device_pairwise = E > 0 && (n > 16384 || force_device_pairwise);
-			if (!d_lab_model.ensure(ctx, ml * sizeof(double)) || !d_unary.ensure(ctx, (size_t)n * 3 * sizeof(double)) ||
-			    !d_pairwise.ensure(ctx, std::max<size_t>(device_pairwise ? E : 0, 1) * sizeof(double)))
-				return fail("gcr_malloc");
-			h_unary.resize((size_t)n * 3); // [n][2] capacities, then [n] clamped distances
-			h_pairwise.resize(device_pairwise ? E : 0);
-			double *d_dist = d_unary.as<double>() + 2 * (size_t)n;
-			if (gcr_memcpy_h2d(ctx, d_lab_model.p, model, ml * sizeof(double)) != GCR_OK)
-				return fail("gcr_memcpy_h2d");
-			if (gcr_labeling_terms(ctx, problem, 0, d_lab_model.as<double>(), S.threshold, lambda, d_edges.as<uint32_t>(), E,
-			                       d_unary.as<double>(), device_pairwise ? d_pairwise.as<double>() : nullptr, d_dist) != GCR_OK)
-				return fail("gcr_labeling_terms");
-			if (gcr_memcpy_d2h_async(ctx, h_unary.data(), d_unary.p, (size_t)n * 3 * sizeof(double)) != GCR_OK ||
-			    (device_pairwise && gcr_memcpy_d2h_async(ctx, h_pairwise.data(), d_pairwise.p, E * sizeof(double)) != GCR_OK) ||
-			    gcr_sync(ctx) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
+			const bool device_pairwise = E > 0 && be->keeps_edges && (n > 16384 || force_device_pairwise);
+			if (!be->labeling_terms(model, S.threshold, lambda, E, device_pairwise, h_unary, h_pairwise))
+				return fail("labeling_terms");
 			++st.exact_rescores; // (one FP64 pass over the points, as the residual read-back it replaces)
 			const auto t0 = std::chrono::steady_clock::now();
 			const double *dist = h_unary.data() + 2 * (size_t)n;
@@ -646,89 +532,27 @@ namespace
 			return true;
 		}
 
-		// the run's edge list from a host-side structure (grids / radius graphs of up to 16384 points are built on the host)
+		// the run's edge list from a host-side structure (grids of up to 16384 points are built on the host)
 		bool upload_edges()
 		{
 			n_edges = edges.size() / 2;
-			if (n_edges == 0)
-				return true;
-			if (!d_edges.ensure(ctx, edges.size() * sizeof(uint32_t)))
-				return fail("gcr_malloc");
-			// (larger than the pinned ring when the neighbourhood is dense: gcr_memcpy_h2d then copies synchronously)
-			if (gcr_memcpy_h2d(ctx, d_edges.p, edges.data(), edges.size() * sizeof(uint32_t)) != GCR_OK)
-				return fail("gcr_memcpy_h2d");
-			return true;
-		}
-		// ... or built on the device next to the structure it comes from; the host keeps a copy for the max-flow graph
-		bool fetch_edges(uint64_t count)
-		{
-			n_edges = (size_t)count;
-			edges.resize(2 * n_edges);
-			if (n_edges && gcr_memcpy_d2h(ctx, edges.data(), d_edges.p, edges.size() * sizeof(uint32_t)) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			return true;
+			return be->set_edges(edges) || fail("set_edges");
 		}
 
 		// ---- non-minimal refit of `count` index sets (one GPU launch) ----
+		// the reference's default F estimator refines every non-minimal fit by bundle adjustment (types.h:78-80); DEGENSAC's
+		// inner estimator (variant 1) keeps the bare 8-point solver (fundamental_estimator.h:532-533)
+		int ba_frame_of(int rp, int ba_frame_override) const
+		{
+			return ba_frame_override ? ba_frame_override : (rp == GCR_F && variant == 0 && (S.f_bundle_adjustment & 1)) ? GCR_BA_HARTLEY : 0;
+		}
 		bool refit(const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
-		           const double *weights_by_point, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
-		           bool sets_on_device = false, int refit_problem = -1, int ba_frame_override = 0, bool defer_sync = false)
+		           const double *weights, size_t n_weights, int weight_mode, std::vector<double> &models, std::vector<uint8_t> &ok,
+		           int refit_problem = -1, int ba_frame_override = 0)
 		{
 			const int rp = refit_problem < 0 ? problem : refit_problem;
-			const int rm = refit_problem < 0 ? this->rm : gcr_max_refit_models(rp);
-			const int rml = gcr_model_len(rp);
-			const int count = (int)sizes.size();
-			size_t total = 0;
-			for (uint32_t v : sizes) total += v;
-			if (!sets_on_device)
-			{
-				if (!d_sets.ensure(ctx, std::max<size_t>(total, 1) * sizeof(uint32_t)))
-					return fail("gcr_malloc");
-				if (gcr_memcpy_h2d(ctx, d_sets.p, flat, total * sizeof(uint32_t)) != GCR_OK)
-					return fail("gcr_memcpy_h2d");
-			}
-			// offsets and sizes travel as one array (one copy instead of two): [offsets | sizes]
-			if (!d_offsets.ensure(ctx, 2 * count * sizeof(uint32_t)) ||
-			    !d_lmodels.ensure(ctx, (size_t)count * rm * rml * sizeof(double)) || !d_lok.ensure(ctx, (size_t)count * rm))
-				return fail("gcr_malloc");
-			std::vector<uint32_t> offsets_sizes(offsets.begin(), offsets.begin() + count);
-			offsets_sizes.insert(offsets_sizes.end(), sizes.begin(), sizes.begin() + count);
-			if (gcr_memcpy_h2d(ctx, d_offsets.p, offsets_sizes.data(), 2 * count * sizeof(uint32_t)) != GCR_OK)
-				return fail("gcr_memcpy_h2d");
-			const uint32_t *d_set_offsets = d_offsets.as<uint32_t>(), *d_set_sizes = d_offsets.as<uint32_t>() + count;
-			const double *d_w = nullptr;
-			if (weights_by_point)
-			{
-				if (!d_weights.ensure(ctx, (size_t)n * sizeof(double)))
-					return fail("gcr_malloc");
-				if (gcr_memcpy_h2d(ctx, d_weights.p, weights_by_point, (size_t)n * sizeof(double)) != GCR_OK)
-					return fail("gcr_memcpy_h2d");
-				d_w = d_weights.as<double>();
-			}
-			// the reference's default F estimator refines every non-minimal fit by bundle adjustment (types.h:78-80); DEGENSAC's
-			// inner estimator (variant 1) keeps the bare 8-point solver (fundamental_estimator.h:532-533)
-			const int ba_frame = ba_frame_override ? ba_frame_override
-			                                       : (rp == GCR_F && variant == 0 && (S.f_bundle_adjustment & 1)) ? GCR_BA_HARTLEY : 0;
-			if (ba_frame)
-			{
-				if (gcr_refit_f_ba(ctx, 0, d_sets.as<uint32_t>(), d_set_offsets, d_set_sizes, count, d_w, weight_mode,
-				                   ba_frame, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
-					return fail("gcr_refit_f_ba");
-			}
-			else if (gcr_refit(ctx, rp, 0, d_sets.as<uint32_t>(), d_set_offsets, d_set_sizes, count, d_w,
-			                   weight_mode, d_lmodels.as<double>(), d_lok.as<uint8_t>()) != GCR_OK)
-				return fail("gcr_refit");
-			models.resize((size_t)count * rm * rml);
-			ok.resize((size_t)count * rm);
-			if (defer_sync) // the caller queues more work on these models and synchronises once
-				return gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * rml * sizeof(double)) == GCR_OK &&
-				               gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) == GCR_OK
-				           ? true
-				           : fail("gcr_memcpy_d2h");
-			if (gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, (size_t)count * rm * rml * sizeof(double)) != GCR_OK ||
-			    gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, (size_t)count * rm) != GCR_OK || gcr_sync(ctx) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			return true;
+			return be->refit_sets(rp, ba_frame_of(rp, ba_frame_override), flat, offsets, sizes, weights, n_weights, weight_mode, models, ok) ||
+			       fail("refit_sets");
 		}
 
 		// ---- graphCutLocalOptimization (GCRANSAC.h:780-910) ----
@@ -751,44 +575,40 @@ namespace
 				std::vector<uint8_t> ok;
 				std::vector<float> scores32;
 				int n_models = 0;
+				LoSpec lo;
+				lo.pool = inliers.data();
+				lo.pool_size = inliers.size();
+				lo.sample_size = sample_size;
+				lo.first_index = st.lo_samples;
+				lo.trials = trials;
+				lo.seed = S.seed;
+				lo.stream = S.sampler == 1 ? 2u : 1u;
+				lo.refit_problem = problem;
+				lo.ba_frame = ba_frame_of(problem, 0);
+				lo.rm = rm;
+				lo.scoring = scoring;
+				lo.threshold = S.threshold;
 				if (sample_size < inliers.size() && trials > 0)
 				{
 					// inner RANSAC as one batch: `trials` pool samples -> refits -> FP32 scores
-					if (!d_pool.ensure(ctx, inliers.size() * sizeof(uint32_t)) ||
-					    !d_sets.ensure(ctx, (size_t)trials * sample_size * sizeof(uint32_t)))
-						return fail("gcr_malloc");
-					if (gcr_memcpy_h2d(ctx, d_pool.p, inliers.data(), inliers.size() * sizeof(uint32_t)) != GCR_OK)
-						return fail("gcr_memcpy_h2d");
-					if (gcr_sample_from_pool(ctx, d_pool.as<uint32_t>(), (uint32_t)inliers.size(), (int)sample_size, st.lo_samples,
-					                         trials, S.seed, S.sampler == 1 ? 2u : 1u, d_sets.as<uint32_t>()) != GCR_OK)
-						return fail("gcr_sample_from_pool");
+					lo.sample_pool = true;
+					if (!be->lo_batch(lo, models, ok, scores32))
+						return fail("lo_batch");
 					st.lo_samples += trials;
-					std::vector<uint32_t> offsets(trials), sizes(trials, (uint32_t)sample_size);
-					for (int t = 0; t < trials; ++t) offsets[t] = (uint32_t)(t * sample_size);
-					if (!refit(nullptr, offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok, true, -1, 0, true))
-						return false; // (read-backs queued: delivered together with the scores below)
 					n_models = trials * rm; // trial-major, the solver's model order inside a trial (:866)
 				}
 				else if ((size_t)m < inliers.size() && trials > 0)
 				{
 					// all inliers, every trial fits the same model: once is enough (later trials cannot beat it, strict '<')
-					std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
-					if (!refit(inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
-						return false;
+					lo.sample_pool = false;
+					if (!be->lo_batch(lo, models, ok, scores32))
+						return fail("lo_batch");
 					n_models = 0;
 					for (int q = 0; q < rm; ++q)
 						if (ok[q]) n_models = rm;
 				}
 				if (n_models > 0)
 				{
-					if (!d_lscores.ensure(ctx, n_models * sizeof(float)))
-						return fail("gcr_malloc");
-					if (gcr_score(ctx, problem, scoring, d_lmodels.as<double>(), d_lok.as<uint8_t>(), n_models, S.threshold, 0,
-					              d_lscores.as<float>(), nullptr) != GCR_OK)
-						return fail("gcr_score");
-					scores32.resize(n_models);
-					if (gcr_memcpy_d2h(ctx, scores32.data(), d_lscores.p, n_models * sizeof(float)) != GCR_OK)
-						return fail("gcr_memcpy_d2h");
 					st.models_scored += n_models;
 					// the trials that can become the round's best: running records of the FP32 scores, evaluated in FP64
 					// in one launch (the sequential loop below falls back to a single evaluation for anything else)
@@ -878,13 +698,13 @@ namespace
 					}
 					// ... and read by POSITION by the H / 8-point solvers, by POINT by the Stewenius solver
 					// (solver_essential_matrix_five_point_stewenius.h:143): reproduced literally
-					if (!refit(inliers.data(), offsets, sizes, weights.data(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
+					if (!refit(inliers.data(), offsets, sizes, weights.data(), weights.size(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
 					           models, ok))
 						return false;
 					for (uint32_t idx : inliers)
 						weights[idx] = 0;
 				}
-				else if (!refit(inliers.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok)) // :682-688
+				else if (!refit(inliers.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok)) // :682-688
 					return false;
 				std::vector<const double *> found;
 				for (int q = 0; q < rm; ++q)
@@ -932,51 +752,10 @@ namespace
 		bool build_radius_graph()
 		{
 			have_radius_graph = false;
-			DeviceBuffer dc, doff, dn;
-			if (!dc.ensure(ctx, (size_t)n * 4) || !doff.ensure(ctx, ((size_t)n + 1) * 4))
-				return fail("gcr_malloc");
-			if (gcr_radius_graph_count(ctx, 0, S.neighborhood_radius, dc.as<uint32_t>()) != GCR_OK)
-				return fail("gcr_radius_graph_count");
-			std::vector<uint32_t> counts(n);
-			if (gcr_memcpy_d2h(ctx, counts.data(), dc.p, (size_t)n * 4) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
-			nbr_offsets.assign((size_t)n + 1, 0u);
-			uint64_t total64 = 0;
-			for (int i = 0; i < n; ++i)
-			{
-				total64 += counts[i];
-				nbr_offsets[i + 1] = (uint32_t)total64;
-			}
-			if (total64 >= (1ull << 31))
-			{
-				// (a radius this large against the point spread is not a sparse neighbourhood: the reference's own N x N edge
-				// matrix would not fit either)
-				error = "neighborhood_radius gives more than 2^31 neighbour entries: choose a smaller radius";
-				return false;
-			}
-			const size_t total = (size_t)total64;
-			nbr_idx.resize(total);
-			if (total)
-			{
-				if (!dn.ensure(ctx, total * 4))
-					return fail("gcr_malloc");
-				if (gcr_memcpy_h2d(ctx, doff.p, nbr_offsets.data(), ((size_t)n + 1) * 4) != GCR_OK)
-					return fail("gcr_memcpy_h2d");
-				if (gcr_radius_graph_fill(ctx, 0, S.neighborhood_radius, doff.as<uint32_t>(), dn.as<uint32_t>()) != GCR_OK)
-					return fail("gcr_radius_graph_fill");
-				// labeling()'s edges (i, j > i) straight from the CSR on the device (the distance test is symmetric: half the entries)
-				if (!d_edge_offsets.ensure(ctx, ((size_t)n + 1) * 4) || !d_edges.ensure(ctx, std::max<size_t>(total / 2, 1) * 8))
-					return fail("gcr_malloc");
-				if (gcr_csr_edges(ctx, doff.as<uint32_t>(), dn.as<uint32_t>(), d_edge_offsets.as<uint32_t>(), d_edges.as<uint32_t>(),
-				                  total / 2) != GCR_OK)
-					return fail("gcr_csr_edges");
-				if (gcr_memcpy_d2h(ctx, nbr_idx.data(), dn.p, total * 4) != GCR_OK)
-					return fail("gcr_memcpy_d2h");
-				if (!fetch_edges(total / 2))
-					return false;
-			}
-			else
-				n_edges = 0;
+			// the CSR and labeling()'s edges (i, j > i), both built on the device
+			if (!be->radius_graph(S.neighborhood_radius, nbr_offsets, nbr_idx, edges))
+				return fail("radius_graph");
+			n_edges = edges.size() / 2;
 			have_radius_graph = true;
 			return true;
 		}
@@ -1006,9 +785,6 @@ namespace
 				}
 				return true;
 			}
-			DeviceBuffer dk, ds, dof;
-			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
-				return fail("gcr_malloc");
 			for (int l = 0; l < 4; ++l)
 			{
 				double cell_sizes[4];
@@ -1016,15 +792,9 @@ namespace
 					cell_sizes[d] = S.image_sizes[d] / layer_cells[l];
 				uint32_t n_cells = 0;
 				uint64_t neighbor_number = 0;
-				if (gcr_grid_build(ctx, 0, cell_sizes, layer_cells[l], dk.as<uint64_t>(), ds.as<uint32_t>(), dof.as<uint32_t>(),
-				                   &n_cells, &neighbor_number) != GCR_OK)
-					return fail("gcr_grid_build");
 				gcr_host::GridLayer &g = layers[l];
-				g.sorted_idx.resize(n);
-				g.cell_offsets.resize((size_t)n_cells + 1);
-				if (gcr_memcpy_d2h(ctx, g.sorted_idx.data(), ds.p, (size_t)n * 4) != GCR_OK ||
-				    gcr_memcpy_d2h(ctx, g.cell_offsets.data(), dof.p, ((size_t)n_cells + 1) * 4) != GCR_OK)
-					return fail("gcr_memcpy_d2h");
+				if (!be->grid_device(cell_sizes, layer_cells[l], g.sorted_idx, g.cell_offsets, n_cells, neighbor_number, nullptr))
+					return fail("grid_device");
 				g.cell_of_point.resize(n);
 				for (uint32_t c = 0; c < n_cells; ++c)
 					for (uint32_t q = g.cell_offsets[c]; q < g.cell_offsets[c + 1]; ++q)
@@ -1080,36 +850,18 @@ namespace
 				}
 				return upload_edges();
 			}
-			DeviceBuffer dk, ds, dof;
-			if (!dk.ensure(ctx, (size_t)n * 8) || !ds.ensure(ctx, (size_t)n * 4) || !dof.ensure(ctx, ((size_t)n + 1) * 4))
-				return fail("gcr_malloc");
 			uint32_t n_cells = 0;
 			uint64_t neighbor_number = 0;
-			if (gcr_grid_build(ctx, 0, S.cell_sizes, S.cells_per_axis, dk.as<uint64_t>(), ds.as<uint32_t>(), dof.as<uint32_t>(),
-			                   &n_cells, &neighbor_number) != GCR_OK)
-				return fail("gcr_grid_build");
-			sorted_idx.resize(n);
-			cell_offsets.resize((size_t)n_cells + 1);
-			if (gcr_memcpy_d2h(ctx, sorted_idx.data(), ds.p, (size_t)n * 4) != GCR_OK ||
-			    gcr_memcpy_d2h(ctx, cell_offsets.data(), dof.p, ((size_t)n_cells + 1) * 4) != GCR_OK)
-				return fail("gcr_memcpy_d2h");
+			// cells and labeling()'s edge list from the sorted cells, both on the device
+			if (!be->grid_device(S.cell_sizes, S.cells_per_axis, sorted_idx, cell_offsets, n_cells, neighbor_number, &edges))
+				return fail("grid_device");
 			cell_of_point.resize(n);
 			for (uint32_t c = 0; c < n_cells; ++c)
 				for (uint32_t q = cell_offsets[c]; q < cell_offsets[c + 1]; ++q)
 					cell_of_point[sorted_idx[q]] = c;
 			have_grid = true;
-			// labeling()'s edge list from the sorted cells, on the device (neighbor_number = sum over cells of s (s - 1) / 2)
-			if (neighbor_number >= (1ull << 31))
-			{
-				error = "the grid neighbourhood has more than 2^31 point pairs: use more cells per axis";
-				return false;
-			}
-			if (!d_edge_offsets.ensure(ctx, ((size_t)n + 1) * 4) || !d_edges.ensure(ctx, std::max<size_t>((size_t)neighbor_number, 1) * 8))
-				return fail("gcr_malloc");
-			if (gcr_grid_edges(ctx, ds.as<uint32_t>(), dof.as<uint32_t>(), n_cells, d_edge_offsets.as<uint32_t>(), d_edges.as<uint32_t>(),
-			                   neighbor_number) != GCR_OK)
-				return fail("gcr_grid_edges");
-			return fetch_edges(neighbor_number);
+			n_edges = edges.size() / 2;
+			return true;
 		}
 
 		// ---- GCRANSAC::run ----
@@ -1118,6 +870,10 @@ namespace
 			memset(&st, 0, sizeof(st));
 			ml = gcr_model_len(problem);
 			cols = problem == GCR_PNP ? 5 : 4;
+			be->problem = problem;
+			be->n = n;
+			be->ml = ml;
+			be->cols = cols;
 			m = variant == 1 ? 2 : gcr_sample_size(problem);
 			mm = variant == 1 ? 1 : gcr_max_models(problem);
 			B = S.batch > 0 ? S.batch : 1024;
@@ -1136,9 +892,9 @@ namespace
 				// will read them: the radius graph, or grids over more than 16384 points.
 				const bool graph_wanted = S.spatial_coherence_weight > 0.0 && S.do_local_optimization;
 				if (((graph_wanted && S.neighborhood == 1) || ((graph_wanted || S.sampler == 2) && n > 16384)) &&
-				    gcr_points_upload(ctx, grid_pts, n, cols, 1) != GCR_OK)
+				    !be->upload(grid_pts, n, cols))
 				{
-					fail("gcr_points_upload");
+					fail("upload");
 					return -1;
 				}
 				if (!build_grid())
@@ -1148,9 +904,9 @@ namespace
 			}
 			if (!nested)
 			{
-				if (gcr_points_upload(ctx, pts, n, cols, 1) != GCR_OK)
+				if (!be->upload(pts, n, cols))
 				{
-					fail("gcr_points_upload");
+					fail("upload");
 					return -1;
 				}
 				if (!(grid_pts && grid_pts != pts) && !build_grid())
@@ -1180,9 +936,9 @@ namespace
 						error = "sampler 3 (importance sampler) needs gcr_run_settings.point_probabilities";
 						return -1;
 					}
-					if (gcr_set_point_probabilities(ctx, S.point_probabilities, n) != GCR_OK)
+					if (!be->set_point_probabilities(S.point_probabilities, n))
 					{
-						fail("gcr_set_point_probabilities");
+						fail("set_point_probabilities");
 						return -1;
 					}
 				}
@@ -1355,7 +1111,7 @@ namespace
 				std::vector<uint8_t> ok;
 				const uint32_t cnt = (uint32_t)std::min<size_t>(best.inliers, buf[offset].idx.size());
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, cnt);
-				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
+				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok))
 					return -1;
 				for (int q = 0; q < rm; ++q) // :597-613 every returned model, in order; the best SCORE is not updated there
 				{
@@ -1386,7 +1142,7 @@ namespace
 				for (size_t k = 0; k < inl.size(); ++k)
 					weights[k] = std::max(0.0, 1.0 - r2[inl[k]] / T);
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inl.size());
-				if (!refit(inl.data(), offsets, sizes, weights.data(), GCR_WEIGHT_POSITIONAL, models, ok, false, GCR_F, GCR_BA_PIXEL))
+				if (!refit(inl.data(), offsets, sizes, weights.data(), weights.size(), GCR_WEIGHT_POSITIONAL, models, ok, GCR_F, GCR_BA_PIXEL))
 					return -1;
 				if (ok[0])
 				{
@@ -1416,7 +1172,7 @@ namespace
 				std::vector<double> models;
 				std::vector<uint8_t> ok;
 				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)buf[offset].idx.size());
-				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, GCR_WEIGHT_NONE, models, ok))
+				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok))
 					return -1;
 				if (ok[0])
 					memcpy(best_model, models.data(), ml * sizeof(double));
@@ -1434,22 +1190,11 @@ namespace
 				for (size_t k = 0; k < inl.size(); ++k)
 					weights[k] = std::max(0.0, 1.0 - r2[inl[k]] / T);
 				const int R = gcr_max_e_ba_models();
-				if (!d_sets.ensure(ctx, inl.size() * sizeof(uint32_t)) || !d_weights.ensure(ctx, std::max(inl.size(), (size_t)n) * sizeof(double)) ||
-				    !d_lmodels.ensure(ctx, (size_t)R * 9 * sizeof(double)) || !d_lok.ensure(ctx, (size_t)R))
+				std::vector<double> models;
+				std::vector<uint8_t> ok;
+				if (!be->refit_e_ba(inl.data(), inl.size(), weights.data(), models, ok))
 				{
-					fail("gcr_malloc");
-					return -1;
-				}
-				std::vector<double> models((size_t)R * 9);
-				std::vector<uint8_t> ok(R);
-				if (gcr_memcpy_h2d(ctx, d_sets.p, inl.data(), inl.size() * sizeof(uint32_t)) != GCR_OK ||
-				    gcr_memcpy_h2d(ctx, d_weights.p, weights.data(), inl.size() * sizeof(double)) != GCR_OK ||
-				    gcr_refit_e_ba(ctx, 0, d_sets.as<uint32_t>(), (uint32_t)inl.size(), d_weights.as<double>(), d_lmodels.as<double>(),
-				                   d_lok.as<uint8_t>()) != GCR_OK ||
-				    gcr_memcpy_d2h_async(ctx, models.data(), d_lmodels.p, models.size() * sizeof(double)) != GCR_OK ||
-				    gcr_memcpy_d2h_async(ctx, ok.data(), d_lok.p, ok.size()) != GCR_OK || gcr_sync(ctx) != GCR_OK)
-				{
-					fail("gcr_refit_e_ba");
+					fail("refit_e_ba");
 					return -1;
 				}
 				const int run_scoring = scoring;
@@ -1559,8 +1304,9 @@ extern "C" int gcr_find_model(gcr_ctx *ctx, int problem, const double *h_points,
 		return -2;
 	if (problem != GCR_H && problem != GCR_F && problem != GCR_E && problem != GCR_PNP)
 		return -3;
+	DirectBackend direct(ctx);
 	Driver d;
-	d.ctx = ctx;
+	d.be = &direct;
 	d.problem = problem;
 	d.n = n;
 	d.pts = h_points;
@@ -1607,8 +1353,9 @@ extern "C" int gcr_find_essential(gcr_ctx *ctx, const double *h_points, int n, c
 		normalized[4 * (size_t)r + 3] = K2i[3] * x1 + K2i[4] * y1 + K2i[5] * 1.0;
 	}
 	const double threshold_normalizer = 0.25 * (K1[0] + K1[4] + K2[0] + K2[4]);
+	DirectBackend direct(ctx);
 	Driver d;
-	d.ctx = ctx;
+	d.be = &direct;
 	d.problem = GCR_E;
 	d.n = n;
 	d.pts = normalized.data();
