@@ -34,7 +34,16 @@ extern "C" gcr_status gcr_ctx_create(int device, gcr_ctx **out)
 	if (!ctx)
 		return GCR_ERR_NOMEM;
 	ctx->device = device;
-	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+	// the context's stream runs at the HIGHEST priority, its side stream (gcr_round's look-ahead solver) at the lowest: the
+	// block scheduler hands out a later grid's CTAs only after every CTA of the earlier grids of the same priority has been
+	// placed, so a many-CTA solver grid in flight would otherwise hold back the small kernels of the scoring pipeline
+	int prio_least = 0, prio_greatest = 0;
+	if (cudaSetDevice(device) == cudaSuccess)
+		cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+	if (const char *pe = getenv("GCR_STREAM_PRIORITY")) // experiments (tools/overlap_probe.py): 0 = least, 1 = greatest
+		if (atoi(pe) == 0) prio_greatest = prio_least;
+	if (cudaSetDevice(device) != cudaSuccess ||
+	    cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess)
 	{
 		delete ctx;
 		return GCR_ERR_CUDA;
@@ -276,6 +285,60 @@ extern "C" gcr_status gcr_memcpy_d2h(gcr_ctx *ctx, void *h_dst, const void *d_sr
 		return st;
 	return flush_d2h(ctx);
 }
+// ---- large transfers of the batch engine: caller-owned pinned host memory, no bounce buffer ----
+extern "C" gcr_status gcr_host_alloc_pinned(gcr_ctx *ctx, size_t bytes, void **h_out)
+{
+	if (!ctx || !h_out)
+		return GCR_ERR_ARG;
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	GCR_CHECK_CUDA(ctx, cudaMallocHost(h_out, bytes ? bytes : 1));
+	return GCR_OK;
+}
+extern "C" gcr_status gcr_host_free_pinned(gcr_ctx *ctx, void *h_ptr)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (h_ptr)
+		cudaFreeHost(h_ptr);
+	return GCR_OK;
+}
+// queued on the context's stream; h_pinned must come from gcr_host_alloc_pinned.  The data is valid after gcr_sync.
+extern "C" gcr_status gcr_memcpy_pinned_async(gcr_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (bytes == 0)
+		return GCR_OK;
+	GCR_CHECK_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+	return GCR_OK;
+}
+// d_dst[i] = row d_rows[i] of d_src (row_bytes each, a multiple of 4): the batch engine's "fetch these model slots"
+__global__ void k_gather_rows(const uint32_t *__restrict__ src, uint32_t row_words, const uint64_t *__restrict__ rows, uint32_t count,
+                              uint32_t *__restrict__ dst)
+{
+	const uint64_t total = (uint64_t)count * row_words;
+	for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const uint64_t r = e / row_words, w = e % row_words;
+		dst[e] = src[rows[r] * row_words + w];
+	}
+}
+extern "C" gcr_status gcr_gather_rows(gcr_ctx *ctx, const void *d_src, uint32_t row_bytes, const uint64_t *d_rows, uint32_t count,
+                                      void *d_dst)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_src || !d_rows || !d_dst || count == 0 || row_bytes == 0 || (row_bytes & 3))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_gather_rows: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const uint64_t total = (uint64_t)count * (row_bytes / 4);
+	unsigned blocks = (unsigned)((total + 255) / 256);
+	if (blocks > 4u * ctx->sm_count) blocks = 4u * ctx->sm_count;
+	k_gather_rows<<<blocks, 256, 0, ctx->stream>>>((const uint32_t *)d_src, row_bytes / 4, d_rows, count, (uint32_t *)d_dst);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
 extern "C" gcr_status gcr_memset(gcr_ctx *ctx, void *d_dst, int value, size_t bytes)
 {
 	if (!ctx)

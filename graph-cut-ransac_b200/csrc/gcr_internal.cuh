@@ -98,6 +98,9 @@ struct gcr_ctx
 	size_t d2h_off = 0;
 	static const size_t STAGE_BYTES = 4 << 20;
 
+	// gcr_set_active_pairs: the pairs the next sampling / solving calls work on (null = all)
+	const uint8_t *d_active_pairs = nullptr;
+
 	// hypothesis-sharded mode (gcr_comm.cu): NCCL communicator of the ranks that share one problem
 	void *nccl_comm = nullptr;
 	int comm_rank = 0, comm_world = 1;
@@ -109,6 +112,7 @@ struct gcr_ctx
 	std::vector<std::pair<const void *, int>> k3_occupancy; // scoring kernel -> resident CTAs per SM (queried once)
 	int tune_k3_ctas = 0;      // GCR_TUNE_K3_CTAS_PER_SM
 	int tune_round_prefetch = 1; // GCR_TUNE_ROUND_PREFETCH
+	int tune_carveout = -1;      // GCR_TUNE_SMEM_CARVEOUT
 };
 
 #define GCR_CHECK_CUDA(ctx, expr)                                                                              \
@@ -254,6 +258,7 @@ struct GcrSampleSource
 	const unsigned long long *growth;   // PROSAC growth function
 	const double *cdf;                  // importance sampler: cumulative probabilities (n entries)
 	uint32_t n;                         // pool size = number of points
+	const uint8_t *active;              // optional [n_pairs]: pairs with 0 are skipped (their valid flags are zeroed by the launcher)
 };
 
 // closed form of the subset-size recurrence of prosac_sampler.h:65-88 (see oracle gcro_prosac_subset_size)

@@ -25,6 +25,7 @@ struct ExactArgs
 	double thr;
 	double T_override; // > 0: squared truncated threshold handed over as is (ScoringFunction::initialize), else from thr
 	size_t pair_stride; // 0: every model against the selected pair; n * cols: model m against pair m (one model per pair)
+	const int32_t *pair_ids; // with pair_stride: model m against pair pair_ids[m] (gcr_score_exact_multi), or null
 };
 
 template <int PROBLEM, int SCORING>
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_score_exact(const ExactArgs a)
 		{
 			double pt[COLS];
 			for (int c = 0; c < COLS; ++c)
-				pt[c] = a.pts[(size_t)model * a.pair_stride + (size_t)i * COLS + c];
+				pt[c] = a.pts[(size_t)(a.pair_ids ? a.pair_ids[model] : model) * a.pair_stride + (size_t)i * COLS + c];
 			const double r2 = gcr_sqres64<PROBLEM>(pt, M);
 			if (a.residuals)
 				a.residuals[(size_t)model * a.n + i] = r2;
@@ -164,7 +165,21 @@ gcr_status gcr_ensure_magsac_lut64(gcr_ctx *ctx)
 
 static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                    double threshold, double T_override, double *d_scores, uint32_t *d_counts,
-                                   uint32_t *d_inlier_idx, double *d_residuals);
+                                   uint32_t *d_inlier_idx, double *d_residuals, const int32_t *d_pair_ids = nullptr);
+
+// k models that belong to DIFFERENT pairs of the context (model m against pair d_pair_ids[m]), one launch: the batch
+// engine's getScore
+extern "C" gcr_status gcr_score_exact_multi(gcr_ctx *ctx, int problem, int scoring, const int32_t *d_pair_ids, const double *d_models,
+                                            int k, double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
+                                            double *d_residuals)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_pair_ids)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact_multi: d_pair_ids is required");
+	return score_exact_impl(ctx, problem, scoring, -2, d_models, k, threshold, 0.0, d_scores, d_counts, d_inlier_idx, d_residuals,
+	                        d_pair_ids);
+}
 
 extern "C" gcr_status gcr_score_exact(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                       double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx,
@@ -184,7 +199,7 @@ extern "C" gcr_status gcr_score_exact_pairs(gcr_ctx *ctx, int problem, int scori
 
 static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int pair, const double *d_models, int k,
                                    double threshold, double T_override, double *d_scores, uint32_t *d_counts,
-                                   uint32_t *d_inlier_idx, double *d_residuals)
+                                   uint32_t *d_inlier_idx, double *d_residuals, const int32_t *d_pair_ids)
 {
 	if (!ctx)
 		return GCR_ERR_ARG;
@@ -193,7 +208,8 @@ static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int p
 	if (problem < GCR_H || problem > GCR_PNP || gcr_cols_of(problem) != ctx->cols)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: problem does not match the uploaded points");
 	// pair == -1 (internal, gcr_score_exact_pairs): k == n_pairs models, model m scored against pair m
-	if (pair < -1 || pair >= ctx->n_pairs || (pair == -1 && k != ctx->n_pairs) || k <= 0 || !d_models || !d_scores || !d_counts)
+	// pair == -2 (internal, gcr_score_exact_multi): model m scored against pair d_pair_ids[m]
+	if (pair < -2 || pair >= ctx->n_pairs || (pair == -1 && k != ctx->n_pairs) || k <= 0 || !d_models || !d_scores || !d_counts)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_score_exact: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (scoring == GCR_MAGSAC)
@@ -215,7 +231,8 @@ static gcr_status score_exact_impl(gcr_ctx *ctx, int problem, int scoring, int p
 	a.thr = threshold;
 	a.T_override = T_override;
 	a.pair_stride = 0;
-	if (pair < 0) // gcr_score_exact_pairs: model m belongs to pair m
+	a.pair_ids = d_pair_ids;
+	if (pair < 0) // gcr_score_exact_pairs: model m belongs to pair m (gcr_score_exact_multi: to pair d_pair_ids[m])
 	{
 		a.pts = ctx->d_pts64;
 		a.pair_stride = (size_t)ctx->n * ctx->cols;

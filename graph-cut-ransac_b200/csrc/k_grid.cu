@@ -586,3 +586,67 @@ extern "C" gcr_status gcr_labeling_terms(gcr_ctx *ctx, int problem, int pair, co
 	}
 	return GCR_OK;
 }
+
+// The batch engine's labeling terms: k models that belong to DIFFERENT pairs, one launch.  d_out [k][3 n]: per model the
+// [n][2] unary capacities followed by the [n] clamped distances (what gcr_labeling_terms writes to d_unary and d_dist).
+template <int PROBLEM>
+__global__ void __launch_bounds__(GT) k_labeling_unary_multi(const double *__restrict__ pts_all, size_t pair_stride, int n,
+                                                             const int32_t *__restrict__ pair_ids, const double *__restrict__ models,
+                                                             double T, double one_minus_lambda, double *__restrict__ out)
+{
+	constexpr int ML = PROBLEM == GCR_PNP ? 12 : 9;
+	const int m = blockIdx.y;
+	double *o = out + (size_t)m * 3 * n;
+	// (same arithmetic as k_labeling_unary: the single-model kernel with this model's pair, outputs and grid column)
+	constexpr int COLS = PROBLEM == GCR_PNP ? 5 : 4;
+	const double *pts = pts_all + (size_t)pair_ids[m] * pair_stride;
+	double M[ML];
+	for (int j = 0; j < ML; ++j) M[j] = models[(size_t)m * ML + j];
+	double *unary = o, *dist = o + 2 * (size_t)n;
+	for (int i = blockIdx.x * GT + threadIdx.x; i < n; i += gridDim.x * GT)
+	{
+		double pt[COLS];
+		for (int j = 0; j < COLS; ++j) pt[j] = pts[(size_t)i * COLS + j];
+		const double r2 = gcr_sqres64<PROBLEM>(pt, M);
+		const double d = r2 / T;
+		const double dc = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : (d == d ? d : 1.0));
+		dist[i] = dc;
+		const double tmp_energy = 1 - dc;
+		if (r2 <= T)
+		{
+			unary[2 * (size_t)i] = one_minus_lambda * tmp_energy;
+			unary[2 * (size_t)i + 1] = 0.0;
+		}
+		else
+		{
+			unary[2 * (size_t)i] = 0.0;
+			unary[2 * (size_t)i + 1] = one_minus_lambda * (1 - tmp_energy);
+		}
+	}
+}
+
+extern "C" gcr_status gcr_labeling_terms_multi(gcr_ctx *ctx, int problem, const int32_t *d_pair_ids, const double *d_models, int k,
+                                               double threshold, double lambda, double *d_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_labeling_terms_multi: no points uploaded");
+	if (!d_pair_ids || !d_models || !d_out || k <= 0 || !(threshold > 0.0) || gcr_cols_of(problem) != ctx->cols)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_labeling_terms_multi: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int n = ctx->n;
+	const double T = threshold * threshold * 9 / 4;
+	int nb = (n + GT - 1) / GT;
+	if (nb > 8) nb = 8;
+	const dim3 grid(nb, k);
+	const size_t stride = (size_t)n * ctx->cols;
+	if (problem == GCR_H)
+		k_labeling_unary_multi<GCR_H><<<grid, GT, 0, ctx->stream>>>(ctx->d_pts64, stride, n, d_pair_ids, d_models, T, 1.0 - lambda, d_out);
+	else if (problem == GCR_PNP)
+		k_labeling_unary_multi<GCR_PNP><<<grid, GT, 0, ctx->stream>>>(ctx->d_pts64, stride, n, d_pair_ids, d_models, T, 1.0 - lambda, d_out);
+	else
+		k_labeling_unary_multi<GCR_F><<<grid, GT, 0, ctx->stream>>>(ctx->d_pts64, stride, n, d_pair_ids, d_models, T, 1.0 - lambda, d_out);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}

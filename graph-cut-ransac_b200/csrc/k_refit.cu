@@ -53,6 +53,11 @@ struct RefitArgs
 	// gcr_refit_pairs: set s belongs to pair s -- its indices start at sets + s * set_stride (offsets == null) and point into
 	// pts + s * pair_stride
 	size_t pair_stride, set_stride;
+	// gcr_refit_multi (the batch engine): set s belongs to pair pair_of_set[s], reads its weights from weights +
+	// weight_offsets[s] and writes its models to output slot out_slots[s] (all three optional)
+	const int32_t *pair_of_set;
+	const uint32_t *weight_offsets;
+	const uint32_t *out_slots;
 };
 
 // fixed-tree block sum of NV values per thread; result valid in out[] for every thread after the call
@@ -499,7 +504,10 @@ template <int PROBLEM, int BA = 0>
 __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit(const RefitArgs a_in)
 {
 	RefitArgs a = a_in;
-	a.pts += (size_t)blockIdx.x * a_in.pair_stride;
+	a.pts += (size_t)(a_in.pair_of_set ? a_in.pair_of_set[blockIdx.x] : (int)blockIdx.x) * a_in.pair_stride;
+	if (a.weights && a_in.weight_offsets)
+		a.weights += a_in.weight_offsets[blockIdx.x];
+	const size_t oslot = a_in.out_slots ? a_in.out_slots[blockIdx.x] : blockIdx.x;
 	constexpr int NV = PROBLEM == GCR_H ? 44 : 45;
 	__shared__ double red[(BA != 0 ? RF_MAX_WARPS : RF_WARPS) * 45];
 	__shared__ double tot[45];
@@ -511,8 +519,8 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 	{
 		if (tid == 0)
 		{
-			for (int j = 0; j < 9; ++j) a.models[(size_t)set * 9 + j] = 0.0;
-			a.ok[set] = 0;
+			for (int j = 0; j < 9; ++j) a.models[oslot * 9 + j] = 0.0;
+			a.ok[oslot] = 0;
 		}
 		return;
 	}
@@ -574,8 +582,8 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 			double T2i[9] = {1.0 / rd, 0, mdx, 0, 1.0 / rd, mdy, 0, 0, 1}, tmp[9], H[9];
 			mul3(T2i, Hn, tmp);
 			mul3(tmp, T1, H);
-			for (int j = 0; j < 9; ++j) a.models[(size_t)set * 9 + j] = ok ? H[j] : 0.0;
-			a.ok[set] = ok ? 1 : 0;
+			for (int j = 0; j < 9; ++j) a.models[oslot * 9 + j] = ok ? H[j] : 0.0;
+			a.ok[oslot] = ok ? 1 : 0;
 		}
 		return;
 	}
@@ -666,8 +674,8 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 		}
 		for (int i = 0; i < 9; ++i)
 			if (isnan(out[i])) ok = false;
-		for (int j = 0; j < 9; ++j) a.models[(size_t)set * 9 + j] = ok ? out[j] : 0.0;
-		a.ok[set] = ok ? 1 : 0;
+		for (int j = 0; j < 9; ++j) a.models[oslot * 9 + j] = ok ? out[j] : 0.0;
+		a.ok[oslot] = ok ? 1 : 0;
 		return;
 	}
 	if (tid != 0)
@@ -757,8 +765,8 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 		for (int i = 0; i < 9; ++i)
 			if (isnan(out[i])) ok = false;
 	}
-	for (int j = 0; j < 9; ++j) a.models[(size_t)set * 9 + j] = ok ? out[j] : 0.0;
-	a.ok[set] = ok ? 1 : 0;
+	for (int j = 0; j < 9; ++j) a.models[oslot * 9 + j] = ok ? out[j] : 0.0;
+	a.ok[oslot] = ok ? 1 : 0;
 }
 
 // Eigen ColPivHouseholderQR(M).matrixQ().rightCols<4>() of a 9 x 9 row-major M (destroyed): N[b][j] = Q(j, 5 + b).
@@ -850,15 +858,20 @@ __device__ void colpiv_householder_q_last4_9(double *M, double (&N)[4][9])
 
 #define RF_E_MODELS 10
 
-__global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a)
+__global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a_in)
 {
+	RefitArgs a = a_in;
+	a.pts += (size_t)(a_in.pair_of_set ? a_in.pair_of_set[blockIdx.x] : (int)blockIdx.x) * a_in.pair_stride;
+	if (a.weights && a_in.weight_offsets)
+		a.weights += a_in.weight_offsets[blockIdx.x];
+	const size_t oslot = a_in.out_slots ? a_in.out_slots[blockIdx.x] : blockIdx.x;
 	__shared__ double red[RF_WARPS * 45];
 	__shared__ double tot[45];
 	const int set = blockIdx.x, tid = threadIdx.x;
 	const uint32_t *idx = a.sets + a.offsets[set];
 	const int n = (int)a.sizes[set];
-	double *models = a.models + (size_t)set * RF_E_MODELS * 9;
-	uint8_t *ok = a.ok + (size_t)set * RF_E_MODELS;
+	double *models = a.models + oslot * RF_E_MODELS * 9;
+	uint8_t *ok = a.ok + oslot * RF_E_MODELS;
 	if (n < 5) // nonMinimalSampleSize() (essential_estimator.h:315-316)
 	{
 		for (int j = tid; j < RF_E_MODELS * 9; j += RF_THREADS) models[j] = 0.0;
@@ -1006,6 +1019,9 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 	a.ok = d_ok;
 	a.ba_frame = ba_frame;
 	a.pair_stride = a.set_stride = 0;
+	a.pair_of_set = nullptr;
+	a.weight_offsets = nullptr;
+	a.out_slots = nullptr;
 	if (problem == GCR_H)
 		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	else if (problem == GCR_E)
@@ -1043,11 +1059,68 @@ extern "C" gcr_status gcr_refit_pairs(gcr_ctx *ctx, int problem, const uint32_t 
 	a.ok = d_ok;
 	a.ba_frame = 0;
 	a.pair_stride = (size_t)ctx->n * 4;
+	a.pair_of_set = nullptr;
+	a.weight_offsets = nullptr;
+	a.out_slots = nullptr;
 	a.set_stride = (size_t)ctx->n;
 	if (problem == GCR_H)
 		k_refit<GCR_H><<<ctx->n_pairs, RF_THREADS, 0, ctx->stream>>>(a);
 	else
 		k_refit<GCR_F><<<ctx->n_pairs, RF_THREADS, 0, ctx->stream>>>(a);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+// The batch engine's refit: `count` index sets that belong to DIFFERENT pairs of the context, one launch.  Set s: pair
+// d_pair_of_set[s], indices d_index_sets + d_set_offsets[s] (d_set_sizes[s] of them), weights (when d_weights is given) at
+// d_weights + d_weight_offsets[s] read in `weight_mode`, models written to slot d_out_slots[s] of d_models / d_ok (slot x
+// R models each; d_out_slots == NULL: slot s).  ba_frame as gcr_refit_f_ba (F only; 0 = the linear fit); wide != 0: the
+// sets are whole inlier sets (one per request), fitted with the CTA shape of a single-set gcr_refit_f_ba call.
+extern "C" gcr_status gcr_refit_multi(gcr_ctx *ctx, int problem, int ba_frame, const int32_t *d_pair_of_set, const uint32_t *d_index_sets,
+                                      const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count, const double *d_weights,
+                                      const uint32_t *d_weight_offsets, int weight_mode, const uint32_t *d_out_slots, int wide,
+                                      double *d_models, uint8_t *d_ok)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64 || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_refit_multi: no points uploaded");
+	if (ctx->cols != 4 || (problem != GCR_H && problem != GCR_F && problem != GCR_E))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_multi: H, F or E on 4-column points");
+	if (count <= 0 || !d_pair_of_set || !d_index_sets || !d_set_offsets || !d_set_sizes || !d_models || !d_ok)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_multi: bad arguments");
+	if (ba_frame && (problem != GCR_F || (ba_frame != GCR_BA_HARTLEY && ba_frame != GCR_BA_PIXEL)))
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_multi: ba_frame is for F (GCR_BA_HARTLEY / GCR_BA_PIXEL)");
+	if (d_weights && weight_mode != GCR_WEIGHT_POSITIONAL && weight_mode != GCR_WEIGHT_BY_POINT)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_refit_multi: weights given but weight_mode is %d", weight_mode);
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	RefitArgs a;
+	a.pts = ctx->d_pts64;
+	a.sets = d_index_sets;
+	a.offsets = d_set_offsets;
+	a.sizes = d_set_sizes;
+	a.weights = d_weights;
+	a.weight_mode = weight_mode;
+	a.models = d_models;
+	a.ok = d_ok;
+	a.ba_frame = ba_frame;
+	a.pair_stride = (size_t)ctx->n * 4;
+	a.set_stride = 0;
+	a.pair_of_set = d_pair_of_set;
+	a.weight_offsets = d_weight_offsets;
+	a.out_slots = d_out_slots;
+	if (problem == GCR_H)
+		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	else if (problem == GCR_E)
+		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
+	// `wide`: the CTA shape gcr_refit_f_ba gives a call with ONE set (all inliers of a run) -- the block sums associate by
+	// CTA shape, so a batched single-set fit uses the shape the unbatched call would
+	else if (ba_frame == GCR_BA_HARTLEY)
+		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, wide ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+	else if (ba_frame == GCR_BA_PIXEL)
+		k_refit<GCR_F, GCR_BA_PIXEL><<<count, wide ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+	else
+		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }

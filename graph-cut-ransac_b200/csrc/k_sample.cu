@@ -96,6 +96,59 @@ __global__ void __launch_bounds__(128) k_sample_pool(const uint32_t *__restrict_
 		o[j] = pool[o[j]];
 }
 
+// the batch engine's LO sampler: request r draws `trials` samples of desc[r].sample_size positions from ITS pool
+// (pools + desc[r].pool_offset, desc[r].pool_size entries) on ITS stream (seed, first_index, stream id), exactly the draws
+// k_sample_pool makes for that request alone; sample t of request r goes to out + desc[r].out_offset + t * sample_size
+__global__ void __launch_bounds__(128) k_sample_pools(const uint32_t *__restrict__ pools, const gcr_pool_request *__restrict__ desc,
+                                                       int trials, uint32_t *__restrict__ out)
+{
+	const gcr_pool_request d = desc[blockIdx.y];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= trials)
+		return;
+	const uint32_t *pool = pools + d.pool_offset;
+	const int m = (int)d.sample_size;
+	GcrDrawStream s(d.seed, d.first_index + (uint64_t)i, d.stream);
+	uint32_t *o = out + d.out_offset + (size_t)i * m;
+	for (int j = 0; j < m; ++j)
+	{
+		bool dup;
+		uint32_t v;
+		do
+		{
+			v = s.bounded(d.pool_size);
+			dup = false;
+			for (int q = 0; q < j; ++q)
+				if (o[q] == v)
+					dup = true;
+		} while (dup);
+		o[j] = v;
+	}
+	for (int j = 0; j < m; ++j)
+		o[j] = pool[o[j]];
+}
+
+extern "C" gcr_status gcr_sample_from_pools(gcr_ctx *ctx, const uint32_t *d_pools, const gcr_pool_request *d_requests, int n_requests,
+                                            int trials, uint32_t *d_out)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!d_pools || !d_requests || !d_out || n_requests <= 0 || trials <= 0)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample_from_pools: bad arguments");
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	k_sample_pools<<<dim3((trials + 127) / 128, n_requests), 128, 0, ctx->stream>>>(d_pools, d_requests, trials, d_out);
+	GCR_LAUNCHED(ctx);
+	return GCR_OK;
+}
+
+extern "C" gcr_status gcr_set_active_pairs(gcr_ctx *ctx, const uint8_t *d_active)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	ctx->d_active_pairs = d_active;
+	return GCR_OK;
+}
+
 // prosac_sampler.h:129-160 growth function, FP64 recurrence on the host exactly as the reference runs it
 static void prosac_growth_host(uint32_t n, int m, uint64_t convergence_iters, std::vector<unsigned long long> &growth)
 {

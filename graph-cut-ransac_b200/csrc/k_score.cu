@@ -932,6 +932,8 @@ static gcr_status launch_variant(gcr_ctx *ctx, ScoreArgs &a, bool exact)
 	if (per_sm == 0)
 	{
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (ctx->tune_carveout >= 0)
+			GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->tune_carveout));
 		GCR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
 		if (per_sm < 1)
 			GCR_FAIL(ctx, GCR_ERR_CUDA, "gcr_score: scoring kernel does not fit on an SM");

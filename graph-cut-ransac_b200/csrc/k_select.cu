@@ -96,6 +96,7 @@ extern "C" gcr_status gcr_set_tuning(gcr_ctx *ctx, int knob, int value)
 	{
 	case GCR_TUNE_K3_CTAS_PER_SM: ctx->tune_k3_ctas = value < 0 ? 0 : value; return GCR_OK;
 	case GCR_TUNE_ROUND_PREFETCH: ctx->tune_round_prefetch = value != 0; return GCR_OK;
+	case GCR_TUNE_SMEM_CARVEOUT: ctx->tune_carveout = value; return GCR_OK;
 	default: GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_set_tuning: unknown knob %d", knob);
 	}
 }

@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(H4_THREADS) k_solve_h4(const double *__restric
 	__shared__ int s_n;
 	const int tid = threadIdx.x;
 	const int pair = blockIdx.y;
+	if (src.active && !src.active[pair])
+		return; // a pair the batch engine has no request for (valid flags zeroed by the launcher)
 	const double *P = pts + (size_t)pair * n * 4;
 	if (tid == 0)
 		s_n = 0;
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(F7_THREADS, F7_MIN_BLOCKS) k_solve_f7(const do
 	extern __shared__ double f7_smem[];
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int pair = blockIdx.y;
+	if (src.active && !src.active[pair])
+		return; // a pair the batch engine has no request for (valid flags zeroed by the launcher)
 	uint32_t n_ok = 0;
 	if (i < count)
 	{
@@ -300,6 +304,8 @@ __global__ void __launch_bounds__(E5_THREADS, E5_MIN_BLOCKS) k_solve_e5(const do
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int g = lane / 10, li = lane - 10 * g;
 	const int pair = blockIdx.y;
+	if (src.active && !src.active[pair])
+		return; // a pair the batch engine has no request for (valid flags zeroed by the launcher)
 	const int slot = warp * 3 + g;
 	const int i = blockIdx.x * E5_SAMPLES_PER_CTA + slot;
 	if (threadIdx.x == 0)
@@ -345,6 +351,8 @@ __global__ void __launch_bounds__(128) k_solve_p3p(const double *__restrict__ pt
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int pair = blockIdx.y;
+	if (src.active && !src.active[pair])
+		return; // a pair the batch engine has no request for (valid flags zeroed by the launcher)
 	uint32_t n_ok = 0;
 	if (i < count)
 	{
@@ -463,6 +471,8 @@ static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource 
 	if (!d_models || !d_valid || count <= 0)
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_solve_minimal: bad arguments");
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (src.active) // skipped pairs keep no stale flags
+		GCR_CHECK_CUDA(ctx, cudaMemsetAsync(d_valid, 0, (size_t)ctx->n_pairs * count * gcr_max_models(problem), ctx->stream));
 	const dim3 grid((count + 127) / 128, ctx->n_pairs);
 	switch (problem)
 	{
@@ -471,11 +481,15 @@ static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource 
 		break;
 	case GCR_F:
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SMEM));
+		if (ctx->tune_carveout >= 0)
+			GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_f7, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->tune_carveout));
 		k_solve_f7<<<dim3((count + F7_THREADS - 1) / F7_THREADS, ctx->n_pairs), F7_THREADS, F7_SMEM, ctx->stream>>>(
 		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_E:
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_e5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E5_SMEM));
+		if (ctx->tune_carveout >= 0)
+			GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_e5, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->tune_carveout));
 		k_solve_e5<<<dim3((count + E5_SAMPLES_PER_CTA - 1) / E5_SAMPLES_PER_CTA, ctx->n_pairs), E5_THREADS, E5_SMEM, ctx->stream>>>(
 		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
@@ -503,6 +517,7 @@ extern "C" gcr_status gcr_solve_minimal(gcr_ctx *ctx, int problem, const uint32_
 	src.growth = nullptr;
 	src.cdf = nullptr;
 	src.n = (uint32_t)ctx->n;
+	src.active = ctx->d_active_pairs;
 	return solve_launch(ctx, problem, src, count, d_models, d_valid);
 }
 
@@ -524,6 +539,7 @@ gcr_status gcr_solve_minimal_generated(gcr_ctx *ctx, int problem, int sampler, u
 	src.growth = nullptr;
 	src.cdf = nullptr;
 	src.n = (uint32_t)ctx->n;
+	src.active = ctx->d_active_pairs;
 	if (sampler == GCR_PROSAC)
 	{
 		if (first_index < 1)

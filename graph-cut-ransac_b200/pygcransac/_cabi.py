@@ -16,7 +16,7 @@ MSAC, MAGSAC = 0, 1
 UNIFORM, PROSAC, IMPORTANCE = 0, 1, 2
 WEIGHT_NONE, WEIGHT_POSITIONAL, WEIGHT_BY_POINT = 0, 1, 2
 SCORE_EXACT_COUNTS = 1
-TUNE_K3_CTAS_PER_SM, TUNE_ROUND_PREFETCH = 0, 1
+TUNE_K3_CTAS_PER_SM, TUNE_ROUND_PREFETCH, TUNE_SMEM_CARVEOUT = 0, 1, 2
 
 # every symbol include/gcr/gcr.h declares (tests check the library exports all of them)
 BA_HARTLEY, BA_PIXEL = 1, 2
@@ -36,6 +36,8 @@ EXPORTS = [
     "gcr_winners_reduce", "gcr_ubench_fp32", "gcr_points_upload_f32", "gcr_set_tuning",
     "gcr_grid_edges", "gcr_csr_edges", "gcr_labeling_terms", "gcr_score_dropped_async",
     "gcr_refit_e_ba", "gcr_max_e_ba_models",
+    "gcr_set_active_pairs", "gcr_score_exact_multi", "gcr_labeling_terms_multi", "gcr_sample_from_pools", "gcr_refit_multi",
+    "gcr_host_alloc_pinned", "gcr_host_free_pinned", "gcr_memcpy_pinned_async", "gcr_gather_rows",
 ]
 
 

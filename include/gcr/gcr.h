@@ -59,7 +59,9 @@ gcr_status gcr_set_score_variant(gcr_ctx *ctx, int variant);
 /* generic tuning knobs (experiments / benches; every knob has a sane default) */
 enum {
 	GCR_TUNE_K3_CTAS_PER_SM = 0, /* cap on the resident CTAs per SM of the scoring kernel (0 = as many as fit) */
-	GCR_TUNE_ROUND_PREFETCH = 1  /* gcr_round: solve the NEXT round's samples on a side stream while this round is scored (default 1) */
+	GCR_TUNE_ROUND_PREFETCH = 1, /* gcr_round: solve the NEXT round's samples on a side stream while this round is scored (default 1) */
+	GCR_TUNE_SMEM_CARVEOUT = 2   /* preferred shared-memory carve-out (percent, -1 = driver's choice) of the solver / scoring kernels:
+	                                kernels with the SAME carve-out can share an SM (set before the first launch) */
 };
 gcr_status gcr_set_tuning(gcr_ctx *ctx, int knob, int value);
 /* per-CTA timeline of the following K3 launches: d_trace (device, >= 4 * 148 * 8 uint64, or NULL to stop) receives per
@@ -275,6 +277,42 @@ gcr_status gcr_csr_edges(gcr_ctx *ctx, const uint32_t *d_offsets, const uint32_t
  * reference's Boykov-Kolmogorov solver on the host. */
 gcr_status gcr_labeling_terms(gcr_ctx *ctx, int problem, int pair, const double *d_model, double threshold, double lambda,
                               const uint32_t *d_edges, uint64_t n_edges, double *d_unary, double *d_pairwise, double *d_dist);
+
+/* ---- many pairs, one launch: the operations of the batched multi-pair driver (host/gcr_batch_engine.cpp) ------------ */
+/* The lock-step driver keeps P image pairs resident on one context and executes the pending operation of every pair as
+ * one launch; these are the per-pair entry points above with a pair index PER ITEM instead of one per call.  Results are
+ * bit-identical to the single-pair calls (same kernels, same CTA shapes). */
+/* gcr_sample / gcr_solve_minimal / gcr_score work on every pair of the context: restrict the next sampling / solving
+ * calls to the pairs with d_active[pair] != 0 (their model slots' valid flags are 0 for the others, so gcr_score spends
+ * nothing on them).  NULL = all pairs.  The array is read at launch time on the context's stream. */
+gcr_status gcr_set_active_pairs(gcr_ctx *ctx, const uint8_t *d_active);
+/* gcr_score_exact for k models of different pairs: model m against pair d_pair_ids[m] */
+gcr_status gcr_score_exact_multi(gcr_ctx *ctx, int problem, int scoring, const int32_t *d_pair_ids, const double *d_models, int k,
+                                 double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx, double *d_residuals);
+/* gcr_labeling_terms for k models of different pairs; d_out [k][3 n]: per model the [n][2] capacities, then [n] distances */
+gcr_status gcr_labeling_terms_multi(gcr_ctx *ctx, int problem, const int32_t *d_pair_ids, const double *d_models, int k,
+                                    double threshold, double lambda, double *d_out);
+/* gcr_sample_from_pool for several requests at once: request r draws `trials` samples of sample_size positions from its
+ * pool (d_pools + pool_offset) on its own stream of draws and writes them to d_out + out_offset + t * sample_size */
+typedef struct gcr_pool_request
+{
+	uint32_t pool_offset, pool_size, sample_size, out_offset;
+	uint64_t first_index, seed;
+	uint32_t stream, reserved;
+} gcr_pool_request;
+gcr_status gcr_sample_from_pools(gcr_ctx *ctx, const uint32_t *d_pools, const gcr_pool_request *d_requests, int n_requests,
+                                 int trials, uint32_t *d_out);
+/* gcr_refit / gcr_refit_f_ba for `count` index sets of different pairs: set s belongs to pair d_pair_of_set[s], reads its
+ * weights (if any) from d_weights + d_weight_offsets[s] and writes its models to slot d_out_slots[s] (NULL: slot s) */
+gcr_status gcr_refit_multi(gcr_ctx *ctx, int problem, int ba_frame, const int32_t *d_pair_of_set, const uint32_t *d_index_sets,
+                           const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count, const double *d_weights,
+                           const uint32_t *d_weight_offsets, int weight_mode, const uint32_t *d_out_slots, int wide,
+                           double *d_models, uint8_t *d_ok);
+/* pinned host memory + direct asynchronous copies for the engine's large transfers (no bounce buffer), and a row gather */
+gcr_status gcr_host_alloc_pinned(gcr_ctx *ctx, size_t bytes, void **h_out);
+gcr_status gcr_host_free_pinned(gcr_ctx *ctx, void *h_ptr);
+gcr_status gcr_memcpy_pinned_async(gcr_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device);
+gcr_status gcr_gather_rows(gcr_ctx *ctx, const void *d_src, uint32_t row_bytes, const uint64_t *d_rows, uint32_t count, void *d_dst);
 
 /* ---- fused fixed-K round (the benchmarked step) ------------------------------------------------------------ */
 /* One pass of the hot path over every pair on the context: K1 sample `count` minimal samples -> K2 solve -> K3

@@ -13,9 +13,16 @@ from pygcransac import _cabi, synth  # noqa: E402
 
 K, N = 262144, 4096
 pts = synth.epipolar_pair(N, 0.5, seed=1)[0]
-a, b = _cabi.Context(0), _cabi.Context(0)
+os.environ["GCR_STREAM_PRIORITY"] = os.environ.get("PRIO_A", "1")
+a = _cabi.Context(0)
+os.environ["GCR_STREAM_PRIORITY"] = os.environ.get("PRIO_B", "0")
+b = _cabi.Context(0)
+print("priority a", os.environ.get("PRIO_A", "1"), "b", os.environ.get("PRIO_B", "0"), flush=True)
+CARVE = int(os.environ.get("CARVEOUT", "-1"))
 for c in (a, b):
     c.points_upload(pts)
+    c.set_tuning(_cabi.TUNE_SMEM_CARVEOUT, CARVE)
+print("carveout", CARVE, flush=True)
 vp = C.c_void_p
 
 
@@ -42,7 +49,7 @@ solve(a, A)
 solve(b, B)
 a.sync(); b.sync()
 IT = 30
-for cap in (0, 4, 3, 2, 1):
+for cap in (0, 3, 2, 1):
     a.set_tuning(_cabi.TUNE_K3_CTAS_PER_SM, cap)
     for mode in ("k3 only", "k2 only", "sequential", "concurrent"):
         for rep in range(2):
