@@ -622,14 +622,25 @@ __device__ __forceinline__ void convert_point(const double *__restrict__ pts_pai
 // separate launches below cost ~12 us of launch latency on a 128 KB upload.
 #define K0_FUSED_THREADS 1024
 #define K0_FUSED_MAX_POINTS 32768
+// seats != null (gcr_points_replace_pairs): CTA b first copies row b of `incoming` over the points of pair seats[b]
 template <int COLS>
 __global__ void __launch_bounds__(K0_FUSED_THREADS) k_prepare_fused(const double *__restrict__ pts, int n, int n_pad,
-                                                                  double *__restrict__ norm, float4 *__restrict__ out32)
+                                                                  double *__restrict__ norm, float4 *__restrict__ out32,
+                                                                  const int32_t *__restrict__ seats = nullptr,
+                                                                  const double *__restrict__ incoming = nullptr)
 {
 	__shared__ double s_mn[32][COLS], s_mx[32][COLS];
 	__shared__ double s_nm[8];
-	const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int pair = seats ? seats[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const double *p = pts + (size_t)pair * n * COLS;
+	if (seats)
+	{
+		double *dst = const_cast<double *>(p);
+		const double *src = incoming + (size_t)blockIdx.x * n * COLS;
+		for (int e = tid; e < n * COLS; e += K0_FUSED_THREADS)
+			dst[e] = src[e];
+		__syncthreads(); // (each thread re-reads elements other threads wrote: block-level visibility)
+	}
 	double mn[COLS], mx[COLS];
 #pragma unroll
 	for (int c = 0; c < COLS; ++c)
@@ -871,6 +882,48 @@ extern "C" gcr_status gcr_points_upload_f32(gcr_ctx *ctx, const float *h_points,
 	ctx->cols = cols;
 	ctx->n_pairs = n_pairs;
 	return prepare_points(ctx);
+}
+
+// pairs h_pairs[0..count) of the uploaded context <- rows of h_points; frames and FP32 copies re-derived by the same kernel
+// (same arithmetic, same reduction order) as the whole-context upload
+extern "C" gcr_status gcr_points_replace_pairs(gcr_ctx *ctx, const int32_t *h_pairs, int count, const double *h_points)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	if (!ctx->d_pts64_owned || ctx->d_pts64 != ctx->d_pts64_owned || ctx->n == 0)
+		GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_points_replace_pairs: needs points uploaded with gcr_points_upload");
+	if (!h_pairs || !h_points || count <= 0 || count > ctx->n_pairs)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_points_replace_pairs: bad arguments");
+	if (ctx->n > K0_FUSED_MAX_POINTS)
+		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_points_replace_pairs: at most %d points per pair", K0_FUSED_MAX_POINTS);
+	for (int r = 0; r < count; ++r)
+		if (h_pairs[r] < 0 || h_pairs[r] >= ctx->n_pairs)
+			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_points_replace_pairs: pair %d out of range", h_pairs[r]);
+	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t row = (size_t)ctx->n * ctx->cols * sizeof(double), bytes = row * count, seat_bytes = ((size_t)count * 4 + 255) & ~(size_t)255;
+	void *d_in = nullptr;
+	gcr_status st = gcr_malloc(ctx, seat_bytes + bytes, &d_in);
+	if (st)
+		return st;
+	// pageable sources: synchronous copies (the caller may reuse its buffers on return); stream-ordered after earlier work
+	cudaError_t e = cudaMemcpyAsync(d_in, h_pairs, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync((char *)d_in + seat_bytes, h_points, bytes, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess)
+	{
+		const int32_t *d_seats = (const int32_t *)d_in;
+		const double *d_rows = (const double *)((char *)d_in + seat_bytes);
+		if (ctx->cols == 4)
+			k_prepare_fused<4><<<count, K0_FUSED_THREADS, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, ctx->n_pad, ctx->d_norm, ctx->d_pts32, d_seats, d_rows);
+		else
+			k_prepare_fused<5><<<count, K0_FUSED_THREADS, 0, ctx->stream>>>(ctx->d_pts64, ctx->n, ctx->n_pad, ctx->d_norm, ctx->d_pts32, d_seats, d_rows);
+		++ctx->launches;
+		e = cudaGetLastError();
+	}
+	// the block returns to the cache: the next user is ordered after this kernel on the context's stream
+	gcr_free(ctx, d_in);
+	GCR_CHECK_CUDA(ctx, e);
+	return GCR_OK;
 }
 
 extern "C" gcr_status gcr_points_set_device(gcr_ctx *ctx, const double *d_points, int n, int cols, int n_pairs)

@@ -100,6 +100,8 @@ struct gcr_ctx
 
 	// gcr_set_active_pairs: the pairs the next sampling / solving calls work on (null = all)
 	const uint8_t *d_active_pairs = nullptr;
+	// gcr_set_pair_streams: per-pair additions to gcr_sample's (first_index, seed) (null = none)
+	const uint64_t *d_pair_first = nullptr, *d_pair_seed = nullptr;
 
 	// hypothesis-sharded mode (gcr_comm.cu): NCCL communicator of the ranks that share one problem
 	void *nccl_comm = nullptr;

@@ -14,13 +14,24 @@
 #include <vector>
 
 
+// ps: optional per-pair additions to (first_index, seed) -- gcr_set_pair_streams, the batch engine's seats
+struct PairStreams
+{
+	const uint64_t *first, *seed;
+	const uint8_t *active;
+};
+
 __global__ void __launch_bounds__(256) k_sample_uniform(uint32_t *__restrict__ out, int count, int m, uint32_t n,
-                                                         uint64_t first_index, uint64_t seed)
+                                                         uint64_t first_index, uint64_t seed, const PairStreams ps)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
 	const int pair = blockIdx.y;
+	if (ps.active && !ps.active[pair])
+		return;
+	if (ps.first) first_index += ps.first[pair];
+	if (ps.seed) seed += ps.seed[pair];
 	uint32_t v[8];
 	gcr_gen_uniform(seed, pair, first_index + (uint64_t)i, m, n, v);
 	uint32_t *o = out + ((size_t)pair * count + i) * m;
@@ -33,12 +44,16 @@ __global__ void __launch_bounds__(256) k_sample_uniform(uint32_t *__restrict__ o
 __global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ out, int count, int m, uint32_t n,
                                                         uint64_t first_k, uint64_t seed,
                                                         const unsigned long long *__restrict__ growth,
-                                                        unsigned long long convergence)
+                                                        unsigned long long convergence, const PairStreams ps)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
 	const int pair = blockIdx.y;
+	if (ps.active && !ps.active[pair])
+		return;
+	if (ps.first) first_k += ps.first[pair];
+	if (ps.seed) seed += ps.seed[pair];
 	const unsigned long long k = first_k + (unsigned long long)i;
 	uint32_t v[8];
 	gcr_gen_prosac(seed, pair, k, m, n, growth, convergence, v);
@@ -52,12 +67,16 @@ __global__ void __launch_bounds__(256) k_sample_prosac(uint32_t *__restrict__ ou
 // importance_sampler.h:126-137 (NG-RANSAC): m independent draws from the point-probability distribution
 __global__ void __launch_bounds__(256) k_sample_importance(uint32_t *__restrict__ out, int count, int m, uint32_t n,
                                                             uint64_t first_index, uint64_t seed,
-                                                            const double *__restrict__ cdf)
+                                                            const double *__restrict__ cdf, const PairStreams ps)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
 	const int pair = blockIdx.y;
+	if (ps.active && !ps.active[pair])
+		return;
+	if (ps.first) first_index += ps.first[pair];
+	if (ps.seed) seed += ps.seed[pair];
 	uint32_t v[8];
 	gcr_gen_importance(seed, pair, first_index + (uint64_t)i, m, n, cdf, v);
 	uint32_t *o = out + ((size_t)pair * count + i) * m;
@@ -149,6 +168,15 @@ extern "C" gcr_status gcr_set_active_pairs(gcr_ctx *ctx, const uint8_t *d_active
 	return GCR_OK;
 }
 
+extern "C" gcr_status gcr_set_pair_streams(gcr_ctx *ctx, const uint64_t *d_first_offsets, const uint64_t *d_seed_offsets)
+{
+	if (!ctx)
+		return GCR_ERR_ARG;
+	ctx->d_pair_first = d_first_offsets;
+	ctx->d_pair_seed = d_seed_offsets;
+	return GCR_OK;
+}
+
 // prosac_sampler.h:129-160 growth function, FP64 recurrence on the host exactly as the reference runs it
 static void prosac_growth_host(uint32_t n, int m, uint64_t convergence_iters, std::vector<unsigned long long> &growth)
 {
@@ -202,24 +230,28 @@ extern "C" gcr_status gcr_sample(gcr_ctx *ctx, int sampler, int m, uint64_t firs
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: sample size %d exceeds the %d points (uniform_sampler.h:87-88)", m, ctx->n);
 	GCR_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
 	const dim3 grid((count + 255) / 256, ctx->n_pairs);
+	PairStreams ps;
+	ps.first = ctx->d_pair_first;
+	ps.seed = ctx->d_pair_seed;
+	ps.active = ctx->d_active_pairs;
 	if (sampler == GCR_UNIFORM)
-		k_sample_uniform<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed);
+		k_sample_uniform<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed, ps);
 	else if (sampler == GCR_PROSAC)
 	{
-		if (first_index < 1)
+		if (first_index < 1 && !ps.first)
 			GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: PROSAC draws are numbered from k = 1");
 		gcr_status st = gcr_ensure_prosac_growth(ctx, m);
 		if (st)
 			return st;
 		k_sample_prosac<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed,
-		                                                ctx->d_prosac_growth, 100000ull);
+		                                                ctx->d_prosac_growth, 100000ull, ps);
 	}
 	else if (sampler == GCR_IMPORTANCE)
 	{
 		if (!ctx->d_importance_cdf || ctx->importance_n != ctx->n)
 			GCR_FAIL(ctx, GCR_ERR_STATE, "gcr_sample: GCR_IMPORTANCE needs gcr_set_point_probabilities for the %d points", ctx->n);
 		k_sample_importance<<<grid, 256, 0, ctx->stream>>>(d_out, count, m, (uint32_t)ctx->n, first_index, seed,
-		                                                    ctx->d_importance_cdf);
+		                                                    ctx->d_importance_cdf, ps);
 	}
 	else
 		GCR_FAIL(ctx, GCR_ERR_ARG, "gcr_sample: unknown sampler %d", sampler);

@@ -38,6 +38,7 @@ EXPORTS = [
     "gcr_refit_e_ba", "gcr_max_e_ba_models",
     "gcr_set_active_pairs", "gcr_score_exact_multi", "gcr_labeling_terms_multi", "gcr_sample_from_pools", "gcr_refit_multi",
     "gcr_host_alloc_pinned", "gcr_host_free_pinned", "gcr_memcpy_pinned_async", "gcr_gather_rows",
+    "gcr_set_pair_streams", "gcr_points_replace_pairs",
 ]
 
 
@@ -87,6 +88,8 @@ def load_library():
         "gcr_points_set_device": (i32, [vp, vp, i32, i32, i32]),
         "gcr_points_upload_f32": (i32, [vp, vp, i32, i32, i32]),
         "gcr_set_tuning": (i32, [vp, i32, i32]),
+        "gcr_set_pair_streams": (i32, [vp, vp, vp]),
+        "gcr_points_replace_pairs": (i32, [vp, vp, i32, vp]),
         "gcr_score_dropped_async": (i32, [vp, vp]),
         "gcr_refit_e_ba": (i32, [vp, i32, vp, u32, vp, vp, vp]),
         "gcr_max_e_ba_models": (i32, []),

@@ -286,6 +286,14 @@ gcr_status gcr_labeling_terms(gcr_ctx *ctx, int problem, int pair, const double 
  * calls to the pairs with d_active[pair] != 0 (their model slots' valid flags are 0 for the others, so gcr_score spends
  * nothing on them).  NULL = all pairs.  The array is read at launch time on the context's stream. */
 gcr_status gcr_set_active_pairs(gcr_ctx *ctx, const uint8_t *d_active);
+/* gcr_sample on a context whose pairs advance independently (the seats of the batch engine): pair p draws sample i at
+ * index first_index + i + d_first_offsets[p] of the stream of seed + d_seed_offsets[p] (+ the usual p * 0x9E3779B97F4A7C15;
+ * 64-bit wrapping sums).  Either array may be NULL (= zeros); read at launch time on the context's stream. */
+gcr_status gcr_set_pair_streams(gcr_ctx *ctx, const uint64_t *d_first_offsets, const uint64_t *d_seed_offsets);
+/* Replaces the points of `count` pairs of an uploaded multi-pair context in place: pair h_pairs[r] <- row r of h_points
+ * ([count][n][cols] FP64, host), its normalisation frame and FP32 copy re-derived exactly as gcr_points_upload derives
+ * them (n <= 32768).  Queued on the context's stream; h_points / h_pairs may be reused when the call returns. */
+gcr_status gcr_points_replace_pairs(gcr_ctx *ctx, const int32_t *h_pairs, int count, const double *h_points);
 /* gcr_score_exact for k models of different pairs: model m against pair d_pair_ids[m] */
 gcr_status gcr_score_exact_multi(gcr_ctx *ctx, int problem, int scoring, const int32_t *d_pair_ids, const double *d_models, int k,
                                  double threshold, double *d_scores, uint32_t *d_counts, uint32_t *d_inlier_idx, double *d_residuals);
