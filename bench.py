@@ -710,14 +710,34 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
         extra["graph_cut_seconds"] = extra.get("graph_cut_seconds", 0.0) + st["graph_cut_seconds"]
         return int(mask.sum()), st["iteration_number"]
 
+    batch_api = args.pairs_api == "batch"
+    if wl["problem"] == "e":
+        find_batch = lambda c, *a, **kw: pygcransac.findEssentialMatrixBatch(c, synth.K_MAT, synth.K_MAT, *a, **kw)
+    else:
+        find_batch = pygcransac.findHomographyBatch if wl["problem"] == "h" else pygcransac.findFundamentalMatrixBatch
+
     def one_pass(s):
-        """`workers` host threads, each with its own gcr_ctx / stream, take the pairs of the step from a queue."""
+        """batch: ONE call for the step's pairs -- they sit on the GPU together and advance in lock-step, every kind of
+        device operation one launch for all of them (host/gcr_batch_engine.h).  threads: `workers` host threads, each with
+        its own gcr_ctx / stream, take the pairs of the step from a queue (pygcransac.find*, one pair per call)."""
+        if batch_api:
+            seeds = np.array([100 * s + p + 1 for p in range(n_pairs)], dtype=np.uint64)
+            M, masks, counts = find_batch(pts, *sizes, threshold=wl["thr"], conf=0.99, spatial_coherence_weight=weight,
+                                          max_iters=max_iters, min_iters=50, use_sprt=False, sampler=wl.get("sampler", 0), neighborhood=0,
+                                          neighborhood_size=4.0, lo_number=50, seeds=seeds, device=local_rank,
+                                          scoring=1 if wl.get("scoring") == "magsac" else 0, seats=args.seats, engines=args.engines)
+            stats = pygcransac.last_batch_statistics
+            for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):
+                extra[k] = extra.get(k, 0) + sum(getattr(stats[p], k) for p in range(n_pairs))
+            extra["graph_cut_seconds"] = extra.get("graph_cut_seconds", 0.0) + sum(stats[p].graph_cut_seconds for p in range(n_pairs))
+            return int(counts.sum()), sum(stats[p].iteration_number for p in range(n_pairs))
         out = list(pool.map(one_pair, [(s, p) for p in range(n_pairs)]))
         return sum(o[0] for o in out), sum(o[1] for o in out)
 
     for s in range(warmup):
         one_pass(s)
-    launch_total = lambda: sum(c.launch_count() for (d, _), c in list(pygcransac._contexts.items()) if d == local_rank)
+    launch_total = lambda: (sum(c.launch_count() for (d, _), c in list(pygcransac._contexts.items()) if d == local_rank) +
+                            pygcransac.batch_launch_count())
     launches0 = launch_total()
     clocks = ClockSampler(local_rank).start()
     sess.barrier()
@@ -743,6 +763,8 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
                          "d2h_bytes_per_step": int(n_pairs * (72 + wl["n"]))},
                  "roofline": None})
     line["config"].update({"name": name, "per_pair_mean": {k: v / (n_pairs * (steps + warmup)) for k, v in extra.items()}})
+    line["config"].update({"pairs_api": "find*Batch: one call per step, lock-step multi-pair driver" if batch_api else
+                           "find*: one pair per call from a pool of host threads"})
     line["config"].update({"host_threads_per_gpu": workers, "mean_inliers": inl / (n_pairs * steps), "mean_iterations": its / (n_pairs * steps),
                            "timing": "host wall clock around synchronous API calls (each returns host results), "
                                      "max over ranks"})
@@ -791,12 +813,19 @@ def main():
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--pairs-api", default="threads", choices=["batch", "threads"],
+                    help="pipeline workloads: pygcransac.find*Batch (one call per step) or find* from a pool of host threads")
+    ap.add_argument("--pairs", type=int, default=0, help="pipeline workloads: image pairs per step per GPU (default: workload's)")
+    ap.add_argument("--seats", type=int, default=0, help="batch API: pairs resident on the GPU at a time (0 = library default)")
+    ap.add_argument("--engines", type=int, default=0, help="batch API: contexts / dispatcher threads (0 = library default)")
     ap.add_argument("--workers", type=int, default=0, help="pipeline workloads: host threads (one gcr_ctx each) per GPU")
     args = ap.parse_args()
     name = args.workload or "f4k"
     wl = dict(WORKLOADS[name])
     if args.samples:
         wl["samples"] = args.samples
+    if args.pairs and wl.get("pipeline"):
+        wl["pairs"] = args.pairs
     rank = int(os.environ.get("RANK", "0"))
 
     if args.impl == "reference":

@@ -1230,6 +1230,8 @@ namespace
 	thread_local std::string g_driver_error;
 }
 
+#include "gcr_batch_engine_impl.h" // the lock-step multi-pair driver over the same Driver class
+
 extern "C" void gcr_run_settings_default(gcr_run_settings *s)
 {
 	if (!s)

@@ -75,6 +75,20 @@ def _load_driver():
         lib.gcr_find_essential.restype = C.c_int
         lib.gcr_find_essential.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(RunSettings),
                                            C.c_void_p, C.c_void_p, C.POINTER(RunStats)]
+        u64p = C.c_void_p
+        lib.gcr_find_model_batch.restype = C.c_int
+        lib.gcr_find_model_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(RunSettings), u64p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gcr_find_essential_batch.restype = C.c_int
+        lib.gcr_find_essential_batch.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.POINTER(RunSettings), u64p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]
+        lib.gcr_batch_engines_release.restype = None
+        lib.gcr_batch_engines_release.argtypes = []
+        lib.gcr_batch_launch_count.restype = C.c_uint64
+        lib.gcr_batch_launch_count.argtypes = []
+        lib.gcr_driver_last_error.restype = C.c_char_p
+        lib.gcr_driver_last_error.argtypes = []
         _driver = lib
     return _driver
 
@@ -92,6 +106,39 @@ def _context(device=0):
 
 _tls = threading.local()  # _tls.last_statistics: the calling thread's most recent RunStats
 last_statistics = None  # RunStats of the most recent call (the reference fills utils::RANSACStatistics; not returned by its API either)
+
+
+def _settings(lib, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler, neighborhood,
+              neighborhood_size, lo_number, eps_in_cell_size, seed, use_degensac, f_bundle_adjustment, prob, sampler_variance,
+              scoring, e_bundle_adjustment, pnp_bundle_adjustment):
+    """gcr_run_settings as the reference's drivers fill utils::Settings (py/gcransac_python.cpp:4498-4504)."""
+    s = RunSettings()
+    lib.gcr_run_settings_default(C.byref(s))
+    s.threshold, s.confidence, s.spatial_coherence_weight = threshold, conf, spatial_coherence_weight
+    s.max_iteration_number, s.min_iteration_number = max_iters, min_iters
+    s.max_local_optimization_number = lo_number
+    cells = int(neighborhood_size)                                          # static_cast<size_t>(neighborhood_size)
+    h1, w1, h2, w2 = sizes
+    eps = np.finfo(np.float64).eps if eps_in_cell_size else 0.0            # gcransac_python.cpp:4290-4297 vs :1672-1677
+    s.cells_per_axis = max(cells, 1)
+    for i, v in enumerate((w1, h1, w2, h2)):
+        s.cell_sizes[i] = (v + eps) / max(cells, 1)
+    s.seed = seed
+    s.use_degensac = 1 if use_degensac else 0
+    s.sampler = sampler
+    # neighborhood=1: the reference builds a FLANN radius graph with radius neighborhood_size (py/gcransac_python.cpp
+    # :123-125); here the exact radius graph (gcr_radius_graph_*).  The grid settings below are then unused.
+    s.neighborhood = neighborhood
+    s.neighborhood_radius = float(neighborhood_size)
+    s.f_bundle_adjustment = f_bundle_adjustment
+    s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
+    s.sampler_variance = float(sampler_variance)
+    s.scoring = int(scoring)
+    s.e_bundle_adjustment = int(e_bundle_adjustment)
+    s.pnp_bundle_adjustment = int(pnp_bundle_adjustment)
+    for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
+        s.image_sizes[i] = float(v)
+    return s
 
 
 def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
@@ -123,32 +170,9 @@ def _find(problem, correspondences, sizes, threshold, conf, spatial_coherence_we
         raise ValueError("neighborhood should be 0 (grid) or 1 (radius)")
     lib = _load_driver()
     ctx = _context(device)
-    s = RunSettings()
-    lib.gcr_run_settings_default(C.byref(s))
-    s.threshold, s.confidence, s.spatial_coherence_weight = threshold, conf, spatial_coherence_weight
-    s.max_iteration_number, s.min_iteration_number = max_iters, min_iters
-    s.max_local_optimization_number = lo_number
-    cells = int(neighborhood_size)                                          # static_cast<size_t>(neighborhood_size)
-    h1, w1, h2, w2 = sizes
-    eps = np.finfo(np.float64).eps if eps_in_cell_size else 0.0            # gcransac_python.cpp:4290-4297 vs :1672-1677
-    s.cells_per_axis = max(cells, 1)
-    for i, v in enumerate((w1, h1, w2, h2)):
-        s.cell_sizes[i] = (v + eps) / max(cells, 1)
-    s.seed = seed
-    s.use_degensac = 1 if use_degensac else 0
-    s.sampler = sampler
-    # neighborhood=1: the reference builds a FLANN radius graph with radius neighborhood_size (py/gcransac_python.cpp
-    # :123-125); here the exact radius graph (gcr_radius_graph_*).  The grid settings below are then unused.
-    s.neighborhood = neighborhood
-    s.neighborhood_radius = float(neighborhood_size)
-    s.f_bundle_adjustment = f_bundle_adjustment
-    s.point_probabilities = prob.ctypes.data if sampler in (3, 4) else None
-    s.sampler_variance = float(sampler_variance)
-    s.scoring = int(scoring)
-    s.e_bundle_adjustment = int(e_bundle_adjustment)
-    s.pnp_bundle_adjustment = int(pnp_bundle_adjustment)
-    for i, v in enumerate((w1, h1, w2, h2)):                                # sampler 2: ProgressiveNapsacSampler's `sizes_`
-        s.image_sizes[i] = float(v)
+    s = _settings(lib, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler, neighborhood,
+                  neighborhood_size, lo_number, eps_in_cell_size, seed, use_degensac, f_bundle_adjustment, prob, sampler_variance,
+                  scoring, e_bundle_adjustment, pnp_bundle_adjustment)
     model = np.zeros(12 if problem == _cabi.PNP else 9)
     mask = np.zeros(len(pts), dtype=np.uint8)
     stats = RunStats()
@@ -247,3 +271,98 @@ def find6DPose(correspondences, probabilities=(), threshold=0.001, conf=0.99, sp
     return _find(_cabi.PNP, correspondences, (0, 0, 0, 0), threshold, conf, spatial_coherence_weight, max_iters, min_iters,
                  sampler, 1, neighborhood_size, lo_number, False, seed, device, probabilities=probabilities,
                  sampler_variance=sampler_variance, scoring=scoring, pnp_bundle_adjustment=1 if bundle_adjustment else 0)
+
+
+# ------------------------------------------------------------------------------------------------ batches ----
+# P image pairs per call.  The reference has no such entry point (its counterpart is one problem per
+# host core); here the pairs sit on the GPU together and advance in lock-step -- host/gcr_batch_engine.h -- and every
+# pair returns what the single-pair function returns for it with seed seeds[p].
+last_batch_statistics = None
+
+
+def _find_batch(problem, correspondences, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler,
+                neighborhood, neighborhood_size, lo_number, eps_in_cell_size, seeds, device, seats, engines, intrinsics=None,
+                use_degensac=False, f_bundle_adjustment=0, scoring=0, e_bundle_adjustment=0):
+    global last_batch_statistics
+    pts = np.ascontiguousarray(correspondences, dtype=np.float64)
+    min_n = {_cabi.H: 4, _cabi.F: 7, _cabi.E: 5}[problem]
+    if pts.ndim != 3 or pts.shape[2] != 4 or pts.shape[1] < min_n:
+        raise ValueError("correspondences should be an array with dims [pairs,n,4], n>=%d" % min_n)
+    if sampler not in (0, 1, 2):
+        raise NotImplementedError("sampler=%d needs per-pair probabilities: use the single-pair function" % sampler)
+    if neighborhood not in (0, 1):
+        raise ValueError("neighborhood should be 0 (grid) or 1 (radius)")
+    P, n = pts.shape[0], pts.shape[1]
+    if seeds is None:
+        seeds = np.arange(1, P + 1, dtype=np.uint64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    if seeds.shape != (P,):
+        raise ValueError("seeds should have one entry per pair")
+    lib = _load_driver()
+    s = _settings(lib, sizes, threshold, conf, spatial_coherence_weight, max_iters, min_iters, sampler, neighborhood,
+                  neighborhood_size, lo_number, eps_in_cell_size, 0, use_degensac, f_bundle_adjustment, None, 0.1,
+                  scoring, e_bundle_adjustment, 0)
+    models = np.zeros((P, 3, 3))
+    masks = np.zeros((P, n), dtype=np.uint8)
+    counts = np.zeros(P, dtype=np.int32)
+    stats = (RunStats * P)()
+    if intrinsics is None:
+        r = lib.gcr_find_model_batch(device, problem, pts.ctypes.data, n, P, C.byref(s), seeds.ctypes.data, seats, engines,
+                                     models.ctypes.data, masks.ctypes.data, counts.ctypes.data, C.cast(stats, C.c_void_p))
+    else:
+        K1, K2 = intrinsics
+        per_pair = 1 if K1.ndim == 3 else 0
+        r = lib.gcr_find_essential_batch(device, pts.ctypes.data, n, P, K1.ctypes.data, K2.ctypes.data, per_pair, C.byref(s),
+                                         seeds.ctypes.data, seats, engines, models.ctypes.data, masks.ctypes.data,
+                                         counts.ctypes.data, C.cast(stats, C.c_void_p))
+    if r < 0:
+        raise _cabi.GcrError("gcr_find_model_batch failed (%d): %s" % (r, lib.gcr_driver_last_error().decode()))
+    last_batch_statistics = stats
+    return models, masks.astype(bool), counts
+
+
+def findHomographyBatch(correspondences, h1, w1, h2, w2, threshold=1.0, conf=0.99, spatial_coherence_weight=0.975,
+                        max_iters=10000, min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.00001, sampler=1, neighborhood=0,
+                        neighborhood_size=4.0, use_space_partitioning=True, lo_number=50, seeds=None, device=0, scoring=0,
+                        seats=0, engines=0):
+    """findHomography for P pairs of n correspondences each ([P][n][4]): returns (H [P][3][3], masks bool [P][n],
+    inlier counts [P]; count 0 = no model, where findHomography returns None).  seeds: one sample-stream seed per pair
+    (default 1..P); pair p's result equals findHomography(correspondences[p], ..., seed=seeds[p])."""
+    if use_space_partitioning and neighborhood != 0:
+        neighborhood = 0                                                    # py/gcransac_python.cpp:4282-4286
+    return _find_batch(_cabi.H, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters, min_iters,
+                       sampler, neighborhood, neighborhood_size, lo_number, True, seeds, device, seats, engines, scoring=scoring)
+
+
+def findFundamentalMatrixBatch(correspondences, h1, w1, h2, w2, threshold=1.0, conf=0.99, spatial_coherence_weight=0.0,
+                               max_iters=10000, min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.00001, sampler=1,
+                               neighborhood=1, neighborhood_size=20.0, lo_number=50, seeds=None, device=0, use_degensac=True,
+                               bundle_adjustment=True, scoring=0, seats=0, engines=0):
+    """findFundamentalMatrix (the reference's default pipeline: BA refits, DEGENSAC, post-run BA) for P pairs ([P][n][4])."""
+    return _find_batch(_cabi.F, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters, min_iters,
+                       sampler, neighborhood, neighborhood_size, lo_number, False, seeds, device, seats, engines,
+                       use_degensac=use_degensac, f_bundle_adjustment=3 if bundle_adjustment else 0, scoring=scoring)
+
+
+def findEssentialMatrixBatch(correspondences, K1, K2, h1, w1, h2, w2, threshold=1.0, conf=0.99, spatial_coherence_weight=0.1,
+                             max_iters=10000, min_iters=50, use_sprt=True, min_inlier_ratio_for_sprt=0.01, sampler=1,
+                             neighborhood=1, neighborhood_size=20.0, lo_number=50, seeds=None, device=0, scoring=0,
+                             bundle_adjustment=True, seats=0, engines=0):
+    """findEssentialMatrix for P pairs ([P][n][4] pixel correspondences); K1 / K2: 3 x 3 for all pairs or [P][3][3]."""
+    K1 = np.ascontiguousarray(K1, dtype=np.float64)
+    K2 = np.ascontiguousarray(K2, dtype=np.float64)
+    if K1.shape != K2.shape or K1.shape[-2:] != (3, 3) or K1.ndim not in (2, 3):
+        raise ValueError("K1 / K2 shape should be [3x3] or [pairs,3,3]")
+    return _find_batch(_cabi.E, correspondences, (h1, w1, h2, w2), threshold, conf, spatial_coherence_weight, max_iters, min_iters,
+                       sampler, neighborhood, neighborhood_size, lo_number, False, seeds, device, seats, engines,
+                       intrinsics=(K1, K2), scoring=scoring, e_bundle_adjustment=1 if bundle_adjustment else 0)
+
+
+def batch_launch_count():
+    """Kernels launched so far by the batch engines of this process."""
+    return int(_load_driver().gcr_batch_launch_count())
+
+
+def release_batch_engines():
+    """Frees the GPU contexts / buffers the batch calls keep between calls."""
+    _load_driver().gcr_batch_engines_release()
