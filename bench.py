@@ -487,6 +487,51 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         pts_host32 = pts_host.to(torch.float32).pin_memory() if use_f32 else None
     h2d_bytes_per_round = int(pts_host.numel() * (4 if use_f32 else 8))
 
+    # ONE pair, many rounds: consecutive rounds alternate between a few contexts (streams, model slots, workspaces), so the
+    # solver kernel of round i + 1 (FP64 pipe, latency-bound) runs beside the scoring kernel of round i (FP32 FMA pipe) and the
+    # upload of the next round's points hides behind both.  The resident leg stays on ONE stream so that K3's launch times
+    # (the roofline) are undisturbed; its multi-stream figure is reported beside it (config.multi_stream_resident).
+    two_lanes = (not overlap) and (not hyps_sharded) and n_pairs == 1 and args.lanes >= 2
+    lanes = []
+    if two_lanes:
+        pairs_cs = [(ctx, stream)]
+        for _ in range(args.lanes - 1):
+            cB = _cabi.Context(local_rank)
+            sB = torch.cuda.Stream()
+            cB.set_stream(sB.cuda_stream)
+            if args.variant >= 0:
+                cB.set_score_variant(args.variant)
+            pairs_cs.append((cB, sB))
+        for c_, s_ in pairs_cs:
+            lanes.append({"ctx": c_, "stream": s_, "keys": torch.zeros(1, dtype=torch.int64, device="cuda"),
+                          "best": torch.zeros(1, 9, dtype=torch.float64, device="cuda"),
+                          "keys_host": torch.zeros(1, dtype=torch.int64).pin_memory(),
+                          "best_host": torch.zeros(1, 9, dtype=torch.float64).pin_memory()})
+
+    def lane_round(i, lane, with_copies):
+        c_ = lane["ctx"]
+        with torch.cuda.stream(lane["stream"]):
+            if with_copies:
+                upload(c_, 0, 1)
+            ev = c_.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345, wl["thr"], flags, 0,
+                                 lane["keys"].data_ptr(), lane["best"].data_ptr())
+            if with_copies:
+                lane["keys_host"].copy_(lane["keys"], non_blocking=True)
+                lane["best_host"].copy_(lane["best"], non_blocking=True)
+        return ev
+
+    def step_lanes(i, with_copies):
+        start = torch.cuda.Event()
+        start.record(stream)
+        for lane in lanes[1:]:
+            lane["stream"].wait_event(start)
+        ev = sum(lane_round(i * rounds + r, lanes[r % len(lanes)], with_copies) for r in range(rounds))
+        for lane in lanes[1:]:
+            done = torch.cuda.Event()
+            done.record(lane["stream"])
+            stream.wait_event(done)
+        return ev
+
     def upload(c, lo, hi):
         if use_f32:
             c.check(c.lib.gcr_points_upload_f32(c.h, pts_host32[lo:hi].data_ptr(), n, 4, hi - lo))
@@ -518,6 +563,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         return ev
 
     def step_e2e(i):
+        if two_lanes:
+            return step_lanes(i, True)
         if not overlap:
             return sum(round_e2e(i * rounds + r) for r in range(rounds))
         # the side streams start after the step's start event and the step's end event waits for all of them; inside the
@@ -580,6 +627,20 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         frac_counts = (c_valid * n, c_ms)
     ctx.profile_enable(False)
 
+    # ---- the resident pass once more with the rounds alternating between two streams (what the e2e leg does) ----
+    ms_two = None
+    if two_lanes:
+        for lane in lanes[1:]:
+            lane["ctx"].points_set_device(pts_dev.data_ptr(), n, 4, 1)
+        for i in range(2):
+            step_lanes(i, False)
+        for lane in lanes:
+            lane["ctx"].counters(reset=True)
+        n2 = max(1, min(steps, 5))
+        ms_two, _ = timed(lambda i: step_lanes(i, False), warmup + steps, n2)
+        ev_two = sum(lane["ctx"].counters(reset=True)[0] for lane in lanes) * n
+        ms_two = (ms_two / (n2 * rounds), ev_two / (ms_two * 1e-3))
+
     # ---- hardware proof of SURVEY 8(e) row 2: the N-rank winner record == the 1-rank record, bit for bit ----
     sharded_equal, rec = None, None
     if hyps_sharded:
@@ -603,12 +664,17 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
     if overlap:
         for c2, _ in side:
             c2.counters(reset=True)
+    if two_lanes:
+        for lane in lanes[1:]:
+            lane["ctx"].counters(reset=True)
     ms_e2e, _ = timed(step_e2e, warmup, steps)
     sess.barrier()
     clock_info = clocks.stop()
     evals_e2e = ctx.counters(reset=True)[0] * n
     if overlap:
         evals_e2e = sum(c2.counters(reset=True)[0] for c2, _ in side) * n
+    if two_lanes:
+        evals_e2e += sum(lane["ctx"].counters(reset=True)[0] for lane in lanes[1:]) * n
 
     # ---- max over ranks, sum of work ----
     ms, ms_e2e = sess.reduce([ms, ms_e2e], "max")
@@ -658,9 +724,16 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
                     "ms_per_round": ms_e2e / total_rounds,
                     "h2d_gbs": h2d_bytes_per_round * total_rounds / (ms_e2e * 1e-3) / 1e9,
                     "overlap": ("%d chunks of pairs on %d contexts / streams: uploads overlap scoring; %s upload" % (
-                        E2E_CHUNKS, E2E_SIDE, args.upload)) if overlap else "none"},
+                        E2E_CHUNKS, E2E_SIDE, args.upload)) if overlap else
+                        ("rounds alternate between %d contexts / streams:" % len(lanes) + " the solver kernel and the upload of round i + 1 run "
+                         "beside the scoring kernel of round i") if two_lanes else "none"},
             "gpu_launches": int(launches),
         }
+        if ms_two:
+            line["config"]["multi_stream_resident"] = {"streams": len(lanes), "ms_per_round": ms_two[0], "evals_per_s": ms_two[1],
+                                                      "note": "the resident pass with consecutive rounds alternating between the streams (K2 of "
+                                                              "round i + 1 beside K3 of round i), as the e2e leg runs; `value` and the roofline "
+                                                              "are the one-stream pass, where K3's launch time is undisturbed"}
         if frac_counts:
             a_c = frac_counts[0] * flop / (frac_counts[1] * 1e-3) / 1e12 if frac_counts[1] > 0 else None
             line["roofline"]["frac_with_exact_counts"] = a_c / peak["sustained"] if a_c else None
@@ -672,6 +745,9 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
     if overlap:
         for c2, _ in side:
             c2.close()
+    if two_lanes:
+        for lane in lanes[1:]:
+            lane["ctx"].close()
     ctx.close()
     return line
 
@@ -812,6 +888,8 @@ def main():
     ap.add_argument("--exact-counts", action="store_true",
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")
+    ap.add_argument("--lanes", type=int, default=4, choices=[1, 2, 3, 4],
+                    help="single-pair workloads, e2e leg: consecutive rounds alternate between this many contexts / streams")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--pairs-api", default="threads", choices=["batch", "threads"],
                     help="pipeline workloads: pygcransac.find*Batch (one call per step) or find* from a pool of host threads")
