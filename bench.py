@@ -538,7 +538,7 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         else:
             c.check(c.lib.gcr_points_upload(c.h, pts_host[lo:hi].data_ptr(), n, 4, hi - lo))
 
-    def round_e2e(i):
+    def round_e2e(i, with_copies=True):
         """one round through the C ABI with HOST buffers: H2D of the points, the round, D2H of the result"""
         if not overlap:
             upload(ctx, 0, n_pairs)
@@ -554,17 +554,19 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
             c2, s2 = side[c % E2E_SIDE]
             lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
             with torch.cuda.stream(s2):
-                upload(c2, lo, hi)
+                if with_copies:
+                    upload(c2, lo, hi)
                 ev += c2.round_device(prob, scoring, _cabi.UNIFORM, i * wl["samples"], wl["samples"], 12345 + c, wl["thr"], flags, 0,
                                       keys[lo:hi].data_ptr(), best[lo:hi].data_ptr())
                 tail(c2, lo, hi)
-                keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
-                best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
+                if with_copies:
+                    keys_host[lo:hi].copy_(keys[lo:hi], non_blocking=True)
+                    best_host[lo:hi].copy_(t_refit[lo:hi], non_blocking=True)
         return ev
 
-    def step_e2e(i):
+    def step_e2e(i, with_copies=True):
         if two_lanes:
-            return step_lanes(i, True)
+            return step_lanes(i, with_copies)
         if not overlap:
             return sum(round_e2e(i * rounds + r) for r in range(rounds))
         # the side streams start after the step's start event and the step's end event waits for all of them; inside the
@@ -574,7 +576,7 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         start.record(stream)
         for c2, s2 in side:
             s2.wait_event(start)
-        ev = sum(round_e2e(i * rounds + r) for r in range(rounds))
+        ev = sum(round_e2e(i * rounds + r, with_copies) for r in range(rounds))
         for c2, s2 in side:
             done = torch.cuda.Event()
             done.record(s2)
@@ -639,6 +641,22 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         n2 = max(1, min(steps, 5))
         ms_two, _ = timed(lambda i: step_lanes(i, False), warmup + steps, n2)
         ev_two = sum(lane["ctx"].counters(reset=True)[0] for lane in lanes) * n
+        ms_two = (ms_two / (n2 * rounds), ev_two / (ms_two * 1e-3))
+
+    if overlap and E2E_CHUNKS == E2E_SIDE:
+        # a batch of pairs: the same, with the chunks of pairs the e2e leg uses (every side context keeps its chunk resident)
+        for c in range(E2E_CHUNKS):
+            lo, hi = c * chunk, n_pairs if c == E2E_CHUNKS - 1 else (c + 1) * chunk
+            with torch.cuda.stream(side[c][1]):
+                side[c][0].points_set_device(pts_dev[lo:hi].data_ptr(), n, 4, hi - lo)
+        torch.cuda.synchronize()
+        for i in range(2):
+            step_e2e(i, False)
+        for c2, _ in side:
+            c2.counters(reset=True)
+        n2 = max(1, min(steps, 5))
+        ms_two, _ = timed(lambda i: step_e2e(i, False), warmup + steps, n2)
+        ev_two = sum(c2.counters(reset=True)[0] for c2, _ in side) * n
         ms_two = (ms_two / (n2 * rounds), ev_two / (ms_two * 1e-3))
 
     # ---- hardware proof of SURVEY 8(e) row 2: the N-rank winner record == the 1-rank record, bit for bit ----
@@ -729,8 +747,10 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
                          "beside the scoring kernel of round i") if two_lanes else "none"},
             "gpu_launches": int(launches),
         }
+        if ms_two and n_pairs > 1:
+            line["config"]["pairs_per_s_multi_stream"] = world * n_pairs / (ms_two[0] * 1e-3)
         if ms_two:
-            line["config"]["multi_stream_resident"] = {"streams": len(lanes), "ms_per_round": ms_two[0], "evals_per_s": ms_two[1],
+            line["config"]["multi_stream_resident"] = {"streams": len(lanes) if two_lanes else E2E_SIDE, "ms_per_round": ms_two[0], "evals_per_s": ms_two[1],
                                                       "note": "the resident pass with consecutive rounds alternating between the streams (K2 of "
                                                               "round i + 1 beside K3 of round i), as the e2e leg runs; `value` and the roofline "
                                                               "are the one-stream pass, where K3's launch time is undisturbed"}
@@ -853,7 +873,7 @@ def compact(line):
            "steps": line["steps"], "scaling": line["scaling"], "e2e": line["e2e"]["value"], "workload": line["config"]["workload"],
            "gpu_launches": line.get("gpu_launches")}
     cfg = line["config"]
-    for k in ("rounds_per_step", "ms_per_round", "timed_region_s", "pairs_per_s", "pairs_per_s_e2e", "sharded_equals_single_gpu",
+    for k in ("rounds_per_step", "ms_per_round", "timed_region_s", "pairs_per_s", "pairs_per_s_e2e", "pairs_per_s_multi_stream", "multi_stream_resident", "sharded_equals_single_gpu",
               "winner_record", "mean_inliers", "mean_iterations", "host_threads_per_gpu", "models_scored_per_round"):
         if cfg.get(k) is not None:
             out[k] = cfg[k]
@@ -931,7 +951,7 @@ def main():
         for ename in EXTRA_PIPELINES:
             t0 = time.perf_counter()
             ewl = dict(WORKLOADS[ename])
-            l2 = gpu_pairs(sess, args, ename, ewl, 2, 1)
+            l2 = gpu_pairs(sess, args, ename, ewl, 3, 2)
             if rank == 0:
                 extra[ename] = compact(l2)
                 if with_cpu:
