@@ -839,8 +839,11 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     sess.barrier()
     t0 = time.perf_counter()
     inl = its = 0
+    step_ms = []
     for s in range(steps):
+        ts = time.perf_counter()
         a, b = one_pass(warmup + s)
+        step_ms.append(round(1e3 * (time.perf_counter() - ts), 2))
         inl, its = inl + a, its + b
     sess.barrier()
     wall = time.perf_counter() - t0
@@ -861,7 +864,7 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     line["config"].update({"name": name, "per_pair_mean": {k: v / (n_pairs * (steps + warmup)) for k, v in extra.items()}})
     line["config"].update({"pairs_api": "find*Batch: one call per step, lock-step multi-pair driver" if batch_api else
                            "find*: one pair per call from a pool of host threads"})
-    line["config"].update({"host_threads_per_gpu": workers, "mean_inliers": inl / (n_pairs * steps), "mean_iterations": its / (n_pairs * steps),
+    line["config"].update({"step_ms": step_ms, "host_threads_per_gpu": workers, "mean_inliers": inl / (n_pairs * steps), "mean_iterations": its / (n_pairs * steps),
                            "timing": "host wall clock around synchronous API calls (each returns host results), "
                                      "max over ranks"})
     return line

@@ -33,7 +33,14 @@ namespace gcr_e5g
 	constexpr int OFF_POLY = OFF_P + 39;          // c[11] -> f[11] in place, df[11]
 	constexpr int OFF_DEG = OFF_POLY + 22;        // 12 ints: deg[11], len
 	constexpr int OFF_IV = OFF_DEG + 6;           // isolated intervals (a, b) x 10, then the finite / valid flags
-	constexpr int SAMPLE_DOUBLES = OFF_IV + 30;
+	// + 2: 464 doubles = 928 words would put the three samples of a warp on the SAME banks (928 % 32 == 0) -- three wavefronts
+	// for every row / chain access of the 30 lanes; shifted by 4 words per sample the three ten-lane patterns (stride 42 or 22
+	// words) interleave with at most two lanes per bank: 44 M -> 9 M bank conflicts, k_solve_e5 620 -> 590 us per 65 536 samples.
+	// (+ 14 pushes the CTA over 45 KB: four CTAs per SM instead of five, slower.)
+#ifndef E5_SAMPLE_PAD
+#define E5_SAMPLE_PAD 2
+#endif
+	constexpr int SAMPLE_DOUBLES = OFF_IV + 30 + E5_SAMPLE_PAD;
 	static_assert(OFF_STACK + STACK_DOUBLES <= OFF_CHAIN, "the interval stack must end before the Sturm chain");
 
 	__device__ __forceinline__ int sgn_of(double v) { return v > 0.0 ? 1 : (v < 0.0 ? -1 : 0); }

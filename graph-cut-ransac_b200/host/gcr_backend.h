@@ -88,6 +88,29 @@ namespace gcr_host
 		virtual bool refit_sets(int refit_problem, int ba_frame, const uint32_t *flat, const std::vector<uint32_t> &offsets,
 		                        const std::vector<uint32_t> &sizes, const double *weights, size_t n_weights, int weight_mode,
 		                        std::vector<double> &models, std::vector<uint8_t> &ok) = 0;
+		// refit_sets followed by the FP64 getScore of every model it returned, as ONE submission where the backend can (the
+		// IRLS round, the final fit and the post-run polish are "fit, then score the fit"): score / count [k], idx [k][n]
+		// (the first count entries of a row), residuals [k][n] when wanted; k = sets x models per fit.  Same kernels on the
+		// same inputs as the two separate operations.
+		virtual bool refit_and_score(int refit_problem, int ba_frame, const uint32_t *flat, const std::vector<uint32_t> &offsets,
+		                             const std::vector<uint32_t> &sizes, const double *weights, size_t n_weights, int weight_mode,
+		                             int scoring, double T, double threshold, bool want_residuals, std::vector<double> &models,
+		                             std::vector<uint8_t> &ok, std::vector<double> &score, std::vector<uint32_t> &count,
+		                             std::vector<uint32_t> &idx, std::vector<double> &residuals)
+		{
+			if (!refit_sets(refit_problem, ba_frame, flat, offsets, sizes, weights, n_weights, weight_mode, models, ok))
+				return false;
+			const size_t k = ok.size();
+			score.assign(k, 0.0);
+			count.assign(k, 0u);
+			idx.resize(k * (size_t)n);
+			residuals.resize(want_residuals ? k * (size_t)n : 0);
+			for (size_t q = 0; q < k; ++q)
+				if (ok[q] && !exact(&models[q * ml], scoring, T, threshold, score[q], count[q], &idx[q * (size_t)n],
+				                    want_residuals ? &residuals[q * (size_t)n] : nullptr))
+					return false;
+			return true;
+		}
 		virtual bool lo_batch(const LoSpec &spec, std::vector<double> &models, std::vector<uint8_t> &ok, std::vector<float> &scores32) = 0;
 		virtual bool refit_e_ba(const uint32_t *set, size_t count, const double *weights, std::vector<double> &models,
 		                        std::vector<uint8_t> &ok) = 0;
@@ -378,6 +401,36 @@ namespace gcr_host
 			if (!launch_refit(rp, ba_frame, flat, offsets, sizes, weights, n_weights, weight_mode, models, ok))
 				return false;
 			return gcr_sync(ctx) == GCR_OK || fail("gcr_sync");
+		}
+		bool refit_and_score(int rp, int ba_frame, const uint32_t *flat, const std::vector<uint32_t> &offsets, const std::vector<uint32_t> &sizes,
+		                     const double *weights, size_t n_weights, int weight_mode, int scoring, double, double threshold,
+		                     bool want_residuals, std::vector<double> &models, std::vector<uint8_t> &ok, std::vector<double> &score,
+		                     std::vector<uint32_t> &count, std::vector<uint32_t> &idx, std::vector<double> &residuals) override
+		{
+			if (gcr_model_len(rp) != ml) // (a fit of another model family: scored by its own call)
+				return Backend::refit_and_score(rp, ba_frame, flat, offsets, sizes, weights, n_weights, weight_mode, scoring, 0.0, threshold,
+				                                want_residuals, models, ok, score, count, idx, residuals);
+			if (!launch_refit(rp, ba_frame, flat, offsets, sizes, weights, n_weights, weight_mode, models, ok))
+				return false; // (its read-backs are queued; the scores below travel with them)
+			const size_t k = ok.size();
+			if (!d_cand_scores.ensure(ctx, k * sizeof(double)) || !d_cand_counts.ensure(ctx, k * sizeof(uint32_t)) ||
+			    !d_cand_idx.ensure(ctx, k * (size_t)n * sizeof(uint32_t)) || (want_residuals && !d_res.ensure(ctx, k * (size_t)n * sizeof(double))))
+				return fail("gcr_malloc");
+			// every slot of the fit is scored, a failed fit's zero model included (its numbers are never read)
+			if (gcr_score_exact(ctx, problem, scoring, pair, d_lmodels.as<double>(), (int)k, threshold, d_cand_scores.as<double>(),
+			                    d_cand_counts.as<uint32_t>(), d_cand_idx.as<uint32_t>(), want_residuals ? d_res.as<double>() : nullptr) != GCR_OK)
+				return fail("gcr_score_exact");
+			score.resize(k);
+			count.resize(k);
+			idx.resize(k * (size_t)n);
+			residuals.resize(want_residuals ? k * (size_t)n : 0);
+			if (gcr_memcpy_d2h_async(ctx, score.data(), d_cand_scores.p, k * sizeof(double)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, count.data(), d_cand_counts.p, k * sizeof(uint32_t)) != GCR_OK ||
+			    gcr_memcpy_d2h_async(ctx, idx.data(), d_cand_idx.p, k * (size_t)n * sizeof(uint32_t)) != GCR_OK ||
+			    (want_residuals && gcr_memcpy_d2h_async(ctx, residuals.data(), d_res.p, k * (size_t)n * sizeof(double)) != GCR_OK) ||
+			    gcr_sync(ctx) != GCR_OK)
+				return fail("gcr_memcpy_d2h");
+			return true;
 		}
 		bool lo_batch(const LoSpec &spec, std::vector<double> &models, std::vector<uint8_t> &ok, std::vector<float> &scores32) override
 		{

@@ -511,7 +511,9 @@ namespace
 			++st.exact_rescores; // (one FP64 pass over the points, as the residual read-back it replaces)
 			const auto t0 = std::chrono::steady_clock::now();
 			const double *dist = h_unary.data() + 2 * (size_t)n;
-			Energy<double, double, double> *problem_graph = new Energy<double, double, double>(n, 0, NULL);
+			// (the reference passes edge_num_max = 0 and lets the arc array grow by reallocation, ~20 times with a pointer fix-up
+			// pass each; the edge count is known here -- same graph, same arc order, same cut)
+			Energy<double, double, double> *problem_graph = new Energy<double, double, double>(n, (int)E, NULL);
 			for (int i = 0; i < n; ++i)
 				problem_graph->add_node();
 			for (int i = 0; i < n; ++i)
@@ -671,25 +673,55 @@ namespace
 			return true;
 		}
 
+		// refit + FP64 getScore of every model the fit returned, one submission (Backend::refit_and_score)
+		struct Fitted
+		{
+			std::vector<double> models, score, residuals;
+			std::vector<uint8_t> ok;
+			std::vector<uint32_t> count, idx;
+		};
+		bool refit_scored(const uint32_t *flat, uint32_t size, const double *weights, size_t n_weights, int weight_mode, bool want_residuals,
+		                  Fitted &f, int refit_problem = -1, int ba_frame_override = 0)
+		{
+			const int rp = refit_problem < 0 ? problem : refit_problem;
+			std::vector<uint32_t> offsets(1, 0u), sizes(1, size);
+			if (!be->refit_and_score(rp, ba_frame_of(rp, ba_frame_override), flat, offsets, sizes, weights, n_weights, weight_mode, scoring, T,
+			                         S.threshold, want_residuals, f.models, f.ok, f.score, f.count, f.idx, f.residuals))
+				return fail("refit_and_score");
+			for (uint8_t v : f.ok)
+				st.exact_rescores += v ? 1 : 0;
+			return true;
+		}
+		// model q of a scored fit as the reference's getScore would have left it: score, inlier list
+		void take_scored(const Fitted &f, int q, Score &s, std::vector<uint32_t> &inliers) const
+		{
+			s.value = f.score[q];
+			s.inliers = f.count[q];
+			inliers.assign(f.idx.begin() + (size_t)q * n, f.idx.begin() + (size_t)q * n + f.count[q]);
+		}
+
 		// ---- iteratedLeastSquaresFitting (GCRANSAC.h:630-758), single-model estimators ----
+		// One round of the reference = getScore (residuals for the weights) -> weighted fit -> getScore of the fit.  The
+		// fit and the score of its result travel as one submission, and an accepted fit's residuals come back with it: they
+		// are the next round's "getScore of the current model".
 		bool iterated_least_squares(std::vector<uint32_t> &inliers, double *model, bool &success)
 		{
 			success = false;
 			if (inliers.size() <= (size_t)m)
 				return true;
 			size_t iterations = 0;
-			std::vector<double> weights(n, 0.0), r2, models;
-			std::vector<uint8_t> ok;
+			std::vector<double> weights(n, 0.0), r2;
+			bool have_r2 = false;
 			std::vector<uint32_t> tmp;
+			Fitted fit;
 			Score irls_best; // :648
+			const bool weighting = problem != GCR_PNP; // _ModelEstimator::isWeightingApplicable() (:652): false for PnP
 			while (++iterations < S.max_least_squares_iterations)
 			{
 				Score s;
-				const bool weighting = problem != GCR_PNP; // _ModelEstimator::isWeightingApplicable() (:652): false for PnP
-				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inliers.size());
 				if (weighting)
 				{
-					if (!exact(model, s, nullptr, &r2))
+					if (!have_r2 && !exact(model, s, nullptr, &r2))
 						return false;
 					for (uint32_t idx : inliers) // Tukey bisquare weights, written by POINT index (:657-668)
 					{
@@ -698,37 +730,43 @@ namespace
 					}
 					// ... and read by POSITION by the H / 8-point solvers, by POINT by the Stewenius solver
 					// (solver_essential_matrix_five_point_stewenius.h:143): reproduced literally
-					if (!refit(inliers.data(), offsets, sizes, weights.data(), weights.size(), problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL,
-					           models, ok))
+					if (!refit_scored(inliers.data(), (uint32_t)inliers.size(), weights.data(), weights.size(),
+					                  problem == GCR_E ? GCR_WEIGHT_BY_POINT : GCR_WEIGHT_POSITIONAL, true, fit))
 						return false;
 					for (uint32_t idx : inliers)
 						weights[idx] = 0;
 				}
-				else if (!refit(inliers.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok)) // :682-688
+				else if (!refit_scored(inliers.data(), (uint32_t)inliers.size(), nullptr, 0, GCR_WEIGHT_NONE, false, fit)) // :682-688
 					return false;
-				std::vector<const double *> found;
+				std::vector<int> found;
 				for (int q = 0; q < rm; ++q)
-					if (ok[q]) found.push_back(&models[(size_t)q * ml]);
+					if (fit.ok[q]) found.push_back(q);
 				if (found.empty()) // :690
 					break;
+				auto accept = [&](int q) {
+					memcpy(model, &fit.models[(size_t)q * ml], ml * sizeof(double));
+					inliers.swap(tmp);
+					if (weighting)
+					{
+						r2.assign(fit.residuals.begin() + (size_t)q * n, fit.residuals.begin() + (size_t)(q + 1) * n);
+						have_r2 = true;
+					}
+				};
 				if (found.size() == 1) // :692-714
 				{
-					if (!exact(found[0], s, &tmp))
-						return false;
+					take_scored(fit, found[0], s, tmp);
 					if (tmp.size() < (size_t)m)
 						break;
 					if (s.inliers <= inliers.size())
 						break;
-					memcpy(model, found[0], ml * sizeof(double));
-					inliers.swap(tmp);
+					accept(found[0]);
 				}
 				else // :715-748 several models: the best by inlier count, `best_score` lives across the rounds
 				{
 					bool updated = false;
-					for (const double *cand : found)
+					for (int q : found)
 					{
-						if (!exact(cand, s, &tmp))
-							return false;
+						take_scored(fit, q, s, tmp);
 						if (tmp.size() < (size_t)m)
 							continue;
 						if (s.inliers <= inliers.size())
@@ -737,8 +775,7 @@ namespace
 						{
 							updated = true;
 							irls_best = s;
-							memcpy(model, cand, ml * sizeof(double));
-							inliers.swap(tmp);
+							accept(q);
 						}
 					}
 					if (!updated)
@@ -1107,24 +1144,21 @@ namespace
 			PhaseTimer final_timer(st.phase_seconds[5]);
 			if (!iterative_refitting_applied) // :588-617: one least-squares fit on the first best.inliers entries
 			{
-				std::vector<double> models;
-				std::vector<uint8_t> ok;
 				const uint32_t cnt = (uint32_t)std::min<size_t>(best.inliers, buf[offset].idx.size());
-				std::vector<uint32_t> offsets(1, 0u), sizes(1, cnt);
-				if (!refit(buf[offset].idx.data(), offsets, sizes, nullptr, 0, GCR_WEIGHT_NONE, models, ok))
+				Fitted fit;
+				if (!refit_scored(buf[offset].idx.data(), cnt, nullptr, 0, GCR_WEIGHT_NONE, false, fit))
 					return -1;
 				for (int q = 0; q < rm; ++q) // :597-613 every returned model, in order; the best SCORE is not updated there
 				{
-					if (!ok[q])
+					if (!fit.ok[q])
 						continue;
 					const int idx2 = (offset + 1) % 2;
 					Score cur;
 					buf[idx2].lazy = false;
-					if (!exact(&models[(size_t)q * ml], cur, &buf[idx2].idx))
-						return -1;
+					take_scored(fit, q, cur, buf[idx2].idx);
 					if (best.value < cur.value)
 					{
-						memcpy(best_model, &models[(size_t)q * ml], ml * sizeof(double));
+						memcpy(best_model, &fit.models[(size_t)q * ml], ml * sizeof(double));
 						offset = idx2;
 					}
 				}
@@ -1141,25 +1175,25 @@ namespace
 					return -1;
 				for (size_t k = 0; k < inl.size(); ++k)
 					weights[k] = std::max(0.0, 1.0 - r2[inl[k]] / T);
-				std::vector<uint32_t> offsets(1, 0u), sizes(1, (uint32_t)inl.size());
-				if (!refit(inl.data(), offsets, sizes, weights.data(), weights.size(), GCR_WEIGHT_POSITIONAL, models, ok, GCR_F, GCR_BA_PIXEL))
+				// the driver code scores the polished model with an MSACScoringFunction of its own (:1866-1875), whatever
+				// scoring function the run was instantiated with
+				const int run_scoring = scoring;
+				scoring = GCR_MSAC;
+				Fitted fit;
+				const bool fitted = refit_scored(inl.data(), (uint32_t)inl.size(), weights.data(), weights.size(), GCR_WEIGHT_POSITIONAL, false, fit,
+				                                 GCR_F, GCR_BA_PIXEL);
+				scoring = run_scoring;
+				if (!fitted)
 					return -1;
-				if (ok[0])
+				if (fit.ok[0])
 				{
 					const int idx2 = (offset + 1) % 2;
 					Score cur;
 					buf[idx2].lazy = false;
-					// the driver code scores the polished model with an MSACScoringFunction of its own (:1866-1875), whatever
-					// scoring function the run was instantiated with
-					const int run_scoring = scoring;
-					scoring = GCR_MSAC;
-					const bool scored = exact(models.data(), cur, &buf[idx2].idx);
-					scoring = run_scoring;
-					if (!scored)
-						return -1;
+					take_scored(fit, 0, cur, buf[idx2].idx);
 					if (st.score < cur.value) // :1877
 					{
-						memcpy(best_model, models.data(), 9 * sizeof(double));
+						memcpy(best_model, fit.models.data(), 9 * sizeof(double));
 						st.score = cur.value;
 						offset = idx2;
 					}
