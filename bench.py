@@ -954,7 +954,7 @@ def main():
         for ename in EXTRA_PIPELINES:
             t0 = time.perf_counter()
             ewl = dict(WORKLOADS[ename])
-            l2 = gpu_pairs(sess, args, ename, ewl, 3, 2)
+            l2 = gpu_pairs(sess, args, ename, ewl, 6, 2)
             if rank == 0:
                 extra[ename] = compact(l2)
                 if with_cpu:
