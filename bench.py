@@ -419,6 +419,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
     ctx.set_stream(stream.cuda_stream)
     if args.variant >= 0:
         ctx.set_score_variant(args.variant)
+    if args.k3_cap > 0:
+        ctx.set_tuning(_cabi.TUNE_K3_CTAS_PER_SM, args.k3_cap)
     peak = sess.fp32_peak(ctx)
 
     pts_host = torch.from_numpy(make_points(wl, rank)).pin_memory()          # [pairs, n, 4] f64, pinned
@@ -482,6 +484,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
             c2.set_stream(s2.cuda_stream)
             if args.variant >= 0:
                 c2.set_score_variant(args.variant)
+            if args.k3_cap > 0:
+                c2.set_tuning(_cabi.TUNE_K3_CTAS_PER_SM, args.k3_cap)
             side.append((c2, s2))
         chunk = n_pairs // E2E_CHUNKS
         pts_host32 = pts_host.to(torch.float32).pin_memory() if use_f32 else None
@@ -501,6 +505,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
             cB.set_stream(sB.cuda_stream)
             if args.variant >= 0:
                 cB.set_score_variant(args.variant)
+            if args.k3_cap > 0:
+                cB.set_tuning(_cabi.TUNE_K3_CTAS_PER_SM, args.k3_cap)
             pairs_cs.append((cB, sB))
         for c_, s_ in pairs_cs:
             lanes.append({"ctx": c_, "stream": s_, "keys": torch.zeros(1, dtype=torch.int64, device="cuda"),
@@ -794,8 +800,11 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     extra = {}
     sizes = fixture_sizes(wl)
 
+    slow = []
+
     def one_pair(job):
         s, p = job
+        t_pair = time.perf_counter()
         M, mask = find(pts[p], *sizes, [], threshold=wl["thr"], conf=0.99,
                        spatial_coherence_weight=weight, max_iters=max_iters, min_iters=50, use_sprt=False, sampler=wl.get("sampler", 0),
                        neighborhood=0, neighborhood_size=4.0, lo_number=50, seed=100 * s + p + 1, device=local_rank,
@@ -804,6 +813,9 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):
             extra[k] = extra.get(k, 0) + st[k]                          # (approximate under threads: diagnostics only)
         extra["graph_cut_seconds"] = extra.get("graph_cut_seconds", 0.0) + st["graph_cut_seconds"]
+        if os.environ.get("GCR_BENCH_SLOW_PAIRS"):
+            slow.append((round(1e3 * (time.perf_counter() - t_pair), 1), s, p, st["iteration_number"], st["degensac_runs"], st["gpu_batches"],
+                         st["graph_cut_number"], [round(1e3 * v, 1) for v in st["phase_seconds"]]))
         return int(mask.sum()), st["iteration_number"]
 
     batch_api = args.pairs_api == "batch"
@@ -850,6 +862,9 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     clock_info = clocks.stop()
     launches = launch_total() - launches0
     pool.shutdown()
+    if slow:
+        for row in sorted(slow, reverse=True)[:8]:
+            print("slow pair: ms %s step %d pair %d iterations %d degensac_runs %d batches %d graph cuts %d phases %s" % row, file=sys.stderr)
     wall, = sess.reduce([wall], "max")
     total_pairs, launches = sess.reduce([n_pairs * steps, launches], "sum")
     if rank != 0:
@@ -911,6 +926,7 @@ def main():
     ap.add_argument("--exact-counts", action="store_true",
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")
+    ap.add_argument("--k3-cap", type=int, default=0, help="experiment: resident K3 CTAs per SM (0 = all that fit)")
     ap.add_argument("--lanes", type=int, default=4, choices=[1, 2, 3, 4],
                     help="single-pair workloads, e2e leg: consecutive rounds alternate between this many contexts / streams")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")

@@ -35,7 +35,7 @@ namespace gcr_e5g
 	constexpr int OFF_IV = OFF_DEG + 6;           // isolated intervals (a, b) x 10, then the finite / valid flags
 	// + 2: 464 doubles = 928 words would put the three samples of a warp on the SAME banks (928 % 32 == 0) -- three wavefronts
 	// for every row / chain access of the 30 lanes; shifted by 4 words per sample the three ten-lane patterns (stride 42 or 22
-	// words) interleave with at most two lanes per bank: 44 M -> 9 M bank conflicts, k_solve_e5 620 -> 590 us per 65 536 samples.
+	// words) interleave with at most two lanes per bank: 44 M -> 15 M bank conflicts, k_solve_e5 622 -> 593 us per 65 536 samples
 	// (+ 14 pushes the CTA over 45 KB: four CTAs per SM instead of five, slower.)
 #ifndef E5_SAMPLE_PAD
 #define E5_SAMPLE_PAD 2
