@@ -813,7 +813,7 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
         for k in ("exact_rescores", "gpu_batches", "graph_cut_number", "lo_samples"):
             extra[k] = extra.get(k, 0) + st[k]                          # (approximate under threads: diagnostics only)
         extra["graph_cut_seconds"] = extra.get("graph_cut_seconds", 0.0) + st["graph_cut_seconds"]
-        if os.environ.get("GCR_BENCH_SLOW_PAIRS"):
+        if os.environ.get("GCR_BENCH_SLOW_PAIRS") and s >= warmup:
             slow.append((round(1e3 * (time.perf_counter() - t_pair), 1), s, p, st["iteration_number"], st["degensac_runs"], st["gpu_batches"],
                          st["graph_cut_number"], [round(1e3 * v, 1) for v in st["phase_seconds"]]))
         return int(mask.sum()), st["iteration_number"]

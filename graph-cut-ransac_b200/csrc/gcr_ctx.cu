@@ -78,6 +78,7 @@ extern "C" gcr_status gcr_ctx_destroy(gcr_ctx *ctx)
 	cudaFree(ctx->d_upload32);
 	cudaFree(ctx->d_pts32);
 	cudaFree(ctx->d_score_ws);
+	cudaFree(ctx->d_score_amb);
 	cudaFree(ctx->d_norm);
 	cudaFree(ctx->d_bbox);
 	cudaFree(ctx->d_magsac_lut);

@@ -74,6 +74,7 @@ struct gcr_ctx
 	// workspace of gcr_score (compact model list, accumulators, FP64 work list)
 	void *d_score_ws = nullptr;
 	size_t score_ws_capacity = 0;
+	void *d_score_amb = nullptr; // the FP64 re-check list of gcr_score (fixed capacity: allocated once, never with the workspace)
 
 	// scratch
 	void *d_scratch = nullptr;

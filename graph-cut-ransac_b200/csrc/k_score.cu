@@ -887,15 +887,23 @@ static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
 	const size_t o_m32 = take(PK * ml * sizeof(float));
 	const size_t o_accS = take(PK * sizeof(unsigned long long));
 	const size_t o_accC = take(PK * sizeof(uint32_t));
-	const size_t o_amb = take((size_t)AMB_CAPACITY * sizeof(unsigned long long));
+	// The workspace grows geometrically (at least 2 x, from 4 MiB) and the 32 MiB re-check list lives in a block of its own
+	// that is allocated once: cudaFree / cudaMalloc stall every stream of the process, and a host driver's batches come
+	// in a few sizes per run (1 x / 4 x / 16 x the configured one) -- one reallocation per size and context showed up as
+	// 70 ms stalls of every thread of a multi-context pipeline.
+	if (!ctx->d_score_amb)
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_score_amb, (size_t)AMB_CAPACITY * sizeof(unsigned long long)));
 	if (off > ctx->score_ws_capacity)
 	{
+		size_t want = ctx->score_ws_capacity ? 2 * ctx->score_ws_capacity : ((size_t)4 << 20);
+		while (want < off)
+			want *= 2;
 		GCR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_score_ws);
 		ctx->d_score_ws = nullptr;
 		ctx->score_ws_capacity = 0;
-		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_score_ws, off));
-		ctx->score_ws_capacity = off;
+		GCR_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_score_ws, want));
+		ctx->score_ws_capacity = want;
 	}
 	char *base = (char *)ctx->d_score_ws;
 	a.plan = (ScorePlan *)(base + o_head);
@@ -906,7 +914,7 @@ static gcr_status ensure_score_ws(gcr_ctx *ctx, ScoreArgs &a, int ml)
 	a.m32 = (float *)(base + o_m32);
 	a.accS = (unsigned long long *)(base + o_accS);
 	a.accC = (uint32_t *)(base + o_accC);
-	a.amb = (unsigned long long *)(base + o_amb);
+	a.amb = (unsigned long long *)ctx->d_score_amb;
 	GCR_CHECK_CUDA(ctx, cudaMemsetAsync(base + o_head, 0, sizeof(ScorePlan) + (size_t)a.n_pairs * sizeof(uint32_t), ctx->stream));
 	return GCR_OK;
 }
