@@ -140,14 +140,16 @@ extern "C" gcr_status gcr_device_info(gcr_ctx *ctx, int *sm_count, int *sm_clock
 
 extern "C" uint64_t gcr_launch_count(const gcr_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// powers of two up to 256 MiB, 256 MiB granules above: a caller whose requests vary (index lists, staging areas of the
+// multi-pair driver) settles on a handful of block sizes instead of one cudaMalloc -- a device-wide stall -- per size
 static size_t bucket_of(size_t bytes)
 {
 	size_t b = 256;
-	while (b < bytes && b < ((size_t)1 << 20))
+	while (b < bytes && b < ((size_t)256 << 20))
 		b <<= 1;
 	if (b >= bytes)
 		return b;
-	return (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1); // above 1 MiB: MiB granules
+	return (bytes + ((size_t)256 << 20) - 1) & ~(((size_t)256 << 20) - 1);
 }
 extern "C" gcr_status gcr_malloc(gcr_ctx *ctx, size_t bytes, void **d_out)
 {
