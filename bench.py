@@ -32,6 +32,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "graph-cut-ransac_b200"))
+# One hardware work queue per stream: the pipelines run one context (= stream) per host thread, and with the default of 8
+# connections sixteen streams share queues, so a latency-bound kernel of one pair holds up another pair's launches
+# (f4k_pairs 2.2 k -> 2.8 k pairs/s, e2k_pairs 330 -> 370).  Must be in the environment before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 # H-MSAC 21, Sampson-MSAC 35, Sampson-MAGSAC++ 43 flop per evaluation (counted from the reference lines)
 FLOP_PER_EVAL = {("h", "msac"): 21.0, ("f", "msac"): 35.0, ("e", "msac"): 35.0, ("e", "magsac"): 43.0,
@@ -796,6 +800,7 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     from concurrent.futures import ThreadPoolExecutor
     workers = args.workers if args.workers > 0 else max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     pygcransac._load_driver()
+    contexts_before = set(pygcransac._contexts)
     pool = ThreadPoolExecutor(workers)
     extra = {}
     sizes = fixture_sizes(wl)
@@ -862,6 +867,8 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     clock_info = clocks.stop()
     launches = launch_total() - launches0
     pool.shutdown()
+    for key in set(pygcransac._contexts) - contexts_before:      # the contexts of this pool's threads (one per thread)
+        pygcransac._contexts.pop(key).close()
     if slow:
         for row in sorted(slow, reverse=True)[:8]:
             print("slow pair: ms %s step %d pair %d iterations %d degensac_runs %d batches %d graph cuts %d phases %s" % row, file=sys.stderr)
@@ -891,7 +898,7 @@ def compact(line):
            "steps": line["steps"], "scaling": line["scaling"], "e2e": line["e2e"]["value"], "workload": line["config"]["workload"],
            "gpu_launches": line.get("gpu_launches")}
     cfg = line["config"]
-    for k in ("rounds_per_step", "ms_per_round", "timed_region_s", "pairs_per_s", "pairs_per_s_e2e", "pairs_per_s_multi_stream", "multi_stream_resident", "sharded_equals_single_gpu",
+    for k in ("rounds_per_step", "ms_per_round", "timed_region_s", "pairs_per_s", "pairs_per_s_e2e", "pairs_per_s_multi_stream", "multi_stream_resident", "step_ms", "pairs_api", "sharded_equals_single_gpu",
               "winner_record", "mean_inliers", "mean_iterations", "host_threads_per_gpu", "models_scored_per_round"):
         if cfg.get(k) is not None:
             out[k] = cfg[k]

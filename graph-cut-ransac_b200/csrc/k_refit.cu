@@ -281,34 +281,115 @@ __device__ __forceinline__ double ba_weight_of(const RefitArgs &a, const uint32_
 	return !a.weights ? 1.0 : a.weight_mode == GCR_WEIGHT_BY_POINT ? a.weights[idx[i]] : a.weights[i];
 }
 
-// sum over the set of w_k * min(r_k^2, 1) for the matrix F (shared memory); every thread gets the result
-__device__ double ba_cost(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, const double *F, double *red, double *tot)
-{
-	double v[1] = {0.0};
-	for (int i = threadIdx.x; i < n; i += (int)blockDim.x)
-	{
-		const double *p = a.pts + (size_t)idx[i] * 4;
-		const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
-		const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
-		const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
-		const double Ft0 = F[0] * x2 + F[3] * y2 + F[6], Ft1 = F[1] * x2 + F[4] * y2 + F[7];
-		const double nJc_sq = (Fx0 * Fx0 + Fx1 * Fx1) + (Ft0 * Ft0 + Ft1 * Ft1);
-		const double r2 = (C * C) / nJc_sq;
-		const double loss = fmin(r2, 1.0);
-		v[0] += a.weights ? ba_weight_of(a, idx, i) * loss : loss;
-	}
-	block_sum<1>(v, red, tot);
-	const double c = tot[0];
-	__syncthreads();
-	return c;
-}
-
 // refines sh->F in place (shared memory); all threads of the CTA call it
 struct BaShared
 {
 	double F[9], U[9], V[9], Un[9], Vn[9], Fn[9], JtJ[49], Jtr[7], sigma, sigman, lambda;
 	int flag; // 0 go on, 1 stop
 };
+
+// One pass over the set for the model (F, U, V): the 28 + 7 sums of J^T J / J^T r AND the cost, 36 values through one
+// block_sum.  The LM loop needs the cost of a candidate to accept or reject it and, if it accepts, the Jacobian sums at
+// that same candidate for the next step: evaluated together, an accepted step costs one pass and one reduction instead
+// of two (a rejected one wastes the Jacobian arithmetic, no barrier).  Every sum is formed by the statements, in the
+// order, of the two separate passes it replaces (a cost pass and a Jacobian pass per round): the same bits.
+__device__ void ba_pass(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, const double *F, const double *U, const double *V,
+                        double *red, double *tot)
+{
+	const int tid = threadIdx.x;
+	double ds[9];
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c)
+			ds[3 * r + c] = U[3 * r + 1] * V[3 * c + 1];
+#define F_(r, c) F[3 * (r) + (c)]
+#define D_(r, c) ds[3 * (r) + (c)]
+	const double dFdp[9][7] = {
+	    {0, F_(2, 0), -F_(1, 0), 0, F_(0, 2), -F_(0, 1), D_(0, 0)},
+	    {-F_(2, 0), 0, F_(0, 0), 0, F_(1, 2), -F_(1, 1), D_(1, 0)},
+	    {F_(1, 0), -F_(0, 0), 0, 0, F_(2, 2), -F_(2, 1), D_(2, 0)},
+	    {0, F_(2, 1), -F_(1, 1), -F_(0, 2), 0, F_(0, 0), D_(0, 1)},
+	    {-F_(2, 1), 0, F_(0, 1), -F_(1, 2), 0, F_(1, 0), D_(1, 1)},
+	    {F_(1, 1), -F_(0, 1), 0, -F_(2, 2), 0, F_(2, 0), D_(2, 1)},
+	    {0, F_(2, 2), -F_(1, 2), F_(0, 1), -F_(0, 0), 0, D_(0, 2)},
+	    {-F_(2, 2), 0, F_(0, 2), F_(1, 1), -F_(1, 0), 0, D_(1, 2)},
+	    {F_(1, 2), -F_(0, 2), 0, F_(2, 1), -F_(2, 0), 0, D_(2, 2)}};
+#undef F_
+#undef D_
+	double acc[36]; // lower triangle of J^T J row by row (28), J^T r (7), the cost
+#pragma unroll
+	for (int j = 0; j < 36; ++j) acc[j] = 0.0;
+	for (int i = tid; i < n; i += (int)blockDim.x)
+	{
+		const double *p = a.pts + (size_t)idx[i] * 4;
+		const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
+		const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+		const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+		const double JC[4] = {F[0] * x2 + F[3] * y2 + F[6], F[1] * x2 + F[4] * y2 + F[7], Fx0, Fx1};
+		{
+			// the cost term of this point: w_k * min(r_k^2, 1), r_k^2 = C^2 / |J_C|^2 (bundle.cpp's TruncatedLoss(1))
+			const double nJc_sq = (Fx0 * Fx0 + Fx1 * Fx1) + (JC[0] * JC[0] + JC[1] * JC[1]);
+			const double r2 = (C * C) / nJc_sq;
+			const double loss = fmin(r2, 1.0);
+			acc[35] += a.weights ? ba_weight_of(a, idx, i) * loss : loss;
+		}
+		const double nJ_C = sqrt(JC[0] * JC[0] + JC[1] * JC[1] + JC[2] * JC[2] + JC[3] * JC[3]);
+		const double inv_nJ_C = 1.0 / nJ_C;
+		const double r = C * inv_nJ_C;
+		double weight = ((r * r) < 1.0 ? 1.0 : 0.0) / n;
+		if (a.weights)
+			weight = ba_weight_of(a, idx, i) * weight;
+		if (weight == 0.0)
+			continue;
+		double dF[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0};
+		const double s = C * inv_nJ_C * inv_nJ_C;
+		dF[0] -= s * (JC[2] * x1 + JC[0] * x2);
+		dF[1] -= s * (JC[3] * x1 + JC[0] * y2);
+		dF[2] -= s * (JC[0]);
+		dF[3] -= s * (JC[2] * y1 + JC[1] * x2);
+		dF[4] -= s * (JC[3] * y1 + JC[1] * y2);
+		dF[5] -= s * (JC[1]);
+		dF[6] -= s * (JC[2]);
+		dF[7] -= s * (JC[3]);
+#pragma unroll
+		for (int q = 0; q < 9; ++q) dF[q] *= inv_nJ_C;
+		double J[7];
+#pragma unroll
+		for (int j = 0; j < 7; ++j)
+		{
+			double t = 0.0;
+#pragma unroll
+			for (int q = 0; q < 9; ++q) t += dF[q] * dFdp[q][j];
+			J[j] = t;
+		}
+		int q = 0;
+#pragma unroll
+		for (int r7 = 0; r7 < 7; ++r7)
+#pragma unroll
+			for (int c7 = 0; c7 <= r7; ++c7)
+				acc[q++] += weight * (J[r7] * J[c7]);
+#pragma unroll
+		for (int r7 = 0; r7 < 7; ++r7)
+			acc[28 + r7] += weight * C * inv_nJ_C * J[r7];
+	}
+	block_sum<36>(acc, red, tot);
+}
+
+// thread 0: the sums of a pass become the normal equations; gradient_tol (bundle.cpp: |J^T r| < 1e-8) sets the stop flag
+__device__ void ba_take_sums(BaShared *sh, const double *tot)
+{
+	int q = 0;
+	for (int r7 = 0; r7 < 7; ++r7)
+		for (int c7 = 0; c7 <= r7; ++c7)
+			sh->JtJ[7 * r7 + c7] = tot[q++];
+	double g = 0.0;
+	for (int r7 = 0; r7 < 7; ++r7)
+	{
+		sh->Jtr[r7] = tot[28 + r7];
+		g += tot[28 + r7] * tot[28 + r7];
+	}
+	if (sqrt(g) < 1e-8) // gradient_tol
+		sh->flag = 1;
+}
 
 __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, const BaFrame &fr, BaShared *sh, double *red, double *tot,
                             int max_iterations)
@@ -318,112 +399,21 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 	{
 		double s[3];
 		jacobi_svd3(sh->F, sh->U, s, sh->V); // FactorizedFundamentalMatrix(F) (jacobian_impl.h:474-480)
-#ifdef GCR_BA_DEBUG
-		if (blockIdx.x == 0) printf("svd s %g %g %g U %g %g V %g %g\n", s[0], s[1], s[2], sh->U[0], sh->U[1], sh->V[0], sh->V[1]);
-#endif
 		sh->sigma = s[1] / s[0];
 		factorized_f(sh->U, sh->V, sh->sigma, sh->F);
 		sh->lambda = 1e-3;
 		sh->flag = 0;
 	}
 	__syncthreads();
-	double cost = ba_cost(a, idx, n, fr, sh->F, red, tot);
-#ifdef GCR_BA_DEBUG
-	if (tid == 0 && blockIdx.x == 0) printf("BA init: n %d sigma %g cost %g F %g %g %g\n", n, sh->sigma, cost, sh->F[0], sh->F[4], sh->F[8]);
-#endif
-	bool recompute_jac = true;
+	ba_pass(a, idx, n, fr, sh->F, sh->U, sh->V, red, tot);
+	double cost = tot[35];
+	if (tid == 0)
+		ba_take_sums(sh, tot);
+	__syncthreads();
+	if (sh->flag)
+		return;
 	for (int iter = 0; iter < max_iterations; ++iter)
 	{
-		if (recompute_jac)
-		{
-			const double *F = sh->F;
-			double ds[9];
-			for (int r = 0; r < 3; ++r)
-				for (int c = 0; c < 3; ++c)
-					ds[3 * r + c] = sh->U[3 * r + 1] * sh->V[3 * c + 1];
-#define F_(r, c) F[3 * (r) + (c)]
-#define D_(r, c) ds[3 * (r) + (c)]
-			const double dFdp[9][7] = {
-			    {0, F_(2, 0), -F_(1, 0), 0, F_(0, 2), -F_(0, 1), D_(0, 0)},
-			    {-F_(2, 0), 0, F_(0, 0), 0, F_(1, 2), -F_(1, 1), D_(1, 0)},
-			    {F_(1, 0), -F_(0, 0), 0, 0, F_(2, 2), -F_(2, 1), D_(2, 0)},
-			    {0, F_(2, 1), -F_(1, 1), -F_(0, 2), 0, F_(0, 0), D_(0, 1)},
-			    {-F_(2, 1), 0, F_(0, 1), -F_(1, 2), 0, F_(1, 0), D_(1, 1)},
-			    {F_(1, 1), -F_(0, 1), 0, -F_(2, 2), 0, F_(2, 0), D_(2, 1)},
-			    {0, F_(2, 2), -F_(1, 2), F_(0, 1), -F_(0, 0), 0, D_(0, 2)},
-			    {-F_(2, 2), 0, F_(0, 2), F_(1, 1), -F_(1, 0), 0, D_(1, 2)},
-			    {F_(1, 2), -F_(0, 2), 0, F_(2, 1), -F_(2, 0), 0, D_(2, 2)}};
-#undef F_
-#undef D_
-			double acc[35]; // lower triangle of J^T J row by row (28), then J^T r (7)
-#pragma unroll
-			for (int j = 0; j < 35; ++j) acc[j] = 0.0;
-			for (int i = tid; i < n; i += (int)blockDim.x)
-			{
-				const double *p = a.pts + (size_t)idx[i] * 4;
-				const double x1 = (p[0] - fr.msx) * fr.rs, y1 = (p[1] - fr.msy) * fr.rs, x2 = (p[2] - fr.mdx) * fr.rd, y2 = (p[3] - fr.mdy) * fr.rd;
-				const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
-				const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
-				const double JC[4] = {F[0] * x2 + F[3] * y2 + F[6], F[1] * x2 + F[4] * y2 + F[7], Fx0, Fx1};
-				const double nJ_C = sqrt(JC[0] * JC[0] + JC[1] * JC[1] + JC[2] * JC[2] + JC[3] * JC[3]);
-				const double inv_nJ_C = 1.0 / nJ_C;
-				const double r = C * inv_nJ_C;
-				double weight = ((r * r) < 1.0 ? 1.0 : 0.0) / n;
-				if (a.weights)
-					weight = ba_weight_of(a, idx, i) * weight;
-				if (weight == 0.0)
-					continue;
-				double dF[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0};
-				const double s = C * inv_nJ_C * inv_nJ_C;
-				dF[0] -= s * (JC[2] * x1 + JC[0] * x2);
-				dF[1] -= s * (JC[3] * x1 + JC[0] * y2);
-				dF[2] -= s * (JC[0]);
-				dF[3] -= s * (JC[2] * y1 + JC[1] * x2);
-				dF[4] -= s * (JC[3] * y1 + JC[1] * y2);
-				dF[5] -= s * (JC[1]);
-				dF[6] -= s * (JC[2]);
-				dF[7] -= s * (JC[3]);
-#pragma unroll
-				for (int q = 0; q < 9; ++q) dF[q] *= inv_nJ_C;
-				double J[7];
-#pragma unroll
-				for (int j = 0; j < 7; ++j)
-				{
-					double t = 0.0;
-#pragma unroll
-					for (int q = 0; q < 9; ++q) t += dF[q] * dFdp[q][j];
-					J[j] = t;
-				}
-				int q = 0;
-#pragma unroll
-				for (int r7 = 0; r7 < 7; ++r7)
-#pragma unroll
-					for (int c7 = 0; c7 <= r7; ++c7)
-						acc[q++] += weight * (J[r7] * J[c7]);
-#pragma unroll
-				for (int r7 = 0; r7 < 7; ++r7)
-					acc[28 + r7] += weight * C * inv_nJ_C * J[r7];
-			}
-			block_sum<35>(acc, red, tot);
-			if (tid == 0)
-			{
-				int q = 0;
-				for (int r7 = 0; r7 < 7; ++r7)
-					for (int c7 = 0; c7 <= r7; ++c7)
-						sh->JtJ[7 * r7 + c7] = tot[q++];
-				double g = 0.0;
-				for (int r7 = 0; r7 < 7; ++r7)
-				{
-					sh->Jtr[r7] = tot[28 + r7];
-					g += tot[28 + r7] * tot[28 + r7];
-				}
-				if (sqrt(g) < 1e-8) // gradient_tol
-					sh->flag = 1;
-			}
-			__syncthreads();
-			if (sh->flag)
-				break;
-		}
 		if (tid == 0)
 		{
 			for (int k = 0; k < 7; ++k) sh->JtJ[7 * k + k] += sh->lambda;
@@ -473,11 +463,10 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 		__syncthreads();
 		if (sh->flag)
 			break;
-		const double cost_new = ba_cost(a, idx, n, fr, sh->Fn, red, tot);
+		// the candidate's cost and, should it be accepted, its normal equations: one pass
+		ba_pass(a, idx, n, fr, sh->Fn, sh->Un, sh->Vn, red, tot);
+		const double cost_new = tot[35];
 		const bool accept = cost_new < cost; // the same value in every thread
-#ifdef GCR_BA_DEBUG
-		if (tid == 0 && blockIdx.x == 0) printf("BA it %d: cost %g new %g lambda %g Jtr0 %g JtJ00 %g sigman %g\n", iter, cost, cost_new, sh->lambda, sh->Jtr[0], sh->JtJ[0], sh->sigman);
-#endif
 		if (tid == 0)
 		{
 			if (accept)
@@ -485,6 +474,7 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 				for (int i = 0; i < 9; ++i) { sh->U[i] = sh->Un[i]; sh->V[i] = sh->Vn[i]; sh->F[i] = sh->Fn[i]; }
 				sh->sigma = sh->sigman;
 				sh->lambda /= 10;
+				ba_take_sums(sh, tot); // (the gradient test the next round would start with)
 			}
 			else
 			{
@@ -494,8 +484,9 @@ __device__ void ba_refine_f(const RefitArgs &a, const uint32_t *idx, int n, cons
 		}
 		if (accept)
 			cost = cost_new;
-		recompute_jac = accept;
 		__syncthreads();
+		if (sh->flag)
+			break;
 	}
 	__syncthreads();
 }

@@ -25,6 +25,11 @@ import ctypes as C
 import os
 import threading
 
+# One context (= stream) per host thread (`_context`): give every stream a hardware work queue of its own.  With CUDA's
+# default of 8 connections the streams of sixteen threads share queues and one pair's latency-bound kernels hold up another
+# pair's launches.  Only effective if CUDA has not been initialised in this process yet; a value set by the user stays.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 from . import _cabi
