@@ -38,6 +38,11 @@
 
 #define RF_THREADS 128
 #define RF_WARPS (RF_THREADS / 32)
+// A call with MANY sets is the inner RANSAC of the local optimisation: `lo_number` samples of at most 7 m points each
+// (GCRANSAC.h:842-866).  One warp per set: the serial parts of a fit (decompositions, LM steps) keep one thread busy either
+// way, and a 128-thread CTA idling around it holds four times the registers -- with sixteen pairs in flight the 50-set
+// launches queued for SM slots.  A call with ONE set (all inliers: IRLS, the final fit) keeps the wide shapes.
+#define RF_SMALL_THREADS 32
 #define RF_MAX_THREADS 512 /* the single-set launches of the bundle adjustment (all inliers of a run) use 512 threads */
 #define RF_MAX_WARPS (RF_MAX_THREADS / 32)
 
@@ -865,7 +870,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a_in)
 	uint8_t *ok = a.ok + oslot * RF_E_MODELS;
 	if (n < 5) // nonMinimalSampleSize() (essential_estimator.h:315-316)
 	{
-		for (int j = tid; j < RF_E_MODELS * 9; j += RF_THREADS) models[j] = 0.0;
+		for (int j = tid; j < RF_E_MODELS * 9; j += (int)blockDim.x) models[j] = 0.0;
 		if (tid < RF_E_MODELS) ok[tid] = 0;
 		return;
 	}
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a_in)
 		double acc[45];
 #pragma unroll
 		for (int j = 0; j < 45; ++j) acc[j] = 0.0;
-		for (int i = tid; i < n; i += RF_THREADS)
+		for (int i = tid; i < n; i += (int)blockDim.x)
 		{
 			const double *p = a.pts + (size_t)idx[i] * 4;
 			const double w = !a.weights ? 1.0 : a.weight_mode == GCR_WEIGHT_BY_POINT ? a.weights[idx[i]] : a.weights[i];
@@ -1013,16 +1018,17 @@ static gcr_status refit_launch(gcr_ctx *ctx, int problem, int pair, const uint32
 	a.pair_of_set = nullptr;
 	a.weight_offsets = nullptr;
 	a.out_slots = nullptr;
+	const int threads = count == 1 ? RF_THREADS : RF_SMALL_THREADS, ba_threads = count == 1 ? RF_MAX_THREADS : RF_SMALL_THREADS;
 	if (problem == GCR_H)
-		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_H><<<count, threads, 0, ctx->stream>>>(a);
 	else if (problem == GCR_E)
-		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit_e<<<count, threads, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_HARTLEY)
-		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, count == 1 ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, ba_threads, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_PIXEL)
-		k_refit<GCR_F, GCR_BA_PIXEL><<<count, count == 1 ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_PIXEL><<<count, ba_threads, 0, ctx->stream>>>(a);
 	else
-		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F><<<count, threads, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }
@@ -1066,7 +1072,8 @@ extern "C" gcr_status gcr_refit_pairs(gcr_ctx *ctx, int problem, const uint32_t 
 // d_pair_of_set[s], indices d_index_sets + d_set_offsets[s] (d_set_sizes[s] of them), weights (when d_weights is given) at
 // d_weights + d_weight_offsets[s] read in `weight_mode`, models written to slot d_out_slots[s] of d_models / d_ok (slot x
 // R models each; d_out_slots == NULL: slot s).  ba_frame as gcr_refit_f_ba (F only; 0 = the linear fit); wide != 0: the
-// sets are whole inlier sets (one per request), fitted with the CTA shape of a single-set gcr_refit_f_ba call.
+// sets are whole inlier sets (one per request), fitted with the CTA shape of a single-set gcr_refit / gcr_refit_f_ba call;
+// wide == 0: the sets are the samples of local-optimisation rounds, one warp each like a many-set call.
 extern "C" gcr_status gcr_refit_multi(gcr_ctx *ctx, int problem, int ba_frame, const int32_t *d_pair_of_set, const uint32_t *d_index_sets,
                                       const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count, const double *d_weights,
                                       const uint32_t *d_weight_offsets, int weight_mode, const uint32_t *d_out_slots, int wide,
@@ -1100,18 +1107,20 @@ extern "C" gcr_status gcr_refit_multi(gcr_ctx *ctx, int problem, int ba_frame, c
 	a.pair_of_set = d_pair_of_set;
 	a.weight_offsets = d_weight_offsets;
 	a.out_slots = d_out_slots;
+	// `wide`: the CTA shapes gcr_refit / gcr_refit_f_ba give a call with ONE set (all inliers of a run) -- the block sums
+	// associate by CTA shape, so a batched single-set fit uses the shape the unbatched call would; else the one-warp shape
+	// of a many-set call
+	const int threads = wide ? RF_THREADS : RF_SMALL_THREADS, ba_threads = wide ? RF_MAX_THREADS : RF_SMALL_THREADS;
 	if (problem == GCR_H)
-		k_refit<GCR_H><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_H><<<count, threads, 0, ctx->stream>>>(a);
 	else if (problem == GCR_E)
-		k_refit_e<<<count, RF_THREADS, 0, ctx->stream>>>(a);
-	// `wide`: the CTA shape gcr_refit_f_ba gives a call with ONE set (all inliers of a run) -- the block sums associate by
-	// CTA shape, so a batched single-set fit uses the shape the unbatched call would
+		k_refit_e<<<count, threads, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_HARTLEY)
-		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, wide ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_HARTLEY><<<count, ba_threads, 0, ctx->stream>>>(a);
 	else if (ba_frame == GCR_BA_PIXEL)
-		k_refit<GCR_F, GCR_BA_PIXEL><<<count, wide ? RF_MAX_THREADS : RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F, GCR_BA_PIXEL><<<count, ba_threads, 0, ctx->stream>>>(a);
 	else
-		k_refit<GCR_F><<<count, RF_THREADS, 0, ctx->stream>>>(a);
+		k_refit<GCR_F><<<count, threads, 0, ctx->stream>>>(a);
 	GCR_LAUNCHED(ctx);
 	return GCR_OK;
 }

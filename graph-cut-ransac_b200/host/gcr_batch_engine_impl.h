@@ -503,7 +503,7 @@ namespace
 				grouped(reqs,
 				        [](Request *r) {
 					        return std::make_tuple(r->rp, r->ba_frame, r->weights ? r->weight_mode : (int)GCR_WEIGHT_NONE, r->weights != nullptr,
-					                               r->ba_frame != 0 && r->sizes->size() == 1);
+					                               r->sizes->size() == 1);
 				        },
 				        [&](std::vector<Request *> &g, Issued &rec) { return do_refit(g, *rec.slot); });
 				break;
@@ -890,7 +890,7 @@ namespace
 			const Request &r0 = *g[0];
 			const int rm = gcr_max_refit_models(r0.rp), rml = gcr_model_len(r0.rp);
 			const bool has_w = r0.weights != nullptr;
-			const int wide = r0.ba_frame != 0 && r0.sizes->size() == 1;
+			const int wide = r0.sizes->size() == 1; // the CTA shape of a one-set call of the unbatched driver
 			size_t n_sets = 0, n_idx = 0, n_w = 0;
 			for (Request *r : g)
 			{
@@ -1008,8 +1008,9 @@ namespace
 				p_at += s.pool_size;
 				d_at += (size_t)trials * s.sample_size;
 			}
-			// a fit of ONE set per call takes gcr_refit_f_ba's wide CTA shape in the unbatched driver (the block sums associate by shape)
-			const int wide = s0.ba_frame != 0 && trials == 1;
+			// a fit of ONE set per call takes the wide CTA shape in the unbatched driver, many sets one warp each (the block sums
+			// associate by shape)
+			const int wide = trials == 1;
 			bool ok = in.upload(ctx, 0, in.used) && gcr_memset(ctx, lo_ok.p, 0, (size_t)S * row_ok) == GCR_OK;
 			if (ok && pool)
 				ok = gcr_sample_from_pools(ctx, in.dev<uint32_t>(o_pools), in.dev<gcr_pool_request>(o_reqs), (int)nreq, trials, sl.d_d.as<uint32_t>()) == GCR_OK;

@@ -210,7 +210,9 @@ uint32_t gcr_key_index(uint64_t key);
  * `count` index sets of pair `pair`; set j has set_sizes[j] indices at d_index_sets + set_offsets[j].
  * d_weights: per-point weights or NULL; weight_mode: GCR_WEIGHT_POSITIONAL reproduces the reference's positional
  * read, GCR_WEIGHT_BY_POINT reads weights[index].
- * d_models [count][R][9], d_ok [count][R] with R = gcr_max_refit_models(problem): 1 (H, F), 10 (E). */
+ * d_models [count][R][9], d_ok [count][R] with R = gcr_max_refit_models(problem): 1 (H, F), 10 (E).
+ * One CTA per set: 128 threads for a call with one set (all inliers of a run), one warp per set for a call with many (the
+ * samples of a local-optimisation round, <= 7 m points each; larger sets are fitted correctly, just by 32 threads). */
 gcr_status gcr_refit(gcr_ctx *ctx, int problem, int pair, const uint32_t *d_index_sets, const uint32_t *d_set_offsets,
                      const uint32_t *d_set_sizes, int count, const double *d_weights, int weight_mode,
                      double *d_models, uint8_t *d_ok);
@@ -311,7 +313,9 @@ typedef struct gcr_pool_request
 gcr_status gcr_sample_from_pools(gcr_ctx *ctx, const uint32_t *d_pools, const gcr_pool_request *d_requests, int n_requests,
                                  int trials, uint32_t *d_out);
 /* gcr_refit / gcr_refit_f_ba for `count` index sets of different pairs: set s belongs to pair d_pair_of_set[s], reads its
- * weights (if any) from d_weights + d_weight_offsets[s] and writes its models to slot d_out_slots[s] (NULL: slot s) */
+ * weights (if any) from d_weights + d_weight_offsets[s] and writes its models to slot d_out_slots[s] (NULL: slot s).
+ * wide != 0: every set is a whole inlier set fitted with the CTA shape of a one-set gcr_refit call; 0: one warp per set,
+ * the shape of a many-set call (the block sums associate by CTA shape: a batched fit equals the unbatched one bit for bit) */
 gcr_status gcr_refit_multi(gcr_ctx *ctx, int problem, int ba_frame, const int32_t *d_pair_of_set, const uint32_t *d_index_sets,
                            const uint32_t *d_set_offsets, const uint32_t *d_set_sizes, int count, const double *d_weights,
                            const uint32_t *d_weight_offsets, int weight_mode, const uint32_t *d_out_slots, int wide,
