@@ -763,7 +763,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
         if ms_two and n_pairs > 1:
             line["config"]["pairs_per_s_multi_stream"] = world * n_pairs / (ms_two[0] * 1e-3)
         if ms_two:
-            line["config"]["multi_stream_resident"] = {"streams": len(lanes) if two_lanes else E2E_SIDE, "ms_per_round": ms_two[0], "evals_per_s": ms_two[1],
+            line["config"]["multi_stream_resident"] = {"streams": len(lanes) if two_lanes else E2E_SIDE, "ms_per_round": ms_two[0],
+                                                      "evals_per_s": ms_two[1] * world,  # (rank 0's rate x ranks: every rank runs the same pass)
                                                       "note": "the resident pass with consecutive rounds alternating between the streams (K2 of "
                                                               "round i + 1 beside K3 of round i), as the e2e leg runs; `value` and the roofline "
                                                               "are the one-stream pass, where K3's launch time is undisturbed"}
