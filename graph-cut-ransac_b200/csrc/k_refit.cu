@@ -43,6 +43,17 @@
 // way, and a 128-thread CTA idling around it holds four times the registers -- with sixteen pairs in flight the 50-set
 // launches queued for SM slots.  A call with ONE set (all inliers: IRLS, the final fit) keeps the wide shapes.
 #define RF_SMALL_THREADS 32
+#ifndef GCR_SVD3_MAX_SWEEPS
+#define GCR_SVD3_MAX_SWEEPS 100
+#endif
+// Two columns count as orthogonal when |a_p . a_q| <= 4 eps |a_p| |a_q| (Eigen's JacobiSVD stops at 2 eps of the largest
+// diagonal entry).  The 1e-17 of round 1 lies BELOW the rounding noise of the dot product itself, so the sweep loop never
+// saw a sweep without a rotation and always ran its 100 sweeps of noise-level rotations: 107 of the 195 us of a
+// bundle-adjustment fit (tools/refit_bench.py).  oracle/linalg.h carries the same tolerance.
+#define GCR_SVD3_TOL 8.881784197001252e-16
+#ifndef GCR_BA_MAX_IT
+#define GCR_BA_MAX_IT 25 /* max_iterations of lm_F_impl (relative_pose/bundle.cpp:253-339); overridable for timing experiments */
+#endif
 #define RF_MAX_THREADS 512 /* the single-set launches of the bundle adjustment (all inliers of a run) use 512 threads */
 #define RF_MAX_WARPS (RF_MAX_THREADS / 32)
 
@@ -207,7 +218,7 @@ __device__ void jacobi_svd3(const double *A_in, double *U, double *s, double *V)
 	// one-sided Jacobi, columns of A rotated until orthogonal: A = U diag(s) V^T, s descending (oracle/linalg.h jacobi_svd)
 	double A[9], Vt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	for (int i = 0; i < 9; ++i) A[i] = A_in[i];
-	for (int sweep = 0; sweep < 100; ++sweep)
+	for (int sweep = 0; sweep < GCR_SVD3_MAX_SWEEPS; ++sweep)
 	{
 		bool rotated = false;
 		for (int p = 0; p < 2; ++p)
@@ -219,7 +230,7 @@ __device__ void jacobi_svd3(const double *A_in, double *U, double *s, double *V)
 					const double ap = A[3 * i + p], aq = A[3 * i + q];
 					alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
 				}
-				if (fabs(gamma) <= 1e-17 * sqrt(alpha * beta) || gamma == 0.0)
+				if (fabs(gamma) <= GCR_SVD3_TOL * sqrt(alpha * beta) || gamma == 0.0)
 					continue;
 				rotated = true;
 				const double zeta = (beta - alpha) / (2.0 * gamma);
@@ -648,7 +659,7 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 		}
 		__syncthreads();
 		const BaFrame fr = {msx, msy, mdx, mdy, rs, rd};
-		ba_refine_f(a, idx, n, fr, &ba, red, tot, 25);
+		ba_refine_f(a, idx, n, fr, &ba, red, tot, GCR_BA_MAX_IT);
 		if (tid != 0)
 			return;
 		double out[9];

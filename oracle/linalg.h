@@ -404,7 +404,8 @@ namespace gcro
 						const double ap = A[(size_t)i * n + p], aq = A[(size_t)i * n + q];
 						alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
 					}
-					if (std::fabs(gamma) <= 1e-17 * std::sqrt(alpha * beta) || gamma == 0.0)
+					// orthogonal to 4 eps (below that the dot product is its own rounding noise and the sweeps never end)
+					if (std::fabs(gamma) <= 8.881784197001252e-16 * std::sqrt(alpha * beta) || gamma == 0.0)
 						continue;
 					rotated = true;
 					const double zeta = (beta - alpha) / (2.0 * gamma);
