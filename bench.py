@@ -36,9 +36,6 @@ sys.path.insert(0, os.path.join(ROOT, "graph-cut-ransac_b200"))
 # connections sixteen streams share queues, so a latency-bound kernel of one pair holds up another pair's launches
 # (f4k_pairs 2.2 k -> 2.8 k pairs/s, e2k_pairs 330 -> 370).  Must be in the environment before CUDA initialises.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# every kernel of the library loaded when CUDA starts, not on its first launch: a rarely used variant (a second, larger batch;
-# DEGENSAC's inner run) otherwise loads in the middle of a multi-threaded pipeline and every stream waits for it
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 # H-MSAC 21, Sampson-MSAC 35, Sampson-MAGSAC++ 43 flop per evaluation (counted from the reference lines)
 FLOP_PER_EVAL = {("h", "msac"): 21.0, ("f", "msac"): 35.0, ("e", "msac"): 35.0, ("e", "magsac"): 43.0,

@@ -29,9 +29,6 @@ import threading
 # default of 8 connections the streams of sixteen threads share queues and one pair's latency-bound kernels hold up another
 # pair's launches.  Only effective if CUDA has not been initialised in this process yet; a value set by the user stays.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# every kernel of the library loaded when CUDA starts, not on its first launch: a rarely used variant (a second, larger batch;
-# DEGENSAC's inner run) otherwise loads in the middle of a multi-threaded pipeline and every stream waits for it
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import numpy as np
 
