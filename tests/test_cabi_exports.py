@@ -52,8 +52,10 @@ def test_driver_library_exports_every_declared_symbol():
     _cabi.load_library()
     lib = C.CDLL(path)
     header = open(os.path.join(ROOT, "graph-cut-ransac_b200", "host", "gcr_driver.h")).read()
+    header += open(os.path.join(ROOT, "graph-cut-ransac_b200", "host", "gcr_batch_engine.h")).read()   # the multi-pair calls
     declared = set(re.findall(r"\b(gcr_[a-z0-9_]+)\s*\(", header)) - {"gcr_ctx"}
-    assert {"gcr_find_model", "gcr_find_essential", "gcr_run_settings_default"} <= declared
+    assert {"gcr_find_model", "gcr_find_essential", "gcr_run_settings_default", "gcr_find_model_batch", "gcr_find_essential_batch",
+            "gcr_batch_engines_release", "gcr_driver_last_error"} <= declared
     for name in declared:
         assert hasattr(lib, name), name
     s = pygcransac.RunSettings()
