@@ -855,6 +855,11 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
     launches0 = launch_total()
     clocks = ClockSampler(local_rank).start()
     sess.barrier()
+    # no cyclic garbage collection inside the timed passes: a full collection holds the GIL for ~100 ms once the process has
+    # run a few workloads, and sixteen threads that each need the GIL between two 0.3 ms calls all stand still for it
+    import gc
+    gc.collect()
+    gc.disable()
     t0 = time.perf_counter()
     inl = its = 0
     step_ms = []
@@ -865,6 +870,7 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
         inl, its = inl + a, its + b
     sess.barrier()
     wall = time.perf_counter() - t0
+    gc.enable()
     clock_info = clocks.stop()
     launches = launch_total() - launches0
     pool.shutdown()
