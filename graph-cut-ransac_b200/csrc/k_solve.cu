@@ -14,8 +14,6 @@
 // per-thread local arrays; no attempt is made to put them on tensor cores.
 #include "gcr_internal.cuh"
 
-#include <algorithm>
-
 #include <math.h>
 
 #include "solve_f7.cuh"
@@ -296,51 +294,46 @@ struct GroupSync
 	__device__ __forceinline__ unsigned ballot(bool x) const { return (__ballot_sync(mask, x) >> shift) & 0x3ffu; }
 };
 
-// Persistent warps: the grid is at most one resident wave (E5_MIN_BLOCKS CTAs per SM) and every warp walks the sample
-// triples t = first, first + stride, ...  A sample's cost varies with its root count and bisection depth; a CTA that
-// lives for ONE triple per warp holds its 45 KB of shared memory until its slowest warp is done (7.5 % of the warp samples
-// of the one-shot kernel sat at that final barrier), a warp that takes the next triple instead does not wait for anybody.
 __global__ void __launch_bounds__(E5_THREADS, E5_MIN_BLOCKS) k_solve_e5(const double *__restrict__ pts, int n,
                                                          const GcrSampleSource src, int count,
                                                          double *__restrict__ models, uint8_t *__restrict__ valid,
                                                          unsigned long long *__restrict__ counters)
 {
 	extern __shared__ double e5_smem[];
+	__shared__ uint32_t cnt;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int g = lane / 10, li = lane - 10 * g;
 	const int pair = blockIdx.y;
 	if (src.active && !src.active[pair])
 		return; // a pair the batch engine has no request for (valid flags zeroed by the launcher)
-	const int slot = warp * 3 + g; // this group's block of shared memory, reused triple after triple
-	double *S = e5_smem + (size_t)slot * gcr_e5g::SAMPLE_DOUBLES;
-	const int n_triples = (count + 2) / 3, warps = E5_THREADS / 32;
-	uint32_t n_ok_total = 0;
-	for (int t = blockIdx.x * warps + warp; t < n_triples; t += gridDim.x * warps)
+	const int slot = warp * 3 + g;
+	const int i = blockIdx.x * E5_SAMPLES_PER_CTA + slot;
+	if (threadIdx.x == 0)
+		cnt = 0;
+	__syncthreads();
+	const unsigned warp_mask = __ballot_sync(0xffffffffu, g < 3 && i < count);
+	if (g < 3 && i < count)
 	{
-		const int i = 3 * t + g;
-		const bool active = g < 3 && i < count;
-		const unsigned warp_mask = __ballot_sync(0xffffffffu, active);
-		if (active)
+		double *S = e5_smem + (size_t)slot * gcr_e5g::SAMPLE_DOUBLES;
+		const GroupSync sync{0x3ffu << (10 * g), warp_mask, 10 * g};
+		uint32_t sidx[5];
+		gcr_load_sample<5>(src, pair, count, i, sidx); // every lane draws the same five indices
+		if (li < 5)
 		{
-			const GroupSync sync{0x3ffu << (10 * g), warp_mask, 10 * g};
-			uint32_t sidx[5];
-			gcr_load_sample<5>(src, pair, count, i, sidx); // every lane draws the same five indices
-			if (li < 5)
-			{
-				const double *p = pts + ((size_t)pair * n + sidx[li]) * 4;
-				double *d = S + gcr_e5g::OFF_PT + 4 * li;
-				d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
-			}
-			sync();
-			double *out = models + ((size_t)pair * count + i) * 90;
-			uint8_t *v = valid + ((size_t)pair * count + i) * 10;
-			const int n_ok = gcr_e5g::solve_group(li, S, sync, out, v);
-			if (li == 0)
-				n_ok_total += (uint32_t)n_ok;
+			const double *p = pts + ((size_t)pair * n + sidx[li]) * 4;
+			double *d = S + gcr_e5g::OFF_PT + 4 * li;
+			d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
 		}
-		__syncwarp(); // the groups of this warp start their next triple together (one ballot, lockstep bisection)
+		sync();
+		double *out = models + ((size_t)pair * count + i) * 90;
+		uint8_t *v = valid + ((size_t)pair * count + i) * 10;
+		const int n_ok = gcr_e5g::solve_group(li, S, sync, out, v);
+		if (li == 0 && n_ok)
+			atomicAdd(&cnt, (uint32_t)n_ok);
 	}
-	count_valid(counters, n_ok_total);
+	__syncthreads();
+	if (threadIdx.x == 0 && cnt)
+		atomicAdd(&counters[0], (unsigned long long)cnt);
 }
 
 // --------------------------------------------------------------------------------------------------- P3P ----
@@ -497,8 +490,7 @@ static gcr_status solve_launch(gcr_ctx *ctx, int problem, const GcrSampleSource 
 		GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_e5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E5_SMEM));
 		if (ctx->tune_carveout >= 0)
 			GCR_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_solve_e5, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->tune_carveout));
-		k_solve_e5<<<dim3(std::min((count + E5_SAMPLES_PER_CTA - 1) / E5_SAMPLES_PER_CTA, std::max(1, ctx->sm_count * E5_MIN_BLOCKS / std::min(ctx->n_pairs, ctx->sm_count * E5_MIN_BLOCKS))),
-		                  ctx->n_pairs), E5_THREADS, E5_SMEM, ctx->stream>>>(
+		k_solve_e5<<<dim3((count + E5_SAMPLES_PER_CTA - 1) / E5_SAMPLES_PER_CTA, ctx->n_pairs), E5_THREADS, E5_SMEM, ctx->stream>>>(
 		    ctx->d_pts64, ctx->n, src, count, d_models, d_valid, ctx->d_counters);
 		break;
 	case GCR_PNP:
