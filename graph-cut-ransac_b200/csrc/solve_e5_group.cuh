@@ -572,9 +572,7 @@ namespace gcr_e5g
 				const Pts pt{PT};
 				ok = gcr_f7::orientation_valid(E, pt, 5);
 			}
-			if (!ok)
-				for (int j = 0; j < 9; ++j)
-					E[j] = 0.0;
+			// (a slot that fails keeps the candidate written above: slots with flag 0 are never read)
 			valid_out[li] = ok ? 1 : 0;
 			okf[li] = ok ? 1 : 0;
 		}
