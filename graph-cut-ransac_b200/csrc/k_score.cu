@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_score_prepare(const ScoreArgs a)
 	const size_t g = (size_t)pair * a.k + slot;
 	const bool in_range = slot < a.k;
 	const bool ok = in_range && (a.valid == nullptr || a.valid[g] != 0);
-	if (in_range)
+	if (ok) // (only the slots that will be scored: finalize does not read the accumulators of the others)
 	{
 		a.accS[g] = 0ull;
 		a.accC[g] = 0u;
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(256) k_score_finalize(const ScoreArgs a)
 	{
 		const size_t g = (size_t)pair * a.k + slot;
 		const bool present = a.valid == nullptr || a.valid[g] != 0;
-		const uint32_t c = a.accC[g];
+		const uint32_t c = present ? a.accC[g] : 0u;
 		float score;
 		if (!present)
 			score = -1.f;
