@@ -1001,6 +1001,11 @@ def main():
             sess.barrier()
         if rank == 0:
             line["extra"] = extra
+            # the other half of BASELINE's metric, gathered where a reader of the headline line looks first
+            line["config"]["pairs_per_s"] = {k: (v.get("pairs_per_s") if v["unit"] == "evals/s" else v["value"])
+                                             for k, v in extra.items() if v.get("pairs_per_s") or v["unit"] == "pairs/s"}
+            line["config"]["pairs_per_s_e2e"] = {k: (v.get("pairs_per_s_e2e") if v["unit"] == "evals/s" else v["e2e"])
+                                                 for k, v in extra.items() if v.get("pairs_per_s_e2e") or v["unit"] == "pairs/s"}
     for kind, target, jwl, scale, gpu_value in cpu_jobs:
         if kind == "rounds":
             target["cpu_baseline"] = cpu_baseline_rounds(jwl, make_points(dict(jwl, pairs=1), 0)[0].copy(), scale)
