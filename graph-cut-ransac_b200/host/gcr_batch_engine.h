@@ -12,9 +12,10 @@
 // the host-only work between two requests -- the reference's Boykov-Kolmogorov min-cut above all -- is fanned out over the
 // cores without more runnable threads than cores and without a kernel wake-up per request.
 //
-// Results per pair equal gcr_find_model's with the pair's seed (tests/test_gpu_batch.py).  Measured: the
-// homography pipelines are bound by the host cores either way (the min-cut and its graph construction are ~3 ms of one core
-// per pair), so the batch call matches the one-pair-per-thread path there rather than beating it.
+// Results per pair equal gcr_find_model's with the pair's seed (tests/test_gpu_batch.py).  Measured: ahead
+// of the one-pair-per-thread path where pairs are small and driver calls were the cost (configs[0]: 5.9 k against 4.6 k
+// pairs/s), level on F, behind where the host cores (the min-cut, ~3 ms of one core per H pair) or one pair's own GPU
+// kernels (E) are the bound.
 #ifndef GCR_BATCH_ENGINE_H_INCLUDED
 #define GCR_BATCH_ENGINE_H_INCLUDED
 

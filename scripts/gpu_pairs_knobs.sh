@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { # workload pairs seats engines
-  timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --workload $1 --pairs-api batch --pairs $2 --seats $3 --engines $4 > gpurun_out/knob.log 2>&1
+  timeout 300 python bench.py --steps 8 --warmup 4 --no-cpu --workload $1 --pairs-api batch --pairs $2 --seats $3 --engines $4 > gpurun_out/knob.log 2>&1
   python - <<PY
 import json
 v=None
@@ -12,7 +12,7 @@ PY
 }
 for w in h2k_pairs cfg1_pairs f4k_pairs; do
   run $w 128 128 2
-  run $w 512 256 2
   run $w 512 512 2
+  run $w 512 512 4
 done
 run e2k_pairs 64 64 2
