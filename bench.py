@@ -825,6 +825,8 @@ def gpu_pairs(sess, args, name, wl, steps, warmup):
         return int(mask.sum()), st["iteration_number"]
 
     batch_api = args.pairs_api == "batch"
+    if batch_api and world > 1:   # the ranks of one node share its host cores
+        os.environ.setdefault("GCR_BATCH_THREADS", str(max(2, (os.cpu_count() or 2) // world - 2)))
     if wl["problem"] == "e":
         find_batch = lambda c, *a, **kw: pygcransac.findEssentialMatrixBatch(c, synth.K_MAT, synth.K_MAT, *a, **kw)
     else:
@@ -993,8 +995,18 @@ def main():
             t0 = time.perf_counter()
             ewl = dict(WORKLOADS[ename])
             l2 = gpu_pairs(sess, args, ename, ewl, 6, 4)
+            l3 = None
+            if ename == "cfg1_pairs" and args.pairs_api == "threads":
+                # configs[0] once more through the batch call (findHomographyBatch: 512 pairs resident, lock-step): small pairs,
+                # where the driver calls per pair were the cost, are where it is ahead of one pair per host thread
+                args.pairs_api = "batch"
+                l3 = gpu_pairs(sess, args, ename, dict(ewl, pairs=512), 4, 4)
+                args.pairs_api = "threads"
             if rank == 0:
                 extra[ename] = compact(l2)
+                if l3:
+                    extra[ename]["batch_api"] = {"pairs_per_s": l3["value"], "pairs_per_call": 512, "step_ms": l3["config"]["step_ms"],
+                                                 "api": "pygcransac.findHomographyBatch (gcr_find_model_batch)"}
                 extra[ename]["bench_wall_s"] = time.perf_counter() - t0
                 if with_cpu:
                     cpu_jobs.append(("pairs", extra[ename], ewl, 0, l2["value"]))
