@@ -1001,17 +1001,6 @@ def main():
                 if with_cpu:
                     cpu_jobs.append(("pairs", extra[ename], ewl, 0, l2["value"]))
             sess.barrier()
-        if args.pairs_api == "threads":
-            # configs[0] once more through the batch call (findHomographyBatch: 512 pairs resident, lock-step): small pairs,
-            # where the driver calls per pair were the cost, are where it is ahead of one pair per host thread.  (Last: the
-            # engines keep their contexts and pinned staging areas for the rest of the process.)
-            args.pairs_api = "batch"
-            l3 = gpu_pairs(sess, args, "cfg1_pairs", dict(WORKLOADS["cfg1_pairs"], pairs=512), 4, 4)
-            args.pairs_api = "threads"
-            if rank == 0:
-                extra["cfg1_pairs"]["batch_api"] = {"pairs_per_s": l3["value"], "pairs_per_call": 512, "step_ms": l3["config"]["step_ms"],
-                                                    "api": "pygcransac.findHomographyBatch (gcr_find_model_batch)"}
-            sess.barrier()
         if rank == 0:
             line["extra"] = extra
             # the other half of BASELINE's metric, gathered where a reader of the headline line looks first
