@@ -54,9 +54,9 @@ namespace
 			if (p) gcr_host_free_pinned(ctx, p);
 			p = nullptr;
 			bytes = 0;
-			// grow in powers of two from 256 KB: the groups of consecutive super-steps differ in size, and allocating pinned memory
+			// grow in powers of two from 1 MiB: the groups of consecutive super-steps differ in size, and allocating pinned memory
 			// stalls every stream of the process
-			size_t want = (size_t)256 << 10;
+			size_t want = (size_t)1 << 20;
 			while (want < need)
 				want <<= 1;
 			if (gcr_host_alloc_pinned(ctx, want, &p) != GCR_OK)
@@ -262,7 +262,8 @@ namespace
 		{
 			// every device / pinned block goes back before the context it came from
 			classes.clear();
-			slots.clear();
+			for (auto &pool : slots_of_kind)
+				pool.clear();
 			issued.clear();
 			for (DeviceBuffer *b : {&lo_models, &lo_ok, &lo_scores})
 				if (b->p)
@@ -399,7 +400,10 @@ namespace
 			Staging st;
 			bool busy = false;
 		};
-		std::vector<std::unique_ptr<Slot>> slots;
+		// one pool per kind of request: a slot's buffers then see groups of similar size and stop regrowing after a call or
+		// two (pinned reallocations stall every stream: with one shared pool the passes of a call varied 2-8 x)
+		std::vector<std::unique_ptr<Slot>> slots_of_kind[Request::KINDS];
+		Request::Kind acquiring = Request::UPLOAD;
 		struct Issued
 		{
 			std::vector<Request *> group;
@@ -410,6 +414,7 @@ namespace
 		std::vector<Issued> issued;
 		Slot &acquire()
 		{
+			std::vector<std::unique_ptr<Slot>> &slots = slots_of_kind[acquiring];
 			for (auto &sl : slots)
 				if (!sl->busy && sl->st.readers.load(std::memory_order_acquire) == 0)
 				{
@@ -478,6 +483,7 @@ namespace
 
 		void execute_kind(Request::Kind kind, std::vector<Request *> &reqs)
 		{
+			acquiring = kind;
 			switch (kind)
 			{
 			case Request::UPLOAD:
@@ -593,6 +599,7 @@ namespace
 		{
 			Issued rec;
 			rec.group = g;
+			acquiring = Request::BATCH;
 			rec.slot = &acquire();
 			bool ok = do_batch(g, B, rec) && (gcr_sync(ctx) == GCR_OK || fail("gcr_sync"));
 			bool completed = false;

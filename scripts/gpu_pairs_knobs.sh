@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_batch.py -q -x -p no:cacheprovider 2>&1 | tail -1
 run() { # workload pairs seats engines
-  timeout 300 python bench.py --steps 8 --warmup 4 --no-cpu --workload $1 --pairs-api batch --pairs $2 --seats $3 --engines $4 > gpurun_out/knob.log 2>&1
+  timeout 300 python bench.py --steps 12 --warmup 4 --no-cpu --workload $1 --pairs-api batch --pairs $2 --seats $3 --engines $4 > gpurun_out/knob.log 2>&1
   python - <<PY
 import json
 v=None
@@ -10,9 +11,7 @@ for line in open("gpurun_out/knob.log"):
 print("$1 pairs $2 seats $3 engines $4 -> %s pairs/s  steps %s" % ("%.0f" % v if v else "FAILED", st if v else ""))
 PY
 }
-for w in h2k_pairs cfg1_pairs f4k_pairs; do
-  run $w 128 128 2
-  run $w 512 512 2
-  run $w 512 512 4
-done
-run e2k_pairs 64 64 2
+run cfg1_pairs 512 512 2
+run cfg1_pairs 512 512 2
+run f4k_pairs 512 512 2
+run h2k_pairs 512 512 2
