@@ -1012,7 +1012,7 @@ def main():
         if kind == "rounds":
             target["cpu_baseline"] = cpu_baseline_rounds(jwl, make_points(dict(jwl, pairs=1), 0)[0].copy(), scale)
         else:
-            ref = reference_pairs(args, jwl, steps=1, warmup=0)
+            ref = reference_pairs(args, jwl, steps=1, warmup=1)   # (one warm-up pass of one pair per core: the workers start warm)
             target["cpu_baseline"] = ref["cpu_baseline"]
             target["speedup_vs_cpu_baseline"] = gpu_value / ref["value"]
     if rank == 0:
