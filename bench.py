@@ -642,6 +642,11 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
     # ---- the resident pass once more with the rounds alternating between two streams (what the e2e leg does) ----
     ms_two = None
     if two_lanes:
+        # with several streams in flight the scoring kernel keeps 3 of its 5 CTA slots per SM (gcr_set_tuning): alone it loses
+        # ~1 % that way, but the other streams' solver / select / upload kernels then find room beside it (e2e -3 %)
+        if args.k3_cap == 0:
+            for lane in lanes:
+                lane["ctx"].set_tuning(_cabi.TUNE_K3_CTAS_PER_SM, args.lanes_k3_cap)
         for lane in lanes[1:]:
             lane["ctx"].points_set_device(pts_dev.data_ptr(), n, 4, 1)
         for i in range(2):
@@ -754,7 +759,8 @@ def gpu_rounds(sess, args, name, wl, steps, warmup, with_cpu, headline):
                     "overlap": ("%d chunks of pairs on %d contexts / streams: uploads overlap scoring; %s upload" % (
                         E2E_CHUNKS, E2E_SIDE, args.upload)) if overlap else
                         ("rounds alternate between %d contexts / streams:" % len(lanes) + " the solver kernel and the upload of round i + 1 run "
-                         "beside the scoring kernel of round i") if two_lanes else "none"},
+                         "beside the scoring kernel of round i (which keeps %d of its 5 CTA slots per SM meanwhile)" % (
+                             args.k3_cap or args.lanes_k3_cap)) if two_lanes else "none"},
             "gpu_launches": int(launches),
         }
         if ms_two and n_pairs > 1:
@@ -943,6 +949,8 @@ def main():
                     help="K3 also produces FP64-exact per-model inlier counts (threshold-band re-check); not an output of the "
                          "round -- the winner's FP64 score / exact count come from K4 either way")
     ap.add_argument("--k3-cap", type=int, default=0, help="experiment: resident K3 CTAs per SM (0 = all that fit)")
+    ap.add_argument("--lanes-k3-cap", type=int, default=3,
+                    help="K3 CTAs per SM while the rounds alternate between several streams (multi-stream resident pass, e2e leg)")
     ap.add_argument("--lanes", type=int, default=4, choices=[1, 2, 3, 4],
                     help="single-pair workloads, e2e leg: consecutive rounds alternate between this many contexts / streams")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
