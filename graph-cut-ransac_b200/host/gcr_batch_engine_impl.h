@@ -31,6 +31,8 @@
 #include <deque>
 
 #include <sys/mman.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
 #include <ucontext.h>
 #include <unistd.h>
 
@@ -178,6 +180,11 @@ namespace
 	// the loop of one OS worker thread
 	void fiber_thread(RunQueue *rq)
 	{
+		// the dispatcher threads must get a core the moment requests are pending; the fiber threads (host min-cuts) yield to
+		// them ($GCR_BATCH_WORKER_NICE, default 5; raising one's own niceness needs no privilege)
+		static const int worker_nice = getenv("GCR_BATCH_WORKER_NICE") ? atoi(getenv("GCR_BATCH_WORKER_NICE")) : 5;
+		if (worker_nice > 0)
+			setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
 		ucontext_t self;
 		tl_scheduler = &self;
 		while (Fiber *f = rq->pop_wait())
