@@ -422,12 +422,25 @@ namespace
 		Slot &acquire()
 		{
 			std::vector<std::unique_ptr<Slot>> &slots = slots_of_kind[acquiring];
-			for (auto &sl : slots)
-				if (!sl->busy && sl->st.readers.load(std::memory_order_acquire) == 0)
-				{
-					sl->busy = true;
-					return *sl;
-				}
+			// A slot is free again once the last requester of its group has copied its rows out, i.e. once those fibers have
+			// run.  A pool that simply grew whenever nothing was free kept allocating pinned areas (each a device-wide stall)
+			// for as long as the fiber threads were busy with min-cuts: at most `kMaxSlots` per kind, then wait for one.
+			const size_t kMaxSlots = 12;
+			for (;;)
+			{
+				for (auto &sl : slots)
+					if (!sl->busy && sl->st.readers.load(std::memory_order_acquire) == 0)
+					{
+						sl->busy = true;
+						return *sl;
+					}
+				bool waiting_for_readers = false; // (slots of THIS super-step's groups stay busy until it completes: never wait for those)
+				for (auto &sl : slots)
+					waiting_for_readers |= !sl->busy;
+				if (slots.size() < kMaxSlots || !waiting_for_readers)
+					break;
+				std::this_thread::yield();
+			}
 			slots.emplace_back(new Slot());
 			slots.back()->busy = true;
 			return *slots.back();
