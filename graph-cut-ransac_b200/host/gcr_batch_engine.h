@@ -46,6 +46,11 @@ int gcr_find_essential_batch(int device, const double *h_points, int n, int n_pa
 /* frees the engines (contexts, device buffers, pinned staging) the batch calls keep between calls */
 void gcr_batch_engines_release(void);
 
+/* the engine's host-side concurrency core (fibers, run queue, request / completion protocol) exercised without a GPU: n_fibers
+ * fibers post `rounds` requests each, a dispatcher thread completes them, n_threads OS threads run the fibers.  Returns
+ * n_fibers x rounds, or < 0 if a request was lost or a fiber resumed twice. */
+long long gcr_fiber_selftest(int n_fibers, int n_threads, int rounds);
+
 /* kernels launched so far on the engines' contexts (gcr_launch_count summed over them) */
 uint64_t gcr_batch_launch_count(void);
 

@@ -1504,6 +1504,81 @@ extern "C" void gcr_batch_engines_release(void)
 	g_nested_free.clear();
 }
 
+// The engine's host-side concurrency core without a GPU: `n_fibers` fibers each post `rounds` requests (a token in a
+// pending list) and switch out; a dispatcher thread completes whatever is pending; `n_threads` OS threads run the fibers.
+// Same Fiber / RunQueue / state protocol as Engine::submit and Engine::complete.  Returns the number of completed requests
+// (n_fibers x rounds when nothing was lost or resumed twice), < 0 on a set-up error.  For the CPU tier of the tests.
+extern "C" long long gcr_fiber_selftest(int n_fibers, int n_threads, int rounds)
+{
+	if (n_fibers <= 0 || n_threads <= 0 || rounds < 0)
+		return -1;
+	RunQueue rq;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<Fiber *> pending;
+	int live = n_fibers;
+	std::atomic<long long> total{0};
+	std::vector<long long> per_fiber(n_fibers, 0);
+	std::vector<std::unique_ptr<Fiber>> fibers;
+	for (int i = 0; i < n_fibers; ++i)
+	{
+		fibers.emplace_back(new Fiber());
+		Fiber *f = fibers.back().get();
+		f->body = [&, i]() {
+			for (int r = 0; r < rounds; ++r)
+			{
+				Fiber *self = current_fiber();
+				{
+					std::lock_guard<std::mutex> lock(mu);
+					pending.push_back(self);
+					cv.notify_one();
+				}
+				swapcontext(&self->uc, current_scheduler()); // back when the dispatcher has completed the request (on any thread)
+				++per_fiber[i];
+				total.fetch_add(1, std::memory_order_relaxed);
+			}
+			std::lock_guard<std::mutex> lock(mu);
+			--live;
+			cv.notify_one();
+		};
+		if (!fiber_start(f, (size_t)256 << 10))
+			return -2;
+	}
+	rq.live = n_fibers;
+	for (auto &f : fibers)
+		rq.q.push_back(f.get());
+	std::thread dispatcher([&]() {
+		std::vector<Fiber *> batch;
+		for (;;)
+		{
+			{
+				std::unique_lock<std::mutex> lock(mu);
+				cv.wait(lock, [&] { return !pending.empty() || live == 0; });
+				if (pending.empty() && live == 0)
+					return;
+				batch.swap(pending);
+			}
+			for (Fiber *f : batch)
+				if (f->state.exchange(Fiber::READY, std::memory_order_acq_rel) == Fiber::PARKED) // (else its thread enqueues it)
+				{
+					f->state.store(Fiber::RUNNING, std::memory_order_release);
+					rq.push(f);
+				}
+			batch.clear();
+		}
+	});
+	std::vector<std::thread> threads;
+	for (int t = 0; t < n_threads; ++t)
+		threads.emplace_back(fiber_thread, &rq);
+	for (std::thread &t : threads)
+		t.join();
+	dispatcher.join();
+	for (int i = 0; i < n_fibers; ++i)
+		if (per_fiber[i] != rounds)
+			return -3;
+	return total.load();
+}
+
 extern "C" uint64_t gcr_batch_launch_count(void)
 {
 	std::lock_guard<std::mutex> lock(g_engine_mu);

@@ -64,3 +64,21 @@ def test_driver_library_exports_every_declared_symbol():
     lib.gcr_run_settings_default(C.byref(s))
     assert (s.threshold, s.confidence, s.batch, s.sampler, s.scoring, s.sampler_variance) == (2.0, 0.95, 1024, 0, 0, 0.1)
     assert not s.point_probabilities and list(s.image_sizes) == [0.0] * 4 and s.neighborhood_radius == 20.0
+
+
+def test_batch_engine_fibers_without_a_gpu():
+    """The lock-step driver's host-side concurrency core (host/gcr_batch_engine_impl.h: fibers on their own stacks, a run
+    queue served by a few OS threads, requests completed by a dispatcher thread, the PARKED / READY hand-over that lets a
+    fiber resume on any thread exactly once) -- exercised with plain tokens instead of GPU requests."""
+    import ctypes as C
+    path = os.path.join(ROOT, "graph-cut-ransac_b200", "host", "_ref", "libgcr_driver.so")
+    if not os.path.exists(path):
+        pytest.skip("host driver not built (needs the reference tree for its BK max-flow)")
+    from pygcransac import _cabi
+    _cabi.load_library()
+    lib = C.CDLL(path)
+    lib.gcr_fiber_selftest.restype = C.c_longlong
+    lib.gcr_fiber_selftest.argtypes = [C.c_int, C.c_int, C.c_int]
+    for fibers, threads, rounds in ((1, 1, 10), (64, 4, 200), (300, 8, 50), (7, 16, 1000)):
+        assert lib.gcr_fiber_selftest(fibers, threads, rounds) == fibers * rounds, (fibers, threads, rounds)
+    assert lib.gcr_fiber_selftest(0, 1, 1) < 0
