@@ -1,4 +1,5 @@
-// Host build of the DEVICE solver headers (graph-cut-ransac_b200/csrc/solve_f7.cuh, solve_e5_group.cuh): the CUDA
+// Host build of the DEVICE solver headers (graph-cut-ransac_b200/csrc/solve_f7.cuh, solve_e5_group.cuh, solve_e_stewenius.cuh,
+// solve_p3p.cuh): the CUDA
 // qualifiers are defined away, the ten lanes of a 5-point group become ten threads and the group barrier a
 // pthread barrier.  Lets the CPU-only test tier check the kernels' arithmetic against the oracle without a GPU
 // (tests/test_device_solvers_on_host.py).  Test infrastructure, not part of the product.
@@ -15,6 +16,8 @@ using std::isfinite;
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 #include "solve_f7.cuh"
 #include "solve_e5_group.cuh"
+#include "solve_e_stewenius.cuh"
+#include "solve_p3p.cuh"
 
 namespace
 {
@@ -100,4 +103,28 @@ extern "C" int host_e5_group(const double *pts5, double *models, unsigned char *
 	for (int l = 1; l < 10; ++l)
 		if (jobs[l].ret != jobs[0].ret) return -100; // the lanes must agree
 	return jobs[0].ret;
+}
+
+// Stewenius non-minimal solver from a 4-D null-space basis N[4][9] (what k_refit_e hands it): E_out[10][9] un-normalised,
+// returns the number of models
+extern "C" int host_stewenius_from_basis(const double *N36, double *E90)
+{
+	double N[4][9];
+	for (int b = 0; b < 4; ++b)
+		for (int j = 0; j < 9; ++j)
+			N[b][j] = N36[9 * b + j];
+	return gcr_e_nm::solve_from_basis(N, E90);
+}
+
+// P3P (Lambda-Twist) on three 2D-3D matches, rows u v X Y Z: P48 = up to four 3 x 4 poses, returns their number
+extern "C" int host_p3p(const double *pts5, const uint32_t *sidx, double *P48)
+{
+	struct Pt5
+	{
+		const double *P;
+		const uint32_t *s;
+		double operator()(int i, int c) const { return P[(size_t)s[i] * 5 + c]; }
+	};
+	const Pt5 pt{pts5, sidx};
+	return gcr_p3p::solve(pt, P48);
 }

@@ -67,3 +67,59 @@ def test_e5_group_device_code_matches_oracle(host, oracle):
     for p5 in (np.zeros((5, 4)), np.ones((5, 4))):             # rank-deficient samples: no models, no hang
         n_ok, got, valid = _models(host.host_e5_group, p5, slots=10)
         assert n_ok == 0 and not valid.any() and not got.any()
+
+
+def _same_up_to_sign(a, b, tol):
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max()) <= tol
+
+
+def test_stewenius_device_code_matches_oracle(host, oracle):
+    """csrc/solve_e_stewenius.cuh (constraints, 10 x 10 elimination, action matrix, Hessenberg-QR eigenvalues, inverse-iteration
+    eigenvectors: what k_refit_e's thread runs) on the HOST, fed the 4-D null-space basis of A^T A from the oracle's
+    column-pivoted Householder QR, against the oracle's own estimateModelNonminimal on the same index sets."""
+    rng = np.random.default_rng(11)
+    host.host_stewenius_from_basis.restype = C.c_int
+    checked = 0
+    for seed, outliers in ((1, 0.0), (2, 0.3)):
+        px, _, _, Kc, inl = synth.epipolar_pair(400, outliers, seed)
+        pts = oracle.normalize_correspondences(px, Kc, Kc)
+        pool = np.flatnonzero(inl)
+        for size in (6, 12, 35, 120):
+            for _ in range(6):
+                s = np.sort(rng.choice(pool, size, replace=False)).astype(np.uint32)
+                P = pts[s]
+                A = np.stack([P[:, 0] * P[:, 2], P[:, 0] * P[:, 3], P[:, 0], P[:, 1] * P[:, 2], P[:, 1] * P[:, 3], P[:, 1],
+                              P[:, 2], P[:, 3], np.ones(len(P))], axis=1)
+                Q = oracle.colpiv_q(A.T @ A)
+                N = np.ascontiguousarray(Q[:, 5:].T)                      # N[b][j] = Q[j][5 + b] (k_refit.cu colpiv_householder_q_last4_9)
+                E = np.zeros(90)
+                count = host.host_stewenius_from_basis(N.ctypes.data_as(C.c_void_p), E.ctypes.data_as(C.c_void_p))
+                want = oracle.refit_e(pts, s)
+                assert count == len(want), (seed, size, count, len(want))
+                got = E[: 9 * count].reshape(count, 3, 3)
+                for w in want:                                            # same model set (order by eigenvalue on both sides, but
+                    assert any(_same_up_to_sign(g, w, 1e-7) for g in got)   # compared as sets: A^T A is summed in another order)
+                checked += count
+    assert checked > 100
+
+
+def test_p3p_device_code_matches_oracle(host, oracle):
+    """csrc/solve_p3p.cuh (Lambda-Twist) on the host against the oracle's restatement of estimators/solver_p3p.h."""
+    rng = np.random.default_rng(12)
+    host.host_p3p.restype = C.c_int
+    n_models = 0
+    for seed in (1, 2, 3):
+        pts5 = np.ascontiguousarray(synth.pnp_scene(300, 0.3, seed)[0])
+        for _ in range(200):
+            s = np.ascontiguousarray(rng.choice(300, 3, replace=False), dtype=np.uint32)
+            P = np.zeros(48)
+            nm = host.host_p3p(pts5.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), P.ctypes.data_as(C.c_void_p))
+            want = oracle.solve_p3p(pts5, s)
+            got = P[: 12 * nm].reshape(nm, 3, 4)
+            got = got[np.isfinite(got).all(axis=(1, 2))]
+            assert len(got) == len(want), (seed, s, len(got), len(want))
+            for g, w in zip(got, want):
+                assert np.abs(g - w).max() <= 1e-9 * max(1.0, np.abs(w).max())
+            n_models += len(want)
+    assert n_models > 300
