@@ -779,7 +779,11 @@ __global__ void __launch_bounds__(BA != 0 ? RF_MAX_THREADS : RF_THREADS) k_refit
 // Eigen ColPivHouseholderQR(M).matrixQ().rightCols<4>() of a 9 x 9 row-major M (destroyed): N[b][j] = Q(j, 5 + b).
 // Same pivoting rule as Eigen 3.4 computeInPlace (first column of largest down-dated norm, LAPACK-style down-dating,
 // recomputation below sqrt(eps)) and makeHouseholder's (beta, tau, essential) convention.
-__device__ void colpiv_householder_q_last4_9(double *M, double (&N)[4][9])
+// __noinline__ ON PURPOSE: inlined into k_refit_e's lane-parallel form, nvcc 12.9 gave `updated[9]` the stack slot of the
+// caller's live AtA[81] (SASS: both at R1 + 0 -- the column norms overwrote row 0 of the matrix, wrong pivots, a basis
+// that is not the null space; tools/refit_e_dump.py + scripts/gpu_refit_e_ab.sh found it).  As a real call its locals get
+// a frame of their own.
+__device__ __noinline__ void colpiv_householder_q_last4_9(double *M, double (&N)[4][9])
 {
 	const int n = 9;
 	double updated[9], direct[9], tau[9];
@@ -885,6 +889,8 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a_in)
 		if (tid < RF_E_MODELS) ok[tid] = 0;
 		return;
 	}
+	__shared__ double s_N[4][9], s_Am[100], s_w[20];
+	__shared__ int s_slot[RF_E_MODELS];
 	double N[4][9];
 	bool have_basis = true;
 	if (n == 5)
@@ -937,38 +943,51 @@ __global__ void __launch_bounds__(RF_THREADS) k_refit_e(const RefitArgs a_in)
 			colpiv_householder_q_last4_9(AtA, N);
 		}
 	}
-	if (tid != 0)
-		return;
-	double E[RF_E_MODELS * 9];
-	int count = 0;
-	if (have_basis)
+	// Thread 0: basis -> action matrix + eigenvalues (serial: 10 x 10 LU, Hessenberg QR).  Then one lane per eigenvalue:
+	// the inverse iterations are independent, model m = the m-th REAL eigenvalue in the order of the eigenvalues.
+	if (tid == 0)
 	{
-		bool finite = true;
+		int n_eig = 0;
+		if (have_basis)
+		{
+			bool finite = true;
+			for (int b = 0; b < 4; ++b)
+				for (int j = 0; j < 9; ++j)
+					if (!isfinite(N[b][j])) finite = false;
+			if (finite)
+				n_eig = gcr_e_nm::action_matrix(N, s_Am, s_w, s_w + 10);
+		}
+		int count = 0;
+		for (int e = 0; e < RF_E_MODELS; ++e)
+			s_slot[e] = e < n_eig && s_w[10 + e] == 0.0 ? count++ : -1;
 		for (int b = 0; b < 4; ++b)
 			for (int j = 0; j < 9; ++j)
-				if (!isfinite(N[b][j])) finite = false;
-		if (finite)
-			count = gcr_e_nm::solve_from_basis(N, E);
-	}
-	// essential_estimator.h:327-333: Frobenius-normalise, sign so that E(2,2) >= 0
-	for (int m = 0; m < RF_E_MODELS; ++m)
-	{
-		bool good = m < count;
-		double out[9];
-		if (good)
+				s_N[b][j] = N[b][j];
+		// slots beyond the number of real eigenvalues
+		for (int m = count; m < RF_E_MODELS; ++m)
 		{
-			double nrm = 0.0;
-			for (int i = 0; i < 9; ++i) nrm += E[9 * m + i] * E[9 * m + i];
-			nrm = sqrt(nrm);
-			for (int i = 0; i < 9; ++i) out[i] = E[9 * m + i] / nrm;
-			if (out[8] < 0)
-				for (int i = 0; i < 9; ++i) out[i] = -out[i];
-			for (int i = 0; i < 9; ++i)
-				if (isnan(out[i])) good = false;
+			for (int i = 0; i < 9; ++i) models[9 * m + i] = 0.0;
+			ok[m] = 0;
 		}
-		for (int i = 0; i < 9; ++i) models[9 * m + i] = good ? out[i] : 0.0;
-		ok[m] = good ? 1 : 0;
 	}
+	__syncthreads();
+	if (tid >= RF_E_MODELS || s_slot[tid] < 0)
+		return;
+	const int m = s_slot[tid];
+	double E[9];
+	gcr_e_nm::model_of_eigenvalue(s_N, s_Am, s_w[tid], E);
+	// essential_estimator.h:327-333: Frobenius-normalise, sign so that E(2,2) >= 0
+	bool good = true;
+	double out[9], nrm = 0.0;
+	for (int i = 0; i < 9; ++i) nrm += E[i] * E[i];
+	nrm = sqrt(nrm);
+	for (int i = 0; i < 9; ++i) out[i] = E[i] / nrm;
+	if (out[8] < 0)
+		for (int i = 0; i < 9; ++i) out[i] = -out[i];
+	for (int i = 0; i < 9; ++i)
+		if (isnan(out[i])) good = false;
+	for (int i = 0; i < 9; ++i) models[9 * m + i] = good ? out[i] : 0.0;
+	ok[m] = good ? 1 : 0;
 }
 
 extern "C" int gcr_max_refit_models(int problem)

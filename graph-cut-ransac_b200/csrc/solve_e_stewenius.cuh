@@ -257,8 +257,10 @@ namespace gcr_e_nm
 		}
 	}
 
-	// N[b][j]: coefficient j (column-major E.data() index) of basis vector b.  E_out: up to 10 x 9 row-major, un-normalised.
-	__device__ inline int solve_from_basis(const double (&N)[4][9], double *E_out)
+	// Part 1 (one thread).  N[b][j]: coefficient j (column-major E.data() index) of basis vector b -> the 10 x 10 action
+	// matrix Am and its eigenvalues (wr, wi).  Returns the number of eigenvalues to look at (10), 0 when the system is
+	// singular / not finite / the eigenvalue iteration does not converge.
+	__device__ inline int action_matrix(const double (&N)[4][9], double *Am, double *wr, double *wi)
 	{
 		// ---- constraints in the 5-point kernel's monomial order, rows 0..8 = (E E^T - 1/2 tr) E, row 9 = det ----
 		double C5[10][20];
@@ -348,7 +350,6 @@ namespace gcr_e_nm
 			}
 		// B now holds Y with X[cp[j]] = Y[j]
 		// ---- action matrix (:201-209): rows 0,1,2,4,5,7 of X, then the four -1 entries ----
-		double Am[100];
 		for (int i = 0; i < 100; ++i) Am[i] = 0.0;
 		const int src_row[6] = {0, 1, 2, 4, 5, 7};
 		for (int j = 0; j < 10; ++j)
@@ -362,20 +363,34 @@ namespace gcr_e_nm
 		for (int i = 0; i < 100; ++i)
 			if (!isfinite(Am[i]))
 				return 0;
-		double wr[10], wi[10];
 		for (int i = 0; i < 100; ++i) A[i] = Am[i];
 		if (!eigenvalues10(A, wr, wi))
+			return 0;
+		return 10;
+	}
+
+	// Part 2 (any thread, one REAL eigenvalue): its eigenvector -> the model E (row-major, un-normalised).  The eigenvalues
+	// are independent of each other: k_refit_e gives each one a lane of its own.
+	__device__ inline void model_of_eigenvalue(const double (&N)[4][9], const double *Am, double lambda, double *E)
+	{
+		double v[10];
+		eigenvector10(Am, lambda, v);
+		for (int k = 0; k < 9; ++k)
+			E[3 * (k % 3) + k / 3] = N[0][k] * v[6] + N[1][k] * v[7] + N[2][k] * v[8] + N[3][k] * v[9];
+	}
+
+	// the two parts in sequence: E_out: up to 10 x 9 row-major, un-normalised, in the order of the eigenvalues
+	__device__ inline int solve_from_basis(const double (&N)[4][9], double *E_out)
+	{
+		double Am[100], wr[10], wi[10];
+		if (!action_matrix(N, Am, wr, wi))
 			return 0;
 		int n_models = 0;
 		for (int e = 0; e < 10; ++e)
 		{
 			if (wi[e] != 0.0)
 				continue;
-			double v[10];
-			eigenvector10(Am, wr[e], v);
-			double *E = E_out + 9 * n_models;
-			for (int k = 0; k < 9; ++k)
-				E[3 * (k % 3) + k / 3] = N[0][k] * v[6] + N[1][k] * v[7] + N[2][k] * v[8] + N[3][k] * v[9];
+			model_of_eigenvalue(N, Am, wr[e], E_out + 9 * n_models);
 			++n_models;
 		}
 		return n_models;
