@@ -13,6 +13,13 @@
 #include <cstring>
 #include <vector>
 
+// Test hook (tests/test_reference_solver_sources.py): another real-root finder for the degree-10 polynomial, ascending
+// coefficients in, roots out, returns their number.  oracle/ref_solvers_glue.cpp plugs in the reference's own
+// maths/sturm_polynomial_solver.h to show that the root finder is the ONLY place where the restated five-point solver and
+// the reference's source part ways (by design: the reference stops bisecting at depth 30 and drops roots it has not
+// separated by then, and accepts a root after ten Newton steps whatever its residual).  Null = the oracle's own (sturm.h).
+int (*gcro_e5_root_finder)(const double *c11, double *roots10) = nullptr;
+
 namespace
 {
 	// Monomials of degree <= 3 in (x, y, z), in the column order of the reference's 10 x 20 constraint matrix
@@ -145,7 +152,7 @@ int gcro_solve_e5_nister(const double *pts, const uint32_t *sample, double *E90)
 	}
 	// :574 real roots
 	double roots[10];
-	const int n_sols = gcro_sturm::real_roots(c, 10, roots);
+	const int n_sols = gcro_e5_root_finder ? gcro_e5_root_finder(c, roots) : gcro_sturm::real_roots(c, 10, roots);
 	// :583-612 back substitution
 	int n_models = 0;
 	for (int s = 0; s < n_sols; ++s)

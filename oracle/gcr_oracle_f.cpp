@@ -267,6 +267,9 @@ static void fullpiv_householder_q_lastcol(const double *M_in, int n, double *q)
 	}
 }
 
+// exported for oracle/shim_solvers (the reference's eight-point solver compiled verbatim calls the same routine)
+void gcro_fullpiv_householder_q_lastcol(const double *M_in, int n, double *q) { fullpiv_householder_q_lastcol(M_in, n, q); }
+
 // fundamental_estimator.h:574-618 (+ normalizePoints :637-734) + solver_fundamental_matrix_eight_point.h:93-182.
 // The 8-point solver receives the normalised copy with sample_ == nullptr, so it reads weights_[i] by POSITION (:113-118).
 // FundamentalMatrixEightPointSolver::estimateModel (solver_fundamental_matrix_eight_point.h:93-182) on n points given

@@ -41,6 +41,19 @@ def build_ref(force=False):
     return so if os.path.exists(so) else None
 
 
+def build_ref_solvers(force=False):
+    """Build oracle/_ref/libgcr_ref_solvers.so (the reference's solver / estimator headers compiled verbatim over
+    oracle/shim_solvers) when the reference tree is present; returns the path or None."""
+    so = os.path.join(HERE, "_ref", "libgcr_ref_solvers.so")
+    ref_dir = os.environ.get("GCR_REFERENCE_DIR", "/root/reference")
+    if os.path.isdir(ref_dir):
+        srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cpp", ".h"))]
+        srcs += [os.path.join(HERE, "shim_solvers", "Eigen", "Eigen"), os.path.join(HERE, "shim_solvers", "unsupported", "Eigen", "Polynomials")]
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_ref_solvers.sh")], stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
 def _as_pts(pts):
     return np.ascontiguousarray(pts, dtype=np.float64)
 

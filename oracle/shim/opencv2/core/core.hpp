@@ -29,6 +29,7 @@
 #endif
 #define CV_32F 5
 #define CV_64F 6
+#define CV_64FC1 CV_64F
 
 namespace cv
 {
@@ -83,8 +84,19 @@ namespace cv
 		template <class T> T &at(int j) { return reinterpret_cast<T *>(data)[j]; }
 		template <class T> const T &at(int j) const { return reinterpret_cast<const T *>(data)[j]; }
 
+		// container operations math_utils.h's (unused) JAMA class names: (re)allocate, drop, copy out
+		void create(int r, int c, int t) { *this = Mat(r, c, t); }
+		void release() { *this = Mat(); }
+		void convertTo(Mat &dst, int t) const
+		{
+			dst = Mat(rows, cols, t);
+			if (rows * cols) std::memcpy(dst.data, data, sizeof(double) * static_cast<size_t>(rows) * cols);
+		}
+		const Mat &getMat() const { return *this; }
+
 	private:
 		int type_;
 		std::shared_ptr<std::vector<double>> storage_;
 	};
+	typedef const Mat &InputArray;
 }
