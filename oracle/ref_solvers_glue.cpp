@@ -23,6 +23,9 @@
 #include "estimators/solver_essential_matrix_five_point_stewenius.h"
 #include "estimators/solver_p3p.h"
 #include "estimators/essential_estimator.h"
+#include "estimators/perspective_n_point_estimator.h"
+#include "estimators/solver_fundamental_matrix_bundle_adjustment.h"
+#include "estimators/solver_essential_matrix_bundle_adjustment.h"
 
 #include "gcr_oracle.h"
 
@@ -163,6 +166,106 @@ extern "C"
 		const std::vector<size_t> idx = indices(sample, m);
 		if (!e.estimateModelNonminimal(view(pts, n, 4), idx.data(), (size_t)m, &models, weights)) return 0;
 		return copy_out(models, 3, 3, 10, E90);
+	}
+
+	// ---- residuals and model tests of the estimator classes ----
+	// problem: 0 H (homography_estimator.h:175-199), 1 F Sampson (fundamental_estimator.h:195-222), 2 E Sampson
+	// (essential_estimator.h:186-213), 4 F symmetric epipolar (fundamental_estimator.h:225-252)
+	void gcr_refsrc_residuals(int problem, const double *pts, int n, const double *model9, double *out)
+	{
+		Eigen::MatrixXd d(3, 3);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) d(i, j) = model9[3 * i + j];
+		const cv::Mat data = view(pts, n, 4);
+		HEstimator he;
+		FEstimator fe(0.0, false);
+		EEstimator ee(Eigen::Matrix3d::Identity(), Eigen::Matrix3d::Identity(), 0.0);
+		for (int i = 0; i < n; ++i)
+			out[i] = problem == 0 ? he.squaredResidual(data.row(i), d) : problem == 1 ? fe.squaredResidual(data.row(i), d)
+			       : problem == 2 ? ee.squaredResidual(data.row(i), d) : fe.squaredSymmetricEpipolarDistance(data.row(i), d);
+	}
+	// PerspectiveNPointEstimator::squaredResidual (perspective_n_point_estimator.h:148-203): rows x y X Y Z, model 3 x 4
+	void gcr_refsrc_residuals_pnp(const double *pts5, int n, const double *model12, double *out)
+	{
+		Eigen::MatrixXd d(3, 4);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) d(i, j) = model12[4 * i + j];
+		const cv::Mat data = view(pts5, n, 5);
+		estimator::PerspectiveNPointEstimator<estimator::solver::P3PSolver, estimator::solver::P3PSolver> e;
+		for (int i = 0; i < n; ++i) out[i] = e.squaredResidual(data.row(i), d);
+	}
+	int gcr_refsrc_h_valid_model(const double *H9)
+	{
+		HEstimator e;
+		Model m;
+		m.descriptor.resize(3, 3);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.descriptor(i, j) = H9[3 * i + j];
+		bool updated = false;
+		return e.isValidModel(m, cv::Mat(), std::vector<size_t>(), nullptr, 0.0, updated) ? 1 : 0;
+	}
+	// FundamentalMatrixEstimator::isValidModel without DEGENSAC (fundamental_estimator.h:287-338): the symmetric-epipolar ratio test
+	int gcr_refsrc_f_valid_model_ratio(const double *F9, const double *pts, int n, const uint32_t *inl, int n_inl, double threshold, double min_ratio)
+	{
+		FEstimator e(min_ratio, false);
+		Model m;
+		m.descriptor.resize(3, 3);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.descriptor(i, j) = F9[3 * i + j];
+		const std::vector<size_t> inliers = indices(inl, n_inl);
+		bool updated = false;
+		return e.isValidModel(m, view(pts, n, 4), inliers, nullptr, threshold, updated) ? 1 : 0;
+	}
+	// solver_fundamental_matrix_plane_and_parallax.h:105-160 (two correspondences + the plane's homography); `oriented`: through
+	// FundamentalMatrixEstimator<PlaneParallax, EightPoint>::estimateModel, i.e. with the oriented epipolar constraint
+	int gcr_refsrc_solve_f_plane_parallax(const double *pts, int n, const uint32_t *sample, const double *H9, int oriented, double *F9)
+	{
+		Eigen::Matrix3d Hm;
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Hm(i, j) = H9[3 * i + j];
+		std::vector<Model> models;
+		const std::vector<size_t> idx = indices(sample, 2);
+		if (oriented)
+		{
+			estimator::FundamentalMatrixEstimator<estimator::solver::FundamentalMatrixPlaneParallaxSolver,
+			                                      estimator::solver::FundamentalMatrixEightPointSolver> e(0.0, false);
+			e.getMutableMinimalSolver()->setHomography(&Hm);
+			if (!e.estimateModel(view(pts, n, 4), idx.data(), &models)) return 0;
+		}
+		else
+		{
+			estimator::solver::FundamentalMatrixPlaneParallaxSolver s;
+			s.setHomography(&Hm);
+			if (!s.estimateModel(view(pts, n, 4), idx.data(), 2, models, nullptr)) return 0;
+		}
+		return copy_out(models, 3, 3, 1, F9);
+	}
+
+	// ---- bundle adjustment (relative_pose/bundle.cpp, jacobian_impl.h, essential.cpp compiled verbatim beside this file) ----
+	// the default F estimator's non-minimal fit (types.h:78-80): estimateModelNonminimal with the BA solver = normalise,
+	// eight-point, LM in the Hartley frame, denormalise (fundamental_estimator.h:574-618, solver_fundamental_matrix_bundle_adjustment.h:113-177)
+	int gcr_refsrc_refit_f_ba(const double *pts, int n, const uint32_t *sample, int m, const double *weights, double *F9)
+	{
+		estimator::FundamentalMatrixEstimator<estimator::solver::FundamentalMatrixSevenPointSolver,
+		                                      estimator::solver::FundamentalMatrixBundleAdjustmentSolver> e(0.0, false);
+		std::vector<Model> models;
+		const std::vector<size_t> idx = indices(sample, m);
+		if (!e.estimateModelNonminimal(view(pts, n, 4), idx.data(), (size_t)m, &models, weights)) return 0;
+		return copy_out(models, 3, 3, 1, F9);
+	}
+	// the post-run polish of findFundamentalMatrix_ (py/gcransac_python.cpp:1851-1858): the BA solver on the inliers, pixel frame
+	int gcr_refsrc_polish_f_ba(const double *pts, int n, const uint32_t *inliers, int m, const double *weights, double *F9)
+	{
+		estimator::solver::FundamentalMatrixBundleAdjustmentSolver s;
+		std::vector<Model> models;
+		const std::vector<size_t> idx = indices(inliers, m);
+		if (!s.estimateModel(view(pts, n, 4), idx.data(), (size_t)m, models, weights)) return 0;
+		return copy_out(models, 3, 3, 1, F9);
+	}
+	// solver_essential_matrix_bundle_adjustment.h:113-186: Stewenius models -> poses -> LM of the relative pose; every refined
+	// model, in the solver's order
+	int gcr_refsrc_polish_e_ba(const double *pts, int n, const uint32_t *inliers, int m, const double *weights, int max_models, double *E)
+	{
+		estimator::solver::EssentialMatrixBundleAdjustmentSolver s;
+		std::vector<Model> models;
+		const std::vector<size_t> idx = indices(inliers, m);
+		if (!s.estimateModel(view(pts, n, 4), idx.data(), (size_t)m, models, weights)) return 0;
+		return copy_out(models, 3, 3, max_models, E);
 	}
 
 	// ---- the oracle's RESTATED five-point solver over the reference's own root finder (maths/sturm_polynomial_solver.h,

@@ -219,3 +219,98 @@ def test_p3p(src, oracle):
         want = oracle.solve_p3p(pts, s)
         d, tol = _same(got, want, 1e-9)
         assert d <= tol, (t, d)
+
+
+def test_residuals_and_model_tests(src, oracle):
+    """squaredResidual of the three two-view estimators (homography_estimator.h:175-199, fundamental_estimator.h:195-222,
+    essential_estimator.h:186-213), RobustHomographyEstimator::isValidModel (:326-342), FundamentalMatrixEstimator::
+    isValidModel without DEGENSAC (:287-338), the plane-and-parallax solver DEGENSAC's inner run uses
+    (solver_fundamental_matrix_plane_and_parallax.h:105-160) with and without the oriented epipolar constraint"""
+    rng = np.random.default_rng(6)
+    pts_h, Hm, inl_h = synth.homography_pair(500, 0.3, seed=11)
+    pts_f, Fm, Em, K, inl_f = synth.epipolar_pair(500, 0.4, seed=12)
+    pts_e = np.ascontiguousarray(oracle.normalize_correspondences(pts_f, K, K))
+    for prob_src, prob, pts, model in ((0, O.H, pts_h, Hm), (1, O.F, pts_f, Fm), (2, O.E, pts_e, Em)):
+        for m in synth.perturbed_models(model, 20, rng):
+            pts = np.ascontiguousarray(pts, dtype=np.float64)
+            m9 = np.ascontiguousarray(m, dtype=np.float64).reshape(9)
+            out = np.zeros(len(pts))
+            src.gcr_refsrc_residuals(prob_src, _p(pts), len(pts), _p(m9), _p(out))
+            assert np.array_equal(out, oracle.residuals(prob, pts, m)), (prob_src,)      # bit for bit
+    pts_p, Pm, inl_p = synth.pnp_scene(400, 0.3, seed=13)
+    pts_p = np.ascontiguousarray(pts_p, dtype=np.float64)
+    for m in synth.perturbed_models(Pm, 20, rng):
+        out = np.zeros(len(pts_p))
+        src.gcr_refsrc_residuals_pnp(_p(pts_p), len(pts_p), _p(np.ascontiguousarray(m, dtype=np.float64).reshape(12)), _p(out))
+        assert np.array_equal(out, oracle.residuals(O.PNP, pts_p, m))                    # perspective_n_point_estimator.h:148-203
+    for t in range(200):
+        Hc = Hm * (1.0 if t % 2 else 10.0 ** rng.uniform(-3, 0)) + rng.normal(0, 1e-3, (3, 3)) * (t % 3)
+        h9 = np.ascontiguousarray(Hc, dtype=np.float64).reshape(9)
+        assert bool(src.gcr_refsrc_h_valid_model(_p(h9))) == oracle.h_valid_model(Hc)
+    pts_f = np.ascontiguousarray(pts_f, dtype=np.float64)
+    idx = np.flatnonzero(inl_f)
+    for t in range(200):
+        Fc = synth.perturbed_models(Fm, 1, rng)[0] if t % 2 else Fm
+        f9 = np.ascontiguousarray(Fc, dtype=np.float64).reshape(9)
+        inl = rng.choice(500, int(rng.integers(7, 300)), replace=False).astype(np.uint32)
+        thr, ratio = float(rng.uniform(0.2, 3.0)), float(rng.choice([0.0, 0.1, 0.5, 0.9]))
+        got = src.gcr_refsrc_f_valid_model_ratio(_p(f9), _p(pts_f), len(pts_f), _p(inl), len(inl), C.c_double(thr), C.c_double(ratio))
+        want = oracle.lib.gcro_f_valid_model_ratio(f9, pts_f, inl, len(inl), 7, thr, ratio)
+        assert got == want, (t, thr, ratio)
+    # plane and parallax: a homography of a plane of the scene = H compatible with F; any H exercises the arithmetic
+    for t in range(200):
+        s = rng.choice(idx, 2, replace=False).astype(np.uint32)
+        Hc = np.ascontiguousarray(Hm + rng.normal(0, 1e-2, (3, 3)), dtype=np.float64)
+        for oriented in (0, 1):
+            out = np.zeros(9)
+            k = src.gcr_refsrc_solve_f_plane_parallax(_p(pts_f), len(pts_f), _p(s), _p(Hc.reshape(9)), oriented, _p(out))
+            want = oracle.solve_f_plane_parallax(pts_f, s, Hc, oriented=bool(oriented))
+            assert (k == 0) == (want is None), (t, oriented)
+            if k:
+                assert np.abs(out.reshape(3, 3) - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (t, oriented)
+
+
+def test_bundle_adjustment_solvers(src, oracle):
+    """relative_pose/bundle.cpp, jacobian_impl.h, essential.cpp (compiled verbatim beside the glue) behind
+    * the default F estimator's non-minimal fit: FundamentalMatrixEstimator<7-point, FundamentalMatrixBundleAdjustmentSolver>::
+      estimateModelNonminimal (types.h:78-80; normalise, eight-point, LM of refine_fundamental in the Hartley frame, denormalise),
+    * the post-run polish of findFundamentalMatrix_ (py/gcransac_python.cpp:1851-1858: the BA solver on the inliers, pixels),
+    * EssentialMatrixBundleAdjustmentSolver::estimateModel (solver_essential_matrix_bundle_adjustment.h:113-186: Stewenius
+      models -> motion_from_essential + cheirality -> the 5-dof LM of refine_relpose), findEssentialMatrix_'s polish.
+    Weights: the polish calls hand the solvers an array filled by inlier POSITION that the initialisers index by POINT
+    (DESIGN.md section 8); the weighted cases below put the inliers first, so that both readings coincide."""
+    rng = np.random.default_rng(8)
+    pts, Fm, Em, K, inl = synth.epipolar_pair(800, 0.4, seed=3)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    idx = np.flatnonzero(inl)
+    first = np.ascontiguousarray(np.concatenate([pts[idx], pts[~inl]]))
+    for t in range(40):
+        n = int(rng.integers(8, 300))
+        s = rng.choice(idx, n, replace=False).astype(np.uint32)
+        w = rng.random(n) if t % 2 else None            # estimateModelNonminimal: weights by position (normalised copy)
+        got = _call(src.gcr_refsrc_refit_f_ba, pts, s, 1, 3, 3, weights=w)
+        want = oracle.refit_f_ba(pts, s, w)
+        d, tol = _same(got, want, 1e-10)
+        assert d <= tol, (t, n, d)                       # measured: bit for bit
+        if t % 2:
+            s, w, p = np.arange(n, dtype=np.uint32), rng.random(n), first
+        else:
+            w, p = None, pts
+        got = _call(src.gcr_refsrc_polish_f_ba, p, s, 1, 3, 3, weights=w)
+        want = oracle.refit_f_ba(p, s, w, polish=True)
+        d, tol = _same(got, want, 1e-10)
+        assert d <= tol, (t, n, d)
+    pe = np.ascontiguousarray(oracle.normalize_correspondences(pts, K, K))
+    first = np.ascontiguousarray(np.concatenate([pe[idx], pe[~inl]]))
+    for t in range(30):
+        n = int(rng.integers(6, 200))
+        if t % 2:
+            s, w, p = np.arange(n, dtype=np.uint32), rng.random(n), first
+        else:
+            s, w, p = rng.choice(idx, n, replace=False).astype(np.uint32), None, pe
+        out = np.zeros(360)
+        k = src.gcr_refsrc_polish_e_ba(_p(p), len(p), _p(s), len(s), _p(w), 40, _p(out))
+        got = out[: 9 * k].reshape(k, 3, 3)
+        want = oracle.polish_e_ba(p, s, w)
+        d, tol = _same_set(got, want, 1e-7)              # measured 8e-10; the order is the Stewenius initialiser's (see above:
+        assert d <= tol, (t, n, d)                       # one set of these thirty has two of its models swapped)
