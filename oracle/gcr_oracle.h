@@ -14,7 +14,12 @@
  * Pinning status: the reference ships no operator-level golden vectors.  The functions marked
  * [pinned:_ref] are checked bit-for-bit (or to 1e-15) against the reference's own headers compiled verbatim into
  * oracle/_ref/libgcr_ref.so (oracle/build_ref.sh); fixtures generated from that library are committed under
- * tests/golden/.  Functions marked [unpinned] restate Eigen-dependent code that cannot be compiled here.
+ * tests/golden/.  Functions marked [pinned:source] restate Eigen-dependent code: Eigen itself cannot be had here, but the
+ * reference's own solver / estimator SOURCE compiles verbatim over a stand-in for the part of Eigen's API it uses whose
+ * decompositions are oracle/linalg.h (oracle/shim_solvers, oracle/build_ref_solvers.sh -> oracle/_ref/libgcr_ref_solvers.so),
+ * and tests/test_reference_solver_sources.py holds restatement and source side by side: coefficient layouts, polynomial
+ * expansions, elimination templates, normalisation, orientation tests, the order and sign / scale of the returned models
+ * are pinned to the reference; Eigen's own floating-point behaviour stays restated (oracle/linalg.h, pinned against numpy).
  */
 #ifndef GCR_ORACLE_H
 #define GCR_ORACLE_H
@@ -99,13 +104,13 @@ void gcro_normalize_points(const double *pts, int cols, const uint32_t *sample, 
 int gcro_refit_h(const double *pts, const uint32_t *sample, int n, const double *weights, double *H9);
 
 /* ---- fundamental (a8, a9, a11, a22) ----------------------------------------------------------------------- */
-/* solver_fundamental_matrix_seven_point.h:91-291; returns #models (0..3), F row-major 9 each  [unpinned]       */
+/* solver_fundamental_matrix_seven_point.h:91-291; returns #models (0..3), F row-major 9 each  [pinned:source]       */
 int gcro_solve_f7(const double *pts, const uint32_t *sample, double *F27);
 /* fundamental_estimator.h:737-800 oriented epipolar constraint on the sample (1 valid / 0 not) */
 int gcro_f_orientation_valid(const double *F9, const double *pts, const uint32_t *sample, int m);
 /* fundamental_estimator.h:161-184 estimateModel = 7pt + orientation filter */
 int gcro_estimate_f7(const double *pts, const uint32_t *sample, double *F27);
-/* fundamental_estimator.h:574-618 + :637-734 + solver_fundamental_matrix_eight_point.h:93-182  [unpinned]      */
+/* fundamental_estimator.h:574-618 + :637-734 + solver_fundamental_matrix_eight_point.h:93-182  [pinned:source]      */
 int gcro_refit_f8(const double *pts, const uint32_t *sample, int n, const double *weights, double *F9);
 /* LM bundle adjustment of F (relative_pose/bundle.cpp:253-339, jacobian_impl.h:472-606): refinement of F9 on n points
  * in the working frame; the estimator's default non-minimal fit (fundamental_estimator.h:574-618 with the BA solver);
@@ -124,12 +129,12 @@ int gcro_f_valid_model_ratio(const double *F9, const double *pts, const uint32_t
                              double truncated_thr, double min_ratio);
 
 /* ---- essential (a12, a13, a14) ---------------------------------------------------------------------------- */
-/* solver_essential_matrix_five_point_nister.h:263-615; returns #models (0..10)  [unpinned] */
+/* solver_essential_matrix_five_point_nister.h:263-615; returns #models (0..10)  [pinned:source] */
 int gcro_solve_e5_nister(const double *pts, const uint32_t *sample, double *E90);
-/* solver_essential_matrix_five_point_stewenius.h:114-231 (n >= 5, optional weights[sample[i]])  [unpinned]      */
+/* solver_essential_matrix_five_point_stewenius.h:114-231 (n >= 5, optional weights[sample[i]])  [pinned:source]      */
 int gcro_solve_e5_stewenius(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
 /* essential_estimator.h:306-336 estimateModelNonminimal = Stewenius + Frobenius normalisation + sign (E33 >= 0);
- * weights (optional) are read by POINT index (stewenius.h:143)  [unpinned]                                      */
+ * weights (optional) are read by POINT index (stewenius.h:143)  [pinned:source]                                      */
 int gcro_refit_e(const double *pts, const uint32_t *sample, int n, const double *weights, double *E90);
 /* essential_estimator.h:152-175 estimateModel = nister + orientation filter (:338-401) */
 int gcro_estimate_e5(const double *pts, const uint32_t *sample, double *E90);
@@ -145,7 +150,7 @@ int gcro_test_eigenvalues(const double *A, int n, double *wr, double *wi);
 void gcro_test_eigenvector(const double *A, int n, double lambda, double *v);
 
 /* ---- absolute pose (a15) ---------------------------------------------------------------------------------- */
-/* solver_p3p.h:177-385 Lambda-Twist; returns #models (0..4), 3x4 row-major each  [unpinned] */
+/* solver_p3p.h:177-385 Lambda-Twist; returns #models (0..4), 3x4 row-major each  [pinned:source] */
 int gcro_solve_p3p(const double *pts5, const uint32_t *sample, double *P48);
 /* non-minimal absolute pose (gcr_oracle_pba.cpp): normalised DLT + the LM of refine_pnp; weights by position or NULL */
 int gcro_refit_pnp(const double *pts5, const uint32_t *sample, int n, const double *weights, double *P12);

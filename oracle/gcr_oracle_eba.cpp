@@ -5,8 +5,10 @@
 //     (relative_pose/essential.cpp:44-117) -> refine_relpose = lm_5dof_impl over RelativePoseJacobianAccumulator with
 //     TruncatedLoss(1.0), <= 25 iterations (relative_pose/bundle.cpp:176-250, 412-452; jacobian_impl.h:307-460)
 //     -> essential_from_motion.
-// [unpinned against the reference: needs Eigen]; pinned against an independent scipy least-squares solve of the same
-// cost in tests/test_oracle_solvers.py.  Restated with plain arrays in the reference's operation order.
+// Pinned against an independent scipy least-squares solve of the same cost in tests/test_oracle_solvers.py and against the
+// reference's own source (solver_essential_matrix_bundle_adjustment.h + relative_pose/*.cpp compiled verbatim over
+// oracle/shim_solvers, tests/test_reference_solver_sources.py: same model sets to 1e-9).  Restated with plain arrays in the
+// reference's operation order.
 //
 // One deliberate deviation.  The reference fills its weight vector BY POSITION in the inlier list
 // (py/gcransac_python.cpp:2776-2786) and the LM accumulator reads it by position (jacobian_impl.h:342, 416), but the

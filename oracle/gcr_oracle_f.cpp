@@ -1,9 +1,11 @@
 // oracle/gcr_oracle_f.cpp -- TEST INFRASTRUCTURE ONLY (see gcr_oracle.h).
 // Fundamental-matrix path: 7-point minimal solver, oriented epipolar constraint, normalised 8-point refit and the
 // symmetric-epipolar validity test, restated from the reference (file:line beside each function).
-// [unpinned]: the reference versions call Eigen (FullPivLU::kernel, PolynomialSolver, FullPivHouseholderQR), which is
+// [pinned:source]: the reference versions call Eigen (FullPivLU::kernel, PolynomialSolver, FullPivHouseholderQR), which is
 // neither vendored in /root/reference nor installed here; the restatement follows Eigen 3.4's documented semantics
-//  and is cross-checked against numpy in tests/test_oracle_solvers.py.
+// (SURVEY.md A.2), is cross-checked against numpy in tests/test_oracle_solvers.py and held against the reference's own
+// source compiled verbatim over oracle/shim_solvers in tests/test_reference_solver_sources.py (7-point: same model sets to
+// 1e-7, the order of the cubic's roots aside; 8-point refit 1e-9; the default estimator's BA refit and the polish bit for bit).
 #include "gcr_oracle.h"
 #include "linalg.h"
 

@@ -1,5 +1,5 @@
-"""Pins the [unpinned] oracle solvers (Eigen-dependent in the reference) against independent numpy/scipy statements
-of the same problems.  CPU only."""
+"""Pins the oracle solvers that are Eigen-dependent in the reference against independent numpy/scipy statements of the same
+problems (tests/test_reference_solver_sources.py holds them against the reference's own source).  CPU only."""
 import numpy as np
 import oracle as O
 from pygcransac import synth
