@@ -27,6 +27,10 @@
 #include "estimators/solver_fundamental_matrix_bundle_adjustment.h"
 #include "estimators/solver_essential_matrix_bundle_adjustment.h"
 
+#include "GCRANSAC.h"
+#include "neighborhood/grid_neighborhood_graph.h"
+#include "samplers/sampler.h"
+
 #include "gcr_oracle.h"
 
 using namespace gcransac;
@@ -278,4 +282,162 @@ extern "C"
 		gcro_e5_root_finder = nullptr;
 		return k;
 	}
+}
+
+// ---- whole runs: the reference's GCRANSAC<> (verbatim) over (a) the reference's OWN estimator classes, (b) an adapter over
+// the oracle's restated solvers -- the Estimator the verbatim driver of oracle/_ref/libgcr_ref.so runs with (ref_glue.cpp's
+// OracleEstimator, restated here for this library's column-major matrices).  Same counter-based samplers in both (the
+// reference's draw from std::mt19937 seeded by std::random_device), same grid graph, MSAC.  Equal runs pin what the adapter
+// restates by hand: sampleSize / nonMinimalSampleSize / inlierLimit / isWeightingApplicable, which checks run where. ----
+namespace
+{
+	class CounterSampler : public sampler::Sampler<cv::Mat, size_t>
+	{
+		uint64_t seed, next;
+		uint32_t stream;
+		std::vector<uint32_t> tmp;
+
+	public:
+		CounterSampler(const cv::Mat *c, uint64_t seed_, uint32_t stream_) : sampler::Sampler<cv::Mat, size_t>(c), seed(seed_), next(0), stream(stream_) { initialized = true; }
+		const std::string getName() const { return "counter-based uniform sampler"; }
+		void reset() {}
+		void update(const size_t *const, const size_t &, const size_t &, const double &) {}
+		bool initialize(const cv::Mat *const) { return true; }
+		uint64_t drawn() const { return next; }
+		bool sample(const std::vector<size_t> &pool_, size_t *const subset_, size_t sample_size_)
+		{
+			if (sample_size_ > pool_.size()) return false;
+			tmp.resize(sample_size_);
+			gcro_sample_uniform(seed, next++, stream, (uint32_t)pool_.size(), (int)sample_size_, tmp.data());
+			for (size_t i = 0; i < sample_size_; ++i) subset_[i] = pool_[tmp[i]];
+			return true;
+		}
+	};
+
+	void flat_of(const Eigen::MatrixXd &d, double *out)
+	{
+		for (int i = 0; i < d.rows(); ++i) for (int j = 0; j < d.cols(); ++j) out[i * d.cols() + j] = d(i, j);
+	}
+	Model model_of(const double *in)
+	{
+		Model m;
+		m.descriptor.resize(3, 3);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.descriptor(i, j) = in[3 * i + j];
+		return m;
+	}
+
+	template <int PROBLEM> class RestatedEstimator
+	{
+	public:
+		bool f_nonminimal_ba = false;
+		double min_ratio = 0.5;
+		static constexpr size_t sampleSize() { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? 7 : 5; }
+		// FundamentalMatrixBundleAdjustmentSolver::sampleSize() is 7 (it falls back to the 7-point solver), the 8-point solver's 8
+		size_t nonMinimalSampleSizeRuntime() const { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? (f_nonminimal_ba ? 7 : 8) : 5; }
+		static constexpr size_t nonMinimalSampleSize() { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? 8 : 5; }
+		static constexpr size_t maximumMinimalSolutions() { return PROBLEM == GCRO_H ? 1 : PROBLEM == GCRO_F ? 3 : 10; }
+		static constexpr bool isWeightingApplicable() { return true; }
+		size_t inlierLimit() const { return 7 * sampleSize(); }
+		double squaredResidual(const cv::Mat &point_, const Eigen::MatrixXd &d) const
+		{
+			double flat[9];
+			flat_of(d, flat);
+			const double *pt = reinterpret_cast<const double *>(point_.data);
+			return PROBLEM == GCRO_H ? gcro_sqres_h(pt, flat) : gcro_sqres_sampson(pt, flat);
+		}
+		double squaredResidual(const cv::Mat &point_, const Model &m) const { return squaredResidual(point_, m.descriptor); }
+		double residual(const cv::Mat &point_, const Eigen::MatrixXd &d) const { return sqrt(squaredResidual(point_, d)); }
+		double residual(const cv::Mat &point_, const Model &m) const { return residual(point_, m.descriptor); }
+		bool isValidSample(const cv::Mat &data_, const size_t *sample_) const
+		{
+			if (PROBLEM != GCRO_H) return true;
+			uint32_t s4[4] = {(uint32_t)sample_[0], (uint32_t)sample_[1], (uint32_t)sample_[2], (uint32_t)sample_[3]};
+			return gcro_h_valid_sample(reinterpret_cast<const double *>(data_.data), s4) != 0;
+		}
+		bool estimateModel(const cv::Mat &data_, const size_t *sample_, std::vector<Model> *models_) const
+		{
+			uint32_t s8[8];
+			for (size_t i = 0; i < sampleSize(); ++i) s8[i] = (uint32_t)sample_[i];
+			const double *pts = reinterpret_cast<const double *>(data_.data);
+			double out[90];
+			const int count = PROBLEM == GCRO_H ? gcro_solve_h4(pts, data_.cols, s8, out) : PROBLEM == GCRO_F ? gcro_estimate_f7(pts, s8, out) : gcro_estimate_e5(pts, s8, out);
+			for (int i = 0; i < count; ++i) models_->emplace_back(model_of(out + 9 * i));
+			return PROBLEM == GCRO_H ? count > 0 : models_->size() > 0;
+		}
+		bool estimateModelNonminimal(const cv::Mat &data_, const size_t *sample_, const size_t &n_, std::vector<Model> *models_, const double *weights_ = nullptr) const
+		{
+			if (n_ < nonMinimalSampleSizeRuntime()) return false;
+			std::vector<uint32_t> sv(n_);
+			for (size_t i = 0; i < n_; ++i) sv[i] = (uint32_t)sample_[i];
+			const double *pts = reinterpret_cast<const double *>(data_.data);
+			double out[90];
+			const int count = PROBLEM == GCRO_H   ? gcro_refit_h(pts, sv.data(), (int)n_, weights_, out)
+			                  : PROBLEM == GCRO_F ? (f_nonminimal_ba ? gcro_refit_f_ba(pts, sv.data(), (int)n_, weights_, out) : gcro_refit_f8(pts, sv.data(), (int)n_, weights_, out))
+			                                      : gcro_refit_e(pts, sv.data(), (int)n_, weights_, out);
+			for (int i = 0; i < count; ++i) models_->emplace_back(model_of(out + 9 * i));
+			return count > 0;
+		}
+		bool isValidModel(Model &model, const cv::Mat &data, const std::vector<size_t> &inliers, const size_t *, const double threshold_, bool &model_updated_) const
+		{
+			model_updated_ = false;
+			double flat[9];
+			flat_of(model.descriptor, flat);
+			if (PROBLEM == GCRO_H) return gcro_h_valid_model(flat) != 0;
+			std::vector<uint32_t> inl(inliers.begin(), inliers.end());
+			return gcro_f_valid_model_ratio(flat, reinterpret_cast<const double *>(data.data), inl.data(), (int)inl.size(), (int)sampleSize(), threshold_, min_ratio) != 0;
+		}
+	};
+
+	template <class Est>
+	int run_with(Est &estimator, const cv::Mat &points, const double *cell_sizes, int cells, double threshold, double conf, double lambda,
+	             int max_iters, int min_iters, int lo_number, uint64_t seed, double *model_out, uint8_t *mask, uint64_t *stats, double *score)
+	{
+		CounterSampler main_sampler(&points, seed, 0u), lo_sampler(&points, seed, 1u);
+		std::vector<double> cs(cell_sizes, cell_sizes + 4);
+		neighborhood::GridNeighborhoodGraph<4> graph(&points, cs, (size_t)cells);
+		Model model;
+		GCRANSAC<Est, neighborhood::GridNeighborhoodGraph<4>> gcransac;
+		gcransac.settings.threshold = threshold;
+		gcransac.settings.spatial_coherence_weight = lambda;
+		gcransac.settings.confidence = conf;
+		gcransac.settings.max_local_optimization_number = lo_number;
+		gcransac.settings.max_iteration_number = max_iters;
+		gcransac.settings.min_iteration_number = min_iters;
+		gcransac.settings.neighborhood_sphere_radius = cells;
+		gcransac.run(points, estimator, &main_sampler, &lo_sampler, &graph, model);
+		const utils::RANSACStatistics &st = gcransac.getRansacStatistics();
+		for (int i = 0; i < points.rows; ++i) mask[i] = 0;
+		for (size_t idx : st.inliers) mask[idx] = 1;
+		if (st.inliers.size() > 0) flat_of(model.descriptor, model_out);
+		stats[0] = st.iteration_number; stats[1] = st.graph_cut_number; stats[2] = st.local_optimization_number;
+		stats[3] = st.neighbor_number; stats[4] = main_sampler.drawn(); stats[5] = lo_sampler.drawn();
+		*score = st.score;
+		return (int)st.inliers.size();
+	}
+}
+
+extern "C" int gcr_refsrc_run(int problem, int own_estimators, const double *pts, int n, const double *cell_sizes, int cells, double threshold,
+                              double conf, double lambda, int max_iters, int min_iters, int lo_number, uint64_t seed, int f_ba,
+                              double *model_out, uint8_t *mask, uint64_t *stats, double *score)
+{
+	const cv::Mat points = view(pts, n, 4);
+#define GCR_RUN_ARGS points, cell_sizes, cells, threshold, conf, lambda, max_iters, min_iters, lo_number, seed, model_out, mask, stats, score
+	if (own_estimators)
+	{
+		if (problem == GCRO_H) { HEstimator e; return run_with(e, GCR_RUN_ARGS); }
+		if (problem == GCRO_F && !(f_ba & 1)) { FEstimator e(0.5, false); return run_with(e, GCR_RUN_ARGS); }
+		if (problem == GCRO_F)
+		{
+			estimator::FundamentalMatrixEstimator<estimator::solver::FundamentalMatrixSevenPointSolver,
+			                                      estimator::solver::FundamentalMatrixBundleAdjustmentSolver> e(0.5, false);
+			return run_with(e, GCR_RUN_ARGS);
+		}
+		if (problem == GCRO_E) { EEstimator e(Eigen::Matrix3d::Identity(), Eigen::Matrix3d::Identity(), 0.1); return run_with(e, GCR_RUN_ARGS); }
+		return -1;
+	}
+	if (problem == GCRO_H) { RestatedEstimator<GCRO_H> e; return run_with(e, GCR_RUN_ARGS); }
+	if (problem == GCRO_F) { RestatedEstimator<GCRO_F> e; e.f_nonminimal_ba = (f_ba & 1) != 0; return run_with(e, GCR_RUN_ARGS); }
+	if (problem == GCRO_E) { RestatedEstimator<GCRO_E> e; e.min_ratio = 0.1; return run_with(e, GCR_RUN_ARGS); }
+	return -1;
+#undef GCR_RUN_ARGS
 }

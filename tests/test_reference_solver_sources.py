@@ -314,3 +314,44 @@ def test_bundle_adjustment_solvers(src, oracle):
         want = oracle.polish_e_ba(p, s, w)
         d, tol = _same_set(got, want, 1e-7)              # measured 8e-10; the order is the Stewenius initialiser's (see above:
         assert d <= tol, (t, n, d)                       # one set of these thirty has two of its models swapped)
+
+
+def test_whole_runs_reference_estimators_vs_restated_adapter(src, oracle):
+    """The reference's GCRANSAC<> (verbatim) over the reference's OWN estimator classes against the same driver over an adapter
+    on the oracle's restated solvers -- the Estimator oracle/_ref/libgcr_ref.so runs with, i.e. what the GPU drivers are compared
+    with in tests/test_gpu_driver.py.  Same counter-based samplers, grid graph, MSAC.  Iteration / LO / graph-cut / sample
+    counts, score, mask and model must be equal: that pins what the adapter restates by hand (sampleSize, inlierLimit,
+    isWeightingApplicable, which test runs where) and closes the chain GPU driver == verbatim driver over the adapter ==
+    verbatim driver over the reference's estimators."""
+    src.gcr_refsrc_run.restype = C.c_int
+    src.gcr_refsrc_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def run(problem, own, pts, cells, thr, lam, seed, f_ba, max_iters):
+        n = len(pts)
+        model, mask, stats, score = np.zeros(9), np.zeros(n, dtype=np.uint8), np.zeros(6, dtype=np.uint64), C.c_double()
+        k = src.gcr_refsrc_run(problem, own, _p(pts), n, _p(cells), 8, thr, 0.99, lam, max_iters, 50, 50, seed, f_ba,
+                               _p(model), _p(mask), _p(stats), C.byref(score))
+        return k, model.reshape(3, 3), mask, stats, score.value
+
+    pts_h = np.ascontiguousarray(synth.homography_pair(800, 0.4, seed=21)[0], dtype=np.float64)
+    pts_f, Fm, Em, K, inl = synth.epipolar_pair(800, 0.4, seed=22)
+    pts_f = np.ascontiguousarray(pts_f, dtype=np.float64)
+    px = synth.epipolar_pair(800, 0.5, seed=23)[0]
+    pts_e = np.ascontiguousarray(oracle.normalize_correspondences(px, K, K))
+    image_cells = np.array([1024 / 8.0] * 4)
+    e_cells = np.array([(pts_e[:, i].max() - pts_e[:, i].min() + 1e-9) / 8 for i in range(4)])
+    cases = (("H", O.H, pts_h, image_cells, 2.0, 0.975, 0, 2000, 0.0),
+             ("F, 8-point refits", O.F, pts_f, image_cells, 0.75, 0.1, 0, 2000, 0.0),
+             ("F, default estimator (BA refits)", O.F, pts_f, image_cells, 0.75, 0.1, 1, 2000, 1e-12),
+             ("E", O.E, pts_e, e_cells, 0.75 / K[0, 0], 0.1, 0, 3000, 1e-8))
+    for name, problem, pts, cells, thr, lam, f_ba, max_iters, model_tol in cases:
+        for seed in (1, 2, 3):
+            a = run(problem, 1, pts, cells, thr, lam, seed, f_ba, max_iters)
+            b = run(problem, 0, pts, cells, thr, lam, seed, f_ba, max_iters)
+            assert a[0] == b[0] and a[0] > 300, (name, seed, a[0], b[0])
+            assert np.array_equal(a[3], b[3]), (name, seed, a[3], b[3])          # iterations, graph cuts, LO runs, neighbours, samples drawn
+            assert np.array_equal(a[2], b[2]), (name, seed)
+            assert abs(a[4] - b[4]) <= 1e-9 * abs(a[4]), (name, seed, a[4], b[4])
+            ma, mb = a[1] / np.linalg.norm(a[1]), b[1] / np.linalg.norm(b[1])
+            assert np.abs(ma - mb).max() <= model_tol, (name, seed, np.abs(ma - mb).max())
