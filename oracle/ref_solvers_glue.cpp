@@ -33,6 +33,21 @@
 
 #include "gcr_oracle.h"
 
+#include "relative_pose/jacobian_impl.h"
+#include "relative_pose/robust_loss.h"
+#include <type_traits>
+
+// DESIGN.md section 8, checked by the compiler: refine_pnp (relative_pose/bundle.cpp:578-597) constructs its accumulator as
+// (correspondences, sample, sample_size, loss_fn, weights), but CameraJacobianAccumulator's fourth parameter is the Camera
+// (relative_pose/jacobian_impl.h:12-18) -- the template only compiles because nothing instantiates it.  That is why the
+// non-minimal PnP fit has no reference behaviour to match and a stated one is built instead (csrc/k_refit_pnp.cu).
+static_assert(!std::is_constructible<pose_lib::CameraJacobianAccumulator<pose_lib::NullCameraModel, pose_lib::TruncatedLoss>,
+                                     const cv::Mat &, const size_t *, const size_t &, pose_lib::TruncatedLoss &, const double *>::value,
+              "refine_pnp's accumulator construction would compile: the reference's non-minimal PnP fit has a defined behaviour after all");
+static_assert(std::is_constructible<pose_lib::CameraJacobianAccumulator<pose_lib::NullCameraModel, pose_lib::TruncatedLoss>,
+                                    const cv::Mat &, const size_t *, const size_t &, const pose_lib::Camera &, pose_lib::TruncatedLoss &, const double *>::value,
+              "the accumulator's declared constructor");
+
 using namespace gcransac;
 
 // gcr_oracle_e.cpp's test hook (this library carries its own copy of the oracle's sources)
