@@ -11,102 +11,9 @@
 
 #include <cstdint>
 #include <cstddef>
-// The reference's samplers draw through utils::UniformRandomGenerator<size_t> (uniform_random_generator.h): a
-// std::mt19937 seeded from std::random_device.  For the samplers whose own code has to run verbatim on a reproducible
-// stream (ProgressiveNapsacSampler and the two ProsacSamplers inside it), the member functions that consume random
-// numbers are explicitly specialised HERE, before anything instantiates them: same contracts (values uniform in the
-// range of the last resetGenerator, draw-and-reject for distinct sets, the `to_skip_` value never returned), the words
-// taken from the counter-based stream gcr_ref_words, which the sampler wrappers below point at (seed, sample number,
-// stream) before every sample() call.  Everything else in uniform_random_generator.h and every sampler header is the
-// reference's text.  (The counter-based uniform / PROSAC adapters of this file do not go through this class at all.)
-extern "C" void gcro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-namespace gcr_ref_words
-{
-	static uint32_t ctr[4], key[2], buf[4];
-	static int pos = 4;
-	inline void begin(uint64_t seed, uint64_t index, uint32_t stream)
-	{
-		ctr[0] = (uint32_t)index; ctr[1] = (uint32_t)(index >> 32); ctr[2] = 0; ctr[3] = stream;
-		key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-		pos = 4;
-	}
-	inline uint32_t next()
-	{
-		if (pos == 4)
-		{
-			gcro_philox4x32(ctr, key, buf);
-			++ctr[2];
-			pos = 0;
-		}
-		return buf[pos++];
-	}
-	// unbiased integer in [lo, hi] (Lemire's multiply-shift with rejection; the product's GcrDrawStream::bounded)
-	inline size_t in_range(size_t lo, size_t hi)
-	{
-		const uint32_t range = (uint32_t)(hi - lo + 1);
-		for (;;)
-		{
-			const uint64_t p = (uint64_t)next() * range;
-			const uint32_t l = (uint32_t)p;
-			if (l < range)
-			{
-				const uint32_t thresh = (uint32_t)(0u - range) % range;
-				if (l < thresh)
-					continue;
-			}
-			return lo + (size_t)(p >> 32);
-		}
-	}
-}
-#ifndef OLGA_INLINE
-#define OLGA_INLINE inline
-#define GCR_REF_DEFINED_OLGA_INLINE
-#endif
-#include "uniform_random_generator.h"
-namespace gcransac
-{
-	namespace utils
-	{
-		template <> inline int UniformRandomGenerator<size_t>::getRandomNumber() { return (int)gcr_ref_words::in_range(generate.a(), generate.b()); }
-		// uniform_random_generator.h:75-88
-		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_)
-		{
-			for (size_t i = 0; i < sample_size_; i++)
-			{
-				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
-				for (int j = (int)i - 1; j >= 0; j--)
-					if (sample_[i] == sample_[j]) { i--; break; }
-			}
-		}
-		// :90-103
-		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_, size_t max_)
-		{
-			resetGenerator(0, max_);
-			for (size_t i = 0; i < sample_size_; i++)
-			{
-				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
-				for (int j = (int)i - 1; j >= 0; j--)
-					if (sample_[i] == sample_[j]) { i--; break; }
-			}
-		}
-		// :105-124
-		template <> inline void UniformRandomGenerator<size_t>::generateUniqueRandomSet(size_t *sample_, size_t sample_size_, size_t max_, size_t to_skip_)
-		{
-			resetGenerator(0, max_);
-			for (size_t i = 0; i < sample_size_; i++)
-			{
-				sample_[i] = gcr_ref_words::in_range(generate.a(), generate.b());
-				if (sample_[i] == to_skip_) { i--; continue; }
-				for (int j = (int)i - 1; j >= 0; j--)
-					if (sample_[i] == sample_[j]) { i--; break; }
-			}
-		}
-	}
-}
-#ifdef GCR_REF_DEFINED_OLGA_INLINE
-#undef OLGA_INLINE
-#undef GCR_REF_DEFINED_OLGA_INLINE
-#endif
+// the reference's random-number class redirected to the counter-based word stream (ProgressiveNapsacSampler and the two
+// ProsacSamplers inside it run verbatim on it; the counter-based uniform / PROSAC adapters of this file do not go through it)
+#include "ref_rng_redirect.h"
 
 #include "GCRANSAC.h"
 #include "neighborhood/grid_neighborhood_graph.h"
@@ -116,6 +23,7 @@ namespace gcransac
 #include "samplers/uniform_sampler.h"
 
 #include "gcr_oracle.h"
+#include "degensac_front.h"
 
 // The reference's AR-Sampler (samplers/adaptive_reordering_sampler.h) takes its noise from C rand() -- process-global
 // state.  The header is compiled UNMODIFIED, with the one call redirected to the counter-based word stream the product
@@ -779,24 +687,11 @@ namespace
 	                           bool &model_updated_)
 	{
 		model_updated_ = false;
-		const double squared_homography_threshold = 2.0 * 2.0; // homography_threshold_ = 2.0 (:93)
-		const double *pts = reinterpret_cast<const double *>(data_.data);
-		double F[9], H[9];
+		double F[9], Hn[9];
 		to_flat(model_.descriptor, F);
-		uint32_t s7[7];
-		for (int i = 0; i < 7; ++i)
-			s7[i] = (uint32_t)minimal_sample_[i];
-		if (!gcro_degensac_sample_homography(F, pts, s7, squared_homography_threshold, H))
-			return true; // not H-degenerate: the model stands (:571)
-		std::vector<uint32_t> h_inliers; // :501-509
-		for (const size_t &idx : inliers_)
-			if (gcro_sqres_h(pts + 4 * idx, H) < squared_homography_threshold)
-				h_inliers.push_back((uint32_t)idx);
-		if (h_inliers.size() < 4) // homography_estimator.nonMinimalSampleSize() (:512)
-			return false;
-		double Hn[9];
-		if (gcro_refit_h(pts, h_inliers.data(), (int)h_inliers.size(), nullptr, Hn) != 1) // :520-528
-			return false;
+		const int front = gcro_degensac_front(F, reinterpret_cast<const double *>(data_.data), inliers_, minimal_sample_, Hn);
+		if (front <= 0)
+			return front == 0; // 0: not H-degenerate, the model stands (:571); -1: too few homography inliers / no refit (:512, :523)
 		typedef OracleEstimator<GCRO_FPP> Inner;
 		Inner inner;
 		inner.pp_homography = Hn;

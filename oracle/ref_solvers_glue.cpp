@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "ref_rng_redirect.h" // before any header of the reference: its random-number class on a reproducible word stream
+
 #include "estimators/solver_fundamental_matrix_seven_point.h"
 #include "estimators/solver_fundamental_matrix_eight_point.h"
 #include "estimators/solver_homography_four_point.h"
@@ -32,6 +34,7 @@
 #include "samplers/sampler.h"
 
 #include "gcr_oracle.h"
+#include "degensac_front.h"
 
 #include "relative_pose/jacobian_impl.h"
 #include "relative_pose/robust_loss.h"
@@ -341,16 +344,18 @@ namespace
 		return m;
 	}
 
+	constexpr int GCRO_FPP = 100; // DEGENSAC's inner estimator: plane-and-parallax minimal solver, eight-point non-minimal solver (fundamental_estimator.h:532-541)
 	template <int PROBLEM> class RestatedEstimator
 	{
 	public:
 		bool f_nonminimal_ba = false;
 		double min_ratio = 0.5;
-		static constexpr size_t sampleSize() { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? 7 : 5; }
+		const double *pp_homography = nullptr;
+		static constexpr size_t sampleSize() { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? 7 : PROBLEM == GCRO_FPP ? 2 : 5; }
 		// FundamentalMatrixBundleAdjustmentSolver::sampleSize() is 7 (it falls back to the 7-point solver), the 8-point solver's 8
-		size_t nonMinimalSampleSizeRuntime() const { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? (f_nonminimal_ba ? 7 : 8) : 5; }
-		static constexpr size_t nonMinimalSampleSize() { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? 8 : 5; }
-		static constexpr size_t maximumMinimalSolutions() { return PROBLEM == GCRO_H ? 1 : PROBLEM == GCRO_F ? 3 : 10; }
+		size_t nonMinimalSampleSizeRuntime() const { return PROBLEM == GCRO_H ? 4 : PROBLEM == GCRO_F ? (f_nonminimal_ba ? 7 : 8) : PROBLEM == GCRO_FPP ? 8 : 5; }
+		static constexpr size_t nonMinimalSampleSize() { return PROBLEM == GCRO_H ? 4 : (PROBLEM == GCRO_F || PROBLEM == GCRO_FPP) ? 8 : 5; }
+		static constexpr size_t maximumMinimalSolutions() { return (PROBLEM == GCRO_H || PROBLEM == GCRO_FPP) ? 1 : PROBLEM == GCRO_F ? 3 : 10; }
 		static constexpr bool isWeightingApplicable() { return true; }
 		size_t inlierLimit() const { return 7 * sampleSize(); }
 		double squaredResidual(const cv::Mat &point_, const Eigen::MatrixXd &d) const
@@ -375,7 +380,8 @@ namespace
 			for (size_t i = 0; i < sampleSize(); ++i) s8[i] = (uint32_t)sample_[i];
 			const double *pts = reinterpret_cast<const double *>(data_.data);
 			double out[90];
-			const int count = PROBLEM == GCRO_H ? gcro_solve_h4(pts, data_.cols, s8, out) : PROBLEM == GCRO_F ? gcro_estimate_f7(pts, s8, out) : gcro_estimate_e5(pts, s8, out);
+			const int count = PROBLEM == GCRO_H ? gcro_solve_h4(pts, data_.cols, s8, out) : PROBLEM == GCRO_F ? gcro_estimate_f7(pts, s8, out)
+			                  : PROBLEM == GCRO_FPP ? gcro_estimate_f_plane_parallax(pts, s8, pp_homography, out) : gcro_estimate_e5(pts, s8, out);
 			for (int i = 0; i < count; ++i) models_->emplace_back(model_of(out + 9 * i));
 			return PROBLEM == GCRO_H ? count > 0 : models_->size() > 0;
 		}
@@ -388,6 +394,7 @@ namespace
 			double out[90];
 			const int count = PROBLEM == GCRO_H   ? gcro_refit_h(pts, sv.data(), (int)n_, weights_, out)
 			                  : PROBLEM == GCRO_F ? (f_nonminimal_ba ? gcro_refit_f_ba(pts, sv.data(), (int)n_, weights_, out) : gcro_refit_f8(pts, sv.data(), (int)n_, weights_, out))
+			                  : PROBLEM == GCRO_FPP ? gcro_refit_f8(pts, sv.data(), (int)n_, weights_, out)
 			                                      : gcro_refit_e(pts, sv.data(), (int)n_, weights_, out);
 			for (int i = 0; i < count; ++i) models_->emplace_back(model_of(out + 9 * i));
 			return count > 0;
@@ -455,4 +462,56 @@ extern "C" int gcr_refsrc_run(int problem, int own_estimators, const double *pts
 	if (problem == GCRO_E) { RestatedEstimator<GCRO_E> e; e.min_ratio = 0.1; return run_with(e, GCR_RUN_ARGS); }
 	return -1;
 #undef GCR_RUN_ARGS
+}
+
+// ---- DEGENSAC: FundamentalMatrixEstimator::isValidModel with use_degensac (fundamental_estimator.h:287-572), the reference's own
+// code (own = 1) against the restatement the verbatim driver's adapter runs (own = 0: gcro_f_valid_model_ratio, degensac_front.h,
+// then the same inner run -- the reference's GCRANSAC<> and the reference's UniformSampler, settings :543-553 -- over the
+// restated plane-and-parallax estimator).  Both inner runs draw from the same word stream (ref_rng_redirect.h, begun at `key`).
+// Returns bit 0: the verdict, bit 1: model_updated_; the (possibly replaced) model in model_out. ----
+extern "C" int gcr_refsrc_degensac(int own, const double *F9, const double *pts, int n, const uint32_t *inl, int n_inl, const uint32_t *sample7,
+                                   double threshold, uint64_t key, double *model_out)
+{
+	const cv::Mat data = view(pts, n, 4);
+	const std::vector<size_t> inliers = indices(inl, n_inl), sample = indices(sample7, 7);
+	Model model = model_of(F9);
+	bool updated = false, verdict;
+	gcr_ref_words::begin(key, 0, 7u);
+	if (own)
+	{
+		FEstimator e(0.5, true);
+		verdict = e.isValidModel(model, data, inliers, sample.data(), threshold, updated);
+	}
+	else
+	{
+		verdict = gcro_f_valid_model_ratio(F9, pts, inl, n_inl, 7, threshold, 0.5) != 0;
+		if (verdict)
+		{
+			double Hn[9];
+			const int front = gcro_degensac_front(F9, pts, inliers, sample.data(), Hn);
+			if (front < 0)
+				verdict = false;
+			else if (front > 0)
+			{
+				RestatedEstimator<GCRO_FPP> inner;
+				inner.pp_homography = Hn;
+				inner.min_ratio = 0.0;
+				GCRANSAC<RestatedEstimator<GCRO_FPP>, neighborhood::GridNeighborhoodGraph<4>> gcransac;
+				gcransac.settings.threshold = threshold;
+				gcransac.settings.spatial_coherence_weight = 0;
+				gcransac.settings.confidence = 0.99;
+				gcransac.settings.neighborhood_sphere_radius = 8;
+				sampler::UniformSampler uniform(&data);
+				Model inner_model;
+				gcransac.run(data, inner, &uniform, &uniform, nullptr, inner_model);
+				if (gcransac.getRansacStatistics().inliers.size() > inliers.size())
+				{
+					updated = true;
+					model = inner_model;
+				}
+			}
+		}
+	}
+	flat_of(model.descriptor, model_out);
+	return (verdict ? 1 : 0) | (updated ? 2 : 0);
 }

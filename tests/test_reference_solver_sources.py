@@ -355,3 +355,41 @@ def test_whole_runs_reference_estimators_vs_restated_adapter(src, oracle):
             assert abs(a[4] - b[4]) <= 1e-9 * abs(a[4]), (name, seed, a[4], b[4])
             ma, mb = a[1] / np.linalg.norm(a[1]), b[1] / np.linalg.norm(b[1])
             assert np.abs(ma - mb).max() <= model_tol, (name, seed, np.abs(ma - mb).max())
+
+
+def test_degensac_against_the_reference_own_code(src, oracle):
+    """FundamentalMatrixEstimator::isValidModel with use_degensac (fundamental_estimator.h:287-572) -- the symmetric-epipolar
+    ratio test, the H-degeneracy test of the sample over its five triplets, the plane homography refitted on its inliers,
+    the nested plane-and-parallax GCRANSAC<> and the update rule -- the reference's own code against the restatement the
+    verbatim driver's adapter runs (gcro_f_valid_model_ratio, oracle/degensac_front.h = gcro_degensac_sample_homography +
+    refit, then the same nested run over the restated plane-and-parallax estimator).  The reference's nested run draws from a
+    std::mt19937 seeded by std::random_device; here both nested runs are the reference's GCRANSAC<> with the reference's
+    UniformSampler, whose random-number class reads a reproducible word stream (oracle/ref_rng_redirect.h)."""
+    src.gcr_refsrc_degensac.restype = C.c_int
+    src.gcr_refsrc_degensac.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
+                                        C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(11)
+    cases = updated = rejected = 0
+    for scene, (seed, plane) in enumerate(((1, 0.8), (2, 0.95), (3, 0.6))):
+        pts, Fm, inl, on_plane = synth.epipolar_pair_planar(600, 0.4, plane, seed + 10)
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        idx_plane, idx_in = np.flatnonzero(on_plane & inl), np.flatnonzero(inl)
+        off_plane = np.setdiff1d(idx_in, idx_plane)
+        for t in range(40):
+            k = min(int(rng.choice([7, 6, 5, 3, 0])), len(idx_plane))      # points of the sample on the plane: 5+ = H-degenerate
+            s = np.concatenate([rng.choice(idx_plane, k, replace=False), rng.choice(off_plane, 7 - k, replace=False)]).astype(np.uint32)
+            rng.shuffle(s)
+            for Fc in oracle.estimate_f7(pts, s):
+                inliers = np.flatnonzero(oracle.residuals(O.F, pts, Fc) <= (1.5 * 0.75) ** 2).astype(np.uint32)
+                if len(inliers) < 8:
+                    continue
+                f9 = np.ascontiguousarray(Fc, dtype=np.float64).reshape(9)
+                out_a, out_b, key = np.zeros(9), np.zeros(9), 1000 * scene + t
+                a = src.gcr_refsrc_degensac(1, _p(f9), _p(pts), len(pts), _p(inliers), len(inliers), _p(s), 0.75, key, _p(out_a))
+                b = src.gcr_refsrc_degensac(0, _p(f9), _p(pts), len(pts), _p(inliers), len(inliers), _p(s), 0.75, key, _p(out_b))
+                assert a == b, (scene, t, k, a, b)                          # verdict and model_updated_
+                assert np.array_equal(out_a, out_b), (scene, t, k)          # the model, replaced by the nested run's or not
+                cases += 1
+                updated += (a >> 1) & 1
+                rejected += (a & 1) == 0
+    assert cases > 200 and updated > 10 and rejected > 10, (cases, updated, rejected)   # every branch was taken
