@@ -234,6 +234,17 @@ extern "C"
 		bool updated = false;
 		return e.isValidModel(m, view(pts, n, 4), inliers, nullptr, threshold, updated) ? 1 : 0;
 	}
+	// EssentialMatrixEstimator::isValidModel (essential_estimator.h:279-305): the same ratio test over five-point samples
+	int gcr_refsrc_e_valid_model_ratio(const double *E9, const double *pts, int n, const uint32_t *inl, int n_inl, double threshold, double min_ratio)
+	{
+		EEstimator e(Eigen::Matrix3d::Identity(), Eigen::Matrix3d::Identity(), min_ratio);
+		Model m = Model();
+		m.descriptor.resize(3, 3);
+		for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.descriptor(i, j) = E9[3 * i + j];
+		const std::vector<size_t> inliers = indices(inl, n_inl);
+		bool updated = false;
+		return e.isValidModel(m, view(pts, n, 4), inliers, nullptr, threshold, updated) ? 1 : 0;
+	}
 	// solver_fundamental_matrix_plane_and_parallax.h:105-160 (two correspondences + the plane's homography); `oriented`: through
 	// FundamentalMatrixEstimator<PlaneParallax, EightPoint>::estimateModel, i.e. with the oriented epipolar constraint
 	int gcr_refsrc_solve_f_plane_parallax(const double *pts, int n, const uint32_t *sample, const double *H9, int oriented, double *F9)

@@ -257,6 +257,13 @@ def test_residuals_and_model_tests(src, oracle):
         got = src.gcr_refsrc_f_valid_model_ratio(_p(f9), _p(pts_f), len(pts_f), _p(inl), len(inl), C.c_double(thr), C.c_double(ratio))
         want = oracle.lib.gcro_f_valid_model_ratio(f9, pts_f, inl, len(inl), 7, thr, ratio)
         assert got == want, (t, thr, ratio)
+    for t in range(200):                                   # essential_estimator.h:279-305, sample size 5
+        Ec = synth.perturbed_models(Em, 1, rng)[0] if t % 2 else Em
+        e9 = np.ascontiguousarray(Ec, dtype=np.float64).reshape(9)
+        inl = rng.choice(500, int(rng.integers(5, 300)), replace=False).astype(np.uint32)
+        thr, ratio = float(rng.uniform(0.2, 3.0)) / K[0, 0], float(rng.choice([0.0, 0.1, 0.5]))
+        got = src.gcr_refsrc_e_valid_model_ratio(_p(e9), _p(pts_e), len(pts_e), _p(inl), len(inl), C.c_double(thr), C.c_double(ratio))
+        assert got == oracle.lib.gcro_f_valid_model_ratio(e9, pts_e, inl, len(inl), 5, thr, ratio), (t, thr, ratio)
     # plane and parallax: a homography of a plane of the scene = H compatible with F; any H exercises the arithmetic
     for t in range(200):
         s = rng.choice(idx, 2, replace=False).astype(np.uint32)
