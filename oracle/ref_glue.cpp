@@ -4,9 +4,11 @@
 // BK max-flow) through the two container shims in oracle/shim/, and exposes them over a small C API so that
 //   (1) the self-contained restatement in oracle/gcr_oracle*.cpp can be pinned against the real reference code, and
 //   (2) golden fixtures (tests/golden/) can be generated from the reference itself (oracle/gen_golden.py).
-// The reference's estimator classes need real Eigen decompositions and cannot be compiled here, so the Estimator
+// The reference's estimator classes need Eigen's decompositions, which are not to be had here, so the Estimator
 // template parameter is an adapter over the restated solvers of oracle/gcr_oracle*.cpp (kind = "reference driver +
-// restated estimators"; stated wherever results of this library are quoted).
+// restated estimators"; stated wherever results of this library are quoted).  oracle/ref_solvers_glue.cpp compiles those
+// estimator classes verbatim over a stand-in for Eigen's API and shows that runs over them and over this adapter are equal
+// (tests/test_reference_solver_sources.py).
 #include <opencv2/core/core.hpp>
 
 #include <cstdint>
