@@ -82,3 +82,17 @@ def test_batch_engine_fibers_without_a_gpu():
     for fibers, threads, rounds in ((1, 1, 10), (64, 4, 200), (300, 8, 50), (7, 16, 1000)):
         assert lib.gcr_fiber_selftest(fibers, threads, rounds) == fibers * rounds, (fibers, threads, rounds)
     assert lib.gcr_fiber_selftest(0, 1, 1) < 0
+
+
+def test_reference_citations_point_into_the_reference_tree():
+    """Every `file.h:line[-line]` citation of a reference file in this repository's sources and documents lies inside that
+    file (tools/check_citations.py); only where the reference tree exists."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(os.environ.get("GCR_REFERENCE_DIR", "/root/reference"), "src", "pygcransac", "include")):
+        import pytest
+        pytest.skip("no reference tree")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_citations.py")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
